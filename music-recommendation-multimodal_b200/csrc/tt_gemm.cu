@@ -1,0 +1,422 @@
+// Persistent warp-specialised tcgen05 GEMM for sm_100a.
+//
+//   C[M,N] = epilogue(alpha * A[M,K] * B[N,K]^T), bf16 operands, fp32 accumulate in TMEM.
+//
+// One CTA per SM, 256 threads:
+//   warp 0      : TMA producer (one elected lane) — A/B tiles, 128B swizzle, N-stage ring
+//   warp 1      : MMA issuer (one elected lane)  — tcgen05.mma M=128, N=block_n, K=16
+//   warp 2      : TMEM allocator (2 accumulator buffers of block_n columns)
+//   warps 4..7  : epilogue — tcgen05.ld (each warp owns a 32-lane quarter), fused
+//                 bias / ReLU / dropout / gate / residual, vector stores or red.add
+// Three pipelines: smem full/empty (TMA<->MMA), TMEM full/empty (MMA<->epilogue) and the
+// static persistent tile loop. Operands may be K-major or MN-major (the transposed
+// layouts dgrad/wgrad need), selected by template flags and the UMMA descriptors.
+#include "../../include/tt_b200.h"
+#include "tt_common.cuh"
+
+namespace tt {
+
+struct GemmParams {
+  int M, N, K;
+  int block_n, stages, k_splits;
+  float alpha;
+  const float* bias;
+  int relu;
+  uint32_t drop_thresh;
+  float drop_scale;
+  uint64_t drop_seed;
+  uint32_t drop_site;
+  const __nv_bfloat16* gate;
+  int ld_gate;
+  float gate_scale;
+  const float* residual;
+  int ld_res;
+  float* out_f32;
+  int ld_f32;
+  __nv_bfloat16* out_bf16;
+  int ld_bf16;
+  int accumulate;
+};
+
+static constexpr int kBlockM = 128;
+static constexpr int kBlockK = 64;
+static constexpr uint32_t kABytes = kBlockM * kBlockK * 2;  // 16 KB
+static constexpr int kGemmThreads = 256;
+
+__device__ __forceinline__ void gemm_epilogue_chunk(const GemmParams& p, const uint32_t (&r)[32],
+                                                    int row, int col0) {
+  const int ncols = min(32, p.N - col0);
+  float v[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * p.alpha;
+
+  if (ncols == 32) {
+    if (p.bias) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
+        v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+      }
+    }
+    if (p.relu) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+    }
+    if (p.drop_thresh) {
+      const uint64_t base = static_cast<uint64_t>(row) * p.N + col0;
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        v[j] = drop_keep(p.drop_seed, p.drop_site, base + j, p.drop_thresh) ? v[j] * p.drop_scale
+                                                                            : 0.f;
+    }
+    if (p.gate) {
+      const uint4* g = reinterpret_cast<const uint4*>(p.gate + static_cast<size_t>(row) * p.ld_gate + col0);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        uint4 u = __ldg(g + q);
+        uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+          float2 f = unpack_bf16(w[h]);
+          int j = q * 8 + h * 2;
+          v[j] = f.x > 0.f ? v[j] * p.gate_scale : 0.f;
+          v[j + 1] = f.y > 0.f ? v[j + 1] * p.gate_scale : 0.f;
+        }
+      }
+    }
+    if (p.residual) {
+      const float4* rs = reinterpret_cast<const float4*>(p.residual + static_cast<size_t>(row) * p.ld_res + col0);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        float4 x = __ldg(rs + q);
+        v[q * 4] += x.x; v[q * 4 + 1] += x.y; v[q * 4 + 2] += x.z; v[q * 4 + 3] += x.w;
+      }
+    }
+    if (p.out_f32) {
+      float* o = p.out_f32 + static_cast<size_t>(row) * p.ld_f32 + col0;
+      if (p.accumulate) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) atomicAdd(o + j, v[j]);
+      } else {
+        float4* o4 = reinterpret_cast<float4*>(o);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) o4[q] = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+      }
+    }
+    if (p.out_bf16) {
+      uint4* o = reinterpret_cast<uint4*>(p.out_bf16 + static_cast<size_t>(row) * p.ld_bf16 + col0);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        uint4 u;
+        u.x = pack_bf16(v[q * 8 + 0], v[q * 8 + 1]);
+        u.y = pack_bf16(v[q * 8 + 2], v[q * 8 + 3]);
+        u.z = pack_bf16(v[q * 8 + 4], v[q * 8 + 5]);
+        u.w = pack_bf16(v[q * 8 + 6], v[q * 8 + 7]);
+        o[q] = u;
+      }
+    }
+  } else {
+    // ragged right edge: scalar, fully guarded
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      if (j < ncols) {
+        const int col = col0 + j;
+        float x = v[j];
+        if (p.bias) x += __ldg(p.bias + col);
+        if (p.relu) x = fmaxf(x, 0.f);
+        if (p.drop_thresh)
+          x = drop_keep(p.drop_seed, p.drop_site, static_cast<uint64_t>(row) * p.N + col, p.drop_thresh)
+                  ? x * p.drop_scale
+                  : 0.f;
+        if (p.gate) {
+          float g = __bfloat162float(p.gate[static_cast<size_t>(row) * p.ld_gate + col]);
+          x = g > 0.f ? x * p.gate_scale : 0.f;
+        }
+        if (p.residual) x += __ldg(p.residual + static_cast<size_t>(row) * p.ld_res + col);
+        if (p.out_f32) {
+          float* o = p.out_f32 + static_cast<size_t>(row) * p.ld_f32 + col;
+          if (p.accumulate) atomicAdd(o, x); else *o = x;
+        }
+        if (p.out_bf16) p.out_bf16[static_cast<size_t>(row) * p.ld_bf16 + col] = __float2bfloat16_rn(x);
+      }
+    }
+  }
+}
+
+template <bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const GemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t pad = (1024u - (smem_u32(smem_raw) & 1023u)) & 1023u;
+  uint8_t* smem = smem_raw + pad;
+
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
+  const int stages = p.stages;
+  const int block_n = p.block_n;
+  const uint32_t b_bytes = static_cast<uint32_t>(block_n) * kBlockK * 2;
+
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + static_cast<size_t>(stages) * kABytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sB + static_cast<size_t>(stages) * b_bytes);
+  uint64_t* empty_bar = full_bar + stages;
+  uint64_t* tfull_bar = empty_bar + stages;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const uint32_t tmem_cols = static_cast<uint32_t>(2 * block_n);  // 128 / 256 / 512
+
+  if (warp == 0 && elect_one()) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && elect_one()) {
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull_bar[a], 1);
+      mbar_init(&tempty_bar[a], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, tmem_cols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int tiles_m = (p.M + kBlockM - 1) / kBlockM;
+  const int tiles_n = (p.N + block_n - 1) / block_n;
+  const int num_tiles = tiles_m * tiles_n * p.k_splits;
+  const int kblocks = (p.K + kBlockK - 1) / kBlockK;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        const int split = t % p.k_splits;
+        const int mn = t / p.k_splits;
+        const int m_blk = mn / tiles_n, n_blk = mn % tiles_n;
+        const int kb0 = static_cast<int>(static_cast<long long>(split) * kblocks / p.k_splits);
+        const int kb1 = static_cast<int>(static_cast<long long>(split + 1) * kblocks / p.k_splits);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          mbar_arrive_expect_tx(&full_bar[stage], kABytes + b_bytes);
+          uint8_t* a_dst = sA + static_cast<size_t>(stage) * kABytes;
+          uint8_t* b_dst = sB + static_cast<size_t>(stage) * b_bytes;
+          if (A_MN) tma_load_3d(a_dst, &tmA, &full_bar[stage], 0, kb * kBlockK, m_blk * (kBlockM / 64));
+          else      tma_load_2d(a_dst, &tmA, &full_bar[stage], kb * kBlockK, m_blk * kBlockM);
+          if (B_MN) tma_load_3d(b_dst, &tmB, &full_bar[stage], 0, kb * kBlockK, n_blk * (block_n / 64));
+          else      tma_load_2d(b_dst, &tmB, &full_bar[stage], kb * kBlockK, n_blk * block_n);
+          if (++stage == stages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      const uint32_t idesc = umma_idesc_bf16(kBlockM, block_n, A_MN, B_MN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        const int split = t % p.k_splits;
+        const int kb0 = static_cast<int>(static_cast<long long>(split) * kblocks / p.k_splits);
+        const int kb1 = static_cast<int>(static_cast<long long>(split + 1) * kblocks / p.k_splits);
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * block_n);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_base = smem_u32(sA + static_cast<size_t>(stage) * kABytes);
+          const uint32_t b_base = smem_u32(sB + static_cast<size_t>(stage) * b_bytes);
+#pragma unroll
+          for (int k = 0; k < kBlockK / 16; ++k) {
+            // K-major: +32 B per 16 K-elements inside the 128 B swizzled row.
+            // MN-major: +16 K-rows of 128 B; 64-wide MN chunks are kBlockK*128 B apart.
+            const uint64_t adesc = A_MN ? umma_desc_mnmajor(a_base + k * 2048, kBlockK * 128)
+                                        : umma_desc_kmajor(a_base + k * 32);
+            const uint64_t bdesc = B_MN ? umma_desc_mnmajor(b_base + k * 2048, kBlockK * 128)
+                                        : umma_desc_kmajor(b_base + k * 32);
+            umma_bf16(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
+          if (++stage == stages) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1u;
+      }
+    }
+  } else if (warp >= 4) {
+    const int ew = warp - 4;  // == warp % 4: the TMEM lane quarter this warp may read
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      const int mn = t / p.k_splits;
+      const int m_blk = mn / tiles_n, n_blk = mn % tiles_n;
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const int row = m_blk * kBlockM + ew * 32 + lane;
+      const uint32_t t_base = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) +
+                              static_cast<uint32_t>(acc * block_n);
+      for (int c = 0; c < block_n / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld32(t_base + static_cast<uint32_t>(c * 32), r);
+        tmem_ld_wait();
+        const int col0 = n_blk * block_n + c * 32;
+        if (row < p.M && col0 < p.N) gemm_epilogue_chunk(p, r, row, col0);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1u;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, tmem_cols);
+}
+
+static size_t gemm_smem_bytes(int block_n, int stages) {
+  return 1024 + static_cast<size_t>(stages) * (kABytes + static_cast<size_t>(block_n) * kBlockK * 2) +
+         (2 * stages + 4) * sizeof(uint64_t) + 16;
+}
+
+template <bool A_MN, bool B_MN>
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, int grid,
+                       size_t smem, cudaStream_t stream) {
+  static bool configured = false;
+  if (!configured) {
+    TT_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<A_MN, B_MN>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    configured = true;
+  }
+  TT_REQUIRE(smem <= 232448, "tt_gemm_bf16: %zu B of shared memory requested", smem);
+  gemm_bf16_kernel<A_MN, B_MN><<<grid, kGemmThreads, smem, stream>>>(tmA, tmB, p);
+  TT_LAUNCH_CHECK();
+  return TT_OK;
+}
+
+}  // namespace tt
+
+extern "C" int tt_gemm_bf16(const tt_gemm_args* a, void* stream_) {
+  using namespace tt;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  TT_REQUIRE(a != nullptr, "tt_gemm_bf16: null args");
+  TT_REQUIRE(a->A && a->B, "tt_gemm_bf16: null operand");
+  TT_REQUIRE(a->M > 0 && a->N > 0 && a->K > 0, "tt_gemm_bf16: empty problem %d x %d x %d", a->M,
+             a->N, a->K);
+  TT_REQUIRE(a->out_f32 || a->out_bf16, "tt_gemm_bf16: no output");
+  TT_REQUIRE(a->lda % 8 == 0 && a->ldb % 8 == 0, "tt_gemm_bf16: lda/ldb must be multiples of 8");
+  TT_REQUIRE(!a->a_mn || a->M % 64 == 0, "tt_gemm_bf16: MN-major A needs M %% 64 == 0 (M=%d)", a->M);
+  TT_REQUIRE(!a->b_mn || a->N % 64 == 0, "tt_gemm_bf16: MN-major B needs N %% 64 == 0 (N=%d)", a->N);
+  TT_REQUIRE(!a->out_f32 || a->ld_f32 % 4 == 0, "tt_gemm_bf16: ld_f32 must be a multiple of 4");
+  TT_REQUIRE(!a->out_bf16 || a->ld_bf16 % 8 == 0, "tt_gemm_bf16: ld_bf16 must be a multiple of 8");
+  TT_REQUIRE(!a->residual || a->ld_res % 4 == 0, "tt_gemm_bf16: ld_res must be a multiple of 4");
+  TT_REQUIRE(!a->gate || a->ld_gate % 8 == 0, "tt_gemm_bf16: ld_gate must be a multiple of 8");
+  TT_REQUIRE(a->drop_p >= 0.f && a->drop_p < 1.f, "tt_gemm_bf16: drop_p out of range");
+  TT_REQUIRE(!a->accumulate || (a->out_f32 && !a->out_bf16),
+             "tt_gemm_bf16: accumulate needs an fp32-only output");
+
+  GemmParams p;
+  p.M = a->M; p.N = a->N; p.K = a->K;
+  int bn = a->block_n;
+  if (bn == 0) bn = a->N > 128 ? 256 : (a->N > 64 ? 128 : 64);
+  TT_REQUIRE(bn == 64 || bn == 128 || bn == 256, "tt_gemm_bf16: block_n must be 64/128/256");
+  p.block_n = bn;
+  const size_t stage_bytes = kABytes + static_cast<size_t>(bn) * kBlockK * 2;
+  int stages = static_cast<int>((200 * 1024) / stage_bytes);
+  if (stages > 8) stages = 8;
+  p.stages = stages;
+
+  const int tiles_m = (a->M + kBlockM - 1) / kBlockM;
+  const int tiles_n = (a->N + bn - 1) / bn;
+  const int kblocks = (a->K + kBlockK - 1) / kBlockK;
+  int ks = a->k_splits;
+  if (ks <= 0) {
+    ks = 1;
+    if (a->accumulate) {
+      const int sms = num_sms();
+      ks = sms / (tiles_m * tiles_n);
+      if (ks < 1) ks = 1;
+      // keep at least 4 k-blocks per split so the pipeline has something to stream
+      if (ks > (kblocks + 3) / 4) ks = (kblocks + 3) / 4;
+    }
+  }
+  if (ks > kblocks) ks = kblocks;
+  if (ks < 1) ks = 1;
+  TT_REQUIRE(ks == 1 || a->accumulate, "tt_gemm_bf16: k_splits > 1 requires accumulate");
+  p.k_splits = ks;
+
+  p.alpha = a->alpha;
+  p.bias = a->bias;
+  p.relu = a->relu;
+  p.drop_thresh = 0;
+  p.drop_scale = 1.f;
+  if (a->drop_p > 0.f) {
+    double t = static_cast<double>(a->drop_p) * 4294967296.0;
+    p.drop_thresh = t >= 4294967295.0 ? 4294967295u : static_cast<uint32_t>(t);
+    if (p.drop_thresh == 0) p.drop_thresh = 1;
+    p.drop_scale = 1.f / (1.f - a->drop_p);
+  }
+  p.drop_seed = a->drop_seed;
+  p.drop_site = a->drop_site;
+  p.gate = static_cast<const __nv_bfloat16*>(a->gate);
+  p.ld_gate = a->ld_gate;
+  p.gate_scale = a->gate_scale;
+  p.residual = a->residual;
+  p.ld_res = a->ld_res;
+  p.out_f32 = a->out_f32;
+  p.ld_f32 = a->ld_f32;
+  p.out_bf16 = static_cast<__nv_bfloat16*>(a->out_bf16);
+  p.ld_bf16 = a->ld_bf16;
+  p.accumulate = a->accumulate;
+
+  CUtensorMap tmA, tmB;
+  int rc;
+  if (a->a_mn) {
+    uint64_t dims[3] = {64, static_cast<uint64_t>(a->K), static_cast<uint64_t>(a->M / 64)};
+    uint64_t str[2] = {static_cast<uint64_t>(a->lda) * 2, 128};
+    uint32_t box[3] = {64, kBlockK, kBlockM / 64};
+    rc = make_tmap_bf16(&tmA, a->A, 3, dims, str, box);
+  } else {
+    uint64_t dims[2] = {static_cast<uint64_t>(a->K), static_cast<uint64_t>(a->M)};
+    uint64_t str[1] = {static_cast<uint64_t>(a->lda) * 2};
+    uint32_t box[2] = {kBlockK, kBlockM};
+    rc = make_tmap_bf16(&tmA, a->A, 2, dims, str, box);
+  }
+  if (rc) return rc;
+  if (a->b_mn) {
+    uint64_t dims[3] = {64, static_cast<uint64_t>(a->K), static_cast<uint64_t>(a->N / 64)};
+    uint64_t str[2] = {static_cast<uint64_t>(a->ldb) * 2, 128};
+    uint32_t box[3] = {64, kBlockK, static_cast<uint32_t>(bn / 64)};
+    rc = make_tmap_bf16(&tmB, a->B, 3, dims, str, box);
+  } else {
+    uint64_t dims[2] = {static_cast<uint64_t>(a->K), static_cast<uint64_t>(a->N)};
+    uint64_t str[1] = {static_cast<uint64_t>(a->ldb) * 2};
+    uint32_t box[2] = {kBlockK, static_cast<uint32_t>(bn)};
+    rc = make_tmap_bf16(&tmB, a->B, 2, dims, str, box);
+  }
+  if (rc) return rc;
+
+  const int num_tiles = tiles_m * tiles_n * ks;
+  int grid = num_tiles < num_sms() ? num_tiles : num_sms();
+  const size_t smem = gemm_smem_bytes(bn, stages);
+  if (a->a_mn) {
+    return a->b_mn ? launch_gemm<true, true>(tmA, tmB, p, grid, smem, stream)
+                   : launch_gemm<true, false>(tmA, tmB, p, grid, smem, stream);
+  }
+  return a->b_mn ? launch_gemm<false, true>(tmA, tmB, p, grid, smem, stream)
+                 : launch_gemm<false, false>(tmA, tmB, p, grid, smem, stream);
+}
