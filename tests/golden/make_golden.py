@@ -1,0 +1,186 @@
+"""Generate golden vectors from the REFERENCE's own modules (dev container only).
+
+Imports /root/reference unmodified, with the three harness-side stubs of SURVEY.md §8c
+(`peft`, `src.data.dataset`, identity modality encoders), loads the seeded synthetic
+parameters of `synthetic.make_state_dict`, runs the reference's TwoTowerModel.forward /
+backward, get_user_embedding and calculate_metrics_global on seeded synthetic batches and
+stores the OUTPUTS (not the inputs: those are regenerated from the seed) as small .pt files.
+
+    python tests/golden/make_golden.py          # writes tests/golden/*.pt
+
+/root/reference does not exist on the GPU box; tests only read the committed fixtures.
+"""
+import importlib
+import os
+import sys
+import types
+
+import torch
+import torch.nn as nn
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+REF = "/root/reference"
+sys.path.insert(0, ROOT)
+
+import mrm_b200  # noqa: E402
+from mrm_b200 import synthetic  # noqa: E402
+
+
+def import_reference():
+    peft = types.ModuleType("peft")
+    peft.get_peft_model = lambda m, c: m
+    peft.LoraConfig = lambda **kw: None
+    peft.TaskType = types.SimpleNamespace(FEATURE_EXTRACTION=0)
+    sys.modules["peft"] = peft
+    data = types.ModuleType("src.data")
+    ds = types.ModuleType("src.data.dataset")
+    ds.MultimodalDataset = type("MultimodalDataset", (), {})
+    sys.modules["src.data"] = data
+    sys.modules["src.data.dataset"] = ds
+    sys.path.insert(0, REF)
+    item_tower = importlib.import_module("src.models.item_tower")
+
+    class Identity(nn.Module):
+        def __init__(self, *a, **kw):
+            super().__init__()
+
+        def forward(self, x, *rest):
+            return x
+
+    for name in ("AudioEncoder", "VisualEncoder", "TextEncoder", "TabularEncoder"):
+        setattr(item_tower, name, Identity)
+    two_tower = importlib.import_module("src.models.two_tower")
+    evalm = importlib.import_module("src.evaluate_metrics")
+    return two_tower, evalm
+
+
+def build_reference_model(two_tower, cfg, sd, dtype):
+    m = two_tower.TwoTowerModel(
+        vocab_size=cfg.vocab_size, tabular_input_dim=cfg.modality_dim, num_genders=cfg.num_genders,
+        num_countries=cfg.num_countries, max_seq_len=cfg.max_seq_len,
+        user_embedding_dim=cfg.embedding_dim, user_num_heads=cfg.num_heads,
+        user_num_layers=cfg.num_layers, user_dropout=0.0, item_embedding_dim=cfg.embedding_dim,
+        audio_dim=cfg.modality_dim, visual_dim=cfg.modality_dim, text_dim=cfg.modality_dim,
+        tabular_dim=cfg.modality_dim, temperature=cfg.temperature)
+    m.item_tower.fusion_layer[3].p = 0.0   # hard-coded Dropout(0.1), item_tower.py:126
+    missing, unexpected = m.load_state_dict(sd, strict=True)
+    return m.to(dtype)
+
+
+def cast_batch(batch, dtype):
+    return {k: (v.to(dtype) if v.is_floating_point() else v) for k, v in batch.items()}
+
+
+def golden_train(two_tower, name, cfg, B, seed_w, seed_b, full_length=False):
+    sd = synthetic.make_state_dict(cfg, seed=seed_w)
+    batch = synthetic.make_batch(cfg, B, seed=seed_b, full_length=full_length)
+    out = {"config": cfg.as_dict(), "batch_size": B, "seed_w": seed_w, "seed_b": seed_b,
+           "full_length": full_length}
+    for dtype, tag in ((torch.float64, "f64"), (torch.float32, "f32")):
+        m = build_reference_model(two_tower, cfg, sd, dtype)
+        m.train()
+        loss, logits, u, i = m(cast_batch(batch, dtype))
+        loss.backward()
+        grads = {k: p.grad.detach() for k, p in m.named_parameters() if p.grad is not None}
+        out[tag] = {
+            "loss": loss.detach(), "logits": logits.detach(), "user_emb": u.detach(),
+            "item_emb": i.detach(),
+            "bn_running_mean": m.item_tower.fusion_layer[1].running_mean.detach().clone(),
+            "bn_running_var": m.item_tower.fusion_layer[1].running_var.detach().clone(),
+        }
+        # Parameter gradients: full tensors for the small ones, norm + a few rows for the table.
+        gsel = {}
+        for k, g in grads.items():
+            if k == "user_tower.item_embedding.weight":
+                ids = torch.unique(batch["history_ids"])[:8]
+                gsel[k + "#rows_ids"] = ids
+                gsel[k + "#rows"] = g[ids].clone()
+                gsel[k + "#norm"] = g.norm()
+                gsel[k + "#row0_absmax"] = g[0].abs().max()
+            elif g.numel() <= 1024:
+                gsel[k] = g.clone()
+            else:
+                gsel[k + "#norm"] = g.norm()
+                gsel[k + "#head"] = g.flatten()[:64].clone()
+        out[tag]["grads"] = gsel
+        # eval-mode user embedding (fast-path encoder) and item embedding
+        m.eval()
+        with torch.no_grad():
+            b = cast_batch(batch, dtype)
+            out[tag]["eval_user_emb"] = m.get_user_embedding(
+                b["history_ids"], b["history_mask"], b["user_gender"], b["user_country"])
+            out[tag]["eval_user_emb_nomask"] = m.get_user_embedding(b["history_ids"])
+            out[tag]["eval_item_emb"] = m.get_item_embedding(
+                b["target_image"], b["target_audio"], b["target_input_ids"],
+                b["target_attention_mask"], b["target_tabular"])
+    torch.save(out, os.path.join(HERE, name))
+    print(name, "loss f64", out["f64"]["loss"].item(), "f32", out["f32"]["loss"].item())
+
+
+class _FakeModel(nn.Module):
+    """calculate_metrics_global only needs .eval() and .get_user_embedding(); feeding it
+    precomputed user embeddings isolates the scoring/top-K/metric part."""
+
+    def __init__(self, users):
+        super().__init__()
+        self.users = users
+        self.pos = 0
+
+    def get_user_embedding(self, history_ids, history_mask=None, user_gender=None, user_country=None):
+        n = history_ids.shape[0]
+        u = self.users[self.pos:self.pos + n]
+        self.pos += n
+        return u
+
+
+def golden_retrieval(evalm, name, num_items, num_users, k_list, grid, seed, noise):
+    table = synthetic.make_catalog(num_items, 256, seed=seed, grid=grid)
+    users, targets = synthetic.make_queries(table, num_users, seed=seed + 1, noise=noise, grid=grid)
+    loader = []
+    for s in range(0, num_users, 64):
+        n = min(64, num_users - s)
+        loader.append({"history_ids": torch.ones((n, 4), dtype=torch.long),
+                       "history_mask": torch.ones((n, 4), dtype=torch.long),
+                       "user_gender": torch.zeros(n, dtype=torch.long),
+                       "user_country": torch.zeros(n, dtype=torch.long),
+                       "target_id": targets[s:s + n]})
+    metrics = evalm.calculate_metrics_global(_FakeModel(users), loader, table, torch.device("cpu"),
+                                             k_list=list(k_list))
+    # the reference's own scores; top-K under the canonical order (stable sort) for index pins
+    scores = users @ table.t()
+    scores[:, 0] = -float("inf")
+    vals, idx = torch.sort(scores, dim=1, descending=True, stable=True)
+    kmax = max(k_list)
+    # cross-check: torch.topk's value multiset must agree with the canonical one
+    tv, ti = torch.topk(scores, kmax, dim=1)
+    assert torch.equal(tv, vals[:, :kmax])
+    ties = (vals[:, :kmax][:, 1:] == vals[:, :kmax][:, :-1]).sum().item()
+    print(name, "adjacent ties inside the top-K lists:", ties)
+    out = {"num_items": num_items, "num_users": num_users, "k_list": list(k_list), "grid": grid,
+           "seed": seed, "noise": noise, "metrics": metrics, "topk_idx": idx[:, :kmax].to(torch.int32),
+           "topk_val": vals[:, :kmax].clone()}
+    torch.save(out, os.path.join(HERE, name))
+    print(name, metrics)
+
+
+def main():
+    torch.manual_seed(0)
+    torch.set_num_threads(8)
+    two_tower, evalm = import_reference()
+    small = synthetic.TwoTowerConfig(vocab_size=501, num_genders=3, num_countries=7, max_seq_len=12,
+                                     embedding_dim=64, num_heads=4, num_layers=2, modality_dim=16,
+                                     fusion_hidden=512)
+    # the reference hard-codes the 512-wide fusion hidden layer and 16/32-d demographic embeddings
+    golden_train(two_tower, "train_small.pt", small, B=8, seed_w=10, seed_b=11)
+    c1 = synthetic.TwoTowerConfig(vocab_size=10_001, max_seq_len=50)
+    golden_train(two_tower, "train_c1.pt", c1, B=32, seed_w=0, seed_b=1)
+    c1s = synthetic.TwoTowerConfig(vocab_size=2_001, max_seq_len=200)
+    golden_train(two_tower, "train_l200.pt", c1s, B=16, seed_w=20, seed_b=21)
+    golden_retrieval(evalm, "retrieval_grid.pt", 5_000, 192, (10, 20, 50, 100), 2.0 ** -7, 30, 5.0)
+    golden_retrieval(evalm, "retrieval_grid_coarse.pt", 5_000, 192, (10, 20, 50, 100), 2.0 ** -3, 50, 5.0)
+    golden_retrieval(evalm, "retrieval_float.pt", 5_000, 192, (10, 20, 50, 100), 0.0, 40, 5.0)
+
+
+if __name__ == "__main__":
+    main()

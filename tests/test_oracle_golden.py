@@ -1,0 +1,100 @@
+"""Pin the CPU oracle (oracle/two_tower_oracle.py) against outputs of the reference's own
+modules (tests/golden/*.pt, produced by tests/golden/make_golden.py from /root/reference).
+
+fp64 against fp64 must agree to ~1e-10 (same algorithm, different op order); fp32 against
+the reference's fp32 to ~1e-5. Retrieval indices / metrics must be bit-identical.
+"""
+import os
+
+import pytest
+import torch
+
+from mrm_b200 import synthetic
+from oracle import two_tower_oracle as oracle
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _load(name):
+    return torch.load(os.path.join(GOLDEN, name), weights_only=False)
+
+
+def _cast(batch, dtype):
+    return {k: (v.to(dtype) if v.is_floating_point() else v) for k, v in batch.items()}
+
+
+@pytest.mark.parametrize("name", ["train_small.pt", "train_c1.pt", "train_l200.pt"])
+@pytest.mark.parametrize("tag,dtype,tol", [("f64", torch.float64, 1e-9), ("f32", torch.float32, 3e-5)])
+def test_oracle_train_matches_reference(name, tag, dtype, tol):
+    gold = _load(name)
+    cfg = synthetic.TwoTowerConfig(**gold["config"])
+    sd = synthetic.make_state_dict(cfg, seed=gold["seed_w"])
+    batch = synthetic.make_batch(cfg, gold["batch_size"], seed=gold["seed_b"],
+                                 full_length=gold["full_length"])
+    g = gold[tag]
+    loss, logits, u, i, grads, stats = oracle.loss_and_grads(
+        sd, _cast(batch, dtype), cfg.temperature, cfg.num_heads, dtype=dtype)
+    assert abs(loss.item() - g["loss"].item()) <= tol * 10
+    assert (u - g["user_emb"]).abs().max().item() <= tol
+    assert (i - g["item_emb"]).abs().max().item() <= tol
+    assert (logits - g["logits"]).abs().max().item() <= tol * 100   # logits are x14.3, masked = -1e4
+    # BatchNorm running statistics after one training forward
+    rm, rv = oracle.bn_running_update(sd["item_tower.fusion_layer.1.running_mean"].to(dtype),
+                                      sd["item_tower.fusion_layer.1.running_var"].to(dtype),
+                                      stats[0], stats[1], gold["batch_size"])
+    assert (rm - g["bn_running_mean"]).abs().max().item() <= tol * 10
+    assert (rv - g["bn_running_var"]).abs().max().item() <= tol * 10
+    # parameter gradients
+    gtol = tol * 50
+    for key, ref in g["grads"].items():
+        if "#" not in key:
+            assert (grads[key] - ref).abs().max().item() <= gtol, key
+            continue
+        base, what = key.split("#")
+        if what == "norm":
+            assert abs(grads[base].norm().item() - ref.item()) <= gtol * max(1.0, ref.item()), key
+        elif what == "head":
+            assert (grads[base].flatten()[:64] - ref).abs().max().item() <= gtol, key
+        elif what == "rows":
+            ids = g["grads"][base + "#rows_ids"]
+            assert (grads[base][ids] - ref).abs().max().item() <= gtol, key
+        elif what == "row0_absmax":
+            assert grads[base][0].abs().max().item() == 0.0 and ref.item() == 0.0
+
+
+@pytest.mark.parametrize("name", ["train_small.pt", "train_c1.pt"])
+def test_oracle_eval_embeddings(name):
+    gold = _load(name)
+    cfg = synthetic.TwoTowerConfig(**gold["config"])
+    sd = synthetic.make_state_dict(cfg, seed=gold["seed_w"])
+    batch = synthetic.make_batch(cfg, gold["batch_size"], seed=gold["seed_b"],
+                                 full_length=gold["full_length"])
+    p = {k: (v.double() if v.is_floating_point() else v) for k, v in sd.items()}
+    b = _cast(batch, torch.float64)
+    u = oracle.l2_normalize(oracle.user_tower(p, b["history_ids"], b["user_gender"], b["user_country"],
+                                              b["history_mask"], cfg.num_heads))
+    assert (u - gold["f64"]["eval_user_emb"]).abs().max().item() <= 1e-9
+    z = torch.zeros_like(b["user_gender"])
+    u2 = oracle.l2_normalize(oracle.user_tower(p, b["history_ids"], z, z, None, cfg.num_heads))
+    assert (u2 - gold["f64"]["eval_user_emb_nomask"]).abs().max().item() <= 1e-9
+    # the reference model had done one training forward before .eval(): use its running stats
+    p["item_tower.fusion_layer.1.running_mean"] = gold["f64"]["bn_running_mean"]
+    p["item_tower.fusion_layer.1.running_var"] = gold["f64"]["bn_running_var"]
+    it, _ = oracle.item_fusion(p, b["target_audio"], b["target_image"], b["target_input_ids"],
+                               b["target_tabular"], training=False)
+    assert (oracle.l2_normalize(it) - gold["f64"]["eval_item_emb"]).abs().max().item() <= 1e-9
+
+
+@pytest.mark.parametrize("name", ["retrieval_grid.pt", "retrieval_grid_coarse.pt", "retrieval_float.pt"])
+def test_oracle_retrieval_matches_reference(name):
+    gold = _load(name)
+    table = synthetic.make_catalog(gold["num_items"], 256, seed=gold["seed"], grid=gold["grid"])
+    users, targets = synthetic.make_queries(table, gold["num_users"], seed=gold["seed"] + 1,
+                                            noise=gold["noise"], grid=gold["grid"])
+    scores = oracle.retrieval_scores(users, table)
+    vals, idx = oracle.canonical_topk(scores, max(gold["k_list"]))
+    assert torch.equal(idx.to(torch.int32), gold["topk_idx"])
+    assert torch.equal(vals, gold["topk_val"])
+    m = oracle.calculate_metrics_global(users, table, targets, gold["k_list"])
+    for k, v in gold["metrics"].items():
+        assert m[k] == v, (k, m[k], v)
