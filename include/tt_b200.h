@@ -79,6 +79,22 @@ typedef struct tt_gemm_args {
 
 int tt_gemm_bf16(const tt_gemm_args* args, void* stream);
 
+/* ---- causal self-attention, d_head = 64 -------------------------------------------
+ * Replaces F.scaled_dot_product_attention inside nn.TransformerEncoderLayer
+ * (src/models/user_tower.py:37-45, 111-116) for right-padded histories.
+ *   qkv  : bf16 [B*L, 3*H*64], columns [Q | K | V], head h at h*64 inside each third
+ *          (the packed in_proj output, rows [Q;K;V] of in_proj_weight)
+ *   ctx  : bf16 [B*L, H*64]     attention output before out_proj
+ *   lse  : fp32 [B, H, L]       natural-log sum-exp of the scaled scores (for backward)
+ * Dropout (p > 0) is applied to the attention probabilities with the counter-based hash
+ * (seed, site, ((b*H+h)*L+i)*L+j). L <= 512 forward, L <= 256 backward.
+ */
+int tt_attn_causal_fwd(const void* qkv, void* ctx, float* lse, int B, int L, int H, float drop_p,
+                       uint64_t drop_seed, uint32_t drop_site, void* stream);
+int tt_attn_causal_bwd(const void* qkv, const void* ctx, const void* dctx, const float* lse,
+                       void* dqkv, int B, int L, int H, float drop_p, uint64_t drop_seed,
+                       uint32_t drop_site, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -53,6 +53,12 @@ def _declare(l):
     l.tt_num_sms.restype = c_int32
     l.tt_gemm_bf16.restype = c_int32
     l.tt_gemm_bf16.argtypes = [ctypes.POINTER(GemmArgs), c_void_p]
+    l.tt_attn_causal_fwd.restype = c_int32
+    l.tt_attn_causal_fwd.argtypes = [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_float,
+                                     c_uint64, c_uint32, c_void_p]
+    l.tt_attn_causal_bwd.restype = c_int32
+    l.tt_attn_causal_bwd.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32,
+                                     c_int32, c_float, c_uint64, c_uint32, c_void_p]
 
 
 def lib():

@@ -1,0 +1,634 @@
+// Causal self-attention for the SASRec user tower on tcgen05 (sm_100a), d_head = 64.
+//
+// Replaces the scaled_dot_product_attention call the reference reaches through
+// nn.TransformerEncoderLayer (src/models/user_tower.py:37-45,111-116). The reference feeds a
+// dense additive (causal + key-padding) float mask; here the histories are right-padded, so
+// for every VALID query row the causal predicate alone is the full mask (keys <= query <
+// length) and no mask tensor exists. Pad-query rows produce finite values nobody reads.
+//
+// Forward: one CTA (128 threads = 128 query rows = 128 TMEM lanes) per (sequence, head,
+// 128-row query tile). All S_j = Q K_j^T tiles (j <= query tile) are issued up front into
+// TMEM (128 columns each, L <= 512), the row max is taken from TMEM, then per key tile
+// P_j = exp2(.) is written as bf16 into a 128B-swizzled K-major smem tile (double-buffered)
+// and O += P_j V_j accumulates in TMEM (V consumed MN-major straight from the QKV buffer's
+// layout). O reuses the first 64 columns of S_0 once S_0 has been drained.
+//
+// Backward: one CTA per (sequence, head) walks key tiles j and query tiles i >= j with the
+// five products of the standard attention backward, all on tcgen05 (see attn_bwd_kernel).
+#include "../../include/tt_b200.h"
+#include "tt_common.cuh"
+
+namespace tt {
+
+static constexpr int kDh = 64;
+static constexpr int kTile = 128;
+static constexpr uint32_t kTileBytes = kTile * kDh * 2;  // 16 KB: 128 rows x 64 bf16
+static constexpr float kLog2e = 1.4426950408889634f;
+
+struct AttnParams {
+  int B, L, H;
+  int nq;            // query tiles per sequence
+  float scale;       // 1/sqrt(d_head)
+  uint32_t drop_thresh;
+  float drop_scale;
+  uint64_t drop_seed;
+  uint32_t drop_site;
+  __nv_bfloat16* ctx;  // [T, H*64]
+  float* lse;          // [B, H, L]
+};
+
+// Write 8 consecutive bf16 (one 16-byte unit) of row r, unit u (0..7) into a K-major
+// 128B-swizzled [128][64] bf16 tile.
+__device__ __forceinline__ void st_swizzled_unit(uint8_t* tile, int r, int u, uint4 v) {
+  *reinterpret_cast<uint4*>(tile + r * 128 + ((u ^ (r & 7)) << 4)) = v;
+}
+
+__global__ void __launch_bounds__(128, 1)
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t pad = (1024u - (smem_u32(smem_raw) & 1023u)) & 1023u;
+  uint8_t* smem = smem_raw + pad;
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  const int bh_count = p.B * p.H;
+  const int qt = p.nq - 1 - static_cast<int>(blockIdx.x) / bh_count;  // heavy tiles first
+  const int bh = static_cast<int>(blockIdx.x) % bh_count;
+  const int b = bh / p.H, h = bh % p.H;
+  const int n_kv = qt + 1;
+  const int D = p.H * kDh;
+
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + kTileBytes;
+  uint8_t* sV = sK + static_cast<size_t>(p.nq) * kTileBytes;
+  uint8_t* sP = sV + static_cast<size_t>(p.nq) * kTileBytes;  // 2 buffers x 2 chunks x 16 KB
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 4 * kTileBytes);
+  uint64_t* bar_qk = bars + 0;
+  uint64_t* bar_v = bars + 1;
+  uint64_t* bar_s = bars + 2;
+  uint64_t* bar_pv = bars + 3;  // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+
+  uint32_t tmem_cols = 128;
+  while (tmem_cols < static_cast<uint32_t>(n_kv * kTile)) tmem_cols <<= 1;
+
+  if (tid == 0) {
+    tma_prefetch_desc(&tmQKV);
+    mbar_init(bar_qk, 1);
+    mbar_init(bar_v, 1);
+    mbar_init(bar_s, 1);
+    mbar_init(&bar_pv[0], 1);
+    mbar_init(&bar_pv[1], 1);
+    fence_barrier_init();
+  }
+  __syncwarp();
+  if (warp == 0) {
+    tmem_alloc(tmem_slot, tmem_cols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int seq_row0 = b * p.L;
+  const int q_row0 = seq_row0 + qt * kTile;
+
+  if (tid == 0) {
+    mbar_arrive_expect_tx(bar_qk, (1 + n_kv) * kTileBytes);
+    tma_load_2d(sQ, &tmQKV, bar_qk, h * kDh, q_row0);
+    for (int j = 0; j < n_kv; ++j)
+      tma_load_2d(sK + static_cast<size_t>(j) * kTileBytes, &tmQKV, bar_qk, D + h * kDh,
+                  seq_row0 + j * kTile);
+    mbar_arrive_expect_tx(bar_v, n_kv * kTileBytes);
+    for (int j = 0; j < n_kv; ++j)
+      tma_load_2d(sV + static_cast<size_t>(j) * kTileBytes, &tmQKV, bar_v, 2 * D + h * kDh,
+                  seq_row0 + j * kTile);
+    // S_j = Q K_j^T for every key tile, back to back
+    mbar_wait(bar_qk, 0);
+    tc_fence_after();
+    const uint32_t idesc_s = umma_idesc_bf16(kTile, kTile, false, false);
+    const uint32_t q_base = smem_u32(sQ);
+    for (int j = 0; j < n_kv; ++j) {
+      const uint32_t k_base = smem_u32(sK + static_cast<size_t>(j) * kTileBytes);
+#pragma unroll
+      for (int k = 0; k < kDh / 16; ++k)
+        umma_bf16(tmem_base + j * kTile, umma_desc_kmajor(q_base + k * 32),
+                  umma_desc_kmajor(k_base + k * 32), idesc_s, k > 0 ? 1u : 0u);
+    }
+    umma_commit(bar_s);
+  }
+
+  // ---- pass A: row maximum over the causal prefix --------------------------------------
+  mbar_wait(bar_s, 0);
+  __syncwarp();
+  tc_fence_after();
+  const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+  const int q_pos = qt * kTile + tid;  // position of this thread's query inside the sequence
+  float m = -INFINITY;
+  for (int j = 0; j < n_kv; ++j) {
+    const bool diag = (j == qt);
+    const int nchunks = diag ? (warp + 1) : 4;  // chunks right of the warp's rows are fully masked
+    for (int c = 0; c < nchunks; ++c) {
+      uint32_t r[32];
+      tmem_ld32(lane_base + j * kTile + c * 32, r);
+      tmem_ld_wait();
+      const int kv0 = j * kTile + c * 32;
+#pragma unroll
+      for (int t = 0; t < 32; ++t) {
+        const float s = __uint_as_float(r[t]);
+        if (!diag || kv0 + t <= q_pos) m = fmaxf(m, s);
+      }
+    }
+  }
+  const float c1 = p.scale * kLog2e;
+  const float mc = m * c1;
+
+  // ---- pass B: P_j -> smem (bf16, swizzled), O += P_j V_j ------------------------------
+  float l = 0.f;
+  const uint32_t idesc_pv = umma_idesc_bf16(kTile, kDh, false, true);
+  for (int j = 0; j < n_kv; ++j) {
+    const int buf = j & 1;
+    uint8_t* pbuf = sP + static_cast<size_t>(buf) * 2 * kTileBytes;
+    if (j >= 2) {  // the MMA that consumed this buffer two tiles ago must have retired
+      mbar_wait(&bar_pv[buf], ((j >> 1) - 1) & 1);
+    }
+    __syncwarp();  // tcgen05.ld is warp-collective: reconverge after the single-thread MMA issue
+    const bool diag = (j == qt);
+    const int nchunks = diag ? (warp + 1) : 4;
+    for (int c = 0; c < 4; ++c) {
+      uint8_t* chunk = pbuf + static_cast<size_t>(c >> 1) * kTileBytes;  // 64 kv columns per chunk
+      const int u0 = (c & 1) * 4;                                       // 16B unit inside the row
+      if (c < nchunks) {
+        uint32_t r[32];
+        tmem_ld32(lane_base + j * kTile + c * 32, r);
+        tmem_ld_wait();
+        const int kv0 = j * kTile + c * 32;
+        float pv[32];
+#pragma unroll
+        for (int t = 0; t < 32; ++t) {
+          float e = exp2f(__uint_as_float(r[t]) * c1 - mc);
+          if (diag && kv0 + t > q_pos) e = 0.f;
+          l += e;
+          if (p.drop_thresh) {
+            const uint64_t idx = (static_cast<uint64_t>(bh) * p.L + q_pos) * p.L + (kv0 + t);
+            e = drop_keep(p.drop_seed, p.drop_site, idx, p.drop_thresh) ? e * p.drop_scale : 0.f;
+          }
+          pv[t] = e;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          uint4 v;
+          v.x = pack_bf16(pv[u * 8 + 0], pv[u * 8 + 1]);
+          v.y = pack_bf16(pv[u * 8 + 2], pv[u * 8 + 3]);
+          v.z = pack_bf16(pv[u * 8 + 4], pv[u * 8 + 5]);
+          v.w = pack_bf16(pv[u * 8 + 6], pv[u * 8 + 7]);
+          st_swizzled_unit(chunk, tid, u0 + u, v);
+        }
+      } else {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) st_swizzled_unit(chunk, tid, u0 + u, make_uint4(0, 0, 0, 0));
+      }
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      if (j == 0) mbar_wait(bar_v, 0);
+      const uint32_t p_base = smem_u32(pbuf);
+      const uint32_t v_base = smem_u32(sV + static_cast<size_t>(j) * kTileBytes);
+#pragma unroll
+      for (int k = 0; k < kTile / 16; ++k) {
+        // A = P: chunk (k/4), 32 B per 16 kv columns; B = V rows (MN-major): 16 kv rows = 2048 B
+        const uint64_t adesc = umma_desc_kmajor(p_base + (k >> 2) * kTileBytes + (k & 3) * 32);
+        const uint64_t bdesc = umma_desc_mnmajor(v_base + k * 2048, kTileBytes);
+        umma_bf16(tmem_base, adesc, bdesc, idesc_pv, (j > 0 || k > 0) ? 1u : 0u);
+      }
+      umma_commit(&bar_pv[buf]);
+    }
+  }
+
+  // ---- epilogue: O / l -> ctx, log-sum-exp -> lse ---------------------------------------
+  {
+    const int last = n_kv - 1;
+    mbar_wait(&bar_pv[last & 1], (last >> 1) & 1);
+    __syncwarp();
+    tc_fence_after();
+    const float inv_l = 1.f / l;
+    const bool valid = q_pos < p.L;
+    __nv_bfloat16* orow = p.ctx + static_cast<size_t>(seq_row0 + q_pos) * D + h * kDh;
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      uint32_t r[32];
+      tmem_ld32(lane_base + c * 32, r);
+      tmem_ld_wait();
+      if (valid) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          uint4 v;
+          v.x = pack_bf16(__uint_as_float(r[u * 8 + 0]) * inv_l, __uint_as_float(r[u * 8 + 1]) * inv_l);
+          v.y = pack_bf16(__uint_as_float(r[u * 8 + 2]) * inv_l, __uint_as_float(r[u * 8 + 3]) * inv_l);
+          v.z = pack_bf16(__uint_as_float(r[u * 8 + 4]) * inv_l, __uint_as_float(r[u * 8 + 5]) * inv_l);
+          v.w = pack_bf16(__uint_as_float(r[u * 8 + 6]) * inv_l, __uint_as_float(r[u * 8 + 7]) * inv_l);
+          *reinterpret_cast<uint4*>(orow + c * 32 + u * 8) = v;
+        }
+      }
+    }
+    if (valid && p.lse) p.lse[static_cast<size_t>(bh) * p.L + q_pos] = m * p.scale + __logf(l);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, tmem_cols);
+}
+
+// --------------------------------------------------------------------------------------------
+// Backward. One CTA (128 threads) per (sequence, head). For key tile j and query tile i >= j:
+//   S   = Q_i K_j^T                    (TMEM cols [0,128))
+//   dP  = dO_i V_j^T                   (TMEM cols [128,256))
+//   P   = exp2(scale*log2e*S - lse_i*log2e) under the causal mask; Pd = dropout(P)
+//   dS  = P * (dropout(dP) - delta_i) * scale,  delta_i = rowsum(dO_i * O_i)
+//   dV_j += Pd^T dO_i   (A = Pd stored [q][kv] read MN-major, B = dO_i read MN-major)
+//   dK_j += dS^T Q_i    (A = dS read MN-major,               B = Q_i  read MN-major)
+//   dQ_i += dS K_j      (A = dS K-major,                     B = K_j  read MN-major)
+// dV_j, dK_j live in TMEM (cols [256,320), [320,384)) across the inner loop; dQ_i
+// (cols [384 + 64*i ...)) is kept for up to two query tiles, i.e. L <= 256.
+// Pd and dS are staged as bf16 in 128B-swizzled smem tiles.
+// --------------------------------------------------------------------------------------------
+struct AttnBwdParams {
+  int B, L, H, nq;
+  float scale;
+  uint32_t drop_thresh;
+  float drop_scale;
+  uint64_t drop_seed;
+  uint32_t drop_site;
+  const __nv_bfloat16* ctx;   // O  [T, H*64]
+  const __nv_bfloat16* dctx;  // dO [T, H*64]
+  const float* lse;           // [B,H,L]
+  __nv_bfloat16* dqkv;        // [T, 3*H*64]
+};
+
+__global__ void __launch_bounds__(128, 1)
+attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
+                const AttnBwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t pad = (1024u - (smem_u32(smem_raw) & 1023u)) & 1023u;
+  uint8_t* smem = smem_raw + pad;
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  const int bh = blockIdx.x;
+  const int b = bh / p.H, h = bh % p.H;
+  const int D = p.H * kDh;
+  const int nq = p.nq;
+  const int seq_row0 = b * p.L;
+
+  // smem: Q[nq], dO[nq], K_j, V_j, Pd (2 chunks), dS (2 chunks)
+  uint8_t* sQ = smem;
+  uint8_t* sDO = sQ + static_cast<size_t>(nq) * kTileBytes;
+  uint8_t* sK = sDO + static_cast<size_t>(nq) * kTileBytes;
+  uint8_t* sV = sK + kTileBytes;
+  uint8_t* sPd = sV + kTileBytes;
+  uint8_t* sDS = sPd + 2 * kTileBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sDS + 2 * kTileBytes);
+  uint64_t* bar_q = bars + 0;    // Q/dO tiles loaded
+  uint64_t* bar_kv = bars + 1;   // K_j/V_j loaded (phase per j)
+  uint64_t* bar_mm1 = bars + 2;  // S and dP ready (phase per (j,i))
+  uint64_t* bar_mm2 = bars + 3;  // dV/dK/dQ MMAs of this (j,i) retired
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+  float* sDelta = reinterpret_cast<float*>(bars + 6);  // [nq*128]
+  float* sLse = sDelta + nq * kTile;                   // [nq*128], pre-multiplied by log2e
+
+  const uint32_t tmem_cols = 512;
+  if (tid == 0) {
+    tma_prefetch_desc(&tmQKV);
+    tma_prefetch_desc(&tmDO);
+    mbar_init(bar_q, 1);
+    mbar_init(bar_kv, 1);
+    mbar_init(bar_mm1, 1);
+    mbar_init(bar_mm2, 1);
+    fence_barrier_init();
+  }
+  __syncwarp();
+  if (warp == 0) {
+    tmem_alloc(tmem_slot, tmem_cols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+  const uint32_t T_S = 0, T_DP = 128, T_DV = 256, T_DK = 320, T_DQ = 384;
+
+  if (tid == 0) {
+    mbar_arrive_expect_tx(bar_q, 2 * nq * kTileBytes);
+    for (int i = 0; i < nq; ++i) {
+      tma_load_2d(sQ + static_cast<size_t>(i) * kTileBytes, &tmQKV, bar_q, h * kDh, seq_row0 + i * kTile);
+      tma_load_2d(sDO + static_cast<size_t>(i) * kTileBytes, &tmDO, bar_q, h * kDh, seq_row0 + i * kTile);
+    }
+  }
+  // delta_i = rowsum(dO * O), lse -> smem (generic loads; rows beyond L are treated as zero)
+  for (int i = 0; i < nq; ++i) {
+    const int pos = i * kTile + tid;
+    float delta = 0.f, lse2 = 0.f;
+    if (pos < p.L) {
+      const uint4* o = reinterpret_cast<const uint4*>(p.ctx + static_cast<size_t>(seq_row0 + pos) * D + h * kDh);
+      const uint4* g = reinterpret_cast<const uint4*>(p.dctx + static_cast<size_t>(seq_row0 + pos) * D + h * kDh);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const uint4 a = __ldg(o + u), c = __ldg(g + u);
+        const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, cw[4] = {c.x, c.y, c.z, c.w};
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+          const float2 x = unpack_bf16(aw[w]), y = unpack_bf16(cw[w]);
+          delta += x.x * y.x + x.y * y.y;
+        }
+      }
+      lse2 = p.lse[static_cast<size_t>(bh) * p.L + pos] * kLog2e;
+    }
+    sDelta[pos] = delta;
+    sLse[pos] = lse2;
+  }
+  __syncthreads();
+
+  const float c1 = p.scale * kLog2e;
+  const uint32_t idesc_s = umma_idesc_bf16(kTile, kTile, false, false);    // Q K^T, dO V^T
+  const uint32_t idesc_t = umma_idesc_bf16(kTile, kDh, true, true);        // X^T Y (dV, dK)
+  const uint32_t idesc_q = umma_idesc_bf16(kTile, kDh, false, true);       // dS K
+  uint32_t it = 0;  // (j,i) iteration counter -> mbarrier phase
+  uint32_t dq_started = 0;  // bit i set once dQ_i has received its first MMA
+
+  for (int j = 0; j < nq; ++j) {
+    if (tid == 0) {
+      // previous key tile's MMAs (which read sK/sV) have retired: bar_mm2 waited in-loop
+      mbar_arrive_expect_tx(bar_kv, 2 * kTileBytes);
+      tma_load_2d(sK, &tmQKV, bar_kv, D + h * kDh, seq_row0 + j * kTile);
+      tma_load_2d(sV, &tmQKV, bar_kv, 2 * D + h * kDh, seq_row0 + j * kTile);
+    }
+    for (int i = j; i < nq; ++i, ++it) {
+      if (tid == 0) {
+        if (it == 0) mbar_wait(bar_q, 0);
+        if (i == j) mbar_wait(bar_kv, j & 1);
+        tc_fence_after();
+        const uint32_t q_base = smem_u32(sQ + static_cast<size_t>(i) * kTileBytes);
+        const uint32_t do_base = smem_u32(sDO + static_cast<size_t>(i) * kTileBytes);
+        const uint32_t k_base = smem_u32(sK), v_base = smem_u32(sV);
+#pragma unroll
+        for (int k = 0; k < kDh / 16; ++k)
+          umma_bf16(tmem_base + T_S, umma_desc_kmajor(q_base + k * 32), umma_desc_kmajor(k_base + k * 32),
+                    idesc_s, k > 0 ? 1u : 0u);
+#pragma unroll
+        for (int k = 0; k < kDh / 16; ++k)
+          umma_bf16(tmem_base + T_DP, umma_desc_kmajor(do_base + k * 32), umma_desc_kmajor(v_base + k * 32),
+                    idesc_s, k > 0 ? 1u : 0u);
+        umma_commit(bar_mm1);
+      }
+      mbar_wait(bar_mm1, it & 1);
+      __syncwarp();
+      tc_fence_after();
+
+      const int q_pos = i * kTile + tid;
+      const float lse2 = sLse[q_pos];
+      const float delta = sDelta[q_pos];
+      const bool diag = (i == j);
+      const int nchunks = diag ? (warp + 1) : 4;
+      for (int c = 0; c < 4; ++c) {
+        uint8_t* pchunk = sPd + static_cast<size_t>(c >> 1) * kTileBytes;
+        uint8_t* dchunk = sDS + static_cast<size_t>(c >> 1) * kTileBytes;
+        const int u0 = (c & 1) * 4;
+        if (c < nchunks) {
+          uint32_t rs[32], rp[32];
+          tmem_ld32(lane_base + T_S + c * 32, rs);
+          tmem_ld32(lane_base + T_DP + c * 32, rp);
+          tmem_ld_wait();
+          const int kv0 = j * kTile + c * 32;
+          float pd[32], ds[32];
+#pragma unroll
+          for (int t = 0; t < 32; ++t) {
+            float pr = exp2f(__uint_as_float(rs[t]) * c1 - lse2);
+            if ((diag && kv0 + t > q_pos) || q_pos >= p.L) pr = 0.f;
+            float dp = __uint_as_float(rp[t]);
+            float pdrop = pr;
+            if (p.drop_thresh) {
+              const uint64_t idx = (static_cast<uint64_t>(bh) * p.L + q_pos) * p.L + (kv0 + t);
+              const bool keep = drop_keep(p.drop_seed, p.drop_site, idx, p.drop_thresh);
+              pdrop = keep ? pr * p.drop_scale : 0.f;
+              dp = keep ? dp * p.drop_scale : 0.f;
+            }
+            pd[t] = pdrop;
+            ds[t] = pr * (dp - delta) * p.scale;
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            uint4 v, w;
+            v.x = pack_bf16(pd[u * 8 + 0], pd[u * 8 + 1]);
+            v.y = pack_bf16(pd[u * 8 + 2], pd[u * 8 + 3]);
+            v.z = pack_bf16(pd[u * 8 + 4], pd[u * 8 + 5]);
+            v.w = pack_bf16(pd[u * 8 + 6], pd[u * 8 + 7]);
+            w.x = pack_bf16(ds[u * 8 + 0], ds[u * 8 + 1]);
+            w.y = pack_bf16(ds[u * 8 + 2], ds[u * 8 + 3]);
+            w.z = pack_bf16(ds[u * 8 + 4], ds[u * 8 + 5]);
+            w.w = pack_bf16(ds[u * 8 + 6], ds[u * 8 + 7]);
+            st_swizzled_unit(pchunk, tid, u0 + u, v);
+            st_swizzled_unit(dchunk, tid, u0 + u, w);
+          }
+        } else {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            st_swizzled_unit(pchunk, tid, u0 + u, make_uint4(0, 0, 0, 0));
+            st_swizzled_unit(dchunk, tid, u0 + u, make_uint4(0, 0, 0, 0));
+          }
+        }
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncthreads();
+      if (tid == 0) {
+        tc_fence_after();
+        const uint32_t pd_base = smem_u32(sPd), ds_base = smem_u32(sDS);
+        const uint32_t q_base = smem_u32(sQ + static_cast<size_t>(i) * kTileBytes);
+        const uint32_t do_base = smem_u32(sDO + static_cast<size_t>(i) * kTileBytes);
+        const uint32_t k_base = smem_u32(sK);
+        // Pd / dS are stored [q row][kv col] in two 64-column chunks. Read as the TRANSPOSED
+        // operand (M = kv, contraction = q) they are MN-major: 16 q rows = 2048 B per K step,
+        // 64-wide kv chunks are kTileBytes apart.
+#pragma unroll
+        for (int k = 0; k < kTile / 16; ++k) {
+          // dV_j += Pd^T dO_i
+          umma_bf16(tmem_base + T_DV, umma_desc_mnmajor(pd_base + k * 2048, kTileBytes),
+                    umma_desc_mnmajor(do_base + k * 2048, kTileBytes), idesc_t, (i > j || k > 0) ? 1u : 0u);
+        }
+#pragma unroll
+        for (int k = 0; k < kTile / 16; ++k) {
+          // dK_j += dS^T Q_i
+          umma_bf16(tmem_base + T_DK, umma_desc_mnmajor(ds_base + k * 2048, kTileBytes),
+                    umma_desc_mnmajor(q_base + k * 2048, kTileBytes), idesc_t, (i > j || k > 0) ? 1u : 0u);
+        }
+        const uint32_t first = ((dq_started >> i) & 1u) ? 0u : 1u;
+#pragma unroll
+        for (int k = 0; k < kTile / 16; ++k) {
+          // dQ_i += dS K_j : A = dS K-major (chunk k/4, 32 B per 16 kv), B = K_j rows MN-major
+          umma_bf16(tmem_base + T_DQ + i * kDh,
+                    umma_desc_kmajor(ds_base + (k >> 2) * kTileBytes + (k & 3) * 32),
+                    umma_desc_mnmajor(k_base + k * 2048, kTileBytes), idesc_q, (first && k == 0) ? 0u : 1u);
+        }
+        dq_started |= (1u << i);
+        umma_commit(bar_mm2);
+      }
+      // Pd/dS (and, on the last i, K_j/V_j) may only be overwritten once these MMAs retire.
+      mbar_wait(bar_mm2, it & 1);
+      __syncwarp();
+      tc_fence_after();
+    }
+    // ---- dK_j, dV_j complete: TMEM -> dqkv -------------------------------------------------
+    {
+      const int pos = j * kTile + tid;
+      const bool valid = pos < p.L;
+      __nv_bfloat16* row = p.dqkv + static_cast<size_t>(seq_row0 + pos) * (3 * D);
+#pragma unroll
+      for (int which = 0; which < 2; ++which) {  // 0: dK, 1: dV
+        const uint32_t tcol = which == 0 ? T_DK : T_DV;
+        __nv_bfloat16* dst = row + (which == 0 ? D : 2 * D) + h * kDh;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          uint32_t r[32];
+          tmem_ld32(lane_base + tcol + c * 32, r);
+          tmem_ld_wait();
+          if (valid) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              uint4 v;
+              v.x = pack_bf16(__uint_as_float(r[u * 8 + 0]), __uint_as_float(r[u * 8 + 1]));
+              v.y = pack_bf16(__uint_as_float(r[u * 8 + 2]), __uint_as_float(r[u * 8 + 3]));
+              v.z = pack_bf16(__uint_as_float(r[u * 8 + 4]), __uint_as_float(r[u * 8 + 5]));
+              v.w = pack_bf16(__uint_as_float(r[u * 8 + 6]), __uint_as_float(r[u * 8 + 7]));
+              *reinterpret_cast<uint4*>(dst + c * 32 + u * 8) = v;
+            }
+          }
+        }
+      }
+    }
+    tc_fence_before();
+    __syncthreads();  // everyone has drained dK/dV before the next j overwrites them
+    tc_fence_after();
+  }
+
+  // ---- dQ_i -> dqkv ---------------------------------------------------------------------
+  for (int i = 0; i < nq; ++i) {
+    const int pos = i * kTile + tid;
+    const bool valid = pos < p.L;
+    __nv_bfloat16* dst = p.dqkv + static_cast<size_t>(seq_row0 + pos) * (3 * D) + h * kDh;
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      uint32_t r[32];
+      tmem_ld32(lane_base + T_DQ + i * kDh + c * 32, r);
+      tmem_ld_wait();
+      if (valid) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          uint4 v;
+          v.x = pack_bf16(__uint_as_float(r[u * 8 + 0]), __uint_as_float(r[u * 8 + 1]));
+          v.y = pack_bf16(__uint_as_float(r[u * 8 + 2]), __uint_as_float(r[u * 8 + 3]));
+          v.z = pack_bf16(__uint_as_float(r[u * 8 + 4]), __uint_as_float(r[u * 8 + 5]));
+          v.w = pack_bf16(__uint_as_float(r[u * 8 + 6]), __uint_as_float(r[u * 8 + 7]));
+          *reinterpret_cast<uint4*>(dst + c * 32 + u * 8) = v;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, tmem_cols);
+}
+
+static int make_rows_map(CUtensorMap* m, const void* base, int rows, int cols) {
+  uint64_t dims[2] = {static_cast<uint64_t>(cols), static_cast<uint64_t>(rows)};
+  uint64_t str[1] = {static_cast<uint64_t>(cols) * 2};
+  uint32_t box[2] = {kDh, kTile};
+  return make_tmap_bf16(m, base, 2, dims, str, box);
+}
+
+static uint32_t drop_threshold(float p) {
+  if (p <= 0.f) return 0;
+  double t = static_cast<double>(p) * 4294967296.0;
+  uint32_t v = t >= 4294967295.0 ? 4294967295u : static_cast<uint32_t>(t);
+  return v == 0 ? 1 : v;
+}
+
+}  // namespace tt
+
+extern "C" int tt_attn_causal_fwd(const void* qkv, void* ctx, float* lse, int B, int L, int H, float drop_p,
+                                  uint64_t drop_seed, uint32_t drop_site, void* stream_) {
+  using namespace tt;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  TT_REQUIRE(qkv && ctx, "tt_attn_causal_fwd: null pointer");
+  TT_REQUIRE(B > 0 && L > 0 && H > 0, "tt_attn_causal_fwd: empty problem");
+  TT_REQUIRE(L <= 512, "tt_attn_causal_fwd: L=%d > 512 unsupported", L);
+  TT_REQUIRE(drop_p >= 0.f && drop_p < 1.f, "tt_attn_causal_fwd: drop_p out of range");
+  const int D = H * kDh;
+  AttnParams p;
+  p.B = B; p.L = L; p.H = H;
+  p.nq = (L + kTile - 1) / kTile;
+  p.scale = 0.125f;
+  p.drop_thresh = drop_threshold(drop_p);
+  p.drop_scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+  p.drop_seed = drop_seed;
+  p.drop_site = drop_site;
+  p.ctx = static_cast<__nv_bfloat16*>(ctx);
+  p.lse = lse;
+  CUtensorMap tm;
+  int rc = make_rows_map(&tm, qkv, B * L, 3 * D);
+  if (rc) return rc;
+  const size_t smem = 1024 + static_cast<size_t>(1 + 2 * p.nq + 4) * kTileBytes + 128;
+  static bool configured = false;
+  if (!configured) {
+    TT_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    configured = true;
+  }
+  TT_REQUIRE(smem <= 232448, "tt_attn_causal_fwd: shared memory %zu too large", smem);
+  attn_fwd_kernel<<<B * H * p.nq, 128, smem, stream>>>(tm, p);
+  TT_LAUNCH_CHECK();
+  return TT_OK;
+}
+
+extern "C" int tt_attn_causal_bwd(const void* qkv, const void* ctx, const void* dctx, const float* lse, void* dqkv,
+                                  int B, int L, int H, float drop_p, uint64_t drop_seed, uint32_t drop_site,
+                                  void* stream_) {
+  using namespace tt;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  TT_REQUIRE(qkv && ctx && dctx && lse && dqkv, "tt_attn_causal_bwd: null pointer");
+  TT_REQUIRE(B > 0 && L > 0 && H > 0, "tt_attn_causal_bwd: empty problem");
+  TT_REQUIRE(L <= 256, "tt_attn_causal_bwd: L=%d > 256 unsupported in this build", L);
+  const int D = H * kDh;
+  AttnBwdParams p;
+  p.B = B; p.L = L; p.H = H;
+  p.nq = (L + kTile - 1) / kTile;
+  p.scale = 0.125f;
+  p.drop_thresh = drop_threshold(drop_p);
+  p.drop_scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+  p.drop_seed = drop_seed;
+  p.drop_site = drop_site;
+  p.ctx = static_cast<const __nv_bfloat16*>(ctx);
+  p.dctx = static_cast<const __nv_bfloat16*>(dctx);
+  p.lse = lse;
+  p.dqkv = static_cast<__nv_bfloat16*>(dqkv);
+  CUtensorMap tmQ, tmDO;
+  int rc = make_rows_map(&tmQ, qkv, B * L, 3 * D);
+  if (rc) return rc;
+  rc = make_rows_map(&tmDO, dctx, B * L, D);
+  if (rc) return rc;
+  const size_t smem = 1024 + static_cast<size_t>(2 * p.nq + 2 + 4) * kTileBytes + 64 +
+                      static_cast<size_t>(2 * p.nq * kTile) * sizeof(float);
+  static bool configured = false;
+  if (!configured) {
+    TT_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    configured = true;
+  }
+  TT_REQUIRE(smem <= 232448, "tt_attn_causal_bwd: shared memory %zu too large", smem);
+  attn_bwd_kernel<<<B * H, 128, smem, stream>>>(tmQ, tmDO, p);
+  TT_LAUNCH_CHECK();
+  return TT_OK;
+}

@@ -264,6 +264,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int mn = t / p.k_splits;
       const int m_blk = mn / tiles_n, n_blk = mn % tiles_n;
       mbar_wait(&tfull_bar[acc], acc_phase);
+      __syncwarp();
       tc_fence_after();
       const int row = m_blk * kBlockM + ew * 32 + lane;
       const uint32_t t_base = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) +

@@ -81,3 +81,28 @@ def gemm(A: torch.Tensor, B: torch.Tensor, *, a_mn: bool = False, b_mn: bool = F
     args.k_splits = k_splits
     args.block_n = block_n
     check(lib().tt_gemm_bf16(ctypes.byref(args), _stream()), "tt_gemm_bf16")
+
+
+def attn_fwd(qkv: torch.Tensor, ctx: torch.Tensor, lse: Optional[torch.Tensor], B: int, L: int, H: int,
+             drop_p: float = 0.0, drop_seed: int = 0, drop_site: int = 0) -> None:
+    """Causal self-attention forward (tt_attn_causal_fwd). qkv bf16 [B*L, 3*H*64] -> ctx bf16 [B*L, H*64]."""
+    _require_cuda(qkv, ctx, lse)
+    assert qkv.dtype == torch.bfloat16 and qkv.is_contiguous() and qkv.shape == (B * L, 3 * H * 64)
+    assert ctx.dtype == torch.bfloat16 and ctx.is_contiguous() and ctx.shape == (B * L, H * 64)
+    if lse is not None:
+        assert lse.dtype == torch.float32 and lse.is_contiguous() and lse.numel() == B * H * L
+    check(lib().tt_attn_causal_fwd(qkv.data_ptr(), ctx.data_ptr(), _ptr(lse), B, L, H, drop_p,
+                                   drop_seed, drop_site, _stream()), "tt_attn_causal_fwd")
+
+
+def attn_bwd(qkv: torch.Tensor, ctx: torch.Tensor, dctx: torch.Tensor, lse: torch.Tensor,
+             dqkv: torch.Tensor, B: int, L: int, H: int, drop_p: float = 0.0, drop_seed: int = 0,
+             drop_site: int = 0) -> None:
+    """Causal self-attention backward (tt_attn_causal_bwd): dqkv bf16 [B*L, 3*H*64]."""
+    _require_cuda(qkv, ctx, dctx, lse, dqkv)
+    for t in (qkv, ctx, dctx, dqkv):
+        assert t.dtype == torch.bfloat16 and t.is_contiguous()
+    assert lse.dtype == torch.float32 and lse.is_contiguous()
+    check(lib().tt_attn_causal_bwd(qkv.data_ptr(), ctx.data_ptr(), dctx.data_ptr(), lse.data_ptr(),
+                                   dqkv.data_ptr(), B, L, H, drop_p, drop_seed, drop_site, _stream()),
+          "tt_attn_causal_bwd")
