@@ -44,9 +44,12 @@ int tt_num_sms(void);
  *
  * Operand layouts (bf16):
  *   a_mn = 0 : A is [M, lda]  (K contiguous;  "K-major")
- *   a_mn = 1 : A is [K, lda]  (M contiguous; "MN-major", i.e. A^T stored) — M % 64 == 0
+ *   a_mn = 1 : A is [K, lda]  (M contiguous; "MN-major", i.e. A^T stored) — M % 8 == 0
  *   b_mn = 0 : B is [N, ldb]  (K contiguous; nn.Linear weight layout)
- *   b_mn = 1 : B is [K, ldb]  (N contiguous) — N % 64 == 0
+ *   b_mn = 1 : B is [K, ldb]  (N contiguous) — N % 8 == 0
+ *   MN-major operands are fetched in 64-element chunks: when M (N) is not a multiple of 64 the
+ *   last chunk of each K row reads past it (values never stored), so the buffer must stay
+ *   readable up to the next multiple of 64 after its last row.
  * Epilogue, applied in this order to v = alpha * acc:
  *   v += bias[n]; relu; dropout(seed, site, m*N+n); gate (v = gate[m,n] > 0 ? v*gate_scale : 0);
  *   v += residual[m,n]; store fp32 (optionally atomically accumulated) and/or bf16.
@@ -62,6 +65,7 @@ typedef struct tt_gemm_args {
   int32_t relu;
   float drop_p;            /* 0 => no dropout */
   uint64_t drop_seed;
+  const uint64_t* drop_seed_dev; /* optional device scalar added to drop_seed (graph replay) */
   uint32_t drop_site;
   const void* gate;        /* bf16 [M, ld_gate] or NULL */
   int32_t ld_gate;
@@ -87,13 +91,146 @@ int tt_gemm_bf16(const tt_gemm_args* args, void* stream);
  *   ctx  : bf16 [B*L, H*64]     attention output before out_proj
  *   lse  : fp32 [B, H, L]       natural-log sum-exp of the scaled scores (for backward)
  * Dropout (p > 0) is applied to the attention probabilities with the counter-based hash
- * (seed, site, ((b*H+h)*L+i)*L+j). L <= 512 forward, L <= 256 backward.
+ * (seed + *seed_dev, site, ((b*H+h)*L+i)*L+j). L <= 512 forward, L <= 256 backward.
  */
 int tt_attn_causal_fwd(const void* qkv, void* ctx, float* lse, int B, int L, int H, float drop_p,
-                       uint64_t drop_seed, uint32_t drop_site, void* stream);
+                       uint64_t drop_seed, const uint64_t* drop_seed_dev, uint32_t drop_site, void* stream);
 int tt_attn_causal_bwd(const void* qkv, const void* ctx, const void* dctx, const float* lse,
                        void* dqkv, int B, int L, int H, float drop_p, uint64_t drop_seed,
-                       uint32_t drop_site, void* stream);
+                       const uint64_t* drop_seed_dev, uint32_t drop_site, void* stream);
+
+/* ---- bandwidth-bound row-wise kernels ------------------------------------------------
+ * Dropout everywhere is the counter-based hash of (seed [+ *seed_dev], site, element index);
+ * the same triple in forward and backward reproduces the mask, so no mask is stored.
+ */
+
+/* fp32 -> bf16 copy of n (multiple of 4) elements: tensor-core operand shadows of the dense
+ * weights (the reference's autocast casts, src/train.py:57). */
+int tt_cast_bf16(const float* src, void* dst_bf16, int64_t n, void* stream);
+
+/* last_idx[b] = max(sum(mask[b,:] != 0) - 1, 0); mask == NULL uses ids != 0
+ * (src/models/user_tower.py:122-128). ids/mask int64 [B, L]. */
+int tt_last_index(const int64_t* ids, const int64_t* mask, int B, int L, int32_t* last_idx, void* stream);
+
+/* x0 = dropout(LayerNorm(E[ids] + P[pos])) fp32 [B*L,256]; h = LayerNorm_next(x0) bf16.
+ * Replaces nn.Embedding lookup + positional add + layer_norm + dropout
+ * (src/models/user_tower.py:86-93) and the first encoder norm1. */
+int tt_embed_ln_fwd(const int64_t* ids, const float* E, const float* P, const float* ln_w, const float* ln_b,
+                    const float* next_w, const float* next_b, int B, int L, float drop_p, uint64_t seed,
+                    const uint64_t* seed_dev, uint32_t site, float* x0, void* h_bf16, void* stream);
+
+/* backward of the embedding LayerNorm + lookup: dx0 -> dE (scatter-add, row 0 skipped:
+ * padding_idx, src/models/user_tower.py:26), dP, d(ln_w), d(ln_b); all accumulated. */
+int tt_embed_ln_bwd(const int64_t* ids, const float* E, const float* P, const float* ln_w, const float* ln_b,
+                    const float* dx0, int B, int L, float drop_p, uint64_t seed, const uint64_t* seed_dev,
+                    uint32_t site, float* dE, float* dP, float* dgamma, float* dbeta, void* stream);
+
+/* Row chain on fp32 rows of width 256 or 512:
+ *   forward : [LayerNorm] -> [ReLU] -> [dropout] -> [L2 normalise] -> out_f32 / out_bf16
+ *   backward: recomputes the forward from x, then dout -> ... -> (+resid) -> dx_f32 / dx_bf16,
+ *             accumulating dgamma/dbeta and (optionally) the column sums of dx_bf16; dx_bf16 may
+ *             receive a second dropout mask (drop2_*), the one of the residual branch it feeds.
+ * Covers nn.LayerNorm, F.normalize, the user fusion LN+ReLU and the item LN+normalise
+ * (src/models/user_tower.py:47,54-55; item_tower.py:128; two_tower.py:100-101). */
+typedef struct tt_chain_args {
+  const float* x;
+  int32_t rows, width;
+  const float* ln_w;
+  const float* ln_b;
+  float ln_eps;
+  int32_t relu;
+  float drop_p;
+  uint64_t drop_seed;
+  const uint64_t* drop_seed_dev;
+  uint32_t drop_site;
+  int32_t l2norm;
+  float l2_eps;
+  float* out_f32;
+  void* out_bf16;
+  /* backward */
+  const float* dout;
+  const float* resid;
+  float* dx_f32;
+  void* dx_bf16;
+  float drop2_p;
+  uint32_t drop2_site;
+  float* dgamma;
+  float* dbeta;
+  float* dx_colsum;
+} tt_chain_args;
+int tt_chain_fwd(const tt_chain_args* args, void* stream);
+int tt_chain_bwd(const tt_chain_args* args, void* stream);
+
+/* cat[b] = [x[b*L + last_idx[b], :256] | G[gender[b]] (16) | C[country[b]] (32)] as bf16 [B,304]
+ * (src/models/user_tower.py:132-139) and its backward (dx must be zero-initialised). */
+int tt_gather_cat_fwd(const float* x, const int32_t* last_idx, const int64_t* gender, const int64_t* country,
+                      const float* G, const float* C, int B, int L, void* cat_bf16, void* stream);
+int tt_gather_cat_bwd(const float* dcat, const int32_t* last_idx, const int64_t* gender, const int64_t* country,
+                      int B, int L, float* dx, void* dx_bf16, float* dG, float* dC, void* stream);
+
+/* [audio | visual | text | tabular] -> bf16 [B, 4*m] (src/models/item_tower.py:147). */
+int tt_concat4_bf16(const float* audio, const float* visual, const float* text, const float* tabular, int B, int m,
+                    void* out_bf16, void* stream);
+
+/* BatchNorm1d + ReLU + Dropout on fp32 [B, C] -> bf16 (src/models/item_tower.py:124-126).
+ * training != 0: batch statistics, running stats / num_batches_tracked updated (momentum 0.1,
+ * unbiased variance); else running statistics. */
+typedef struct tt_bn_args {
+  const float* y;
+  int32_t B, C;
+  const float* w;
+  const float* b;
+  float* running_mean;
+  float* running_var;
+  int64_t* num_batches_tracked;
+  int32_t training;
+  float momentum, eps;
+  float drop_p;
+  uint64_t drop_seed;
+  const uint64_t* drop_seed_dev;
+  uint32_t drop_site;
+  float* save_mean;
+  float* save_rstd;
+  void* out_bf16;
+  /* backward */
+  const float* dout;
+  void* dy_bf16;
+  float* dgamma;
+  float* dbeta;
+  float* dy_colsum;
+} tt_bn_args;
+int tt_bn_relu_fwd(const tt_bn_args* args, void* stream);
+int tt_bn_relu_bwd(const tt_bn_args* args, void* stream);
+
+/* out[n] += sum_r x[r, n] for a bf16 [R, N] matrix (bias gradients). */
+int tt_colsum_bf16(const void* x_bf16, int R, int N, int ld, float* out, void* stream);
+
+/* Fused dense AdamW over a flat fp32 buffer (torch.optim.AdamW as used at src/train.py:302,
+ * 64-65): p,g,m,v [n]; *step_dev is the 1-based step count on the device; optionally writes a
+ * bf16 shadow of p[shadow_begin:shadow_end] and zeroes g. */
+int tt_adamw_step(float* p, float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
+                  float weight_decay, const int64_t* step_dev, void* shadow_bf16, int64_t shadow_begin,
+                  int64_t shadow_end, int zero_grad, void* stream);
+/* ++*step_dev; *seed_dev += golden-ratio increment (either may be NULL). */
+int tt_step_counters_advance(int64_t* step_dev, uint64_t* seed_dev, void* stream);
+
+/* ---- symmetric InfoNCE (src/models/two_tower.py:106-140) --------------------------------
+ * Row formulation: S [R, C] fp32 holds logits of R local rows against C (all-gathered)
+ * columns, the positive of row i sits at column pos0 + i.
+ * tt_infonce_rows : in place, S[i][j] = -1e4 where uid_rows[i] == uid_cols[j] and j != pos0+i
+ *                   (uid_* may be NULL: no masking); row_lse[i] = logsumexp(S[i,:]);
+ *                   pos_logit[i] = S[i][pos0+i].
+ * tt_infonce_grad : dS[i][j] = coef * (exp(S-row_lse[i]) + exp(S-col_lse[j]) - 2*[j==pos0+i]), bf16.
+ *                   col_lse[j] is the log-sum-exp of column j over ALL rows of all ranks, i.e. the
+ *                   row_lse of the transposed problem.
+ * tt_infonce_loss : loss = coef * sum_i (lse_a-pos_a + lse_b-pos_b)[i]   (coef = 0.5 / global batch)
+ */
+int tt_infonce_rows(float* S, int R, int C, int ld, const int64_t* uid_rows, const int64_t* uid_cols, int pos0,
+                    float* row_lse, float* pos_logit, void* stream);
+int tt_infonce_grad(const float* S, int R, int C, int ld, const float* row_lse, const float* col_lse, int pos0,
+                    float coef, void* dS_bf16, int ld_d, void* stream);
+int tt_infonce_loss(const float* lse_a, const float* pos_a, const float* lse_b, const float* pos_b, int R, float coef,
+                    float* loss, void* stream);
 
 #ifdef __cplusplus
 }

@@ -30,6 +30,7 @@ class GemmArgs(ctypes.Structure):
         ("relu", c_int32),
         ("drop_p", c_float),
         ("drop_seed", c_uint64),
+        ("drop_seed_dev", c_void_p),
         ("drop_site", c_uint32),
         ("gate", c_void_p),
         ("ld_gate", c_int32),
@@ -55,10 +56,10 @@ def _declare(l):
     l.tt_gemm_bf16.argtypes = [ctypes.POINTER(GemmArgs), c_void_p]
     l.tt_attn_causal_fwd.restype = c_int32
     l.tt_attn_causal_fwd.argtypes = [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_float,
-                                     c_uint64, c_uint32, c_void_p]
+                                     c_uint64, c_void_p, c_uint32, c_void_p]
     l.tt_attn_causal_bwd.restype = c_int32
     l.tt_attn_causal_bwd.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32,
-                                     c_int32, c_float, c_uint64, c_uint32, c_void_p]
+                                     c_int32, c_float, c_uint64, c_void_p, c_uint32, c_void_p]
 
 
 def lib():
@@ -75,7 +76,86 @@ def lib():
     return _lib
 
 
+#: number of kernels launched through the C ABI by this process (every launcher = 1 kernel)
+launch_count = 0
+
+
 def check(rc: int, what: str) -> None:
+    global launch_count
+    launch_count += 1
     if rc != 0:
         msg = lib().tt_last_error().decode("utf-8", "replace")
         raise TTError(f"{what} failed (code {rc}): {msg}")
+
+
+class ChainArgs(ctypes.Structure):
+    """Mirror of ``tt_chain_args``."""
+
+    _fields_ = [
+        ("x", c_void_p), ("rows", c_int32), ("width", c_int32),
+        ("ln_w", c_void_p), ("ln_b", c_void_p), ("ln_eps", c_float),
+        ("relu", c_int32),
+        ("drop_p", c_float), ("drop_seed", c_uint64), ("drop_seed_dev", c_void_p), ("drop_site", c_uint32),
+        ("l2norm", c_int32), ("l2_eps", c_float),
+        ("out_f32", c_void_p), ("out_bf16", c_void_p),
+        ("dout", c_void_p), ("resid", c_void_p), ("dx_f32", c_void_p), ("dx_bf16", c_void_p),
+        ("drop2_p", c_float), ("drop2_site", c_uint32),
+        ("dgamma", c_void_p), ("dbeta", c_void_p), ("dx_colsum", c_void_p),
+    ]
+
+
+class BnArgs(ctypes.Structure):
+    """Mirror of ``tt_bn_args``."""
+
+    _fields_ = [
+        ("y", c_void_p), ("B", c_int32), ("C", c_int32),
+        ("w", c_void_p), ("b", c_void_p),
+        ("running_mean", c_void_p), ("running_var", c_void_p), ("num_batches_tracked", c_void_p),
+        ("training", c_int32), ("momentum", c_float), ("eps", c_float),
+        ("drop_p", c_float), ("drop_seed", c_uint64), ("drop_seed_dev", c_void_p), ("drop_site", c_uint32),
+        ("save_mean", c_void_p), ("save_rstd", c_void_p), ("out_bf16", c_void_p),
+        ("dout", c_void_p), ("dy_bf16", c_void_p), ("dgamma", c_void_p), ("dbeta", c_void_p),
+        ("dy_colsum", c_void_p),
+    ]
+
+
+_I64 = ctypes.c_int64
+_SIGNATURES = {
+    "tt_cast_bf16": [c_void_p, c_void_p, _I64, c_void_p],
+    "tt_last_index": [c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p],
+    "tt_embed_ln_fwd": [c_void_p] * 7 + [c_int32, c_int32, c_float, c_uint64, c_void_p, c_uint32,
+                                         c_void_p, c_void_p, c_void_p],
+    "tt_embed_ln_bwd": [c_void_p] * 6 + [c_int32, c_int32, c_float, c_uint64, c_void_p, c_uint32,
+                                         c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
+    "tt_chain_fwd": [ctypes.POINTER(ChainArgs), c_void_p],
+    "tt_chain_bwd": [ctypes.POINTER(ChainArgs), c_void_p],
+    "tt_gather_cat_fwd": [c_void_p] * 6 + [c_int32, c_int32, c_void_p, c_void_p],
+    "tt_gather_cat_bwd": [c_void_p] * 4 + [c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
+    "tt_concat4_bf16": [c_void_p] * 4 + [c_int32, c_int32, c_void_p, c_void_p],
+    "tt_bn_relu_fwd": [ctypes.POINTER(BnArgs), c_void_p],
+    "tt_bn_relu_bwd": [ctypes.POINTER(BnArgs), c_void_p],
+    "tt_colsum_bf16": [c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p],
+    "tt_adamw_step": [c_void_p] * 4 + [_I64, c_float, c_float, c_float, c_float, c_float, c_void_p, c_void_p,
+                                       _I64, _I64, c_int32, c_void_p],
+    "tt_step_counters_advance": [c_void_p, c_void_p, c_void_p],
+    "tt_infonce_rows": [c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_int32, c_void_p, c_void_p,
+                        c_void_p],
+    "tt_infonce_grad": [c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_int32, c_float, c_void_p,
+                        c_int32, c_void_p],
+    "tt_infonce_loss": [c_void_p] * 4 + [c_int32, c_float, c_void_p, c_void_p],
+}
+
+_declare_base = _declare
+
+
+def _declare(l):  # noqa: F811 - extends the base declarations with the row-wise / loss entry points
+    _declare_base(l)
+    for name, argtypes in _SIGNATURES.items():
+        fn = getattr(l, name)
+        fn.restype = c_int32
+        fn.argtypes = argtypes
+
+
+#: every symbol include/tt_b200.h declares (checked by tests/test_abi.py)
+EXPORTED_SYMBOLS = ["tt_last_error", "tt_version", "tt_num_sms", "tt_gemm_bf16", "tt_attn_causal_fwd",
+                    "tt_attn_causal_bwd", *sorted(_SIGNATURES)]

@@ -32,6 +32,7 @@ struct AttnParams {
   uint32_t drop_thresh;
   float drop_scale;
   uint64_t drop_seed;
+  const uint64_t* drop_seed_dev;
   uint32_t drop_site;
   __nv_bfloat16* ctx;  // [T, H*64]
   float* lse;          // [B, H, L]
@@ -143,6 +144,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
   }
   const float c1 = p.scale * kLog2e;
   const float mc = m * c1;
+  const uint64_t seed = p.drop_seed + ((p.drop_thresh && p.drop_seed_dev) ? *p.drop_seed_dev : 0ull);
 
   // ---- pass B: P_j -> smem (bf16, swizzled), O += P_j V_j ------------------------------
   float l = 0.f;
@@ -172,7 +174,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
           l += e;
           if (p.drop_thresh) {
             const uint64_t idx = (static_cast<uint64_t>(bh) * p.L + q_pos) * p.L + (kv0 + t);
-            e = drop_keep(p.drop_seed, p.drop_site, idx, p.drop_thresh) ? e * p.drop_scale : 0.f;
+            e = drop_keep(seed, p.drop_site, idx, p.drop_thresh) ? e * p.drop_scale : 0.f;
           }
           pv[t] = e;
         }
@@ -262,6 +264,7 @@ struct AttnBwdParams {
   uint32_t drop_thresh;
   float drop_scale;
   uint64_t drop_seed;
+  const uint64_t* drop_seed_dev;
   uint32_t drop_site;
   const __nv_bfloat16* ctx;   // O  [T, H*64]
   const __nv_bfloat16* dctx;  // dO [T, H*64]
@@ -354,6 +357,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
   __syncthreads();
 
   const float c1 = p.scale * kLog2e;
+  const uint64_t seed = p.drop_seed + ((p.drop_thresh && p.drop_seed_dev) ? *p.drop_seed_dev : 0ull);
   const uint32_t idesc_s = umma_idesc_bf16(kTile, kTile, false, false);    // Q K^T, dO V^T
   const uint32_t idesc_t = umma_idesc_bf16(kTile, kDh, true, true);        // X^T Y (dV, dK)
   const uint32_t idesc_q = umma_idesc_bf16(kTile, kDh, false, true);       // dS K
@@ -413,7 +417,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
             float pdrop = pr;
             if (p.drop_thresh) {
               const uint64_t idx = (static_cast<uint64_t>(bh) * p.L + q_pos) * p.L + (kv0 + t);
-              const bool keep = drop_keep(p.drop_seed, p.drop_site, idx, p.drop_thresh);
+              const bool keep = drop_keep(seed, p.drop_site, idx, p.drop_thresh);
               pdrop = keep ? pr * p.drop_scale : 0.f;
               dp = keep ? dp * p.drop_scale : 0.f;
             }
@@ -561,7 +565,8 @@ static uint32_t drop_threshold(float p) {
 }  // namespace tt
 
 extern "C" int tt_attn_causal_fwd(const void* qkv, void* ctx, float* lse, int B, int L, int H, float drop_p,
-                                  uint64_t drop_seed, uint32_t drop_site, void* stream_) {
+                                  uint64_t drop_seed, const uint64_t* drop_seed_dev, uint32_t drop_site,
+                                  void* stream_) {
   using namespace tt;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   TT_REQUIRE(qkv && ctx, "tt_attn_causal_fwd: null pointer");
@@ -576,6 +581,7 @@ extern "C" int tt_attn_causal_fwd(const void* qkv, void* ctx, float* lse, int B,
   p.drop_thresh = drop_threshold(drop_p);
   p.drop_scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
   p.drop_seed = drop_seed;
+  p.drop_seed_dev = drop_seed_dev;
   p.drop_site = drop_site;
   p.ctx = static_cast<__nv_bfloat16*>(ctx);
   p.lse = lse;
@@ -595,8 +601,8 @@ extern "C" int tt_attn_causal_fwd(const void* qkv, void* ctx, float* lse, int B,
 }
 
 extern "C" int tt_attn_causal_bwd(const void* qkv, const void* ctx, const void* dctx, const float* lse, void* dqkv,
-                                  int B, int L, int H, float drop_p, uint64_t drop_seed, uint32_t drop_site,
-                                  void* stream_) {
+                                  int B, int L, int H, float drop_p, uint64_t drop_seed,
+                                  const uint64_t* drop_seed_dev, uint32_t drop_site, void* stream_) {
   using namespace tt;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   TT_REQUIRE(qkv && ctx && dctx && lse && dqkv, "tt_attn_causal_bwd: null pointer");
@@ -610,6 +616,7 @@ extern "C" int tt_attn_causal_bwd(const void* qkv, const void* ctx, const void* 
   p.drop_thresh = drop_threshold(drop_p);
   p.drop_scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
   p.drop_seed = drop_seed;
+  p.drop_seed_dev = drop_seed_dev;
   p.drop_site = drop_site;
   p.ctx = static_cast<const __nv_bfloat16*>(ctx);
   p.dctx = static_cast<const __nv_bfloat16*>(dctx);

@@ -25,6 +25,7 @@ struct GemmParams {
   uint32_t drop_thresh;
   float drop_scale;
   uint64_t drop_seed;
+  const uint64_t* drop_seed_dev;
   uint32_t drop_site;
   const __nv_bfloat16* gate;
   int ld_gate;
@@ -44,7 +45,7 @@ static constexpr uint32_t kABytes = kBlockM * kBlockK * 2;  // 16 KB
 static constexpr int kGemmThreads = 256;
 
 __device__ __forceinline__ void gemm_epilogue_chunk(const GemmParams& p, const uint32_t (&r)[32],
-                                                    int row, int col0) {
+                                                    int row, int col0, uint64_t seed) {
   const int ncols = min(32, p.N - col0);
   float v[32];
 #pragma unroll
@@ -66,7 +67,7 @@ __device__ __forceinline__ void gemm_epilogue_chunk(const GemmParams& p, const u
       const uint64_t base = static_cast<uint64_t>(row) * p.N + col0;
 #pragma unroll
       for (int j = 0; j < 32; ++j)
-        v[j] = drop_keep(p.drop_seed, p.drop_site, base + j, p.drop_thresh) ? v[j] * p.drop_scale
+        v[j] = drop_keep(seed, p.drop_site, base + j, p.drop_thresh) ? v[j] * p.drop_scale
                                                                             : 0.f;
     }
     if (p.gate) {
@@ -125,7 +126,7 @@ __device__ __forceinline__ void gemm_epilogue_chunk(const GemmParams& p, const u
         if (p.bias) x += __ldg(p.bias + col);
         if (p.relu) x = fmaxf(x, 0.f);
         if (p.drop_thresh)
-          x = drop_keep(p.drop_seed, p.drop_site, static_cast<uint64_t>(row) * p.N + col, p.drop_thresh)
+          x = drop_keep(seed, p.drop_site, static_cast<uint64_t>(row) * p.N + col, p.drop_thresh)
                   ? x * p.drop_scale
                   : 0.f;
         if (p.gate) {
@@ -258,6 +259,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else if (warp >= 4) {
     const int ew = warp - 4;  // == warp % 4: the TMEM lane quarter this warp may read
+    const uint64_t seed = p.drop_seed + ((p.drop_thresh && p.drop_seed_dev) ? *p.drop_seed_dev : 0ull);
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
@@ -274,7 +276,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         tmem_ld32(t_base + static_cast<uint32_t>(c * 32), r);
         tmem_ld_wait();
         const int col0 = n_blk * block_n + c * 32;
-        if (row < p.M && col0 < p.N) gemm_epilogue_chunk(p, r, row, col0);
+        if (row < p.M && col0 < p.N) gemm_epilogue_chunk(p, r, row, col0, seed);
       }
       tc_fence_before();
       __syncwarp();
@@ -320,8 +322,11 @@ extern "C" int tt_gemm_bf16(const tt_gemm_args* a, void* stream_) {
              a->N, a->K);
   TT_REQUIRE(a->out_f32 || a->out_bf16, "tt_gemm_bf16: no output");
   TT_REQUIRE(a->lda % 8 == 0 && a->ldb % 8 == 0, "tt_gemm_bf16: lda/ldb must be multiples of 8");
-  TT_REQUIRE(!a->a_mn || a->M % 64 == 0, "tt_gemm_bf16: MN-major A needs M %% 64 == 0 (M=%d)", a->M);
-  TT_REQUIRE(!a->b_mn || a->N % 64 == 0, "tt_gemm_bf16: MN-major B needs N %% 64 == 0 (N=%d)", a->N);
+  // MN-major operands are fetched in 64-wide chunks: a ragged last chunk reads up to 63 elements
+  // past M (resp. N) inside each K row (results there are never stored), so the dimension must be
+  // a multiple of 8 and the buffer readable up to the next multiple of 64 on its last row.
+  TT_REQUIRE(!a->a_mn || a->M % 8 == 0, "tt_gemm_bf16: MN-major A needs M %% 8 == 0 (M=%d)", a->M);
+  TT_REQUIRE(!a->b_mn || a->N % 8 == 0, "tt_gemm_bf16: MN-major B needs N %% 8 == 0 (N=%d)", a->N);
   TT_REQUIRE(!a->out_f32 || a->ld_f32 % 4 == 0, "tt_gemm_bf16: ld_f32 must be a multiple of 4");
   TT_REQUIRE(!a->out_bf16 || a->ld_bf16 % 8 == 0, "tt_gemm_bf16: ld_bf16 must be a multiple of 8");
   TT_REQUIRE(!a->residual || a->ld_res % 4 == 0, "tt_gemm_bf16: ld_res must be a multiple of 4");
@@ -372,6 +377,7 @@ extern "C" int tt_gemm_bf16(const tt_gemm_args* a, void* stream_) {
     p.drop_scale = 1.f / (1.f - a->drop_p);
   }
   p.drop_seed = a->drop_seed;
+  p.drop_seed_dev = a->drop_seed_dev;
   p.drop_site = a->drop_site;
   p.gate = static_cast<const __nv_bfloat16*>(a->gate);
   p.ld_gate = a->ld_gate;
@@ -387,7 +393,7 @@ extern "C" int tt_gemm_bf16(const tt_gemm_args* a, void* stream_) {
   CUtensorMap tmA, tmB;
   int rc;
   if (a->a_mn) {
-    uint64_t dims[3] = {64, static_cast<uint64_t>(a->K), static_cast<uint64_t>(a->M / 64)};
+    uint64_t dims[3] = {64, static_cast<uint64_t>(a->K), static_cast<uint64_t>((a->M + 63) / 64)};
     uint64_t str[2] = {static_cast<uint64_t>(a->lda) * 2, 128};
     uint32_t box[3] = {64, kBlockK, kBlockM / 64};
     rc = make_tmap_bf16(&tmA, a->A, 3, dims, str, box);
@@ -399,7 +405,7 @@ extern "C" int tt_gemm_bf16(const tt_gemm_args* a, void* stream_) {
   }
   if (rc) return rc;
   if (a->b_mn) {
-    uint64_t dims[3] = {64, static_cast<uint64_t>(a->K), static_cast<uint64_t>(a->N / 64)};
+    uint64_t dims[3] = {64, static_cast<uint64_t>(a->K), static_cast<uint64_t>((a->N + 63) / 64)};
     uint64_t str[2] = {static_cast<uint64_t>(a->ldb) * 2, 128};
     uint32_t box[3] = {64, kBlockK, static_cast<uint32_t>(bn / 64)};
     rc = make_tmap_bf16(&tmB, a->B, 3, dims, str, box);

@@ -1,0 +1,427 @@
+"""Kernel sequencing for the two-tower hot path: forward, backward and the fused AdamW step.
+
+The engine owns
+  * one flat fp32 parameter buffer (reference state-dict tensors are views into it), a flat
+    fp32 gradient buffer of the same layout, AdamW moments, and a bf16 shadow of the dense
+    region (tensor-core operands);
+  * per-(batch, seq_len) activation workspaces, allocated once and reused (CUDA-graph safe);
+and launches the C-ABI kernels of libtt_b200.so in order on the current stream. There is no
+autograd here: the backward pass is written out by hand, mirroring the forward.
+
+Reference call sites: SequentialUserEncoder.forward (src/models/user_tower.py:73-144),
+MultimodalItemEncoder.fusion_layer (src/models/item_tower.py:121-129,147-150),
+TwoTowerModel.forward (src/models/two_tower.py:68-142), the step body of train_one_epoch
+(src/train.py:48-67).
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Tuple
+
+import torch
+
+from . import ops
+from .synthetic import TwoTowerConfig
+
+_ALIGN = 64  # elements; keeps every bf16 view 128-byte aligned (TMA needs 16)
+
+# dropout sites (hash domain separation)
+SITE_EMB = 1
+SITE_ITEM = 60
+
+
+def _site(layer: int, which: int) -> int:
+    """which: 0 attention probabilities, 1 after out_proj, 2 inside FFN, 3 after linear2."""
+    return 10 + 4 * layer + which
+
+
+def param_shapes(cfg: TwoTowerConfig) -> List[Tuple[str, Tuple[int, ...]]]:
+    """(name, shape) of every trainable tensor, reference key names.
+    Order = flat-buffer order: ID table, small embeddings, then the dense region."""
+    D, FF, H = cfg.embedding_dim, cfg.ff_dim, cfg.fusion_hidden
+    ut = "user_tower."
+    out = [
+        (ut + "item_embedding.weight", (cfg.vocab_size, D)),
+        (ut + "position_embedding.weight", (cfg.max_seq_len, D)),
+        (ut + "gender_embedding.weight", (cfg.num_genders, 16)),
+        (ut + "country_embedding.weight", (cfg.num_countries, 32)),
+    ]
+    for l in range(cfg.num_layers):
+        p = f"{ut}transformer_encoder.layers.{l}."
+        out += [
+            (p + "self_attn.in_proj_weight", (3 * D, D)), (p + "self_attn.in_proj_bias", (3 * D,)),
+            (p + "self_attn.out_proj.weight", (D, D)), (p + "self_attn.out_proj.bias", (D,)),
+            (p + "linear1.weight", (FF, D)), (p + "linear1.bias", (FF,)),
+            (p + "linear2.weight", (D, FF)), (p + "linear2.bias", (D,)),
+            (p + "norm1.weight", (D,)), (p + "norm1.bias", (D,)),
+            (p + "norm2.weight", (D,)), (p + "norm2.bias", (D,)),
+        ]
+    out += [
+        (ut + "layer_norm.weight", (D,)), (ut + "layer_norm.bias", (D,)),
+        (ut + "fusion_layer.0.weight", (D, D + 48)), (ut + "fusion_layer.0.bias", (D,)),
+        (ut + "fusion_layer.1.weight", (D,)), (ut + "fusion_layer.1.bias", (D,)),
+        (ut + "fusion_layer.3.weight", (D, D)), (ut + "fusion_layer.3.bias", (D,)),
+    ]
+    it = "item_tower.fusion_layer."
+    out += [
+        (it + "0.weight", (H, 4 * cfg.modality_dim)), (it + "0.bias", (H,)),
+        (it + "1.weight", (H,)), (it + "1.bias", (H,)),
+        (it + "4.weight", (D, H)), (it + "4.bias", (D,)),
+        (it + "5.weight", (D,)), (it + "5.bias", (D,)),
+    ]
+    return out
+
+
+_NUM_SPARSE = 4  # table, positions, gender, country come before the dense region
+
+
+class TwoTowerEngine:
+    def __init__(self, cfg: TwoTowerConfig, device: Optional[torch.device] = None):
+        assert cfg.embedding_dim == 256 and cfg.num_heads == 4, \
+            "the sm_100a kernels are specialised for d_model=256, 4 heads of 64 (the reference's configuration)"
+        assert cfg.fusion_hidden == 512 and 4 * cfg.modality_dim == 512
+        self.cfg = cfg
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else device
+        shapes = param_shapes(cfg)
+        self.layout: Dict[str, Tuple[int, Tuple[int, ...]]] = {}
+        off = 0
+        for i, (name, shape) in enumerate(shapes):
+            if i == _NUM_SPARSE:
+                self.dense_begin = off
+            n = 1
+            for s in shape:
+                n *= s
+            self.layout[name] = (off, shape)
+            off += (n + _ALIGN - 1) // _ALIGN * _ALIGN
+        off += _ALIGN  # tail padding: ragged MN-major chunks may read up to 63 elements past a tensor
+        self.numel = off
+        dev = self.device
+        self.flat = torch.zeros(off, device=dev)
+        self.grad = torch.zeros(off, device=dev)
+        self.exp_avg: Optional[torch.Tensor] = None
+        self.exp_avg_sq: Optional[torch.Tensor] = None
+        self.shadow = torch.zeros(off - self.dense_begin, device=dev, dtype=torch.bfloat16)
+        self.p: Dict[str, torch.Tensor] = {}
+        self.g: Dict[str, torch.Tensor] = {}
+        self.w: Dict[str, torch.Tensor] = {}   # bf16 shadows (dense region only)
+        for name, (o, shape) in self.layout.items():
+            n = 1
+            for s in shape:
+                n *= s
+            self.p[name] = self.flat[o:o + n].view(shape)
+            self.g[name] = self.grad[o:o + n].view(shape)
+            if o >= self.dense_begin:
+                so = o - self.dense_begin
+                self.w[name] = self.shadow[so:so + n].view(shape)
+        H = cfg.fusion_hidden
+        self.bn_running_mean = torch.zeros(H, device=dev)
+        self.bn_running_var = torch.ones(H, device=dev)
+        self.bn_num_batches = torch.zeros((), device=dev, dtype=torch.long)
+        self.step_dev = torch.zeros((), device=dev, dtype=torch.long)     # AdamW step count
+        self.seed_dev = torch.zeros((), device=dev, dtype=torch.long)     # dropout seed offset
+        self.base_seed = 0x5EED
+        self._ws: Dict[Tuple[int, int], Dict[str, torch.Tensor]] = {}
+        self.shadow_valid = False
+
+    # ------------------------------------------------------------------ parameters
+    def load_state_dict(self, sd: Dict[str, torch.Tensor]) -> None:
+        """Copy a reference-format state dict (src/train.py:327-330; optional 'module.' prefix,
+        encoder keys ignored) into the flat buffer."""
+        sd = {(k[7:] if k.startswith("module.") else k): v for k, v in sd.items()}
+        for name, t in self.p.items():
+            t.copy_(sd[name].to(device=self.device, dtype=torch.float32))
+        it = "item_tower.fusion_layer.1."
+        if it + "running_mean" in sd:
+            self.bn_running_mean.copy_(sd[it + "running_mean"])
+            self.bn_running_var.copy_(sd[it + "running_var"])
+            self.bn_num_batches.copy_(sd[it + "num_batches_tracked"])
+        self.shadow_valid = False
+
+    def state_dict(self) -> Dict[str, torch.Tensor]:
+        out = {k: v.detach().clone() for k, v in self.p.items()}
+        it = "item_tower.fusion_layer.1."
+        out[it + "running_mean"] = self.bn_running_mean.clone()
+        out[it + "running_var"] = self.bn_running_var.clone()
+        out[it + "num_batches_tracked"] = self.bn_num_batches.clone()
+        return out
+
+    def refresh_shadow(self) -> None:
+        ops.cast_bf16(self.flat[self.dense_begin:], self.shadow)
+        self.shadow_valid = True
+
+    # ------------------------------------------------------------------ workspaces
+    def workspace(self, B: int, L: int) -> Dict[str, torch.Tensor]:
+        key = (B, L)
+        if key in self._ws:
+            return self._ws[key]
+        cfg, dev = self.cfg, self.device
+        D, FF, NL, Hh = cfg.embedding_dim, cfg.ff_dim, cfg.num_layers, cfg.num_heads
+        T = B * L
+        f32 = dict(device=dev, dtype=torch.float32)
+        bf = dict(device=dev, dtype=torch.bfloat16)
+        ws: Dict[str, torch.Tensor] = {}
+        ws["last_idx"] = torch.zeros(B, device=dev, dtype=torch.int32)
+        ws["x_in0"] = torch.empty(T, D, **f32)
+        for l in range(NL):
+            ws[f"h1_{l}"] = torch.empty(T, D, **bf)
+            ws[f"qkv_{l}"] = torch.empty(T, 3 * D, **bf)
+            ws[f"ctx_{l}"] = torch.empty(T, D, **bf)
+            ws[f"lse_{l}"] = torch.empty(B, Hh, L, **f32)
+            ws[f"xmid_{l}"] = torch.empty(T, D, **f32)
+            ws[f"h2_{l}"] = torch.empty(T, D, **bf)
+            ws[f"f_{l}"] = torch.empty(T, FF, **bf)
+            ws[f"xout_{l}"] = torch.empty(T, D, **f32)
+        ws["cat"] = torch.zeros(B + 1, D + 48, **bf)[:B]          # +1 row: ragged MN-major reads
+        ws["z1"] = torch.empty(B, D, **f32)
+        ws["a1"] = torch.empty(B, D, **bf)
+        ws["u"] = torch.empty(B, D, **f32)
+        ws["un"] = torch.empty(B, D, **f32)
+        ws["un_bf"] = torch.empty(B, D, **bf)
+        ws["xi"] = torch.empty(B, 4 * cfg.modality_dim, **bf)
+        ws["y1"] = torch.empty(B, cfg.fusion_hidden, **f32)
+        ws["bn_mean"] = torch.empty(cfg.fusion_hidden, **f32)
+        ws["bn_rstd"] = torch.empty(cfg.fusion_hidden, **f32)
+        ws["a"] = torch.empty(B, cfg.fusion_hidden, **bf)
+        ws["y2"] = torch.empty(B, D, **f32)
+        ws["in"] = torch.empty(B, D, **f32)
+        ws["in_bf"] = torch.empty(B, D, **bf)
+        # loss
+        ws["S"] = torch.empty(B, B, **f32)
+        ws["S2"] = torch.empty(B, B, **f32)
+        for k in ("lse_r", "pos_r", "lse_c", "pos_c"):
+            ws[k] = torch.empty(B, **f32)
+        ws["loss"] = torch.zeros((), **f32)
+        # backward
+        ws["dS"] = torch.empty(B, B, **bf)
+        ws["dS2"] = torch.empty(B, B, **bf)
+        ws["dun"] = torch.empty(B, D, **f32)
+        ws["din"] = torch.empty(B, D, **f32)
+        ws["du_bf"] = torch.empty(B, D, **bf)
+        ws["da1"] = torch.empty(B, D, **f32)
+        ws["dz1_bf"] = torch.empty(B, D, **bf)
+        ws["dcat"] = torch.empty(B, D + 48, **f32)
+        ws["dy2i_bf"] = torch.empty(B, D, **bf)
+        ws["da"] = torch.empty(B, cfg.fusion_hidden, **f32)
+        ws["dy1i_bf"] = torch.empty(B, cfg.fusion_hidden, **bf)
+        ws["dx_a"] = torch.empty(T, D, **f32)      # gradient of the residual stream (ping)
+        ws["dx_b"] = torch.empty(T, D, **f32)      # (pong)
+        ws["dy_bf"] = torch.empty(T, D, **bf)      # bf16 grad fed to the dgrad/wgrad GEMMs
+        ws["dh"] = torch.empty(T, D, **f32)        # grad w.r.t. a LayerNorm output
+        ws["dpre"] = torch.empty(T, FF, **bf)
+        ws["dctx"] = torch.empty(T, D, **bf)
+        ws["dqkv"] = torch.empty(T, 3 * D, **bf)
+        self._ws[key] = ws
+        return ws
+
+    # ------------------------------------------------------------------ helpers
+    def _gemm(self, *a, **kw):
+        ops.gemm(*a, **kw)
+
+    def _lp(self, l: int, name: str) -> str:
+        return f"user_tower.transformer_encoder.layers.{l}.{name}"
+
+    def _drop(self, training: bool) -> float:
+        return self.cfg.dropout if training else 0.0
+
+    # ------------------------------------------------------------------ forward pieces
+    def user_forward(self, ws, ids, mask, gender, country, training: bool) -> torch.Tensor:
+        """SASRec user tower -> L2-normalised user embedding (fp32 [B,256])."""
+        cfg, p, w = self.cfg, self.p, self.w
+        B, L = ids.shape
+        dp = self._drop(training)
+        seed, sdev = self.base_seed, self.seed_dev
+        ut = "user_tower."
+        ops.last_index(ids, mask, ws["last_idx"])
+        ops.embed_ln_fwd(ids.view(-1), p[ut + "item_embedding.weight"], p[ut + "position_embedding.weight"],
+                         p[ut + "layer_norm.weight"], p[ut + "layer_norm.bias"],
+                         p[self._lp(0, "norm1.weight")], p[self._lp(0, "norm1.bias")], B, L,
+                         ws["x_in0"], ws["h1_0"], drop_p=dp, seed=seed, seed_dev=sdev, site=SITE_EMB)
+        x_in = ws["x_in0"]
+        for l in range(cfg.num_layers):
+            self._gemm(ws[f"h1_{l}"], w[self._lp(l, "self_attn.in_proj_weight")],
+                       bias=p[self._lp(l, "self_attn.in_proj_bias")], out_bf16=ws[f"qkv_{l}"])
+            ops.attn_fwd(ws[f"qkv_{l}"], ws[f"ctx_{l}"], ws[f"lse_{l}"], B, L, cfg.num_heads, drop_p=dp,
+                         drop_seed=seed, drop_seed_dev=sdev, drop_site=_site(l, 0))
+            self._gemm(ws[f"ctx_{l}"], w[self._lp(l, "self_attn.out_proj.weight")],
+                       bias=p[self._lp(l, "self_attn.out_proj.bias")], drop_p=dp, drop_seed=seed,
+                       drop_seed_dev=sdev, drop_site=_site(l, 1), residual=x_in, out_f32=ws[f"xmid_{l}"])
+            ops.chain_fwd(ws[f"xmid_{l}"], ln=(p[self._lp(l, "norm2.weight")], p[self._lp(l, "norm2.bias")]),
+                          out_bf16=ws[f"h2_{l}"])
+            self._gemm(ws[f"h2_{l}"], w[self._lp(l, "linear1.weight")], bias=p[self._lp(l, "linear1.bias")],
+                       relu=True, drop_p=dp, drop_seed=seed, drop_seed_dev=sdev, drop_site=_site(l, 2),
+                       out_bf16=ws[f"f_{l}"])
+            self._gemm(ws[f"f_{l}"], w[self._lp(l, "linear2.weight")], bias=p[self._lp(l, "linear2.bias")],
+                       drop_p=dp, drop_seed=seed, drop_seed_dev=sdev, drop_site=_site(l, 3),
+                       residual=ws[f"xmid_{l}"], out_f32=ws[f"xout_{l}"])
+            x_in = ws[f"xout_{l}"]
+            if l + 1 < cfg.num_layers:
+                ops.chain_fwd(x_in, ln=(p[self._lp(l + 1, "norm1.weight")], p[self._lp(l + 1, "norm1.bias")]),
+                              out_bf16=ws[f"h1_{l + 1}"])
+        ops.gather_cat_fwd(x_in, ws["last_idx"], gender, country, p[ut + "gender_embedding.weight"],
+                           p[ut + "country_embedding.weight"], B, L, ws["cat"])
+        self._gemm(ws["cat"], w[ut + "fusion_layer.0.weight"], bias=p[ut + "fusion_layer.0.bias"], out_f32=ws["z1"])
+        ops.chain_fwd(ws["z1"], ln=(p[ut + "fusion_layer.1.weight"], p[ut + "fusion_layer.1.bias"]), relu=True,
+                      out_bf16=ws["a1"])
+        self._gemm(ws["a1"], w[ut + "fusion_layer.3.weight"], bias=p[ut + "fusion_layer.3.bias"], out_f32=ws["u"])
+        ops.chain_fwd(ws["u"], l2norm=True, out_f32=ws["un"], out_bf16=ws["un_bf"])
+        return ws["un"]
+
+    def item_forward(self, ws, audio, visual, text, tabular, training: bool) -> torch.Tensor:
+        """Late-fusion item tower on precomputed modality embeddings -> normalised item embedding."""
+        p, w = self.p, self.w
+        it = "item_tower.fusion_layer."
+        ops.concat4_bf16(audio, visual, text, tabular, ws["xi"])
+        self._gemm(ws["xi"], w[it + "0.weight"], bias=p[it + "0.bias"], out_f32=ws["y1"])
+        ops.bn_relu_fwd(ws["y1"], p[it + "1.weight"], p[it + "1.bias"], self.bn_running_mean, self.bn_running_var,
+                        self.bn_num_batches, training=training, drop_p=(0.1 if training and self.cfg.dropout > 0 else 0.0),
+                        seed=self.base_seed, seed_dev=self.seed_dev, site=SITE_ITEM, save_mean=ws["bn_mean"],
+                        save_rstd=ws["bn_rstd"], out_bf16=ws["a"])
+        self._gemm(ws["a"], w[it + "4.weight"], bias=p[it + "4.bias"], out_f32=ws["y2"])
+        ops.chain_fwd(ws["y2"], ln=(p[it + "5.weight"], p[it + "5.bias"]), l2norm=True, out_f32=ws["in"],
+                      out_bf16=ws["in_bf"])
+        return ws["in"]
+
+    def loss_forward(self, ws, user_idx: Optional[torch.Tensor]) -> torch.Tensor:
+        B = ws["un"].shape[0]
+        inv_t = 1.0 / self.cfg.temperature
+        self._gemm(ws["un_bf"], ws["in_bf"], alpha=inv_t, out_f32=ws["S"])
+        self._gemm(ws["in_bf"], ws["un_bf"], alpha=inv_t, out_f32=ws["S2"])
+        ops.infonce_rows(ws["S"], user_idx, user_idx, 0, ws["lse_r"], ws["pos_r"])
+        ops.infonce_rows(ws["S2"], user_idx, user_idx, 0, ws["lse_c"], ws["pos_c"])
+        ops.infonce_loss(ws["lse_r"], ws["pos_r"], ws["lse_c"], ws["pos_c"], 0.5 / B, ws["loss"])
+        return ws["loss"]
+
+    def forward(self, batch: Dict[str, torch.Tensor], training: bool = True):
+        """TwoTowerModel.forward (src/models/two_tower.py:68-142) ->
+        (loss, logits, user_emb, item_emb); tensors are workspace views valid until the next call."""
+        ids = batch["history_ids"]
+        B, L = ids.shape
+        ws = self.workspace(B, L)
+        if not self.shadow_valid:
+            self.refresh_shadow()
+        self.user_forward(ws, ids, batch.get("history_mask"), batch["user_gender"], batch["user_country"], training)
+        self.item_forward(ws, batch["target_audio"], batch["target_image"], batch["target_input_ids"],
+                          batch["target_tabular"], training)
+        self.loss_forward(ws, batch.get("user_idx"))
+        self._last = (ws, batch, training)
+        return ws["loss"], ws["S"], ws["un"], ws["in"]
+
+    # ------------------------------------------------------------------ backward
+    def backward(self, loss_scale: float = 1.0) -> None:
+        """Accumulates d(loss_scale * loss)/d(param) into self.grad (self.g views)."""
+        ws, batch, training = self._last
+        cfg, p, w, g = self.cfg, self.p, self.w, self.g
+        ids = batch["history_ids"]
+        B, L = ids.shape
+        T, D = B * L, cfg.embedding_dim
+        dp = self._drop(training)
+        seed, sdev = self.base_seed, self.seed_dev
+        inv_t = 1.0 / cfg.temperature
+        ut, it = "user_tower.", "item_tower.fusion_layer."
+        gemm = self._gemm
+
+        # ---- InfoNCE -> d(normalised embeddings)
+        coef = 0.5 / B * loss_scale
+        ops.infonce_grad(ws["S"], ws["lse_r"], ws["lse_c"], 0, coef, ws["dS"])
+        ops.infonce_grad(ws["S2"], ws["lse_c"], ws["lse_r"], 0, coef, ws["dS2"])
+        gemm(ws["dS"], ws["in_bf"], b_mn=True, alpha=inv_t, out_f32=ws["dun"])
+        gemm(ws["dS2"], ws["un_bf"], b_mn=True, alpha=inv_t, out_f32=ws["din"])
+
+        # ---- item tower
+        ops.chain_bwd(ws["y2"], ln=(p[it + "5.weight"], p[it + "5.bias"]), l2norm=True, dout=ws["din"],
+                      dx_bf16=ws["dy2i_bf"], dgamma=g[it + "5.weight"], dbeta=g[it + "5.bias"],
+                      dx_colsum=g[it + "4.bias"])
+        gemm(ws["dy2i_bf"], ws["a"], a_mn=True, b_mn=True, out_f32=g[it + "4.weight"], accumulate=True)
+        gemm(ws["dy2i_bf"], w[it + "4.weight"], b_mn=True, out_f32=ws["da"])
+        ops.bn_relu_bwd(ws["y1"], p[it + "1.weight"], p[it + "1.bias"], self.bn_running_mean, self.bn_running_var,
+                        None, training=training, drop_p=(0.1 if training and cfg.dropout > 0 else 0.0),
+                        seed=seed, seed_dev=sdev, site=SITE_ITEM, save_mean=ws["bn_mean"], save_rstd=ws["bn_rstd"],
+                        dout=ws["da"], dy_bf16=ws["dy1i_bf"], dgamma=g[it + "1.weight"], dbeta=g[it + "1.bias"],
+                        dy_colsum=g[it + "0.bias"])
+        gemm(ws["dy1i_bf"], ws["xi"], a_mn=True, b_mn=True, out_f32=g[it + "0.weight"], accumulate=True)
+
+        # ---- user head
+        ops.chain_bwd(ws["u"], l2norm=True, dout=ws["dun"], dx_bf16=ws["du_bf"],
+                      dx_colsum=g[ut + "fusion_layer.3.bias"])
+        gemm(ws["du_bf"], ws["a1"], a_mn=True, b_mn=True, out_f32=g[ut + "fusion_layer.3.weight"], accumulate=True)
+        gemm(ws["du_bf"], w[ut + "fusion_layer.3.weight"], b_mn=True, out_f32=ws["da1"])
+        ops.chain_bwd(ws["z1"], ln=(p[ut + "fusion_layer.1.weight"], p[ut + "fusion_layer.1.bias"]), relu=True,
+                      dout=ws["da1"], dx_bf16=ws["dz1_bf"], dgamma=g[ut + "fusion_layer.1.weight"],
+                      dbeta=g[ut + "fusion_layer.1.bias"], dx_colsum=g[ut + "fusion_layer.0.bias"])
+        gemm(ws["dz1_bf"], ws["cat"], a_mn=True, b_mn=True, out_f32=g[ut + "fusion_layer.0.weight"], accumulate=True)
+        gemm(ws["dz1_bf"], w[ut + "fusion_layer.0.weight"], b_mn=True, out_f32=ws["dcat"])
+        dx, dx_other = ws["dx_a"], ws["dx_b"]
+        dx.zero_()
+        ops.gather_cat_bwd(ws["dcat"], ws["last_idx"], batch["user_gender"], batch["user_country"], B, L, dx, None,
+                           g[ut + "gender_embedding.weight"], g[ut + "country_embedding.weight"])
+        # dy = dropout-mask(dx) as bf16 for the top layer's linear2, with its column sums (bias grad)
+        top = cfg.num_layers - 1
+        ops.chain_bwd(dx, dout=dx, dx_bf16=ws["dy_bf"], drop2_p=dp, drop2_site=_site(top, 3), seed=seed,
+                      seed_dev=sdev, dx_colsum=g[self._lp(top, "linear2.bias")])
+
+        # ---- encoder layers, last to first
+        for l in range(cfg.num_layers - 1, -1, -1):
+            x_in = ws[f"xout_{l - 1}"] if l > 0 else ws["x_in0"]
+            ffn_scale = 1.0 / (1.0 - dp) if dp > 0 else 1.0
+            # linear2: dW2 = dy^T f ; dpre = (dy W2) gated by f (ReLU and FFN dropout in one test)
+            gemm(ws["dy_bf"], ws[f"f_{l}"], a_mn=True, b_mn=True, out_f32=g[self._lp(l, "linear2.weight")],
+                 accumulate=True)
+            gemm(ws["dy_bf"], w[self._lp(l, "linear2.weight")], b_mn=True, gate=ws[f"f_{l}"], gate_scale=ffn_scale,
+                 out_bf16=ws["dpre"])
+            ops.colsum_bf16(ws["dpre"], g[self._lp(l, "linear1.bias")])
+            gemm(ws["dpre"], ws[f"h2_{l}"], a_mn=True, b_mn=True, out_f32=g[self._lp(l, "linear1.weight")],
+                 accumulate=True)
+            gemm(ws["dpre"], w[self._lp(l, "linear1.weight")], b_mn=True, out_f32=ws["dh"])
+            # norm2 backward (+ residual); emits dy for out_proj (dropout-1 mask) and its bias grad
+            ops.chain_bwd(ws[f"xmid_{l}"], ln=(p[self._lp(l, "norm2.weight")], p[self._lp(l, "norm2.bias")]),
+                          dout=ws["dh"], resid=dx, dx_f32=dx_other, dx_bf16=ws["dy_bf"], drop2_p=dp,
+                          drop2_site=_site(l, 1), seed=seed, seed_dev=sdev,
+                          dgamma=g[self._lp(l, "norm2.weight")], dbeta=g[self._lp(l, "norm2.bias")],
+                          dx_colsum=g[self._lp(l, "self_attn.out_proj.bias")])
+            dx, dx_other = dx_other, dx
+            gemm(ws["dy_bf"], ws[f"ctx_{l}"], a_mn=True, b_mn=True,
+                 out_f32=g[self._lp(l, "self_attn.out_proj.weight")], accumulate=True)
+            gemm(ws["dy_bf"], w[self._lp(l, "self_attn.out_proj.weight")], b_mn=True, out_bf16=ws["dctx"])
+            ops.attn_bwd(ws[f"qkv_{l}"], ws[f"ctx_{l}"], ws["dctx"], ws[f"lse_{l}"], ws["dqkv"], B, L, cfg.num_heads,
+                         drop_p=dp, drop_seed=seed, drop_seed_dev=sdev, drop_site=_site(l, 0))
+            ops.colsum_bf16(ws["dqkv"], g[self._lp(l, "self_attn.in_proj_bias")])
+            gemm(ws["dqkv"], ws[f"h1_{l}"], a_mn=True, b_mn=True, out_f32=g[self._lp(l, "self_attn.in_proj_weight")],
+                 accumulate=True)
+            gemm(ws["dqkv"], w[self._lp(l, "self_attn.in_proj_weight")], b_mn=True, out_f32=ws["dh"])
+            # norm1 backward (+ residual); for l > 0 also dy for the previous layer's linear2
+            extra = {}
+            if l > 0:
+                extra = dict(dx_bf16=ws["dy_bf"], drop2_p=dp, drop2_site=_site(l - 1, 3),
+                             dx_colsum=g[self._lp(l - 1, "linear2.bias")])
+            ops.chain_bwd(x_in, ln=(p[self._lp(l, "norm1.weight")], p[self._lp(l, "norm1.bias")]), dout=ws["dh"],
+                          resid=dx, dx_f32=dx_other, seed=seed, seed_dev=sdev,
+                          dgamma=g[self._lp(l, "norm1.weight")], dbeta=g[self._lp(l, "norm1.bias")], **extra)
+            dx, dx_other = dx_other, dx
+
+        # ---- embedding LayerNorm + lookup
+        ops.embed_ln_bwd(ids.view(-1), p[ut + "item_embedding.weight"], p[ut + "position_embedding.weight"],
+                         p[ut + "layer_norm.weight"], p[ut + "layer_norm.bias"], dx, B, L,
+                         g[ut + "item_embedding.weight"], g[ut + "position_embedding.weight"],
+                         g[ut + "layer_norm.weight"], g[ut + "layer_norm.bias"], drop_p=dp, seed=seed,
+                         seed_dev=sdev, site=SITE_EMB)
+
+    # ------------------------------------------------------------------ optimizer
+    def adamw_step(self, lr: float = 1e-4, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.01,
+                   zero_grad: bool = True) -> None:
+        """torch.optim.AdamW semantics over the whole flat buffer (src/train.py:302, 64-65), dense
+        on the ID table like the reference; refreshes the bf16 shadow of the dense region and
+        zeroes the gradient buffer in the same pass; advances the step / dropout-seed counters."""
+        if self.exp_avg is None:
+            self.exp_avg = torch.zeros_like(self.flat)
+            self.exp_avg_sq = torch.zeros_like(self.flat)
+        ops.step_counters_advance(self.step_dev, self.seed_dev)
+        ops.adamw_step(self.flat, self.grad, self.exp_avg, self.exp_avg_sq, self.step_dev, lr, betas[0], betas[1],
+                       eps, weight_decay, shadow=self.shadow, shadow_begin=self.dense_begin, shadow_end=self.numel,
+                       zero_grad=zero_grad)
+        self.shadow_valid = True
+
+    def train_step(self, batch: Dict[str, torch.Tensor], lr: float = 1e-4) -> torch.Tensor:
+        """One step of the train_one_epoch body (src/train.py:54-65): forward, backward, AdamW."""
+        loss, _, _, _ = self.forward(batch, training=True)
+        self.backward()
+        self.adamw_step(lr=lr)
+        return loss

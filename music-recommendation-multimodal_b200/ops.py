@@ -26,7 +26,7 @@ def _require_cuda(*ts):
 def gemm(A: torch.Tensor, B: torch.Tensor, *, a_mn: bool = False, b_mn: bool = False,
          alpha: float = 1.0, bias: Optional[torch.Tensor] = None, relu: bool = False,
          drop_p: float = 0.0, drop_seed: int = 0, drop_site: int = 0,
-         gate: Optional[torch.Tensor] = None, gate_scale: float = 1.0,
+         drop_seed_dev: Optional[torch.Tensor] = None, gate: Optional[torch.Tensor] = None, gate_scale: float = 1.0,
          residual: Optional[torch.Tensor] = None,
          out_f32: Optional[torch.Tensor] = None, out_bf16: Optional[torch.Tensor] = None,
          accumulate: bool = False, k_splits: int = 0, block_n: int = 0,
@@ -60,6 +60,7 @@ def gemm(A: torch.Tensor, B: torch.Tensor, *, a_mn: bool = False, b_mn: bool = F
     args.bias = _ptr(bias)
     args.relu = int(relu)
     args.drop_p, args.drop_seed, args.drop_site = drop_p, drop_seed, drop_site
+    args.drop_seed_dev = _ptr(drop_seed_dev)
     if gate is not None:
         assert gate.dtype == torch.bfloat16 and gate.stride(1) == 1
         args.ld_gate = gate.stride(0)
@@ -84,7 +85,8 @@ def gemm(A: torch.Tensor, B: torch.Tensor, *, a_mn: bool = False, b_mn: bool = F
 
 
 def attn_fwd(qkv: torch.Tensor, ctx: torch.Tensor, lse: Optional[torch.Tensor], B: int, L: int, H: int,
-             drop_p: float = 0.0, drop_seed: int = 0, drop_site: int = 0) -> None:
+             drop_p: float = 0.0, drop_seed: int = 0, drop_site: int = 0,
+             drop_seed_dev: Optional[torch.Tensor] = None) -> None:
     """Causal self-attention forward (tt_attn_causal_fwd). qkv bf16 [B*L, 3*H*64] -> ctx bf16 [B*L, H*64]."""
     _require_cuda(qkv, ctx, lse)
     assert qkv.dtype == torch.bfloat16 and qkv.is_contiguous() and qkv.shape == (B * L, 3 * H * 64)
@@ -92,17 +94,175 @@ def attn_fwd(qkv: torch.Tensor, ctx: torch.Tensor, lse: Optional[torch.Tensor], 
     if lse is not None:
         assert lse.dtype == torch.float32 and lse.is_contiguous() and lse.numel() == B * H * L
     check(lib().tt_attn_causal_fwd(qkv.data_ptr(), ctx.data_ptr(), _ptr(lse), B, L, H, drop_p,
-                                   drop_seed, drop_site, _stream()), "tt_attn_causal_fwd")
+                                   drop_seed, _ptr(drop_seed_dev), drop_site, _stream()), "tt_attn_causal_fwd")
 
 
 def attn_bwd(qkv: torch.Tensor, ctx: torch.Tensor, dctx: torch.Tensor, lse: torch.Tensor,
              dqkv: torch.Tensor, B: int, L: int, H: int, drop_p: float = 0.0, drop_seed: int = 0,
-             drop_site: int = 0) -> None:
+             drop_site: int = 0, drop_seed_dev: Optional[torch.Tensor] = None) -> None:
     """Causal self-attention backward (tt_attn_causal_bwd): dqkv bf16 [B*L, 3*H*64]."""
     _require_cuda(qkv, ctx, dctx, lse, dqkv)
     for t in (qkv, ctx, dctx, dqkv):
         assert t.dtype == torch.bfloat16 and t.is_contiguous()
     assert lse.dtype == torch.float32 and lse.is_contiguous()
     check(lib().tt_attn_causal_bwd(qkv.data_ptr(), ctx.data_ptr(), dctx.data_ptr(), lse.data_ptr(),
-                                   dqkv.data_ptr(), B, L, H, drop_p, drop_seed, drop_site, _stream()),
+                                   dqkv.data_ptr(), B, L, H, drop_p, drop_seed, _ptr(drop_seed_dev), drop_site, _stream()),
           "tt_attn_causal_bwd")
+
+
+# --------------------------------------------------------------------------------------
+# row-wise kernels
+# --------------------------------------------------------------------------------------
+from ._lib import BnArgs, ChainArgs  # noqa: E402
+
+
+def cast_bf16(src: torch.Tensor, dst: torch.Tensor) -> None:
+    _require_cuda(src, dst)
+    assert src.dtype == torch.float32 and dst.dtype == torch.bfloat16 and src.numel() == dst.numel()
+    assert src.is_contiguous() and dst.is_contiguous()
+    check(lib().tt_cast_bf16(src.data_ptr(), dst.data_ptr(), src.numel(), _stream()), "tt_cast_bf16")
+
+
+def last_index(ids: torch.Tensor, mask: Optional[torch.Tensor], out: torch.Tensor) -> None:
+    _require_cuda(ids, mask, out)
+    B, L = ids.shape
+    assert ids.dtype == torch.int64 and ids.is_contiguous() and out.dtype == torch.int32
+    if mask is not None:
+        assert mask.dtype == torch.int64 and mask.is_contiguous() and mask.shape == ids.shape
+    check(lib().tt_last_index(ids.data_ptr(), _ptr(mask), B, L, out.data_ptr(), _stream()), "tt_last_index")
+
+
+def embed_ln_fwd(ids, E, P, ln_w, ln_b, next_w, next_b, B, L, x0, h, drop_p=0.0, seed=0, seed_dev=None, site=0):
+    _require_cuda(ids, E, P, x0, h)
+    assert ids.dtype == torch.int64 and E.dtype == torch.float32 and E.shape[1] == 256 and P.shape[0] >= L
+    check(lib().tt_embed_ln_fwd(ids.data_ptr(), E.data_ptr(), P.data_ptr(), ln_w.data_ptr(), ln_b.data_ptr(),
+                                next_w.data_ptr(), next_b.data_ptr(), B, L, drop_p, seed, _ptr(seed_dev), site,
+                                x0.data_ptr(), h.data_ptr(), _stream()), "tt_embed_ln_fwd")
+
+
+def embed_ln_bwd(ids, E, P, ln_w, ln_b, dx0, B, L, dE, dP, dgamma, dbeta, drop_p=0.0, seed=0, seed_dev=None, site=0):
+    _require_cuda(ids, E, P, dx0, dE, dP, dgamma, dbeta)
+    check(lib().tt_embed_ln_bwd(ids.data_ptr(), E.data_ptr(), P.data_ptr(), ln_w.data_ptr(), ln_b.data_ptr(),
+                                dx0.data_ptr(), B, L, drop_p, seed, _ptr(seed_dev), site, dE.data_ptr(),
+                                dP.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(), _stream()), "tt_embed_ln_bwd")
+
+
+def _chain_args(x, *, ln=None, relu=False, drop_p=0.0, seed=0, seed_dev=None, site=0, l2norm=False,
+                l2_eps=1e-12, out_f32=None, out_bf16=None, dout=None, resid=None, dx_f32=None, dx_bf16=None,
+                drop2_p=0.0, drop2_site=0, dgamma=None, dbeta=None, dx_colsum=None) -> ChainArgs:
+    _require_cuda(x, out_f32, out_bf16, dout, resid, dx_f32, dx_bf16, dgamma, dbeta, dx_colsum)
+    assert x.dtype == torch.float32 and x.dim() == 2 and x.is_contiguous()
+    a = ChainArgs()
+    a.x, a.rows, a.width = x.data_ptr(), x.shape[0], x.shape[1]
+    if ln is not None:
+        a.ln_w, a.ln_b = ln[0].data_ptr(), ln[1].data_ptr()
+    a.ln_eps = 1e-5
+    a.relu = int(relu)
+    a.drop_p, a.drop_seed, a.drop_seed_dev, a.drop_site = drop_p, seed, _ptr(seed_dev), site
+    a.l2norm, a.l2_eps = int(l2norm), l2_eps
+    a.out_f32, a.out_bf16 = _ptr(out_f32), _ptr(out_bf16)
+    a.dout, a.resid, a.dx_f32, a.dx_bf16 = _ptr(dout), _ptr(resid), _ptr(dx_f32), _ptr(dx_bf16)
+    a.drop2_p, a.drop2_site = drop2_p, drop2_site
+    a.dgamma, a.dbeta, a.dx_colsum = _ptr(dgamma), _ptr(dbeta), _ptr(dx_colsum)
+    return a
+
+
+def chain_fwd(x, **kw) -> None:
+    """[LayerNorm] -> [ReLU] -> [dropout] -> [L2 normalise] (tt_chain_fwd)."""
+    a = _chain_args(x, **kw)
+    check(lib().tt_chain_fwd(ctypes.byref(a), _stream()), "tt_chain_fwd")
+
+
+def chain_bwd(x, **kw) -> None:
+    a = _chain_args(x, **kw)
+    check(lib().tt_chain_bwd(ctypes.byref(a), _stream()), "tt_chain_bwd")
+
+
+def gather_cat_fwd(x, last_idx, gender, country, G, C, B, L, cat) -> None:
+    _require_cuda(x, last_idx, gender, country, G, C, cat)
+    check(lib().tt_gather_cat_fwd(x.data_ptr(), last_idx.data_ptr(), _ptr(gender), _ptr(country), G.data_ptr(),
+                                  C.data_ptr(), B, L, cat.data_ptr(), _stream()), "tt_gather_cat_fwd")
+
+
+def gather_cat_bwd(dcat, last_idx, gender, country, B, L, dx, dx_bf16, dG, dC) -> None:
+    _require_cuda(dcat, last_idx, gender, country, dx, dx_bf16, dG, dC)
+    check(lib().tt_gather_cat_bwd(dcat.data_ptr(), last_idx.data_ptr(), _ptr(gender), _ptr(country), B, L,
+                                  _ptr(dx), _ptr(dx_bf16), dG.data_ptr(), dC.data_ptr(), _stream()),
+          "tt_gather_cat_bwd")
+
+
+def concat4_bf16(a, b, c, d, out) -> None:
+    _require_cuda(a, b, c, d, out)
+    B, m = a.shape
+    for t in (a, b, c, d):
+        assert t.dtype == torch.float32 and t.is_contiguous() and t.shape == (B, m)
+    check(lib().tt_concat4_bf16(a.data_ptr(), b.data_ptr(), c.data_ptr(), d.data_ptr(), B, m, out.data_ptr(),
+                                _stream()), "tt_concat4_bf16")
+
+
+def _bn_args(y, w, b, running_mean, running_var, num_batches, *, training, momentum=0.1, eps=1e-5, drop_p=0.0,
+             seed=0, seed_dev=None, site=0, save_mean=None, save_rstd=None, out_bf16=None, dout=None,
+             dy_bf16=None, dgamma=None, dbeta=None, dy_colsum=None) -> BnArgs:
+    _require_cuda(y, w, b, running_mean, running_var, num_batches, save_mean, save_rstd, out_bf16, dout, dy_bf16)
+    a = BnArgs()
+    a.y, a.B, a.C = y.data_ptr(), y.shape[0], y.shape[1]
+    a.w, a.b = w.data_ptr(), b.data_ptr()
+    a.running_mean, a.running_var, a.num_batches_tracked = _ptr(running_mean), _ptr(running_var), _ptr(num_batches)
+    a.training, a.momentum, a.eps = int(training), momentum, eps
+    a.drop_p, a.drop_seed, a.drop_seed_dev, a.drop_site = drop_p, seed, _ptr(seed_dev), site
+    a.save_mean, a.save_rstd, a.out_bf16 = _ptr(save_mean), _ptr(save_rstd), _ptr(out_bf16)
+    a.dout, a.dy_bf16, a.dgamma, a.dbeta, a.dy_colsum = _ptr(dout), _ptr(dy_bf16), _ptr(dgamma), _ptr(dbeta), _ptr(dy_colsum)
+    return a
+
+
+def bn_relu_fwd(y, w, b, running_mean, running_var, num_batches, **kw) -> None:
+    a = _bn_args(y, w, b, running_mean, running_var, num_batches, **kw)
+    check(lib().tt_bn_relu_fwd(ctypes.byref(a), _stream()), "tt_bn_relu_fwd")
+
+
+def bn_relu_bwd(y, w, b, running_mean, running_var, num_batches, **kw) -> None:
+    a = _bn_args(y, w, b, running_mean, running_var, num_batches, **kw)
+    check(lib().tt_bn_relu_bwd(ctypes.byref(a), _stream()), "tt_bn_relu_bwd")
+
+
+def colsum_bf16(x: torch.Tensor, out: torch.Tensor) -> None:
+    _require_cuda(x, out)
+    assert x.dtype == torch.bfloat16 and x.stride(1) == 1 and out.dtype == torch.float32
+    check(lib().tt_colsum_bf16(x.data_ptr(), x.shape[0], x.shape[1], x.stride(0), out.data_ptr(), _stream()),
+          "tt_colsum_bf16")
+
+
+def adamw_step(p, g, m, v, step_dev, lr=1e-4, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.01,
+               shadow=None, shadow_begin=0, shadow_end=0, zero_grad=True) -> None:
+    _require_cuda(p, g, m, v, step_dev, shadow)
+    for t in (p, g, m, v):
+        assert t.dtype == torch.float32 and t.is_contiguous() and t.numel() == p.numel()
+    assert step_dev.dtype == torch.int64
+    check(lib().tt_adamw_step(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), lr, beta1, beta2,
+                              eps, weight_decay, step_dev.data_ptr(), _ptr(shadow), shadow_begin, shadow_end,
+                              int(zero_grad), _stream()), "tt_adamw_step")
+
+
+def step_counters_advance(step_dev, seed_dev) -> None:
+    check(lib().tt_step_counters_advance(_ptr(step_dev), _ptr(seed_dev), _stream()), "tt_step_counters_advance")
+
+
+def infonce_rows(S, uid_rows, uid_cols, pos0, row_lse, pos_logit) -> None:
+    _require_cuda(S, uid_rows, uid_cols, row_lse, pos_logit)
+    assert S.dtype == torch.float32 and S.stride(1) == 1
+    check(lib().tt_infonce_rows(S.data_ptr(), S.shape[0], S.shape[1], S.stride(0), _ptr(uid_rows), _ptr(uid_cols),
+                                pos0, row_lse.data_ptr(), pos_logit.data_ptr(), _stream()), "tt_infonce_rows")
+
+
+def infonce_grad(S, row_lse, col_lse, pos0, coef, dS) -> None:
+    _require_cuda(S, row_lse, col_lse, dS)
+    assert dS.dtype == torch.bfloat16 and dS.stride(1) == 1
+    check(lib().tt_infonce_grad(S.data_ptr(), S.shape[0], S.shape[1], S.stride(0), row_lse.data_ptr(),
+                                col_lse.data_ptr(), pos0, coef, dS.data_ptr(), dS.stride(0), _stream()),
+          "tt_infonce_grad")
+
+
+def infonce_loss(lse_a, pos_a, lse_b, pos_b, coef, loss) -> None:
+    _require_cuda(lse_a, pos_a, lse_b, pos_b, loss)
+    check(lib().tt_infonce_loss(lse_a.data_ptr(), pos_a.data_ptr(), lse_b.data_ptr(), pos_b.data_ptr(),
+                                lse_a.numel(), coef, loss.data_ptr(), _stream()), "tt_infonce_loss")

@@ -147,7 +147,20 @@ def test_gemm_dropout_is_deterministic_and_scaled():
 def test_gemm_rejects_bad_args():
     from mrm_b200 import TTError, ops
     A = _mk((128, 64), 0)
-    B = _mk((96, 64), 1)
-    out = torch.empty((128, 96), device="cuda")
+    B = _mk((100, 64), 1)
+    out = torch.empty((128, 100), device="cuda")
     with pytest.raises(TTError):
-        ops.gemm(A, B.t().contiguous(), b_mn=True, out_f32=out)  # N % 64 != 0 for MN-major B
+        ops.gemm(A, B.t().contiguous(), b_mn=True, out_f32=out)  # ldb = 100 is not a multiple of 8
+
+
+def test_gemm_mn_major_ragged_n():
+    """MN-major B with N = 304 (the user-fusion input width): ragged last 64-chunk."""
+    from mrm_b200 import ops
+    M, N, K = 256, 304, 256
+    A = _mk((M, K), 21)
+    Bfull = _mk((K + 1, N), 22)            # one spare row keeps the ragged chunk readable
+    B = Bfull[:K]
+    out = torch.empty((M, N), device="cuda")
+    ops.gemm(A, B, b_mn=True, out_f32=out, N=N, K=K)
+    torch.cuda.synchronize()
+    _check(out, A.float() @ B.float(), K, "ragged MN-major N")
