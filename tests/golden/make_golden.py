@@ -114,8 +114,34 @@ def golden_train(two_tower, name, cfg, B, seed_w, seed_b, full_length=False):
             out[tag]["eval_item_emb"] = m.get_item_embedding(
                 b["target_image"], b["target_audio"], b["target_input_ids"],
                 b["target_attention_mask"], b["target_tabular"])
+    # Tolerance anchor: the reference's own modules under bf16 autocast,
+    # measured against its fp64 run. Per-tensor relative gradient error and output errors.
+    m64 = build_reference_model(two_tower, cfg, sd, torch.float64)
+    m64.train()
+    l64, lg64, u64, i64 = m64(cast_batch(batch, torch.float64))
+    l64.backward()
+    g64 = {k: p.grad.detach() for k, p in m64.named_parameters() if p.grad is not None}
+    mb = build_reference_model(two_tower, cfg, sd, torch.float32)
+    mb.train()
+    with torch.autocast(device_type="cpu", dtype=torch.bfloat16):
+        lb, lgb, ub, ib = mb(cast_batch(batch, torch.float32))
+    lb.backward()
+    gb = {k: p.grad.detach() for k, p in mb.named_parameters() if p.grad is not None}
+    auto = {
+        "loss_abs": abs(lb.item() - l64.item()),
+        "logits_abs": (lgb.double() - lg64).abs().max().item(),
+        "user_emb_abs": (ub.double() - u64).abs().max().item(),
+        "item_emb_abs": (ib.double() - i64).abs().max().item(),
+        "grad_rel": {k: ((gb[k].double() - g64[k]).norm() / g64[k].norm().clamp_min(1e-300)).item() for k in g64},
+        "grad_abs": {k: (gb[k].double() - g64[k]).norm().item() for k in g64},
+        "grad_norm64": {k: g64[k].norm().item() for k in g64},
+    }
+    out["bf16_autocast_err"] = auto
     torch.save(out, os.path.join(HERE, name))
-    print(name, "loss f64", out["f64"]["loss"].item(), "f32", out["f32"]["loss"].item())
+    worst = sorted(((v, k) for k, v in auto["grad_rel"].items() if auto["grad_norm64"][k] > 1e-6), reverse=True)[:4]
+    print(name, "loss f64", out["f64"]["loss"].item(), "f32", out["f32"]["loss"].item(),
+          "| reference under bf16 autocast: loss", auto["loss_abs"], "logits", auto["logits_abs"], "user",
+          auto["user_emb_abs"], "item", auto["item_emb_abs"], "worst grad rel", worst)
 
 
 class _FakeModel(nn.Module):

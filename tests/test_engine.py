@@ -4,12 +4,16 @@ Forward outputs are compared with the golden vectors produced by the REFERENCE's
 (tests/golden/*.pt, fp64 run); full parameter gradients with the CPU oracle (itself pinned to
 those vectors in test_oracle_golden.py).
 
-Tolerances (bf16 tensor-core operands, fp32 accumulation, fp32 residual stream / statistics):
-  normalised embeddings  abs <= 2e-2      (unit vectors, per element ~1/16)
-  logits (x 1/0.07)      abs <= 0.25
-  loss                   abs <= 3e-2
-  parameter gradients    ||g - g_ref|| / ||g_ref|| <= 6e-2 per tensor
+Tolerance rule. The kernels compute with bf16 tensor-core operands, fp32
+accumulation and an fp32 residual stream; the reference trains under 16-bit autocast. The
+goldens therefore also store the error of the REFERENCE's own modules under bf16 autocast
+against its fp64 run ("bf16_autocast_err"), and every quantity must satisfy
+    err(ours, fp64) <= max(2 * err(reference under bf16 autocast, fp64), floor)
+with floors: normalised embeddings 5e-3 abs, logits (x 1/0.07) 8e-2 abs, loss 5e-3 abs,
+parameter gradients 3e-2 * ||g_ref|| + 1e-5 * sqrt(numel) in L2 norm per tensor.
+Measured values are appended to gpurun_out/parity_report.jsonl.
 """
+import json
 import os
 
 import pytest
@@ -18,6 +22,12 @@ import torch
 pytestmark = pytest.mark.gpu
 
 GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _report(**kw):
+    os.makedirs("gpurun_out", exist_ok=True)
+    with open("gpurun_out/parity_report.jsonl", "a") as f:
+        f.write(json.dumps(kw) + "\n")
 
 
 def _setup(name):
@@ -39,11 +49,17 @@ def test_forward_matches_reference_golden(name):
     gold, cfg, sd, batch, eng, dbatch = _setup(name)
     loss, logits, u, i = eng.forward(dbatch, training=True)
     torch.cuda.synchronize()
-    g = gold["f64"]
-    assert (u.cpu().double() - g["user_emb"]).abs().max().item() <= 2e-2
-    assert (i.cpu().double() - g["item_emb"]).abs().max().item() <= 2e-2
-    assert (logits.cpu().double() - g["logits"]).abs().max().item() <= 0.25
-    assert abs(loss.item() - g["loss"].item()) <= 3e-2
+    g, auto = gold["f64"], gold["bf16_autocast_err"]
+    eu = (u.cpu().double() - g["user_emb"]).abs().max().item()
+    ei = (i.cpu().double() - g["item_emb"]).abs().max().item()
+    el = (logits.cpu().double() - g["logits"]).abs().max().item()
+    eloss = abs(loss.item() - g["loss"].item())
+    _report(test="forward", fixture=name, user_emb_abs=eu, item_emb_abs=ei, logits_abs=el, loss_abs=eloss,
+            reference_bf16_autocast={k: auto[k] for k in ("user_emb_abs", "item_emb_abs", "logits_abs", "loss_abs")})
+    assert eu <= max(2 * auto["user_emb_abs"], 5e-3), eu
+    assert ei <= max(2 * auto["item_emb_abs"], 5e-3), ei
+    assert el <= max(2 * auto["logits_abs"], 8e-2), el
+    assert eloss <= max(2 * auto["loss_abs"], 5e-3), eloss
     assert (eng.bn_running_mean.cpu().double() - g["bn_running_mean"]).abs().max().item() <= 2e-3
     assert (eng.bn_running_var.cpu().double() - g["bn_running_var"]).abs().max().item() <= 2e-3
     assert eng.bn_num_batches.item() == 1
@@ -56,14 +72,23 @@ def test_backward_matches_oracle(name):
     eng.forward(dbatch, training=True)
     eng.backward()
     torch.cuda.synchronize()
-    _, _, _, _, grads, _ = oracle.loss_and_grads(sd, batch, cfg.temperature, cfg.num_heads, dtype=torch.float32)
-    worst = []
+    b64 = {k: (v.double() if v.is_floating_point() else v) for k, v in batch.items()}
+    _, _, _, _, grads, _ = oracle.loss_and_grads(sd, b64, cfg.temperature, cfg.num_heads, dtype=torch.float64)
+    auto = gold["bf16_autocast_err"]
+    rows, bad = [], []
     for k, ref in grads.items():
-        got = eng.g[k].cpu()
-        rel = (got - ref).norm().item() / max(ref.norm().item(), 1e-12)
-        worst.append((rel, k))
-    worst.sort(reverse=True)
-    assert worst[0][0] <= 6e-2, worst[:6]
+        got = eng.g[k].cpu().double()
+        err = (got - ref).norm().item()
+        bound = max(2 * auto["grad_abs"].get(k, 0.0), 3e-2 * ref.norm().item() + 1e-5 * ref.numel() ** 0.5)
+        rows.append((err / max(ref.norm().item(), 1e-12), k, err, bound))
+        if err > bound:
+            bad.append((k, err, bound))
+    rows.sort(reverse=True)
+    _report(test="backward", fixture=name,
+            worst_rel=[(r, k) for r, k, _, _ in rows if grads[k].norm().item() > 1e-6][:5],
+            reference_bf16_autocast_worst_rel=sorted(
+                ((v, k) for k, v in auto["grad_rel"].items() if auto["grad_norm64"][k] > 1e-6), reverse=True)[:5])
+    assert not bad, bad[:6]
     assert eng.g["user_tower.item_embedding.weight"][0].abs().max().item() == 0.0
 
 
