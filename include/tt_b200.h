@@ -232,6 +232,46 @@ int tt_infonce_grad(const float* S, int R, int C, int ld, const float* row_lse, 
 int tt_infonce_loss(const float* lse_a, const float* pos_a, const float* lse_b, const float* pos_b, int R, float coef,
                     float* loss, void* stream);
 
+/* ---- catalog retrieval (src/evaluate_metrics.py:106-192) ------------------------------
+ * Canonical order everywhere: score descending, then item index ascending (torch.topk leaves
+ * ties unspecified). Keys are 64-bit: (order-preserving score bits << 32) | (2^32-1 - index).
+ *
+ * tt_topk_plan_make : sizes the work decomposition and the scratch buffers for U users against
+ *                     N items (this shard), K' = kprime candidates per user (8..256).
+ * tt_score_topk     : fused U E^T (bf16 tensor cores, fp32 accumulate) + streaming top-K' per
+ *                     user; replaces the matmul at :148, the column-0 mask at :152 and topk at
+ *                     :156 without materialising the (U, N) score matrix.
+ *                     users_bf16 [U,256], items_bf16 [N,256]; item_base = global index of row 0
+ *                     of this shard; mask_item0 excludes global item 0 (the padding id).
+ *                     cand/cand_cnt/thr are scratch of plan->{cand,cnt,thr}_bytes.
+ * tt_topk_finalize  : per user, K' best keys -> exact re-score (fp32 inputs, fp64 accumulate,
+ *                     rounded once to fp32) -> canonical sort -> top K (global indices, -1 pad)
+ *                     and flags[u] = 1 when the certificate "no non-candidate can reach the
+ *                     exact top K" fails (eps bounds |bf16-path score - exact score|).
+ * tt_topk_merge     : top K of the union of G per-shard lists [G][U][K].
+ * tt_exact_topk     : brute-force exact top K of one user (fallback for flagged users);
+ *                     key_scratch = N * 8 bytes.
+ * tt_rank_metrics   : per-row Recall@k / NDCG@k (:159-185); gain_table[r] = 1/log2(r+2) comes
+ *                     from the host so rows are bit-identical to the reference's; outputs [nk][U].
+ */
+typedef struct tt_topk_plan {
+  int32_t U, N, kprime, cap;
+  int32_t n_ut, n_ranges, tiles_per_range;
+  int64_t cand_bytes, cnt_bytes, thr_bytes;
+} tt_topk_plan;
+int tt_topk_plan_make(int U, int N, int kprime, tt_topk_plan* plan);
+int tt_score_topk(const void* users_bf16, const void* items_bf16, int item_base, const tt_topk_plan* plan,
+                  void* cand, int32_t* cand_cnt, void* thr, int mask_item0, void* stream);
+int tt_topk_finalize(const tt_topk_plan* plan, const void* cand, const int32_t* cand_cnt, const float* users_f32,
+                     const float* items_f32, int item_base, int K, float eps, int32_t* out_idx, float* out_score,
+                     int32_t* flags, void* stream);
+int tt_topk_merge(const float* scores, const int32_t* idx, int G, int U, int K, float* out_score, int32_t* out_idx,
+                  void* stream);
+int tt_exact_topk(const float* user_f32, const float* items_f32, int N, int item_base, int mask_item0, int K,
+                  void* key_scratch, float* out_score, int32_t* out_idx, void* stream);
+int tt_rank_metrics(const int32_t* topk_idx, const int64_t* targets, int U, int K, const int32_t* k_list, int nk,
+                    const float* gain_table, float* recall, float* ndcg, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

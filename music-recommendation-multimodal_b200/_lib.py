@@ -119,8 +119,25 @@ class BnArgs(ctypes.Structure):
     ]
 
 
+class TopkPlan(ctypes.Structure):
+    """Mirror of ``tt_topk_plan``."""
+
+    _fields_ = [("U", c_int32), ("N", c_int32), ("kprime", c_int32), ("cap", c_int32),
+                ("n_ut", c_int32), ("n_ranges", c_int32), ("tiles_per_range", c_int32),
+                ("cand_bytes", ctypes.c_int64), ("cnt_bytes", ctypes.c_int64), ("thr_bytes", ctypes.c_int64)]
+
+
 _I64 = ctypes.c_int64
 _SIGNATURES = {
+    "tt_topk_plan_make": [c_int32, c_int32, c_int32, ctypes.POINTER(TopkPlan)],
+    "tt_score_topk": [c_void_p, c_void_p, c_int32, ctypes.POINTER(TopkPlan), c_void_p, c_void_p, c_void_p, c_int32,
+                      c_void_p],
+    "tt_topk_finalize": [ctypes.POINTER(TopkPlan), c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_float,
+                         c_void_p, c_void_p, c_void_p, c_void_p],
+    "tt_topk_merge": [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p],
+    "tt_exact_topk": [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p],
+    "tt_rank_metrics": [c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_int32, c_void_p, c_void_p, c_void_p,
+                        c_void_p],
     "tt_cast_bf16": [c_void_p, c_void_p, _I64, c_void_p],
     "tt_last_index": [c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p],
     "tt_embed_ln_fwd": [c_void_p] * 7 + [c_int32, c_int32, c_float, c_uint64, c_void_p, c_uint32,

@@ -1,0 +1,654 @@
+// Catalog retrieval: scores = U E^T fused with a streaming per-user top-K' selection, exact
+// re-scoring of the candidates, canonical ordering, cross-shard merge and Recall/NDCG.
+//
+// Replaces, in calculate_metrics_global (src/evaluate_metrics.py:106-192):
+//   scores = user_emb @ item_embeddings.T   (:148, fp32 SGEMM, (B, V) matrix materialised)
+//   scores[:, 0] = -inf                     (:152)
+//   torch.topk(scores, max_k)               (:156, radix select over V-long rows)
+//   per-k hit / NDCG bookkeeping            (:159-185, nonzero() syncs)
+//
+// tt_score_topk (tcgen05): a work unit = 256 users x one contiguous item range. The user tile
+// (2 x 128 rows x 256 dims, bf16, 128 KB) stays resident in shared memory, item tiles of 128
+// rows stream through a 5-stage TMA ring, two M=128,N=128 accumulators per item tile live in
+// TMEM (double-buffered: 512 columns). Eight epilogue warps read the accumulators with
+// tcgen05.ld; each thread owns one user row, keeps that row's running threshold in a register
+// and appends (score, item) keys that beat it to a per-(range,row) candidate list in global
+// memory; a full list is pruned to its K' best by the whole warp (bitwise binary search on
+// the 64-bit keys with ballot/popc + compaction). The score matrix never exists.
+// Keys are totally ordered: (score descending, item index ascending) — the canonical order.
+//
+// tt_topk_finalize: per user, select the K' best keys over all ranges, re-score them EXACTLY
+// (fp32 inputs, fp64 accumulation, rounded once to fp32), sort canonically, emit the top K and
+// a certificate that no non-candidate can belong to the exact top K.
+#include "../../include/tt_b200.h"
+#include "tt_common.cuh"
+
+namespace tt {
+
+static constexpr int kUT = 256;        // users per work unit
+static constexpr int kIT = 128;        // items per MMA tile
+static constexpr int kD = 256;         // embedding dim
+static constexpr int kKB = kD / 64;    // k-blocks
+static constexpr uint32_t kTile16K = 128 * 64 * 2;
+static constexpr int kBStages = 5;
+static constexpr int kTopkThreads = 384;
+static constexpr int kCap = 512;       // candidate list capacity per (range, row)
+
+__device__ __forceinline__ uint32_t f2ord(float f) {
+  const uint32_t u = __float_as_uint(f + 0.0f);  // -0 -> +0
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float ord2f(uint32_t o) {
+  const uint32_t u = (o & 0x80000000u) ? (o & 0x7fffffffu) : ~o;
+  return __uint_as_float(u);
+}
+__device__ __forceinline__ uint64_t make_key(float s, uint32_t gidx) {
+  return (static_cast<uint64_t>(f2ord(s)) << 32) | static_cast<uint64_t>(0xFFFFFFFFu - gidx);
+}
+__device__ __forceinline__ uint32_t key_idx(uint64_t k) { return 0xFFFFFFFFu - static_cast<uint32_t>(k); }
+__device__ __forceinline__ float key_score(uint64_t k) { return ord2f(static_cast<uint32_t>(k >> 32)); }
+
+struct TopkParams {
+  int U, N, item_base;
+  int n_ut, n_ranges, tiles_per_range, total_tiles;
+  int kprime;
+  int u_pad;
+  unsigned long long* cand;  // [n_ranges][u_pad][kCap]
+  int* cand_cnt;             // [n_ranges][u_pad]
+  unsigned long long* thr;   // [u_pad]
+  int mask_item0;
+};
+
+// Warp-cooperative prune of one row's candidate list to its kprime largest keys.
+// Returns the new count; T receives a threshold with count(keys >= T) == new count.
+__device__ int warp_prune(unsigned long long* buf, int n, int kprime, int lane, unsigned long long& T) {
+  __syncwarp();
+  unsigned long long k[kCap / 32];
+#pragma unroll
+  for (int e = 0; e < kCap / 32; ++e) {
+    const int i = e * 32 + lane;
+    k[e] = i < n ? buf[i] : 0ull;
+  }
+  unsigned long long t = 0;
+  for (int bit = 63; bit >= 0; --bit) {
+    const unsigned long long cand = t | (1ull << bit);
+    int c = 0;
+#pragma unroll
+    for (int e = 0; e < kCap / 32; ++e) c += (k[e] >= cand);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if (c >= kprime) {
+      t = cand;
+      if (c == kprime) break;
+    }
+  }
+  int base = 0;
+  const unsigned lt = (1u << lane) - 1u;
+#pragma unroll
+  for (int e = 0; e < kCap / 32; ++e) {
+    const bool keep = k[e] >= t && k[e] != 0ull;
+    const unsigned m = __ballot_sync(0xffffffffu, keep);
+    if (keep) buf[base + __popc(m & lt)] = k[e];
+    base += __popc(m);
+  }
+  __syncwarp();
+  T = t;
+  return base;
+}
+
+__global__ void __launch_bounds__(kTopkThreads, 1)
+score_topk_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUtensorMap tmI,
+                  const TopkParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t pad = (1024u - (smem_u32(smem_raw) & 1023u)) & 1023u;
+  uint8_t* smem = smem_raw + pad;
+
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
+
+  uint8_t* sA = smem;                                   // [2 mt][4 kb] x 16 KB
+  uint8_t* sB = smem + 2 * kKB * kTile16K;              // kBStages x 16 KB
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + kBStages * kTile16K);
+  uint64_t* a_full = bars + 0;
+  uint64_t* a_empty = bars + 1;
+  uint64_t* b_full = bars + 2;
+  uint64_t* b_empty = b_full + kBStages;
+  uint64_t* t_full = b_empty + kBStages;
+  uint64_t* t_empty = t_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
+
+  if (warp == 0 && elect_one()) {
+    tma_prefetch_desc(&tmU);
+    tma_prefetch_desc(&tmI);
+  }
+  if (warp == 1 && elect_one()) {
+    mbar_init(a_full, 1);
+    mbar_init(a_empty, 1);
+    for (int s = 0; s < kBStages; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&t_full[a], 1); mbar_init(&t_empty[a], 8); }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int units = p.n_ut * p.n_ranges;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0, it = 0;
+      for (int unit = blockIdx.x; unit < units; unit += gridDim.x, ++it) {
+        const int ut = unit % p.n_ut, range = unit / p.n_ut;
+        mbar_wait(a_empty, (it & 1u) ^ 1u);
+        mbar_arrive_expect_tx(a_full, 2 * kKB * kTile16K);
+        for (int mt = 0; mt < 2; ++mt)
+          for (int kb = 0; kb < kKB; ++kb)
+            tma_load_2d(sA + (mt * kKB + kb) * kTile16K, &tmU, a_full, kb * 64, ut * kUT + mt * 128);
+        const int tile0 = range * p.tiles_per_range;
+        const int tile1 = min(p.total_tiles, tile0 + p.tiles_per_range);
+        for (int tile = tile0; tile < tile1; ++tile) {
+          for (int kb = 0; kb < kKB; ++kb) {
+            mbar_wait(&b_empty[stage], phase ^ 1u);
+            mbar_arrive_expect_tx(&b_full[stage], kTile16K);
+            tma_load_2d(sB + stage * kTile16K, &tmI, &b_full[stage], kb * 64, tile * kIT);
+            if (++stage == kBStages) { stage = 0; phase ^= 1u; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      const uint32_t idesc = umma_idesc_bf16(128, kIT, false, false);
+      int stage = 0, acc = 0;
+      uint32_t phase = 0, acc_phase = 0, it = 0;
+      for (int unit = blockIdx.x; unit < units; unit += gridDim.x, ++it) {
+        const int range = unit / p.n_ut;
+        const int tile0 = range * p.tiles_per_range;
+        const int tile1 = min(p.total_tiles, tile0 + p.tiles_per_range);
+        mbar_wait(a_full, it & 1u);
+        tc_fence_after();
+        for (int tile = tile0; tile < tile1; ++tile) {
+          mbar_wait(&t_empty[acc], acc_phase ^ 1u);
+          tc_fence_after();
+          for (int kb = 0; kb < kKB; ++kb) {
+            mbar_wait(&b_full[stage], phase);
+            tc_fence_after();
+            const uint32_t b_base = smem_u32(sB + stage * kTile16K);
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) {
+              const uint32_t a_base = smem_u32(sA + (mt * kKB + kb) * kTile16K);
+              const uint32_t d = tmem_base + static_cast<uint32_t>(acc * 256 + mt * 128);
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                umma_bf16(d, umma_desc_kmajor(a_base + k * 32), umma_desc_kmajor(b_base + k * 32), idesc,
+                          (kb > 0 || k > 0) ? 1u : 0u);
+            }
+            umma_commit(&b_empty[stage]);
+            if (++stage == kBStages) { stage = 0; phase ^= 1u; }
+          }
+          umma_commit(&t_full[acc]);
+          acc ^= 1;
+          if (acc == 0) acc_phase ^= 1u;
+        }
+        umma_commit(a_empty);  // the resident user tile may be replaced once these MMAs retire
+      }
+    }
+  } else if (warp >= 4) {
+    const int e = warp - 4;          // 0..7
+    const int mt = e >> 2, q = e & 3;  // q == warp % 4: TMEM lane quarter
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int unit = blockIdx.x; unit < units; unit += gridDim.x) {
+      const int ut = unit % p.n_ut, range = unit / p.n_ut;
+      const int tile0 = range * p.tiles_per_range;
+      const int tile1 = min(p.total_tiles, tile0 + p.tiles_per_range);
+      const int row = ut * kUT + mt * 128 + q * 32 + lane;
+      const bool active = row < p.U;
+      unsigned long long* buf = p.cand + (static_cast<size_t>(range) * p.u_pad + row) * kCap;
+      unsigned long long thr_key = active ? p.thr[row] : ~0ull;
+      float thr_s = thr_key == 0ull ? -INFINITY : (active ? key_score(thr_key) : INFINITY);
+      int cnt = 0;
+      for (int tile = tile0; tile < tile1; ++tile) {
+        mbar_wait(&t_full[acc], acc_phase);
+        __syncwarp();
+        tc_fence_after();
+        const uint32_t t_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
+                                static_cast<uint32_t>(acc * 256 + mt * 128);
+#pragma unroll 1
+        for (int c = 0; c < kIT / 32; ++c) {
+          uint32_t r[32];
+          tmem_ld32(t_base + c * 32, r);
+          tmem_ld_wait();
+          float mx = __uint_as_float(r[0]);
+#pragma unroll
+          for (int t = 1; t < 32; ++t) mx = fmaxf(mx, __uint_as_float(r[t]));
+          if (__any_sync(0xffffffffu, mx >= thr_s)) {
+            const int idx0 = tile * kIT + c * 32;  // shard-local item index of r[0]
+#pragma unroll
+            for (int t = 0; t < 32; ++t) {
+              const float s = __uint_as_float(r[t]);
+              if (s >= thr_s) {
+                const int idx = idx0 + t;
+                const uint32_t gidx = static_cast<uint32_t>(p.item_base + idx);
+                if (idx < p.N && !(p.mask_item0 && gidx == 0u)) {
+                  const unsigned long long key = make_key(s, gidx);
+                  if (key > thr_key) buf[cnt++] = key;
+                }
+              }
+            }
+            unsigned full = __ballot_sync(0xffffffffu, cnt > kCap - 32);
+            while (full) {
+              const int src = __ffs(full) - 1;
+              full &= full - 1;
+              const unsigned long long bsrc =
+                  __shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(buf), src);
+              const int nsrc = __shfl_sync(0xffffffffu, cnt, src);
+              unsigned long long T;
+              const int ncnt = warp_prune(reinterpret_cast<unsigned long long*>(bsrc), nsrc, p.kprime, lane, T);
+              if (lane == src) {
+                cnt = ncnt;
+                thr_key = T;
+                thr_s = key_score(T);
+                atomicMax(p.thr + row, T);
+              }
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&t_empty[acc]);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1u;
+      }
+      p.cand_cnt[static_cast<size_t>(range) * p.u_pad + row] = active ? cnt : 0;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
+// --------------------------------------------------------------------------------------------
+// Finalize: one block (256 threads) per user.
+// --------------------------------------------------------------------------------------------
+struct FinalizeParams {
+  int U, N, item_base, n_ranges, u_pad, kprime, K;
+  const unsigned long long* cand;
+  const int* cand_cnt;
+  const float* users;   // [U, 256] fp32
+  const float* items;   // [N, 256] fp32 (this shard)
+  float eps;            // bound on |bf16-path score - exact score|
+  int* out_idx;         // [U, K] global item index, -1 padded
+  float* out_score;     // [U, K]
+  int* flags;           // [U] 1 = certificate failed (fallback needed)
+};
+
+__device__ __forceinline__ int block_sum_int(int v, int* s_red) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  int t = 0;
+  for (int w = 0; w < static_cast<int>(blockDim.x >> 5); ++w) t += s_red[w];
+  __syncthreads();
+  return t;
+}
+
+// Bitonic sort (descending) of 256 keys in shared memory by 256 threads.
+__device__ __forceinline__ void bitonic_sort_desc_256(unsigned long long* keys) {
+  const int i = threadIdx.x;
+  for (int size = 2; size <= 256; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      __syncthreads();
+      const int j = i ^ stride;
+      if (j > i) {
+        const unsigned long long a = keys[i], b = keys[j];
+        const bool desc = ((i & size) == 0);
+        if (desc ? (a < b) : (a > b)) { keys[i] = b; keys[j] = a; }
+      }
+    }
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(256) topk_finalize_kernel(const FinalizeParams p) {
+  __shared__ unsigned long long s_keys[256];
+  __shared__ unsigned long long s_sel[256];
+  __shared__ int s_red[8];
+  __shared__ int s_n;
+  const int u = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+  // total number of candidate keys of this user
+  int total = 0;
+  for (int r = 0; r < p.n_ranges; ++r) total += p.cand_cnt[static_cast<size_t>(r) * p.u_pad + u];
+
+  // K'-th largest key over all ranges (bitwise binary search, counts re-read from L2)
+  unsigned long long T = 0;
+  if (total > p.kprime) {
+    for (int bit = 63; bit >= 0; --bit) {
+      const unsigned long long cand = T | (1ull << bit);
+      int c = 0;
+      for (int r = 0; r < p.n_ranges; ++r) {
+        const int n = p.cand_cnt[static_cast<size_t>(r) * p.u_pad + u];
+        const unsigned long long* b = p.cand + (static_cast<size_t>(r) * p.u_pad + u) * kCap;
+        for (int i = tid; i < n; i += 256) c += (b[i] >= cand);
+      }
+      c = block_sum_int(c, s_red);
+      if (c >= p.kprime) {
+        T = cand;
+        if (c == p.kprime) break;
+      }
+    }
+  }
+  // compaction of keys >= T into s_sel (order irrelevant: re-sorted after the exact re-score)
+  if (tid == 0) s_n = 0;
+  s_keys[tid] = 0ull;
+  __syncthreads();
+  for (int r = 0; r < p.n_ranges; ++r) {
+    const int n = p.cand_cnt[static_cast<size_t>(r) * p.u_pad + u];
+    const unsigned long long* b = p.cand + (static_cast<size_t>(r) * p.u_pad + u) * kCap;
+    for (int i = tid; i < n; i += 256) {
+      const unsigned long long k = b[i];
+      if (k >= T) {
+        const int pos = atomicAdd(&s_n, 1);
+        if (pos < 256) s_sel[pos] = k;
+      }
+    }
+  }
+  __syncthreads();
+  const int nsel = min(s_n, 256);
+
+  // exact re-score: fp32 inputs, fp64 accumulate, one rounding to fp32
+  const float* urow = p.users + static_cast<size_t>(u) * kD;
+  float uf[8];
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const float4 x = __ldg(reinterpret_cast<const float4*>(urow) + k * 32 + lane);
+    uf[4 * k] = x.x; uf[4 * k + 1] = x.y; uf[4 * k + 2] = x.z; uf[4 * k + 3] = x.w;
+  }
+  for (int cidx = warp; cidx < nsel; cidx += 8) {
+    const uint32_t gidx = key_idx(s_sel[cidx]);
+    const float* irow = p.items + static_cast<size_t>(gidx - p.item_base) * kD;
+    double acc = 0.0;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const float4 x = __ldg(reinterpret_cast<const float4*>(irow) + k * 32 + lane);
+      acc += static_cast<double>(uf[4 * k]) * x.x + static_cast<double>(uf[4 * k + 1]) * x.y +
+             static_cast<double>(uf[4 * k + 2]) * x.z + static_cast<double>(uf[4 * k + 3]) * x.w;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) s_keys[cidx] = make_key(static_cast<float>(acc), gidx);
+  }
+  __syncthreads();
+  bitonic_sort_desc_256(s_keys);
+
+  for (int k = tid; k < p.K; k += 256) {
+    const bool ok = k < nsel;
+    p.out_idx[static_cast<size_t>(u) * p.K + k] = ok ? static_cast<int>(key_idx(s_keys[k])) : -1;
+    p.out_score[static_cast<size_t>(u) * p.K + k] = ok ? key_score(s_keys[k]) : -INFINITY;
+  }
+  if (tid == 0) {
+    // Certificate: every non-candidate has bf16-path key < T, hence exact score <= score(T) + eps.
+    // If the exact K-th best beats that, no non-candidate can enter the top K.
+    int flag = 0;
+    if (total > p.kprime) {
+      const int kth = min(p.K, nsel) - 1;
+      flag = !(key_score(s_keys[kth]) > key_score(T) + p.eps);
+    }
+    p.flags[u] = flag;
+  }
+}
+
+// --------------------------------------------------------------------------------------------
+// Cross-shard merge: lists [G][U][K] of (score, global idx) sorted canonically per shard ->
+// top K of their union, canonical order. One block per user; G*K <= 1024.
+// --------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) topk_merge_kernel(const float* __restrict__ scores, const int* __restrict__ idx,
+                                                         int G, int U, int K, float* __restrict__ out_score,
+                                                         int* __restrict__ out_idx) {
+  extern __shared__ unsigned long long s_all[];  // G*K keys
+  const int u = blockIdx.x;
+  const int n = G * K;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int g = i / K, k = i % K;
+    const size_t o = (static_cast<size_t>(g) * U + u) * K + k;
+    const int id = idx[o];
+    s_all[i] = id < 0 ? 0ull : make_key(scores[o], static_cast<uint32_t>(id));
+  }
+  __syncthreads();
+  // rank by counting: keys are unique (distinct items), n is small
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const unsigned long long k = s_all[i];
+    if (k == 0ull) continue;
+    int rank = 0;
+    for (int j = 0; j < n; ++j) rank += (s_all[j] > k);
+    if (rank < K) {
+      out_score[static_cast<size_t>(u) * K + rank] = key_score(k);
+      out_idx[static_cast<size_t>(u) * K + rank] = static_cast<int>(key_idx(k));
+    }
+  }
+}
+
+// --------------------------------------------------------------------------------------------
+// Exact fallback for users whose certificate failed: brute-force fp64-accumulated scores over
+// the whole shard into a key array, then K-th largest by bitwise search + sort. Slow and rare.
+// --------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) exact_keys_kernel(const float* __restrict__ user, const float* __restrict__ items,
+                                                         int N, int item_base, int mask_item0,
+                                                         unsigned long long* __restrict__ keys) {
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  float uf[8];
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const float4 x = __ldg(reinterpret_cast<const float4*>(user) + k * 32 + lane);
+    uf[4 * k] = x.x; uf[4 * k + 1] = x.y; uf[4 * k + 2] = x.z; uf[4 * k + 3] = x.w;
+  }
+  for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < N; i += warps) {
+    const float* irow = items + static_cast<size_t>(i) * kD;
+    double acc = 0.0;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const float4 x = __ldg(reinterpret_cast<const float4*>(irow) + k * 32 + lane);
+      acc += static_cast<double>(uf[4 * k]) * x.x + static_cast<double>(uf[4 * k + 1]) * x.y +
+             static_cast<double>(uf[4 * k + 2]) * x.z + static_cast<double>(uf[4 * k + 3]) * x.w;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) {
+      const uint32_t gidx = static_cast<uint32_t>(item_base + i);
+      keys[i] = (mask_item0 && gidx == 0u) ? 0ull : make_key(static_cast<float>(acc), gidx);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) exact_select_kernel(const unsigned long long* __restrict__ keys, int N, int K,
+                                                           float* __restrict__ out_score, int* __restrict__ out_idx) {
+  __shared__ unsigned long long s_keys[256];
+  __shared__ int s_red[8];
+  __shared__ int s_n;
+  const int tid = threadIdx.x;
+  unsigned long long T = 0;
+  const int want = min(K, 256);
+  for (int bit = 63; bit >= 0; --bit) {
+    const unsigned long long cand = T | (1ull << bit);
+    int c = 0;
+    for (int i = tid; i < N; i += 256) c += (keys[i] >= cand);
+    c = block_sum_int(c, s_red);
+    if (c >= want) {
+      T = cand;
+      if (c == want) break;
+    }
+  }
+  if (tid == 0) s_n = 0;
+  s_keys[tid] = 0ull;
+  __syncthreads();
+  for (int i = tid; i < N; i += 256) {
+    const unsigned long long k = keys[i];
+    if (k >= T && k != 0ull) {
+      const int pos = atomicAdd(&s_n, 1);
+      if (pos < 256) s_keys[pos] = k;
+    }
+  }
+  __syncthreads();
+  const int nsel = min(s_n, 256);
+  bitonic_sort_desc_256(s_keys);
+  for (int k = tid; k < K; k += 256) {
+    const bool ok = k < nsel;
+    out_idx[k] = ok ? static_cast<int>(key_idx(s_keys[k])) : -1;
+    out_score[k] = ok ? key_score(s_keys[k]) : -INFINITY;
+  }
+}
+
+// --------------------------------------------------------------------------------------------
+// Recall@k / NDCG@k per row (src/evaluate_metrics.py:159-185). gain_table[r] = 1/log2(r+2) is
+// supplied by the host (computed with the same fp32 torch ops as the reference) so the per-row
+// values are bit-identical; the host then takes the mean exactly like the reference.
+// --------------------------------------------------------------------------------------------
+__global__ void rank_metrics_kernel(const int* __restrict__ topk, const int64_t* __restrict__ targets, int U, int K,
+                                    const int* __restrict__ k_list, int nk, const float* __restrict__ gain_table,
+                                    float* __restrict__ recall, float* __restrict__ ndcg) {
+  const int u = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (u >= U) return;
+  const int target = static_cast<int>(targets[u]);
+  int rank = K;  // first position where the target appears
+  for (int i = lane; i < K; i += 32)
+    if (topk[static_cast<size_t>(u) * K + i] == target) rank = min(rank, i);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) rank = min(rank, __shfl_xor_sync(0xffffffffu, rank, o));
+  for (int j = lane; j < nk; j += 32) {
+    const bool hit = rank < k_list[j];
+    recall[static_cast<size_t>(j) * U + u] = hit ? 1.f : 0.f;
+    ndcg[static_cast<size_t>(j) * U + u] = hit ? gain_table[rank] : 0.f;
+  }
+}
+
+}  // namespace tt
+
+using namespace tt;
+
+extern "C" int tt_topk_plan_make(int U, int N, int kprime, tt_topk_plan* plan) {
+  TT_REQUIRE(plan && U > 0 && N > 0, "tt_topk_plan_make: bad arguments");
+  TT_REQUIRE(kprime >= 8 && kprime <= 256, "tt_topk_plan_make: kprime %d outside [8, 256]", kprime);
+  plan->U = U; plan->N = N; plan->kprime = kprime; plan->cap = kCap;
+  plan->n_ut = (U + kUT - 1) / kUT;
+  const int total_tiles = (N + kIT - 1) / kIT;
+  int n_ranges = (4 * num_sms() + plan->n_ut - 1) / plan->n_ut;
+  const int max_ranges = (total_tiles + 15) / 16;  // at least 16 item tiles per range
+  if (n_ranges > max_ranges) n_ranges = max_ranges;
+  if (n_ranges < 1) n_ranges = 1;
+  plan->tiles_per_range = (total_tiles + n_ranges - 1) / n_ranges;
+  plan->n_ranges = (total_tiles + plan->tiles_per_range - 1) / plan->tiles_per_range;
+  const int64_t u_pad = static_cast<int64_t>(plan->n_ut) * kUT;
+  plan->cand_bytes = static_cast<int64_t>(plan->n_ranges) * u_pad * kCap * 8;
+  plan->cnt_bytes = static_cast<int64_t>(plan->n_ranges) * u_pad * 4;
+  plan->thr_bytes = u_pad * 8;
+  return TT_OK;
+}
+
+extern "C" int tt_score_topk(const void* users_bf16, const void* items_bf16, int item_base, const tt_topk_plan* plan,
+                             void* cand, int32_t* cand_cnt, void* thr, int mask_item0, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  TT_REQUIRE(users_bf16 && items_bf16 && plan && cand && cand_cnt && thr, "tt_score_topk: null pointer");
+  TopkParams p;
+  p.U = plan->U; p.N = plan->N; p.item_base = item_base;
+  p.n_ut = plan->n_ut; p.n_ranges = plan->n_ranges; p.tiles_per_range = plan->tiles_per_range;
+  p.total_tiles = (plan->N + kIT - 1) / kIT;
+  p.kprime = plan->kprime;
+  p.u_pad = plan->n_ut * kUT;
+  p.cand = static_cast<unsigned long long*>(cand);
+  p.cand_cnt = cand_cnt;
+  p.thr = static_cast<unsigned long long*>(thr);
+  p.mask_item0 = mask_item0;
+  TT_CHECK_CUDA(cudaMemsetAsync(thr, 0, static_cast<size_t>(plan->thr_bytes), stream));
+  CUtensorMap tmU, tmI;
+  {
+    uint64_t dims[2] = {kD, static_cast<uint64_t>(plan->U)};
+    uint64_t str[1] = {kD * 2};
+    uint32_t box[2] = {64, 128};
+    int rc = make_tmap_bf16(&tmU, users_bf16, 2, dims, str, box);
+    if (rc) return rc;
+  }
+  {
+    uint64_t dims[2] = {kD, static_cast<uint64_t>(plan->N)};
+    uint64_t str[1] = {kD * 2};
+    uint32_t box[2] = {64, 128};
+    int rc = make_tmap_bf16(&tmI, items_bf16, 2, dims, str, box);
+    if (rc) return rc;
+  }
+  const size_t smem = 1024 + (2 * kKB + kBStages) * kTile16K + 256;
+  static bool configured = false;
+  if (!configured) {
+    TT_CHECK_CUDA(cudaFuncSetAttribute(score_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    configured = true;
+  }
+  const int units = p.n_ut * p.n_ranges;
+  const int grid = units < num_sms() ? units : num_sms();
+  score_topk_kernel<<<grid, kTopkThreads, smem, stream>>>(tmU, tmI, p);
+  TT_LAUNCH_CHECK();
+  return TT_OK;
+}
+
+extern "C" int tt_topk_finalize(const tt_topk_plan* plan, const void* cand, const int32_t* cand_cnt,
+                                const float* users_f32, const float* items_f32, int item_base, int K, float eps,
+                                int32_t* out_idx, float* out_score, int32_t* flags, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  TT_REQUIRE(plan && cand && cand_cnt && users_f32 && items_f32 && out_idx && out_score && flags,
+             "tt_topk_finalize: null pointer");
+  TT_REQUIRE(K > 0 && K <= plan->kprime, "tt_topk_finalize: K=%d must be in [1, kprime=%d]", K, plan->kprime);
+  FinalizeParams p;
+  p.U = plan->U; p.N = plan->N; p.item_base = item_base; p.n_ranges = plan->n_ranges;
+  p.u_pad = plan->n_ut * kUT; p.kprime = plan->kprime; p.K = K;
+  p.cand = static_cast<const unsigned long long*>(cand);
+  p.cand_cnt = cand_cnt; p.users = users_f32; p.items = items_f32; p.eps = eps;
+  p.out_idx = out_idx; p.out_score = out_score; p.flags = flags;
+  topk_finalize_kernel<<<plan->U, 256, 0, stream>>>(p);
+  TT_LAUNCH_CHECK();
+  return TT_OK;
+}
+
+extern "C" int tt_topk_merge(const float* scores, const int32_t* idx, int G, int U, int K, float* out_score,
+                             int32_t* out_idx, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  TT_REQUIRE(scores && idx && out_score && out_idx && G > 0 && U > 0 && K > 0, "tt_topk_merge: bad arguments");
+  TT_REQUIRE(G * K <= 4096, "tt_topk_merge: G*K = %d too large", G * K);
+  topk_merge_kernel<<<U, 256, static_cast<size_t>(G) * K * 8, stream>>>(scores, idx, G, U, K, out_score, out_idx);
+  TT_LAUNCH_CHECK();
+  return TT_OK;
+}
+
+extern "C" int tt_exact_topk(const float* user_f32, const float* items_f32, int N, int item_base, int mask_item0,
+                             int K, void* key_scratch, float* out_score, int32_t* out_idx, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  TT_REQUIRE(user_f32 && items_f32 && key_scratch && out_score && out_idx && N > 0 && K > 0 && K <= 256,
+             "tt_exact_topk: bad arguments");
+  int grid = (N + 7) / 8;
+  if (grid > num_sms() * 8) grid = num_sms() * 8;
+  exact_keys_kernel<<<grid, 256, 0, stream>>>(user_f32, items_f32, N, item_base, mask_item0,
+                                              static_cast<unsigned long long*>(key_scratch));
+  TT_LAUNCH_CHECK();
+  exact_select_kernel<<<1, 256, 0, stream>>>(static_cast<const unsigned long long*>(key_scratch), N, K, out_score,
+                                             out_idx);
+  TT_LAUNCH_CHECK();
+  return TT_OK;
+}
+
+extern "C" int tt_rank_metrics(const int32_t* topk_idx, const int64_t* targets, int U, int K, const int32_t* k_list,
+                               int nk, const float* gain_table, float* recall, float* ndcg, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  TT_REQUIRE(topk_idx && targets && k_list && gain_table && recall && ndcg && U > 0 && K > 0 && nk > 0,
+             "tt_rank_metrics: bad arguments");
+  rank_metrics_kernel<<<(U * 32 + 255) / 256, 256, 0, stream>>>(topk_idx, targets, U, K, k_list, nk, gain_table,
+                                                               recall, ndcg);
+  TT_LAUNCH_CHECK();
+  return TT_OK;
+}

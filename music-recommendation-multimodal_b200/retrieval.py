@@ -1,0 +1,159 @@
+"""Catalog retrieval on the B200: fused scoring + streaming top-K, exact re-score, canonical
+order, Recall@K / NDCG@K — the device side of the reference's ``calculate_metrics_global``
+(src/evaluate_metrics.py:106-192) and of its item-embedding cache (:92-104, 323-326).
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import ops
+from ._lib import TopkPlan, check, lib
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+class CatalogIndex:
+    """Device-resident item table in the reference's cache layout: fp32 (V, 256), row i = embedding
+    of item id i, row 0 = padding. ``shard`` = (first_row, num_rows) keeps only a contiguous slice
+    on this GPU (catalog sharding); indices returned by retrieval are always global."""
+
+    def __init__(self, item_embeddings: torch.Tensor, device=None, shard: Optional[Tuple[int, int]] = None):
+        dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        V = item_embeddings.shape[0]
+        first, rows = (0, V) if shard is None else shard
+        self.vocab_size = V
+        self.item_base = first
+        self.table = item_embeddings[first:first + rows].to(device=dev, dtype=torch.float32).contiguous()
+        assert self.table.shape[1] == 256
+        self.table_bf16 = torch.empty(self.table.shape, device=dev, dtype=torch.bfloat16)
+        ops.cast_bf16(self.table.view(-1), self.table_bf16.view(-1))
+        # terms of the error bound |bf16-path score - exact score| that depend on the items only
+        t16 = self.table_bf16.float()
+        self.de_max = (t16 - self.table).norm(dim=1).max().item()
+        self.ne_max = t16.norm(dim=1).max().item()
+        self._scratch: Dict[Tuple[int, int], Dict[str, torch.Tensor]] = {}
+        self._plans: Dict[Tuple[int, int], TopkPlan] = {}
+
+    @property
+    def num_rows(self) -> int:
+        return self.table.shape[0]
+
+    def plan(self, U: int, kprime: int) -> TopkPlan:
+        key = (U, kprime)
+        if key not in self._plans:
+            p = TopkPlan()
+            check(lib().tt_topk_plan_make(U, self.num_rows, kprime, ctypes.byref(p)), "tt_topk_plan_make")
+            self._plans[key] = p
+            dev = self.table.device
+            self._scratch[key] = {
+                "cand": torch.empty(p.cand_bytes // 8, device=dev, dtype=torch.int64),
+                "cnt": torch.empty(p.cnt_bytes // 4, device=dev, dtype=torch.int32),
+                "thr": torch.empty(p.thr_bytes // 8, device=dev, dtype=torch.int64),
+                "users_bf16": torch.empty(U, 256, device=dev, dtype=torch.bfloat16),
+                "keys": None,
+            }
+        return self._plans[key]
+
+
+def retrieve_topk(user_emb: torch.Tensor, index: CatalogIndex, K: int, kprime: int = 256,
+                  mask_item0: bool = True, exact_fallback: bool = True):
+    """Top-K items of this shard for every user, canonical order.
+
+    Returns (idx int32 (U, K) global item ids, score fp32 (U, K), n_fallback). Scores are the
+    exact fp32 dot products (fp64-accumulated, rounded once). Users whose exactness certificate
+    fails are recomputed by brute force (``n_fallback`` of them; needs one host sync)."""
+    assert user_emb.is_cuda and user_emb.dtype == torch.float32 and user_emb.shape[1] == 256
+    user_emb = user_emb.contiguous()
+    U = user_emb.shape[0]
+    kprime = max(kprime, K)
+    plan = index.plan(U, kprime)
+    sc = index._scratch[(U, kprime)]
+    ops.cast_bf16(user_emb.view(-1), sc["users_bf16"].view(-1))
+    check(lib().tt_score_topk(sc["users_bf16"].data_ptr(), index.table_bf16.data_ptr(), index.item_base,
+                              ctypes.byref(plan), sc["cand"].data_ptr(), sc["cnt"].data_ptr(), sc["thr"].data_ptr(),
+                              int(mask_item0), _stream()), "tt_score_topk")
+    # rigorous bound on |u^.e^ - u.e| (Cauchy-Schwarz on the bf16 rounding errors) + fp32 accumulation slack
+    u16 = sc["users_bf16"].float()
+    du = (u16 - user_emb).norm(dim=1).max()
+    nu = user_emb.norm(dim=1).max()
+    eps = float((du * index.ne_max + nu * index.de_max + nu * index.ne_max * 2.0 ** -18).item())
+    dev = user_emb.device
+    out_idx = torch.empty(U, K, device=dev, dtype=torch.int32)
+    out_score = torch.empty(U, K, device=dev, dtype=torch.float32)
+    flags = torch.empty(U, device=dev, dtype=torch.int32)
+    check(lib().tt_topk_finalize(ctypes.byref(plan), sc["cand"].data_ptr(), sc["cnt"].data_ptr(), user_emb.data_ptr(),
+                                 index.table.data_ptr(), index.item_base, K, eps, out_idx.data_ptr(),
+                                 out_score.data_ptr(), flags.data_ptr(), _stream()), "tt_topk_finalize")
+    n_fallback = 0
+    if exact_fallback:
+        bad = torch.nonzero(flags).flatten().tolist()
+        n_fallback = len(bad)
+        if bad:
+            if sc["keys"] is None:
+                sc["keys"] = torch.empty(index.num_rows, device=dev, dtype=torch.int64)
+            for u in bad:
+                check(lib().tt_exact_topk(user_emb[u].data_ptr(), index.table.data_ptr(), index.num_rows,
+                                          index.item_base, int(mask_item0), K, sc["keys"].data_ptr(),
+                                          out_score[u].data_ptr(), out_idx[u].data_ptr(), _stream()), "tt_exact_topk")
+    return out_idx, out_score, n_fallback
+
+
+def merge_topk(scores: torch.Tensor, idx: torch.Tensor):
+    """Merge per-shard lists [G, U, K] (each canonical) into the global top-K per user."""
+    G, U, K = scores.shape
+    scores, idx = scores.contiguous(), idx.contiguous()
+    out_s = torch.empty(U, K, device=scores.device, dtype=torch.float32)
+    out_i = torch.empty(U, K, device=scores.device, dtype=torch.int32)
+    check(lib().tt_topk_merge(scores.data_ptr(), idx.data_ptr(), G, U, K, out_s.data_ptr(), out_i.data_ptr(),
+                              _stream()), "tt_topk_merge")
+    return out_i, out_s
+
+
+def gain_table(K: int) -> torch.Tensor:
+    """1/log2(rank+2) exactly as the reference computes it (fp32 torch ops, evaluate_metrics.py:180)."""
+    return 1.0 / torch.log2(torch.arange(K).float() + 2.0)
+
+
+def rank_metrics(topk_idx: torch.Tensor, targets: torch.Tensor, k_list: Sequence[int]):
+    """Per-row Recall@k / NDCG@k on the device -> (recall [nk, U], ndcg [nk, U]) fp32."""
+    U, K = topk_idx.shape
+    dev = topk_idx.device
+    kl = torch.tensor(list(k_list), dtype=torch.int32, device=dev)
+    gt = gain_table(K).to(dev)
+    recall = torch.empty(len(k_list), U, device=dev)
+    ndcg = torch.empty(len(k_list), U, device=dev)
+    check(lib().tt_rank_metrics(topk_idx.data_ptr(), targets.contiguous().data_ptr(), U, K, kl.data_ptr(),
+                                len(k_list), gt.data_ptr(), recall.data_ptr(), ndcg.data_ptr(), _stream()),
+          "tt_rank_metrics")
+    return recall, ndcg
+
+
+def metrics_from_embeddings(user_emb: torch.Tensor, targets: torch.Tensor, index: CatalogIndex,
+                            k_list: Sequence[int] = (10, 20), kprime: int = 256,
+                            group=None) -> Dict[str, float]:
+    """Recall@k / NDCG@k of precomputed user embeddings against the (possibly sharded) catalog.
+    With a process group, every rank scores its shard and the per-shard top-K lists are
+    all-gathered and merged (result independent of the number of shards)."""
+    import torch.distributed as dist
+    K = max(k_list)
+    idx, score, _ = retrieve_topk(user_emb, index, K, kprime)
+    if group is not None or (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+        ws = dist.get_world_size(group)
+        all_s = torch.empty(ws, *score.shape, device=score.device, dtype=score.dtype)
+        all_i = torch.empty(ws, *idx.shape, device=idx.device, dtype=idx.dtype)
+        dist.all_gather_into_tensor(all_s, score, group=group)
+        dist.all_gather_into_tensor(all_i, idx, group=group)
+        idx, score = merge_topk(all_s, all_i)
+    recall, ndcg = rank_metrics(idx, targets.to(idx.device), k_list)
+    r, n = recall.cpu(), ndcg.cpu()     # the mean is taken on the host exactly like the reference (:188-190)
+    out = {}
+    for j, k in enumerate(k_list):
+        out[f"Recall@{k}"] = r[j].mean().item()
+    for j, k in enumerate(k_list):
+        out[f"NDCG@{k}"] = n[j].mean().item()
+    return out

@@ -1,0 +1,144 @@
+"""Catalog retrieval (fused scoring + streaming top-K + exact re-score) against the reference.
+
+Bit-exactness contract: canonical order = (score desc, item index asc).
+ (a) grid fixtures: every dot product is exact in any precision/order -> indices must equal the
+     reference-derived golden lists bit for bit (thousands of ties on the coarse grid);
+ (b) generic float fixture: our scores are the correctly rounded fp32 dot products, the reference's
+     are fp32 SGEMM sums; lists must agree except where two scores differ by <= 2 ulp, and
+     Recall@K / NDCG@K must be bit-identical to the reference's.
+"""
+import os
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _fixture(name):
+    from mrm_b200 import synthetic
+    gold = torch.load(os.path.join(GOLDEN, name), weights_only=False)
+    table = synthetic.make_catalog(gold["num_items"], 256, seed=gold["seed"], grid=gold["grid"])
+    users, targets = synthetic.make_queries(table, gold["num_users"], seed=gold["seed"] + 1, noise=gold["noise"],
+                                            grid=gold["grid"])
+    return gold, table, users, targets
+
+
+@pytest.mark.parametrize("name", ["retrieval_grid.pt", "retrieval_grid_coarse.pt"])
+def test_topk_bit_exact_on_grid_fixtures(name):
+    from mrm_b200 import retrieval
+    gold, table, users, targets = _fixture(name)
+    index = retrieval.CatalogIndex(table)
+    K = max(gold["k_list"])
+    idx, score, nfb = retrieval.retrieve_topk(users.cuda(), index, K)
+    torch.cuda.synchronize()
+    assert torch.equal(idx.cpu(), gold["topk_idx"]), "top-K indices differ from the reference"
+    assert torch.equal(score.cpu(), gold["topk_val"]), "scores differ from the reference"
+    m = retrieval.metrics_from_embeddings(users.cuda(), targets.cuda(), index, gold["k_list"])
+    if name == "retrieval_grid.pt":
+        for k, v in gold["metrics"].items():
+            assert m[k] == v, (k, m[k], v)
+
+
+def test_topk_float_fixture_and_metrics_bit_identical():
+    from mrm_b200 import retrieval
+    gold, table, users, targets = _fixture("retrieval_float.pt")
+    index = retrieval.CatalogIndex(table)
+    K = max(gold["k_list"])
+    idx, score, nfb = retrieval.retrieve_topk(users.cuda(), index, K)
+    torch.cuda.synchronize()
+    idx, score = idx.cpu(), score.cpu()
+    ref_idx, ref_val = gold["topk_idx"], gold["topk_val"]
+    mism = idx != ref_idx
+    # any positional mismatch must sit inside a <= 2 ulp score gap (fp32 summation-order noise)
+    if mism.any():
+        gap = (score - ref_val).abs()[mism]
+        ulp = torch.finfo(torch.float32).eps * ref_val.abs()[mism]
+        assert (gap <= 2 * ulp + 1e-9).all(), gap.max()
+        assert mism.float().mean().item() < 0.01
+    assert (score - ref_val).abs().max().item() <= 2e-7
+    m = retrieval.metrics_from_embeddings(users.cuda(), targets.cuda(), index, gold["k_list"])
+    for k, v in gold["metrics"].items():
+        assert m[k] == v, (k, m[k], v)
+
+
+def test_sharded_equals_unsharded_and_merge():
+    """Catalog split into 3 shards (as on 3 GPUs), per-shard top-K merged == single-shard result."""
+    from mrm_b200 import retrieval
+    gold, table, users, targets = _fixture("retrieval_grid_coarse.pt")
+    K = 100
+    full, _, _ = retrieval.retrieve_topk(users.cuda(), retrieval.CatalogIndex(table), K)
+    V = table.shape[0]
+    cuts = [0, 1700, 3333, V]
+    parts_i, parts_s = [], []
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        shard = retrieval.CatalogIndex(table, shard=(a, b - a))
+        i, s, _ = retrieval.retrieve_topk(users.cuda(), shard, K)
+        parts_i.append(i)
+        parts_s.append(s)
+    mi, ms = retrieval.merge_topk(torch.stack(parts_s), torch.stack(parts_i))
+    torch.cuda.synchronize()
+    assert torch.equal(mi, full)
+    assert torch.equal(mi.cpu(), gold["topk_idx"])
+
+
+def test_exact_fallback_path_agrees():
+    from mrm_b200 import retrieval
+    from mrm_b200._lib import check, lib
+    gold, table, users, targets = _fixture("retrieval_float.pt")
+    index = retrieval.CatalogIndex(table)
+    K = 50
+    idx, score, _ = retrieval.retrieve_topk(users.cuda(), index, K)
+    u = users.cuda()
+    keys = torch.empty(index.num_rows, device="cuda", dtype=torch.int64)
+    for row in (0, 7, 191):
+        oi = torch.empty(K, device="cuda", dtype=torch.int32)
+        os_ = torch.empty(K, device="cuda")
+        check(lib().tt_exact_topk(u[row].data_ptr(), index.table.data_ptr(), index.num_rows, 0, 1, K,
+                                  keys.data_ptr(), os_.data_ptr(), oi.data_ptr(),
+                                  torch.cuda.current_stream().cuda_stream), "tt_exact_topk")
+        torch.cuda.synchronize()
+        assert torch.equal(oi, idx[row])
+        assert torch.equal(os_, score[row])
+
+
+def test_large_catalog_properties():
+    """200k items x 1500 users (not a multiple of any tile): against an fp64 torch scoring of the
+    same inputs — identical index sets, sorted output, item 0 never returned, certificate holds."""
+    from mrm_b200 import retrieval, synthetic
+    N, U, K = 200_000, 1500, 100
+    table = synthetic.make_catalog(N, 256, seed=77)
+    users, targets = synthetic.make_queries(table, U, seed=78, noise=3.0)
+    index = retrieval.CatalogIndex(table)
+    idx, score, nfb = retrieval.retrieve_topk(users.cuda(), index, K)
+    torch.cuda.synchronize()
+    assert nfb == 0
+    assert (idx > 0).all() and (idx <= N).all()
+    assert (score[:, 1:] <= score[:, :-1]).all()
+    ref = (users.cuda().double() @ table.cuda().double().t())
+    ref[:, 0] = -float("inf")
+    rv, ri = torch.sort(ref, dim=1, descending=True, stable=True)
+    ri, rv = ri[:, :K].int(), rv[:, :K].float()
+    same = (idx == ri)
+    assert same.float().mean().item() > 0.999
+    assert (score - rv).abs().max().item() <= 1e-6
+    # membership: every returned item scores at least the fp64 K-th value minus rounding
+    kth = rv[:, -1:]
+    assert (score >= kth - 1e-6).all()
+
+
+def test_rank_metrics_kernel():
+    from mrm_b200 import retrieval
+    from oracle import two_tower_oracle as oracle
+    g = torch.Generator().manual_seed(5)
+    U, K = 333, 100
+    topk = torch.stack([torch.randperm(1000, generator=g)[:K] for _ in range(U)]).int()
+    targets = torch.where(torch.rand(U, generator=g) < 0.6, topk[torch.arange(U), torch.randint(0, K, (U,), generator=g)].long(),
+                          torch.full((U,), 5000))
+    r, n = retrieval.rank_metrics(topk.cuda(), targets.cuda(), [10, 20, 50, 100])
+    ref = oracle.rank_metrics(topk.long(), targets, [10, 20, 50, 100])
+    for j, k in enumerate([10, 20, 50, 100]):
+        assert torch.equal(r[j].cpu(), ref[f"Recall@{k}"])
+        assert torch.equal(n[j].cpu(), ref[f"NDCG@{k}"])
