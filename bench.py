@@ -1,0 +1,383 @@
+#!/usr/bin/env python
+"""Benchmark of the two-tower hot path on B200 (one JSON line on rank 0).
+
+Headline metric (BASELINE.json configs[1]): two-tower train samples/sec — one step = forward +
+backward + InfoNCE + dense AdamW on batch 256/GPU, seq len 200, 100k-item ID table, dropout 0.1,
+all histories full length, synthetic precomputed modality embeddings.
+  value : device-resident inputs, the whole step replayed as one CUDA graph, CUDA-event timing.
+  e2e   : through the public train_one_epoch-style call with HOST (pinned) batches: H2D of every
+          step's batch and D2H of its loss inside the timed region.
+  roofline     : the tcgen05 GEMM (dominant kernel): algorithmic FLOPs / event-timed duration of
+                 the step's own GEMM launches, against MEASURED_PEAKS.json bf16 sustained.
+  cpu_baseline : the oracle port of the reference step on this box's host cores (bounded sample).
+  retrieval    : evaluate_metrics workload (BASELINE.json configs[2]): 10k users x 1M items,
+                 top-100 + Recall/NDCG, catalog sharded over the N GPUs.
+`--impl reference` times the reference's CPU implementation (oracle port) for the same metric.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+C2 = dict(batch=256, seq_len=200, vocab=100_001)      # BASELINE.json configs[1]
+C3 = dict(users=10_000, items=1_000_000, k=100, hist_len=50)  # BASELINE.json configs[2]
+CPU_SAMPLE_BATCH = 64
+
+
+def flops_per_sample_fwd(L, B_neg, D=256, FF=1024, NL=2):
+    """SURVEY.md §8d algorithmic work per sample (all positions valid)."""
+    return (L * NL * (2 * D * 3 * D + 2 * D * D + 4 * D * FF + 4 * ((L + 1) / 2) * D)
+            + (2 * 304 * 256 + 2 * 256 * 256) + (2 * 512 * 512 + 2 * 512 * 256) + 2 * B_neg * D)
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d, "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clocks / throttle reasons with nvidia-smi while the timed region runs."""
+
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.gpu, self.samples, self.stop_flag = gpu_index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.FIELDS}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5)
+                parts = [x.strip() for x in out.stdout.strip().split(",")]
+                if len(parts) >= 6:
+                    self.samples.append(parts)
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(int(float(s[0])) for s in self.samples)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for j, n in enumerate(names) if any(s[2 + j].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": int(float(self.samples[0][1])), "reasons": reasons,
+                "samples": len(sm)}
+
+
+def pin(batch):
+    return {k: v.pin_memory() for k, v in batch.items()}
+
+
+# ------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference step / retrieval on the host cores
+# ------------------------------------------------------------------------------------------
+def cpu_train_samples_per_s(steps, warmup, batch_size):
+    from mrm_b200 import synthetic
+    from oracle import two_tower_oracle as oracle
+    cfg = synthetic.TwoTowerConfig(vocab_size=C2["vocab"], max_seq_len=C2["seq_len"], dropout=0.0)
+    sd = synthetic.make_state_dict(cfg, seed=0)
+    batch = synthetic.make_batch(cfg, batch_size, seed=1, full_length=True, num_users=1_000_000)
+    p = {k: v.clone() for k, v in sd.items()}
+    m = {k: torch.zeros_like(v) for k, v in p.items() if v.is_floating_point()}
+    v2 = {k: torch.zeros_like(v) for k, v in p.items() if v.is_floating_point()}
+    times = []
+    for t in range(1, warmup + steps + 1):
+        t0 = time.perf_counter()
+        _, _, _, _, grads, _ = oracle.loss_and_grads(p, batch, cfg.temperature, cfg.num_heads)
+        for k, g in grads.items():
+            p[k], m[k], v2[k] = oracle.adamw_step(p[k], g, m[k], v2[k], t)
+        dt = time.perf_counter() - t0
+        if t > warmup:
+            times.append(dt)
+    total = sum(times)
+    return batch_size * len(times) / total, total / len(times) * 1e3
+
+
+def cpu_retrieval_users_per_s(num_users=128):
+    from mrm_b200 import synthetic
+    from oracle import two_tower_oracle as oracle
+    table = synthetic.make_catalog(C3["items"], 256, seed=2)
+    users, targets = synthetic.make_queries(table, num_users, seed=3)
+    oracle.calculate_metrics_global(users[:64], table, targets[:64], [10, 20, 50, 100])
+    t0 = time.perf_counter()
+    oracle.calculate_metrics_global(users, table, targets, [10, 20, 50, 100])
+    return num_users / (time.perf_counter() - t0)
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    torch.set_num_threads(os.cpu_count() or 1)
+    sps, ms = cpu_train_samples_per_s(args.steps, args.warmup, CPU_SAMPLE_BATCH)
+    sample = (f"oracle port of the reference step (fp32 torch CPU: fwd+bwd+InfoNCE+AdamW), batch {CPU_SAMPLE_BATCH} "
+              f"of the c2 workload (L={C2['seq_len']}, V={C2['vocab']}) per step")
+    line = {
+        "impl": "reference", "metric": "two-tower train samples/sec", "value": sps, "unit": "samples/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "c2: two-tower train step, batch 256/GPU, seq_len 200, 100k items",
+                   "reference_step_batch": CPU_SAMPLE_BATCH},
+        "cpu_baseline": {"value": sps, "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": sps, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------
+def time_gemm_roofline(eng, B, L, iters=5):
+    """Event-time every distinct GEMM shape of one training step (the step's own launch arguments)
+    and return (algorithmic flops per step in GEMMs, seconds per step spent in them)."""
+    from mrm_b200 import ops
+    T, D, FF = B * L, 256, 1024
+    dev = eng.device
+    bf = dict(device=dev, dtype=torch.bfloat16)
+    x = torch.randn(T, FF, **bf)
+    w = torch.randn(FF, FF, **bf) * 0.05
+    o32 = torch.empty(T, D, device=dev)
+    o16 = torch.empty(T, FF, **bf)
+    g32 = torch.zeros(FF, FF, device=dev)
+    NL = eng.cfg.num_layers
+    shapes = [  # (count per step, M, N, K, kind)
+        (NL, T, 3 * D, D, "fwd16"), (NL, T, D, D, "fwd32"), (NL, T, FF, D, "fwd16"), (NL, T, D, FF, "fwd32"),
+        (NL, T, FF, D, "dgrad16"), (NL, T, D, FF, "dgrad32"), (NL, T, D, D, "dgrad16"), (NL, T, D, 3 * D, "dgrad32"),
+        (NL, D, FF, T, "wgrad"), (NL, FF, D, T, "wgrad"), (NL, D, D, T, "wgrad"), (NL, 3 * D, D, T, "wgrad"),
+    ]
+    flops, secs = 0.0, 0.0
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for cnt, M, N, K, kind in shapes:
+        def launch():
+            if kind == "fwd16":
+                ops.gemm(x[:M, :K], w[:N, :K], out_bf16=o16[:M, :N])
+            elif kind == "fwd32":
+                ops.gemm(x[:M, :K], w[:N, :K], out_f32=o32[:M, :N])
+            elif kind == "dgrad16":
+                ops.gemm(x[:M, :K], w[:K, :N], b_mn=True, out_bf16=o16[:M, :N])
+            elif kind == "dgrad32":
+                ops.gemm(x[:M, :K], w[:K, :N], b_mn=True, out_f32=o32[:M, :N])
+            else:
+                ops.gemm(x[:K, :M], x[:K, :N], a_mn=True, b_mn=True, out_f32=g32[:M, :N], accumulate=True)
+        for _ in range(2):
+            launch()
+        e0.record()
+        for _ in range(iters):
+            launch()
+        e1.record()
+        torch.cuda.synchronize()
+        secs += cnt * e0.elapsed_time(e1) * 1e-3 / iters
+        flops += cnt * 2.0 * M * N * K
+    return flops, secs
+
+
+def run_ours(args, rank, world, local_rank):
+    import mrm_b200
+    from mrm_b200 import _lib, retrieval, synthetic
+    from mrm_b200.engine import TwoTowerEngine
+    from mrm_b200.train import TrainStepRunner
+
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    peaks, peak_src = load_peaks()
+    B, L, V = C2["batch"], C2["seq_len"], C2["vocab"]
+    cfg = synthetic.TwoTowerConfig(vocab_size=V, max_seq_len=L, dropout=0.1)
+    eng = TwoTowerEngine(cfg, dev)
+    eng.load_state_dict(synthetic.make_state_dict(cfg, seed=0))
+    runner = TrainStepRunner(eng, B, L, world_size=world)
+    host_batches = [pin(synthetic.make_batch(cfg, B, seed=100 + rank * 17 + i, full_length=True,
+                                             num_users=1_000_000)) for i in range(4)]
+    h2d_bytes = sum(v.numel() * v.element_size() for k, v in host_batches[0].items() if k in runner.static)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up (includes graph capture) -------------------------------------------------
+    runner.load_batch(host_batches[0])
+    for _ in range(max(args.warmup, 3)):
+        runner.step_resident()
+    torch.cuda.synchronize()
+
+    # ---- value: device-resident inputs ----------------------------------------------------
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    l0 = _lib.launch_count
+    e0.record()
+    for _ in range(args.steps):
+        runner.step_resident()
+    e1.record()
+    barrier()
+    ms_total = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms_total, op=dist.ReduceOp.MAX)
+    ms_step = ms_total.item() / args.steps
+    value = world * B * 1e3 / ms_step
+    launches = runner.kernels_per_step * args.steps + (_lib.launch_count - l0)
+
+    # ---- e2e: host batches, H2D + step + D2H of the loss every step -----------------------
+    for i in range(3):
+        runner.step_from_host(host_batches[i % 4])
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        runner.step_from_host(host_batches[i % 4])
+    torch.cuda.synchronize()
+    e2e_s = torch.tensor([time.perf_counter() - t0], device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * args.steps / e2e_s.item()
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+
+    # ---- roofline of the dominant kernel (tcgen05 GEMM) -----------------------------------
+    gemm_flops, gemm_secs = time_gemm_roofline(eng, B, L)
+    peak_tf = peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops"))
+    achieved_tf = gemm_flops / gemm_secs / 1e12
+    step_flops = 3.0 * flops_per_sample_fwd(L, B) * B
+
+    # ---- retrieval (configs[2]) -----------------------------------------------------------
+    retr = bench_retrieval(eng, rank, world, dev, peaks)
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.skip_cpu:
+        torch.set_num_threads(os.cpu_count() or 1)
+        sps, _ = cpu_train_samples_per_s(2, 1, CPU_SAMPLE_BATCH)
+        cpu = {"value": sps, "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
+               "sample": f"oracle port of the reference step on batch {CPU_SAMPLE_BATCH} of the c2 workload, "
+                         f"1 warm-up + 2 timed steps",
+               "retrieval_users_per_s": cpu_retrieval_users_per_s(128),
+               "retrieval_sample": "oracle calculate_metrics_global, 128 users x 1M items, top-100"}
+
+    if rank == 0:
+        line = {
+            "metric": "two-tower train samples/sec", "value": value, "unit": "samples/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "c2: two-tower train step (fwd+bwd+InfoNCE+dense AdamW), batch 256/GPU, "
+                                   "seq_len 200 (all positions valid), 100k-item ID table, dropout 0.1",
+                       "global_batch": world * B, "seq_len": L, "vocab_size": V,
+                       "parallelism": f"dp{world}" if world > 1 else "single",
+                       "negatives": "per-rank in-batch (reference DDP semantics)",
+                       "l2": "per-step working set (~1.2 GB activations + 410 MB optimizer state) exceeds the 126 MB L2"},
+            "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4},
+            "gpu_launches": launches,
+            "kernels_per_step": runner.kernels_per_step,
+            "step_tflops": step_flops / (ms_step * 1e-3) / 1e12,
+            "roofline": {"bound": "tensor", "kernel": "tt::gemm_bf16_kernel (tcgen05)", "achieved": achieved_tf,
+                         "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf, "traffic": None,
+                         "peak_source": f"{peak_src} bf16_tflops_sustained",
+                         "gemm_share_of_step": gemm_secs * 1e3 / ms_step},
+            "clocks": sampler.summary(),
+            "retrieval": retr,
+        }
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+
+
+def bench_retrieval(eng, rank, world, dev, peaks):
+    """10k users x 1M items, top-100 + Recall/NDCG; the catalog is sharded over the ranks."""
+    from mrm_b200 import retrieval
+    U, N, K = C3["users"], C3["items"], C3["k"]
+    rows = (N + 1 + world - 1) // world
+    first = rank * rows
+    n_local = max(0, min(N + 1, first + rows) - first)
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    shard = torch.nn.functional.normalize(torch.randn(n_local, 256, device=dev, generator=g), dim=1)
+    if rank == 0:
+        shard[0] = 0
+    index = retrieval.CatalogIndex(shard, device=dev)
+    index.item_base, index.vocab_size = first, N + 1
+    gu = torch.Generator(device=dev).manual_seed(99)
+    targets = torch.randint(1, n_local, (U,), device=dev, generator=gu)
+    users = torch.nn.functional.normalize(shard[targets] + 3.3 / 16.0 * torch.randn(U, 256, device=dev, generator=gu),
+                                          dim=1)
+    targets = targets + first
+    if world > 1:
+        dist.broadcast(users, 0)
+        dist.broadcast(targets, 0)
+    host_users = users.cpu().pin_memory()
+    host_targets = targets.cpu().pin_memory()
+    kl = [10, 20, 50, 100]
+    for _ in range(2):
+        m = retrieval.metrics_from_embeddings(users, targets, index, kl)
+    torch.cuda.synchronize()
+    iters = 5
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(iters):
+        idx, score, nfb = retrieval.retrieve_topk(users, index, K, exact_fallback=False)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1) / iters], device=dev)
+    # e2e: host user embeddings -> device, retrieval, merge, metrics -> host
+    t0 = time.perf_counter()
+    for _ in range(iters):
+        m = retrieval.metrics_from_embeddings(host_users.to(dev, non_blocking=True),
+                                              host_targets.to(dev, non_blocking=True), index, kl)
+    torch.cuda.synchronize()
+    e2e = torch.tensor([(time.perf_counter() - t0) / iters], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(e2e, op=dist.ReduceOp.MAX)
+    flops = 2.0 * U * (N + 1) * 256 / world
+    peak_tf = peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops"))
+    return {"metric": "top-100 retrieval users/sec @1M items", "users_per_s": U / (ms.item() * 1e-3),
+            "ms_per_pass": ms.item(), "e2e_users_per_s": U / e2e.item(),
+            "scoring_tflops_per_gpu": flops / (ms.item() * 1e-3) / 1e12,
+            "roofline_frac_tensor": flops / (ms.item() * 1e-3) / 1e12 / peak_tf,
+            "config": {"workload": f"c3: {U} users x {N} items, top-{K}, Recall/NDCG@10/20/50/100, catalog sharded "
+                                   f"over {world} GPU(s); user embeddings precomputed",
+                       "kprime": 256},
+            "recall_at_10": m["Recall@10"], "fallback_users": int(nfb)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--skip-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world > 1:
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local_rank))
+    try:
+        run_ours(args, rank, world, local_rank)
+    finally:
+        if world > 1 and dist.is_initialized():
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,177 @@
+"""Training-loop entry points with the reference's signatures (src/train.py:41-111) plus the
+graph-replayed step runner bench.py and the fast path use.
+
+  train_one_epoch(model, dataloader, optimizer, device, epoch, is_main_process=True, log_interval=50)
+  evaluate(model, dataloader, device, k=10)
+
+With a ``FusedAdamW`` optimizer the step is forward + hand-written backward + fused AdamW, captured
+once as a CUDA graph and replayed; batches go host -> static device buffers with non-blocking
+copies and the loss comes back through a pinned scalar. With any other torch optimizer the model's
+autograd node is used (reference-compatible, slower). bf16 needs no GradScaler.
+"""
+from __future__ import annotations
+
+import logging
+from typing import Dict, Optional
+
+import torch
+import torch.distributed as dist
+
+from . import _lib
+from .engine import TwoTowerEngine
+
+logger = logging.getLogger(__name__)
+
+_BATCH_KEYS = ("history_ids", "history_mask", "user_gender", "user_country", "user_idx", "target_audio",
+               "target_image", "target_input_ids", "target_tabular")
+
+
+class FusedAdamW:
+    """Marker optimizer: AdamW(lr, betas, eps, weight_decay) applied by the engine's fused kernel over the
+    whole flat parameter buffer (torch.optim.AdamW defaults, src/train.py:302)."""
+
+    def __init__(self, model, lr: float = 1e-4, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.01):
+        self.engine: TwoTowerEngine = model.engine if hasattr(model, "engine") else model
+        self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
+
+    def zero_grad(self, set_to_none: bool = True) -> None:
+        self.engine.grad.zero_()
+
+    def step(self) -> None:
+        self.engine.adamw_step(self.lr, self.betas, self.eps, self.weight_decay)
+
+
+class TrainStepRunner:
+    """One training step (src/train.py:54-65) over static device buffers, replayed as a CUDA graph.
+
+    Data parallel (world_size > 1): gradients are averaged with one NCCL all-reduce over the flat
+    gradient buffer between the backward graph and the optimizer graph — the reference's DDP
+    semantics (per-rank in-batch negatives, per-rank BatchNorm statistics, src/train.py:300)."""
+
+    def __init__(self, engine: TwoTowerEngine, B: int, L: int, world_size: int = 1, lr: float = 1e-4,
+                 use_graph: bool = True, with_user_idx: bool = True):
+        self.eng, self.B, self.L, self.world, self.lr, self.use_graph = engine, B, L, world_size, lr, use_graph
+        dev, m = engine.device, engine.cfg.modality_dim
+        i64 = dict(device=dev, dtype=torch.long)
+        self.static: Dict[str, torch.Tensor] = {
+            "history_ids": torch.zeros(B, L, **i64), "history_mask": torch.zeros(B, L, **i64),
+            "user_gender": torch.zeros(B, **i64), "user_country": torch.zeros(B, **i64),
+            "target_audio": torch.zeros(B, m, device=dev), "target_image": torch.zeros(B, m, device=dev),
+            "target_input_ids": torch.zeros(B, m, device=dev), "target_tabular": torch.zeros(B, m, device=dev),
+        }
+        if with_user_idx:
+            self.static["user_idx"] = torch.zeros(B, **i64)
+        self.loss_host = torch.zeros((), dtype=torch.float32).pin_memory()
+        self._graphs = None
+        self.kernels_per_step = 0
+        self._warm = False
+
+    def load_batch(self, batch: Dict[str, torch.Tensor]) -> None:
+        for k, dst in self.static.items():
+            dst.copy_(batch[k], non_blocking=True)
+
+    def _fwd_bwd(self):
+        self.eng.forward(self.static, training=True)
+        self.eng.backward()
+
+    def _opt(self):
+        self.eng.adamw_step(lr=self.lr)
+
+    def _eager(self):
+        self._fwd_bwd()
+        if self.world > 1:
+            dist.all_reduce(self.eng.grad, op=dist.ReduceOp.AVG)
+        self._opt()
+
+    def step_resident(self) -> torch.Tensor:
+        """One step on whatever is in the static buffers; returns the device loss scalar."""
+        if not self._warm:
+            c0 = _lib.launch_count
+            self._eager()                      # allocates workspaces / moments, sets func attributes
+            self.kernels_per_step = _lib.launch_count - c0
+            self._warm = True
+            torch.cuda.synchronize()
+            return self.eng.workspace(self.B, self.L)["loss"]
+        if not self.use_graph:
+            self._eager()
+            return self.eng.workspace(self.B, self.L)["loss"]
+        if self._graphs is None:
+            g1, g2 = torch.cuda.CUDAGraph(), None
+            if self.world > 1:
+                g2 = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g1):
+                    self._fwd_bwd()
+                with torch.cuda.graph(g2):
+                    self._opt()
+            else:
+                with torch.cuda.graph(g1):
+                    self._fwd_bwd()
+                    self._opt()
+            self._graphs = (g1, g2)
+        g1, g2 = self._graphs
+        g1.replay()
+        if g2 is not None:
+            dist.all_reduce(self.eng.grad, op=dist.ReduceOp.AVG)
+            g2.replay()
+        return self.eng.workspace(self.B, self.L)["loss"]
+
+    def step_from_host(self, host_batch: Dict[str, torch.Tensor]) -> float:
+        """Host batch -> device -> step -> loss on the host (one sync, like the reference's loss.item())."""
+        self.load_batch(host_batch)
+        loss = self.step_resident()
+        self.loss_host.copy_(loss, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return float(self.loss_host)
+
+
+def train_one_epoch(model, dataloader, optimizer, device, epoch, is_main_process=True, log_interval=50):
+    """Reference signature and return value (mean loss), src/train.py:41-76."""
+    model.train()
+    total_loss, num_batches = 0.0, len(dataloader)
+    runner: Optional[TrainStepRunner] = None
+    fused = isinstance(optimizer, FusedAdamW)
+    world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+    for i, batch in enumerate(dataloader):
+        if fused:
+            B, L = batch["history_ids"].shape
+            if runner is None or (runner.B, runner.L) != (B, L):
+                runner = TrainStepRunner(model.engine, B, L, world_size=world, lr=optimizer.lr,
+                                         with_user_idx="user_idx" in batch)
+            loss_val = runner.step_from_host({k: v for k, v in batch.items() if k in _BATCH_KEYS})
+        else:
+            for k, v in batch.items():
+                if isinstance(v, torch.Tensor):
+                    batch[k] = v.to(device)
+            optimizer.zero_grad(set_to_none=True)
+            loss, _, _, _ = model(batch)
+            loss.backward()
+            optimizer.step()
+            model.engine.shadow_valid = False     # the fp32 masters changed behind the bf16 shadow
+            loss_val = loss.item()
+        total_loss += loss_val
+        if is_main_process and (i + 1) % log_interval == 0:
+            logger.info(f"Epoch {epoch} [{i+1}/{num_batches}] | Loss: {loss_val:.4f}")
+    return total_loss / max(num_batches, 1)
+
+
+def evaluate(model, dataloader, device, k=10):
+    """In-batch Recall@k (src/train.py:78-111): the positive must be among the k best logits of its row
+    under the canonical order; hits/total are summed over ranks when a process group exists."""
+    model.eval()
+    hits = torch.tensor(0.0, device=device)
+    total = torch.tensor(0.0, device=device)
+    with torch.no_grad():
+        for batch in dataloader:
+            b = {kk: v.to(device) for kk, v in batch.items() if isinstance(v, torch.Tensor)}
+            _, logits, _, _ = model(b)
+            n = logits.shape[0]
+            diag = logits.diagonal().unsqueeze(1)
+            col = torch.arange(n, device=logits.device).unsqueeze(0)
+            row = torch.arange(n, device=logits.device).unsqueeze(1)
+            better = (logits > diag) | ((logits == diag) & (col < row))   # rank of the positive, ties by index
+            hits += (better.sum(dim=1) < k).sum()
+            total += n
+    if dist.is_available() and dist.is_initialized():
+        dist.all_reduce(hits, op=dist.ReduceOp.SUM)
+        dist.all_reduce(total, op=dist.ReduceOp.SUM)
+    return (hits / total).item() if total > 0 else 0.0

@@ -1,0 +1,102 @@
+"""world_size-2 gloo tests (CPU) of the multi-GPU protocols' host-side logic:
+ - retrieval: contiguous catalog shards, padding row masked only where it lives, per-shard canonical
+   top-K, all-gather, merge == unsharded result (the CUDA merge kernel implements the same rule);
+ - data-parallel training: averaging per-rank gradients of per-rank losses (reference DDP semantics,
+   src/train.py:300) == gradient of the mean of the per-rank losses.
+The per-rank compute here is the CPU oracle; the CUDA kernels are covered by the -m gpu tests."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from mrm_b200 import synthetic
+from mrm_b200.sharding import merge_canonical, shard_bounds
+from oracle import two_tower_oracle as oracle
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _run(fn, world, *args):
+    port = _free_port()
+    mp.spawn(_entry, args=(world, port, fn, args), nprocs=world, join=True)
+
+
+def _entry(rank, world, port, fn, args):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        fn(rank, world, *args)
+    finally:
+        dist.destroy_process_group()
+
+
+def _retrieval_worker(rank, world, K):
+    torch.set_num_threads(1)
+    table = synthetic.make_catalog(2999, 256, seed=5, grid=2.0 ** -3)      # heavy ties
+    users, _ = synthetic.make_queries(table, 40, seed=6, noise=5.0, grid=2.0 ** -3)
+    first, rows = shard_bounds(table.shape[0], world, rank)
+    local = table[first:first + rows]
+    s = users @ local.t()
+    if first == 0:
+        s[:, 0] = float("-inf")
+    v, i = oracle.canonical_topk(s, K)
+    i = (i + first).to(torch.int32)
+    all_v = [torch.empty_like(v) for _ in range(world)]
+    all_i = [torch.empty_like(i) for _ in range(world)]
+    dist.all_gather(all_v, v)
+    dist.all_gather(all_i, i)
+    mi, mv = merge_canonical(torch.stack(all_v), torch.stack(all_i))
+    rv, ri = oracle.canonical_topk(oracle.retrieval_scores(users, table), K)
+    assert torch.equal(mi.long(), ri), f"rank {rank}: merged shards differ from the unsharded top-K"
+    assert torch.equal(mv, rv)
+
+
+def test_sharded_retrieval_protocol_world2():
+    _run(_retrieval_worker, 2, 50)
+
+
+def test_shard_bounds_cover_catalog():
+    for V in (1, 7, 1000, 1_000_001):
+        for world in (1, 2, 3, 8):
+            spans = [shard_bounds(V, world, r) for r in range(world)]
+            assert spans[0][0] == 0
+            pos = 0
+            for first, rows in spans:
+                assert first == min(pos, V) or rows == 0
+                pos = first + rows
+            assert pos == V
+
+
+def _dp_worker(rank, world):
+    torch.set_num_threads(1)
+    cfg = synthetic.TwoTowerConfig(vocab_size=301, num_countries=7, max_seq_len=10, embedding_dim=64,
+                                   modality_dim=16, dropout=0.0)
+    sd = synthetic.make_state_dict(cfg, seed=1)
+    batch = synthetic.make_batch(cfg, 8, seed=10 + rank)
+    _, _, _, _, grads, _ = oracle.loss_and_grads(sd, batch, cfg.temperature, cfg.num_heads, dtype=torch.float64)
+    flat = torch.cat([g.flatten() for g in grads.values()])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+    flat /= world
+    # every rank now holds the same averaged gradient = gradient of mean_r(loss_r)
+    ref = None
+    for r in range(world):
+        b = synthetic.make_batch(cfg, 8, seed=10 + r)
+        _, _, _, _, g, _ = oracle.loss_and_grads(sd, b, cfg.temperature, cfg.num_heads, dtype=torch.float64)
+        f = torch.cat([x.flatten() for x in g.values()])
+        ref = f if ref is None else ref + f
+    ref /= world
+    assert (flat - ref).abs().max().item() < 1e-12
+
+
+def test_dp_gradient_average_world2():
+    _run(_dp_worker, 2)
