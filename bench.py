@@ -67,7 +67,7 @@ class ClockSampler(threading.Thread):
                     self.samples.append(parts)
             except Exception:
                 pass
-            time.sleep(0.2)
+            time.sleep(0.05)
 
     def summary(self):
         if not self.samples:
