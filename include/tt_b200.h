@@ -262,7 +262,8 @@ typedef struct tt_topk_plan {
 int tt_topk_plan_make(int U, int N, int kprime, tt_topk_plan* plan);
 int tt_score_topk(const void* users_bf16, const void* items_bf16, int item_base, const tt_topk_plan* plan,
                   void* cand, int32_t* cand_cnt, void* thr, int mask_item0, void* stream);
-int tt_topk_finalize(const tt_topk_plan* plan, const void* cand, const int32_t* cand_cnt, const float* users_f32,
+int tt_topk_finalize(const tt_topk_plan* plan, const void* cand, const int32_t* cand_cnt, const void* thr,
+                     const float* users_f32,
                      const float* items_f32, int item_base, int K, float eps, int32_t* out_idx, float* out_score,
                      int32_t* flags, void* stream);
 int tt_topk_merge(const float* scores, const int32_t* idx, int G, int U, int K, float* out_score, int32_t* out_idx,

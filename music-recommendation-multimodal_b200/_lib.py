@@ -132,7 +132,7 @@ _SIGNATURES = {
     "tt_topk_plan_make": [c_int32, c_int32, c_int32, ctypes.POINTER(TopkPlan)],
     "tt_score_topk": [c_void_p, c_void_p, c_int32, ctypes.POINTER(TopkPlan), c_void_p, c_void_p, c_void_p, c_int32,
                       c_void_p],
-    "tt_topk_finalize": [ctypes.POINTER(TopkPlan), c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_float,
+    "tt_topk_finalize": [ctypes.POINTER(TopkPlan), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_float,
                          c_void_p, c_void_p, c_void_p, c_void_p],
     "tt_topk_merge": [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p],
     "tt_exact_topk": [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p],

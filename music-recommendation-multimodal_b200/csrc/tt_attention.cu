@@ -44,14 +44,26 @@ __device__ __forceinline__ void st_swizzled_unit(uint8_t* tile, int r, int u, ui
   *reinterpret_cast<uint4*>(tile + r * 128 + ((u ^ (r & 7)) << 4)) = v;
 }
 
-__global__ void __launch_bounds__(128, 1)
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// Forward. 256 threads: warp w -> TMEM lane quarter (w & 3), column half (w >> 2). Thread
+// (row, hf) owns query row `row` of the tile and the 64-column half `hf` of every 128-key tile.
+// Shared memory per CTA (nq = 2): Q 16 KB + K/V slots 32 KB (K first, then reused for V once the
+// S MMAs have retired) + P 32 KB = 80 KB -> two CTAs per SM (TMEM: 128 or 256 columns each).
+__global__ void __launch_bounds__(256, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t pad = (1024u - (smem_u32(smem_raw) & 1023u)) & 1023u;
   uint8_t* smem = smem_raw + pad;
 
   const int tid = threadIdx.x;
-  const int warp = tid >> 5;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int q = warp & 3, hf = warp >> 2;
+  const int row = q * 32 + lane;
   const int bh_count = p.B * p.H;
   const int qt = p.nq - 1 - static_cast<int>(blockIdx.x) / bh_count;  // heavy tiles first
   const int bh = static_cast<int>(blockIdx.x) % bh_count;
@@ -60,15 +72,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
   const int D = p.H * kDh;
 
   uint8_t* sQ = smem;
-  uint8_t* sK = sQ + kTileBytes;
-  uint8_t* sV = sK + static_cast<size_t>(p.nq) * kTileBytes;
-  uint8_t* sP = sV + static_cast<size_t>(p.nq) * kTileBytes;  // 2 buffers x 2 chunks x 16 KB
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 4 * kTileBytes);
+  uint8_t* sKV = sQ + kTileBytes;
+  uint8_t* sP = sKV + static_cast<size_t>(p.nq) * kTileBytes;  // 2 chunks x 16 KB
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * kTileBytes);
   uint64_t* bar_qk = bars + 0;
   uint64_t* bar_v = bars + 1;
   uint64_t* bar_s = bars + 2;
-  uint64_t* bar_pv = bars + 3;  // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+  uint64_t* bar_pv = bars + 3;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+  float* s_red = reinterpret_cast<float*>(bars + 6);  // [2][128]
 
   uint32_t tmem_cols = 128;
   while (tmem_cols < static_cast<uint32_t>(n_kv * kTile)) tmem_cols <<= 1;
@@ -78,8 +90,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
     mbar_init(bar_qk, 1);
     mbar_init(bar_v, 1);
     mbar_init(bar_s, 1);
-    mbar_init(&bar_pv[0], 1);
-    mbar_init(&bar_pv[1], 1);
+    mbar_init(bar_pv, 1);
     fence_barrier_init();
   }
   __syncwarp();
@@ -99,42 +110,43 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
     mbar_arrive_expect_tx(bar_qk, (1 + n_kv) * kTileBytes);
     tma_load_2d(sQ, &tmQKV, bar_qk, h * kDh, q_row0);
     for (int j = 0; j < n_kv; ++j)
-      tma_load_2d(sK + static_cast<size_t>(j) * kTileBytes, &tmQKV, bar_qk, D + h * kDh,
-                  seq_row0 + j * kTile);
-    mbar_arrive_expect_tx(bar_v, n_kv * kTileBytes);
-    for (int j = 0; j < n_kv; ++j)
-      tma_load_2d(sV + static_cast<size_t>(j) * kTileBytes, &tmQKV, bar_v, 2 * D + h * kDh,
-                  seq_row0 + j * kTile);
-    // S_j = Q K_j^T for every key tile, back to back
+      tma_load_2d(sKV + static_cast<size_t>(j) * kTileBytes, &tmQKV, bar_qk, D + h * kDh, seq_row0 + j * kTile);
     mbar_wait(bar_qk, 0);
     tc_fence_after();
     const uint32_t idesc_s = umma_idesc_bf16(kTile, kTile, false, false);
     const uint32_t q_base = smem_u32(sQ);
     for (int j = 0; j < n_kv; ++j) {
-      const uint32_t k_base = smem_u32(sK + static_cast<size_t>(j) * kTileBytes);
+      const uint32_t k_base = smem_u32(sKV + static_cast<size_t>(j) * kTileBytes);
 #pragma unroll
       for (int k = 0; k < kDh / 16; ++k)
-        umma_bf16(tmem_base + j * kTile, umma_desc_kmajor(q_base + k * 32),
-                  umma_desc_kmajor(k_base + k * 32), idesc_s, k > 0 ? 1u : 0u);
+        umma_bf16(tmem_base + j * kTile, umma_desc_kmajor(q_base + k * 32), umma_desc_kmajor(k_base + k * 32),
+                  idesc_s, k > 0 ? 1u : 0u);
     }
     umma_commit(bar_s);
+    // the K slots are free once the S MMAs retired: V tiles take their place
+    mbar_wait(bar_s, 0);
+    mbar_arrive_expect_tx(bar_v, n_kv * kTileBytes);
+    for (int j = 0; j < n_kv; ++j)
+      tma_load_2d(sKV + static_cast<size_t>(j) * kTileBytes, &tmQKV, bar_v, 2 * D + h * kDh, seq_row0 + j * kTile);
   }
 
-  // ---- pass A: row maximum over the causal prefix --------------------------------------
+  // ---- pass A: row maximum over the causal prefix (each thread: its column half) ----------
   mbar_wait(bar_s, 0);
   __syncwarp();
   tc_fence_after();
-  const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
-  const int q_pos = qt * kTile + tid;  // position of this thread's query inside the sequence
+  const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+  const int q_pos = qt * kTile + row;  // position of this thread's query inside the sequence
   float m = -INFINITY;
   for (int j = 0; j < n_kv; ++j) {
     const bool diag = (j == qt);
-    const int nchunks = diag ? (warp + 1) : 4;  // chunks right of the warp's rows are fully masked
-    for (int c = 0; c < nchunks; ++c) {
+#pragma unroll
+    for (int cc = 0; cc < 2; ++cc) {
+      const int cg = 2 * hf + cc;       // 32-column chunk index inside the key tile
+      if (diag && cg > q) continue;     // fully above the diagonal for every row of this warp
       uint32_t r[32];
-      tmem_ld32(lane_base + j * kTile + c * 32, r);
+      tmem_ld32(lane_base + j * kTile + cg * 32, r);
       tmem_ld_wait();
-      const int kv0 = j * kTile + c * 32;
+      const int kv0 = j * kTile + cg * 32;
 #pragma unroll
       for (int t = 0; t < 32; ++t) {
         const float s = __uint_as_float(r[t]);
@@ -142,6 +154,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
       }
     }
   }
+  s_red[hf * 128 + row] = m;
+  __syncthreads();
+  m = fmaxf(s_red[row], s_red[128 + row]);
+  __syncthreads();
   const float c1 = p.scale * kLog2e;
   const float mc = m * c1;
   const uint64_t seed = p.drop_seed + ((p.drop_thresh && p.drop_seed_dev) ? *p.drop_seed_dev : 0ull);
@@ -149,33 +165,28 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
   // ---- pass B: P_j -> smem (bf16, swizzled), O += P_j V_j ------------------------------
   float l = 0.f;
   const uint32_t idesc_pv = umma_idesc_bf16(kTile, kDh, false, true);
+  uint8_t* chunk = sP + static_cast<size_t>(hf) * kTileBytes;  // this thread's 64 key columns
   for (int j = 0; j < n_kv; ++j) {
-    const int buf = j & 1;
-    uint8_t* pbuf = sP + static_cast<size_t>(buf) * 2 * kTileBytes;
-    if (j >= 2) {  // the MMA that consumed this buffer two tiles ago must have retired
-      mbar_wait(&bar_pv[buf], ((j >> 1) - 1) & 1);
-    }
-    __syncwarp();  // tcgen05.ld is warp-collective: reconverge after the single-thread MMA issue
+    if (j >= 1) mbar_wait(bar_pv, (j - 1) & 1);  // previous P tile consumed
+    __syncwarp();
     const bool diag = (j == qt);
-    const int nchunks = diag ? (warp + 1) : 4;
-    for (int c = 0; c < 4; ++c) {
-      uint8_t* chunk = pbuf + static_cast<size_t>(c >> 1) * kTileBytes;  // 64 kv columns per chunk
-      const int u0 = (c & 1) * 4;                                       // 16B unit inside the row
-      if (c < nchunks) {
+#pragma unroll
+    for (int cc = 0; cc < 2; ++cc) {
+      const int cg = 2 * hf + cc;
+      const int u0 = cc * 4;
+      if (!(diag && cg > q)) {
         uint32_t r[32];
-        tmem_ld32(lane_base + j * kTile + c * 32, r);
+        tmem_ld32(lane_base + j * kTile + cg * 32, r);
         tmem_ld_wait();
-        const int kv0 = j * kTile + c * 32;
+        const int kv0 = j * kTile + cg * 32;
+        const uint32_t didx0 = (static_cast<uint32_t>(bh) * p.L + q_pos) * p.L + kv0;
         float pv[32];
 #pragma unroll
         for (int t = 0; t < 32; ++t) {
-          float e = exp2f(__uint_as_float(r[t]) * c1 - mc);
+          float e = fast_exp2(__uint_as_float(r[t]) * c1 - mc);
           if (diag && kv0 + t > q_pos) e = 0.f;
           l += e;
-          if (p.drop_thresh) {
-            const uint64_t idx = (static_cast<uint64_t>(bh) * p.L + q_pos) * p.L + (kv0 + t);
-            e = drop_keep(seed, p.drop_site, idx, p.drop_thresh) ? e * p.drop_scale : 0.f;
-          }
+          if (p.drop_thresh) e = drop_keep(seed, p.drop_site, didx0 + t, p.drop_thresh) ? e * p.drop_scale : 0.f;
           pv[t] = e;
         }
 #pragma unroll
@@ -185,11 +196,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
           v.y = pack_bf16(pv[u * 8 + 2], pv[u * 8 + 3]);
           v.z = pack_bf16(pv[u * 8 + 4], pv[u * 8 + 5]);
           v.w = pack_bf16(pv[u * 8 + 6], pv[u * 8 + 7]);
-          st_swizzled_unit(chunk, tid, u0 + u, v);
+          st_swizzled_unit(chunk, row, u0 + u, v);
         }
       } else {
 #pragma unroll
-        for (int u = 0; u < 4; ++u) st_swizzled_unit(chunk, tid, u0 + u, make_uint4(0, 0, 0, 0));
+        for (int u = 0; u < 4; ++u) st_swizzled_unit(chunk, row, u0 + u, make_uint4(0, 0, 0, 0));
       }
     }
     fence_proxy_async_smem();
@@ -198,8 +209,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
     if (tid == 0) {
       tc_fence_after();
       if (j == 0) mbar_wait(bar_v, 0);
-      const uint32_t p_base = smem_u32(pbuf);
-      const uint32_t v_base = smem_u32(sV + static_cast<size_t>(j) * kTileBytes);
+      const uint32_t p_base = smem_u32(sP);
+      const uint32_t v_base = smem_u32(sKV + static_cast<size_t>(j) * kTileBytes);
 #pragma unroll
       for (int k = 0; k < kTile / 16; ++k) {
         // A = P: chunk (k/4), 32 B per 16 kv columns; B = V rows (MN-major): 16 kv rows = 2048 B
@@ -207,37 +218,35 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
         const uint64_t bdesc = umma_desc_mnmajor(v_base + k * 2048, kTileBytes);
         umma_bf16(tmem_base, adesc, bdesc, idesc_pv, (j > 0 || k > 0) ? 1u : 0u);
       }
-      umma_commit(&bar_pv[buf]);
+      umma_commit(bar_pv);
     }
   }
 
   // ---- epilogue: O / l -> ctx, log-sum-exp -> lse ---------------------------------------
+  s_red[hf * 128 + row] = l;
+  mbar_wait(bar_pv, (n_kv - 1) & 1);
+  __syncthreads();
+  tc_fence_after();
+  l = s_red[row] + s_red[128 + row];
   {
-    const int last = n_kv - 1;
-    mbar_wait(&bar_pv[last & 1], (last >> 1) & 1);
-    __syncwarp();
-    tc_fence_after();
     const float inv_l = 1.f / l;
     const bool valid = q_pos < p.L;
-    __nv_bfloat16* orow = p.ctx + static_cast<size_t>(seq_row0 + q_pos) * D + h * kDh;
+    __nv_bfloat16* orow = p.ctx + static_cast<size_t>(seq_row0 + q_pos) * D + h * kDh + hf * 32;
+    uint32_t r[32];
+    tmem_ld32(lane_base + hf * 32, r);
+    tmem_ld_wait();
+    if (valid) {
 #pragma unroll
-    for (int c = 0; c < 2; ++c) {
-      uint32_t r[32];
-      tmem_ld32(lane_base + c * 32, r);
-      tmem_ld_wait();
-      if (valid) {
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          uint4 v;
-          v.x = pack_bf16(__uint_as_float(r[u * 8 + 0]) * inv_l, __uint_as_float(r[u * 8 + 1]) * inv_l);
-          v.y = pack_bf16(__uint_as_float(r[u * 8 + 2]) * inv_l, __uint_as_float(r[u * 8 + 3]) * inv_l);
-          v.z = pack_bf16(__uint_as_float(r[u * 8 + 4]) * inv_l, __uint_as_float(r[u * 8 + 5]) * inv_l);
-          v.w = pack_bf16(__uint_as_float(r[u * 8 + 6]) * inv_l, __uint_as_float(r[u * 8 + 7]) * inv_l);
-          *reinterpret_cast<uint4*>(orow + c * 32 + u * 8) = v;
-        }
+      for (int u = 0; u < 4; ++u) {
+        uint4 v;
+        v.x = pack_bf16(__uint_as_float(r[u * 8 + 0]) * inv_l, __uint_as_float(r[u * 8 + 1]) * inv_l);
+        v.y = pack_bf16(__uint_as_float(r[u * 8 + 2]) * inv_l, __uint_as_float(r[u * 8 + 3]) * inv_l);
+        v.z = pack_bf16(__uint_as_float(r[u * 8 + 4]) * inv_l, __uint_as_float(r[u * 8 + 5]) * inv_l);
+        v.w = pack_bf16(__uint_as_float(r[u * 8 + 6]) * inv_l, __uint_as_float(r[u * 8 + 7]) * inv_l);
+        *reinterpret_cast<uint4*>(orow + u * 8) = v;
       }
+      if (hf == 0 && p.lse) p.lse[static_cast<size_t>(bh) * p.L + q_pos] = m * p.scale + __logf(l);
     }
-    if (valid && p.lse) p.lse[static_cast<size_t>(bh) * p.L + q_pos] = m * p.scale + __logf(l);
   }
 
   tc_fence_before();
@@ -246,7 +255,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
 }
 
 // --------------------------------------------------------------------------------------------
-// Backward. One CTA (128 threads) per (sequence, head). For key tile j and query tile i >= j:
+// Backward. One CTA (256 threads) per (sequence, head). For key tile j and query tile i >= j:
 //   S   = Q_i K_j^T                    (TMEM cols [0,128))
 //   dP  = dO_i V_j^T                   (TMEM cols [128,256))
 //   P   = exp2(scale*log2e*S - lse_i*log2e) under the causal mask; Pd = dropout(P)
@@ -256,7 +265,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
 //   dQ_i += dS K_j      (A = dS K-major,                     B = K_j  read MN-major)
 // dV_j, dK_j live in TMEM (cols [256,320), [320,384)) across the inner loop; dQ_i
 // (cols [384 + 64*i ...)) is kept for up to two query tiles, i.e. L <= 256.
-// Pd and dS are staged as bf16 in 128B-swizzled smem tiles.
+// Pd and dS are staged as bf16 in 128B-swizzled smem tiles. Thread (row, hf) owns query row
+// `row` and the 64-column half `hf` of the 128-key tile (warp & 3 = TMEM lane quarter).
 // --------------------------------------------------------------------------------------------
 struct AttnBwdParams {
   int B, L, H, nq;
@@ -272,7 +282,19 @@ struct AttnBwdParams {
   __nv_bfloat16* dqkv;        // [T, 3*H*64]
 };
 
-__global__ void __launch_bounds__(128, 1)
+__device__ __forceinline__ void store_row32_bf16(__nv_bfloat16* dst, const uint32_t (&r)[32]) {
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    uint4 v;
+    v.x = pack_bf16(__uint_as_float(r[u * 8 + 0]), __uint_as_float(r[u * 8 + 1]));
+    v.y = pack_bf16(__uint_as_float(r[u * 8 + 2]), __uint_as_float(r[u * 8 + 3]));
+    v.z = pack_bf16(__uint_as_float(r[u * 8 + 4]), __uint_as_float(r[u * 8 + 5]));
+    v.w = pack_bf16(__uint_as_float(r[u * 8 + 6]), __uint_as_float(r[u * 8 + 7]));
+    *reinterpret_cast<uint4*>(dst + u * 8) = v;
+  }
+}
+
+__global__ void __launch_bounds__(256, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
                 const AttnBwdParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -280,7 +302,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
   uint8_t* smem = smem_raw + pad;
 
   const int tid = threadIdx.x;
-  const int warp = tid >> 5;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int q = warp & 3, hf = warp >> 2;
+  const int row = q * 32 + lane;
   const int bh = blockIdx.x;
   const int b = bh / p.H, h = bh % p.H;
   const int D = p.H * kDh;
@@ -322,7 +346,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+  const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
   const uint32_t T_S = 0, T_DP = 128, T_DV = 256, T_DK = 320, T_DQ = 384;
 
   if (tid == 0) {
@@ -333,8 +357,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     }
   }
   // delta_i = rowsum(dO * O), lse -> smem (generic loads; rows beyond L are treated as zero)
-  for (int i = 0; i < nq; ++i) {
-    const int pos = i * kTile + tid;
+  for (int pos = tid; pos < nq * kTile; pos += 256) {
     float delta = 0.f, lse2 = 0.f;
     if (pos < p.L) {
       const uint4* o = reinterpret_cast<const uint4*>(p.ctx + static_cast<size_t>(seq_row0 + pos) * D + h * kDh);
@@ -363,6 +386,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
   const uint32_t idesc_q = umma_idesc_bf16(kTile, kDh, false, true);       // dS K
   uint32_t it = 0;  // (j,i) iteration counter -> mbarrier phase
   uint32_t dq_started = 0;  // bit i set once dQ_i has received its first MMA
+  uint8_t* pchunk = sPd + static_cast<size_t>(hf) * kTileBytes;
+  uint8_t* dchunk = sDS + static_cast<size_t>(hf) * kTileBytes;
 
   for (int j = 0; j < nq; ++j) {
     if (tid == 0) {
@@ -393,31 +418,31 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       __syncwarp();
       tc_fence_after();
 
-      const int q_pos = i * kTile + tid;
+      const int q_pos = i * kTile + row;
       const float lse2 = sLse[q_pos];
       const float delta = sDelta[q_pos];
       const bool diag = (i == j);
-      const int nchunks = diag ? (warp + 1) : 4;
-      for (int c = 0; c < 4; ++c) {
-        uint8_t* pchunk = sPd + static_cast<size_t>(c >> 1) * kTileBytes;
-        uint8_t* dchunk = sDS + static_cast<size_t>(c >> 1) * kTileBytes;
-        const int u0 = (c & 1) * 4;
-        if (c < nchunks) {
+      const bool row_ok = q_pos < p.L;
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc) {
+        const int cg = 2 * hf + cc;
+        const int u0 = cc * 4;
+        if (!(diag && cg > q)) {
           uint32_t rs[32], rp[32];
-          tmem_ld32(lane_base + T_S + c * 32, rs);
-          tmem_ld32(lane_base + T_DP + c * 32, rp);
+          tmem_ld32(lane_base + T_S + cg * 32, rs);
+          tmem_ld32(lane_base + T_DP + cg * 32, rp);
           tmem_ld_wait();
-          const int kv0 = j * kTile + c * 32;
+          const int kv0 = j * kTile + cg * 32;
+          const uint32_t didx0 = (static_cast<uint32_t>(bh) * p.L + q_pos) * p.L + kv0;
           float pd[32], ds[32];
 #pragma unroll
           for (int t = 0; t < 32; ++t) {
-            float pr = exp2f(__uint_as_float(rs[t]) * c1 - lse2);
-            if ((diag && kv0 + t > q_pos) || q_pos >= p.L) pr = 0.f;
+            float pr = fast_exp2(__uint_as_float(rs[t]) * c1 - lse2);
+            if ((diag && kv0 + t > q_pos) || !row_ok) pr = 0.f;
             float dp = __uint_as_float(rp[t]);
             float pdrop = pr;
             if (p.drop_thresh) {
-              const uint64_t idx = (static_cast<uint64_t>(bh) * p.L + q_pos) * p.L + (kv0 + t);
-              const bool keep = drop_keep(seed, p.drop_site, idx, p.drop_thresh);
+              const bool keep = drop_keep(seed, p.drop_site, didx0 + t, p.drop_thresh);
               pdrop = keep ? pr * p.drop_scale : 0.f;
               dp = keep ? dp * p.drop_scale : 0.f;
             }
@@ -435,14 +460,14 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
             w.y = pack_bf16(ds[u * 8 + 2], ds[u * 8 + 3]);
             w.z = pack_bf16(ds[u * 8 + 4], ds[u * 8 + 5]);
             w.w = pack_bf16(ds[u * 8 + 6], ds[u * 8 + 7]);
-            st_swizzled_unit(pchunk, tid, u0 + u, v);
-            st_swizzled_unit(dchunk, tid, u0 + u, w);
+            st_swizzled_unit(pchunk, row, u0 + u, v);
+            st_swizzled_unit(dchunk, row, u0 + u, w);
           }
         } else {
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
-            st_swizzled_unit(pchunk, tid, u0 + u, make_uint4(0, 0, 0, 0));
-            st_swizzled_unit(dchunk, tid, u0 + u, make_uint4(0, 0, 0, 0));
+            st_swizzled_unit(pchunk, row, u0 + u, make_uint4(0, 0, 0, 0));
+            st_swizzled_unit(dchunk, row, u0 + u, make_uint4(0, 0, 0, 0));
           }
         }
       }
@@ -459,25 +484,19 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         // operand (M = kv, contraction = q) they are MN-major: 16 q rows = 2048 B per K step,
         // 64-wide kv chunks are kTileBytes apart.
 #pragma unroll
-        for (int k = 0; k < kTile / 16; ++k) {
-          // dV_j += Pd^T dO_i
+        for (int k = 0; k < kTile / 16; ++k)   // dV_j += Pd^T dO_i
           umma_bf16(tmem_base + T_DV, umma_desc_mnmajor(pd_base + k * 2048, kTileBytes),
                     umma_desc_mnmajor(do_base + k * 2048, kTileBytes), idesc_t, (i > j || k > 0) ? 1u : 0u);
-        }
 #pragma unroll
-        for (int k = 0; k < kTile / 16; ++k) {
-          // dK_j += dS^T Q_i
+        for (int k = 0; k < kTile / 16; ++k)   // dK_j += dS^T Q_i
           umma_bf16(tmem_base + T_DK, umma_desc_mnmajor(ds_base + k * 2048, kTileBytes),
                     umma_desc_mnmajor(q_base + k * 2048, kTileBytes), idesc_t, (i > j || k > 0) ? 1u : 0u);
-        }
         const uint32_t first = ((dq_started >> i) & 1u) ? 0u : 1u;
 #pragma unroll
-        for (int k = 0; k < kTile / 16; ++k) {
-          // dQ_i += dS K_j : A = dS K-major (chunk k/4, 32 B per 16 kv), B = K_j rows MN-major
+        for (int k = 0; k < kTile / 16; ++k)   // dQ_i += dS K_j (A K-major, B = K_j rows MN-major)
           umma_bf16(tmem_base + T_DQ + i * kDh,
                     umma_desc_kmajor(ds_base + (k >> 2) * kTileBytes + (k & 3) * 32),
                     umma_desc_mnmajor(k_base + k * 2048, kTileBytes), idesc_q, (first && k == 0) ? 0u : 1u);
-        }
         dq_started |= (1u << i);
         umma_commit(bar_mm2);
       }
@@ -486,32 +505,17 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       __syncwarp();
       tc_fence_after();
     }
-    // ---- dK_j, dV_j complete: TMEM -> dqkv -------------------------------------------------
+    // ---- dK_j, dV_j complete: TMEM -> dqkv (each thread: 32 of the 64 columns) -------------
     {
-      const int pos = j * kTile + tid;
-      const bool valid = pos < p.L;
-      __nv_bfloat16* row = p.dqkv + static_cast<size_t>(seq_row0 + pos) * (3 * D);
-#pragma unroll
-      for (int which = 0; which < 2; ++which) {  // 0: dK, 1: dV
-        const uint32_t tcol = which == 0 ? T_DK : T_DV;
-        __nv_bfloat16* dst = row + (which == 0 ? D : 2 * D) + h * kDh;
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          uint32_t r[32];
-          tmem_ld32(lane_base + tcol + c * 32, r);
-          tmem_ld_wait();
-          if (valid) {
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              uint4 v;
-              v.x = pack_bf16(__uint_as_float(r[u * 8 + 0]), __uint_as_float(r[u * 8 + 1]));
-              v.y = pack_bf16(__uint_as_float(r[u * 8 + 2]), __uint_as_float(r[u * 8 + 3]));
-              v.z = pack_bf16(__uint_as_float(r[u * 8 + 4]), __uint_as_float(r[u * 8 + 5]));
-              v.w = pack_bf16(__uint_as_float(r[u * 8 + 6]), __uint_as_float(r[u * 8 + 7]));
-              *reinterpret_cast<uint4*>(dst + c * 32 + u * 8) = v;
-            }
-          }
-        }
+      const int pos = j * kTile + row;
+      __nv_bfloat16* grow = p.dqkv + static_cast<size_t>(seq_row0 + pos) * (3 * D) + h * kDh + hf * 32;
+      uint32_t rk[32], rv[32];
+      tmem_ld32(lane_base + T_DK + hf * 32, rk);
+      tmem_ld32(lane_base + T_DV + hf * 32, rv);
+      tmem_ld_wait();
+      if (pos < p.L) {
+        store_row32_bf16(grow + D, rk);
+        store_row32_bf16(grow + 2 * D, rv);
       }
     }
     tc_fence_before();
@@ -521,26 +525,12 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
 
   // ---- dQ_i -> dqkv ---------------------------------------------------------------------
   for (int i = 0; i < nq; ++i) {
-    const int pos = i * kTile + tid;
-    const bool valid = pos < p.L;
-    __nv_bfloat16* dst = p.dqkv + static_cast<size_t>(seq_row0 + pos) * (3 * D) + h * kDh;
-#pragma unroll
-    for (int c = 0; c < 2; ++c) {
-      uint32_t r[32];
-      tmem_ld32(lane_base + T_DQ + i * kDh + c * 32, r);
-      tmem_ld_wait();
-      if (valid) {
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          uint4 v;
-          v.x = pack_bf16(__uint_as_float(r[u * 8 + 0]), __uint_as_float(r[u * 8 + 1]));
-          v.y = pack_bf16(__uint_as_float(r[u * 8 + 2]), __uint_as_float(r[u * 8 + 3]));
-          v.z = pack_bf16(__uint_as_float(r[u * 8 + 4]), __uint_as_float(r[u * 8 + 5]));
-          v.w = pack_bf16(__uint_as_float(r[u * 8 + 6]), __uint_as_float(r[u * 8 + 7]));
-          *reinterpret_cast<uint4*>(dst + c * 32 + u * 8) = v;
-        }
-      }
-    }
+    const int pos = i * kTile + row;
+    uint32_t r[32];
+    tmem_ld32(lane_base + T_DQ + i * kDh + hf * 32, r);
+    tmem_ld_wait();
+    if (pos < p.L)
+      store_row32_bf16(p.dqkv + static_cast<size_t>(seq_row0 + pos) * (3 * D) + h * kDh + hf * 32, r);
   }
 
   tc_fence_before();
@@ -588,14 +578,14 @@ extern "C" int tt_attn_causal_fwd(const void* qkv, void* ctx, float* lse, int B,
   CUtensorMap tm;
   int rc = make_rows_map(&tm, qkv, B * L, 3 * D);
   if (rc) return rc;
-  const size_t smem = 1024 + static_cast<size_t>(1 + 2 * p.nq + 4) * kTileBytes + 128;
+  const size_t smem = 1024 + static_cast<size_t>(1 + p.nq + 2) * kTileBytes + 64 + 2 * 128 * sizeof(float);
   static bool configured = false;
   if (!configured) {
     TT_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
     configured = true;
   }
   TT_REQUIRE(smem <= 232448, "tt_attn_causal_fwd: shared memory %zu too large", smem);
-  attn_fwd_kernel<<<B * H * p.nq, 128, smem, stream>>>(tm, p);
+  attn_fwd_kernel<<<B * H * p.nq, 256, smem, stream>>>(tm, p);
   TT_LAUNCH_CHECK();
   return TT_OK;
 }
@@ -635,7 +625,7 @@ extern "C" int tt_attn_causal_bwd(const void* qkv, const void* ctx, const void* 
     configured = true;
   }
   TT_REQUIRE(smem <= 232448, "tt_attn_causal_bwd: shared memory %zu too large", smem);
-  attn_bwd_kernel<<<B * H, 128, smem, stream>>>(tmQ, tmDO, p);
+  attn_bwd_kernel<<<B * H, 256, smem, stream>>>(tmQ, tmDO, p);
   TT_LAUNCH_CHECK();
   return TT_OK;
 }

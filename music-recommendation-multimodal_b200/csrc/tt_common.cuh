@@ -89,21 +89,29 @@ __device__ __forceinline__ float2 unpack_bf16(uint32_t u) {
   return __bfloat1622float2(v);
 }
 
-// Counter-based dropout decision. keep-probability = 1 - p, encoded as a 32-bit
-// threshold by the host (thresh = p * 2^32). Same (seed, site, idx) -> same bit in
-// forward and backward, so no mask tensor is stored.
-__device__ __forceinline__ uint32_t hash32(uint64_t x) {
-  x ^= x >> 33;
-  x *= 0xff51afd7ed558ccdULL;
-  x ^= x >> 33;
-  x *= 0xc4ceb9fe1a85ec53ULL;
-  x ^= x >> 33;
-  return static_cast<uint32_t>(x);
+// Counter-based dropout decision. keep-probability = 1 - p, encoded as a 32-bit threshold by
+// the host (thresh = p * 2^32). Same (seed, site, idx) -> same bit in forward and backward, so
+// no mask tensor is stored. The per-call key (seed, site) is loop-invariant; the per-element
+// cost is one xor + a 32-bit integer finaliser (two IMULs).
+__device__ __forceinline__ uint32_t mix32(uint32_t x) {
+  x ^= x >> 16;
+  x *= 0x7feb352dU;
+  x ^= x >> 15;
+  x *= 0x846ca68bU;
+  x ^= x >> 16;
+  return x;
 }
-__device__ __forceinline__ bool drop_keep(uint64_t seed, uint32_t site, uint64_t idx,
-                                          uint32_t thresh) {
-  return hash32(seed ^ (static_cast<uint64_t>(site) << 56) ^ (idx * 0x9E3779B97F4A7C15ULL)) >=
-         thresh;
+__device__ __forceinline__ uint32_t drop_key(uint64_t seed, uint32_t site) {
+  return mix32(static_cast<uint32_t>(seed) ^ mix32(static_cast<uint32_t>(seed >> 32) + site * 0x9E3779B9u));
+}
+__device__ __forceinline__ bool drop_keep(uint64_t seed, uint32_t site, uint64_t idx, uint32_t thresh) {
+  const uint32_t x = static_cast<uint32_t>(idx) ^ (static_cast<uint32_t>(idx >> 32) * 0x85EBCA6Bu);
+  return mix32(x ^ drop_key(seed, site)) >= thresh;
+}
+// 16-byte vector reduction into global memory (sm_90+: one RED instead of four)
+__device__ __forceinline__ void red_add_f32x4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d)
+               : "memory");
 }
 
 // ----------------------------------------------------------------------------

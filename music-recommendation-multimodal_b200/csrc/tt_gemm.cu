@@ -2,12 +2,14 @@
 //
 //   C[M,N] = epilogue(alpha * A[M,K] * B[N,K]^T), bf16 operands, fp32 accumulate in TMEM.
 //
-// One CTA per SM, 256 threads:
+// One CTA per SM, 384 threads:
 //   warp 0      : TMA producer (one elected lane) — A/B tiles, 128B swizzle, N-stage ring
 //   warp 1      : MMA issuer (one elected lane)  — tcgen05.mma M=128, N=block_n, K=16
 //   warp 2      : TMEM allocator (2 accumulator buffers of block_n columns)
-//   warps 4..7  : epilogue — tcgen05.ld (each warp owns a 32-lane quarter), fused
-//                 bias / ReLU / dropout / gate / residual, vector stores or red.add
+//   warps 4..11 : epilogue — tcgen05.ld (warp % 4 = TMEM lane quarter, two warps per quarter take
+//                 alternate 32-column chunks, next chunk prefetched), fused bias / ReLU / dropout /
+//                 gate / residual; all global traffic goes through a swizzled per-warp smem tile so
+//                 loads/stores are coalesced (4 rows x 128 B per instruction), split-K via red.v4
 // Three pipelines: smem full/empty (TMA<->MMA), TMEM full/empty (MMA<->epilogue) and the
 // static persistent tile loop. Operands may be K-major or MN-major (the transposed
 // layouts dgrad/wgrad need), selected by template flags and the UMMA descriptors.
@@ -42,106 +44,160 @@ struct GemmParams {
 static constexpr int kBlockM = 128;
 static constexpr int kBlockK = 64;
 static constexpr uint32_t kABytes = kBlockM * kBlockK * 2;  // 16 KB
-static constexpr int kGemmThreads = 256;
+static constexpr int kEpiWarps = 8;
+static constexpr int kGemmThreads = 128 + 32 * kEpiWarps;   // 4 control warps + 8 epilogue warps
+static constexpr uint32_t kStageBytesPerWarp = 32 * 128;     // 32 rows x 128 B staging tile
 
-__device__ __forceinline__ void gemm_epilogue_chunk(const GemmParams& p, const uint32_t (&r)[32],
-                                                    int row, int col0, uint64_t seed) {
+// Per-warp staging tile: 32 rows x 128 B, 16-byte units XOR-swizzled by (row & 7) so that both
+// the row-per-lane accesses (thread = accumulator row) and the transposed, coalesced accesses
+// (8 lanes = one 128 B row segment) are bank-conflict free.
+__device__ __forceinline__ uint4* stg_unit(uint8_t* stg, int row, int unit) {
+  return reinterpret_cast<uint4*>(stg + row * 128 + ((unit ^ (row & 7)) << 4));
+}
+
+// One 32-column chunk of one accumulator row per lane. The fused epilogue works on the lane's
+// row in registers; every global access goes through the staging tile so that a warp
+// instruction touches 4 rows x 128 contiguous bytes (fp32) or 8 rows x 64 bytes (bf16).
+__device__ __forceinline__ void gemm_epilogue_chunk(const GemmParams& p, const uint32_t (&r)[32], uint8_t* stg,
+                                                    int lane, int row0, int col0, uint64_t seed) {
+  const int row = row0 + lane;
   const int ncols = min(32, p.N - col0);
   float v[32];
 #pragma unroll
   for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * p.alpha;
 
-  if (ncols == 32) {
-    if (p.bias) {
+  if (p.bias) {
+    if (ncols == 32) {
 #pragma unroll
       for (int j = 0; j < 32; j += 4) {
-        float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
+        const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
         v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
       }
-    }
-    if (p.relu) {
-#pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-    }
-    if (p.drop_thresh) {
-      const uint64_t base = static_cast<uint64_t>(row) * p.N + col0;
+    } else {
 #pragma unroll
       for (int j = 0; j < 32; ++j)
-        v[j] = drop_keep(seed, p.drop_site, base + j, p.drop_thresh) ? v[j] * p.drop_scale
-                                                                            : 0.f;
+        if (j < ncols) v[j] += __ldg(p.bias + col0 + j);
     }
-    if (p.gate) {
-      const uint4* g = reinterpret_cast<const uint4*>(p.gate + static_cast<size_t>(row) * p.ld_gate + col0);
+  }
+  if (p.relu) {
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        uint4 u = __ldg(g + q);
-        uint32_t w[4] = {u.x, u.y, u.z, u.w};
+    for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+  }
+  if (p.drop_thresh) {
+    const uint64_t base = static_cast<uint64_t>(row) * p.N + col0;
 #pragma unroll
-        for (int h = 0; h < 4; ++h) {
-          float2 f = unpack_bf16(w[h]);
-          int j = q * 8 + h * 2;
-          v[j] = f.x > 0.f ? v[j] * p.gate_scale : 0.f;
-          v[j + 1] = f.y > 0.f ? v[j + 1] * p.gate_scale : 0.f;
-        }
+    for (int j = 0; j < 32; ++j)
+      v[j] = drop_keep(seed, p.drop_site, base + j, p.drop_thresh) ? v[j] * p.drop_scale : 0.f;
+  }
+  if (p.gate) {
+    // bf16 [M, ld_gate]: 32 columns = 64 B per row; a warp instruction covers 8 rows x 64 B
+    __syncwarp();
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const int rr = it * 8 + (lane >> 2), u = lane & 3;
+      uint4 x = make_uint4(0, 0, 0, 0);
+      const int gr = row0 + rr, gc = col0 + u * 8;
+      if (gr < p.M && gc + 8 <= p.N)
+        x = __ldg(reinterpret_cast<const uint4*>(p.gate + static_cast<size_t>(gr) * p.ld_gate + gc));
+      else if (gr < p.M) {
+        __nv_bfloat16 t[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+          t[e] = gc + e < p.N ? p.gate[static_cast<size_t>(gr) * p.ld_gate + gc + e] : __float2bfloat16_rn(0.f);
+        x = *reinterpret_cast<uint4*>(t);
       }
+      *stg_unit(stg, rr, u) = x;
     }
-    if (p.residual) {
-      const float4* rs = reinterpret_cast<const float4*>(p.residual + static_cast<size_t>(row) * p.ld_res + col0);
+    __syncwarp();
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        float4 x = __ldg(rs + q);
-        v[q * 4] += x.x; v[q * 4 + 1] += x.y; v[q * 4 + 2] += x.z; v[q * 4 + 3] += x.w;
-      }
-    }
-    if (p.out_f32) {
-      float* o = p.out_f32 + static_cast<size_t>(row) * p.ld_f32 + col0;
-      if (p.accumulate) {
+    for (int u = 0; u < 4; ++u) {
+      const uint4 x = *stg_unit(stg, lane, u);
+      const uint32_t w[4] = {x.x, x.y, x.z, x.w};
 #pragma unroll
-        for (int j = 0; j < 32; ++j) atomicAdd(o + j, v[j]);
-      } else {
-        float4* o4 = reinterpret_cast<float4*>(o);
-#pragma unroll
-        for (int q = 0; q < 8; ++q) o4[q] = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
-      }
-    }
-    if (p.out_bf16) {
-      uint4* o = reinterpret_cast<uint4*>(p.out_bf16 + static_cast<size_t>(row) * p.ld_bf16 + col0);
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        uint4 u;
-        u.x = pack_bf16(v[q * 8 + 0], v[q * 8 + 1]);
-        u.y = pack_bf16(v[q * 8 + 2], v[q * 8 + 3]);
-        u.z = pack_bf16(v[q * 8 + 4], v[q * 8 + 5]);
-        u.w = pack_bf16(v[q * 8 + 6], v[q * 8 + 7]);
-        o[q] = u;
-      }
-    }
-  } else {
-    // ragged right edge: scalar, fully guarded
-#pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      if (j < ncols) {
-        const int col = col0 + j;
-        float x = v[j];
-        if (p.bias) x += __ldg(p.bias + col);
-        if (p.relu) x = fmaxf(x, 0.f);
-        if (p.drop_thresh)
-          x = drop_keep(seed, p.drop_site, static_cast<uint64_t>(row) * p.N + col, p.drop_thresh)
-                  ? x * p.drop_scale
-                  : 0.f;
-        if (p.gate) {
-          float g = __bfloat162float(p.gate[static_cast<size_t>(row) * p.ld_gate + col]);
-          x = g > 0.f ? x * p.gate_scale : 0.f;
-        }
-        if (p.residual) x += __ldg(p.residual + static_cast<size_t>(row) * p.ld_res + col);
-        if (p.out_f32) {
-          float* o = p.out_f32 + static_cast<size_t>(row) * p.ld_f32 + col;
-          if (p.accumulate) atomicAdd(o, x); else *o = x;
-        }
-        if (p.out_bf16) p.out_bf16[static_cast<size_t>(row) * p.ld_bf16 + col] = __float2bfloat16_rn(x);
+      for (int h = 0; h < 4; ++h) {
+        const float2 f = unpack_bf16(w[h]);
+        const int j = u * 8 + h * 2;
+        v[j] = f.x > 0.f ? v[j] * p.gate_scale : 0.f;
+        v[j + 1] = f.y > 0.f ? v[j + 1] * p.gate_scale : 0.f;
       }
     }
   }
+  if (p.residual) {
+    __syncwarp();
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int rr = it * 4 + (lane >> 3), u = lane & 7;
+      float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+      const int gr = row0 + rr, gc = col0 + u * 4;
+      if (gr < p.M && gc + 4 <= p.N)
+        x = __ldg(reinterpret_cast<const float4*>(p.residual + static_cast<size_t>(gr) * p.ld_res + gc));
+      else if (gr < p.M) {
+        float t[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) t[e] = gc + e < p.N ? p.residual[static_cast<size_t>(gr) * p.ld_res + gc + e] : 0.f;
+        x = make_float4(t[0], t[1], t[2], t[3]);
+      }
+      *reinterpret_cast<float4*>(stg_unit(stg, rr, u)) = x;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const float4 x = *reinterpret_cast<const float4*>(stg_unit(stg, lane, u));
+      v[4 * u] += x.x; v[4 * u + 1] += x.y; v[4 * u + 2] += x.z; v[4 * u + 3] += x.w;
+    }
+  }
+  if (p.out_f32) {
+    __syncwarp();
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+      *reinterpret_cast<float4*>(stg_unit(stg, lane, u)) = make_float4(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]);
+    __syncwarp();
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int rr = it * 4 + (lane >> 3), u = lane & 7;
+      const int gr = row0 + rr, gc = col0 + u * 4;
+      if (gr >= p.M || gc >= p.N) continue;
+      const float4 x = *reinterpret_cast<const float4*>(stg_unit(stg, rr, u));
+      float* o = p.out_f32 + static_cast<size_t>(gr) * p.ld_f32 + gc;
+      if (gc + 4 <= p.N) {
+        if (p.accumulate) red_add_f32x4(o, x.x, x.y, x.z, x.w);
+        else *reinterpret_cast<float4*>(o) = x;
+      } else {
+        const float t[4] = {x.x, x.y, x.z, x.w};
+        for (int e = 0; e < 4 && gc + e < p.N; ++e) {
+          if (p.accumulate) atomicAdd(o + e, t[e]); else o[e] = t[e];
+        }
+      }
+    }
+  }
+  if (p.out_bf16) {
+    __syncwarp();
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      uint4 x;
+      x.x = pack_bf16(v[u * 8 + 0], v[u * 8 + 1]);
+      x.y = pack_bf16(v[u * 8 + 2], v[u * 8 + 3]);
+      x.z = pack_bf16(v[u * 8 + 4], v[u * 8 + 5]);
+      x.w = pack_bf16(v[u * 8 + 6], v[u * 8 + 7]);
+      *stg_unit(stg, lane, u) = x;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const int rr = it * 8 + (lane >> 2), u = lane & 3;
+      const int gr = row0 + rr, gc = col0 + u * 8;
+      if (gr >= p.M || gc >= p.N) continue;
+      const uint4 x = *stg_unit(stg, rr, u);
+      __nv_bfloat16* o = p.out_bf16 + static_cast<size_t>(gr) * p.ld_bf16 + gc;
+      if (gc + 8 <= p.N) {
+        *reinterpret_cast<uint4*>(o) = x;
+      } else {
+        const __nv_bfloat16* t = reinterpret_cast<const __nv_bfloat16*>(&x);
+        for (int e = 0; e < 8 && gc + e < p.N; ++e) o[e] = t[e];
+      }
+    }
+  }
+  __syncwarp();
 }
 
 template <bool A_MN, bool B_MN>
@@ -160,7 +216,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   uint8_t* sA = smem;
   uint8_t* sB = smem + static_cast<size_t>(stages) * kABytes;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sB + static_cast<size_t>(stages) * b_bytes);
+  uint8_t* sStage = sB + static_cast<size_t>(stages) * b_bytes;  // kEpiWarps x 4 KB staging tiles
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sStage + kEpiWarps * kStageBytesPerWarp);
   uint64_t* empty_bar = full_bar + stages;
   uint64_t* tfull_bar = empty_bar + stages;
   uint64_t* tempty_bar = tfull_bar + 2;
@@ -179,7 +236,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull_bar[a], 1);
-      mbar_init(&tempty_bar[a], 4);
+      mbar_init(&tempty_bar[a], kEpiWarps);
     }
     fence_barrier_init();
   }
@@ -258,8 +315,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
     }
   } else if (warp >= 4) {
-    const int ew = warp - 4;  // == warp % 4: the TMEM lane quarter this warp may read
+    // 8 epilogue warps: warp % 4 selects the TMEM lane quarter (hardware rule), the two warps
+    // sharing a quarter take alternate 32-column chunks of the tile.
+    const int ew = warp - 4;
+    const int q = ew & 3, half = ew >> 2;
+    uint8_t* stg = sStage + static_cast<size_t>(ew) * kStageBytesPerWarp;
     const uint64_t seed = p.drop_seed + ((p.drop_thresh && p.drop_seed_dev) ? *p.drop_seed_dev : 0ull);
+    const int nchunks = block_n / 32;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
@@ -268,16 +330,25 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_wait(&tfull_bar[acc], acc_phase);
       __syncwarp();
       tc_fence_after();
-      const int row = m_blk * kBlockM + ew * 32 + lane;
-      const uint32_t t_base = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) +
+      const int row0 = m_blk * kBlockM + q * 32;
+      const uint32_t t_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
                               static_cast<uint32_t>(acc * block_n);
-      for (int c = 0; c < block_n / 32; ++c) {
-        uint32_t r[32];
-        tmem_ld32(t_base + static_cast<uint32_t>(c * 32), r);
+      uint32_t r0[32], r1[32];
+      const int colbase = n_blk * block_n;
+      int c = half;
+      if (c < nchunks) tmem_ld32(t_base + static_cast<uint32_t>(c * 32), r0);
+      while (c < nchunks) {
         tmem_ld_wait();
-        const int col0 = n_blk * block_n + c * 32;
-        if (row < p.M && col0 < p.N) gemm_epilogue_chunk(p, r, row, col0, seed);
+        if (c + 2 < nchunks) tmem_ld32(t_base + static_cast<uint32_t>((c + 2) * 32), r1);
+        if (row0 < p.M && colbase + c * 32 < p.N) gemm_epilogue_chunk(p, r0, stg, lane, row0, colbase + c * 32, seed);
+        c += 2;
+        if (c >= nchunks) break;
+        tmem_ld_wait();
+        if (c + 2 < nchunks) tmem_ld32(t_base + static_cast<uint32_t>((c + 2) * 32), r0);
+        if (row0 < p.M && colbase + c * 32 < p.N) gemm_epilogue_chunk(p, r1, stg, lane, row0, colbase + c * 32, seed);
+        c += 2;
       }
+      tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
@@ -293,7 +364,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
 static size_t gemm_smem_bytes(int block_n, int stages) {
   return 1024 + static_cast<size_t>(stages) * (kABytes + static_cast<size_t>(block_n) * kBlockK * 2) +
-         (2 * stages + 4) * sizeof(uint64_t) + 16;
+         kEpiWarps * kStageBytesPerWarp + (2 * stages + 4) * sizeof(uint64_t) + 16;
 }
 
 template <bool A_MN, bool B_MN>
@@ -338,11 +409,14 @@ extern "C" int tt_gemm_bf16(const tt_gemm_args* a, void* stream_) {
   GemmParams p;
   p.M = a->M; p.N = a->N; p.K = a->K;
   int bn = a->block_n;
-  if (bn == 0) bn = a->N > 128 ? 256 : (a->N > 64 ? 128 : 64);
+  if (bn == 0) {
+    if (a->accumulate) bn = a->N >= 512 ? 128 : 64;   // split-K: prefer output tiles over k-splits
+    else bn = a->N > 128 ? 256 : (a->N > 64 ? 128 : 64);
+  }
   TT_REQUIRE(bn == 64 || bn == 128 || bn == 256, "tt_gemm_bf16: block_n must be 64/128/256");
   p.block_n = bn;
   const size_t stage_bytes = kABytes + static_cast<size_t>(bn) * kBlockK * 2;
-  int stages = static_cast<int>((200 * 1024) / stage_bytes);
+  int stages = static_cast<int>((232448 - 1024 - kEpiWarps * kStageBytesPerWarp - 256) / stage_bytes);
   if (stages > 8) stages = 8;
   p.stages = stages;
 

@@ -33,6 +33,7 @@ static constexpr uint32_t kTile16K = 128 * 64 * 2;
 static constexpr int kBStages = 5;
 static constexpr int kTopkThreads = 384;
 static constexpr int kCap = 512;       // candidate list capacity per (range, row)
+static constexpr int kPoolCap = 4096;  // finalize: per-user key pool in shared memory
 
 __device__ __forceinline__ uint32_t f2ord(float f) {
   const uint32_t u = __float_as_uint(f + 0.0f);  // -0 -> +0
@@ -94,6 +95,53 @@ __device__ int warp_prune(unsigned long long* buf, int n, int kprime, int lane, 
   __syncwarp();
   T = t;
   return base;
+}
+
+// Filter one 32-score chunk of this lane's user row against the row threshold. The common case
+// (no score of any lane beats its threshold) costs a max tree and one vote; otherwise only the
+// 4-score groups that actually contain a candidate are examined.
+__device__ __forceinline__ void scan_chunk(const uint32_t (&r)[32], int idx0, const TopkParams& p, int lane, int row,
+                                           unsigned long long* buf, int& cnt, unsigned long long& thr_key,
+                                           float& thr_s) {
+  float g[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k)
+    g[k] = fmaxf(fmaxf(__uint_as_float(r[4 * k]), __uint_as_float(r[4 * k + 1])),
+                 fmaxf(__uint_as_float(r[4 * k + 2]), __uint_as_float(r[4 * k + 3])));
+  const float mx = fmaxf(fmaxf(fmaxf(g[0], g[1]), fmaxf(g[2], g[3])), fmaxf(fmaxf(g[4], g[5]), fmaxf(g[6], g[7])));
+  if (!__any_sync(0xffffffffu, mx >= thr_s)) return;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    if (g[k] >= thr_s) {
+#pragma unroll
+      for (int t = 4 * k; t < 4 * k + 4; ++t) {
+        const float s = __uint_as_float(r[t]);
+        if (s >= thr_s) {
+          const int idx = idx0 + t;
+          const uint32_t gidx = static_cast<uint32_t>(p.item_base + idx);
+          if (idx < p.N && !(p.mask_item0 && gidx == 0u)) {
+            const unsigned long long key = make_key(s, gidx);
+            if (key > thr_key) buf[cnt++] = key;
+          }
+        }
+      }
+    }
+  }
+  unsigned full = __ballot_sync(0xffffffffu, cnt > kCap - 32);
+  while (full) {
+    const int src = __ffs(full) - 1;
+    full &= full - 1;
+    const unsigned long long bsrc = __shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(buf), src);
+    const int nsrc = __shfl_sync(0xffffffffu, cnt, src);
+    unsigned long long T;
+    const int ncnt = warp_prune(reinterpret_cast<unsigned long long*>(bsrc), nsrc, p.kprime, lane, T);
+    if (lane == src) {
+      cnt = ncnt;
+      thr_key = T;
+      thr_s = key_score(T);
+      atomicMax(p.thr + row, T);
+    }
+  }
 }
 
 __global__ void __launch_bounds__(kTopkThreads, 1)
@@ -220,45 +268,16 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant
         tc_fence_after();
         const uint32_t t_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
                                 static_cast<uint32_t>(acc * 256 + mt * 128);
+        uint32_t r0[32], r1[32];
+        tmem_ld32(t_base, r0);
 #pragma unroll 1
-        for (int c = 0; c < kIT / 32; ++c) {
-          uint32_t r[32];
-          tmem_ld32(t_base + c * 32, r);
+        for (int c = 0; c < kIT / 32; c += 2) {
           tmem_ld_wait();
-          float mx = __uint_as_float(r[0]);
-#pragma unroll
-          for (int t = 1; t < 32; ++t) mx = fmaxf(mx, __uint_as_float(r[t]));
-          if (__any_sync(0xffffffffu, mx >= thr_s)) {
-            const int idx0 = tile * kIT + c * 32;  // shard-local item index of r[0]
-#pragma unroll
-            for (int t = 0; t < 32; ++t) {
-              const float s = __uint_as_float(r[t]);
-              if (s >= thr_s) {
-                const int idx = idx0 + t;
-                const uint32_t gidx = static_cast<uint32_t>(p.item_base + idx);
-                if (idx < p.N && !(p.mask_item0 && gidx == 0u)) {
-                  const unsigned long long key = make_key(s, gidx);
-                  if (key > thr_key) buf[cnt++] = key;
-                }
-              }
-            }
-            unsigned full = __ballot_sync(0xffffffffu, cnt > kCap - 32);
-            while (full) {
-              const int src = __ffs(full) - 1;
-              full &= full - 1;
-              const unsigned long long bsrc =
-                  __shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(buf), src);
-              const int nsrc = __shfl_sync(0xffffffffu, cnt, src);
-              unsigned long long T;
-              const int ncnt = warp_prune(reinterpret_cast<unsigned long long*>(bsrc), nsrc, p.kprime, lane, T);
-              if (lane == src) {
-                cnt = ncnt;
-                thr_key = T;
-                thr_s = key_score(T);
-                atomicMax(p.thr + row, T);
-              }
-            }
-          }
+          tmem_ld32(t_base + (c + 1) * 32, r1);
+          scan_chunk(r0, tile * kIT + c * 32, p, lane, row, buf, cnt, thr_key, thr_s);
+          tmem_ld_wait();
+          if (c + 2 < kIT / 32) tmem_ld32(t_base + (c + 2) * 32, r0);
+          scan_chunk(r1, tile * kIT + (c + 1) * 32, p, lane, row, buf, cnt, thr_key, thr_s);
         }
         tc_fence_before();
         __syncwarp();
@@ -282,6 +301,7 @@ struct FinalizeParams {
   int U, N, item_base, n_ranges, u_pad, kprime, K;
   const unsigned long long* cand;
   const int* cand_cnt;
+  const unsigned long long* thr;  // [u_pad] published thresholds
   const float* users;   // [U, 256] fp32
   const float* items;   // [N, 256] fp32 (this shard)
   float eps;            // bound on |bf16-path score - exact score|
@@ -321,26 +341,44 @@ __device__ __forceinline__ void bitonic_sort_desc_256(unsigned long long* keys) 
 __global__ void __launch_bounds__(256) topk_finalize_kernel(const FinalizeParams p) {
   __shared__ unsigned long long s_keys[256];
   __shared__ unsigned long long s_sel[256];
+  __shared__ unsigned long long s_pool[kPoolCap];
   __shared__ int s_red[8];
   __shared__ int s_n;
   const int u = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
-  // total number of candidate keys of this user
+  // Gather this user's candidate keys into shared memory, dropping everything below the published
+  // threshold thr[u] (= the largest "K'-th best so far" any work unit reached: at least K' keys
+  // are >= it, so nothing below can be in the final top K').
+  const unsigned long long floor_key = p.thr[u];
+  if (tid == 0) s_n = 0;
+  __syncthreads();
   int total = 0;
-  for (int r = 0; r < p.n_ranges; ++r) total += p.cand_cnt[static_cast<size_t>(r) * p.u_pad + u];
+  for (int r = 0; r < p.n_ranges; ++r) {
+    const int n = p.cand_cnt[static_cast<size_t>(r) * p.u_pad + u];
+    total += n;
+    const unsigned long long* b = p.cand + (static_cast<size_t>(r) * p.u_pad + u) * kCap;
+    for (int i = tid; i < n; i += 256) {
+      const unsigned long long k = b[i];
+      if (k >= floor_key) {
+        const int pos = atomicAdd(&s_n, 1);
+        if (pos < kPoolCap) s_pool[pos] = k;
+      }
+    }
+  }
+  __syncthreads();
+  const int npool = s_n;
+  const bool overflow = npool > kPoolCap;   // pathological tie floods: fall back to the exact path
+  const int np = min(npool, kPoolCap);
+  __syncthreads();
 
-  // K'-th largest key over all ranges (bitwise binary search, counts re-read from L2)
+  // K'-th largest key of the pool (bitwise binary search over shared memory)
   unsigned long long T = 0;
-  if (total > p.kprime) {
+  if (np > p.kprime) {
     for (int bit = 63; bit >= 0; --bit) {
       const unsigned long long cand = T | (1ull << bit);
       int c = 0;
-      for (int r = 0; r < p.n_ranges; ++r) {
-        const int n = p.cand_cnt[static_cast<size_t>(r) * p.u_pad + u];
-        const unsigned long long* b = p.cand + (static_cast<size_t>(r) * p.u_pad + u) * kCap;
-        for (int i = tid; i < n; i += 256) c += (b[i] >= cand);
-      }
+      for (int i = tid; i < np; i += 256) c += (s_pool[i] >= cand);
       c = block_sum_int(c, s_red);
       if (c >= p.kprime) {
         T = cand;
@@ -348,23 +386,19 @@ __global__ void __launch_bounds__(256) topk_finalize_kernel(const FinalizeParams
       }
     }
   }
-  // compaction of keys >= T into s_sel (order irrelevant: re-sorted after the exact re-score)
   if (tid == 0) s_n = 0;
   s_keys[tid] = 0ull;
   __syncthreads();
-  for (int r = 0; r < p.n_ranges; ++r) {
-    const int n = p.cand_cnt[static_cast<size_t>(r) * p.u_pad + u];
-    const unsigned long long* b = p.cand + (static_cast<size_t>(r) * p.u_pad + u) * kCap;
-    for (int i = tid; i < n; i += 256) {
-      const unsigned long long k = b[i];
-      if (k >= T) {
-        const int pos = atomicAdd(&s_n, 1);
-        if (pos < 256) s_sel[pos] = k;
-      }
+  for (int i = tid; i < np; i += 256) {
+    const unsigned long long k = s_pool[i];
+    if (k >= T) {
+      const int pos = atomicAdd(&s_n, 1);
+      if (pos < 256) s_sel[pos] = k;
     }
   }
   __syncthreads();
   const int nsel = min(s_n, 256);
+  if (T < floor_key) T = floor_key;   // every non-pool item has key <= floor_key: bound for the certificate
 
   // exact re-score: fp32 inputs, fp64 accumulate, one rounding to fp32
   const float* urow = p.users + static_cast<size_t>(u) * kD;
@@ -399,8 +433,8 @@ __global__ void __launch_bounds__(256) topk_finalize_kernel(const FinalizeParams
   if (tid == 0) {
     // Certificate: every non-candidate has bf16-path key < T, hence exact score <= score(T) + eps.
     // If the exact K-th best beats that, no non-candidate can enter the top K.
-    int flag = 0;
-    if (total > p.kprime) {
+    int flag = overflow ? 1 : 0;
+    if (!overflow && total > p.kprime) {
       const int kth = min(p.K, nsel) - 1;
       flag = !(key_score(s_keys[kth]) > key_score(T) + p.eps);
     }
@@ -598,18 +632,18 @@ extern "C" int tt_score_topk(const void* users_bf16, const void* items_bf16, int
   return TT_OK;
 }
 
-extern "C" int tt_topk_finalize(const tt_topk_plan* plan, const void* cand, const int32_t* cand_cnt,
+extern "C" int tt_topk_finalize(const tt_topk_plan* plan, const void* cand, const int32_t* cand_cnt, const void* thr,
                                 const float* users_f32, const float* items_f32, int item_base, int K, float eps,
                                 int32_t* out_idx, float* out_score, int32_t* flags, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  TT_REQUIRE(plan && cand && cand_cnt && users_f32 && items_f32 && out_idx && out_score && flags,
+  TT_REQUIRE(plan && cand && cand_cnt && thr && users_f32 && items_f32 && out_idx && out_score && flags,
              "tt_topk_finalize: null pointer");
   TT_REQUIRE(K > 0 && K <= plan->kprime, "tt_topk_finalize: K=%d must be in [1, kprime=%d]", K, plan->kprime);
   FinalizeParams p;
   p.U = plan->U; p.N = plan->N; p.item_base = item_base; p.n_ranges = plan->n_ranges;
   p.u_pad = plan->n_ut * kUT; p.kprime = plan->kprime; p.K = K;
   p.cand = static_cast<const unsigned long long*>(cand);
-  p.cand_cnt = cand_cnt; p.users = users_f32; p.items = items_f32; p.eps = eps;
+  p.cand_cnt = cand_cnt; p.thr = static_cast<const unsigned long long*>(thr); p.users = users_f32; p.items = items_f32; p.eps = eps;
   p.out_idx = out_idx; p.out_score = out_score; p.flags = flags;
   topk_finalize_kernel<<<plan->U, 256, 0, stream>>>(p);
   TT_LAUNCH_CHECK();

@@ -581,13 +581,8 @@ __global__ void __launch_bounds__(kRowThreads) embed_ln_bwd_kernel(const EmbedBw
     if (id != 0) {
       float* dst = p.dE + static_cast<size_t>(id) * W;
 #pragma unroll
-      for (int k = 0; k < NV; ++k) {
-        float* d4 = dst + (k * 32 + lane) * 4;
-        atomicAdd(d4 + 0, g[4 * k + 0]);
-        atomicAdd(d4 + 1, g[4 * k + 1]);
-        atomicAdd(d4 + 2, g[4 * k + 2]);
-        atomicAdd(d4 + 3, g[4 * k + 3]);
-      }
+      for (int k = 0; k < NV; ++k)
+        red_add_f32x4(dst + (k * 32 + lane) * 4, g[4 * k + 0], g[4 * k + 1], g[4 * k + 2], g[4 * k + 3]);
     }
   }
 #pragma unroll

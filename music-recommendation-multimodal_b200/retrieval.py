@@ -86,7 +86,8 @@ def retrieve_topk(user_emb: torch.Tensor, index: CatalogIndex, K: int, kprime: i
     out_idx = torch.empty(U, K, device=dev, dtype=torch.int32)
     out_score = torch.empty(U, K, device=dev, dtype=torch.float32)
     flags = torch.empty(U, device=dev, dtype=torch.int32)
-    check(lib().tt_topk_finalize(ctypes.byref(plan), sc["cand"].data_ptr(), sc["cnt"].data_ptr(), user_emb.data_ptr(),
+    check(lib().tt_topk_finalize(ctypes.byref(plan), sc["cand"].data_ptr(), sc["cnt"].data_ptr(),
+                                 sc["thr"].data_ptr(), user_emb.data_ptr(),
                                  index.table.data_ptr(), index.item_base, K, eps, out_idx.data_ptr(),
                                  out_score.data_ptr(), flags.data_ptr(), _stream()), "tt_topk_finalize")
     n_fallback = 0
