@@ -347,30 +347,51 @@ __global__ void __launch_bounds__(256) topk_finalize_kernel(const FinalizeParams
   const int u = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
-  // Gather this user's candidate keys into shared memory, dropping everything below the published
-  // threshold thr[u] (= the largest "K'-th best so far" any work unit reached: at least K' keys
-  // are >= it, so nothing below can be in the final top K').
-  const unsigned long long floor_key = p.thr[u];
-  if (tid == 0) s_n = 0;
-  __syncthreads();
+  // Gather this user's candidate keys into shared memory, dropping everything below a floor key
+  // that is known to have at least K' keys at or above it. First floor: the published threshold
+  // thr[u] (the largest "K'-th best of one work unit"). If the pool still overflows, the floor is
+  // raised by a bitwise search over the keys in global memory that stops as soon as the count fits.
+  unsigned long long floor_key = p.thr[u];
   int total = 0;
-  for (int r = 0; r < p.n_ranges; ++r) {
-    const int n = p.cand_cnt[static_cast<size_t>(r) * p.u_pad + u];
-    total += n;
-    const unsigned long long* b = p.cand + (static_cast<size_t>(r) * p.u_pad + u) * kCap;
-    for (int i = tid; i < n; i += 256) {
-      const unsigned long long k = b[i];
-      if (k >= floor_key) {
-        const int pos = atomicAdd(&s_n, 1);
-        if (pos < kPoolCap) s_pool[pos] = k;
+  for (int r = 0; r < p.n_ranges; ++r) total += p.cand_cnt[static_cast<size_t>(r) * p.u_pad + u];
+  int npool = 0;
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    if (tid == 0) s_n = 0;
+    __syncthreads();
+    for (int r = 0; r < p.n_ranges; ++r) {
+      const int n = p.cand_cnt[static_cast<size_t>(r) * p.u_pad + u];
+      const unsigned long long* b = p.cand + (static_cast<size_t>(r) * p.u_pad + u) * kCap;
+      for (int i = tid; i < n; i += 256) {
+        const unsigned long long k = b[i];
+        if (k >= floor_key) {
+          const int pos = atomicAdd(&s_n, 1);
+          if (pos < kPoolCap) s_pool[pos] = k;
+        }
       }
     }
+    __syncthreads();
+    npool = s_n;
+    __syncthreads();
+    if (npool <= kPoolCap || attempt == 1) break;
+    unsigned long long t = 0;
+    for (int bit = 63; bit >= 0; --bit) {
+      const unsigned long long cand = t | (1ull << bit);
+      int c = 0;
+      for (int r = 0; r < p.n_ranges; ++r) {
+        const int n = p.cand_cnt[static_cast<size_t>(r) * p.u_pad + u];
+        const unsigned long long* b = p.cand + (static_cast<size_t>(r) * p.u_pad + u) * kCap;
+        for (int i = tid; i < n; i += 256) c += (b[i] >= cand);
+      }
+      c = block_sum_int(c, s_red);
+      if (c >= p.kprime) {
+        t = cand;
+        if (c <= kPoolCap) break;
+      }
+    }
+    if (t > floor_key) floor_key = t;
   }
-  __syncthreads();
-  const int npool = s_n;
-  const bool overflow = npool > kPoolCap;   // pathological tie floods: fall back to the exact path
+  const bool overflow = npool > kPoolCap;   // only massive exact-tie floods: exact fallback
   const int np = min(npool, kPoolCap);
-  __syncthreads();
 
   // K'-th largest key of the pool (bitwise binary search over shared memory)
   unsigned long long T = 0;
@@ -577,7 +598,7 @@ extern "C" int tt_topk_plan_make(int U, int N, int kprime, tt_topk_plan* plan) {
   plan->n_ut = (U + kUT - 1) / kUT;
   const int total_tiles = (N + kIT - 1) / kIT;
   int n_ranges = (4 * num_sms() + plan->n_ut - 1) / plan->n_ut;
-  const int max_ranges = (total_tiles + 15) / 16;  // at least 16 item tiles per range
+  const int max_ranges = (total_tiles + 63) / 64;  // at least 64 item tiles (8192 items) per range
   if (n_ranges > max_ranges) n_ranges = max_ranges;
   if (n_ranges < 1) n_ranges = 1;
   plan->tiles_per_range = (total_tiles + n_ranges - 1) / n_ranges;
