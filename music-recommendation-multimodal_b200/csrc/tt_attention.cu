@@ -161,6 +161,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
   const float c1 = p.scale * kLog2e;
   const float mc = m * c1;
   const uint64_t seed = p.drop_seed + ((p.drop_thresh && p.drop_seed_dev) ? *p.drop_seed_dev : 0ull);
+  const uint32_t dkey = drop_key(seed, p.drop_site);
 
   // ---- pass B: P_j -> smem (bf16, swizzled), O += P_j V_j ------------------------------
   float l = 0.f;
@@ -186,8 +187,22 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
           float e = fast_exp2(__uint_as_float(r[t]) * c1 - mc);
           if (diag && kv0 + t > q_pos) e = 0.f;
           l += e;
-          if (p.drop_thresh) e = drop_keep(seed, p.drop_site, didx0 + t, p.drop_thresh) ? e * p.drop_scale : 0.f;
           pv[t] = e;
+        }
+        if (p.drop_thresh) {
+          if ((didx0 & 1u) == 0u) {
+#pragma unroll
+            for (int t = 0; t < 32; t += 2) {
+              bool k0, k1;
+              drop_keep_pair(dkey, didx0 + t, p.drop_thresh, k0, k1);
+              pv[t] = k0 ? pv[t] * p.drop_scale : 0.f;
+              pv[t + 1] = k1 ? pv[t + 1] * p.drop_scale : 0.f;
+            }
+          } else {
+#pragma unroll
+            for (int t = 0; t < 32; ++t)
+              pv[t] = drop_keep_k(dkey, didx0 + t, p.drop_thresh) ? pv[t] * p.drop_scale : 0.f;
+          }
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
@@ -381,6 +396,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
 
   const float c1 = p.scale * kLog2e;
   const uint64_t seed = p.drop_seed + ((p.drop_thresh && p.drop_seed_dev) ? *p.drop_seed_dev : 0ull);
+  const uint32_t dkey = drop_key(seed, p.drop_site);
   const uint32_t idesc_s = umma_idesc_bf16(kTile, kTile, false, false);    // Q K^T, dO V^T
   const uint32_t idesc_t = umma_idesc_bf16(kTile, kDh, true, true);        // X^T Y (dV, dK)
   const uint32_t idesc_q = umma_idesc_bf16(kTile, kDh, false, true);       // dS K
@@ -434,19 +450,31 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
           tmem_ld_wait();
           const int kv0 = j * kTile + cg * 32;
           const uint32_t didx0 = (static_cast<uint32_t>(bh) * p.L + q_pos) * p.L + kv0;
+          uint32_t keepmask = 0xFFFFFFFFu;
+          if (p.drop_thresh) {
+            keepmask = 0u;
+            if ((didx0 & 1u) == 0u) {
+#pragma unroll
+              for (int t = 0; t < 32; t += 2) {
+                bool k0, k1;
+                drop_keep_pair(dkey, didx0 + t, p.drop_thresh, k0, k1);
+                keepmask |= (k0 ? 1u : 0u) << t;
+                keepmask |= (k1 ? 1u : 0u) << (t + 1);
+              }
+            } else {
+#pragma unroll
+              for (int t = 0; t < 32; ++t)
+                keepmask |= (drop_keep_k(dkey, didx0 + t, p.drop_thresh) ? 1u : 0u) << t;
+            }
+          }
           float pd[32], ds[32];
 #pragma unroll
           for (int t = 0; t < 32; ++t) {
             float pr = fast_exp2(__uint_as_float(rs[t]) * c1 - lse2);
             if ((diag && kv0 + t > q_pos) || !row_ok) pr = 0.f;
-            float dp = __uint_as_float(rp[t]);
-            float pdrop = pr;
-            if (p.drop_thresh) {
-              const bool keep = drop_keep(seed, p.drop_site, didx0 + t, p.drop_thresh);
-              pdrop = keep ? pr * p.drop_scale : 0.f;
-              dp = keep ? dp * p.drop_scale : 0.f;
-            }
-            pd[t] = pdrop;
+            const bool keep = (keepmask >> t) & 1u;
+            const float dp = keep ? __uint_as_float(rp[t]) * p.drop_scale : 0.f;
+            pd[t] = keep ? pr * p.drop_scale : 0.f;
             ds[t] = pr * (dp - delta) * p.scale;
           }
 #pragma unroll

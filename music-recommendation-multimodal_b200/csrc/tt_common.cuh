@@ -104,9 +104,24 @@ __device__ __forceinline__ uint32_t mix32(uint32_t x) {
 __device__ __forceinline__ uint32_t drop_key(uint64_t seed, uint32_t site) {
   return mix32(static_cast<uint32_t>(seed) ^ mix32(static_cast<uint32_t>(seed >> 32) + site * 0x9E3779B9u));
 }
+// One 32-bit hash decides TWO consecutive elements (16 bits each, compared with the top 16 bits
+// of the threshold): element idx uses half (idx & 1) of hash(idx >> 1).
+__device__ __forceinline__ bool drop_keep_k(uint32_t key, uint64_t idx, uint32_t thresh) {
+  const uint64_t pair = idx >> 1;
+  const uint32_t x = static_cast<uint32_t>(pair) ^ (static_cast<uint32_t>(pair >> 32) * 0x85EBCA6Bu);
+  const uint32_t h = mix32(x ^ key);
+  const uint32_t bits = (idx & 1) ? (h >> 16) : (h & 0xFFFFu);
+  return bits >= (thresh >> 16);
+}
 __device__ __forceinline__ bool drop_keep(uint64_t seed, uint32_t site, uint64_t idx, uint32_t thresh) {
-  const uint32_t x = static_cast<uint32_t>(idx) ^ (static_cast<uint32_t>(idx >> 32) * 0x85EBCA6Bu);
-  return mix32(x ^ drop_key(seed, site)) >= thresh;
+  return drop_keep_k(drop_key(seed, site), idx, thresh);
+}
+// Pair form for an EVEN 32-bit index: k0 = keep(idx_even), k1 = keep(idx_even + 1), one hash.
+__device__ __forceinline__ void drop_keep_pair(uint32_t key, uint32_t idx_even, uint32_t thresh, bool& k0, bool& k1) {
+  const uint32_t h = mix32((idx_even >> 1) ^ key);
+  const uint32_t t16 = thresh >> 16;
+  k0 = (h & 0xFFFFu) >= t16;
+  k1 = (h >> 16) >= t16;
 }
 // 16-byte vector reduction into global memory (sm_90+: one RED instead of four)
 __device__ __forceinline__ void red_add_f32x4(float* addr, float a, float b, float c, float d) {

@@ -15,6 +15,7 @@
 // layouts dgrad/wgrad need), selected by template flags and the UMMA descriptors.
 #include "../../include/tt_b200.h"
 #include "tt_common.cuh"
+#include <stdlib.h>
 
 namespace tt {
 
@@ -39,6 +40,7 @@ struct GemmParams {
   __nv_bfloat16* out_bf16;
   int ld_bf16;
   int accumulate;
+  int debug;  // profiling knob: 1 = epilogue drains TMEM only (no math, no global IO)
 };
 
 static constexpr int kBlockM = 128;
@@ -47,6 +49,7 @@ static constexpr uint32_t kABytes = kBlockM * kBlockK * 2;  // 16 KB
 static constexpr int kEpiWarps = 8;
 static constexpr int kGemmThreads = 128 + 32 * kEpiWarps;   // 4 control warps + 8 epilogue warps
 static constexpr uint32_t kStageBytesPerWarp = 32 * 128;     // 32 rows x 128 B staging tile
+static constexpr uint32_t kEpiBytesPerWarp = 2 * kStageBytesPerWarp + 512;  // out tile, in tile, 128 bias floats
 
 // Per-warp staging tile: 32 rows x 128 B, 16-byte units XOR-swizzled by (row & 7) so that both
 // the row-per-lane accesses (thread = accumulator row) and the transposed, coalesced accesses
@@ -54,29 +57,49 @@ static constexpr uint32_t kStageBytesPerWarp = 32 * 128;     // 32 rows x 128 B 
 __device__ __forceinline__ uint4* stg_unit(uint8_t* stg, int row, int unit) {
   return reinterpret_cast<uint4*>(stg + row * 128 + ((unit ^ (row & 7)) << 4));
 }
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
-// One 32-column chunk of one accumulator row per lane. The fused epilogue works on the lane's
-// row in registers; every global access goes through the staging tile so that a warp
-// instruction touches 4 rows x 128 contiguous bytes (fp32) or 8 rows x 64 bytes (bf16).
-__device__ __forceinline__ void gemm_epilogue_chunk(const GemmParams& p, const uint32_t (&r)[32], uint8_t* stg,
-                                                    int lane, int row0, int col0, uint64_t seed) {
+// Asynchronously fetch the residual (fp32, 32 rows x 128 B) or gate (bf16, 32 rows x 64 B) block of
+// one 32-column chunk into the warp's "in" tile: global -> shared without registers, coalesced
+// (4 rows x 128 B resp. 8 rows x 64 B per warp instruction), one chunk ahead of its use.
+__device__ __forceinline__ void epi_prefetch(const GemmParams& p, uint8_t* in, int lane, int row0, int col0) {
+  if (p.residual) {
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int rr = it * 4 + (lane >> 3), u = lane & 7;
+      const int gr = row0 + rr, gc = col0 + u * 4;
+      if (gr < p.M && gc + 4 <= p.N) cp_async16(stg_unit(in, rr, u), p.residual + static_cast<size_t>(gr) * p.ld_res + gc);
+    }
+  } else if (p.gate) {
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const int rr = it * 8 + (lane >> 2), u = lane & 3;
+      const int gr = row0 + rr, gc = col0 + u * 8;
+      if (gr < p.M && gc + 8 <= p.N) cp_async16(stg_unit(in, rr, u), p.gate + static_cast<size_t>(gr) * p.ld_gate + gc);
+    }
+  }
+  cp_async_commit();
+}
+
+// One 32-column chunk of one accumulator row per lane. `next_col0` >= 0 asks for the prefetch of
+// the warp's next chunk once the current "in" tile has been consumed.
+__device__ __forceinline__ void gemm_epilogue_chunk(const GemmParams& p, const uint32_t (&r)[32], uint8_t* out,
+                                                    uint8_t* in, const float* sbias, int lane, int row0, int col0,
+                                                    int next_col0, uint32_t dkey) {
   const int row = row0 + lane;
-  const int ncols = min(32, p.N - col0);
   float v[32];
 #pragma unroll
   for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * p.alpha;
 
   if (p.bias) {
-    if (ncols == 32) {
 #pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
-        v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
-      }
-    } else {
-#pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (j < ncols) v[j] += __ldg(p.bias + col0 + j);
+    for (int j = 0; j < 32; j += 4) {
+      const float4 b = *reinterpret_cast<const float4*>(sbias + j);   // same address in every lane: broadcast
+      v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
     }
   }
   if (p.relu) {
@@ -84,94 +107,60 @@ __device__ __forceinline__ void gemm_epilogue_chunk(const GemmParams& p, const u
     for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
   }
   if (p.drop_thresh) {
-    const uint64_t base = static_cast<uint64_t>(row) * p.N + col0;
+    const uint32_t base = static_cast<uint32_t>(row) * static_cast<uint32_t>(p.N) + static_cast<uint32_t>(col0);
 #pragma unroll
-    for (int j = 0; j < 32; ++j)
-      v[j] = drop_keep(seed, p.drop_site, base + j, p.drop_thresh) ? v[j] * p.drop_scale : 0.f;
-  }
-  if (p.gate) {
-    // bf16 [M, ld_gate]: 32 columns = 64 B per row; a warp instruction covers 8 rows x 64 B
-    __syncwarp();
-#pragma unroll
-    for (int it = 0; it < 4; ++it) {
-      const int rr = it * 8 + (lane >> 2), u = lane & 3;
-      uint4 x = make_uint4(0, 0, 0, 0);
-      const int gr = row0 + rr, gc = col0 + u * 8;
-      if (gr < p.M && gc + 8 <= p.N)
-        x = __ldg(reinterpret_cast<const uint4*>(p.gate + static_cast<size_t>(gr) * p.ld_gate + gc));
-      else if (gr < p.M) {
-        __nv_bfloat16 t[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e)
-          t[e] = gc + e < p.N ? p.gate[static_cast<size_t>(gr) * p.ld_gate + gc + e] : __float2bfloat16_rn(0.f);
-        x = *reinterpret_cast<uint4*>(t);
-      }
-      *stg_unit(stg, rr, u) = x;
-    }
-    __syncwarp();
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const uint4 x = *stg_unit(stg, lane, u);
-      const uint32_t w[4] = {x.x, x.y, x.z, x.w};
-#pragma unroll
-      for (int h = 0; h < 4; ++h) {
-        const float2 f = unpack_bf16(w[h]);
-        const int j = u * 8 + h * 2;
-        v[j] = f.x > 0.f ? v[j] * p.gate_scale : 0.f;
-        v[j + 1] = f.y > 0.f ? v[j + 1] * p.gate_scale : 0.f;
-      }
+    for (int j = 0; j < 32; j += 2) {
+      bool k0, k1;
+      drop_keep_pair(dkey, base + j, p.drop_thresh, k0, k1);
+      v[j] = k0 ? v[j] * p.drop_scale : 0.f;
+      v[j + 1] = k1 ? v[j + 1] * p.drop_scale : 0.f;
     }
   }
-  if (p.residual) {
+  if (p.residual || p.gate) {
+    cp_async_wait_all();
     __syncwarp();
+    if (p.residual) {
 #pragma unroll
-    for (int it = 0; it < 8; ++it) {
-      const int rr = it * 4 + (lane >> 3), u = lane & 7;
-      float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-      const int gr = row0 + rr, gc = col0 + u * 4;
-      if (gr < p.M && gc + 4 <= p.N)
-        x = __ldg(reinterpret_cast<const float4*>(p.residual + static_cast<size_t>(gr) * p.ld_res + gc));
-      else if (gr < p.M) {
-        float t[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) t[e] = gc + e < p.N ? p.residual[static_cast<size_t>(gr) * p.ld_res + gc + e] : 0.f;
-        x = make_float4(t[0], t[1], t[2], t[3]);
+      for (int u = 0; u < 8; ++u) {
+        const float4 x = *reinterpret_cast<const float4*>(stg_unit(in, lane, u));
+        v[4 * u] += x.x; v[4 * u + 1] += x.y; v[4 * u + 2] += x.z; v[4 * u + 3] += x.w;
       }
-      *reinterpret_cast<float4*>(stg_unit(stg, rr, u)) = x;
-    }
-    __syncwarp();
+    } else {
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      const float4 x = *reinterpret_cast<const float4*>(stg_unit(stg, lane, u));
-      v[4 * u] += x.x; v[4 * u + 1] += x.y; v[4 * u + 2] += x.z; v[4 * u + 3] += x.w;
-    }
-  }
-  if (p.out_f32) {
-    __syncwarp();
+      for (int u = 0; u < 4; ++u) {
+        const uint4 x = *stg_unit(in, lane, u);
+        const uint32_t w[4] = {x.x, x.y, x.z, x.w};
 #pragma unroll
-    for (int u = 0; u < 8; ++u)
-      *reinterpret_cast<float4*>(stg_unit(stg, lane, u)) = make_float4(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]);
-    __syncwarp();
-#pragma unroll
-    for (int it = 0; it < 8; ++it) {
-      const int rr = it * 4 + (lane >> 3), u = lane & 7;
-      const int gr = row0 + rr, gc = col0 + u * 4;
-      if (gr >= p.M || gc >= p.N) continue;
-      const float4 x = *reinterpret_cast<const float4*>(stg_unit(stg, rr, u));
-      float* o = p.out_f32 + static_cast<size_t>(gr) * p.ld_f32 + gc;
-      if (gc + 4 <= p.N) {
-        if (p.accumulate) red_add_f32x4(o, x.x, x.y, x.z, x.w);
-        else *reinterpret_cast<float4*>(o) = x;
-      } else {
-        const float t[4] = {x.x, x.y, x.z, x.w};
-        for (int e = 0; e < 4 && gc + e < p.N; ++e) {
-          if (p.accumulate) atomicAdd(o + e, t[e]); else o[e] = t[e];
+        for (int h = 0; h < 4; ++h) {
+          const float2 f = unpack_bf16(w[h]);
+          const int j = u * 8 + h * 2;
+          v[j] = f.x > 0.f ? v[j] * p.gate_scale : 0.f;
+          v[j + 1] = f.y > 0.f ? v[j + 1] * p.gate_scale : 0.f;
         }
       }
     }
+    __syncwarp();
+    if (next_col0 >= 0) epi_prefetch(p, in, lane, row0, next_col0);
+  }
+  if (p.out_f32) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+      *reinterpret_cast<float4*>(stg_unit(out, lane, u)) = make_float4(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]);
+    __syncwarp();
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int rr = it * 4 + (lane >> 3), u = lane & 7;
+      const int gr = row0 + rr, gc = col0 + u * 4;
+      if (gr < p.M && gc + 4 <= p.N) {
+        const float4 x = *reinterpret_cast<const float4*>(stg_unit(out, rr, u));
+        float* o = p.out_f32 + static_cast<size_t>(gr) * p.ld_f32 + gc;
+        if (p.accumulate) red_add_f32x4(o, x.x, x.y, x.z, x.w);
+        else *reinterpret_cast<float4*>(o) = x;
+      }
+    }
+    __syncwarp();
   }
   if (p.out_bf16) {
-    __syncwarp();
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       uint4 x;
@@ -179,25 +168,18 @@ __device__ __forceinline__ void gemm_epilogue_chunk(const GemmParams& p, const u
       x.y = pack_bf16(v[u * 8 + 2], v[u * 8 + 3]);
       x.z = pack_bf16(v[u * 8 + 4], v[u * 8 + 5]);
       x.w = pack_bf16(v[u * 8 + 6], v[u * 8 + 7]);
-      *stg_unit(stg, lane, u) = x;
+      *stg_unit(out, lane, u) = x;
     }
     __syncwarp();
 #pragma unroll
     for (int it = 0; it < 4; ++it) {
       const int rr = it * 8 + (lane >> 2), u = lane & 3;
       const int gr = row0 + rr, gc = col0 + u * 8;
-      if (gr >= p.M || gc >= p.N) continue;
-      const uint4 x = *stg_unit(stg, rr, u);
-      __nv_bfloat16* o = p.out_bf16 + static_cast<size_t>(gr) * p.ld_bf16 + gc;
-      if (gc + 8 <= p.N) {
-        *reinterpret_cast<uint4*>(o) = x;
-      } else {
-        const __nv_bfloat16* t = reinterpret_cast<const __nv_bfloat16*>(&x);
-        for (int e = 0; e < 8 && gc + e < p.N; ++e) o[e] = t[e];
-      }
+      if (gr < p.M && gc + 8 <= p.N)
+        *reinterpret_cast<uint4*>(p.out_bf16 + static_cast<size_t>(gr) * p.ld_bf16 + gc) = *stg_unit(out, rr, u);
     }
+    __syncwarp();
   }
-  __syncwarp();
 }
 
 template <bool A_MN, bool B_MN>
@@ -217,7 +199,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint8_t* sA = smem;
   uint8_t* sB = smem + static_cast<size_t>(stages) * kABytes;
   uint8_t* sStage = sB + static_cast<size_t>(stages) * b_bytes;  // kEpiWarps x 4 KB staging tiles
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sStage + kEpiWarps * kStageBytesPerWarp);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sStage + kEpiWarps * kEpiBytesPerWarp);
   uint64_t* empty_bar = full_bar + stages;
   uint64_t* tfull_bar = empty_bar + stages;
   uint64_t* tempty_bar = tfull_bar + 2;
@@ -319,35 +301,53 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // sharing a quarter take alternate 32-column chunks of the tile.
     const int ew = warp - 4;
     const int q = ew & 3, half = ew >> 2;
-    uint8_t* stg = sStage + static_cast<size_t>(ew) * kStageBytesPerWarp;
+    uint8_t* stg_out = sStage + static_cast<size_t>(ew) * kEpiBytesPerWarp;
+    uint8_t* stg_in = stg_out + kStageBytesPerWarp;
+    float* sbias = reinterpret_cast<float*>(stg_in + kStageBytesPerWarp);   // [4 chunks][32]
     const uint64_t seed = p.drop_seed + ((p.drop_thresh && p.drop_seed_dev) ? *p.drop_seed_dev : 0ull);
+    const uint32_t dkey = drop_key(seed, p.drop_site);
     const int nchunks = block_n / 32;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
       const int mn = t / p.k_splits;
       const int m_blk = mn / tiles_n, n_blk = mn % tiles_n;
+      const int row0 = m_blk * kBlockM + q * 32;
+      const int colbase = n_blk * block_n;
+      // Everything that does not depend on the accumulator is issued before waiting for it:
+      // the bias slice of this warp's chunks and the first residual / gate block.
+      if (p.bias) {
+        __syncwarp();
+        for (int k = 0, c = half; c < nchunks; c += 2, ++k) {
+          const int col = colbase + c * 32 + lane;
+          sbias[k * 32 + lane] = col < p.N ? __ldg(p.bias + col) : 0.f;
+        }
+      }
+      if ((p.residual || p.gate) && half < nchunks) epi_prefetch(p, stg_in, lane, row0, colbase + half * 32);
       mbar_wait(&tfull_bar[acc], acc_phase);
       __syncwarp();
       tc_fence_after();
-      const int row0 = m_blk * kBlockM + q * 32;
       const uint32_t t_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
                               static_cast<uint32_t>(acc * block_n);
       uint32_t r0[32], r1[32];
-      const int colbase = n_blk * block_n;
-      int c = half;
+      int c = half, k = 0;
       if (c < nchunks) tmem_ld32(t_base + static_cast<uint32_t>(c * 32), r0);
       while (c < nchunks) {
         tmem_ld_wait();
         if (c + 2 < nchunks) tmem_ld32(t_base + static_cast<uint32_t>((c + 2) * 32), r1);
-        if (row0 < p.M && colbase + c * 32 < p.N) gemm_epilogue_chunk(p, r0, stg, lane, row0, colbase + c * 32, seed);
-        c += 2;
+        if (!p.debug)
+          gemm_epilogue_chunk(p, r0, stg_out, stg_in, sbias + k * 32, lane, row0, colbase + c * 32,
+                              c + 2 < nchunks ? colbase + (c + 2) * 32 : -1, dkey);
+        c += 2; ++k;
         if (c >= nchunks) break;
         tmem_ld_wait();
         if (c + 2 < nchunks) tmem_ld32(t_base + static_cast<uint32_t>((c + 2) * 32), r0);
-        if (row0 < p.M && colbase + c * 32 < p.N) gemm_epilogue_chunk(p, r1, stg, lane, row0, colbase + c * 32, seed);
-        c += 2;
+        if (!p.debug)
+          gemm_epilogue_chunk(p, r1, stg_out, stg_in, sbias + k * 32, lane, row0, colbase + c * 32,
+                              c + 2 < nchunks ? colbase + (c + 2) * 32 : -1, dkey);
+        c += 2; ++k;
       }
+      if (p.debug) cp_async_wait_all();
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
@@ -364,7 +364,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
 static size_t gemm_smem_bytes(int block_n, int stages) {
   return 1024 + static_cast<size_t>(stages) * (kABytes + static_cast<size_t>(block_n) * kBlockK * 2) +
-         kEpiWarps * kStageBytesPerWarp + (2 * stages + 4) * sizeof(uint64_t) + 16;
+         kEpiWarps * kEpiBytesPerWarp + (2 * stages + 4) * sizeof(uint64_t) + 16;
 }
 
 template <bool A_MN, bool B_MN>
@@ -403,6 +403,9 @@ extern "C" int tt_gemm_bf16(const tt_gemm_args* a, void* stream_) {
   TT_REQUIRE(!a->residual || a->ld_res % 4 == 0, "tt_gemm_bf16: ld_res must be a multiple of 4");
   TT_REQUIRE(!a->gate || a->ld_gate % 8 == 0, "tt_gemm_bf16: ld_gate must be a multiple of 8");
   TT_REQUIRE(a->drop_p >= 0.f && a->drop_p < 1.f, "tt_gemm_bf16: drop_p out of range");
+  TT_REQUIRE(!a->out_f32 || a->N % 4 == 0, "tt_gemm_bf16: fp32 output needs N %% 4 == 0 (N=%d)", a->N);
+  TT_REQUIRE(!(a->out_bf16 || a->gate) || a->N % 8 == 0, "tt_gemm_bf16: bf16 output / gate need N %% 8 == 0 (N=%d)", a->N);
+  TT_REQUIRE(!(a->gate && a->residual), "tt_gemm_bf16: gate and residual cannot be combined");
   TT_REQUIRE(!a->accumulate || (a->out_f32 && !a->out_bf16),
              "tt_gemm_bf16: accumulate needs an fp32-only output");
 
@@ -416,7 +419,7 @@ extern "C" int tt_gemm_bf16(const tt_gemm_args* a, void* stream_) {
   TT_REQUIRE(bn == 64 || bn == 128 || bn == 256, "tt_gemm_bf16: block_n must be 64/128/256");
   p.block_n = bn;
   const size_t stage_bytes = kABytes + static_cast<size_t>(bn) * kBlockK * 2;
-  int stages = static_cast<int>((232448 - 1024 - kEpiWarps * kStageBytesPerWarp - 256) / stage_bytes);
+  int stages = static_cast<int>((232448 - 1024 - kEpiWarps * kEpiBytesPerWarp - 256) / stage_bytes);
   if (stages > 8) stages = 8;
   p.stages = stages;
 
@@ -463,6 +466,11 @@ extern "C" int tt_gemm_bf16(const tt_gemm_args* a, void* stream_) {
   p.out_bf16 = static_cast<__nv_bfloat16*>(a->out_bf16);
   p.ld_bf16 = a->ld_bf16;
   p.accumulate = a->accumulate;
+  {
+    static int dbg = -1;
+    if (dbg < 0) { const char* e = getenv("TT_GEMM_DEBUG"); dbg = e ? atoi(e) : 0; }
+    p.debug = dbg;
+  }
 
   CUtensorMap tmA, tmB;
   int rc;

@@ -67,6 +67,23 @@ __device__ __forceinline__ void ln_stats(const float (&v)[4 * NV], float eps, fl
 __device__ __forceinline__ uint64_t read_seed(uint64_t seed, const uint64_t* seed_dev) {
   return seed_dev ? seed + *seed_dev : seed;
 }
+// Dropout over a lane's row slice: elements come in float4 groups with 4-aligned column indices,
+// so (e, e+1) pairs share one hash. keep[] (optional) receives the decisions.
+template <int NV>
+__device__ __forceinline__ void row_dropout(float (&v)[4 * NV], uint32_t key, uint64_t row, int width, int lane,
+                                            uint32_t thresh, float scale, bool* keep) {
+#pragma unroll
+  for (int e = 0; e < 4 * NV; e += 2) {
+    const uint64_t idx = row * static_cast<uint64_t>(width) + static_cast<uint64_t>(col_of<NV>(lane, e));
+    bool k0, k1;
+    if (idx < 0xFFFFFFFEull) drop_keep_pair(key, static_cast<uint32_t>(idx), thresh, k0, k1);
+    else { k0 = drop_keep_k(key, idx, thresh); k1 = drop_keep_k(key, idx + 1, thresh); }
+    v[e] = k0 ? v[e] * scale : 0.f;
+    v[e + 1] = k1 ? v[e + 1] * scale : 0.f;
+    if (keep) { keep[e] = k0; keep[e + 1] = k1; }
+  }
+}
+
 static uint32_t drop_threshold(float p) {
   if (p <= 0.f) return 0;
   double t = static_cast<double>(p) * 4294967296.0;
@@ -142,13 +159,8 @@ __global__ void __launch_bounds__(kRowThreads) embed_ln_fwd_kernel(const EmbedPa
     float mean, rstd;
     ln_stats<NV>(e, 1e-5f, mean, rstd);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      float y = (e[i] - mean) * rstd * w[i] + b[i];
-      if (p.drop_thresh)
-        y = drop_keep(seed, p.site, static_cast<uint64_t>(row) * 256 + col_of<NV>(lane, i), p.drop_thresh)
-                ? y * p.drop_scale : 0.f;
-      e[i] = y;
-    }
+    for (int i = 0; i < 8; ++i) e[i] = (e[i] - mean) * rstd * w[i] + b[i];
+    if (p.drop_thresh) row_dropout<NV>(e, drop_key(seed, p.site), row, 256, lane, p.drop_thresh, p.drop_scale, nullptr);
     store_row<NV>(p.x0 + static_cast<size_t>(row) * 256, lane, e);
     ln_stats<NV>(e, 1e-5f, mean, rstd);
 #pragma unroll
@@ -201,12 +213,7 @@ __global__ void __launch_bounds__(kRowThreads) chain_fwd_kernel(const ChainParam
 #pragma unroll
       for (int i = 0; i < E; ++i) v[i] = fmaxf(v[i], 0.f);
     }
-    if (p.drop_thresh) {
-#pragma unroll
-      for (int i = 0; i < E; ++i)
-        v[i] = drop_keep(seed, p.site, static_cast<uint64_t>(row) * W + col_of<NV>(lane, i), p.drop_thresh)
-                   ? v[i] * p.drop_scale : 0.f;
-    }
+    if (p.drop_thresh) row_dropout<NV>(v, drop_key(seed, p.site), row, W, lane, p.drop_thresh, p.drop_scale, nullptr);
     if (p.l2norm) {
       float s = 0.f;
 #pragma unroll
@@ -251,14 +258,10 @@ __global__ void __launch_bounds__(kRowThreads) chain_bwd_kernel(const ChainParam
     bool keep[E];
 #pragma unroll
     for (int i = 0; i < E; ++i) {
-      float t = p.relu ? fmaxf(y[i], 0.f) : y[i];
+      z[i] = p.relu ? fmaxf(y[i], 0.f) : y[i];
       keep[i] = true;
-      if (p.drop_thresh) {
-        keep[i] = drop_keep(seed, p.site, static_cast<uint64_t>(row) * W + col_of<NV>(lane, i), p.drop_thresh);
-        t = keep[i] ? t * p.drop_scale : 0.f;
-      }
-      z[i] = t;
     }
+    if (p.drop_thresh) row_dropout<NV>(z, drop_key(seed, p.site), row, W, lane, p.drop_thresh, p.drop_scale, keep);
     if (p.l2norm) {
       float s = 0.f;
 #pragma unroll
@@ -301,12 +304,8 @@ __global__ void __launch_bounds__(kRowThreads) chain_bwd_kernel(const ChainParam
     }
     if (p.dx_f32) store_row<NV>(p.dx_f32 + static_cast<size_t>(row) * W, lane, g);
     if (p.dx_bf16) {
-      if (p.drop2_thresh) {
-#pragma unroll
-        for (int i = 0; i < E; ++i)
-          g[i] = drop_keep(seed, p.site2, static_cast<uint64_t>(row) * W + col_of<NV>(lane, i), p.drop2_thresh)
-                     ? g[i] * p.drop2_scale : 0.f;
-      }
+      if (p.drop2_thresh)
+        row_dropout<NV>(g, drop_key(seed, p.site2), row, W, lane, p.drop2_thresh, p.drop2_scale, nullptr);
       store_row_bf16<NV>(p.dx_bf16 + static_cast<size_t>(row) * W, lane, g);
       if (p.dx_colsum) {
 #pragma unroll
@@ -560,10 +559,9 @@ __global__ void __launch_bounds__(kRowThreads) embed_ln_bwd_kernel(const EmbedBw
     float mean, rstd;
     ln_stats<NV>(e, 1e-5f, mean, rstd);
     float s1 = 0.f, s2 = 0.f;
+    if (p.drop_thresh) row_dropout<NV>(g, drop_key(seed, p.site), row, W, lane, p.drop_thresh, p.drop_scale, nullptr);
 #pragma unroll
     for (int i = 0; i < E_; ++i) {
-      if (p.drop_thresh)
-        g[i] = drop_keep(seed, p.site, row * W + col_of<NV>(lane, i), p.drop_thresh) ? g[i] * p.drop_scale : 0.f;
       xhat[i] = (e[i] - mean) * rstd;
       dg[i] += g[i] * xhat[i];
       db[i] += g[i];
