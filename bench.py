@@ -143,48 +143,22 @@ def run_reference(args, rank, world):
 # ------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------
-def time_gemm_roofline(eng, B, L, iters=5):
-    """Event-time every distinct GEMM shape of one training step (the step's own launch arguments)
-    and return (algorithmic flops per step in GEMMs, seconds per step spent in them)."""
-    from mrm_b200 import ops
-    T, D, FF = B * L, 256, 1024
-    dev = eng.device
-    bf = dict(device=dev, dtype=torch.bfloat16)
-    x = torch.randn(T, FF, **bf)
-    w = torch.randn(FF, FF, **bf) * 0.05
-    o32 = torch.empty(T, D, device=dev)
-    o16 = torch.empty(T, FF, **bf)
-    g32 = torch.zeros(FF, FF, device=dev)
-    NL = eng.cfg.num_layers
-    shapes = [  # (count per step, M, N, K, kind)
-        (NL, T, 3 * D, D, "fwd16"), (NL, T, D, D, "fwd32"), (NL, T, FF, D, "fwd16"), (NL, T, D, FF, "fwd32"),
-        (NL, T, FF, D, "dgrad16"), (NL, T, D, FF, "dgrad32"), (NL, T, D, D, "dgrad16"), (NL, T, D, 3 * D, "dgrad32"),
-        (NL, D, FF, T, "wgrad"), (NL, FF, D, T, "wgrad"), (NL, D, D, T, "wgrad"), (NL, 3 * D, D, T, "wgrad"),
-    ]
+def time_gemm_roofline(eng, static_batch, iters=5):
+    """Event-time every tcgen05 GEMM launch of eager training steps (the step's own operands, epilogues
+    and launch arguments, issued on the current stream) -> (algorithmic flops, seconds) per step."""
     flops, secs = 0.0, 0.0
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    for cnt, M, N, K, kind in shapes:
-        def launch():
-            if kind == "fwd16":
-                ops.gemm(x[:M, :K], w[:N, :K], out_bf16=o16[:M, :N])
-            elif kind == "fwd32":
-                ops.gemm(x[:M, :K], w[:N, :K], out_f32=o32[:M, :N])
-            elif kind == "dgrad16":
-                ops.gemm(x[:M, :K], w[:K, :N], b_mn=True, out_bf16=o16[:M, :N])
-            elif kind == "dgrad32":
-                ops.gemm(x[:M, :K], w[:K, :N], b_mn=True, out_f32=o32[:M, :N])
-            else:
-                ops.gemm(x[:K, :M], x[:K, :N], a_mn=True, b_mn=True, out_f32=g32[:M, :N], accumulate=True)
-        for _ in range(2):
-            launch()
-        e0.record()
-        for _ in range(iters):
-            launch()
-        e1.record()
+    for it in range(iters + 1):
+        eng.gemm_log = []
+        eng.forward(static_batch, training=True)
+        eng.backward()
         torch.cuda.synchronize()
-        secs += cnt * e0.elapsed_time(e1) * 1e-3 / iters
-        flops += cnt * 2.0 * M * N * K
-    return flops, secs
+        if it > 0:       # first pass warms the instruction / L2 state of the eager path
+            flops += sum(f for _, _, f in eng.gemm_log)
+            secs += sum(e0.elapsed_time(e1) for e0, e1, _ in eng.gemm_log) * 1e-3
+        n_launch = len(eng.gemm_log)
+        eng.gemm_log = None
+        eng.grad.zero_()
+    return flops / iters, secs / iters, n_launch
 
 
 def run_ours(args, rank, world, local_rank):
@@ -250,7 +224,7 @@ def run_ours(args, rank, world, local_rank):
     sampler.join(timeout=2)
 
     # ---- roofline of the dominant kernel (tcgen05 GEMM) -----------------------------------
-    gemm_flops, gemm_secs = time_gemm_roofline(eng, B, L)
+    gemm_flops, gemm_secs, gemm_launches = time_gemm_roofline(eng, runner.static)
     peak_tf = peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops"))
     achieved_tf = gemm_flops / gemm_secs / 1e12
     step_flops = 3.0 * flops_per_sample_fwd(L, B) * B
@@ -286,7 +260,10 @@ def run_ours(args, rank, world, local_rank):
             "roofline": {"bound": "tensor", "kernel": "tt::gemm_bf16_kernel (tcgen05)", "achieved": achieved_tf,
                          "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf, "traffic": None,
                          "peak_source": f"{peak_src} bf16_tflops_sustained",
-                         "gemm_share_of_step": gemm_secs * 1e3 / ms_step},
+                         "launches_per_step": gemm_launches, "flops_per_step": gemm_flops,
+                         "us_per_step": gemm_secs * 1e6, "share_of_step": gemm_secs * 1e3 / ms_step,
+                         "how": "CUDA events around each tt_gemm_bf16 launch of eager steps (same operands and "
+                                "fused epilogues as the timed step), summed; includes the small head/item/loss GEMMs"},
             "clocks": sampler.summary(),
             "retrieval": retr,
         }

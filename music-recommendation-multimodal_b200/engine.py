@@ -213,8 +213,22 @@ class TwoTowerEngine:
         return ws
 
     # ------------------------------------------------------------------ helpers
-    def _gemm(self, *a, **kw):
-        ops.gemm(*a, **kw)
+    def _gemm(self, A, B, **kw):
+        """tt_gemm_bf16; with ``self.gemm_log`` set (a list), every launch is bracketed by CUDA events
+        and logged as (event0, event1, algorithmic flops) — bench.py's roofline measurement."""
+        log = getattr(self, "gemm_log", None)
+        if log is None:
+            ops.gemm(A, B, **kw)
+            return
+        a_mn, b_mn = kw.get("a_mn", False), kw.get("b_mn", False)
+        M = A.shape[1] if a_mn else A.shape[0]
+        K = A.shape[0] if a_mn else A.shape[1]
+        N = B.shape[1] if b_mn else B.shape[0]
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        ops.gemm(A, B, **kw)
+        e1.record()
+        log.append((e0, e1, 2.0 * M * N * K))
 
     def _lp(self, l: int, name: str) -> str:
         return f"user_tower.transformer_encoder.layers.{l}.{name}"
@@ -280,19 +294,55 @@ class TwoTowerEngine:
                       out_bf16=ws["in_bf"])
         return ws["in"]
 
-    def loss_forward(self, ws, user_idx: Optional[torch.Tensor]) -> torch.Tensor:
+    # -- InfoNCE, written for data parallelism with all-gathered negatives --------------------
+    # Rank r holds B local users/items and the G*B gathered ones; its positives sit at column
+    # r*B + i. S = U_loc I_all^T / tau and S2 = I_loc U_all^T / tau are ROW problems; the column
+    # log-sum-exps needed by the gradient are the other matrix's row log-sum-exps on the owning
+    # ranks (two small all-gathers, no reduce-scatter). With one rank everything is local.
+    def gathered_workspace(self, ws, G: int) -> Dict[str, torch.Tensor]:
+        B, D = ws["un"].shape
+        key = f"_gath{G}"
+        if key not in ws:
+            dev = self.device
+            ws[key] = {
+                "U_all": torch.empty(G * B, D, device=dev, dtype=torch.bfloat16),
+                "I_all": torch.empty(G * B, D, device=dev, dtype=torch.bfloat16),
+                "uid_all": torch.zeros(G * B, device=dev, dtype=torch.long),
+                "S": torch.empty(B, G * B, device=dev), "S2": torch.empty(B, G * B, device=dev),
+                "dS": torch.empty(B, G * B, device=dev, dtype=torch.bfloat16),
+                "dS2": torch.empty(B, G * B, device=dev, dtype=torch.bfloat16),
+                "lse_r_all": torch.empty(G * B, device=dev), "lse_c_all": torch.empty(G * B, device=dev),
+            }
+        return ws[key]
+
+    def loss_forward(self, ws, user_idx: Optional[torch.Tensor], gathered: Optional[Dict[str, torch.Tensor]] = None,
+                     rank: int = 0) -> torch.Tensor:
+        """Logits + masked row log-sum-exps (+ the local loss when not gathered). With `gathered`
+        (U_all, I_all, uid_all filled by the caller's all-gather) the caller must all-gather
+        ws['lse_r'] / ws['lse_c'] into gathered['lse_r_all' / 'lse_c_all'] and then call loss_value()."""
         B = ws["un"].shape[0]
         inv_t = 1.0 / self.cfg.temperature
-        self._gemm(ws["un_bf"], ws["in_bf"], alpha=inv_t, out_f32=ws["S"])
-        self._gemm(ws["in_bf"], ws["un_bf"], alpha=inv_t, out_f32=ws["S2"])
-        ops.infonce_rows(ws["S"], user_idx, user_idx, 0, ws["lse_r"], ws["pos_r"])
-        ops.infonce_rows(ws["S2"], user_idx, user_idx, 0, ws["lse_c"], ws["pos_c"])
-        ops.infonce_loss(ws["lse_r"], ws["pos_r"], ws["lse_c"], ws["pos_c"], 0.5 / B, ws["loss"])
+        self._gathered = None if gathered is None else (gathered, rank)
+        if gathered is None:
+            S, S2, U_all, I_all, uid_all, pos0 = ws["S"], ws["S2"], ws["un_bf"], ws["in_bf"], user_idx, 0
+        else:
+            S, S2, U_all, I_all, pos0 = gathered["S"], gathered["S2"], gathered["U_all"], gathered["I_all"], rank * B
+            uid_all = gathered["uid_all"] if user_idx is not None else None
+        self._gemm(ws["un_bf"], I_all, alpha=inv_t, out_f32=S)
+        self._gemm(ws["in_bf"], U_all, alpha=inv_t, out_f32=S2)
+        ops.infonce_rows(S, user_idx, uid_all, pos0, ws["lse_r"], ws["pos_r"])
+        ops.infonce_rows(S2, user_idx, uid_all, pos0, ws["lse_c"], ws["pos_c"])
+        if gathered is None:
+            self.loss_value(ws, B)
         return ws["loss"]
 
-    def forward(self, batch: Dict[str, torch.Tensor], training: bool = True):
-        """TwoTowerModel.forward (src/models/two_tower.py:68-142) ->
-        (loss, logits, user_emb, item_emb); tensors are workspace views valid until the next call."""
+    def loss_value(self, ws, global_batch: int) -> torch.Tensor:
+        """loss contribution of the local rows: 0.5/global_batch * sum_i (lse - positive) over both directions
+        (sum over ranks = the global symmetric InfoNCE)."""
+        ops.infonce_loss(ws["lse_r"], ws["pos_r"], ws["lse_c"], ws["pos_c"], 0.5 / global_batch, ws["loss"])
+        return ws["loss"]
+
+    def forward_towers(self, batch: Dict[str, torch.Tensor], training: bool = True):
         ids = batch["history_ids"]
         B, L = ids.shape
         ws = self.workspace(B, L)
@@ -301,8 +351,15 @@ class TwoTowerEngine:
         self.user_forward(ws, ids, batch.get("history_mask"), batch["user_gender"], batch["user_country"], training)
         self.item_forward(ws, batch["target_audio"], batch["target_image"], batch["target_input_ids"],
                           batch["target_tabular"], training)
-        self.loss_forward(ws, batch.get("user_idx"))
         self._last = (ws, batch, training)
+        self._gathered = None
+        return ws
+
+    def forward(self, batch: Dict[str, torch.Tensor], training: bool = True):
+        """TwoTowerModel.forward (src/models/two_tower.py:68-142) ->
+        (loss, logits, user_emb, item_emb); tensors are workspace views valid until the next call."""
+        ws = self.forward_towers(batch, training)
+        self.loss_forward(ws, batch.get("user_idx"))
         return ws["loss"], ws["S"], ws["un"], ws["in"]
 
     # ------------------------------------------------------------------ backward
@@ -320,11 +377,20 @@ class TwoTowerEngine:
         gemm = self._gemm
 
         # ---- InfoNCE -> d(normalised embeddings)
-        coef = 0.5 / B * loss_scale
-        ops.infonce_grad(ws["S"], ws["lse_r"], ws["lse_c"], 0, coef, ws["dS"])
-        ops.infonce_grad(ws["S2"], ws["lse_c"], ws["lse_r"], 0, coef, ws["dS2"])
-        gemm(ws["dS"], ws["in_bf"], b_mn=True, alpha=inv_t, out_f32=ws["dun"])
-        gemm(ws["dS2"], ws["un_bf"], b_mn=True, alpha=inv_t, out_f32=ws["din"])
+        gath = getattr(self, "_gathered", None)
+        if gath is None:
+            coef = 0.5 / B * loss_scale
+            ops.infonce_grad(ws["S"], ws["lse_r"], ws["lse_c"], 0, coef, ws["dS"])
+            ops.infonce_grad(ws["S2"], ws["lse_c"], ws["lse_r"], 0, coef, ws["dS2"])
+            gemm(ws["dS"], ws["in_bf"], b_mn=True, alpha=inv_t, out_f32=ws["dun"])
+            gemm(ws["dS2"], ws["un_bf"], b_mn=True, alpha=inv_t, out_f32=ws["din"])
+        else:
+            g_, rank = gath
+            coef = 0.5 / B * loss_scale     # per-rank normalisation; the gradient all-reduce AVERAGES
+            ops.infonce_grad(g_["S"], ws["lse_r"], g_["lse_c_all"], rank * B, coef, g_["dS"])
+            ops.infonce_grad(g_["S2"], ws["lse_c"], g_["lse_r_all"], rank * B, coef, g_["dS2"])
+            gemm(g_["dS"], g_["I_all"], b_mn=True, alpha=inv_t, out_f32=ws["dun"])
+            gemm(g_["dS2"], g_["U_all"], b_mn=True, alpha=inv_t, out_f32=ws["din"])
 
         # ---- item tower
         ops.chain_bwd(ws["y2"], ln=(p[it + "5.weight"], p[it + "5.bias"]), l2norm=True, dout=ws["din"],

@@ -42,15 +42,24 @@ class FusedAdamW:
 
 
 class TrainStepRunner:
-    """One training step (src/train.py:54-65) over static device buffers, replayed as a CUDA graph.
+    """One training step (src/train.py:54-65) over static device buffers, replayed as CUDA graphs.
 
-    Data parallel (world_size > 1): gradients are averaged with one NCCL all-reduce over the flat
-    gradient buffer between the backward graph and the optimizer graph — the reference's DDP
-    semantics (per-rank in-batch negatives, per-rank BatchNorm statistics, src/train.py:300)."""
+    Data parallel (world_size > 1), one process per GPU:
+      negatives="gathered" (default; BASELINE.json config 4): the normalised user / item embeddings
+        and user ids of all ranks are all-gathered (3 small NCCL calls), every rank forms its
+        (B x G*B) logit blocks, the row log-sum-exps are all-gathered (2 tiny calls) so each rank can
+        form the exact gradient of the GLOBAL symmetric InfoNCE for its own rows;
+      negatives="local": the reference's DDP semantics (per-rank in-batch negatives, src/train.py:300).
+    In both cases BatchNorm statistics are per rank (the reference uses no SyncBatchNorm) and the flat
+    gradient buffer is averaged with ONE all-reduce between the backward and optimizer graphs."""
 
     def __init__(self, engine: TwoTowerEngine, B: int, L: int, world_size: int = 1, lr: float = 1e-4,
-                 use_graph: bool = True, with_user_idx: bool = True):
+                 use_graph: bool = True, with_user_idx: bool = True, negatives: str = "gathered",
+                 rank: Optional[int] = None, group=None):
         self.eng, self.B, self.L, self.world, self.lr, self.use_graph = engine, B, L, world_size, lr, use_graph
+        self.group = group
+        self.rank = (dist.get_rank(group) if world_size > 1 else 0) if rank is None else rank
+        self.gathered = world_size > 1 and negatives == "gathered"
         dev, m = engine.device, engine.cfg.modality_dim
         i64 = dict(device=dev, dtype=torch.long)
         self.static: Dict[str, torch.Tensor] = {
@@ -70,55 +79,114 @@ class TrainStepRunner:
         for k, dst in self.static.items():
             dst.copy_(batch[k], non_blocking=True)
 
-    def _fwd_bwd(self):
-        self.eng.forward(self.static, training=True)
+    # ---- step phases (each is graph-capturable; NCCL calls stay between the graphs) ----------
+    def _phase_towers(self):
+        self._ws = self.eng.forward_towers(self.static, training=True)
+
+    def _phase_loss_rows(self):
+        eng, ws = self.eng, self._ws
+        g = eng.gathered_workspace(ws, self.world) if self.gathered else None
+        eng.loss_forward(ws, self.static.get("user_idx"), gathered=g, rank=self.rank)
+
+    def _phase_backward(self):
+        if self.gathered:
+            self.eng.loss_value(self._ws, self.world * self.B)
         self.eng.backward()
 
-    def _opt(self):
+    def _phase_opt(self):
         self.eng.adamw_step(lr=self.lr)
 
-    def _eager(self):
-        self._fwd_bwd()
+    def _comm_embeddings(self):
+        ws = self._ws
+        g = self.eng.gathered_workspace(ws, self.world)
+        dist.all_gather_into_tensor(g["U_all"], ws["un_bf"], group=self.group)
+        dist.all_gather_into_tensor(g["I_all"], ws["in_bf"], group=self.group)
+        if "user_idx" in self.static:
+            dist.all_gather_into_tensor(g["uid_all"], self.static["user_idx"], group=self.group)
+
+    def _comm_lse(self):
+        ws = self._ws
+        g = self.eng.gathered_workspace(ws, self.world)
+        dist.all_gather_into_tensor(g["lse_r_all"], ws["lse_r"], group=self.group)
+        dist.all_gather_into_tensor(g["lse_c_all"], ws["lse_c"], group=self.group)
+
+    def _comm_grads(self):
+        dist.all_reduce(self.eng.grad, op=dist.ReduceOp.AVG, group=self.group)
+
+    def _sequence(self):
+        """[(callable, is_communication)] of one step."""
+        seq = [(self._phase_towers, False)]
+        if self.gathered:
+            seq += [(self._comm_embeddings, True), (self._phase_loss_rows, False), (self._comm_lse, True)]
+        else:
+            seq += [(self._phase_loss_rows, False)]
+        seq += [(self._phase_backward, False)]
         if self.world > 1:
-            dist.all_reduce(self.eng.grad, op=dist.ReduceOp.AVG)
-        self._opt()
+            seq += [(self._comm_grads, True)]
+        seq += [(self._phase_opt, False)]
+        return seq
+
+    def _eager(self):
+        for fn, _ in self._sequence():
+            fn()
+
+    def _loss_tensor(self) -> torch.Tensor:
+        return self.eng.workspace(self.B, self.L)["loss"]
 
     def step_resident(self) -> torch.Tensor:
-        """One step on whatever is in the static buffers; returns the device loss scalar."""
+        """One step on whatever is in the static buffers; returns the device loss scalar (with gathered
+        negatives: this rank's share of the global loss; step_from_host sums it over ranks)."""
         if not self._warm:
             c0 = _lib.launch_count
             self._eager()                      # allocates workspaces / moments, sets func attributes
             self.kernels_per_step = _lib.launch_count - c0
             self._warm = True
             torch.cuda.synchronize()
-            return self.eng.workspace(self.B, self.L)["loss"]
+            return self._loss_tensor()
         if not self.use_graph:
             self._eager()
-            return self.eng.workspace(self.B, self.L)["loss"]
+            return self._loss_tensor()
         if self._graphs is None:
-            g1, g2 = torch.cuda.CUDAGraph(), None
-            if self.world > 1:
-                g2 = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g1):
-                    self._fwd_bwd()
-                with torch.cuda.graph(g2):
-                    self._opt()
+            # consecutive compute phases are fused into one graph; communication stays eager
+            plan, cur = [], []
+            for fn, is_comm in self._sequence():
+                if is_comm:
+                    if cur:
+                        plan.append(("graph", cur))
+                        cur = []
+                    plan.append(("comm", fn))
+                else:
+                    cur.append(fn)
+            if cur:
+                plan.append(("graph", cur))
+            graphs = []
+            for kind, item in plan:
+                if kind == "comm":
+                    item()                     # keeps the buffers consistent while capturing the rest
+                    graphs.append(("comm", item))
+                else:
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g):
+                        for fn in item:
+                            fn()
+                    g.replay()
+                    graphs.append(("graph", g))
+            self._graphs = graphs
+            return self._loss_tensor()
+        for kind, item in self._graphs:
+            if kind == "comm":
+                item()
             else:
-                with torch.cuda.graph(g1):
-                    self._fwd_bwd()
-                    self._opt()
-            self._graphs = (g1, g2)
-        g1, g2 = self._graphs
-        g1.replay()
-        if g2 is not None:
-            dist.all_reduce(self.eng.grad, op=dist.ReduceOp.AVG)
-            g2.replay()
-        return self.eng.workspace(self.B, self.L)["loss"]
+                item.replay()
+        return self._loss_tensor()
 
     def step_from_host(self, host_batch: Dict[str, torch.Tensor]) -> float:
         """Host batch -> device -> step -> loss on the host (one sync, like the reference's loss.item())."""
         self.load_batch(host_batch)
         loss = self.step_resident()
+        if self.gathered:
+            loss = loss.clone()
+            dist.all_reduce(loss, op=dist.ReduceOp.SUM, group=self.group)
         self.loss_host.copy_(loss, non_blocking=True)
         torch.cuda.current_stream().synchronize()
         return float(self.loss_host)

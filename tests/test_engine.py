@@ -151,3 +151,66 @@ def test_dropout_training_runs_and_is_seeded():
     assert l3 != l1
     assert abs(l1 - gold["f64"]["loss"].item()) < 0.5
     assert torch.isfinite(eng.grad).all()
+
+
+def test_gathered_negatives_two_virtual_ranks_match_global_oracle():
+    """Data parallel with all-gathered negatives (BASELINE config 4), emulated on one GPU with two
+    engines holding the same weights: each 'rank' runs its towers on its own half batch (per-rank
+    BatchNorm statistics, reference DDP semantics), the embeddings / ids / row log-sum-exps are
+    exchanged by hand exactly where the NCCL all-gathers sit, and the averaged gradients must equal
+    the gradient of the GLOBAL symmetric InfoNCE computed by the oracle on the same embeddings."""
+    from mrm_b200 import synthetic
+    from mrm_b200.engine import TwoTowerEngine
+    from oracle import two_tower_oracle as oracle
+    cfg = synthetic.TwoTowerConfig(vocab_size=2001, max_seq_len=50, dropout=0.0)
+    sd = synthetic.make_state_dict(cfg, seed=3)
+    G, B = 2, 16
+    batches = [synthetic.make_batch(cfg, B, seed=40 + r, num_users=12) for r in range(G)]   # collisions across ranks
+    engs = []
+    for r in range(G):
+        e = TwoTowerEngine(cfg)
+        e.load_state_dict(sd)
+        engs.append(e)
+    wss = [e.forward_towers({k: v.cuda() for k, v in b.items()}, training=True) for e, b in zip(engs, batches)]
+    U_all = torch.cat([ws["un_bf"] for ws in wss])
+    I_all = torch.cat([ws["in_bf"] for ws in wss])
+    uid_all = torch.cat([b["user_idx"] for b in batches]).cuda()
+    gs = []
+    for r, (e, ws) in enumerate(zip(engs, wss)):
+        g = e.gathered_workspace(ws, G)
+        g["U_all"].copy_(U_all); g["I_all"].copy_(I_all); g["uid_all"].copy_(uid_all)
+        e.loss_forward(ws, batches[r]["user_idx"].cuda(), gathered=g, rank=r)
+        gs.append(g)
+    lse_r_all = torch.cat([ws["lse_r"] for ws in wss])
+    lse_c_all = torch.cat([ws["lse_c"] for ws in wss])
+    loss = 0.0
+    for r, (e, ws, g) in enumerate(zip(engs, wss, gs)):
+        g["lse_r_all"].copy_(lse_r_all); g["lse_c_all"].copy_(lse_c_all)
+        loss += e.loss_value(ws, G * B).item()
+        e.backward()
+    torch.cuda.synchronize()
+    avg_grad = {k: sum(e.g[k] for e in engs).cpu().double() / G for k in engs[0].g}
+
+    # oracle: per-rank towers (per-rank BN statistics), global loss on the concatenated embeddings
+    p = {k: (v.double().clone().requires_grad_(True) if v.is_floating_point() and not k.endswith(oracle.TRAINABLE_SKIP)
+             else v.clone()) for k, v in sd.items()}
+    us, its = [], []
+    for b in batches:
+        b64 = {k: (v.double() if v.is_floating_point() else v) for k, v in b.items()}
+        us.append(oracle.l2_normalize(oracle.user_tower(p, b64["history_ids"], b64["user_gender"], b64["user_country"],
+                                                        b64["history_mask"], cfg.num_heads)))
+        it, _ = oracle.item_fusion(p, b64["target_audio"], b64["target_image"], b64["target_input_ids"],
+                                   b64["target_tabular"], training=True)
+        its.append(oracle.l2_normalize(it))
+    ref_loss, _ = oracle.infonce(torch.cat(us), torch.cat(its), cfg.temperature, uid_all.cpu())
+    ref_loss.backward()
+    assert abs(loss - ref_loss.item()) <= 2e-2, (loss, ref_loss.item())
+    bad = []
+    for k, got in avg_grad.items():
+        ref = p[k].grad
+        if k == "user_tower.item_embedding.weight":
+            ref = ref.clone(); ref[0] = 0
+        err = (got - ref).norm().item()
+        if err > 8e-2 * ref.norm().item() + 1e-5 * ref.numel() ** 0.5:
+            bad.append((k, err, ref.norm().item()))
+    assert not bad, bad[:5]
