@@ -257,6 +257,9 @@ int tt_infonce_loss(const float* lse_a, const float* pos_a, const float* lse_b, 
 typedef struct tt_topk_plan {
   int32_t U, N, kprime, cap;
   int32_t n_ut, n_ranges, tiles_per_range;
+  int32_t sample_stride, sample_rank, sample_keep; /* sample pass (0 = none): every sample_stride-th item
+                                                      tile is scored first; each user's sample_rank-th best
+                                                      sample score becomes the main pass's start threshold */
   int64_t cand_bytes, cnt_bytes, thr_bytes;
 } tt_topk_plan;
 int tt_topk_plan_make(int U, int N, int kprime, tt_topk_plan* plan);

@@ -124,6 +124,7 @@ class TopkPlan(ctypes.Structure):
 
     _fields_ = [("U", c_int32), ("N", c_int32), ("kprime", c_int32), ("cap", c_int32),
                 ("n_ut", c_int32), ("n_ranges", c_int32), ("tiles_per_range", c_int32),
+                ("sample_stride", c_int32), ("sample_rank", c_int32), ("sample_keep", c_int32),
                 ("cand_bytes", ctypes.c_int64), ("cnt_bytes", ctypes.c_int64), ("thr_bytes", ctypes.c_int64)]
 
 

@@ -52,6 +52,8 @@ __device__ __forceinline__ float key_score(uint64_t k) { return ord2f(static_cas
 struct TopkParams {
   int U, N, item_base;
   int n_ut, n_ranges, tiles_per_range, total_tiles;
+  int tile_stride;           // logical tile t of a range is physical tile t * tile_stride (sample pass: strided tiles)
+  int reset_thr;             // 1: ignore published thresholds at unit start (sample pass)
   int kprime;
   int u_pad;
   unsigned long long* cand;  // [n_ranges][u_pad][kCap]
@@ -139,7 +141,7 @@ __device__ __forceinline__ void scan_chunk(const uint32_t (&r)[32], int idx0, co
       cnt = ncnt;
       thr_key = T;
       thr_s = key_score(T);
-      atomicMax(p.thr + row, T);
+      if (!p.reset_thr) atomicMax(p.thr + row, T);
     }
   }
 }
@@ -204,7 +206,7 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant
           for (int kb = 0; kb < kKB; ++kb) {
             mbar_wait(&b_empty[stage], phase ^ 1u);
             mbar_arrive_expect_tx(&b_full[stage], kTile16K);
-            tma_load_2d(sB + stage * kTile16K, &tmI, &b_full[stage], kb * 64, tile * kIT);
+            tma_load_2d(sB + stage * kTile16K, &tmI, &b_full[stage], kb * 64, tile * p.tile_stride * kIT);
             if (++stage == kBStages) { stage = 0; phase ^= 1u; }
           }
         }
@@ -259,7 +261,7 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant
       const int row = ut * kUT + mt * 128 + q * 32 + lane;
       const bool active = row < p.U;
       unsigned long long* buf = p.cand + (static_cast<size_t>(range) * p.u_pad + row) * kCap;
-      unsigned long long thr_key = active ? p.thr[row] : ~0ull;
+      unsigned long long thr_key = active ? (p.reset_thr ? 0ull : p.thr[row]) : ~0ull;
       float thr_s = thr_key == 0ull ? -INFINITY : (active ? key_score(thr_key) : INFINITY);
       int cnt = 0;
       for (int tile = tile0; tile < tile1; ++tile) {
@@ -274,10 +276,10 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant
         for (int c = 0; c < kIT / 32; c += 2) {
           tmem_ld_wait();
           tmem_ld32(t_base + (c + 1) * 32, r1);
-          scan_chunk(r0, tile * kIT + c * 32, p, lane, row, buf, cnt, thr_key, thr_s);
+          scan_chunk(r0, tile * p.tile_stride * kIT + c * 32, p, lane, row, buf, cnt, thr_key, thr_s);
           tmem_ld_wait();
           if (c + 2 < kIT / 32) tmem_ld32(t_base + (c + 2) * 32, r0);
-          scan_chunk(r1, tile * kIT + (c + 1) * 32, p, lane, row, buf, cnt, thr_key, thr_s);
+          scan_chunk(r1, tile * p.tile_stride * kIT + (c + 1) * 32, p, lane, row, buf, cnt, thr_key, thr_s);
         }
         tc_fence_before();
         __syncwarp();
@@ -292,6 +294,43 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant
   tc_fence_before();
   __syncthreads();
   if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
+// --------------------------------------------------------------------------------------------
+// Sample pass -> per-user start threshold. The sample pass scores every `tile_stride`-th item tile
+// (a fraction f of the catalog) and keeps each user's best keys; the ks-th largest sample score,
+// ks = ceil(target * f), is exceeded by about `target` items of the whole catalog. The main pass
+// then only collects scores above it (no pruning, mostly the fast path). This is a heuristic
+// STARTING point only: tt_topk_finalize verifies that at least K' candidates were found and the
+// exactness certificate; users for which it fails go to the exact fallback.
+// One warp per user.
+// --------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) sample_threshold_kernel(const unsigned long long* __restrict__ cand,
+                                                               const int* __restrict__ cand_cnt, int U, int ks,
+                                                               unsigned long long* __restrict__ thr) {
+  const int u = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (u >= U) return;
+  const int n = cand_cnt[u];
+  const unsigned long long* b = cand + static_cast<size_t>(u) * kCap;
+  unsigned long long k[kCap / 32];
+#pragma unroll
+  for (int e = 0; e < kCap / 32; ++e) {
+    const int i = e * 32 + lane;
+    k[e] = i < n ? b[i] : 0ull;
+  }
+  unsigned long long t = 0;
+  if (n >= ks) {
+    for (int bit = 63; bit >= 32; --bit) {   // score bits only: the threshold is a score level
+      const unsigned long long c0 = t | (1ull << bit);
+      int c = 0;
+#pragma unroll
+      for (int e = 0; e < kCap / 32; ++e) c += (k[e] >= c0);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+      if (c >= ks) t = c0;
+    }
+  }
+  if (lane == 0) thr[u] = t;
 }
 
 // --------------------------------------------------------------------------------------------
@@ -454,10 +493,11 @@ __global__ void __launch_bounds__(256) topk_finalize_kernel(const FinalizeParams
   if (tid == 0) {
     // Certificate: every non-candidate has bf16-path key < T, hence exact score <= score(T) + eps.
     // If the exact K-th best beats that, no non-candidate can enter the top K.
+    // T == 0 means every item of the shard is a candidate (tiny catalog, no threshold): exact.
     int flag = overflow ? 1 : 0;
-    if (!overflow && total > p.kprime) {
-      const int kth = min(p.K, nsel) - 1;
-      flag = !(key_score(s_keys[kth]) > key_score(T) + p.eps);
+    if (!overflow && T != 0ull) {
+      if (nsel < p.K) flag = 1;   // the start threshold was too high for this user
+      else flag = !(key_score(s_keys[p.K - 1]) > key_score(T) + p.eps);
     }
     p.flags[u] = flag;
   }
@@ -607,34 +647,35 @@ extern "C" int tt_topk_plan_make(int U, int N, int kprime, tt_topk_plan* plan) {
   plan->cand_bytes = static_cast<int64_t>(plan->n_ranges) * u_pad * kCap * 8;
   plan->cnt_bytes = static_cast<int64_t>(plan->n_ranges) * u_pad * 4;
   plan->thr_bytes = u_pad * 8;
+  // Sample pass (only worth it for large catalogs): score ~1/32 of the tiles; the start threshold
+  // is the score exceeded by ~4 K' items of the whole catalog, estimated from the sample's order
+  // statistics (rank = 4 K' / stride, at least 24 so the estimate is tight).
+  plan->sample_stride = 0; plan->sample_rank = 0; plan->sample_keep = 0;
+  if (total_tiles >= 2048) {
+    int stride = 32;
+    while (stride > 2 && (4 * kprime) / stride < 24) stride >>= 1;
+    plan->sample_stride = stride;
+    plan->sample_rank = (4 * kprime + stride - 1) / stride;
+    int keep = 2 * plan->sample_rank;
+    if (keep < 64) keep = 64;
+    if (keep > 256) keep = 256;
+    plan->sample_keep = keep;
+  }
   return TT_OK;
 }
 
-extern "C" int tt_score_topk(const void* users_bf16, const void* items_bf16, int item_base, const tt_topk_plan* plan,
-                             void* cand, int32_t* cand_cnt, void* thr, int mask_item0, void* stream_) {
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  TT_REQUIRE(users_bf16 && items_bf16 && plan && cand && cand_cnt && thr, "tt_score_topk: null pointer");
-  TopkParams p;
-  p.U = plan->U; p.N = plan->N; p.item_base = item_base;
-  p.n_ut = plan->n_ut; p.n_ranges = plan->n_ranges; p.tiles_per_range = plan->tiles_per_range;
-  p.total_tiles = (plan->N + kIT - 1) / kIT;
-  p.kprime = plan->kprime;
-  p.u_pad = plan->n_ut * kUT;
-  p.cand = static_cast<unsigned long long*>(cand);
-  p.cand_cnt = cand_cnt;
-  p.thr = static_cast<unsigned long long*>(thr);
-  p.mask_item0 = mask_item0;
-  TT_CHECK_CUDA(cudaMemsetAsync(thr, 0, static_cast<size_t>(plan->thr_bytes), stream));
+static int launch_score_topk(const void* users_bf16, const void* items_bf16, TopkParams& p, int n_items_rows,
+                             cudaStream_t stream) {
   CUtensorMap tmU, tmI;
   {
-    uint64_t dims[2] = {kD, static_cast<uint64_t>(plan->U)};
+    uint64_t dims[2] = {kD, static_cast<uint64_t>(p.U)};
     uint64_t str[1] = {kD * 2};
     uint32_t box[2] = {64, 128};
     int rc = make_tmap_bf16(&tmU, users_bf16, 2, dims, str, box);
     if (rc) return rc;
   }
   {
-    uint64_t dims[2] = {kD, static_cast<uint64_t>(plan->N)};
+    uint64_t dims[2] = {kD, static_cast<uint64_t>(n_items_rows)};
     uint64_t str[1] = {kD * 2};
     uint32_t box[2] = {64, 128};
     int rc = make_tmap_bf16(&tmI, items_bf16, 2, dims, str, box);
@@ -651,6 +692,46 @@ extern "C" int tt_score_topk(const void* users_bf16, const void* items_bf16, int
   score_topk_kernel<<<grid, kTopkThreads, smem, stream>>>(tmU, tmI, p);
   TT_LAUNCH_CHECK();
   return TT_OK;
+}
+
+extern "C" int tt_score_topk(const void* users_bf16, const void* items_bf16, int item_base, const tt_topk_plan* plan,
+                             void* cand, int32_t* cand_cnt, void* thr, int mask_item0, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  TT_REQUIRE(users_bf16 && items_bf16 && plan && cand && cand_cnt && thr, "tt_score_topk: null pointer");
+  TopkParams p;
+  p.U = plan->U; p.N = plan->N; p.item_base = item_base;
+  p.n_ut = plan->n_ut;
+  p.total_tiles = (plan->N + kIT - 1) / kIT;
+  p.kprime = plan->kprime;
+  p.u_pad = plan->n_ut * kUT;
+  p.cand = static_cast<unsigned long long*>(cand);
+  p.cand_cnt = cand_cnt;
+  p.thr = static_cast<unsigned long long*>(thr);
+  p.mask_item0 = mask_item0;
+  TT_CHECK_CUDA(cudaMemsetAsync(thr, 0, static_cast<size_t>(plan->thr_bytes), stream));
+
+  // ---- sample pass: every sample_stride-th tile, one range, best keys per user -> start thresholds
+  if (plan->sample_stride > 1) {
+    p.n_ranges = 1;
+    p.tile_stride = plan->sample_stride;
+    p.tiles_per_range = (p.total_tiles + plan->sample_stride - 1) / plan->sample_stride;
+    const int total_saved = p.total_tiles;
+    p.total_tiles = p.tiles_per_range;
+    p.reset_thr = 1;
+    p.kprime = plan->sample_keep;
+    int rc = launch_score_topk(users_bf16, items_bf16, p, plan->N, stream);
+    if (rc) return rc;
+    sample_threshold_kernel<<<(plan->U * 32 + 255) / 256, 256, 0, stream>>>(p.cand, p.cand_cnt, plan->U,
+                                                                           plan->sample_rank, p.thr);
+    TT_LAUNCH_CHECK();
+    p.total_tiles = total_saved;
+    p.kprime = plan->kprime;
+  }
+  // ---- main pass
+  p.n_ranges = plan->n_ranges; p.tiles_per_range = plan->tiles_per_range;
+  p.tile_stride = 1;
+  p.reset_thr = 0;
+  return launch_score_topk(users_bf16, items_bf16, p, plan->N, stream);
 }
 
 extern "C" int tt_topk_finalize(const tt_topk_plan* plan, const void* cand, const int32_t* cand_cnt, const void* thr,

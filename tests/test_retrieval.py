@@ -105,11 +105,13 @@ def test_exact_fallback_path_agrees():
         assert torch.equal(os_, score[row])
 
 
-def test_large_catalog_properties():
-    """200k items x 1500 users (not a multiple of any tile): against an fp64 torch scoring of the
-    same inputs — identical index sets, sorted output, item 0 never returned, certificate holds."""
+@pytest.mark.parametrize("N", [200_000, 300_001])
+def test_large_catalog_properties(N):
+    """200k / 300k items x 1500 users (not a multiple of any tile; the larger one goes through the
+    sample pass that seeds the thresholds): against an fp64 torch scoring of the same inputs —
+    identical index sets, sorted output, item 0 never returned, certificate holds."""
     from mrm_b200 import retrieval, synthetic
-    N, U, K = 200_000, 1500, 100
+    U, K = 1500, 100
     table = synthetic.make_catalog(N, 256, seed=77)
     users, targets = synthetic.make_queries(table, U, seed=78, noise=3.0)
     index = retrieval.CatalogIndex(table)
