@@ -306,25 +306,23 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant
 // One warp per user.
 // --------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) sample_threshold_kernel(const unsigned long long* __restrict__ cand,
-                                                               const int* __restrict__ cand_cnt, int U, int ks,
+                                                               const int* __restrict__ cand_cnt, int U, int u_pad,
+                                                               int n_ranges, int ks,
                                                                unsigned long long* __restrict__ thr) {
   const int u = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (u >= U) return;
-  const int n = cand_cnt[u];
-  const unsigned long long* b = cand + static_cast<size_t>(u) * kCap;
-  unsigned long long k[kCap / 32];
-#pragma unroll
-  for (int e = 0; e < kCap / 32; ++e) {
-    const int i = e * 32 + lane;
-    k[e] = i < n ? b[i] : 0ull;
-  }
+  int total = 0;
+  for (int r = 0; r < n_ranges; ++r) total += cand_cnt[static_cast<size_t>(r) * u_pad + u];
   unsigned long long t = 0;
-  if (n >= ks) {
+  if (total >= ks) {
     for (int bit = 63; bit >= 32; --bit) {   // score bits only: the threshold is a score level
       const unsigned long long c0 = t | (1ull << bit);
       int c = 0;
-#pragma unroll
-      for (int e = 0; e < kCap / 32; ++e) c += (k[e] >= c0);
+      for (int r = 0; r < n_ranges; ++r) {
+        const int n = cand_cnt[static_cast<size_t>(r) * u_pad + u];
+        const unsigned long long* b = cand + (static_cast<size_t>(r) * u_pad + u) * kCap;
+        for (int i = lane; i < n; i += 32) c += (b[i] >= c0);
+      }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
       if (c >= ks) t = c0;
@@ -712,17 +710,22 @@ extern "C" int tt_score_topk(const void* users_bf16, const void* items_bf16, int
 
   // ---- sample pass: every sample_stride-th tile, one range, best keys per user -> start thresholds
   if (plan->sample_stride > 1) {
-    p.n_ranges = 1;
+    const int sample_tiles = (p.total_tiles + plan->sample_stride - 1) / plan->sample_stride;
+    int sr = (num_sms() + p.n_ut - 1) / p.n_ut;           // enough (user tile, range) units for every SM
+    if (sr > plan->n_ranges) sr = plan->n_ranges;         // scratch is sized for n_ranges
+    if (sr > (sample_tiles + 15) / 16) sr = (sample_tiles + 15) / 16;
+    if (sr < 1) sr = 1;
     p.tile_stride = plan->sample_stride;
-    p.tiles_per_range = (p.total_tiles + plan->sample_stride - 1) / plan->sample_stride;
+    p.tiles_per_range = (sample_tiles + sr - 1) / sr;
+    p.n_ranges = (sample_tiles + p.tiles_per_range - 1) / p.tiles_per_range;
     const int total_saved = p.total_tiles;
-    p.total_tiles = p.tiles_per_range;
+    p.total_tiles = sample_tiles;
     p.reset_thr = 1;
     p.kprime = plan->sample_keep;
     int rc = launch_score_topk(users_bf16, items_bf16, p, plan->N, stream);
     if (rc) return rc;
-    sample_threshold_kernel<<<(plan->U * 32 + 255) / 256, 256, 0, stream>>>(p.cand, p.cand_cnt, plan->U,
-                                                                           plan->sample_rank, p.thr);
+    sample_threshold_kernel<<<(plan->U * 32 + 255) / 256, 256, 0, stream>>>(p.cand, p.cand_cnt, plan->U, p.u_pad,
+                                                                           p.n_ranges, plan->sample_rank, p.thr);
     TT_LAUNCH_CHECK();
     p.total_tiles = total_saved;
     p.kprime = plan->kprime;

@@ -215,7 +215,7 @@ class TwoTowerEngine:
     # ------------------------------------------------------------------ helpers
     def _gemm(self, A, B, **kw):
         """tt_gemm_bf16; with ``self.gemm_log`` set (a list), every launch is bracketed by CUDA events
-        and logged as (event0, event1, algorithmic flops) — bench.py's roofline measurement."""
+        and logged as (event0, event1, algorithmic flops, algorithmic bytes) — bench.py's roofline measurement."""
         log = getattr(self, "gemm_log", None)
         if log is None:
             ops.gemm(A, B, **kw)
@@ -224,11 +224,25 @@ class TwoTowerEngine:
         M = A.shape[1] if a_mn else A.shape[0]
         K = A.shape[0] if a_mn else A.shape[1]
         N = B.shape[1] if b_mn else B.shape[0]
+        nbytes = 2.0 * (M * K + N * K)                      # bf16 operands
+        if kw.get("out_bf16") is not None:
+            nbytes += 2.0 * M * N
+        if kw.get("out_f32") is not None:
+            nbytes += (8.0 if kw.get("accumulate") else 4.0) * M * N
+        if kw.get("residual") is not None:
+            nbytes += 4.0 * M * N
+        if kw.get("gate") is not None:
+            nbytes += 2.0 * M * N
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         ops.gemm(A, B, **kw)
         e1.record()
-        log.append((e0, e1, 2.0 * M * N * K))
+        log.append((e0, e1, 2.0 * M * N * K, nbytes))
+
+    def _side_stream(self) -> torch.cuda.Stream:
+        if getattr(self, "_side", None) is None:
+            self._side = torch.cuda.Stream(device=self.device)
+        return self._side
 
     def _lp(self, l: int, name: str) -> str:
         return f"user_tower.transformer_encoder.layers.{l}.{name}"
@@ -348,9 +362,16 @@ class TwoTowerEngine:
         ws = self.workspace(B, L)
         if not self.shadow_valid:
             self.refresh_shadow()
+        # The item tower (a handful of tiny kernels) is independent of the user tower: it runs on a
+        # side stream (a parallel branch of the captured graph) and fills the tails of the big kernels.
+        main = torch.cuda.current_stream()
+        side = self._side_stream()
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            self.item_forward(ws, batch["target_audio"], batch["target_image"], batch["target_input_ids"],
+                              batch["target_tabular"], training)
         self.user_forward(ws, ids, batch.get("history_mask"), batch["user_gender"], batch["user_country"], training)
-        self.item_forward(ws, batch["target_audio"], batch["target_image"], batch["target_input_ids"],
-                          batch["target_tabular"], training)
+        main.wait_stream(side)
         self._last = (ws, batch, training)
         self._gathered = None
         return ws
@@ -363,6 +384,23 @@ class TwoTowerEngine:
         return ws["loss"], ws["S"], ws["un"], ws["in"]
 
     # ------------------------------------------------------------------ backward
+    def _item_backward(self, ws, training, seed, sdev) -> None:
+        cfg, p, w, g = self.cfg, self.p, self.w, self.g
+        it = "item_tower.fusion_layer."
+        gemm = self._gemm
+        ops.chain_bwd(ws["y2"], ln=(p[it + "5.weight"], p[it + "5.bias"]), l2norm=True, dout=ws["din"],
+                      dx_bf16=ws["dy2i_bf"], dgamma=g[it + "5.weight"], dbeta=g[it + "5.bias"],
+                      dx_colsum=g[it + "4.bias"])
+        gemm(ws["dy2i_bf"], ws["a"], a_mn=True, b_mn=True, out_f32=g[it + "4.weight"], accumulate=True)
+        gemm(ws["dy2i_bf"], w[it + "4.weight"], b_mn=True, out_f32=ws["da"])
+        ops.bn_relu_bwd(ws["y1"], p[it + "1.weight"], p[it + "1.bias"], self.bn_running_mean, self.bn_running_var,
+                        None, training=training, drop_p=(0.1 if training and cfg.dropout > 0 else 0.0),
+                        seed=seed, seed_dev=sdev, site=SITE_ITEM, save_mean=ws["bn_mean"], save_rstd=ws["bn_rstd"],
+                        dout=ws["da"], dy_bf16=ws["dy1i_bf"], dgamma=g[it + "1.weight"], dbeta=g[it + "1.bias"],
+                        dy_colsum=g[it + "0.bias"])
+        gemm(ws["dy1i_bf"], ws["xi"], a_mn=True, b_mn=True, out_f32=g[it + "0.weight"], accumulate=True)
+
+
     def backward(self, loss_scale: float = 1.0) -> None:
         """Accumulates d(loss_scale * loss)/d(param) into self.grad (self.g views)."""
         ws, batch, training = self._last
@@ -392,18 +430,12 @@ class TwoTowerEngine:
             gemm(g_["dS"], g_["I_all"], b_mn=True, alpha=inv_t, out_f32=ws["dun"])
             gemm(g_["dS2"], g_["U_all"], b_mn=True, alpha=inv_t, out_f32=ws["din"])
 
-        # ---- item tower
-        ops.chain_bwd(ws["y2"], ln=(p[it + "5.weight"], p[it + "5.bias"]), l2norm=True, dout=ws["din"],
-                      dx_bf16=ws["dy2i_bf"], dgamma=g[it + "5.weight"], dbeta=g[it + "5.bias"],
-                      dx_colsum=g[it + "4.bias"])
-        gemm(ws["dy2i_bf"], ws["a"], a_mn=True, b_mn=True, out_f32=g[it + "4.weight"], accumulate=True)
-        gemm(ws["dy2i_bf"], w[it + "4.weight"], b_mn=True, out_f32=ws["da"])
-        ops.bn_relu_bwd(ws["y1"], p[it + "1.weight"], p[it + "1.bias"], self.bn_running_mean, self.bn_running_var,
-                        None, training=training, drop_p=(0.1 if training and cfg.dropout > 0 else 0.0),
-                        seed=seed, seed_dev=sdev, site=SITE_ITEM, save_mean=ws["bn_mean"], save_rstd=ws["bn_rstd"],
-                        dout=ws["da"], dy_bf16=ws["dy1i_bf"], dgamma=g[it + "1.weight"], dbeta=g[it + "1.bias"],
-                        dy_colsum=g[it + "0.bias"])
-        gemm(ws["dy1i_bf"], ws["xi"], a_mn=True, b_mn=True, out_f32=g[it + "0.weight"], accumulate=True)
+        # ---- item tower (side stream: independent of the user tower's backward)
+        main = torch.cuda.current_stream()
+        side = self._side_stream()
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            self._item_backward(ws, training, seed, sdev)
 
         # ---- user head
         ops.chain_bwd(ws["u"], l2norm=True, dout=ws["dun"], dx_bf16=ws["du_bf"],
@@ -469,6 +501,7 @@ class TwoTowerEngine:
                          g[ut + "item_embedding.weight"], g[ut + "position_embedding.weight"],
                          g[ut + "layer_norm.weight"], g[ut + "layer_norm.bias"], drop_p=dp, seed=seed,
                          seed_dev=sdev, site=SITE_EMB)
+        main.wait_stream(side)
 
     # ------------------------------------------------------------------ optimizer
     def adamw_step(self, lr: float = 1e-4, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.01,

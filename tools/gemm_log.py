@@ -39,12 +39,9 @@ for it in range(4):
     eng.forward(batch, training=True)
     eng.backward()
     torch.cuda.synchronize()
-    for (e0, e1, f), d in zip(eng.gemm_log, descr):
-        if it > 0:
-            tot.setdefault(len(tot) if it == 1 else None, None)
-    if it == 3:
+        if it == 3:
         total = 0.0
-        for i, ((e0, e1, f), d) in enumerate(zip(eng.gemm_log, descr)):
+        for i, ((e0, e1, f, nb), d) in enumerate(zip(eng.gemm_log, descr)):
             us = e0.elapsed_time(e1) * 1e3
             total += us
             print(f"{i:2d} M={d[0]:6d} N={d[1]:5d} K={d[2]:6d} {us:8.1f} us {f / us / 1e6:8.1f} TF/s  {d[3]}")
