@@ -213,6 +213,7 @@ def test_gathered_negatives_two_virtual_ranks_match_global_oracle():
         err = (got - ref).norm().item()
         # bf16 operand noise on a 2 x 16 batch: the reference itself under bf16 autocast shows 6-9 %
         # per-tensor error on the comparable fixtures; a wrong exchange would show O(1) errors
-        if err > 0.15 * ref.norm().item() + 1e-5 * ref.numel() ** 0.5:
+        # (the Linear bias in front of BatchNorm has an exactly-zero true gradient: absolute floor)
+        if err > 0.15 * ref.norm().item() + 5e-5 * ref.numel() ** 0.5:
             bad.append((k, err, ref.norm().item()))
     assert not bad, bad[:5]
