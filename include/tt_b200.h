@@ -214,6 +214,28 @@ int tt_adamw_step(float* p, float* g, float* m, float* v, int64_t n, float lr, f
 /* ++*step_dev; *seed_dev += golden-ratio increment (either may be NULL). */
 int tt_step_counters_advance(int64_t* step_dev, uint64_t* seed_dev, void* stream);
 
+/* ---- last-layer specialisation ------------------------------------------
+ * Only out[b, len_b-1] of the LAST encoder layer is read (src/models/user_tower.py:122-132), so
+ * that layer needs K/V for every position but the query, attention output, out_proj, norm2 and
+ * FFN for one row per sequence. Exact: identical outputs and gradients, the skipped values are
+ * never consumed.
+ *   tt_gather_rows      : out[b] = x[b*L + last_idx[b]] (fp32 and/or bf16 source/destination pairs)
+ *   tt_scatter_rows_add : x[b*L + last_idx[b]] = rows[b] (+ previous value when accumulate)
+ *   tt_attn_lastq_fwd   : q bf16 [B, H*64], K/V from qkv bf16 [B*L, 3*H*64] -> ctx bf16 [B, H*64],
+ *                         lse fp32 [B, H]; keys 0..last_idx[b]
+ *   tt_attn_lastq_bwd   : -> dq bf16 [B, H*64] and the K/V thirds of dqkv for EVERY position
+ *                         (zeros beyond last_idx[b])
+ */
+int tt_gather_rows(const float* x_f32, const void* x_bf16, const int32_t* last_idx, int B, int L, int W,
+                   float* out_f32, void* out_bf16, void* stream);
+int tt_scatter_rows_add(const float* rows, const int32_t* last_idx, int B, int L, int W, float* x, int accumulate,
+                        void* stream);
+int tt_attn_lastq_fwd(const void* q, const void* qkv, const int32_t* last_idx, void* ctx, float* lse, int B, int L,
+                      int H, float drop_p, uint64_t seed, const uint64_t* seed_dev, uint32_t site, void* stream);
+int tt_attn_lastq_bwd(const void* q, const void* qkv, const int32_t* last_idx, const void* ctx, const void* dctx,
+                      const float* lse, void* dq, void* dqkv, int B, int L, int H, float drop_p, uint64_t seed,
+                      const uint64_t* seed_dev, uint32_t site, void* stream);
+
 /* ---- symmetric InfoNCE (src/models/two_tower.py:106-140) --------------------------------
  * Row formulation: S [R, C] fp32 holds logits of R local rows against C (all-gathered)
  * columns, the positive of row i sits at column pos0 + i.

@@ -130,6 +130,10 @@ class TopkPlan(ctypes.Structure):
 
 _I64 = ctypes.c_int64
 _SIGNATURES = {
+    "tt_gather_rows": [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p],
+    "tt_scatter_rows_add": [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_int32, c_void_p],
+    "tt_attn_lastq_fwd": [c_void_p] * 5 + [c_int32, c_int32, c_int32, c_float, c_uint64, c_void_p, c_uint32, c_void_p],
+    "tt_attn_lastq_bwd": [c_void_p] * 8 + [c_int32, c_int32, c_int32, c_float, c_uint64, c_void_p, c_uint32, c_void_p],
     "tt_topk_plan_make": [c_int32, c_int32, c_int32, ctypes.POINTER(TopkPlan)],
     "tt_score_topk": [c_void_p, c_void_p, c_int32, ctypes.POINTER(TopkPlan), c_void_p, c_void_p, c_void_p, c_int32,
                       c_void_p],

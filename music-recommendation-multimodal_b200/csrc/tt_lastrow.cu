@@ -1,0 +1,299 @@
+// Last-layer specialisation of the SASRec user tower.
+//
+// The reference gathers out[b, len_b - 1] after the LAST encoder layer (src/models/user_tower.py:
+// 122-132); nothing else of that layer's output is ever read, and its pad/other rows carry zero
+// gradient. So in the last layer only K and V are needed for every position; the query, the
+// attention output, out_proj, both residual adds, norm2 and the FFN are needed for ONE row per
+// sequence. These kernels implement that exactly (same results as the full computation):
+//   tt_gather_rows        : rows[b] = x[b*L + last_idx[b]]  (fp32 and/or bf16 copies)
+//   tt_scatter_rows_add   : x[b*L + last_idx[b]] (+)= rows[b]
+//   tt_attn_lastq_fwd/bwd : causal attention for the single query row len-1 of every
+//                           (sequence, head): one warp per (b, h), lane-per-key dot products,
+//                           warp-shuffle softmax, lane-per-dim-pair P*V. HBM/L2-bound gathers of
+//                           128-byte K/V rows; no tensor cores (2*L*64 MACs per problem).
+#include "../../include/tt_b200.h"
+#include "tt_common.cuh"
+
+namespace tt {
+
+static constexpr int kDh = 64;
+static constexpr int kMaxL = 512;
+static constexpr float kLog2e = 1.4426950408889634f;
+
+__global__ void gather_rows_kernel(const float* __restrict__ x32, const __nv_bfloat16* __restrict__ x16,
+                                   const int32_t* __restrict__ last_idx, int B, int L, int W,
+                                   float* __restrict__ out32, __nv_bfloat16* __restrict__ out16) {
+  const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (b >= B) return;
+  const size_t row = static_cast<size_t>(b) * L + last_idx[b];
+  for (int c = lane * 4; c < W; c += 128) {
+    if (x32 && out32)
+      *reinterpret_cast<float4*>(out32 + static_cast<size_t>(b) * W + c) =
+          __ldg(reinterpret_cast<const float4*>(x32 + row * W + c));
+    if (x16 && out16)
+      *reinterpret_cast<uint2*>(out16 + static_cast<size_t>(b) * W + c) =
+          __ldg(reinterpret_cast<const uint2*>(x16 + row * W + c));
+  }
+}
+
+__global__ void scatter_rows_add_kernel(const float* __restrict__ rows, const int32_t* __restrict__ last_idx, int B,
+                                        int L, int W, float* __restrict__ x, int accumulate) {
+  const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (b >= B) return;
+  const size_t row = static_cast<size_t>(b) * L + last_idx[b];
+  for (int c = lane * 4; c < W; c += 128) {
+    float4 v = __ldg(reinterpret_cast<const float4*>(rows + static_cast<size_t>(b) * W + c));
+    float4* dst = reinterpret_cast<float4*>(x + row * W + c);
+    if (accumulate) {
+      const float4 o = *dst;
+      v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+    }
+    *dst = v;
+  }
+}
+
+struct LastQParams {
+  const __nv_bfloat16* q;     // [B, H*64]
+  const __nv_bfloat16* qkv;   // [B*L, 3*H*64] (K, V thirds used)
+  const int32_t* last_idx;    // [B]
+  int B, L, H;
+  float scale;
+  uint32_t drop_thresh; float drop_scale; uint64_t seed; const uint64_t* seed_dev; uint32_t site;
+  __nv_bfloat16* ctx;         // [B, H*64]
+  float* lse;                 // [B, H]
+  // backward
+  const __nv_bfloat16* dctx;  // [B, H*64]
+  __nv_bfloat16* dq;          // [B, H*64]
+  __nv_bfloat16* dqkv;        // [B*L, 3*H*64]: K and V thirds written for every position (zeros beyond len)
+};
+
+__device__ __forceinline__ void load_row64(const __nv_bfloat16* p, float (&v)[64]) {
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    const uint4 x = __ldg(reinterpret_cast<const uint4*>(p) + u);
+    const uint32_t w[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+    for (int h = 0; h < 4; ++h) {
+      const float2 f = unpack_bf16(w[h]);
+      v[u * 8 + h * 2] = f.x;
+      v[u * 8 + h * 2 + 1] = f.y;
+    }
+  }
+}
+__device__ __forceinline__ float dot_row64(const __nv_bfloat16* p, const float (&q)[64]) {
+  float acc = 0.f;
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    const uint4 x = __ldg(reinterpret_cast<const uint4*>(p) + u);
+    const uint32_t w[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+    for (int h = 0; h < 4; ++h) {
+      const float2 f = unpack_bf16(w[h]);
+      acc += f.x * q[u * 8 + h * 2] + f.y * q[u * 8 + h * 2 + 1];
+    }
+  }
+  return acc;
+}
+__device__ __forceinline__ void store_scaled_row64(__nv_bfloat16* p, const float (&v)[64], float s) {
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    uint4 x;
+    x.x = pack_bf16(v[u * 8 + 0] * s, v[u * 8 + 1] * s);
+    x.y = pack_bf16(v[u * 8 + 2] * s, v[u * 8 + 3] * s);
+    x.z = pack_bf16(v[u * 8 + 4] * s, v[u * 8 + 5] * s);
+    x.w = pack_bf16(v[u * 8 + 6] * s, v[u * 8 + 7] * s);
+    reinterpret_cast<uint4*>(p)[u] = x;
+  }
+}
+
+// blockDim = 128 (4 warps); one warp per (b, h); smem: 4 x kMaxL floats
+__global__ void __launch_bounds__(128) attn_lastq_fwd_kernel(const LastQParams p) {
+  __shared__ float s_p[4][kMaxL];
+  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int bh = blockIdx.x * 4 + wib;
+  if (bh >= p.B * p.H) return;
+  const int b = bh / p.H, h = bh % p.H;
+  const int D = p.H * kDh;
+  const int last = p.last_idx[b];
+  const int len = last + 1;
+  float q[64];
+  load_row64(p.q + static_cast<size_t>(b) * D + h * kDh, q);
+  const __nv_bfloat16* kbase = p.qkv + static_cast<size_t>(b) * p.L * 3 * D + D + h * kDh;
+  const __nv_bfloat16* vbase = kbase + D;
+  const float c1 = p.scale * kLog2e;
+  float m = -INFINITY;
+  for (int j = lane; j < len; j += 32) {
+    const float s = dot_row64(kbase + static_cast<size_t>(j) * 3 * D, q) * c1;
+    s_p[wib][j] = s;
+    m = fmaxf(m, s);
+  }
+  m = warp_max(m);
+  const uint64_t seed = p.seed + ((p.drop_thresh && p.seed_dev) ? *p.seed_dev : 0ull);
+  const uint32_t dkey = drop_key(seed, p.site);
+  const uint64_t didx0 = (static_cast<uint64_t>(bh) * p.L + last) * p.L;
+  float l = 0.f;
+  for (int j = lane; j < len; j += 32) {
+    float e = exp2f(s_p[wib][j] - m);
+    l += e;
+    if (p.drop_thresh) e = drop_keep_k(dkey, didx0 + j, p.drop_thresh) ? e * p.drop_scale : 0.f;
+    s_p[wib][j] = e;
+  }
+  l = warp_sum(l);
+  __syncwarp();
+  float a0 = 0.f, a1 = 0.f;
+  for (int j = 0; j < len; ++j) {
+    const float pj = s_p[wib][j];
+    const float2 v = unpack_bf16(__ldg(reinterpret_cast<const uint32_t*>(vbase + static_cast<size_t>(j) * 3 * D) + lane));
+    a0 += pj * v.x;
+    a1 += pj * v.y;
+  }
+  const float inv = 1.f / l;
+  reinterpret_cast<uint32_t*>(p.ctx + static_cast<size_t>(b) * D + h * kDh)[lane] = pack_bf16(a0 * inv, a1 * inv);
+  if (lane == 0 && p.lse) p.lse[bh] = (m + log2f(l)) / kLog2e;   // natural-log sum-exp of the scaled scores
+}
+
+__global__ void __launch_bounds__(128) attn_lastq_bwd_kernel(const LastQParams p) {
+  __shared__ float s_ds[4][kMaxL];
+  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int bh = blockIdx.x * 4 + wib;
+  if (bh >= p.B * p.H) return;
+  const int b = bh / p.H, h = bh % p.H;
+  const int D = p.H * kDh;
+  const int last = p.last_idx[b];
+  const int len = last + 1;
+  float q[64], g[64];
+  load_row64(p.q + static_cast<size_t>(b) * D + h * kDh, q);
+  load_row64(p.dctx + static_cast<size_t>(b) * D + h * kDh, g);
+  // delta = dctx . ctx
+  float delta;
+  {
+    const float2 o = unpack_bf16(reinterpret_cast<const uint32_t*>(p.ctx + static_cast<size_t>(b) * D + h * kDh)[lane]);
+    const float2 d = unpack_bf16(reinterpret_cast<const uint32_t*>(p.dctx + static_cast<size_t>(b) * D + h * kDh)[lane]);
+    delta = warp_sum(o.x * d.x + o.y * d.y);
+  }
+  const size_t seq0 = static_cast<size_t>(b) * p.L;
+  const __nv_bfloat16* kbase = p.qkv + seq0 * 3 * D + D + h * kDh;
+  const __nv_bfloat16* vbase = kbase + D;
+  __nv_bfloat16* dkbase = p.dqkv + seq0 * 3 * D + D + h * kDh;
+  __nv_bfloat16* dvbase = dkbase + D;
+  const float c1 = p.scale * kLog2e;
+  const float lse2 = p.lse[bh] * kLog2e;
+  const uint64_t seed = p.seed + ((p.drop_thresh && p.seed_dev) ? *p.seed_dev : 0ull);
+  const uint32_t dkey = drop_key(seed, p.site);
+  const uint64_t didx0 = (static_cast<uint64_t>(bh) * p.L + last) * p.L;
+  for (int j = lane; j < p.L; j += 32) {
+    __nv_bfloat16* dk = dkbase + static_cast<size_t>(j) * 3 * D;
+    __nv_bfloat16* dv = dvbase + static_cast<size_t>(j) * 3 * D;
+    if (j < len) {
+      const float pr = exp2f(dot_row64(kbase + static_cast<size_t>(j) * 3 * D, q) * c1 - lse2);
+      float dp = dot_row64(vbase + static_cast<size_t>(j) * 3 * D, g);
+      float pd = pr;
+      if (p.drop_thresh) {
+        const bool keep = drop_keep_k(dkey, didx0 + j, p.drop_thresh);
+        pd = keep ? pr * p.drop_scale : 0.f;
+        dp = keep ? dp * p.drop_scale : 0.f;
+      }
+      const float ds = pr * (dp - delta) * p.scale;
+      s_ds[wib][j] = ds;
+      store_scaled_row64(dk, q, ds);    // dK_j = dS_j * q
+      store_scaled_row64(dv, g, pd);    // dV_j = Pd_j * dO
+    } else {
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        reinterpret_cast<uint4*>(dk)[u] = make_uint4(0, 0, 0, 0);
+        reinterpret_cast<uint4*>(dv)[u] = make_uint4(0, 0, 0, 0);
+      }
+    }
+  }
+  __syncwarp();
+  float a0 = 0.f, a1 = 0.f;
+  for (int j = 0; j < len; ++j) {
+    const float ds = s_ds[wib][j];
+    const float2 k = unpack_bf16(__ldg(reinterpret_cast<const uint32_t*>(kbase + static_cast<size_t>(j) * 3 * D) + lane));
+    a0 += ds * k.x;
+    a1 += ds * k.y;
+  }
+  reinterpret_cast<uint32_t*>(p.dq + static_cast<size_t>(b) * D + h * kDh)[lane] = pack_bf16(a0, a1);
+}
+
+static uint32_t drop_threshold(float p) {
+  if (p <= 0.f) return 0;
+  double t = static_cast<double>(p) * 4294967296.0;
+  uint32_t v = t >= 4294967295.0 ? 4294967295u : static_cast<uint32_t>(t);
+  return v == 0 ? 1 : v;
+}
+
+}  // namespace tt
+
+using namespace tt;
+
+extern "C" int tt_gather_rows(const float* x_f32, const void* x_bf16, const int32_t* last_idx, int B, int L, int W,
+                              float* out_f32, void* out_bf16, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  TT_REQUIRE(last_idx && B > 0 && L > 0 && W > 0 && W % 4 == 0, "tt_gather_rows: bad arguments");
+  TT_REQUIRE((x_f32 && out_f32) || (x_bf16 && out_bf16), "tt_gather_rows: nothing to gather");
+  gather_rows_kernel<<<(B * 32 + 255) / 256, 256, 0, stream>>>(x_f32, static_cast<const __nv_bfloat16*>(x_bf16),
+                                                              last_idx, B, L, W, out_f32,
+                                                              static_cast<__nv_bfloat16*>(out_bf16));
+  TT_LAUNCH_CHECK();
+  return TT_OK;
+}
+
+extern "C" int tt_scatter_rows_add(const float* rows, const int32_t* last_idx, int B, int L, int W, float* x,
+                                   int accumulate, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  TT_REQUIRE(rows && last_idx && x && B > 0 && L > 0 && W > 0 && W % 4 == 0, "tt_scatter_rows_add: bad arguments");
+  scatter_rows_add_kernel<<<(B * 32 + 255) / 256, 256, 0, stream>>>(rows, last_idx, B, L, W, x, accumulate);
+  TT_LAUNCH_CHECK();
+  return TT_OK;
+}
+
+static int fill_lastq(LastQParams& p, const void* q, const void* qkv, const int32_t* last_idx, int B, int L, int H,
+                      float drop_p, uint64_t seed, const uint64_t* seed_dev, uint32_t site, const char* who) {
+  TT_REQUIRE(q && qkv && last_idx && B > 0 && L > 0 && H > 0, "%s: bad arguments", who);
+  TT_REQUIRE(L <= kMaxL, "%s: L=%d > %d unsupported", who, L, kMaxL);
+  TT_REQUIRE(drop_p >= 0.f && drop_p < 1.f, "%s: drop_p out of range", who);
+  p.q = static_cast<const __nv_bfloat16*>(q);
+  p.qkv = static_cast<const __nv_bfloat16*>(qkv);
+  p.last_idx = last_idx;
+  p.B = B; p.L = L; p.H = H;
+  p.scale = 0.125f;
+  p.drop_thresh = drop_threshold(drop_p);
+  p.drop_scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+  p.seed = seed; p.seed_dev = seed_dev; p.site = site;
+  p.ctx = nullptr; p.lse = nullptr; p.dctx = nullptr; p.dq = nullptr; p.dqkv = nullptr;
+  return TT_OK;
+}
+
+extern "C" int tt_attn_lastq_fwd(const void* q, const void* qkv, const int32_t* last_idx, void* ctx, float* lse, int B,
+                                 int L, int H, float drop_p, uint64_t seed, const uint64_t* seed_dev, uint32_t site,
+                                 void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  LastQParams p;
+  int rc = fill_lastq(p, q, qkv, last_idx, B, L, H, drop_p, seed, seed_dev, site, "tt_attn_lastq_fwd");
+  if (rc) return rc;
+  TT_REQUIRE(ctx, "tt_attn_lastq_fwd: null ctx");
+  p.ctx = static_cast<__nv_bfloat16*>(ctx);
+  p.lse = lse;
+  attn_lastq_fwd_kernel<<<(B * H + 3) / 4, 128, 0, stream>>>(p);
+  TT_LAUNCH_CHECK();
+  return TT_OK;
+}
+
+extern "C" int tt_attn_lastq_bwd(const void* q, const void* qkv, const int32_t* last_idx, const void* ctx,
+                                 const void* dctx, const float* lse, void* dq, void* dqkv, int B, int L, int H,
+                                 float drop_p, uint64_t seed, const uint64_t* seed_dev, uint32_t site, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  LastQParams p;
+  int rc = fill_lastq(p, q, qkv, last_idx, B, L, H, drop_p, seed, seed_dev, site, "tt_attn_lastq_bwd");
+  if (rc) return rc;
+  TT_REQUIRE(ctx && dctx && lse && dq && dqkv, "tt_attn_lastq_bwd: null pointer");
+  p.ctx = const_cast<__nv_bfloat16*>(static_cast<const __nv_bfloat16*>(ctx));
+  p.dctx = static_cast<const __nv_bfloat16*>(dctx);
+  p.lse = const_cast<float*>(lse);
+  p.dq = static_cast<__nv_bfloat16*>(dq);
+  p.dqkv = static_cast<__nv_bfloat16*>(dqkv);
+  attn_lastq_bwd_kernel<<<(B * H + 3) / 4, 128, 0, stream>>>(p);
+  TT_LAUNCH_CHECK();
+  return TT_OK;
+}

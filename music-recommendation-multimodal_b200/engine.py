@@ -121,6 +121,9 @@ class TwoTowerEngine:
         self.base_seed = 0x5EED
         self._ws: Dict[Tuple[int, int], Dict[str, torch.Tensor]] = {}
         self.shadow_valid = False
+        #: compute the last encoder layer's query / out_proj / FFN only for the row that is read
+        #: (exact). False runs every layer on every position like the reference.
+        self.prune_last_layer = True
 
     # ------------------------------------------------------------------ parameters
     def load_state_dict(self, sd: Dict[str, torch.Tensor]) -> None:
@@ -170,6 +173,25 @@ class TwoTowerEngine:
             ws[f"h2_{l}"] = torch.empty(T, D, **bf)
             ws[f"f_{l}"] = torch.empty(T, FF, **bf)
             ws[f"xout_{l}"] = torch.empty(T, D, **f32)
+        # last-layer single-row path (B rows instead of B*L)
+        ws["zero_idx"] = torch.zeros(B, device=dev, dtype=torch.int32)
+        ws["hq"] = torch.empty(B, D, **bf)
+        ws["xq_in"] = torch.empty(B, D, **f32)
+        ws["qq"] = torch.empty(B, D, **bf)
+        ws["ctxq"] = torch.empty(B, D, **bf)
+        ws["lseq"] = torch.empty(B, Hh, **f32)
+        ws["xmid_q"] = torch.empty(B, D, **f32)
+        ws["h2q"] = torch.empty(B, D, **bf)
+        ws["fq"] = torch.empty(B, FF, **bf)
+        ws["xout_q"] = torch.empty(B, D, **f32)
+        ws["dxq"] = torch.empty(B, D, **f32)
+        ws["dy_q"] = torch.empty(B, D, **bf)
+        ws["dpre_q"] = torch.empty(B, FF, **bf)
+        ws["dh_q"] = torch.empty(B, D, **f32)
+        ws["dxmid_q"] = torch.empty(B, D, **f32)
+        ws["dctx_q"] = torch.empty(B, D, **bf)
+        ws["dq_q"] = torch.empty(B, D, **bf)
+        ws["dhq"] = torch.empty(B, D, **f32)
         ws["cat"] = torch.zeros(B + 1, D + 48, **bf)[:B]          # +1 row: ragged MN-major reads
         ws["z1"] = torch.empty(B, D, **f32)
         ws["a1"] = torch.empty(B, D, **bf)
@@ -265,6 +287,10 @@ class TwoTowerEngine:
                          ws["x_in0"], ws["h1_0"], drop_p=dp, seed=seed, seed_dev=sdev, site=SITE_EMB)
         x_in = ws["x_in0"]
         for l in range(cfg.num_layers):
+            if self.prune_last_layer and l == cfg.num_layers - 1:
+                self._last_layer_forward(ws, l, x_in, B, L, dp, seed, sdev)
+                x_in = None
+                break
             self._gemm(ws[f"h1_{l}"], w[self._lp(l, "self_attn.in_proj_weight")],
                        bias=p[self._lp(l, "self_attn.in_proj_bias")], out_bf16=ws[f"qkv_{l}"])
             ops.attn_fwd(ws[f"qkv_{l}"], ws[f"ctx_{l}"], ws[f"lse_{l}"], B, L, cfg.num_heads, drop_p=dp,
@@ -284,14 +310,88 @@ class TwoTowerEngine:
             if l + 1 < cfg.num_layers:
                 ops.chain_fwd(x_in, ln=(p[self._lp(l + 1, "norm1.weight")], p[self._lp(l + 1, "norm1.bias")]),
                               out_bf16=ws[f"h1_{l + 1}"])
-        ops.gather_cat_fwd(x_in, ws["last_idx"], gender, country, p[ut + "gender_embedding.weight"],
-                           p[ut + "country_embedding.weight"], B, L, ws["cat"])
+        if x_in is None:   # pruned last layer: its output exists for the gathered rows only
+            ops.gather_cat_fwd(ws["xout_q"], ws["zero_idx"], gender, country, p[ut + "gender_embedding.weight"],
+                               p[ut + "country_embedding.weight"], B, 1, ws["cat"])
+        else:
+            ops.gather_cat_fwd(x_in, ws["last_idx"], gender, country, p[ut + "gender_embedding.weight"],
+                               p[ut + "country_embedding.weight"], B, L, ws["cat"])
         self._gemm(ws["cat"], w[ut + "fusion_layer.0.weight"], bias=p[ut + "fusion_layer.0.bias"], out_f32=ws["z1"])
         ops.chain_fwd(ws["z1"], ln=(p[ut + "fusion_layer.1.weight"], p[ut + "fusion_layer.1.bias"]), relu=True,
                       out_bf16=ws["a1"])
         self._gemm(ws["a1"], w[ut + "fusion_layer.3.weight"], bias=p[ut + "fusion_layer.3.bias"], out_f32=ws["u"])
         ops.chain_fwd(ws["u"], l2norm=True, out_f32=ws["un"], out_bf16=ws["un_bf"])
         return ws["un"]
+
+    def _last_layer_forward(self, ws, l, x_in, B, L, dp, seed, sdev) -> None:
+        """Last encoder layer, exact single-row form: K/V for every position, everything downstream of
+        the attention for the row len-1 of each sequence only."""
+        cfg, p, w = self.cfg, self.p, self.w
+        D = cfg.embedding_dim
+        Wqkv, bqkv = w[self._lp(l, "self_attn.in_proj_weight")], p[self._lp(l, "self_attn.in_proj_bias")]
+        self._gemm(ws[f"h1_{l}"], Wqkv[D:], bias=bqkv[D:], out_bf16=ws[f"qkv_{l}"][:, D:])          # K | V
+        ops.gather_rows(ws["last_idx"], B, L, x_f32=x_in, out_f32=ws["xq_in"], x_bf16=ws[f"h1_{l}"], out_bf16=ws["hq"])
+        self._gemm(ws["hq"], Wqkv[:D], bias=bqkv[:D], out_bf16=ws["qq"])                          # Q, B rows
+        ops.attn_lastq_fwd(ws["qq"], ws[f"qkv_{l}"], ws["last_idx"], ws["ctxq"], ws["lseq"], B, L, cfg.num_heads,
+                           drop_p=dp, seed=seed, seed_dev=sdev, site=_site(l, 0))
+        self._gemm(ws["ctxq"], w[self._lp(l, "self_attn.out_proj.weight")], bias=p[self._lp(l, "self_attn.out_proj.bias")],
+                   drop_p=dp, drop_seed=seed, drop_seed_dev=sdev, drop_site=_site(l, 1), residual=ws["xq_in"],
+                   out_f32=ws["xmid_q"])
+        ops.chain_fwd(ws["xmid_q"], ln=(p[self._lp(l, "norm2.weight")], p[self._lp(l, "norm2.bias")]),
+                      out_bf16=ws["h2q"])
+        self._gemm(ws["h2q"], w[self._lp(l, "linear1.weight")], bias=p[self._lp(l, "linear1.bias")], relu=True,
+                   drop_p=dp, drop_seed=seed, drop_seed_dev=sdev, drop_site=_site(l, 2), out_bf16=ws["fq"])
+        self._gemm(ws["fq"], w[self._lp(l, "linear2.weight")], bias=p[self._lp(l, "linear2.bias")], drop_p=dp,
+                   drop_seed=seed, drop_seed_dev=sdev, drop_site=_site(l, 3), residual=ws["xmid_q"],
+                   out_f32=ws["xout_q"])
+
+    def _last_layer_backward(self, ws, l, x_in, B, L, dp, seed, sdev, dx, dx_other):
+        """Backward of _last_layer_forward. ws['dxq'] holds d(loss)/d(xout_q) (B rows). Returns the
+        (dx, dx_other) ping-pong with dx = gradient w.r.t. the layer input (all positions)."""
+        cfg, p, w, g = self.cfg, self.p, self.w, self.g
+        D = cfg.embedding_dim
+        gemm = self._gemm
+        ffn_scale = 1.0 / (1.0 - dp) if dp > 0 else 1.0
+        Wqkv = w[self._lp(l, "self_attn.in_proj_weight")]
+        gW, gb = g[self._lp(l, "self_attn.in_proj_weight")], g[self._lp(l, "self_attn.in_proj_bias")]
+        # --- FFN and out_proj on the B gathered rows
+        ops.chain_bwd(ws["dxq"], dout=ws["dxq"], dx_bf16=ws["dy_q"], drop2_p=dp, drop2_site=_site(l, 3), seed=seed,
+                      seed_dev=sdev, dx_colsum=g[self._lp(l, "linear2.bias")])
+        gemm(ws["dy_q"], ws["fq"], a_mn=True, b_mn=True, out_f32=g[self._lp(l, "linear2.weight")], accumulate=True)
+        gemm(ws["dy_q"], w[self._lp(l, "linear2.weight")], b_mn=True, gate=ws["fq"], gate_scale=ffn_scale,
+             out_bf16=ws["dpre_q"])
+        ops.colsum_bf16(ws["dpre_q"], g[self._lp(l, "linear1.bias")])
+        gemm(ws["dpre_q"], ws["h2q"], a_mn=True, b_mn=True, out_f32=g[self._lp(l, "linear1.weight")], accumulate=True)
+        gemm(ws["dpre_q"], w[self._lp(l, "linear1.weight")], b_mn=True, out_f32=ws["dh_q"])
+        ops.chain_bwd(ws["xmid_q"], ln=(p[self._lp(l, "norm2.weight")], p[self._lp(l, "norm2.bias")]), dout=ws["dh_q"],
+                      resid=ws["dxq"], dx_f32=ws["dxmid_q"], dx_bf16=ws["dy_q"], drop2_p=dp, drop2_site=_site(l, 1),
+                      seed=seed, seed_dev=sdev, dgamma=g[self._lp(l, "norm2.weight")],
+                      dbeta=g[self._lp(l, "norm2.bias")], dx_colsum=g[self._lp(l, "self_attn.out_proj.bias")])
+        gemm(ws["dy_q"], ws["ctxq"], a_mn=True, b_mn=True, out_f32=g[self._lp(l, "self_attn.out_proj.weight")],
+             accumulate=True)
+        gemm(ws["dy_q"], w[self._lp(l, "self_attn.out_proj.weight")], b_mn=True, out_bf16=ws["dctx_q"])
+        # --- single-query attention backward: dq (B rows), dK/dV for every position
+        ops.attn_lastq_bwd(ws["qq"], ws[f"qkv_{l}"], ws["last_idx"], ws["ctxq"], ws["dctx_q"], ws["lseq"], ws["dq_q"],
+                           ws["dqkv"], B, L, cfg.num_heads, drop_p=dp, seed=seed, seed_dev=sdev, site=_site(l, 0))
+        ops.colsum_bf16(ws["dq_q"], gb[:D])
+        gemm(ws["dq_q"], ws["hq"], a_mn=True, b_mn=True, out_f32=gW[:D], accumulate=True)
+        gemm(ws["dq_q"], Wqkv[:D], b_mn=True, out_f32=ws["dhq"])
+        dkv = ws["dqkv"][:, D:]
+        ops.colsum_bf16(dkv, gb[D:])
+        gemm(dkv, ws[f"h1_{l}"], a_mn=True, b_mn=True, out_f32=gW[D:], accumulate=True)
+        gemm(dkv, Wqkv[D:], b_mn=True, out_f32=ws["dh"])
+        ops.scatter_rows_add(ws["dhq"], ws["last_idx"], B, L, ws["dh"], accumulate=True)
+        # --- residual gradient of the layer input: only the gathered rows carry one
+        dx.zero_()
+        ops.scatter_rows_add(ws["dxmid_q"], ws["last_idx"], B, L, dx, accumulate=False)
+        extra = {}
+        if l > 0:
+            extra = dict(dx_bf16=ws["dy_bf"], drop2_p=dp, drop2_site=_site(l - 1, 3),
+                         dx_colsum=g[self._lp(l - 1, "linear2.bias")])
+        ops.chain_bwd(x_in, ln=(p[self._lp(l, "norm1.weight")], p[self._lp(l, "norm1.bias")]), dout=ws["dh"],
+                      resid=dx, dx_f32=dx_other, seed=seed, seed_dev=sdev, dgamma=g[self._lp(l, "norm1.weight")],
+                      dbeta=g[self._lp(l, "norm1.bias")], **extra)
+        return dx_other, dx
 
     def item_forward(self, ws, audio, visual, text, tabular, training: bool) -> torch.Tensor:
         """Late-fusion item tower on precomputed modality embeddings -> normalised item embedding."""
@@ -448,17 +548,25 @@ class TwoTowerEngine:
         gemm(ws["dz1_bf"], ws["cat"], a_mn=True, b_mn=True, out_f32=g[ut + "fusion_layer.0.weight"], accumulate=True)
         gemm(ws["dz1_bf"], w[ut + "fusion_layer.0.weight"], b_mn=True, out_f32=ws["dcat"])
         dx, dx_other = ws["dx_a"], ws["dx_b"]
-        dx.zero_()
-        ops.gather_cat_bwd(ws["dcat"], ws["last_idx"], batch["user_gender"], batch["user_country"], B, L, dx, None,
-                           g[ut + "gender_embedding.weight"], g[ut + "country_embedding.weight"])
-        # dy = dropout-mask(dx) as bf16 for the top layer's linear2, with its column sums (bias grad)
         top = cfg.num_layers - 1
-        ops.chain_bwd(dx, dout=dx, dx_bf16=ws["dy_bf"], drop2_p=dp, drop2_site=_site(top, 3), seed=seed,
-                      seed_dev=sdev, dx_colsum=g[self._lp(top, "linear2.bias")])
+        if self.prune_last_layer:
+            # d(loss)/d(xout_q): one row per sequence; the pruned last layer takes it from there
+            ops.gather_cat_bwd(ws["dcat"], ws["zero_idx"], batch["user_gender"], batch["user_country"], B, 1, ws["dxq"],
+                               None, g[ut + "gender_embedding.weight"], g[ut + "country_embedding.weight"])
+        else:
+            dx.zero_()
+            ops.gather_cat_bwd(ws["dcat"], ws["last_idx"], batch["user_gender"], batch["user_country"], B, L, dx, None,
+                               g[ut + "gender_embedding.weight"], g[ut + "country_embedding.weight"])
+            # dy = dropout-mask(dx) as bf16 for the top layer's linear2, with its column sums (bias grad)
+            ops.chain_bwd(dx, dout=dx, dx_bf16=ws["dy_bf"], drop2_p=dp, drop2_site=_site(top, 3), seed=seed,
+                          seed_dev=sdev, dx_colsum=g[self._lp(top, "linear2.bias")])
 
         # ---- encoder layers, last to first
         for l in range(cfg.num_layers - 1, -1, -1):
             x_in = ws[f"xout_{l - 1}"] if l > 0 else ws["x_in0"]
+            if self.prune_last_layer and l == top:
+                dx, dx_other = self._last_layer_backward(ws, l, x_in, B, L, dp, seed, sdev, dx, dx_other)
+                continue
             ffn_scale = 1.0 / (1.0 - dp) if dp > 0 else 1.0
             # linear2: dW2 = dy^T f ; dpre = (dy W2) gated by f (ReLU and FFN dropout in one test)
             gemm(ws["dy_bf"], ws[f"f_{l}"], a_mn=True, b_mn=True, out_f32=g[self._lp(l, "linear2.weight")],

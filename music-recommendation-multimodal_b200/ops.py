@@ -266,3 +266,34 @@ def infonce_loss(lse_a, pos_a, lse_b, pos_b, coef, loss) -> None:
     _require_cuda(lse_a, pos_a, lse_b, pos_b, loss)
     check(lib().tt_infonce_loss(lse_a.data_ptr(), pos_a.data_ptr(), lse_b.data_ptr(), pos_b.data_ptr(),
                                 lse_a.numel(), coef, loss.data_ptr(), _stream()), "tt_infonce_loss")
+
+
+# --------------------------------------------------------------------------------------
+# last-layer specialisation (one query row per sequence)
+# --------------------------------------------------------------------------------------
+def gather_rows(last_idx, B, L, x_f32=None, out_f32=None, x_bf16=None, out_bf16=None) -> None:
+    _require_cuda(last_idx, x_f32, out_f32, x_bf16, out_bf16)
+    W = (x_f32 if x_f32 is not None else x_bf16).shape[1]
+    check(lib().tt_gather_rows(_ptr(x_f32), _ptr(x_bf16), last_idx.data_ptr(), B, L, W, _ptr(out_f32), _ptr(out_bf16),
+                               _stream()), "tt_gather_rows")
+
+
+def scatter_rows_add(rows, last_idx, B, L, x, accumulate: bool) -> None:
+    _require_cuda(rows, last_idx, x)
+    assert rows.dtype == torch.float32 and x.dtype == torch.float32 and rows.is_contiguous() and x.is_contiguous()
+    check(lib().tt_scatter_rows_add(rows.data_ptr(), last_idx.data_ptr(), B, L, rows.shape[1], x.data_ptr(),
+                                    int(accumulate), _stream()), "tt_scatter_rows_add")
+
+
+def attn_lastq_fwd(q, qkv, last_idx, ctx, lse, B, L, H, drop_p=0.0, seed=0, seed_dev=None, site=0) -> None:
+    _require_cuda(q, qkv, last_idx, ctx, lse)
+    assert q.is_contiguous() and qkv.is_contiguous() and ctx.is_contiguous()
+    check(lib().tt_attn_lastq_fwd(q.data_ptr(), qkv.data_ptr(), last_idx.data_ptr(), ctx.data_ptr(), _ptr(lse), B, L, H,
+                                  drop_p, seed, _ptr(seed_dev), site, _stream()), "tt_attn_lastq_fwd")
+
+
+def attn_lastq_bwd(q, qkv, last_idx, ctx, dctx, lse, dq, dqkv, B, L, H, drop_p=0.0, seed=0, seed_dev=None, site=0) -> None:
+    _require_cuda(q, qkv, last_idx, ctx, dctx, lse, dq, dqkv)
+    check(lib().tt_attn_lastq_bwd(q.data_ptr(), qkv.data_ptr(), last_idx.data_ptr(), ctx.data_ptr(), dctx.data_ptr(),
+                                  lse.data_ptr(), dq.data_ptr(), dqkv.data_ptr(), B, L, H, drop_p, seed, _ptr(seed_dev),
+                                  site, _stream()), "tt_attn_lastq_bwd")

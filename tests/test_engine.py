@@ -217,3 +217,64 @@ def test_gathered_negatives_two_virtual_ranks_match_global_oracle():
         if err > 0.15 * ref.norm().item() + 5e-5 * ref.numel() ** 0.5:
             bad.append((k, err, ref.norm().item()))
     assert not bad, bad[:5]
+
+
+def test_pruned_last_layer_equals_full_computation():
+    """The single-row last layer is exact: same loss / embeddings / gradients as running
+    the last layer on every position (differences are bf16 rounding of different but equivalent paths)."""
+    gold, cfg, sd, batch, eng, dbatch = _setup("train_l200.pt")
+    from mrm_b200.engine import TwoTowerEngine
+    full = TwoTowerEngine(cfg)
+    full.load_state_dict(sd)
+    full.prune_last_layer = False
+    assert eng.prune_last_layer
+    out = {}
+    for name, e in (("pruned", eng), ("full", full)):
+        loss, logits, u, i = e.forward(dbatch, training=True)
+        e.backward()
+        torch.cuda.synchronize()
+        out[name] = (loss.item(), u.clone(), {k: v.clone() for k, v in e.g.items()})
+    assert abs(out["pruned"][0] - out["full"][0]) <= 5e-3
+    assert (out["pruned"][1] - out["full"][1]).abs().max().item() <= 3e-3
+    for k, gp in out["pruned"][2].items():
+        gf = out["full"][2][k]
+        err = (gp - gf).norm().item()
+        assert err <= 5e-2 * gf.norm().item() + 5e-5 * gf.numel() ** 0.5, (k, err, gf.norm().item())
+    # and the full path still matches the reference golden on its own
+    g = gold["f64"]
+    assert abs(out["full"][0] - g["loss"].item()) <= 5e-3
+
+
+def test_lastq_attention_matches_torch():
+    from mrm_b200 import ops
+    B, L, H = 5, 77, 4
+    gen = torch.Generator().manual_seed(9)
+    qkv = torch.randn(B * L, 3 * H * 64, generator=gen).cuda().bfloat16()
+    last = torch.tensor([0, 76, 30, 5, 63], dtype=torch.int32).cuda()
+    q = torch.stack([qkv.view(B, L, -1)[b, last[b], :H * 64] for b in range(B)]).contiguous()
+    ctx = torch.empty(B, H * 64, device="cuda", dtype=torch.bfloat16)
+    lse = torch.empty(B, H, device="cuda")
+    ops.attn_lastq_fwd(q, qkv, last, ctx, lse, B, L, H)
+    dctx = torch.randn(B, H * 64, generator=gen).cuda().bfloat16()
+    dq = torch.empty_like(q)
+    dqkv = torch.full_like(qkv, float("nan"))
+    ops.attn_lastq_bwd(q, qkv, last, ctx, dctx, lse, dq, dqkv, B, L, H)
+    torch.cuda.synchronize()
+    x = qkv.float().view(B, L, 3, H, 64)
+    for b in range(B):
+        n = int(last[b]) + 1
+        qq = q[b].float().view(H, 64).clone().requires_grad_(True)
+        k = x[b, :n, 1].clone().requires_grad_(True)          # (n, H, 64)
+        v = x[b, :n, 2].clone().requires_grad_(True)
+        s = torch.einsum("hd,nhd->hn", qq, k) / 8.0
+        o = torch.einsum("hn,nhd->hd", torch.softmax(s, dim=-1), v)
+        assert (ctx[b].float().view(H, 64) - o).abs().max().item() < 2e-2
+        assert (lse[b] - torch.logsumexp(s, dim=-1)).abs().max().item() < 2e-3
+        o.backward(dctx[b].float().view(H, 64))
+        assert (dq[b].float().view(H, 64) - qq.grad).abs().max().item() < 3e-2 * max(1.0, qq.grad.abs().max().item())
+        dk = dqkv.view(B, L, 3, H, 64)[b, :, 1].float()
+        dv = dqkv.view(B, L, 3, H, 64)[b, :, 2].float()
+        assert (dk[:n] - k.grad).abs().max().item() < 3e-2 * max(1.0, k.grad.abs().max().item())
+        assert (dv[:n] - v.grad).abs().max().item() < 3e-2 * max(1.0, v.grad.abs().max().item())
+        assert dk[n:].abs().max().item() == 0.0 if n < L else True
+        assert dv[n:].abs().max().item() == 0.0 if n < L else True
