@@ -67,9 +67,12 @@ struct LastQParams {
   __nv_bfloat16* dqkv;        // [B*L, 3*H*64]: K and V thirds written for every position (zeros beyond len)
 };
 
-__device__ __forceinline__ void load_row64(const __nv_bfloat16* p, float (&v)[64]) {
+// Lane layout inside a warp: 8 key slots x 4 dim quarters. Lane (ks, dq) = (lane >> 2, lane & 3)
+// handles key j = 8*it + ks and dims [16*dq, 16*dq + 16) (two 16-byte loads), so a warp instruction
+// reads 8 keys x 128 contiguous bytes; the 4 partial dot products meet with two shuffles.
+__device__ __forceinline__ void load16(const __nv_bfloat16* p, float (&v)[16]) {
 #pragma unroll
-  for (int u = 0; u < 8; ++u) {
+  for (int u = 0; u < 2; ++u) {
     const uint4 x = __ldg(reinterpret_cast<const uint4*>(p) + u);
     const uint32_t w[4] = {x.x, x.y, x.z, x.w};
 #pragma unroll
@@ -80,23 +83,20 @@ __device__ __forceinline__ void load_row64(const __nv_bfloat16* p, float (&v)[64
     }
   }
 }
-__device__ __forceinline__ float dot_row64(const __nv_bfloat16* p, const float (&q)[64]) {
+__device__ __forceinline__ float dot16(const float (&a)[16], const float (&b)[16]) {
   float acc = 0.f;
 #pragma unroll
-  for (int u = 0; u < 8; ++u) {
-    const uint4 x = __ldg(reinterpret_cast<const uint4*>(p) + u);
-    const uint32_t w[4] = {x.x, x.y, x.z, x.w};
-#pragma unroll
-    for (int h = 0; h < 4; ++h) {
-      const float2 f = unpack_bf16(w[h]);
-      acc += f.x * q[u * 8 + h * 2] + f.y * q[u * 8 + h * 2 + 1];
-    }
-  }
+  for (int i = 0; i < 16; ++i) acc += a[i] * b[i];
   return acc;
 }
-__device__ __forceinline__ void store_scaled_row64(__nv_bfloat16* p, const float (&v)[64], float s) {
+__device__ __forceinline__ float quad_sum(float v) {
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  v += __shfl_xor_sync(0xffffffffu, v, 2);
+  return v;
+}
+__device__ __forceinline__ void store16_scaled(__nv_bfloat16* p, const float (&v)[16], float s) {
 #pragma unroll
-  for (int u = 0; u < 8; ++u) {
+  for (int u = 0; u < 2; ++u) {
     uint4 x;
     x.x = pack_bf16(v[u * 8 + 0] * s, v[u * 8 + 1] * s);
     x.y = pack_bf16(v[u * 8 + 2] * s, v[u * 8 + 3] * s);
@@ -110,24 +110,33 @@ __device__ __forceinline__ void store_scaled_row64(__nv_bfloat16* p, const float
 __global__ void __launch_bounds__(128) attn_lastq_fwd_kernel(const LastQParams p) {
   __shared__ float s_p[4][kMaxL];
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ks = lane >> 2, dq = lane & 3;
   const int bh = blockIdx.x * 4 + wib;
   if (bh >= p.B * p.H) return;
   const int b = bh / p.H, h = bh % p.H;
   const int D = p.H * kDh;
   const int last = p.last_idx[b];
   const int len = last + 1;
-  float q[64];
-  load_row64(p.q + static_cast<size_t>(b) * D + h * kDh, q);
+  float q[16];
+  load16(p.q + static_cast<size_t>(b) * D + h * kDh + dq * 16, q);
   const __nv_bfloat16* kbase = p.qkv + static_cast<size_t>(b) * p.L * 3 * D + D + h * kDh;
   const __nv_bfloat16* vbase = kbase + D;
   const float c1 = p.scale * kLog2e;
   float m = -INFINITY;
-  for (int j = lane; j < len; j += 32) {
-    const float s = dot_row64(kbase + static_cast<size_t>(j) * 3 * D, q) * c1;
-    s_p[wib][j] = s;
+  for (int j0 = 0; j0 < len; j0 += 8) {
+    const int j = j0 + ks;
+    float s = -INFINITY;
+    if (j < len) {
+      float k[16];
+      load16(kbase + static_cast<size_t>(j) * 3 * D + dq * 16, k);
+      s = dot16(k, q);
+    }
+    s = quad_sum(s) * c1;          // (-inf stays -inf for keys beyond len)
+    if (dq == 0 && j < len) s_p[wib][j] = s;
     m = fmaxf(m, s);
   }
   m = warp_max(m);
+  __syncwarp();
   const uint64_t seed = p.seed + ((p.drop_thresh && p.seed_dev) ? *p.seed_dev : 0ull);
   const uint32_t dkey = drop_key(seed, p.site);
   const uint64_t didx0 = (static_cast<uint64_t>(bh) * p.L + last) * p.L;
@@ -140,32 +149,44 @@ __global__ void __launch_bounds__(128) attn_lastq_fwd_kernel(const LastQParams p
   }
   l = warp_sum(l);
   __syncwarp();
-  float a0 = 0.f, a1 = 0.f;
-  for (int j = 0; j < len; ++j) {
+  // ctx[d] = sum_j p_j V[j][d]: lane owns dims (2*lane, 2*lane+1); 4 independent accumulator pairs
+  float a[4][2] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};
+  int j = 0;
+  for (; j + 4 <= len; j += 4) {
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const float pj = s_p[wib][j + t];
+      const float2 v = unpack_bf16(__ldg(reinterpret_cast<const uint32_t*>(vbase + static_cast<size_t>(j + t) * 3 * D) + lane));
+      a[t][0] += pj * v.x;
+      a[t][1] += pj * v.y;
+    }
+  }
+  for (; j < len; ++j) {
     const float pj = s_p[wib][j];
     const float2 v = unpack_bf16(__ldg(reinterpret_cast<const uint32_t*>(vbase + static_cast<size_t>(j) * 3 * D) + lane));
-    a0 += pj * v.x;
-    a1 += pj * v.y;
+    a[0][0] += pj * v.x;
+    a[0][1] += pj * v.y;
   }
   const float inv = 1.f / l;
-  reinterpret_cast<uint32_t*>(p.ctx + static_cast<size_t>(b) * D + h * kDh)[lane] = pack_bf16(a0 * inv, a1 * inv);
+  const float o0 = (a[0][0] + a[1][0]) + (a[2][0] + a[3][0]), o1 = (a[0][1] + a[1][1]) + (a[2][1] + a[3][1]);
+  reinterpret_cast<uint32_t*>(p.ctx + static_cast<size_t>(b) * D + h * kDh)[lane] = pack_bf16(o0 * inv, o1 * inv);
   if (lane == 0 && p.lse) p.lse[bh] = (m + log2f(l)) / kLog2e;   // natural-log sum-exp of the scaled scores
 }
 
 __global__ void __launch_bounds__(128) attn_lastq_bwd_kernel(const LastQParams p) {
   __shared__ float s_ds[4][kMaxL];
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ks = lane >> 2, dq = lane & 3;
   const int bh = blockIdx.x * 4 + wib;
   if (bh >= p.B * p.H) return;
   const int b = bh / p.H, h = bh % p.H;
   const int D = p.H * kDh;
   const int last = p.last_idx[b];
   const int len = last + 1;
-  float q[64], g[64];
-  load_row64(p.q + static_cast<size_t>(b) * D + h * kDh, q);
-  load_row64(p.dctx + static_cast<size_t>(b) * D + h * kDh, g);
-  // delta = dctx . ctx
-  float delta;
+  float q[16], g[16];
+  load16(p.q + static_cast<size_t>(b) * D + h * kDh + dq * 16, q);
+  load16(p.dctx + static_cast<size_t>(b) * D + h * kDh + dq * 16, g);
+  float delta;   // dctx . ctx
   {
     const float2 o = unpack_bf16(reinterpret_cast<const uint32_t*>(p.ctx + static_cast<size_t>(b) * D + h * kDh)[lane]);
     const float2 d = unpack_bf16(reinterpret_cast<const uint32_t*>(p.dctx + static_cast<size_t>(b) * D + h * kDh)[lane]);
@@ -181,39 +202,62 @@ __global__ void __launch_bounds__(128) attn_lastq_bwd_kernel(const LastQParams p
   const uint64_t seed = p.seed + ((p.drop_thresh && p.seed_dev) ? *p.seed_dev : 0ull);
   const uint32_t dkey = drop_key(seed, p.site);
   const uint64_t didx0 = (static_cast<uint64_t>(bh) * p.L + last) * p.L;
-  for (int j = lane; j < p.L; j += 32) {
-    __nv_bfloat16* dk = dkbase + static_cast<size_t>(j) * 3 * D;
-    __nv_bfloat16* dv = dvbase + static_cast<size_t>(j) * 3 * D;
-    if (j < len) {
-      const float pr = exp2f(dot_row64(kbase + static_cast<size_t>(j) * 3 * D, q) * c1 - lse2);
-      float dp = dot_row64(vbase + static_cast<size_t>(j) * 3 * D, g);
-      float pd = pr;
+  for (int j0 = 0; j0 < p.L; j0 += 8) {
+    const int j = j0 + ks;
+    const bool inrange = j < p.L;      // every lane stays in the loop: the quad shuffles use the full mask
+    __nv_bfloat16* dk = dkbase + static_cast<size_t>(j) * 3 * D + dq * 16;
+    __nv_bfloat16* dv = dvbase + static_cast<size_t>(j) * 3 * D + dq * 16;
+    float sdot = 0.f, vdot = 0.f;
+    const bool live = j < len;
+    if (live) {
+      float k[16], v[16];
+      load16(kbase + static_cast<size_t>(j) * 3 * D + dq * 16, k);
+      load16(vbase + static_cast<size_t>(j) * 3 * D + dq * 16, v);
+      sdot = dot16(k, q);
+      vdot = dot16(v, g);
+    }
+    sdot = quad_sum(sdot);
+    vdot = quad_sum(vdot);
+    if (live) {
+      const float pr = exp2f(sdot * c1 - lse2);
+      float dp = vdot, pd = pr;
       if (p.drop_thresh) {
         const bool keep = drop_keep_k(dkey, didx0 + j, p.drop_thresh);
         pd = keep ? pr * p.drop_scale : 0.f;
         dp = keep ? dp * p.drop_scale : 0.f;
       }
       const float ds = pr * (dp - delta) * p.scale;
-      s_ds[wib][j] = ds;
-      store_scaled_row64(dk, q, ds);    // dK_j = dS_j * q
-      store_scaled_row64(dv, g, pd);    // dV_j = Pd_j * dO
-    } else {
+      if (dq == 0) s_ds[wib][j] = ds;
+      store16_scaled(dk, q, ds);    // dK_j = dS_j * q
+      store16_scaled(dv, g, pd);    // dV_j = Pd_j * dO
+    } else if (inrange) {
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
+      for (int u = 0; u < 2; ++u) {
         reinterpret_cast<uint4*>(dk)[u] = make_uint4(0, 0, 0, 0);
         reinterpret_cast<uint4*>(dv)[u] = make_uint4(0, 0, 0, 0);
       }
     }
   }
   __syncwarp();
-  float a0 = 0.f, a1 = 0.f;
-  for (int j = 0; j < len; ++j) {
+  float a[4][2] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};
+  int j = 0;
+  for (; j + 4 <= len; j += 4) {
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const float ds = s_ds[wib][j + t];
+      const float2 k = unpack_bf16(__ldg(reinterpret_cast<const uint32_t*>(kbase + static_cast<size_t>(j + t) * 3 * D) + lane));
+      a[t][0] += ds * k.x;
+      a[t][1] += ds * k.y;
+    }
+  }
+  for (; j < len; ++j) {
     const float ds = s_ds[wib][j];
     const float2 k = unpack_bf16(__ldg(reinterpret_cast<const uint32_t*>(kbase + static_cast<size_t>(j) * 3 * D) + lane));
-    a0 += ds * k.x;
-    a1 += ds * k.y;
+    a[0][0] += ds * k.x;
+    a[0][1] += ds * k.y;
   }
-  reinterpret_cast<uint32_t*>(p.dq + static_cast<size_t>(b) * D + h * kDh)[lane] = pack_bf16(a0, a1);
+  const float o0 = (a[0][0] + a[1][0]) + (a[2][0] + a[3][0]), o1 = (a[0][1] + a[1][1]) + (a[2][1] + a[3][1]);
+  reinterpret_cast<uint32_t*>(p.dq + static_cast<size_t>(b) * D + h * kDh)[lane] = pack_bf16(o0, o1);
 }
 
 static uint32_t drop_threshold(float p) {

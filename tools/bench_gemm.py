@@ -22,12 +22,18 @@ g32 = torch.zeros(FF, FF, device=dev)
 
 
 def t(fn, iters=10):
+    """CUDA-graph replay of `iters` back-to-back launches: no host launch overhead in the number."""
     for _ in range(3):
         fn()
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(iters):
+            fn()
+    g.replay()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(iters):
-        fn()
+    g.replay()
     e1.record()
     torch.cuda.synchronize()
     return e0.elapsed_time(e1) * 1e3 / iters
@@ -39,6 +45,10 @@ cases = [
     ("oproj fwd f32 bias+res       ", T, 256, 256, lambda: ops.gemm(x[:, :256], w[:256, :256], bias=bias, residual=res, out_f32=o32)),
     ("oproj fwd f32 bias+res+drop  ", T, 256, 256, lambda: ops.gemm(x[:, :256], w[:256, :256], bias=bias, residual=res, drop_p=0.1, drop_site=3, out_f32=o32)),
     ("oproj fwd f32 plain          ", T, 256, 256, lambda: ops.gemm(x[:, :256], w[:256, :256], out_f32=o32)),
+    ("ffn1  fwd bf16 plain         ", T, 1024, 256, lambda: ops.gemm(x[:, :256], w[:, :256], out_bf16=o16)),
+    ("tiny  256x256x256 f32 bias   ", 256, 256, 256, lambda: ops.gemm(x[:256, :256], w[:256, :256], bias=bias, out_f32=o32[:256])),
+    ("tiny  256x1024x256 bf16      ", 256, 1024, 256, lambda: ops.gemm(x[:256, :256], w[:, :256], bias=bias, relu=True, out_bf16=o16[:256])),
+    ("tiny  256x256x1024 f32       ", 256, 256, 1024, lambda: ops.gemm(x[:256], w[:256], bias=bias, out_f32=o32[:256])),
     ("ffn1  fwd bf16 bias+relu     ", T, 1024, 256, lambda: ops.gemm(x[:, :256], w[:, :256], bias=bias, relu=True, out_bf16=o16)),
     ("ffn1  fwd bf16 +drop         ", T, 1024, 256, lambda: ops.gemm(x[:, :256], w[:, :256], bias=bias, relu=True, drop_p=0.1, drop_site=2, out_bf16=o16)),
     ("ffn2  fwd f32 bias+res       ", T, 256, 1024, lambda: ops.gemm(x, w[:256], bias=bias, residual=res, out_f32=o32)),
