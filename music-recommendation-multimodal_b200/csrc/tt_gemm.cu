@@ -85,6 +85,22 @@ __device__ __forceinline__ void epi_prefetch(const GemmParams& p, uint8_t* in, i
   cp_async_commit();
 }
 
+// L2 prefetch of the residual / gate lines of one (tile, warp): lane = row, one 128-byte (fp32) or
+// 64-byte (bf16) segment per 32-column chunk. Issued a whole tile ahead, so the later cp.async only
+// pays L2 latency.
+__device__ __forceinline__ void epi_prefetch_l2(const GemmParams& p, int lane, int row0, int colbase, int half,
+                                                int nchunks) {
+  const int gr = row0 + lane;
+  if (gr >= p.M) return;
+  for (int c = half; c < nchunks; c += 2) {
+    const int gc = colbase + c * 32;
+    if (gc >= p.N) break;
+    const void* ptr = p.residual ? static_cast<const void*>(p.residual + static_cast<size_t>(gr) * p.ld_res + gc)
+                                 : static_cast<const void*>(p.gate + static_cast<size_t>(gr) * p.ld_gate + gc);
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
+  }
+}
+
 // One 32-column chunk of one accumulator row per lane. `next_col0` >= 0 asks for the prefetch of
 // the warp's next chunk once the current "in" tile has been consumed.
 __device__ __forceinline__ void gemm_epilogue_chunk(const GemmParams& p, const uint32_t (&r)[32], uint8_t* out,
@@ -309,11 +325,20 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int nchunks = block_n / 32;
     int acc = 0;
     uint32_t acc_phase = 0;
+    const bool has_in = p.residual || p.gate;
+    if (has_in && static_cast<int>(blockIdx.x) < num_tiles) {
+      const int mn = static_cast<int>(blockIdx.x) / p.k_splits;
+      epi_prefetch_l2(p, lane, (mn / tiles_n) * kBlockM + q * 32, (mn % tiles_n) * block_n, half, nchunks);
+    }
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
       const int mn = t / p.k_splits;
       const int m_blk = mn / tiles_n, n_blk = mn % tiles_n;
       const int row0 = m_blk * kBlockM + q * 32;
       const int colbase = n_blk * block_n;
+      if (has_in && t + static_cast<int>(gridDim.x) < num_tiles) {   // next tile's lines -> L2 while this one computes
+        const int mn2 = (t + static_cast<int>(gridDim.x)) / p.k_splits;
+        epi_prefetch_l2(p, lane, (mn2 / tiles_n) * kBlockM + q * 32, (mn2 % tiles_n) * block_n, half, nchunks);
+      }
       // Everything that does not depend on the accumulator is issued before waiting for it:
       // the bias slice of this warp's chunks and the first residual / gate block.
       if (p.bias) {
