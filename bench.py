@@ -275,12 +275,17 @@ def run_ours(args, rank, world, local_rank):
                                    "seq_len 200 (all positions valid), 100k-item ID table, dropout 0.1",
                        "global_batch": world * B, "seq_len": L, "vocab_size": V,
                        "parallelism": f"dp{world}" if world > 1 else "single",
-                       "negatives": "per-rank in-batch (reference DDP semantics)",
+                       "negatives": ("all-gathered across ranks (NCCL all-gather of embeddings + row log-sum-exps)"
+                                     if world > 1 else "in-batch"),
+                       "last_layer": "exact single-row form (only out[b, len-1] of the last encoder layer is ever "
+                                     "read: K/V for all positions, query/out_proj/FFN for one row per sequence)",
                        "l2": "per-step working set (~1.2 GB activations + 410 MB optimizer state) exceeds the 126 MB L2"},
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4},
             "gpu_launches": launches,
             "kernels_per_step": runner.kernels_per_step,
             "step_tflops": step_flops / (ms_step * 1e-3) / 1e12,
+            "step_tflops_note": "reference-algorithm FLOPs of the step (SURVEY.md §8d formula, every layer on every "
+                                "position) per second; the executed GEMM FLOPs are roofline.flops_per_step",
             "roofline": roof,
             "clocks": sampler.summary(),
             "retrieval": retr,
