@@ -93,6 +93,7 @@ class TwoTowerEngine:
             self.layout[name] = (off, shape)
             off += (n + _ALIGN - 1) // _ALIGN * _ALIGN
         off += _ALIGN  # tail padding: ragged MN-major chunks may read up to 63 elements past a tensor
+        off = (off + 2047) // 2048 * 2048   # divisible into 1/2/4/8 equal, 16-byte aligned optimizer shards
         self.numel = off
         dev = self.device
         self.flat = torch.zeros(off, device=dev)
@@ -617,7 +618,7 @@ class TwoTowerEngine:
         """torch.optim.AdamW semantics over the whole flat buffer (src/train.py:302, 64-65), dense
         on the ID table like the reference; refreshes the bf16 shadow of the dense region and
         zeroes the gradient buffer in the same pass; advances the step / dropout-seed counters."""
-        if self.exp_avg is None:
+        if self.exp_avg is None or self.exp_avg.numel() != self.numel:
             self.exp_avg = torch.zeros_like(self.flat)
             self.exp_avg_sq = torch.zeros_like(self.flat)
         ops.step_counters_advance(self.step_dev, self.seed_dev)
@@ -625,6 +626,24 @@ class TwoTowerEngine:
                        eps, weight_decay, shadow=self.shadow, shadow_begin=self.dense_begin, shadow_end=self.numel,
                        zero_grad=zero_grad)
         self.shadow_valid = True
+
+    def adamw_step_sharded(self, rank: int, world: int, grad_shard: torch.Tensor, lr: float = 1e-4,
+                           betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.01) -> torch.Tensor:
+        """Optimizer-state sharding for data parallelism: this rank owns elements
+        [rank*n/world, (rank+1)*n/world) of the flat buffer, holds AdamW moments for them only and
+        updates them from the reduce-scattered, averaged gradient `grad_shard`. The caller all-gathers
+        the parameter shards afterwards and refreshes the bf16 shadow. Returns the parameter shard view."""
+        n = self.numel // world
+        lo = rank * n
+        if self.exp_avg is None or self.exp_avg.numel() != n:
+            self.exp_avg = torch.zeros(n, device=self.device)
+            self.exp_avg_sq = torch.zeros(n, device=self.device)
+        ops.step_counters_advance(self.step_dev, self.seed_dev)
+        p_shard = self.flat[lo:lo + n]
+        ops.adamw_step(p_shard, grad_shard, self.exp_avg, self.exp_avg_sq, self.step_dev, lr, betas[0], betas[1],
+                       eps, weight_decay, shadow=None, zero_grad=False)
+        self.shadow_valid = False
+        return p_shard
 
     def train_step(self, batch: Dict[str, torch.Tensor], lr: float = 1e-4) -> torch.Tensor:
         """One step of the train_one_epoch body (src/train.py:54-65): forward, backward, AdamW."""

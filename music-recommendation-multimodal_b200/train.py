@@ -55,11 +55,24 @@ class TrainStepRunner:
 
     def __init__(self, engine: TwoTowerEngine, B: int, L: int, world_size: int = 1, lr: float = 1e-4,
                  use_graph: bool = True, with_user_idx: bool = True, negatives: str = "gathered",
-                 rank: Optional[int] = None, group=None):
+                 rank: Optional[int] = None, group=None, shard_optimizer: bool = True):
         self.eng, self.B, self.L, self.world, self.lr, self.use_graph = engine, B, L, world_size, lr, use_graph
         self.group = group
         self.rank = (dist.get_rank(group) if world_size > 1 else 0) if rank is None else rank
         self.gathered = world_size > 1 and negatives == "gathered"
+        # ZeRO-1 style: reduce-scatter the gradient, AdamW on this rank's 1/world shard (moments are
+        # held for the shard only), all-gather the updated parameters. Same bytes on NVLink as one
+        # all-reduce, 1/world of the optimizer's HBM traffic.
+        self.shard_opt = world_size > 1 and shard_optimizer
+        if self.shard_opt:
+            self._grad_shard = torch.empty(engine.numel // world_size, device=engine.device)
+        # packed exchange buffers: one all-gather for (user emb | item emb | user id), one for the two LSE vectors
+        if self.gathered:
+            D = engine.cfg.embedding_dim
+            self._pack_emb = torch.empty(B, 2 * D * 2 + 8, device=engine.device, dtype=torch.uint8)
+            self._pack_emb_all = torch.empty(world_size * B, 2 * D * 2 + 8, device=engine.device, dtype=torch.uint8)
+            self._pack_lse = torch.empty(B, 2, device=engine.device)
+            self._pack_lse_all = torch.empty(world_size * B, 2, device=engine.device)
         dev, m = engine.device, engine.cfg.modality_dim
         i64 = dict(device=dev, dtype=torch.long)
         self.static: Dict[str, torch.Tensor] = {
@@ -94,36 +107,75 @@ class TrainStepRunner:
         self.eng.backward()
 
     def _phase_opt(self):
-        self.eng.adamw_step(lr=self.lr)
+        if self.shard_opt:
+            self.eng.adamw_step_sharded(self.rank, self.world, self._grad_shard, lr=self.lr)
+        else:
+            self.eng.adamw_step(lr=self.lr)
+
+    def _phase_post_opt(self):
+        """After the parameter all-gather: zero the local gradient buffer, refresh the bf16 operand shadow."""
+        self.eng.grad.zero_()
+        self.eng.refresh_shadow()
+
+    # -- packed all-gathers (byte views; every piece is copied by a small device-to-device copy) --
+    def _phase_pack_emb(self):
+        ws, D, B = self._ws, self.eng.cfg.embedding_dim, self.B
+        pk = self._pack_emb
+        pk[:, :2 * D].copy_(ws["un_bf"].view(torch.uint8).view(B, 2 * D))
+        pk[:, 2 * D:4 * D].copy_(ws["in_bf"].view(torch.uint8).view(B, 2 * D))
+        if "user_idx" in self.static:
+            pk[:, 4 * D:].copy_(self.static["user_idx"].view(torch.uint8).view(B, 8))
+
+    def _phase_unpack_emb(self):
+        ws, D, B, G = self._ws, self.eng.cfg.embedding_dim, self.B, self.world
+        g = self.eng.gathered_workspace(ws, G)
+        pk = self._pack_emb_all
+        g["U_all"].view(torch.uint8).view(G * B, 2 * D).copy_(pk[:, :2 * D])
+        g["I_all"].view(torch.uint8).view(G * B, 2 * D).copy_(pk[:, 2 * D:4 * D])
+        if "user_idx" in self.static:
+            g["uid_all"].view(torch.uint8).view(G * B, 8).copy_(pk[:, 4 * D:])
 
     def _comm_embeddings(self):
+        dist.all_gather_into_tensor(self._pack_emb_all, self._pack_emb, group=self.group)
+
+    def _phase_pack_lse(self):
         ws = self._ws
-        g = self.eng.gathered_workspace(ws, self.world)
-        dist.all_gather_into_tensor(g["U_all"], ws["un_bf"], group=self.group)
-        dist.all_gather_into_tensor(g["I_all"], ws["in_bf"], group=self.group)
-        if "user_idx" in self.static:
-            dist.all_gather_into_tensor(g["uid_all"], self.static["user_idx"], group=self.group)
+        self._pack_lse[:, 0].copy_(ws["lse_r"])
+        self._pack_lse[:, 1].copy_(ws["lse_c"])
+
+    def _phase_unpack_lse(self):
+        g = self.eng.gathered_workspace(self._ws, self.world)
+        g["lse_r_all"].copy_(self._pack_lse_all[:, 0])
+        g["lse_c_all"].copy_(self._pack_lse_all[:, 1])
 
     def _comm_lse(self):
-        ws = self._ws
-        g = self.eng.gathered_workspace(ws, self.world)
-        dist.all_gather_into_tensor(g["lse_r_all"], ws["lse_r"], group=self.group)
-        dist.all_gather_into_tensor(g["lse_c_all"], ws["lse_c"], group=self.group)
+        dist.all_gather_into_tensor(self._pack_lse_all, self._pack_lse, group=self.group)
 
     def _comm_grads(self):
-        dist.all_reduce(self.eng.grad, op=dist.ReduceOp.AVG, group=self.group)
+        if self.shard_opt:
+            dist.reduce_scatter_tensor(self._grad_shard, self.eng.grad, op=dist.ReduceOp.AVG, group=self.group)
+        else:
+            dist.all_reduce(self.eng.grad, op=dist.ReduceOp.AVG, group=self.group)
+
+    def _comm_params(self):
+        n = self.eng.numel // self.world
+        dist.all_gather_into_tensor(self.eng.flat, self.eng.flat[self.rank * n:(self.rank + 1) * n], group=self.group)
 
     def _sequence(self):
         """[(callable, is_communication)] of one step."""
         seq = [(self._phase_towers, False)]
         if self.gathered:
-            seq += [(self._comm_embeddings, True), (self._phase_loss_rows, False), (self._comm_lse, True)]
+            seq += [(self._phase_pack_emb, False), (self._comm_embeddings, True), (self._phase_unpack_emb, False),
+                    (self._phase_loss_rows, False), (self._phase_pack_lse, False), (self._comm_lse, True),
+                    (self._phase_unpack_lse, False)]
         else:
             seq += [(self._phase_loss_rows, False)]
         seq += [(self._phase_backward, False)]
         if self.world > 1:
             seq += [(self._comm_grads, True)]
         seq += [(self._phase_opt, False)]
+        if self.shard_opt:
+            seq += [(self._comm_params, True), (self._phase_post_opt, False)]
         return seq
 
     def _eager(self):
