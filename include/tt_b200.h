@@ -265,7 +265,8 @@ int tt_infonce_loss(const float* lse_a, const float* pos_a, const float* lse_b, 
  *                     :156 without materialising the (U, N) score matrix.
  *                     users_bf16 [U,256], items_bf16 [N,256]; item_base = global index of row 0
  *                     of this shard; mask_item0 excludes global item 0 (the padding id).
- *                     cand/cand_cnt/thr are scratch of plan->{cand,cnt,thr}_bytes.
+ *                     cand/cand_cnt/thr/smax are scratch of plan->{cand,cnt,thr,smax}_bytes (smax may be
+ *                     NULL: no sample pass).
  * tt_topk_finalize  : per user, K' best keys -> exact re-score (fp32 inputs, fp64 accumulate,
  *                     rounded once to fp32) -> canonical sort -> top K (global indices, -1 pad)
  *                     and flags[u] = 1 when the certificate "no non-candidate can reach the
@@ -279,14 +280,15 @@ int tt_infonce_loss(const float* lse_a, const float* pos_a, const float* lse_b, 
 typedef struct tt_topk_plan {
   int32_t U, N, kprime, cap;
   int32_t n_ut, n_ranges, tiles_per_range;
-  int32_t sample_stride, sample_rank, sample_keep; /* sample pass (0 = none): every sample_stride-th item
-                                                      tile is scored first; each user's sample_rank-th best
-                                                      sample score becomes the main pass's start threshold */
-  int64_t cand_bytes, cnt_bytes, thr_bytes;
+  int32_t sample_stride, sample_rank, sample_tiles; /* sample pass (0 = none): every sample_stride-th item tile
+                                                       is scored first, keeping the maximum of each 32-score chunk;
+                                                       each user's sample_rank-th largest chunk maximum becomes the
+                                                       main pass's start threshold (verified later, never trusted) */
+  int64_t cand_bytes, cnt_bytes, thr_bytes, smax_bytes;
 } tt_topk_plan;
 int tt_topk_plan_make(int U, int N, int kprime, tt_topk_plan* plan);
 int tt_score_topk(const void* users_bf16, const void* items_bf16, int item_base, const tt_topk_plan* plan,
-                  void* cand, int32_t* cand_cnt, void* thr, int mask_item0, void* stream);
+                  void* cand, int32_t* cand_cnt, void* thr, void* smax, int mask_item0, void* stream);
 int tt_topk_finalize(const tt_topk_plan* plan, const void* cand, const int32_t* cand_cnt, const void* thr,
                      const float* users_f32,
                      const float* items_f32, int item_base, int K, float eps, int32_t* out_idx, float* out_score,

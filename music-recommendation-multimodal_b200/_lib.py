@@ -124,8 +124,9 @@ class TopkPlan(ctypes.Structure):
 
     _fields_ = [("U", c_int32), ("N", c_int32), ("kprime", c_int32), ("cap", c_int32),
                 ("n_ut", c_int32), ("n_ranges", c_int32), ("tiles_per_range", c_int32),
-                ("sample_stride", c_int32), ("sample_rank", c_int32), ("sample_keep", c_int32),
-                ("cand_bytes", ctypes.c_int64), ("cnt_bytes", ctypes.c_int64), ("thr_bytes", ctypes.c_int64)]
+                ("sample_stride", c_int32), ("sample_rank", c_int32), ("sample_tiles", c_int32),
+                ("cand_bytes", ctypes.c_int64), ("cnt_bytes", ctypes.c_int64), ("thr_bytes", ctypes.c_int64),
+                ("smax_bytes", ctypes.c_int64)]
 
 
 _I64 = ctypes.c_int64
@@ -135,8 +136,8 @@ _SIGNATURES = {
     "tt_attn_lastq_fwd": [c_void_p] * 5 + [c_int32, c_int32, c_int32, c_float, c_uint64, c_void_p, c_uint32, c_void_p],
     "tt_attn_lastq_bwd": [c_void_p] * 8 + [c_int32, c_int32, c_int32, c_float, c_uint64, c_void_p, c_uint32, c_void_p],
     "tt_topk_plan_make": [c_int32, c_int32, c_int32, ctypes.POINTER(TopkPlan)],
-    "tt_score_topk": [c_void_p, c_void_p, c_int32, ctypes.POINTER(TopkPlan), c_void_p, c_void_p, c_void_p, c_int32,
-                      c_void_p],
+    "tt_score_topk": [c_void_p, c_void_p, c_int32, ctypes.POINTER(TopkPlan), c_void_p, c_void_p, c_void_p, c_void_p,
+                      c_int32, c_void_p],
     "tt_topk_finalize": [ctypes.POINTER(TopkPlan), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_float,
                          c_void_p, c_void_p, c_void_p, c_void_p],
     "tt_topk_merge": [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p],

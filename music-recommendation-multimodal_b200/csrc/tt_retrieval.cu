@@ -22,6 +22,7 @@
 // a certificate that no non-candidate can belong to the exact top K.
 #include "../../include/tt_b200.h"
 #include "tt_common.cuh"
+#include <math.h>
 
 namespace tt {
 
@@ -53,7 +54,7 @@ struct TopkParams {
   int U, N, item_base;
   int n_ut, n_ranges, tiles_per_range, total_tiles;
   int tile_stride;           // logical tile t of a range is physical tile t * tile_stride (sample pass: strided tiles)
-  int reset_thr;             // 1: ignore published thresholds at unit start (sample pass)
+  float* smax;               // non-null: SAMPLE pass — store each 32-score chunk's maximum, collect nothing
   int kprime;
   int u_pad;
   unsigned long long* cand;  // [n_ranges][u_pad][kCap]
@@ -99,6 +100,13 @@ __device__ int warp_prune(unsigned long long* buf, int n, int kprime, int lane, 
   return base;
 }
 
+__device__ __forceinline__ float chunk_max(const uint32_t (&r)[32]) {
+  float m = __uint_as_float(r[0]);
+#pragma unroll
+  for (int t = 1; t < 32; ++t) m = fmaxf(m, __uint_as_float(r[t]));
+  return m;
+}
+
 // Filter one 32-score chunk of this lane's user row against the row threshold. The common case
 // (no score of any lane beats its threshold) costs a max tree and one vote; otherwise only the
 // 4-score groups that actually contain a candidate are examined.
@@ -141,7 +149,7 @@ __device__ __forceinline__ void scan_chunk(const uint32_t (&r)[32], int idx0, co
       cnt = ncnt;
       thr_key = T;
       thr_s = key_score(T);
-      if (!p.reset_thr) atomicMax(p.thr + row, T);
+      atomicMax(p.thr + row, T);
     }
   }
 }
@@ -261,7 +269,7 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant
       const int row = ut * kUT + mt * 128 + q * 32 + lane;
       const bool active = row < p.U;
       unsigned long long* buf = p.cand + (static_cast<size_t>(range) * p.u_pad + row) * kCap;
-      unsigned long long thr_key = active ? (p.reset_thr ? 0ull : p.thr[row]) : ~0ull;
+      unsigned long long thr_key = active ? p.thr[row] : ~0ull;
       float thr_s = thr_key == 0ull ? -INFINITY : (active ? key_score(thr_key) : INFINITY);
       int cnt = 0;
       for (int tile = tile0; tile < tile1; ++tile) {
@@ -272,14 +280,28 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant
                                 static_cast<uint32_t>(acc * 256 + mt * 128);
         uint32_t r0[32], r1[32];
         tmem_ld32(t_base, r0);
+        if (p.smax != nullptr) {
+          // sample pass: one float per (chunk, user) — the chunk's best score; layout [chunk][user]
+          float* dst = p.smax + (static_cast<size_t>(tile) * (kIT / 32)) * p.u_pad + row;
 #pragma unroll 1
-        for (int c = 0; c < kIT / 32; c += 2) {
-          tmem_ld_wait();
-          tmem_ld32(t_base + (c + 1) * 32, r1);
-          scan_chunk(r0, tile * p.tile_stride * kIT + c * 32, p, lane, row, buf, cnt, thr_key, thr_s);
-          tmem_ld_wait();
-          if (c + 2 < kIT / 32) tmem_ld32(t_base + (c + 2) * 32, r0);
-          scan_chunk(r1, tile * p.tile_stride * kIT + (c + 1) * 32, p, lane, row, buf, cnt, thr_key, thr_s);
+          for (int c = 0; c < kIT / 32; c += 2) {
+            tmem_ld_wait();
+            tmem_ld32(t_base + (c + 1) * 32, r1);
+            dst[static_cast<size_t>(c) * p.u_pad] = chunk_max(r0);
+            tmem_ld_wait();
+            if (c + 2 < kIT / 32) tmem_ld32(t_base + (c + 2) * 32, r0);
+            dst[static_cast<size_t>(c + 1) * p.u_pad] = chunk_max(r1);
+          }
+        } else {
+#pragma unroll 1
+          for (int c = 0; c < kIT / 32; c += 2) {
+            tmem_ld_wait();
+            tmem_ld32(t_base + (c + 1) * 32, r1);
+            scan_chunk(r0, tile * p.tile_stride * kIT + c * 32, p, lane, row, buf, cnt, thr_key, thr_s);
+            tmem_ld_wait();
+            if (c + 2 < kIT / 32) tmem_ld32(t_base + (c + 2) * 32, r0);
+            scan_chunk(r1, tile * p.tile_stride * kIT + (c + 1) * 32, p, lane, row, buf, cnt, thr_key, thr_s);
+          }
         }
         tc_fence_before();
         __syncwarp();
@@ -287,7 +309,7 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1u;
       }
-      p.cand_cnt[static_cast<size_t>(range) * p.u_pad + row] = active ? cnt : 0;
+      if (p.smax == nullptr) p.cand_cnt[static_cast<size_t>(range) * p.u_pad + row] = active ? cnt : 0;
     }
   }
 
@@ -298,37 +320,27 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant
 
 // --------------------------------------------------------------------------------------------
 // Sample pass -> per-user start threshold. The sample pass scores every `tile_stride`-th item tile
-// (a fraction f of the catalog) and keeps each user's best keys; the ks-th largest sample score,
-// ks = ceil(target * f), is exceeded by about `target` items of the whole catalog. The main pass
-// then only collects scores above it (no pruning, mostly the fast path). This is a heuristic
-// STARTING point only: tt_topk_finalize verifies that at least K' candidates were found and the
-// exactness certificate; users for which it fails go to the exact fallback.
-// One warp per user.
+// and stores, per user, the maximum of each 32-score chunk (nothing is collected, nothing pruned:
+// it runs at the fast-path rate). If a fraction q = target / N of the items beat a score t, a chunk
+// maximum beats it with probability p = 1 - (1-q)^32, so the rank-(p * n_chunks) chunk maximum
+// estimates the score that about `target` = 4 K' items of the catalog exceed. The main pass collects
+// only scores above it (no pruning, mostly the fast path). It is a heuristic STARTING point only:
+// tt_topk_finalize verifies that enough candidates were found plus the exactness certificate, and
+// users for which that fails go to the exact fallback. One thread per user, coalesced [chunk][user].
 // --------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) sample_threshold_kernel(const unsigned long long* __restrict__ cand,
-                                                               const int* __restrict__ cand_cnt, int U, int u_pad,
-                                                               int n_ranges, int ks,
+__global__ void __launch_bounds__(128) sample_threshold_kernel(const float* __restrict__ smax, int U, int u_pad,
+                                                               int n_chunks, int rank,
                                                                unsigned long long* __restrict__ thr) {
-  const int u = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const int u = blockIdx.x * blockDim.x + threadIdx.x;
   if (u >= U) return;
-  int total = 0;
-  for (int r = 0; r < n_ranges; ++r) total += cand_cnt[static_cast<size_t>(r) * u_pad + u];
-  unsigned long long t = 0;
-  if (total >= ks) {
-    for (int bit = 63; bit >= 32; --bit) {   // score bits only: the threshold is a score level
-      const unsigned long long c0 = t | (1ull << bit);
-      int c = 0;
-      for (int r = 0; r < n_ranges; ++r) {
-        const int n = cand_cnt[static_cast<size_t>(r) * u_pad + u];
-        const unsigned long long* b = cand + (static_cast<size_t>(r) * u_pad + u) * kCap;
-        for (int i = lane; i < n; i += 32) c += (b[i] >= c0);
-      }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-      if (c >= ks) t = c0;
-    }
+  uint32_t t = 0;
+  for (int bit = 31; bit >= 0; --bit) {
+    const uint32_t cand = t | (1u << bit);
+    int c = 0;
+    for (int i = 0; i < n_chunks; ++i) c += (f2ord(smax[static_cast<size_t>(i) * u_pad + u]) >= cand);
+    if (c >= rank) t = cand;
   }
-  if (lane == 0) thr[u] = t;
+  thr[u] = static_cast<unsigned long long>(t) << 32;
 }
 
 // --------------------------------------------------------------------------------------------
@@ -645,19 +657,23 @@ extern "C" int tt_topk_plan_make(int U, int N, int kprime, tt_topk_plan* plan) {
   plan->cand_bytes = static_cast<int64_t>(plan->n_ranges) * u_pad * kCap * 8;
   plan->cnt_bytes = static_cast<int64_t>(plan->n_ranges) * u_pad * 4;
   plan->thr_bytes = u_pad * 8;
-  // Sample pass (only worth it for large catalogs): score ~1/32 of the tiles; the start threshold
-  // is the score exceeded by ~4 K' items of the whole catalog, estimated from the sample's order
-  // statistics (rank = 4 K' / stride, at least 24 so the estimate is tight).
-  plan->sample_stride = 0; plan->sample_rank = 0; plan->sample_keep = 0;
-  if (total_tiles >= 2048) {
-    int stride = 32;
-    while (stride > 2 && (4 * kprime) / stride < 24) stride >>= 1;
+  // Sample pass: chunk maxima of a strided subset of the tiles (see sample_threshold_kernel).
+  plan->sample_stride = 0; plan->sample_rank = 0; plan->sample_tiles = 0; plan->smax_bytes = 0;
+  if (total_tiles >= 256) {
+    double target = 4.0 * kprime;
+    if (target > N / 4.0) target = N / 4.0;
+    const double q = target / N;
+    const double pc = 1.0 - pow(1.0 - q, 32.0);
+    int tiles = static_cast<int>(24.0 / pc / 4.0 + 0.999);      // expected rank ~ 24
+    if (tiles < 8) tiles = 8;
+    if (tiles > total_tiles / 4) tiles = total_tiles / 4;
+    const int stride = total_tiles / tiles;
     plan->sample_stride = stride;
-    plan->sample_rank = (4 * kprime + stride - 1) / stride;
-    int keep = 2 * plan->sample_rank;
-    if (keep < 64) keep = 64;
-    if (keep > 256) keep = 256;
-    plan->sample_keep = keep;
+    plan->sample_tiles = (total_tiles + stride - 1) / stride;
+    int rank = static_cast<int>(pc * plan->sample_tiles * 4 + 0.5);
+    if (rank < 4) rank = 4;
+    plan->sample_rank = rank;
+    plan->smax_bytes = static_cast<int64_t>(plan->sample_tiles) * 4 * u_pad * 4;
   }
   return TT_OK;
 }
@@ -693,7 +709,7 @@ static int launch_score_topk(const void* users_bf16, const void* items_bf16, Top
 }
 
 extern "C" int tt_score_topk(const void* users_bf16, const void* items_bf16, int item_base, const tt_topk_plan* plan,
-                             void* cand, int32_t* cand_cnt, void* thr, int mask_item0, void* stream_) {
+                             void* cand, int32_t* cand_cnt, void* thr, void* smax, int mask_item0, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   TT_REQUIRE(users_bf16 && items_bf16 && plan && cand && cand_cnt && thr, "tt_score_topk: null pointer");
   TopkParams p;
@@ -708,32 +724,30 @@ extern "C" int tt_score_topk(const void* users_bf16, const void* items_bf16, int
   p.mask_item0 = mask_item0;
   TT_CHECK_CUDA(cudaMemsetAsync(thr, 0, static_cast<size_t>(plan->thr_bytes), stream));
 
-  // ---- sample pass: every sample_stride-th tile, one range, best keys per user -> start thresholds
-  if (plan->sample_stride > 1) {
-    const int sample_tiles = (p.total_tiles + plan->sample_stride - 1) / plan->sample_stride;
+  // ---- sample pass: chunk maxima of every sample_stride-th tile -> per-user start thresholds
+  p.smax = nullptr;
+  if (plan->sample_stride > 1 && smax != nullptr) {
+    const int sample_tiles = plan->sample_tiles;
     int sr = (num_sms() + p.n_ut - 1) / p.n_ut;           // enough (user tile, range) units for every SM
-    if (sr > plan->n_ranges) sr = plan->n_ranges;         // scratch is sized for n_ranges
-    if (sr > (sample_tiles + 15) / 16) sr = (sample_tiles + 15) / 16;
+    if (sr > sample_tiles) sr = sample_tiles;
     if (sr < 1) sr = 1;
     p.tile_stride = plan->sample_stride;
     p.tiles_per_range = (sample_tiles + sr - 1) / sr;
     p.n_ranges = (sample_tiles + p.tiles_per_range - 1) / p.tiles_per_range;
     const int total_saved = p.total_tiles;
     p.total_tiles = sample_tiles;
-    p.reset_thr = 1;
-    p.kprime = plan->sample_keep;
+    p.smax = static_cast<float*>(smax);
     int rc = launch_score_topk(users_bf16, items_bf16, p, plan->N, stream);
     if (rc) return rc;
-    sample_threshold_kernel<<<(plan->U * 32 + 255) / 256, 256, 0, stream>>>(p.cand, p.cand_cnt, plan->U, p.u_pad,
-                                                                           p.n_ranges, plan->sample_rank, p.thr);
+    sample_threshold_kernel<<<(plan->U + 127) / 128, 128, 0, stream>>>(p.smax, plan->U, p.u_pad, sample_tiles * 4,
+                                                                      plan->sample_rank, p.thr);
     TT_LAUNCH_CHECK();
     p.total_tiles = total_saved;
-    p.kprime = plan->kprime;
+    p.smax = nullptr;
   }
   // ---- main pass
   p.n_ranges = plan->n_ranges; p.tiles_per_range = plan->tiles_per_range;
   p.tile_stride = 1;
-  p.reset_thr = 0;
   return launch_score_topk(users_bf16, items_bf16, p, plan->N, stream);
 }
 

@@ -54,6 +54,7 @@ class CatalogIndex:
                 "cand": torch.empty(p.cand_bytes // 8, device=dev, dtype=torch.int64),
                 "cnt": torch.empty(p.cnt_bytes // 4, device=dev, dtype=torch.int32),
                 "thr": torch.empty(p.thr_bytes // 8, device=dev, dtype=torch.int64),
+                "smax": (torch.empty(p.smax_bytes // 4, device=dev, dtype=torch.float32) if p.smax_bytes else None),
                 "users_bf16": torch.empty(U, 256, device=dev, dtype=torch.bfloat16),
                 "keys": None,
             }
@@ -76,7 +77,8 @@ def retrieve_topk(user_emb: torch.Tensor, index: CatalogIndex, K: int, kprime: i
     ops.cast_bf16(user_emb.view(-1), sc["users_bf16"].view(-1))
     check(lib().tt_score_topk(sc["users_bf16"].data_ptr(), index.table_bf16.data_ptr(), index.item_base,
                               ctypes.byref(plan), sc["cand"].data_ptr(), sc["cnt"].data_ptr(), sc["thr"].data_ptr(),
-                              int(mask_item0), _stream()), "tt_score_topk")
+                              None if sc["smax"] is None else sc["smax"].data_ptr(), int(mask_item0), _stream()),
+          "tt_score_topk")
     # rigorous bound on |u^.e^ - u.e| (Cauchy-Schwarz on the bf16 rounding errors) + fp32 accumulation slack
     u16 = sc["users_bf16"].float()
     du = (u16 - user_emb).norm(dim=1).max()
