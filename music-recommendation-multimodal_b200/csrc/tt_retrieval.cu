@@ -281,16 +281,16 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant
         uint32_t r0[32], r1[32];
         tmem_ld32(t_base, r0);
         if (p.smax != nullptr) {
-          // sample pass: one float per (chunk, user) — the chunk's best score; layout [chunk][user]
-          float* dst = p.smax + (static_cast<size_t>(tile) * (kIT / 32)) * p.u_pad + row;
+          // sample pass: one float per (user, chunk) — the chunk's best score; layout [user][chunk]
+          float* dst = p.smax + static_cast<size_t>(row) * (p.total_tiles * (kIT / 32)) + tile * (kIT / 32);
 #pragma unroll 1
           for (int c = 0; c < kIT / 32; c += 2) {
             tmem_ld_wait();
             tmem_ld32(t_base + (c + 1) * 32, r1);
-            dst[static_cast<size_t>(c) * p.u_pad] = chunk_max(r0);
+            dst[c] = chunk_max(r0);
             tmem_ld_wait();
             if (c + 2 < kIT / 32) tmem_ld32(t_base + (c + 2) * 32, r0);
-            dst[static_cast<size_t>(c + 1) * p.u_pad] = chunk_max(r1);
+            dst[c + 1] = chunk_max(r1);
           }
         } else {
 #pragma unroll 1
@@ -326,21 +326,31 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant
 // estimates the score that about `target` = 4 K' items of the catalog exceed. The main pass collects
 // only scores above it (no pruning, mostly the fast path). It is a heuristic STARTING point only:
 // tt_topk_finalize verifies that enough candidates were found plus the exactness certificate, and
-// users for which that fails go to the exact fallback. One thread per user, coalesced [chunk][user].
+// users for which that fails go to the exact fallback. One warp per user, maxima held in registers.
 // --------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) sample_threshold_kernel(const float* __restrict__ smax, int U, int u_pad,
-                                                               int n_chunks, int rank,
-                                                               unsigned long long* __restrict__ thr) {
-  const int u = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(256) sample_threshold_kernel(const float* __restrict__ smax, int U, int n_chunks,
+                                                               int rank, unsigned long long* __restrict__ thr) {
+  constexpr int kMaxPerLane = 32;   // up to 1024 chunk maxima per user
+  const int u = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (u >= U) return;
+  const float* row = smax + static_cast<size_t>(u) * n_chunks;
+  uint32_t v[kMaxPerLane];
+#pragma unroll
+  for (int e = 0; e < kMaxPerLane; ++e) {
+    const int i = e * 32 + lane;
+    v[e] = i < n_chunks ? f2ord(row[i]) : 0u;
+  }
   uint32_t t = 0;
   for (int bit = 31; bit >= 0; --bit) {
     const uint32_t cand = t | (1u << bit);
     int c = 0;
-    for (int i = 0; i < n_chunks; ++i) c += (f2ord(smax[static_cast<size_t>(i) * u_pad + u]) >= cand);
+#pragma unroll
+    for (int e = 0; e < kMaxPerLane; ++e) c += (v[e] >= cand);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
     if (c >= rank) t = cand;
   }
-  thr[u] = static_cast<unsigned long long>(t) << 32;
+  if (lane == 0) thr[u] = static_cast<unsigned long long>(t) << 32;
 }
 
 // --------------------------------------------------------------------------------------------
@@ -667,6 +677,7 @@ extern "C" int tt_topk_plan_make(int U, int N, int kprime, tt_topk_plan* plan) {
     int tiles = static_cast<int>(24.0 / pc / 4.0 + 0.999);      // expected rank ~ 24
     if (tiles < 8) tiles = 8;
     if (tiles > total_tiles / 4) tiles = total_tiles / 4;
+    if (tiles > 240) tiles = 240;                                 // <= 1024 chunk maxima per user (threshold kernel registers)
     const int stride = total_tiles / tiles;
     plan->sample_stride = stride;
     plan->sample_tiles = (total_tiles + stride - 1) / stride;
@@ -726,7 +737,7 @@ extern "C" int tt_score_topk(const void* users_bf16, const void* items_bf16, int
 
   // ---- sample pass: chunk maxima of every sample_stride-th tile -> per-user start thresholds
   p.smax = nullptr;
-  if (plan->sample_stride > 1 && smax != nullptr) {
+  if (plan->sample_stride > 1 && smax != nullptr && plan->sample_tiles * 4 <= 1024) {
     const int sample_tiles = plan->sample_tiles;
     int sr = (num_sms() + p.n_ut - 1) / p.n_ut;           // enough (user tile, range) units for every SM
     if (sr > sample_tiles) sr = sample_tiles;
@@ -739,8 +750,8 @@ extern "C" int tt_score_topk(const void* users_bf16, const void* items_bf16, int
     p.smax = static_cast<float*>(smax);
     int rc = launch_score_topk(users_bf16, items_bf16, p, plan->N, stream);
     if (rc) return rc;
-    sample_threshold_kernel<<<(plan->U + 127) / 128, 128, 0, stream>>>(p.smax, plan->U, p.u_pad, sample_tiles * 4,
-                                                                      plan->sample_rank, p.thr);
+    sample_threshold_kernel<<<(plan->U * 32 + 255) / 256, 256, 0, stream>>>(p.smax, plan->U, sample_tiles * 4,
+                                                                           plan->sample_rank, p.thr);
     TT_LAUNCH_CHECK();
     p.total_tiles = total_saved;
     p.smax = nullptr;
