@@ -343,14 +343,53 @@ def bench_retrieval(eng, rank, world, dev, peaks):
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         dist.all_reduce(e2e, op=dist.ReduceOp.MAX)
+    # ---- the same pass with the user embeddings produced by the CUDA user tower (eval mode) from HOST
+    # histories (L = 50, the reference default): H2D ids -> SASRec forward -> retrieval -> merge -> metrics
+    from mrm_b200 import synthetic
+    from mrm_b200.engine import TwoTowerEngine
+    Lh, UB = C3["hist_len"], 2000
+    tcfg = synthetic.TwoTowerConfig(vocab_size=4096, max_seq_len=Lh, dropout=0.0)   # small ID table: ids are synthetic
+    teng = TwoTowerEngine(tcfg, dev)
+    teng.load_state_dict(synthetic.make_state_dict(tcfg, seed=0))
+    hb = synthetic.make_batch(tcfg, U, seed=7, full_length=True)
+    h_ids, h_mask = hb["history_ids"].pin_memory(), hb["history_mask"].pin_memory()
+    h_g, h_c = hb["user_gender"].pin_memory(), hb["user_country"].pin_memory()
+    uemb = torch.empty(U, 256, device=dev)
+
+    def tower_pass():
+        ws = teng.workspace(UB, Lh)
+        if not teng.shadow_valid:
+            teng.refresh_shadow()
+        for s0 in range(0, U, UB):
+            sl = slice(s0, s0 + UB)
+            u = teng.user_forward(ws, h_ids[sl].to(dev, non_blocking=True), h_mask[sl].to(dev, non_blocking=True),
+                                  h_g[sl].to(dev, non_blocking=True), h_c[sl].to(dev, non_blocking=True), training=False)
+            uemb[sl].copy_(u)
+        return retrieval.metrics_from_embeddings(uemb, host_targets.to(dev, non_blocking=True), index, kl)
+
+    for _ in range(2):
+        tower_pass()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(iters):
+        tower_pass()
+    torch.cuda.synchronize()
+    e2e_tower = torch.tensor([(time.perf_counter() - t0) / iters], device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_tower, op=dist.ReduceOp.MAX)
+
     flops = 2.0 * U * (N + 1) * 256 / world
     peak_tf = peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops"))
     return {"metric": "top-100 retrieval users/sec @1M items", "users_per_s": U / (ms.item() * 1e-3),
             "ms_per_pass": ms.item(), "e2e_users_per_s": U / e2e.item(),
+            "e2e_users_per_s_incl_user_tower": U / e2e_tower.item(),
             "scoring_tflops_per_gpu": flops / (ms.item() * 1e-3) / 1e12,
             "roofline_frac_tensor": flops / (ms.item() * 1e-3) / 1e12 / peak_tf,
             "config": {"workload": f"c3: {U} users x {N} items, top-{K}, Recall/NDCG@10/20/50/100, catalog sharded "
-                                   f"over {world} GPU(s); user embeddings precomputed",
+                                   f"over {world} GPU(s)",
+                       "users_per_s": "device-resident user embeddings: scoring + top-K + exact re-score (events)",
+                       "e2e_users_per_s": "host user embeddings -> device, retrieval, cross-shard merge, metrics -> host",
+                       "e2e_users_per_s_incl_user_tower": f"host histories (L={Lh}) -> CUDA user tower (eval) -> same",
                        "kprime": 256},
             "recall_at_10": m["Recall@10"], "fallback_users": int(nfb)}
 
