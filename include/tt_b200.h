@@ -91,7 +91,7 @@ int tt_gemm_bf16(const tt_gemm_args* args, void* stream);
  *   ctx  : bf16 [B*L, H*64]     attention output before out_proj
  *   lse  : fp32 [B, H, L]       natural-log sum-exp of the scaled scores (for backward)
  * Dropout (p > 0) is applied to the attention probabilities with the counter-based hash
- * (seed + *seed_dev, site, ((b*H+h)*L+i)*L+j). L <= 512 forward, L <= 256 backward.
+ * (seed + *seed_dev, site, ((b*H+h)*L+i)*L+j). L <= 512.
  */
 int tt_attn_causal_fwd(const void* qkv, void* ctx, float* lse, int B, int L, int H, float drop_p,
                        uint64_t drop_seed, const uint64_t* drop_seed_dev, uint32_t drop_site, void* stream);

@@ -279,7 +279,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
 //   dK_j += dS^T Q_i    (A = dS read MN-major,               B = Q_i  read MN-major)
 //   dQ_i += dS K_j      (A = dS K-major,                     B = K_j  read MN-major)
 // dV_j, dK_j live in TMEM (cols [256,320), [320,384)) across the inner loop; dQ_i
-// (cols [384 + 64*i ...)) is kept for up to two query tiles, i.e. L <= 256.
+// (cols [384 + 64*i ...)) is kept for every query tile: two tiles (L <= 256) in the fast layout,
+// four (L <= 512) in the LONG layout described at the kernel.
 // Pd and dS are staged as bf16 in 128B-swizzled smem tiles. Thread (row, hf) owns query row
 // `row` and the 64-column half `hf` of the 128-key tile (warp & 3 = TMEM lane quarter).
 // --------------------------------------------------------------------------------------------
@@ -309,6 +310,11 @@ __device__ __forceinline__ void store_row32_bf16(__nv_bfloat16* dst, const uint3
   }
 }
 
+// LONG = false: L <= 256 (two query tiles): S and dP have their own TMEM columns and are issued
+//   together. LONG = true: L <= 512 (four query tiles): the four dQ accumulators need 256 columns,
+//   so S and dP SHARE one 128-column region — P is formed from S first (un-dropped P parked as bf16
+//   in the dS tile), then dP = dO V^T overwrites S and dS replaces the parked P.
+template <bool LONG>
 __global__ void __launch_bounds__(256, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
                 const AttnBwdParams p) {
@@ -326,10 +332,12 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
   const int nq = p.nq;
   const int seq_row0 = b * p.L;
 
-  // smem: Q[nq], dO[nq], K_j, V_j, Pd (2 chunks), dS (2 chunks)
+  // smem: Q[slots], dO[slots], K_j, V_j, Pd (2 chunks), dS (2 chunks). The fast layout keeps every
+  // query tile resident; LONG re-loads Q_i / dO_i per (j, i) iteration into a single slot.
+  const int slots = LONG ? 1 : nq;
   uint8_t* sQ = smem;
-  uint8_t* sDO = sQ + static_cast<size_t>(nq) * kTileBytes;
-  uint8_t* sK = sDO + static_cast<size_t>(nq) * kTileBytes;
+  uint8_t* sDO = sQ + static_cast<size_t>(slots) * kTileBytes;
+  uint8_t* sK = sDO + static_cast<size_t>(slots) * kTileBytes;
   uint8_t* sV = sK + kTileBytes;
   uint8_t* sPd = sV + kTileBytes;
   uint8_t* sDS = sPd + 2 * kTileBytes;
@@ -338,8 +346,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
   uint64_t* bar_kv = bars + 1;   // K_j/V_j loaded (phase per j)
   uint64_t* bar_mm1 = bars + 2;  // S and dP ready (phase per (j,i))
   uint64_t* bar_mm2 = bars + 3;  // dV/dK/dQ MMAs of this (j,i) retired
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
-  float* sDelta = reinterpret_cast<float*>(bars + 6);  // [nq*128]
+  uint64_t* bar_mm1b = bars + 4; // LONG: dP ready (after S has been consumed)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+  float* sDelta = reinterpret_cast<float*>(bars + 8);  // [nq*128]
   float* sLse = sDelta + nq * kTile;                   // [nq*128], pre-multiplied by log2e
 
   const uint32_t tmem_cols = 512;
@@ -350,6 +359,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     mbar_init(bar_kv, 1);
     mbar_init(bar_mm1, 1);
     mbar_init(bar_mm2, 1);
+    mbar_init(bar_mm1b, 1);
     fence_barrier_init();
   }
   __syncwarp();
@@ -362,9 +372,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-  const uint32_t T_S = 0, T_DP = 128, T_DV = 256, T_DK = 320, T_DQ = 384;
+  constexpr uint32_t T_S = 0, T_DP = LONG ? 0 : 128, T_DV = LONG ? 128 : 256, T_DK = LONG ? 192 : 320,
+                     T_DQ = LONG ? 256 : 384;
 
-  if (tid == 0) {
+  if (!LONG && tid == 0) {
     mbar_arrive_expect_tx(bar_q, 2 * nq * kTileBytes);
     for (int i = 0; i < nq; ++i) {
       tma_load_2d(sQ + static_cast<size_t>(i) * kTileBytes, &tmQKV, bar_q, h * kDh, seq_row0 + i * kTile);
@@ -413,21 +424,31 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       tma_load_2d(sV, &tmQKV, bar_kv, 2 * D + h * kDh, seq_row0 + j * kTile);
     }
     for (int i = j; i < nq; ++i, ++it) {
+      const int slot = LONG ? 0 : i;
       if (tid == 0) {
-        if (it == 0) mbar_wait(bar_q, 0);
+        if constexpr (LONG) {   // the previous iteration's MMAs retired (bar_mm2): the slot is free
+          mbar_arrive_expect_tx(bar_q, 2 * kTileBytes);
+          tma_load_2d(sQ, &tmQKV, bar_q, h * kDh, seq_row0 + i * kTile);
+          tma_load_2d(sDO, &tmDO, bar_q, h * kDh, seq_row0 + i * kTile);
+          mbar_wait(bar_q, it & 1);
+        } else {
+          if (it == 0) mbar_wait(bar_q, 0);
+        }
         if (i == j) mbar_wait(bar_kv, j & 1);
         tc_fence_after();
-        const uint32_t q_base = smem_u32(sQ + static_cast<size_t>(i) * kTileBytes);
-        const uint32_t do_base = smem_u32(sDO + static_cast<size_t>(i) * kTileBytes);
+        const uint32_t q_base = smem_u32(sQ + static_cast<size_t>(slot) * kTileBytes);
+        const uint32_t do_base = smem_u32(sDO + static_cast<size_t>(slot) * kTileBytes);
         const uint32_t k_base = smem_u32(sK), v_base = smem_u32(sV);
 #pragma unroll
         for (int k = 0; k < kDh / 16; ++k)
           umma_bf16(tmem_base + T_S, umma_desc_kmajor(q_base + k * 32), umma_desc_kmajor(k_base + k * 32),
                     idesc_s, k > 0 ? 1u : 0u);
+        if constexpr (!LONG) {
 #pragma unroll
-        for (int k = 0; k < kDh / 16; ++k)
-          umma_bf16(tmem_base + T_DP, umma_desc_kmajor(do_base + k * 32), umma_desc_kmajor(v_base + k * 32),
-                    idesc_s, k > 0 ? 1u : 0u);
+          for (int k = 0; k < kDh / 16; ++k)
+            umma_bf16(tmem_base + T_DP, umma_desc_kmajor(do_base + k * 32), umma_desc_kmajor(v_base + k * 32),
+                      idesc_s, k > 0 ? 1u : 0u);
+        }
         umma_commit(bar_mm1);
       }
       mbar_wait(bar_mm1, it & 1);
@@ -439,6 +460,103 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       const float delta = sDelta[q_pos];
       const bool diag = (i == j);
       const bool row_ok = q_pos < p.L;
+      if constexpr (LONG) {
+        // ---- part A: P from S. Pd -> sPd, un-dropped P parked (bf16) in the dS tile ---------------
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) {
+          const int cg = 2 * hf + cc;
+          const int u0 = cc * 4;
+          if (!(diag && cg > q)) {
+            uint32_t rs[32];
+            tmem_ld32(lane_base + T_S + cg * 32, rs);
+            tmem_ld_wait();
+            const int kv0 = j * kTile + cg * 32;
+            const uint32_t didx0 = (static_cast<uint32_t>(bh) * p.L + q_pos) * p.L + kv0;
+            float pr[32], pd[32];
+#pragma unroll
+            for (int t = 0; t < 32; ++t) {
+              float x = fast_exp2(__uint_as_float(rs[t]) * c1 - lse2);
+              if ((diag && kv0 + t > q_pos) || !row_ok) x = 0.f;
+              pr[t] = x;
+              pd[t] = (p.drop_thresh && !drop_keep_k(dkey, didx0 + t, p.drop_thresh)) ? 0.f : x * p.drop_scale;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              uint4 v, w;
+              v.x = pack_bf16(pd[u * 8 + 0], pd[u * 8 + 1]);
+              v.y = pack_bf16(pd[u * 8 + 2], pd[u * 8 + 3]);
+              v.z = pack_bf16(pd[u * 8 + 4], pd[u * 8 + 5]);
+              v.w = pack_bf16(pd[u * 8 + 6], pd[u * 8 + 7]);
+              w.x = pack_bf16(pr[u * 8 + 0], pr[u * 8 + 1]);
+              w.y = pack_bf16(pr[u * 8 + 2], pr[u * 8 + 3]);
+              w.z = pack_bf16(pr[u * 8 + 4], pr[u * 8 + 5]);
+              w.w = pack_bf16(pr[u * 8 + 6], pr[u * 8 + 7]);
+              st_swizzled_unit(pchunk, row, u0 + u, v);
+              st_swizzled_unit(dchunk, row, u0 + u, w);
+            }
+          } else {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              st_swizzled_unit(pchunk, row, u0 + u, make_uint4(0, 0, 0, 0));
+              st_swizzled_unit(dchunk, row, u0 + u, make_uint4(0, 0, 0, 0));
+            }
+          }
+        }
+        // ---- dP = dO V^T overwrites S once every thread has drained it --------------------------
+        tc_fence_before();
+        __syncthreads();
+        if (tid == 0) {
+          tc_fence_after();
+          const uint32_t do_base = smem_u32(sDO + static_cast<size_t>(slot) * kTileBytes);
+          const uint32_t v_base = smem_u32(sV);
+#pragma unroll
+          for (int k = 0; k < kDh / 16; ++k)
+            umma_bf16(tmem_base + T_DP, umma_desc_kmajor(do_base + k * 32), umma_desc_kmajor(v_base + k * 32),
+                      idesc_s, k > 0 ? 1u : 0u);
+          umma_commit(bar_mm1b);
+        }
+        mbar_wait(bar_mm1b, it & 1);
+        __syncwarp();
+        tc_fence_after();
+        // ---- part B: dS = P * (dropout(dP) - delta) * scale replaces the parked P ------------------
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) {
+          const int cg = 2 * hf + cc;
+          const int u0 = cc * 4;
+          if (!(diag && cg > q)) {
+            uint32_t rp[32];
+            tmem_ld32(lane_base + T_DP + cg * 32, rp);
+            tmem_ld_wait();
+            const int kv0 = j * kTile + cg * 32;
+            const uint32_t didx0 = (static_cast<uint32_t>(bh) * p.L + q_pos) * p.L + kv0;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              uint4* slot = reinterpret_cast<uint4*>(dchunk + row * 128 + (((u0 + u) ^ (row & 7)) << 4));
+              const uint4 pw = *slot;
+              const uint32_t w[4] = {pw.x, pw.y, pw.z, pw.w};
+              float ds[8];
+#pragma unroll
+              for (int h2 = 0; h2 < 4; ++h2) {
+                const float2 pr2 = unpack_bf16(w[h2]);
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                  const int t = u * 8 + h2 * 2 + e;
+                  const float prv = e ? pr2.y : pr2.x;
+                  const bool keep = !p.drop_thresh || drop_keep_k(dkey, didx0 + t, p.drop_thresh);
+                  const float dp = keep ? __uint_as_float(rp[t]) * p.drop_scale : 0.f;
+                  ds[h2 * 2 + e] = prv * (dp - delta) * p.scale;
+                }
+              }
+              uint4 o;
+              o.x = pack_bf16(ds[0], ds[1]);
+              o.y = pack_bf16(ds[2], ds[3]);
+              o.z = pack_bf16(ds[4], ds[5]);
+              o.w = pack_bf16(ds[6], ds[7]);
+              *slot = o;
+            }
+          }
+        }
+      } else {
 #pragma unroll
       for (int cc = 0; cc < 2; ++cc) {
         const int cg = 2 * hf + cc;
@@ -499,14 +617,15 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
           }
         }
       }
+      }
       fence_proxy_async_smem();
       tc_fence_before();
       __syncthreads();
       if (tid == 0) {
         tc_fence_after();
         const uint32_t pd_base = smem_u32(sPd), ds_base = smem_u32(sDS);
-        const uint32_t q_base = smem_u32(sQ + static_cast<size_t>(i) * kTileBytes);
-        const uint32_t do_base = smem_u32(sDO + static_cast<size_t>(i) * kTileBytes);
+        const uint32_t q_base = smem_u32(sQ + static_cast<size_t>(slot) * kTileBytes);
+        const uint32_t do_base = smem_u32(sDO + static_cast<size_t>(slot) * kTileBytes);
         const uint32_t k_base = smem_u32(sK);
         // Pd / dS are stored [q row][kv col] in two 64-column chunks. Read as the TRANSPOSED
         // operand (M = kv, contraction = q) they are MN-major: 16 q rows = 2048 B per K step,
@@ -625,7 +744,7 @@ extern "C" int tt_attn_causal_bwd(const void* qkv, const void* ctx, const void* 
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   TT_REQUIRE(qkv && ctx && dctx && lse && dqkv, "tt_attn_causal_bwd: null pointer");
   TT_REQUIRE(B > 0 && L > 0 && H > 0, "tt_attn_causal_bwd: empty problem");
-  TT_REQUIRE(L <= 256, "tt_attn_causal_bwd: L=%d > 256 unsupported in this build", L);
+  TT_REQUIRE(L <= 512, "tt_attn_causal_bwd: L=%d > 512 unsupported", L);
   const int D = H * kDh;
   AttnBwdParams p;
   p.B = B; p.L = L; p.H = H;
@@ -645,15 +764,18 @@ extern "C" int tt_attn_causal_bwd(const void* qkv, const void* ctx, const void* 
   if (rc) return rc;
   rc = make_rows_map(&tmDO, dctx, B * L, D);
   if (rc) return rc;
-  const size_t smem = 1024 + static_cast<size_t>(2 * p.nq + 2 + 4) * kTileBytes + 64 +
+  const int slots = p.nq <= 2 ? p.nq : 1;
+  const size_t smem = 1024 + static_cast<size_t>(2 * slots + 2 + 4) * kTileBytes + 128 +
                       static_cast<size_t>(2 * p.nq * kTile) * sizeof(float);
   static bool configured = false;
   if (!configured) {
-    TT_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    TT_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    TT_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
     configured = true;
   }
   TT_REQUIRE(smem <= 232448, "tt_attn_causal_bwd: shared memory %zu too large", smem);
-  attn_bwd_kernel<<<B * H, 256, smem, stream>>>(tmQ, tmDO, p);
+  if (p.nq <= 2) attn_bwd_kernel<false><<<B * H, 256, smem, stream>>>(tmQ, tmDO, p);
+  else attn_bwd_kernel<true><<<B * H, 256, smem, stream>>>(tmQ, tmDO, p);
   TT_LAUNCH_CHECK();
   return TT_OK;
 }

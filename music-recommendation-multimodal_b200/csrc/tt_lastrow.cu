@@ -106,13 +106,33 @@ __device__ __forceinline__ void store16_scaled(__nv_bfloat16* p, const float (&v
   }
 }
 
-// blockDim = 128 (4 warps); one warp per (b, h); smem: 4 x kMaxL floats
+// One block (4 warps) per (b, h). The 32 key slots of an iteration are spread over the block:
+// warp w, lane (ks, dq) handles key j = 32*it + 8*w + ks, dims [16*dq, 16*dq+16). Row max / sum and
+// the per-dim outputs are combined across the 4 warps through shared memory.
+__device__ __forceinline__ float block4_max(float v, float* s4, int wib, int lane) {
+  v = warp_max(v);
+  if (lane == 0) s4[wib] = v;
+  __syncthreads();
+  const float r = fmaxf(fmaxf(s4[0], s4[1]), fmaxf(s4[2], s4[3]));
+  __syncthreads();
+  return r;
+}
+__device__ __forceinline__ float block4_sum(float v, float* s4, int wib, int lane) {
+  v = warp_sum(v);
+  if (lane == 0) s4[wib] = v;
+  __syncthreads();
+  const float r = (s4[0] + s4[1]) + (s4[2] + s4[3]);
+  __syncthreads();
+  return r;
+}
+
 __global__ void __launch_bounds__(128) attn_lastq_fwd_kernel(const LastQParams p) {
-  __shared__ float s_p[4][kMaxL];
+  __shared__ float s_p[kMaxL];
+  __shared__ float s_acc[4][64];
+  __shared__ float s4[4];
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ks = lane >> 2, dq = lane & 3;
-  const int bh = blockIdx.x * 4 + wib;
-  if (bh >= p.B * p.H) return;
+  const int bh = blockIdx.x;
   const int b = bh / p.H, h = bh % p.H;
   const int D = p.H * kDh;
   const int last = p.last_idx[b];
@@ -123,8 +143,8 @@ __global__ void __launch_bounds__(128) attn_lastq_fwd_kernel(const LastQParams p
   const __nv_bfloat16* vbase = kbase + D;
   const float c1 = p.scale * kLog2e;
   float m = -INFINITY;
-  for (int j0 = 0; j0 < len; j0 += 8) {
-    const int j = j0 + ks;
+  for (int j0 = 0; j0 < len; j0 += 32) {
+    const int j = j0 + wib * 8 + ks;
     float s = -INFINITY;
     if (j < len) {
       float k[16];
@@ -132,53 +152,54 @@ __global__ void __launch_bounds__(128) attn_lastq_fwd_kernel(const LastQParams p
       s = dot16(k, q);
     }
     s = quad_sum(s) * c1;          // (-inf stays -inf for keys beyond len)
-    if (dq == 0 && j < len) s_p[wib][j] = s;
+    if (dq == 0 && j < len) s_p[j] = s;
     m = fmaxf(m, s);
   }
-  m = warp_max(m);
-  __syncwarp();
+  m = block4_max(m, s4, wib, lane);   // (also orders the s_p writes before the reads below)
   const uint64_t seed = p.seed + ((p.drop_thresh && p.seed_dev) ? *p.seed_dev : 0ull);
   const uint32_t dkey = drop_key(seed, p.site);
   const uint64_t didx0 = (static_cast<uint64_t>(bh) * p.L + last) * p.L;
   float l = 0.f;
-  for (int j = lane; j < len; j += 32) {
-    float e = exp2f(s_p[wib][j] - m);
+  for (int j = threadIdx.x; j < len; j += 128) {
+    float e = exp2f(s_p[j] - m);
     l += e;
     if (p.drop_thresh) e = drop_keep_k(dkey, didx0 + j, p.drop_thresh) ? e * p.drop_scale : 0.f;
-    s_p[wib][j] = e;
+    s_p[j] = e;
   }
-  l = warp_sum(l);
-  __syncwarp();
-  // ctx[d] = sum_j p_j V[j][d]: lane owns dims (2*lane, 2*lane+1); 4 independent accumulator pairs
-  float a[4][2] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};
-  int j = 0;
-  for (; j + 4 <= len; j += 4) {
-#pragma unroll
-    for (int t = 0; t < 4; ++t) {
-      const float pj = s_p[wib][j + t];
-      const float2 v = unpack_bf16(__ldg(reinterpret_cast<const uint32_t*>(vbase + static_cast<size_t>(j + t) * 3 * D) + lane));
-      a[t][0] += pj * v.x;
-      a[t][1] += pj * v.y;
-    }
+  l = block4_sum(l, s4, wib, lane);
+  // ctx[d] = sum_j p_j V[j][d]: warp w takes keys j = w, w+4, ...; lane owns dims (2*lane, 2*lane+1)
+  float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
+  int j = wib;
+  for (; j + 4 < len; j += 8) {
+    const float p0 = s_p[j], p1 = s_p[j + 4];
+    const float2 v0 = unpack_bf16(__ldg(reinterpret_cast<const uint32_t*>(vbase + static_cast<size_t>(j) * 3 * D) + lane));
+    const float2 v1 = unpack_bf16(__ldg(reinterpret_cast<const uint32_t*>(vbase + static_cast<size_t>(j + 4) * 3 * D) + lane));
+    a0 += p0 * v0.x; a1 += p0 * v0.y;
+    b0 += p1 * v1.x; b1 += p1 * v1.y;
   }
-  for (; j < len; ++j) {
-    const float pj = s_p[wib][j];
-    const float2 v = unpack_bf16(__ldg(reinterpret_cast<const uint32_t*>(vbase + static_cast<size_t>(j) * 3 * D) + lane));
-    a[0][0] += pj * v.x;
-    a[0][1] += pj * v.y;
+  for (; j < len; j += 4) {
+    const float p0 = s_p[j];
+    const float2 v0 = unpack_bf16(__ldg(reinterpret_cast<const uint32_t*>(vbase + static_cast<size_t>(j) * 3 * D) + lane));
+    a0 += p0 * v0.x; a1 += p0 * v0.y;
   }
-  const float inv = 1.f / l;
-  const float o0 = (a[0][0] + a[1][0]) + (a[2][0] + a[3][0]), o1 = (a[0][1] + a[1][1]) + (a[2][1] + a[3][1]);
-  reinterpret_cast<uint32_t*>(p.ctx + static_cast<size_t>(b) * D + h * kDh)[lane] = pack_bf16(o0 * inv, o1 * inv);
-  if (lane == 0 && p.lse) p.lse[bh] = (m + log2f(l)) / kLog2e;   // natural-log sum-exp of the scaled scores
+  s_acc[wib][2 * lane] = a0 + b0;
+  s_acc[wib][2 * lane + 1] = a1 + b1;
+  __syncthreads();
+  if (wib == 0) {
+    const float inv = 1.f / l;
+    const float o0 = (s_acc[0][2 * lane] + s_acc[1][2 * lane]) + (s_acc[2][2 * lane] + s_acc[3][2 * lane]);
+    const float o1 = (s_acc[0][2 * lane + 1] + s_acc[1][2 * lane + 1]) + (s_acc[2][2 * lane + 1] + s_acc[3][2 * lane + 1]);
+    reinterpret_cast<uint32_t*>(p.ctx + static_cast<size_t>(b) * D + h * kDh)[lane] = pack_bf16(o0 * inv, o1 * inv);
+    if (lane == 0 && p.lse) p.lse[bh] = (m + log2f(l)) / kLog2e;   // natural-log sum-exp of the scaled scores
+  }
 }
 
 __global__ void __launch_bounds__(128) attn_lastq_bwd_kernel(const LastQParams p) {
-  __shared__ float s_ds[4][kMaxL];
+  __shared__ float s_ds[kMaxL];
+  __shared__ float s_acc[4][64];
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ks = lane >> 2, dq = lane & 3;
-  const int bh = blockIdx.x * 4 + wib;
-  if (bh >= p.B * p.H) return;
+  const int bh = blockIdx.x;
   const int b = bh / p.H, h = bh % p.H;
   const int D = p.H * kDh;
   const int last = p.last_idx[b];
@@ -202,8 +223,8 @@ __global__ void __launch_bounds__(128) attn_lastq_bwd_kernel(const LastQParams p
   const uint64_t seed = p.seed + ((p.drop_thresh && p.seed_dev) ? *p.seed_dev : 0ull);
   const uint32_t dkey = drop_key(seed, p.site);
   const uint64_t didx0 = (static_cast<uint64_t>(bh) * p.L + last) * p.L;
-  for (int j0 = 0; j0 < p.L; j0 += 8) {
-    const int j = j0 + ks;
+  for (int j0 = 0; j0 < p.L; j0 += 32) {
+    const int j = j0 + wib * 8 + ks;
     const bool inrange = j < p.L;      // every lane stays in the loop: the quad shuffles use the full mask
     __nv_bfloat16* dk = dkbase + static_cast<size_t>(j) * 3 * D + dq * 16;
     __nv_bfloat16* dv = dvbase + static_cast<size_t>(j) * 3 * D + dq * 16;
@@ -227,7 +248,7 @@ __global__ void __launch_bounds__(128) attn_lastq_bwd_kernel(const LastQParams p
         dp = keep ? dp * p.drop_scale : 0.f;
       }
       const float ds = pr * (dp - delta) * p.scale;
-      if (dq == 0) s_ds[wib][j] = ds;
+      if (dq == 0) s_ds[j] = ds;
       store16_scaled(dk, q, ds);    // dK_j = dS_j * q
       store16_scaled(dv, g, pd);    // dV_j = Pd_j * dO
     } else if (inrange) {
@@ -238,26 +259,30 @@ __global__ void __launch_bounds__(128) attn_lastq_bwd_kernel(const LastQParams p
       }
     }
   }
-  __syncwarp();
-  float a[4][2] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};
-  int j = 0;
-  for (; j + 4 <= len; j += 4) {
-#pragma unroll
-    for (int t = 0; t < 4; ++t) {
-      const float ds = s_ds[wib][j + t];
-      const float2 k = unpack_bf16(__ldg(reinterpret_cast<const uint32_t*>(kbase + static_cast<size_t>(j + t) * 3 * D) + lane));
-      a[t][0] += ds * k.x;
-      a[t][1] += ds * k.y;
-    }
+  __syncthreads();
+  // dq[d] = sum_j dS_j K[j][d]: warp w takes keys j = w, w+4, ...
+  float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
+  int j = wib;
+  for (; j + 4 < len; j += 8) {
+    const float d0 = s_ds[j], d1 = s_ds[j + 4];
+    const float2 k0 = unpack_bf16(__ldg(reinterpret_cast<const uint32_t*>(kbase + static_cast<size_t>(j) * 3 * D) + lane));
+    const float2 k1 = unpack_bf16(__ldg(reinterpret_cast<const uint32_t*>(kbase + static_cast<size_t>(j + 4) * 3 * D) + lane));
+    a0 += d0 * k0.x; a1 += d0 * k0.y;
+    b0 += d1 * k1.x; b1 += d1 * k1.y;
   }
-  for (; j < len; ++j) {
-    const float ds = s_ds[wib][j];
-    const float2 k = unpack_bf16(__ldg(reinterpret_cast<const uint32_t*>(kbase + static_cast<size_t>(j) * 3 * D) + lane));
-    a[0][0] += ds * k.x;
-    a[0][1] += ds * k.y;
+  for (; j < len; j += 4) {
+    const float d0 = s_ds[j];
+    const float2 k0 = unpack_bf16(__ldg(reinterpret_cast<const uint32_t*>(kbase + static_cast<size_t>(j) * 3 * D) + lane));
+    a0 += d0 * k0.x; a1 += d0 * k0.y;
   }
-  const float o0 = (a[0][0] + a[1][0]) + (a[2][0] + a[3][0]), o1 = (a[0][1] + a[1][1]) + (a[2][1] + a[3][1]);
-  reinterpret_cast<uint32_t*>(p.dq + static_cast<size_t>(b) * D + h * kDh)[lane] = pack_bf16(o0, o1);
+  s_acc[wib][2 * lane] = a0 + b0;
+  s_acc[wib][2 * lane + 1] = a1 + b1;
+  __syncthreads();
+  if (wib == 0) {
+    const float o0 = (s_acc[0][2 * lane] + s_acc[1][2 * lane]) + (s_acc[2][2 * lane] + s_acc[3][2 * lane]);
+    const float o1 = (s_acc[0][2 * lane + 1] + s_acc[1][2 * lane + 1]) + (s_acc[2][2 * lane + 1] + s_acc[3][2 * lane + 1]);
+    reinterpret_cast<uint32_t*>(p.dq + static_cast<size_t>(b) * D + h * kDh)[lane] = pack_bf16(o0, o1);
+  }
 }
 
 static uint32_t drop_threshold(float p) {
@@ -319,7 +344,7 @@ extern "C" int tt_attn_lastq_fwd(const void* q, const void* qkv, const int32_t* 
   TT_REQUIRE(ctx, "tt_attn_lastq_fwd: null ctx");
   p.ctx = static_cast<__nv_bfloat16*>(ctx);
   p.lse = lse;
-  attn_lastq_fwd_kernel<<<(B * H + 3) / 4, 128, 0, stream>>>(p);
+  attn_lastq_fwd_kernel<<<B * H, 128, 0, stream>>>(p);
   TT_LAUNCH_CHECK();
   return TT_OK;
 }
@@ -337,7 +362,7 @@ extern "C" int tt_attn_lastq_bwd(const void* q, const void* qkv, const int32_t* 
   p.lse = const_cast<float*>(lse);
   p.dq = static_cast<__nv_bfloat16*>(dq);
   p.dqkv = static_cast<__nv_bfloat16*>(dqkv);
-  attn_lastq_bwd_kernel<<<(B * H + 3) / 4, 128, 0, stream>>>(p);
+  attn_lastq_bwd_kernel<<<B * H, 128, 0, stream>>>(p);
   TT_LAUNCH_CHECK();
   return TT_OK;
 }

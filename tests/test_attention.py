@@ -42,7 +42,7 @@ def test_attn_fwd(B, L, H):
     assert lerr <= 2e-3, f"lse err {lerr}"
 
 
-@pytest.mark.parametrize("B,L,H", [(2, 128, 4), (3, 200, 4), (2, 50, 4), (2, 256, 4)])
+@pytest.mark.parametrize("B,L,H", [(2, 128, 4), (3, 200, 4), (2, 50, 4), (2, 256, 4), (2, 300, 4), (1, 512, 4)])
 def test_attn_bwd(B, L, H):
     from mrm_b200 import ops
     g = torch.Generator().manual_seed(100 + L)
