@@ -279,3 +279,30 @@ def test_lastq_attention_matches_torch():
         assert (dv[:n] - v.grad).abs().max().item() < 3e-2 * max(1.0, v.grad.abs().max().item())
         assert dk[n:].abs().max().item() == 0.0 if n < L else True
         assert dv[n:].abs().max().item() == 0.0 if n < L else True
+
+
+def test_seq512_training_step_matches_oracle():
+    """BASELINE config 5's sequence length (L = 512, four attention tiles, LONG backward layout)."""
+    from mrm_b200 import synthetic
+    from mrm_b200.engine import TwoTowerEngine
+    from oracle import two_tower_oracle as oracle
+    cfg = synthetic.TwoTowerConfig(vocab_size=3001, max_seq_len=512, dropout=0.0)
+    sd = synthetic.make_state_dict(cfg, seed=12)
+    batch = synthetic.make_batch(cfg, 6, seed=13)
+    batch["history_ids"][0, :] = torch.randint(1, 3001, (512,))      # one full-length history
+    batch["history_mask"][0, :] = 1
+    eng = TwoTowerEngine(cfg)
+    eng.load_state_dict(sd)
+    loss, _, u, i = eng.forward({k: v.cuda() for k, v in batch.items()}, training=True)
+    eng.backward()
+    torch.cuda.synchronize()
+    ref_loss, _, ref_u, ref_i, grads, _ = oracle.loss_and_grads(sd, batch, cfg.temperature, cfg.num_heads)
+    assert abs(loss.item() - ref_loss.item()) <= 2e-2
+    assert (u.cpu() - ref_u).abs().max().item() <= 1e-2
+    for k in ("user_tower.transformer_encoder.layers.0.self_attn.in_proj_weight",
+              "user_tower.transformer_encoder.layers.0.linear1.weight",
+              "user_tower.transformer_encoder.layers.1.self_attn.in_proj_weight",
+              "user_tower.position_embedding.weight", "user_tower.item_embedding.weight"):
+        ref = grads[k]
+        err = (eng.g[k].cpu() - ref).norm().item()
+        assert err <= 0.15 * ref.norm().item() + 5e-5 * ref.numel() ** 0.5, (k, err, ref.norm().item())
