@@ -208,14 +208,15 @@ class TwoTowerEngine:
         ws["in"] = torch.empty(B, D, **f32)
         ws["in_bf"] = torch.empty(B, D, **bf)
         # loss
-        ws["S"] = torch.empty(B, B, **f32)
-        ws["S2"] = torch.empty(B, B, **f32)
+        Bp = (B + 7) // 8 * 8                      # leading dimensions padded for 16-byte rows
+        ws["S"] = torch.empty(B, Bp, **f32)[:, :B]
+        ws["S2"] = torch.empty(B, Bp, **f32)[:, :B]
         for k in ("lse_r", "pos_r", "lse_c", "pos_c"):
             ws[k] = torch.empty(B, **f32)
         ws["loss"] = torch.zeros((), **f32)
         # backward
-        ws["dS"] = torch.empty(B, B, **bf)
-        ws["dS2"] = torch.empty(B, B, **bf)
+        ws["dS"] = torch.zeros(B, Bp, **bf)[:, :B]
+        ws["dS2"] = torch.zeros(B, Bp, **bf)[:, :B]
         ws["dun"] = torch.empty(B, D, **f32)
         ws["din"] = torch.empty(B, D, **f32)
         ws["du_bf"] = torch.empty(B, D, **bf)
@@ -423,9 +424,10 @@ class TwoTowerEngine:
                 "U_all": torch.empty(G * B, D, device=dev, dtype=torch.bfloat16),
                 "I_all": torch.empty(G * B, D, device=dev, dtype=torch.bfloat16),
                 "uid_all": torch.zeros(G * B, device=dev, dtype=torch.long),
-                "S": torch.empty(B, G * B, device=dev), "S2": torch.empty(B, G * B, device=dev),
-                "dS": torch.empty(B, G * B, device=dev, dtype=torch.bfloat16),
-                "dS2": torch.empty(B, G * B, device=dev, dtype=torch.bfloat16),
+                "S": torch.empty(B, (G * B + 7) // 8 * 8, device=dev)[:, :G * B],
+                "S2": torch.empty(B, (G * B + 7) // 8 * 8, device=dev)[:, :G * B],
+                "dS": torch.zeros(B, (G * B + 7) // 8 * 8, device=dev, dtype=torch.bfloat16)[:, :G * B],
+                "dS2": torch.zeros(B, (G * B + 7) // 8 * 8, device=dev, dtype=torch.bfloat16)[:, :G * B],
                 "lse_r_all": torch.empty(G * B, device=dev), "lse_c_all": torch.empty(G * B, device=dev),
             }
         return ws[key]
