@@ -462,6 +462,8 @@ class TwoTowerEngine:
     def forward_towers(self, batch: Dict[str, torch.Tensor], training: bool = True):
         ids = batch["history_ids"]
         B, L = ids.shape
+        if B % 4 != 0:
+            raise ValueError(f"batch size {B}: the InfoNCE logit tiles need a multiple of 4 (16-byte fp32 rows)")
         ws = self.workspace(B, L)
         if not self.shadow_valid:
             self.refresh_shadow()

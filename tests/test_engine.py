@@ -288,7 +288,7 @@ def test_seq512_training_step_matches_oracle():
     from oracle import two_tower_oracle as oracle
     cfg = synthetic.TwoTowerConfig(vocab_size=3001, max_seq_len=512, dropout=0.0)
     sd = synthetic.make_state_dict(cfg, seed=12)
-    batch = synthetic.make_batch(cfg, 6, seed=13)
+    batch = synthetic.make_batch(cfg, 8, seed=13)
     batch["history_ids"][0, :] = torch.randint(1, 3001, (512,))      # one full-length history
     batch["history_mask"][0, :] = 1
     eng = TwoTowerEngine(cfg)
