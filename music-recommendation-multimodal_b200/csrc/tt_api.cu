@@ -3,6 +3,7 @@
 // has no link-time dependency on libcuda), device properties.
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "../../include/tt_b200.h"
@@ -80,6 +81,15 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t*
     return TT_ERR_CUDA;
   }
   return TT_OK;
+}
+
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("TT_NO_PDL");
+    v = (e && atoi(e) != 0) ? 0 : 1;
+  }
+  return v == 1;
 }
 
 int num_sms() {

@@ -102,6 +102,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // The trigger comes AFTER this CTA owns its TMEM columns: a dependent CTA scheduled early on the same
+  // SM could otherwise take them first and wait forever for this grid to finish.
+  pdl_launch_dependents();
+  pdl_wait();   // prologue (barriers, TMEM, tensor-map prefetch) overlapped the previous kernel's tail
 
   const int seq_row0 = b * p.L;
   const int q_row0 = seq_row0 + qt * kTile;
@@ -371,6 +375,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // The trigger comes AFTER this CTA owns its TMEM columns: a dependent CTA scheduled early on the same
+  // SM could otherwise take them first and wait forever for this grid to finish.
+  pdl_launch_dependents();
+  pdl_wait();   // prologue (barriers, TMEM, tensor-map prefetch) overlapped the previous kernel's tail
   const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
   constexpr uint32_t T_S = 0, T_DP = LONG ? 0 : 128, T_DV = LONG ? 128 : 256, T_DK = LONG ? 192 : 320,
                      T_DQ = LONG ? 256 : 384;
@@ -732,7 +740,7 @@ extern "C" int tt_attn_causal_fwd(const void* qkv, void* ctx, float* lse, int B,
     configured = true;
   }
   TT_REQUIRE(smem <= 232448, "tt_attn_causal_fwd: shared memory %zu too large", smem);
-  attn_fwd_kernel<<<B * H * p.nq, 256, smem, stream>>>(tm, p);
+  TT_CHECK_CUDA(launch_k(attn_fwd_kernel, dim3(B * H * p.nq), dim3(256), smem, stream, tm, p));
   TT_LAUNCH_CHECK();
   return TT_OK;
 }
@@ -774,8 +782,8 @@ extern "C" int tt_attn_causal_bwd(const void* qkv, const void* ctx, const void* 
     configured = true;
   }
   TT_REQUIRE(smem <= 232448, "tt_attn_causal_bwd: shared memory %zu too large", smem);
-  if (p.nq <= 2) attn_bwd_kernel<false><<<B * H, 256, smem, stream>>>(tmQ, tmDO, p);
-  else attn_bwd_kernel<true><<<B * H, 256, smem, stream>>>(tmQ, tmDO, p);
+  if (p.nq <= 2) TT_CHECK_CUDA(launch_k(attn_bwd_kernel<false>, dim3(B * H), dim3(256), smem, stream, tmQ, tmDO, p));
+  else TT_CHECK_CUDA(launch_k(attn_bwd_kernel<true>, dim3(B * H), dim3(256), smem, stream, tmQ, tmDO, p));
   TT_LAUNCH_CHECK();
   return TT_OK;
 }

@@ -50,6 +50,37 @@ int num_sms();
 
 #ifdef __CUDACC__
 // ----------------------------------------------------------------------------
+// Programmatic dependent launch (PDL). Every kernel of the library
+//   * signals `launch_dependents` as its first instruction, so the NEXT kernel of the stream (or
+//     graph branch) may be scheduled while this one is still running, and
+//   * executes `griddepcontrol.wait` before its first global-memory access; the wait returns only
+//     when the previous kernel has completed and its writes are visible.
+// What overlaps with the predecessor is therefore only launch latency and the prologue (barrier
+// init, TMEM allocation, tensor-map prefetch) — semantics stay those of a serialized stream.
+// TT_NO_PDL=1 launches without the attribute (the two instructions are then no-ops).
+// ----------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+bool pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                            Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
+// ----------------------------------------------------------------------------
 // Small device utilities
 // ----------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {

@@ -246,6 +246,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // The trigger comes AFTER this CTA owns its TMEM columns: a dependent CTA scheduled early on the same
+  // SM could otherwise take them first and wait forever for this grid to finish.
+  pdl_launch_dependents();
+  pdl_wait();   // prologue (barriers, TMEM, tensor-map prefetch) overlapped the previous kernel's tail
 
   const int tiles_m = (p.M + kBlockM - 1) / kBlockM;
   const int tiles_n = (p.N + block_n - 1) / block_n;
@@ -402,7 +406,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
     configured = true;
   }
   TT_REQUIRE(smem <= 232448, "tt_gemm_bf16: %zu B of shared memory requested", smem);
-  gemm_bf16_kernel<A_MN, B_MN><<<grid, kGemmThreads, smem, stream>>>(tmA, tmB, p);
+  TT_CHECK_CUDA(launch_k(gemm_bf16_kernel<A_MN, B_MN>, dim3(grid), dim3(kGemmThreads), smem, stream, tmA, tmB, p));
   TT_LAUNCH_CHECK();
   return TT_OK;
 }

@@ -23,6 +23,8 @@ static constexpr float kLog2e = 1.4426950408889634f;
 __global__ void gather_rows_kernel(const float* __restrict__ x32, const __nv_bfloat16* __restrict__ x16,
                                    const int32_t* __restrict__ last_idx, int B, int L, int W,
                                    float* __restrict__ out32, __nv_bfloat16* __restrict__ out16) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (b >= B) return;
   const size_t row = static_cast<size_t>(b) * L + last_idx[b];
@@ -38,6 +40,8 @@ __global__ void gather_rows_kernel(const float* __restrict__ x32, const __nv_bfl
 
 __global__ void scatter_rows_add_kernel(const float* __restrict__ rows, const int32_t* __restrict__ last_idx, int B,
                                         int L, int W, float* __restrict__ x, int accumulate) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (b >= B) return;
   const size_t row = static_cast<size_t>(b) * L + last_idx[b];
@@ -127,6 +131,8 @@ __device__ __forceinline__ float block4_sum(float v, float* s4, int wib, int lan
 }
 
 __global__ void __launch_bounds__(128) attn_lastq_fwd_kernel(const LastQParams p) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float s_p[kMaxL];
   __shared__ float s_acc[4][64];
   __shared__ float s4[4];
@@ -195,6 +201,8 @@ __global__ void __launch_bounds__(128) attn_lastq_fwd_kernel(const LastQParams p
 }
 
 __global__ void __launch_bounds__(128) attn_lastq_bwd_kernel(const LastQParams p) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float s_ds[kMaxL];
   __shared__ float s_acc[4][64];
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -301,9 +309,7 @@ extern "C" int tt_gather_rows(const float* x_f32, const void* x_bf16, const int3
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   TT_REQUIRE(last_idx && B > 0 && L > 0 && W > 0 && W % 4 == 0, "tt_gather_rows: bad arguments");
   TT_REQUIRE((x_f32 && out_f32) || (x_bf16 && out_bf16), "tt_gather_rows: nothing to gather");
-  gather_rows_kernel<<<(B * 32 + 255) / 256, 256, 0, stream>>>(x_f32, static_cast<const __nv_bfloat16*>(x_bf16),
-                                                              last_idx, B, L, W, out_f32,
-                                                              static_cast<__nv_bfloat16*>(out_bf16));
+  TT_CHECK_CUDA(launch_k(gather_rows_kernel, dim3((B * 32 + 255) / 256), dim3(256), 0, stream, x_f32, static_cast<const __nv_bfloat16*>(x_bf16), last_idx, B, L, W, out_f32, static_cast<__nv_bfloat16*>(out_bf16)));
   TT_LAUNCH_CHECK();
   return TT_OK;
 }
@@ -312,7 +318,7 @@ extern "C" int tt_scatter_rows_add(const float* rows, const int32_t* last_idx, i
                                    int accumulate, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   TT_REQUIRE(rows && last_idx && x && B > 0 && L > 0 && W > 0 && W % 4 == 0, "tt_scatter_rows_add: bad arguments");
-  scatter_rows_add_kernel<<<(B * 32 + 255) / 256, 256, 0, stream>>>(rows, last_idx, B, L, W, x, accumulate);
+  TT_CHECK_CUDA(launch_k(scatter_rows_add_kernel, dim3((B * 32 + 255) / 256), dim3(256), 0, stream, rows, last_idx, B, L, W, x, accumulate));
   TT_LAUNCH_CHECK();
   return TT_OK;
 }
@@ -344,7 +350,7 @@ extern "C" int tt_attn_lastq_fwd(const void* q, const void* qkv, const int32_t* 
   TT_REQUIRE(ctx, "tt_attn_lastq_fwd: null ctx");
   p.ctx = static_cast<__nv_bfloat16*>(ctx);
   p.lse = lse;
-  attn_lastq_fwd_kernel<<<B * H, 128, 0, stream>>>(p);
+  TT_CHECK_CUDA(launch_k(attn_lastq_fwd_kernel, dim3(B * H), dim3(128), 0, stream, p));
   TT_LAUNCH_CHECK();
   return TT_OK;
 }
@@ -362,7 +368,7 @@ extern "C" int tt_attn_lastq_bwd(const void* q, const void* qkv, const int32_t* 
   p.lse = const_cast<float*>(lse);
   p.dq = static_cast<__nv_bfloat16*>(dq);
   p.dqkv = static_cast<__nv_bfloat16*>(dqkv);
-  attn_lastq_bwd_kernel<<<B * H, 128, 0, stream>>>(p);
+  TT_CHECK_CUDA(launch_k(attn_lastq_bwd_kernel, dim3(B * H), dim3(128), 0, stream, p));
   TT_LAUNCH_CHECK();
   return TT_OK;
 }

@@ -18,6 +18,8 @@ __global__ void __launch_bounds__(256) infonce_rows_kernel(float* __restrict__ S
                                                            const int64_t* __restrict__ uid_rows,
                                                            const int64_t* __restrict__ uid_cols, int pos0,
                                                            float* __restrict__ row_lse, float* __restrict__ pos_logit) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (row >= R) return;
   float* s = S + static_cast<size_t>(row) * ld;
@@ -56,6 +58,8 @@ __global__ void __launch_bounds__(256) infonce_grad_kernel(const float* __restri
                                                            const float* __restrict__ row_lse,
                                                            const float* __restrict__ col_lse, int pos0, float coef,
                                                            __nv_bfloat16* __restrict__ dS, int ld_d) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int row = blockIdx.y;
   const int j = (blockIdx.x * blockDim.x + threadIdx.x) * 2;
   if (j >= C) return;
@@ -84,6 +88,8 @@ __global__ void __launch_bounds__(256) infonce_grad_kernel(const float* __restri
 // loss = coef * ( sum_i (lse_a[i] - pos_a[i]) + sum_i (lse_b[i] - pos_b[i]) ); single block, deterministic.
 __global__ void __launch_bounds__(256) infonce_loss_kernel(const float* lse_a, const float* pos_a, const float* lse_b,
                                                            const float* pos_b, int R, float coef, float* loss) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float s[256];
   float acc = 0.f;
   for (int i = threadIdx.x; i < R; i += 256) acc += (lse_a[i] - pos_a[i]) + (lse_b[i] - pos_b[i]);
@@ -106,8 +112,7 @@ extern "C" int tt_infonce_rows(float* S, int R, int C, int ld, const int64_t* ui
   TT_REQUIRE(S && row_lse && pos_logit && R > 0 && C > 0 && ld >= C, "tt_infonce_rows: bad arguments");
   TT_REQUIRE((uid_rows == nullptr) == (uid_cols == nullptr), "tt_infonce_rows: uid_rows/uid_cols come together");
   TT_REQUIRE(pos0 >= 0 && pos0 + R <= C, "tt_infonce_rows: positives [%d, %d) outside %d columns", pos0, pos0 + R, C);
-  infonce_rows_kernel<<<(R * 32 + 255) / 256, 256, 0, stream>>>(S, R, C, ld, uid_rows, uid_cols, pos0, row_lse,
-                                                                pos_logit);
+  TT_CHECK_CUDA(launch_k(infonce_rows_kernel, dim3((R * 32 + 255) / 256), dim3(256), 0, stream, S, R, C, ld, uid_rows, uid_cols, pos0, row_lse, pos_logit));
   TT_LAUNCH_CHECK();
   return TT_OK;
 }
@@ -119,8 +124,7 @@ extern "C" int tt_infonce_grad(const float* S, int R, int C, int ld, const float
   TT_REQUIRE(ld_d % 2 == 0, "tt_infonce_grad: ld_d must be even");
   dim3 grid((C / 2 + 255) / 256 + ((C / 2) % 256 == 0 && C % 2 ? 1 : 0), R);
   if (grid.x == 0) grid.x = 1;
-  infonce_grad_kernel<<<grid, 256, 0, stream>>>(S, R, C, ld, row_lse, col_lse, pos0, coef,
-                                                static_cast<__nv_bfloat16*>(dS_bf16), ld_d);
+  TT_CHECK_CUDA(launch_k(infonce_grad_kernel, dim3(grid), dim3(256), 0, stream, S, R, C, ld, row_lse, col_lse, pos0, coef, static_cast<__nv_bfloat16*>(dS_bf16), ld_d));
   TT_LAUNCH_CHECK();
   return TT_OK;
 }
@@ -129,7 +133,7 @@ extern "C" int tt_infonce_loss(const float* lse_a, const float* pos_a, const flo
                                float coef, float* loss, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   TT_REQUIRE(lse_a && pos_a && lse_b && pos_b && loss && R > 0, "tt_infonce_loss: bad arguments");
-  infonce_loss_kernel<<<1, 256, 0, stream>>>(lse_a, pos_a, lse_b, pos_b, R, coef, loss);
+  TT_CHECK_CUDA(launch_k(infonce_loss_kernel, dim3(1), dim3(256), 0, stream, lse_a, pos_a, lse_b, pos_b, R, coef, loss));
   TT_LAUNCH_CHECK();
   return TT_OK;
 }

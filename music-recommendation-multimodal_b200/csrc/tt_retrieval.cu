@@ -194,6 +194,10 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // The trigger comes AFTER this CTA owns its TMEM columns: a dependent CTA scheduled early on the same
+  // SM could otherwise take them first and wait forever for this grid to finish.
+  pdl_launch_dependents();
+  pdl_wait();   // prologue (barriers, TMEM, tensor-map prefetch) overlapped the previous kernel's tail
 
   const int units = p.n_ut * p.n_ranges;
 
@@ -330,6 +334,8 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant
 // --------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) sample_threshold_kernel(const float* __restrict__ smax, int U, int n_chunks,
                                                                int rank, unsigned long long* __restrict__ thr) {
+  pdl_launch_dependents();
+  pdl_wait();
   constexpr int kMaxPerLane = 32;   // up to 1024 chunk maxima per user
   const int u = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (u >= U) return;
@@ -398,6 +404,8 @@ __device__ __forceinline__ void bitonic_sort_desc_256(unsigned long long* keys) 
 }
 
 __global__ void __launch_bounds__(256) topk_finalize_kernel(const FinalizeParams p) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ unsigned long long s_keys[256];
   __shared__ unsigned long long s_sel[256];
   __shared__ unsigned long long s_pool[kPoolCap];
@@ -530,6 +538,8 @@ __global__ void __launch_bounds__(256) topk_finalize_kernel(const FinalizeParams
 __global__ void __launch_bounds__(256) topk_merge_kernel(const float* __restrict__ scores, const int* __restrict__ idx,
                                                          int G, int U, int K, float* __restrict__ out_score,
                                                          int* __restrict__ out_idx) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ unsigned long long s_all[];  // G*K keys
   const int u = blockIdx.x;
   const int n = G * K;
@@ -560,6 +570,8 @@ __global__ void __launch_bounds__(256) topk_merge_kernel(const float* __restrict
 __global__ void __launch_bounds__(256) exact_keys_kernel(const float* __restrict__ user, const float* __restrict__ items,
                                                          int N, int item_base, int mask_item0,
                                                          unsigned long long* __restrict__ keys) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int warps = (gridDim.x * blockDim.x) >> 5;
   float uf[8];
@@ -588,6 +600,8 @@ __global__ void __launch_bounds__(256) exact_keys_kernel(const float* __restrict
 
 __global__ void __launch_bounds__(256) exact_select_kernel(const unsigned long long* __restrict__ keys, int N, int K,
                                                            float* __restrict__ out_score, int* __restrict__ out_idx) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ unsigned long long s_keys[256];
   __shared__ int s_red[8];
   __shared__ int s_n;
@@ -632,6 +646,8 @@ __global__ void __launch_bounds__(256) exact_select_kernel(const unsigned long l
 __global__ void rank_metrics_kernel(const int* __restrict__ topk, const int64_t* __restrict__ targets, int U, int K,
                                     const int* __restrict__ k_list, int nk, const float* __restrict__ gain_table,
                                     float* __restrict__ recall, float* __restrict__ ndcg) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int u = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (u >= U) return;
   const int target = static_cast<int>(targets[u]);
@@ -714,7 +730,7 @@ static int launch_score_topk(const void* users_bf16, const void* items_bf16, Top
   }
   const int units = p.n_ut * p.n_ranges;
   const int grid = units < num_sms() ? units : num_sms();
-  score_topk_kernel<<<grid, kTopkThreads, smem, stream>>>(tmU, tmI, p);
+  TT_CHECK_CUDA(launch_k(score_topk_kernel, dim3(grid), dim3(kTopkThreads), smem, stream, tmU, tmI, p));
   TT_LAUNCH_CHECK();
   return TT_OK;
 }
@@ -750,8 +766,7 @@ extern "C" int tt_score_topk(const void* users_bf16, const void* items_bf16, int
     p.smax = static_cast<float*>(smax);
     int rc = launch_score_topk(users_bf16, items_bf16, p, plan->N, stream);
     if (rc) return rc;
-    sample_threshold_kernel<<<(plan->U * 32 + 255) / 256, 256, 0, stream>>>(p.smax, plan->U, sample_tiles * 4,
-                                                                           plan->sample_rank, p.thr);
+    TT_CHECK_CUDA(launch_k(sample_threshold_kernel, dim3((plan->U * 32 + 255) / 256), dim3(256), 0, stream, p.smax, plan->U, sample_tiles * 4, plan->sample_rank, p.thr));
     TT_LAUNCH_CHECK();
     p.total_tiles = total_saved;
     p.smax = nullptr;
@@ -775,7 +790,7 @@ extern "C" int tt_topk_finalize(const tt_topk_plan* plan, const void* cand, cons
   p.cand = static_cast<const unsigned long long*>(cand);
   p.cand_cnt = cand_cnt; p.thr = static_cast<const unsigned long long*>(thr); p.users = users_f32; p.items = items_f32; p.eps = eps;
   p.out_idx = out_idx; p.out_score = out_score; p.flags = flags;
-  topk_finalize_kernel<<<plan->U, 256, 0, stream>>>(p);
+  TT_CHECK_CUDA(launch_k(topk_finalize_kernel, dim3(plan->U), dim3(256), 0, stream, p));
   TT_LAUNCH_CHECK();
   return TT_OK;
 }
@@ -785,7 +800,7 @@ extern "C" int tt_topk_merge(const float* scores, const int32_t* idx, int G, int
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   TT_REQUIRE(scores && idx && out_score && out_idx && G > 0 && U > 0 && K > 0, "tt_topk_merge: bad arguments");
   TT_REQUIRE(G * K <= 4096, "tt_topk_merge: G*K = %d too large", G * K);
-  topk_merge_kernel<<<U, 256, static_cast<size_t>(G) * K * 8, stream>>>(scores, idx, G, U, K, out_score, out_idx);
+  TT_CHECK_CUDA(launch_k(topk_merge_kernel, dim3(U), dim3(256), static_cast<size_t>(G) * K * 8, stream, scores, idx, G, U, K, out_score, out_idx));
   TT_LAUNCH_CHECK();
   return TT_OK;
 }
@@ -797,11 +812,9 @@ extern "C" int tt_exact_topk(const float* user_f32, const float* items_f32, int 
              "tt_exact_topk: bad arguments");
   int grid = (N + 7) / 8;
   if (grid > num_sms() * 8) grid = num_sms() * 8;
-  exact_keys_kernel<<<grid, 256, 0, stream>>>(user_f32, items_f32, N, item_base, mask_item0,
-                                              static_cast<unsigned long long*>(key_scratch));
+  TT_CHECK_CUDA(launch_k(exact_keys_kernel, dim3(grid), dim3(256), 0, stream, user_f32, items_f32, N, item_base, mask_item0, static_cast<unsigned long long*>(key_scratch)));
   TT_LAUNCH_CHECK();
-  exact_select_kernel<<<1, 256, 0, stream>>>(static_cast<const unsigned long long*>(key_scratch), N, K, out_score,
-                                             out_idx);
+  TT_CHECK_CUDA(launch_k(exact_select_kernel, dim3(1), dim3(256), 0, stream, static_cast<const unsigned long long*>(key_scratch), N, K, out_score, out_idx));
   TT_LAUNCH_CHECK();
   return TT_OK;
 }
@@ -811,8 +824,7 @@ extern "C" int tt_rank_metrics(const int32_t* topk_idx, const int64_t* targets, 
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   TT_REQUIRE(topk_idx && targets && k_list && gain_table && recall && ndcg && U > 0 && K > 0 && nk > 0,
              "tt_rank_metrics: bad arguments");
-  rank_metrics_kernel<<<(U * 32 + 255) / 256, 256, 0, stream>>>(topk_idx, targets, U, K, k_list, nk, gain_table,
-                                                               recall, ndcg);
+  TT_CHECK_CUDA(launch_k(rank_metrics_kernel, dim3((U * 32 + 255) / 256), dim3(256), 0, stream, topk_idx, targets, U, K, k_list, nk, gain_table, recall, ndcg));
   TT_LAUNCH_CHECK();
   return TT_OK;
 }

@@ -95,6 +95,8 @@ static uint32_t drop_threshold(float p) {
 // fp32 -> bf16 cast (dense weight shadow copies), grid-stride, 16 B in / 8 B out per thread-step
 // --------------------------------------------------------------------------------------------
 __global__ void cast_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, size_t n4) {
+  pdl_launch_dependents();
+  pdl_wait();
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n4;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
     const float4 x = __ldg(reinterpret_cast<const float4*>(src) + i);
@@ -110,6 +112,8 @@ __global__ void cast_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* _
 // --------------------------------------------------------------------------------------------
 __global__ void last_index_kernel(const int64_t* __restrict__ ids, const int64_t* __restrict__ mask, int B, int L,
                                   int32_t* __restrict__ last_idx) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= B) return;
   int cnt = 0;
@@ -139,6 +143,8 @@ struct EmbedParams {
 };
 
 __global__ void __launch_bounds__(kRowThreads) embed_ln_fwd_kernel(const EmbedParams p) {
+  pdl_launch_dependents();
+  pdl_wait();
   constexpr int NV = 2;
   const int lane = threadIdx.x & 31;
   const int warps_total = (gridDim.x * blockDim.x) >> 5;
@@ -194,6 +200,8 @@ struct ChainParams {
 
 template <int NV>
 __global__ void __launch_bounds__(kRowThreads) chain_fwd_kernel(const ChainParams p) {
+  pdl_launch_dependents();
+  pdl_wait();
   constexpr int W = 128 * NV, E = 4 * NV;
   const int lane = threadIdx.x & 31;
   const int warps_total = (gridDim.x * blockDim.x) >> 5;
@@ -231,6 +239,8 @@ __global__ void __launch_bounds__(kRowThreads) chain_fwd_kernel(const ChainParam
 // dout -> [L2 bwd] -> [dropout] -> [ReLU] -> [LN bwd] -> (+resid) -> dx.
 template <int NV>
 __global__ void __launch_bounds__(kRowThreads) chain_bwd_kernel(const ChainParams p) {
+  pdl_launch_dependents();
+  pdl_wait();
   constexpr int W = 128 * NV, E = 4 * NV;
   __shared__ float s_red[3][kRowThreads / 32][W];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -341,6 +351,8 @@ __global__ void gather_cat_kernel(const float* __restrict__ x, const int32_t* __
                                   const int64_t* __restrict__ gender, const int64_t* __restrict__ country,
                                   const float* __restrict__ G, const float* __restrict__ C, int B, int L,
                                   __nv_bfloat16* __restrict__ cat) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (b >= B) return;
   const float* row = x + (static_cast<size_t>(b) * L + last_idx[b]) * 256;
@@ -359,6 +371,8 @@ __global__ void gather_cat_bwd_kernel(const float* __restrict__ dcat, const int3
                                       const int64_t* __restrict__ gender, const int64_t* __restrict__ country,
                                       int B, int L, float* __restrict__ dx, __nv_bfloat16* __restrict__ dx_bf16,
                                       float* __restrict__ dG, float* __restrict__ dC) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (b >= B) return;
   const float* g = dcat + static_cast<size_t>(b) * 304;
@@ -377,6 +391,8 @@ __global__ void gather_cat_bwd_kernel(const float* __restrict__ dcat, const int3
 // --------------------------------------------------------------------------------------------
 __global__ void concat4_kernel(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ c,
                                const float* __restrict__ d, int B, int m, __nv_bfloat16* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();
   const size_t n = static_cast<size_t>(B) * 4 * m;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
@@ -418,6 +434,8 @@ __device__ __forceinline__ float block_col_reduce(float v, float (*s)[33]) {
 }
 
 __global__ void __launch_bounds__(256) bn_fwd_kernel(const BnParams p) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float s[8][33];
   const int c = blockIdx.x * 32 + threadIdx.x;
   const bool active = c < p.C;
@@ -454,6 +472,8 @@ __global__ void __launch_bounds__(256) bn_fwd_kernel(const BnParams p) {
 }
 
 __global__ void __launch_bounds__(256) bn_bwd_kernel(const BnParams p) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float s[8][33];
   const int c = blockIdx.x * 32 + threadIdx.x;
   const bool active = c < p.C;
@@ -508,6 +528,8 @@ __global__ void __launch_bounds__(256) bn_bwd_kernel(const BnParams p) {
 // --------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* __restrict__ x, int R, int N, int ld,
                                                           float* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int c2 = (blockIdx.x * blockDim.x + threadIdx.x) * 2;  // two adjacent columns per thread
   if (c2 >= N) return;
   const int rows_per = (R + gridDim.y - 1) / gridDim.y;
@@ -538,6 +560,8 @@ struct EmbedBwdParams {
 };
 
 __global__ void __launch_bounds__(kRowThreads) embed_ln_bwd_kernel(const EmbedBwdParams p) {
+  pdl_launch_dependents();
+  pdl_wait();
   constexpr int NV = 2, E_ = 8, W = 256;
   __shared__ float s_red[3][kRowThreads / 32][W];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -612,6 +636,8 @@ __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, float
                                                     float beta2, float eps, float wd, const int64_t* step_dev,
                                                     __nv_bfloat16* __restrict__ shadow, size_t shadow_begin4,
                                                     size_t shadow_end4, int zero_grad) {
+  pdl_launch_dependents();
+  pdl_wait();
   const float step = static_cast<float>(*step_dev);
   const float bc1 = 1.f - powf(beta1, step);
   const float bc2_sqrt = sqrtf(1.f - powf(beta2, step));
@@ -649,6 +675,8 @@ __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, float
 }
 
 __global__ void increment_kernel(int64_t* a, uint64_t* b) {
+  pdl_launch_dependents();
+  pdl_wait();
   if (a) *a += 1;
   if (b) *b += 0x9E3779B97F4A7C15ULL;
 }
@@ -669,7 +697,7 @@ extern "C" int tt_cast_bf16(const float* src, void* dst, int64_t n, void* stream
   const size_t n4 = static_cast<size_t>(n / 4);
   int grid = static_cast<int>((n4 + 255) / 256);
   if (grid > num_sms() * 8) grid = num_sms() * 8;
-  cast_bf16_kernel<<<grid, 256, 0, stream>>>(src, static_cast<__nv_bfloat16*>(dst), n4);
+  TT_CHECK_CUDA(launch_k(cast_bf16_kernel, dim3(grid), dim3(256), 0, stream, src, static_cast<__nv_bfloat16*>(dst), n4));
   TT_LAUNCH_CHECK();
   return TT_OK;
 }
@@ -677,7 +705,7 @@ extern "C" int tt_cast_bf16(const float* src, void* dst, int64_t n, void* stream
 extern "C" int tt_last_index(const int64_t* ids, const int64_t* mask, int B, int L, int32_t* last_idx, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   TT_REQUIRE((ids || mask) && last_idx && B > 0 && L > 0, "tt_last_index: bad arguments");
-  last_index_kernel<<<(B * 32 + 255) / 256, 256, 0, stream>>>(ids, mask, B, L, last_idx);
+  TT_CHECK_CUDA(launch_k(last_index_kernel, dim3((B * 32 + 255) / 256), dim3(256), 0, stream, ids, mask, B, L, last_idx));
   TT_LAUNCH_CHECK();
   return TT_OK;
 }
@@ -696,7 +724,7 @@ extern "C" int tt_embed_ln_fwd(const int64_t* ids, const float* E, const float* 
   p.drop_scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
   p.seed = seed; p.seed_dev = seed_dev; p.site = site;
   p.x0 = x0; p.h = static_cast<__nv_bfloat16*>(h_bf16);
-  embed_ln_fwd_kernel<<<row_grid(p.T), kRowThreads, 0, stream>>>(p);
+  TT_CHECK_CUDA(launch_k(embed_ln_fwd_kernel, dim3(row_grid(p.T)), dim3(kRowThreads), 0, stream, p));
   TT_LAUNCH_CHECK();
   return TT_OK;
 }
@@ -713,7 +741,7 @@ extern "C" int tt_embed_ln_bwd(const int64_t* ids, const float* E, const float* 
   p.drop_scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
   p.seed = seed; p.seed_dev = seed_dev; p.site = site;
   p.dE = dE; p.dP = dP; p.dgamma = dgamma; p.dbeta = dbeta;
-  embed_ln_bwd_kernel<<<L, kRowThreads, 0, stream>>>(p);
+  TT_CHECK_CUDA(launch_k(embed_ln_bwd_kernel, dim3(L), dim3(kRowThreads), 0, stream, p));
   TT_LAUNCH_CHECK();
   return TT_OK;
 }
@@ -745,8 +773,8 @@ extern "C" int tt_chain_fwd(const tt_chain_args* a, void* stream_) {
   int rc = fill_chain(p, a, "tt_chain_fwd");
   if (rc) return rc;
   TT_REQUIRE(p.out_f32 || p.out_bf16, "tt_chain_fwd: no output");
-  if (a->width == 256) chain_fwd_kernel<2><<<row_grid(p.R), kRowThreads, 0, stream>>>(p);
-  else chain_fwd_kernel<4><<<row_grid(p.R), kRowThreads, 0, stream>>>(p);
+  if (a->width == 256) TT_CHECK_CUDA(launch_k(chain_fwd_kernel<2>, dim3(row_grid(p.R)), dim3(kRowThreads), 0, stream, p));
+  else TT_CHECK_CUDA(launch_k(chain_fwd_kernel<4>, dim3(row_grid(p.R)), dim3(kRowThreads), 0, stream, p));
   TT_LAUNCH_CHECK();
   return TT_OK;
 }
@@ -761,7 +789,7 @@ extern "C" int tt_chain_bwd(const tt_chain_args* a, void* stream_) {
   TT_REQUIRE(a->width == 256, "tt_chain_bwd: width %d unsupported (256)", a->width);
   int grid = row_grid(p.R);
   if (grid > num_sms() * 2) grid = num_sms() * 2;  // bounds the per-block atomic combine
-  chain_bwd_kernel<2><<<grid, kRowThreads, 0, stream>>>(p);
+  TT_CHECK_CUDA(launch_k(chain_bwd_kernel<2>, dim3(grid), dim3(kRowThreads), 0, stream, p));
   TT_LAUNCH_CHECK();
   return TT_OK;
 }
@@ -771,8 +799,7 @@ extern "C" int tt_gather_cat_fwd(const float* x, const int32_t* last_idx, const 
                                  void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   TT_REQUIRE(x && last_idx && G && C && cat && B > 0, "tt_gather_cat_fwd: bad arguments");
-  gather_cat_kernel<<<(B * 32 + 255) / 256, 256, 0, stream>>>(x, last_idx, gender, country, G, C, B, L,
-                                                             static_cast<__nv_bfloat16*>(cat));
+  TT_CHECK_CUDA(launch_k(gather_cat_kernel, dim3((B * 32 + 255) / 256), dim3(256), 0, stream, x, last_idx, gender, country, G, C, B, L, static_cast<__nv_bfloat16*>(cat)));
   TT_LAUNCH_CHECK();
   return TT_OK;
 }
@@ -782,8 +809,7 @@ extern "C" int tt_gather_cat_bwd(const float* dcat, const int32_t* last_idx, con
                                  void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   TT_REQUIRE(dcat && last_idx && dG && dC && (dx || dx_bf16) && B > 0, "tt_gather_cat_bwd: bad arguments");
-  gather_cat_bwd_kernel<<<(B * 32 + 255) / 256, 256, 0, stream>>>(dcat, last_idx, gender, country, B, L, dx,
-                                                                 static_cast<__nv_bfloat16*>(dx_bf16), dG, dC);
+  TT_CHECK_CUDA(launch_k(gather_cat_bwd_kernel, dim3((B * 32 + 255) / 256), dim3(256), 0, stream, dcat, last_idx, gender, country, B, L, dx, static_cast<__nv_bfloat16*>(dx_bf16), dG, dC));
   TT_LAUNCH_CHECK();
   return TT_OK;
 }
@@ -795,7 +821,7 @@ extern "C" int tt_concat4_bf16(const float* a, const float* b, const float* c, c
   const size_t n = static_cast<size_t>(B) * 4 * m;
   int grid = static_cast<int>((n + 255) / 256);
   if (grid > num_sms() * 8) grid = num_sms() * 8;
-  concat4_kernel<<<grid, 256, 0, stream>>>(a, b, c, d, B, m, static_cast<__nv_bfloat16*>(out));
+  TT_CHECK_CUDA(launch_k(concat4_kernel, dim3(grid), dim3(256), 0, stream, a, b, c, d, B, m, static_cast<__nv_bfloat16*>(out)));
   TT_LAUNCH_CHECK();
   return TT_OK;
 }
@@ -823,7 +849,7 @@ extern "C" int tt_bn_relu_fwd(const tt_bn_args* a, void* stream_) {
   if (rc) return rc;
   TT_REQUIRE(p.out && p.running_mean && p.running_var, "tt_bn_relu_fwd: missing output or running stats");
   TT_REQUIRE(!p.training || (p.save_mean && p.save_rstd), "tt_bn_relu_fwd: training needs save_mean/save_rstd");
-  bn_fwd_kernel<<<(p.C + 31) / 32, dim3(32, 8), 0, stream>>>(p);
+  TT_CHECK_CUDA(launch_k(bn_fwd_kernel, dim3((p.C + 31) / 32), dim3(dim3(32, 8)), 0, stream, p));
   TT_LAUNCH_CHECK();
   return TT_OK;
 }
@@ -834,7 +860,7 @@ extern "C" int tt_bn_relu_bwd(const tt_bn_args* a, void* stream_) {
   int rc = fill_bn(p, a, "tt_bn_relu_bwd");
   if (rc) return rc;
   TT_REQUIRE(p.dout && p.dy && p.dgamma && p.dbeta && p.save_mean && p.save_rstd, "tt_bn_relu_bwd: missing buffers");
-  bn_bwd_kernel<<<(p.C + 31) / 32, dim3(32, 8), 0, stream>>>(p);
+  TT_CHECK_CUDA(launch_k(bn_bwd_kernel, dim3((p.C + 31) / 32), dim3(dim3(32, 8)), 0, stream, p));
   TT_LAUNCH_CHECK();
   return TT_OK;
 }
@@ -846,7 +872,7 @@ extern "C" int tt_colsum_bf16(const void* x, int R, int N, int ld, float* out, v
   int gy = (num_sms() * 4) / gx;
   if (gy < 1) gy = 1;
   if (gy > (R + 63) / 64) gy = (R + 63) / 64;
-  colsum_bf16_kernel<<<dim3(gx, gy), 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(x), R, N, ld, out);
+  TT_CHECK_CUDA(launch_k(colsum_bf16_kernel, dim3(dim3(gx, gy)), dim3(256), 0, stream, static_cast<const __nv_bfloat16*>(x), R, N, ld, out));
   TT_LAUNCH_CHECK();
   return TT_OK;
 }
@@ -861,16 +887,14 @@ extern "C" int tt_adamw_step(float* p, float* g, float* m, float* v, int64_t n, 
   const size_t n4 = static_cast<size_t>(n / 4);
   int grid = static_cast<int>((n4 + 255) / 256);
   if (grid > num_sms() * 16) grid = num_sms() * 16;
-  adamw_kernel<<<grid, 256, 0, stream>>>(p, g, m, v, n4, lr, beta1, beta2, eps, weight_decay, step_dev,
-                                         static_cast<__nv_bfloat16*>(shadow_bf16), static_cast<size_t>(shadow_begin / 4),
-                                         static_cast<size_t>(shadow_end / 4), zero_grad);
+  TT_CHECK_CUDA(launch_k(adamw_kernel, dim3(grid), dim3(256), 0, stream, p, g, m, v, n4, lr, beta1, beta2, eps, weight_decay, step_dev, static_cast<__nv_bfloat16*>(shadow_bf16), static_cast<size_t>(shadow_begin / 4), static_cast<size_t>(shadow_end / 4), zero_grad));
   TT_LAUNCH_CHECK();
   return TT_OK;
 }
 
 extern "C" int tt_step_counters_advance(int64_t* step_dev, uint64_t* seed_dev, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  increment_kernel<<<1, 1, 0, stream>>>(step_dev, seed_dev);
+  TT_CHECK_CUDA(launch_k(increment_kernel, dim3(1), dim3(1), 0, stream, step_dev, seed_dev));
   TT_LAUNCH_CHECK();
   return TT_OK;
 }
