@@ -86,8 +86,8 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t*
 bool pdl_enabled() {
   static int v = -1;
   if (v < 0) {
-    const char* e = getenv("TT_NO_PDL");
-    v = (e && atoi(e) != 0) ? 0 : 1;
+    const char* e = getenv("TT_PDL");   // opt-in: measured 1.576 ms (on) vs 1.528 ms (off) per c2 step on B200
+    v = (e && atoi(e) != 0) ? 1 : 0;
   }
   return v == 1;
 }
