@@ -17,6 +17,8 @@ from __future__ import annotations
 
 from typing import Dict, List, Optional, Tuple
 
+import os
+
 import torch
 
 from . import ops
@@ -125,6 +127,8 @@ class TwoTowerEngine:
         #: compute the last encoder layer's query / out_proj / FFN only for the row that is read
         #: (exact). False runs every layer on every position like the reference.
         self.prune_last_layer = True
+        #: run weight-gradient GEMMs / bias column sums on a second stream (see _wg)
+        self.overlap_wgrad = os.environ.get("TT_OVERLAP_WGRAD", "1") != "0"
 
     # ------------------------------------------------------------------ parameters
     def load_state_dict(self, sd: Dict[str, torch.Tensor]) -> None:
@@ -187,6 +191,7 @@ class TwoTowerEngine:
         ws["xout_q"] = torch.empty(B, D, **f32)
         ws["dxq"] = torch.empty(B, D, **f32)
         ws["dy_q"] = torch.empty(B, D, **bf)
+        ws["dy_q1"] = torch.empty(B, D, **bf)
         ws["dpre_q"] = torch.empty(B, FF, **bf)
         ws["dh_q"] = torch.empty(B, D, **f32)
         ws["dxmid_q"] = torch.empty(B, D, **f32)
@@ -228,11 +233,16 @@ class TwoTowerEngine:
         ws["dy1i_bf"] = torch.empty(B, cfg.fusion_hidden, **bf)
         ws["dx_a"] = torch.empty(T, D, **f32)      # gradient of the residual stream (ping)
         ws["dx_b"] = torch.empty(T, D, **f32)      # (pong)
-        ws["dy_bf"] = torch.empty(T, D, **bf)      # bf16 grad fed to the dgrad/wgrad GEMMs
+        # bf16 gradients fed to the dgrad/wgrad GEMMs: one buffer per use (the wgrad stream reads them
+        # while the main stream moves on, so nothing is recycled inside one backward pass)
+        for l in range(NL):
+            ws[f"dy2_{l}"] = torch.empty(T, D, **bf)      # grad of linear2's output (dropout-masked)
+            ws[f"dy1_{l}"] = torch.empty(T, D, **bf)      # grad of out_proj's output
+            ws[f"dqkv_{l}"] = torch.empty(T, 3 * D, **bf)
+            if l < NL - 1 or not self.prune_last_layer:
+                ws[f"dpre_{l}"] = torch.empty(T, FF, **bf)
         ws["dh"] = torch.empty(T, D, **f32)        # grad w.r.t. a LayerNorm output
-        ws["dpre"] = torch.empty(T, FF, **bf)
         ws["dctx"] = torch.empty(T, D, **bf)
-        ws["dqkv"] = torch.empty(T, 3 * D, **bf)
         self._ws[key] = ws
         return ws
 
@@ -267,6 +277,27 @@ class TwoTowerEngine:
         if getattr(self, "_side", None) is None:
             self._side = torch.cuda.Stream(device=self.device)
         return self._side
+
+    def _wgrad_stream(self) -> torch.cuda.Stream:
+        if getattr(self, "_wside", None) is None:
+            self._wside = torch.cuda.Stream(device=self.device)
+        return self._wside
+
+    def _wg(self, fn, *a, **kw) -> None:
+        """Issue a weight-gradient kernel (wgrad GEMM, bias column sum) on the wgrad stream, ordered after
+        everything issued so far on the current stream. Nothing on the critical dgrad chain depends on
+        these results before the optimizer, so they become parallel branches of the captured graph; the
+        ~25 tiny B-row wgrads then overlap the dgrad chain instead of extending it. Every buffer they read
+        is written once per backward (no reuse), so the only cross-stream hazard is the read-after-write
+        edge this helper orders."""
+        if not self.overlap_wgrad:
+            fn(*a, **kw)
+            return
+        main = torch.cuda.current_stream()
+        wst = self._wgrad_stream()
+        wst.wait_stream(main)
+        with torch.cuda.stream(wst):
+            fn(*a, **kw)
 
     def _lp(self, l: int, name: str) -> str:
         return f"user_tower.transformer_encoder.layers.{l}.{name}"
@@ -356,31 +387,33 @@ class TwoTowerEngine:
         ffn_scale = 1.0 / (1.0 - dp) if dp > 0 else 1.0
         Wqkv = w[self._lp(l, "self_attn.in_proj_weight")]
         gW, gb = g[self._lp(l, "self_attn.in_proj_weight")], g[self._lp(l, "self_attn.in_proj_bias")]
-        # --- FFN and out_proj on the B gathered rows
+        # --- FFN and out_proj on the B gathered rows (weight gradients go to the wgrad stream)
+        wg = self._wg
         ops.chain_bwd(ws["dxq"], dout=ws["dxq"], dx_bf16=ws["dy_q"], drop2_p=dp, drop2_site=_site(l, 3), seed=seed,
                       seed_dev=sdev, dx_colsum=g[self._lp(l, "linear2.bias")])
-        gemm(ws["dy_q"], ws["fq"], a_mn=True, b_mn=True, out_f32=g[self._lp(l, "linear2.weight")], accumulate=True)
+        wg(gemm, ws["dy_q"], ws["fq"], a_mn=True, b_mn=True, out_f32=g[self._lp(l, "linear2.weight")], accumulate=True)
         gemm(ws["dy_q"], w[self._lp(l, "linear2.weight")], b_mn=True, gate=ws["fq"], gate_scale=ffn_scale,
              out_bf16=ws["dpre_q"])
-        ops.colsum_bf16(ws["dpre_q"], g[self._lp(l, "linear1.bias")])
-        gemm(ws["dpre_q"], ws["h2q"], a_mn=True, b_mn=True, out_f32=g[self._lp(l, "linear1.weight")], accumulate=True)
+        wg(ops.colsum_bf16, ws["dpre_q"], g[self._lp(l, "linear1.bias")])
+        wg(gemm, ws["dpre_q"], ws["h2q"], a_mn=True, b_mn=True, out_f32=g[self._lp(l, "linear1.weight")], accumulate=True)
         gemm(ws["dpre_q"], w[self._lp(l, "linear1.weight")], b_mn=True, out_f32=ws["dh_q"])
         ops.chain_bwd(ws["xmid_q"], ln=(p[self._lp(l, "norm2.weight")], p[self._lp(l, "norm2.bias")]), dout=ws["dh_q"],
-                      resid=ws["dxq"], dx_f32=ws["dxmid_q"], dx_bf16=ws["dy_q"], drop2_p=dp, drop2_site=_site(l, 1),
+                      resid=ws["dxq"], dx_f32=ws["dxmid_q"], dx_bf16=ws["dy_q1"], drop2_p=dp, drop2_site=_site(l, 1),
                       seed=seed, seed_dev=sdev, dgamma=g[self._lp(l, "norm2.weight")],
                       dbeta=g[self._lp(l, "norm2.bias")], dx_colsum=g[self._lp(l, "self_attn.out_proj.bias")])
-        gemm(ws["dy_q"], ws["ctxq"], a_mn=True, b_mn=True, out_f32=g[self._lp(l, "self_attn.out_proj.weight")],
-             accumulate=True)
-        gemm(ws["dy_q"], w[self._lp(l, "self_attn.out_proj.weight")], b_mn=True, out_bf16=ws["dctx_q"])
+        wg(gemm, ws["dy_q1"], ws["ctxq"], a_mn=True, b_mn=True, out_f32=g[self._lp(l, "self_attn.out_proj.weight")],
+           accumulate=True)
+        gemm(ws["dy_q1"], w[self._lp(l, "self_attn.out_proj.weight")], b_mn=True, out_bf16=ws["dctx_q"])
         # --- single-query attention backward: dq (B rows), dK/dV for every position
+        dqkv = ws[f"dqkv_{l}"]
         ops.attn_lastq_bwd(ws["qq"], ws[f"qkv_{l}"], ws["last_idx"], ws["ctxq"], ws["dctx_q"], ws["lseq"], ws["dq_q"],
-                           ws["dqkv"], B, L, cfg.num_heads, drop_p=dp, seed=seed, seed_dev=sdev, site=_site(l, 0))
-        ops.colsum_bf16(ws["dq_q"], gb[:D])
-        gemm(ws["dq_q"], ws["hq"], a_mn=True, b_mn=True, out_f32=gW[:D], accumulate=True)
+                           dqkv, B, L, cfg.num_heads, drop_p=dp, seed=seed, seed_dev=sdev, site=_site(l, 0))
+        wg(ops.colsum_bf16, ws["dq_q"], gb[:D])
+        wg(gemm, ws["dq_q"], ws["hq"], a_mn=True, b_mn=True, out_f32=gW[:D], accumulate=True)
         gemm(ws["dq_q"], Wqkv[:D], b_mn=True, out_f32=ws["dhq"])
-        dkv = ws["dqkv"][:, D:]
-        ops.colsum_bf16(dkv, gb[D:])
-        gemm(dkv, ws[f"h1_{l}"], a_mn=True, b_mn=True, out_f32=gW[D:], accumulate=True)
+        dkv = dqkv[:, D:]
+        wg(ops.colsum_bf16, dkv, gb[D:])
+        wg(gemm, dkv, ws[f"h1_{l}"], a_mn=True, b_mn=True, out_f32=gW[D:], accumulate=True)
         gemm(dkv, Wqkv[D:], b_mn=True, out_f32=ws["dh"])
         ops.scatter_rows_add(ws["dhq"], ws["last_idx"], B, L, ws["dh"], accumulate=True)
         # --- residual gradient of the layer input: only the gathered rows carry one
@@ -388,7 +421,7 @@ class TwoTowerEngine:
         ops.scatter_rows_add(ws["dxmid_q"], ws["last_idx"], B, L, dx, accumulate=False)
         extra = {}
         if l > 0:
-            extra = dict(dx_bf16=ws["dy_bf"], drop2_p=dp, drop2_site=_site(l - 1, 3),
+            extra = dict(dx_bf16=ws[f"dy2_{l - 1}"], drop2_p=dp, drop2_site=_site(l - 1, 3),
                          dx_colsum=g[self._lp(l - 1, "linear2.bias")])
         ops.chain_bwd(x_in, ln=(p[self._lp(l, "norm1.weight")], p[self._lp(l, "norm1.bias")]), dout=ws["dh"],
                       resid=dx, dx_f32=dx_other, seed=seed, seed_dev=sdev, dgamma=g[self._lp(l, "norm1.weight")],
@@ -545,12 +578,13 @@ class TwoTowerEngine:
         # ---- user head
         ops.chain_bwd(ws["u"], l2norm=True, dout=ws["dun"], dx_bf16=ws["du_bf"],
                       dx_colsum=g[ut + "fusion_layer.3.bias"])
-        gemm(ws["du_bf"], ws["a1"], a_mn=True, b_mn=True, out_f32=g[ut + "fusion_layer.3.weight"], accumulate=True)
+        wg = self._wg
+        wg(gemm, ws["du_bf"], ws["a1"], a_mn=True, b_mn=True, out_f32=g[ut + "fusion_layer.3.weight"], accumulate=True)
         gemm(ws["du_bf"], w[ut + "fusion_layer.3.weight"], b_mn=True, out_f32=ws["da1"])
         ops.chain_bwd(ws["z1"], ln=(p[ut + "fusion_layer.1.weight"], p[ut + "fusion_layer.1.bias"]), relu=True,
                       dout=ws["da1"], dx_bf16=ws["dz1_bf"], dgamma=g[ut + "fusion_layer.1.weight"],
                       dbeta=g[ut + "fusion_layer.1.bias"], dx_colsum=g[ut + "fusion_layer.0.bias"])
-        gemm(ws["dz1_bf"], ws["cat"], a_mn=True, b_mn=True, out_f32=g[ut + "fusion_layer.0.weight"], accumulate=True)
+        wg(gemm, ws["dz1_bf"], ws["cat"], a_mn=True, b_mn=True, out_f32=g[ut + "fusion_layer.0.weight"], accumulate=True)
         gemm(ws["dz1_bf"], w[ut + "fusion_layer.0.weight"], b_mn=True, out_f32=ws["dcat"])
         dx, dx_other = ws["dx_a"], ws["dx_b"]
         top = cfg.num_layers - 1
@@ -563,7 +597,7 @@ class TwoTowerEngine:
             ops.gather_cat_bwd(ws["dcat"], ws["last_idx"], batch["user_gender"], batch["user_country"], B, L, dx, None,
                                g[ut + "gender_embedding.weight"], g[ut + "country_embedding.weight"])
             # dy = dropout-mask(dx) as bf16 for the top layer's linear2, with its column sums (bias grad)
-            ops.chain_bwd(dx, dout=dx, dx_bf16=ws["dy_bf"], drop2_p=dp, drop2_site=_site(top, 3), seed=seed,
+            ops.chain_bwd(dx, dout=dx, dx_bf16=ws[f"dy2_{top}"], drop2_p=dp, drop2_site=_site(top, 3), seed=seed,
                           seed_dev=sdev, dx_colsum=g[self._lp(top, "linear2.bias")])
 
         # ---- encoder layers, last to first
@@ -574,34 +608,36 @@ class TwoTowerEngine:
                 continue
             ffn_scale = 1.0 / (1.0 - dp) if dp > 0 else 1.0
             # linear2: dW2 = dy^T f ; dpre = (dy W2) gated by f (ReLU and FFN dropout in one test)
-            gemm(ws["dy_bf"], ws[f"f_{l}"], a_mn=True, b_mn=True, out_f32=g[self._lp(l, "linear2.weight")],
-                 accumulate=True)
-            gemm(ws["dy_bf"], w[self._lp(l, "linear2.weight")], b_mn=True, gate=ws[f"f_{l}"], gate_scale=ffn_scale,
-                 out_bf16=ws["dpre"])
-            ops.colsum_bf16(ws["dpre"], g[self._lp(l, "linear1.bias")])
-            gemm(ws["dpre"], ws[f"h2_{l}"], a_mn=True, b_mn=True, out_f32=g[self._lp(l, "linear1.weight")],
-                 accumulate=True)
-            gemm(ws["dpre"], w[self._lp(l, "linear1.weight")], b_mn=True, out_f32=ws["dh"])
+            if f"dpre_{l}" not in ws:      # prune_last_layer toggled after the workspace was built
+                ws[f"dpre_{l}"] = torch.empty(B * L, cfg.dim_feedforward, dtype=torch.bfloat16, device=self.device)
+            dy2, dy1, dpre, dqkv = ws[f"dy2_{l}"], ws[f"dy1_{l}"], ws[f"dpre_{l}"], ws[f"dqkv_{l}"]
+            wg(gemm, dy2, ws[f"f_{l}"], a_mn=True, b_mn=True, out_f32=g[self._lp(l, "linear2.weight")], accumulate=True)
+            gemm(dy2, w[self._lp(l, "linear2.weight")], b_mn=True, gate=ws[f"f_{l}"], gate_scale=ffn_scale,
+                 out_bf16=dpre)
+            wg(ops.colsum_bf16, dpre, g[self._lp(l, "linear1.bias")])
+            wg(gemm, dpre, ws[f"h2_{l}"], a_mn=True, b_mn=True, out_f32=g[self._lp(l, "linear1.weight")],
+               accumulate=True)
+            gemm(dpre, w[self._lp(l, "linear1.weight")], b_mn=True, out_f32=ws["dh"])
             # norm2 backward (+ residual); emits dy for out_proj (dropout-1 mask) and its bias grad
             ops.chain_bwd(ws[f"xmid_{l}"], ln=(p[self._lp(l, "norm2.weight")], p[self._lp(l, "norm2.bias")]),
-                          dout=ws["dh"], resid=dx, dx_f32=dx_other, dx_bf16=ws["dy_bf"], drop2_p=dp,
+                          dout=ws["dh"], resid=dx, dx_f32=dx_other, dx_bf16=dy1, drop2_p=dp,
                           drop2_site=_site(l, 1), seed=seed, seed_dev=sdev,
                           dgamma=g[self._lp(l, "norm2.weight")], dbeta=g[self._lp(l, "norm2.bias")],
                           dx_colsum=g[self._lp(l, "self_attn.out_proj.bias")])
             dx, dx_other = dx_other, dx
-            gemm(ws["dy_bf"], ws[f"ctx_{l}"], a_mn=True, b_mn=True,
-                 out_f32=g[self._lp(l, "self_attn.out_proj.weight")], accumulate=True)
-            gemm(ws["dy_bf"], w[self._lp(l, "self_attn.out_proj.weight")], b_mn=True, out_bf16=ws["dctx"])
-            ops.attn_bwd(ws[f"qkv_{l}"], ws[f"ctx_{l}"], ws["dctx"], ws[f"lse_{l}"], ws["dqkv"], B, L, cfg.num_heads,
+            wg(gemm, dy1, ws[f"ctx_{l}"], a_mn=True, b_mn=True, out_f32=g[self._lp(l, "self_attn.out_proj.weight")],
+               accumulate=True)
+            gemm(dy1, w[self._lp(l, "self_attn.out_proj.weight")], b_mn=True, out_bf16=ws["dctx"])
+            ops.attn_bwd(ws[f"qkv_{l}"], ws[f"ctx_{l}"], ws["dctx"], ws[f"lse_{l}"], dqkv, B, L, cfg.num_heads,
                          drop_p=dp, drop_seed=seed, drop_seed_dev=sdev, drop_site=_site(l, 0))
-            ops.colsum_bf16(ws["dqkv"], g[self._lp(l, "self_attn.in_proj_bias")])
-            gemm(ws["dqkv"], ws[f"h1_{l}"], a_mn=True, b_mn=True, out_f32=g[self._lp(l, "self_attn.in_proj_weight")],
-                 accumulate=True)
-            gemm(ws["dqkv"], w[self._lp(l, "self_attn.in_proj_weight")], b_mn=True, out_f32=ws["dh"])
+            wg(ops.colsum_bf16, dqkv, g[self._lp(l, "self_attn.in_proj_bias")])
+            wg(gemm, dqkv, ws[f"h1_{l}"], a_mn=True, b_mn=True, out_f32=g[self._lp(l, "self_attn.in_proj_weight")],
+               accumulate=True)
+            gemm(dqkv, w[self._lp(l, "self_attn.in_proj_weight")], b_mn=True, out_f32=ws["dh"])
             # norm1 backward (+ residual); for l > 0 also dy for the previous layer's linear2
             extra = {}
             if l > 0:
-                extra = dict(dx_bf16=ws["dy_bf"], drop2_p=dp, drop2_site=_site(l - 1, 3),
+                extra = dict(dx_bf16=ws[f"dy2_{l - 1}"], drop2_p=dp, drop2_site=_site(l - 1, 3),
                              dx_colsum=g[self._lp(l - 1, "linear2.bias")])
             ops.chain_bwd(x_in, ln=(p[self._lp(l, "norm1.weight")], p[self._lp(l, "norm1.bias")]), dout=ws["dh"],
                           resid=dx, dx_f32=dx_other, seed=seed, seed_dev=sdev,
@@ -615,6 +651,8 @@ class TwoTowerEngine:
                          g[ut + "layer_norm.weight"], g[ut + "layer_norm.bias"], drop_p=dp, seed=seed,
                          seed_dev=sdev, site=SITE_EMB)
         main.wait_stream(side)
+        if self.overlap_wgrad:
+            main.wait_stream(self._wgrad_stream())
 
     # ------------------------------------------------------------------ optimizer
     def adamw_step(self, lr: float = 1e-4, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.01,
