@@ -6,10 +6,12 @@ returns non-zero, a TTError is raised.
 from __future__ import annotations
 
 import ctypes
+import os
 from ctypes import c_char_p, c_float, c_int32, c_uint32, c_uint64, c_void_p
 from pathlib import Path
 
-_LIB_PATH = Path(__file__).resolve().parent / "libtt_b200.so"
+# TT_B200_LIB: load another build of the same ABI (A/B timing of kernel variants on one GPU box)
+_LIB_PATH = Path(os.environ.get("TT_B200_LIB") or Path(__file__).resolve().parent / "libtt_b200.so")
 _lib = None
 
 

@@ -124,8 +124,8 @@ __device__ __forceinline__ float2 unpack_bf16(uint32_t u) {
 
 // Counter-based dropout decision. keep-probability = 1 - p, encoded as a 32-bit threshold by
 // the host (thresh = p * 2^32). Same (seed, site, idx) -> same bit in forward and backward, so
-// no mask tensor is stored. The per-call key (seed, site) is loop-invariant; the per-element
-// cost is one xor + a 32-bit integer finaliser (two IMULs).
+// no mask tensor is stored. The per-call key (seed, site) is loop-invariant; one 32-bit integer
+// finaliser (two IMULs) is shared by four consecutive elements.
 __device__ __forceinline__ uint32_t mix32(uint32_t x) {
   x ^= x >> 16;
   x *= 0x7feb352dU;
@@ -137,24 +137,79 @@ __device__ __forceinline__ uint32_t mix32(uint32_t x) {
 __device__ __forceinline__ uint32_t drop_key(uint64_t seed, uint32_t site) {
   return mix32(static_cast<uint32_t>(seed) ^ mix32(static_cast<uint32_t>(seed >> 32) + site * 0x9E3779B9u));
 }
-// One 32-bit hash decides TWO consecutive elements (16 bits each, compared with the top 16 bits
-// of the threshold): element idx uses half (idx & 1) of hash(idx >> 1).
+// One 32-bit hash decides FOUR consecutive elements: element idx uses word (idx & 3) of
+// h = hash(idx >> 2), where word 0 is h itself and words 1..3 are h times three odd constants
+// (a bijection of a well-mixed word; its high bits depend on every bit of h). Each word is
+// compared with the full 32-bit threshold p * 2^32. Per element: 1/4 finaliser + 1 IMAD + 1 ISETP.
+static constexpr uint32_t kDropMul1 = 0x9E3779B1u;
+static constexpr uint32_t kDropMul2 = 0x85EBCA6Bu;
+static constexpr uint32_t kDropMul3 = 0xC2B2AE35u;
 __device__ __forceinline__ bool drop_keep_k(uint32_t key, uint64_t idx, uint32_t thresh) {
-  const uint64_t pair = idx >> 1;
-  const uint32_t x = static_cast<uint32_t>(pair) ^ (static_cast<uint32_t>(pair >> 32) * 0x85EBCA6Bu);
+  const uint64_t quad = idx >> 2;
+  const uint32_t x = static_cast<uint32_t>(quad) ^ (static_cast<uint32_t>(quad >> 32) * 0x85EBCA6Bu);
   const uint32_t h = mix32(x ^ key);
-  const uint32_t bits = (idx & 1) ? (h >> 16) : (h & 0xFFFFu);
-  return bits >= (thresh >> 16);
+  const uint32_t j = static_cast<uint32_t>(idx) & 3u;
+  const uint32_t mul = j == 0 ? 1u : (j == 1 ? kDropMul1 : (j == 2 ? kDropMul2 : kDropMul3));
+  return h * mul >= thresh;
 }
 __device__ __forceinline__ bool drop_keep(uint64_t seed, uint32_t site, uint64_t idx, uint32_t thresh) {
   return drop_keep_k(drop_key(seed, site), idx, thresh);
 }
 // Pair form for an EVEN 32-bit index: k0 = keep(idx_even), k1 = keep(idx_even + 1), one hash.
 __device__ __forceinline__ void drop_keep_pair(uint32_t key, uint32_t idx_even, uint32_t thresh, bool& k0, bool& k1) {
-  const uint32_t h = mix32((idx_even >> 1) ^ key);
-  const uint32_t t16 = thresh >> 16;
-  k0 = (h & 0xFFFFu) >= t16;
-  k1 = (h >> 16) >= t16;
+  const uint32_t h = mix32((idx_even >> 2) ^ key);
+  const bool hi = (idx_even & 2u) != 0;
+  k0 = h * (hi ? kDropMul2 : 1u) >= thresh;
+  k1 = h * (hi ? kDropMul3 : kDropMul1) >= thresh;
+}
+// Quad form for a 32-bit index that is a multiple of 4: k[j] = keep(idx4 + j), one hash.
+__device__ __forceinline__ void drop_keep_quad(uint32_t key, uint32_t idx4, uint32_t thresh, bool (&k)[4]) {
+  const uint32_t h = mix32((idx4 >> 2) ^ key);
+  k[0] = h >= thresh;
+  k[1] = h * kDropMul1 >= thresh;
+  k[2] = h * kDropMul2 >= thresh;
+  k[3] = h * kDropMul3 >= thresh;
+}
+// Packed fp32 pairs (sm_100 FFMA2 / FMUL2): d = a * b + c on two lanes in one issue slot.
+__device__ __forceinline__ void ffma2(float& a0, float& a1, float b0, float b1, float c0, float c1) {
+  uint64_t d;
+  asm("{\n\t"
+      ".reg .b64 ra, rb, rc;\n\t"
+      "mov.b64 ra, {%1, %2};\n\t"
+      "mov.b64 rb, {%3, %4};\n\t"
+      "mov.b64 rc, {%5, %6};\n\t"
+      "fma.rn.f32x2 %0, ra, rb, rc;\n\t"
+      "}\n"
+      : "=l"(d)
+      : "f"(a0), "f"(a1), "f"(b0), "f"(b1), "f"(c0), "f"(c1));
+  a0 = __uint_as_float(static_cast<uint32_t>(d));
+  a1 = __uint_as_float(static_cast<uint32_t>(d >> 32));
+}
+__device__ __forceinline__ void fadd2(float& a0, float& a1, float b0, float b1) {
+  uint64_t d;
+  asm("{\n\t"
+      ".reg .b64 ra, rb;\n\t"
+      "mov.b64 ra, {%1, %2};\n\t"
+      "mov.b64 rb, {%3, %4};\n\t"
+      "add.rn.f32x2 %0, ra, rb;\n\t"
+      "}\n"
+      : "=l"(d)
+      : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+  a0 = __uint_as_float(static_cast<uint32_t>(d));
+  a1 = __uint_as_float(static_cast<uint32_t>(d >> 32));
+}
+__device__ __forceinline__ void fmul2(float& a0, float& a1, float b0, float b1) {
+  uint64_t d;
+  asm("{\n\t"
+      ".reg .b64 ra, rb;\n\t"
+      "mov.b64 ra, {%1, %2};\n\t"
+      "mov.b64 rb, {%3, %4};\n\t"
+      "mul.rn.f32x2 %0, ra, rb;\n\t"
+      "}\n"
+      : "=l"(d)
+      : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+  a0 = __uint_as_float(static_cast<uint32_t>(d));
+  a1 = __uint_as_float(static_cast<uint32_t>(d >> 32));
 }
 // 16-byte vector reduction into global memory (sm_90+: one RED instead of four)
 __device__ __forceinline__ void red_add_f32x4(float* addr, float a, float b, float c, float d) {

@@ -2,14 +2,14 @@
 //
 //   C[M,N] = epilogue(alpha * A[M,K] * B[N,K]^T), bf16 operands, fp32 accumulate in TMEM.
 //
-// One CTA per SM, 384 threads:
+// One CTA per SM, 640 threads:
 //   warp 0      : TMA producer (one elected lane) — A/B tiles, 128B swizzle, N-stage ring
 //   warp 1      : MMA issuer (one elected lane)  — tcgen05.mma M=128, N=block_n, K=16
 //   warp 2      : TMEM allocator (2 accumulator buffers of block_n columns)
-//   warps 4..11 : epilogue — tcgen05.ld (warp % 4 = TMEM lane quarter, two warps per quarter take
-//                 alternate 32-column chunks, next chunk prefetched), fused bias / ReLU / dropout /
-//                 gate / residual; all global traffic goes through a swizzled per-warp smem tile so
-//                 loads/stores are coalesced (4 rows x 128 B per instruction), split-K via red.v4
+//   warps 4..19 : epilogue — tcgen05.ld (warp % 4 = TMEM lane quarter, the four warps of a quarter
+//                 take every 4th 32-column chunk), fused bias / ReLU / dropout / gate / residual;
+//                 all global traffic goes through a swizzled per-warp smem tile so loads/stores
+//                 are coalesced, split-K via red.v4
 // Three pipelines: smem full/empty (TMA<->MMA), TMEM full/empty (MMA<->epilogue) and the
 // static persistent tile loop. Operands may be K-major or MN-major (the transposed
 // layouts dgrad/wgrad need), selected by template flags and the UMMA descriptors.
@@ -40,22 +40,30 @@ struct GemmParams {
   __nv_bfloat16* out_bf16;
   int ld_bf16;
   int accumulate;
-  int debug;  // profiling knob: 1 = epilogue drains TMEM only (no math, no global IO)
+  int stg_bytes;    // per-epilogue-warp staging bytes (tile + 256 B bias slice)
+  int debug;  // profiling knob: 1 = epilogue drains TMEM only (no math, no global IO); 2 = everything but the global stores
 };
 
 static constexpr int kBlockM = 128;
 static constexpr int kBlockK = 64;
 static constexpr uint32_t kABytes = kBlockM * kBlockK * 2;  // 16 KB
-static constexpr int kEpiWarps = 8;
-static constexpr int kGemmThreads = 128 + 32 * kEpiWarps;   // 4 control warps + 8 epilogue warps
-static constexpr uint32_t kStageBytesPerWarp = 32 * 128;     // 32 rows x 128 B staging tile
-static constexpr uint32_t kEpiBytesPerWarp = 2 * kStageBytesPerWarp + 512;  // out tile, in tile, 128 bias floats
+static constexpr int kEpiWarps = 16;
+static constexpr int kGemmThreads = 128 + 32 * kEpiWarps;   // 4 control warps + 16 epilogue warps
+static constexpr uint32_t kStageBytesF32 = 32 * 128;    // 32 rows x 128 B staging tile (fp32 output / residual)
+static constexpr uint32_t kStageBytesBf16 = 32 * 64;    // 32 rows x 64 B (bf16 output / gate only)
+static constexpr uint32_t kBiasBytesPerWarp = 256;      // 2 chunks x 32 floats
 
 // Per-warp staging tile: 32 rows x 128 B, 16-byte units XOR-swizzled by (row & 7) so that both
 // the row-per-lane accesses (thread = accumulator row) and the transposed, coalesced accesses
 // (8 lanes = one 128 B row segment) are bank-conflict free.
 __device__ __forceinline__ uint4* stg_unit(uint8_t* stg, int row, int unit) {
   return reinterpret_cast<uint4*>(stg + row * 128 + ((unit ^ (row & 7)) << 4));
+}
+// bf16 variant: 32 rows x 64 B. Two rows share a 128 B bank line, so the 4 units are swizzled by
+// (row >> 1) & 3: eight consecutive rows (one row-per-lane wavefront) and 2 rows x 4 units (one
+// transposed wavefront) both cover all 32 banks exactly once.
+__device__ __forceinline__ uint4* stg_unit_bf(uint8_t* stg, int row, int unit) {
+  return reinterpret_cast<uint4*>(stg + row * 64 + ((unit ^ ((row >> 1) & 3)) << 4));
 }
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
@@ -79,7 +87,7 @@ __device__ __forceinline__ void epi_prefetch(const GemmParams& p, uint8_t* in, i
     for (int it = 0; it < 4; ++it) {
       const int rr = it * 8 + (lane >> 2), u = lane & 3;
       const int gr = row0 + rr, gc = col0 + u * 8;
-      if (gr < p.M && gc + 8 <= p.N) cp_async16(stg_unit(in, rr, u), p.gate + static_cast<size_t>(gr) * p.ld_gate + gc);
+      if (gr < p.M && gc + 8 <= p.N) cp_async16(stg_unit_bf(in, rr, u), p.gate + static_cast<size_t>(gr) * p.ld_gate + gc);
     }
   }
   cp_async_commit();
@@ -88,11 +96,11 @@ __device__ __forceinline__ void epi_prefetch(const GemmParams& p, uint8_t* in, i
 // L2 prefetch of the residual / gate lines of one (tile, warp): lane = row, one 128-byte (fp32) or
 // 64-byte (bf16) segment per 32-column chunk. Issued a whole tile ahead, so the later cp.async only
 // pays L2 latency.
-__device__ __forceinline__ void epi_prefetch_l2(const GemmParams& p, int lane, int row0, int colbase, int half,
+__device__ __forceinline__ void epi_prefetch_l2(const GemmParams& p, int lane, int row0, int colbase, int sub,
                                                 int nchunks) {
   const int gr = row0 + lane;
   if (gr >= p.M) return;
-  for (int c = half; c < nchunks; c += 2) {
+  for (int c = sub; c < nchunks; c += kEpiWarps / 4) {
     const int gc = colbase + c * 32;
     if (gc >= p.N) break;
     const void* ptr = p.residual ? static_cast<const void*>(p.residual + static_cast<size_t>(gr) * p.ld_res + gc)
@@ -102,34 +110,39 @@ __device__ __forceinline__ void epi_prefetch_l2(const GemmParams& p, int lane, i
 }
 
 // One 32-column chunk of one accumulator row per lane. `next_col0` >= 0 asks for the prefetch of
-// the warp's next chunk once the current "in" tile has been consumed.
+// the warp's next chunk once the staging tile (`in` and `out` may be the same tile) is free again.
 __device__ __forceinline__ void gemm_epilogue_chunk(const GemmParams& p, const uint32_t (&r)[32], uint8_t* out,
                                                     uint8_t* in, const float* sbias, int lane, int row0, int col0,
                                                     int next_col0, uint32_t dkey) {
   const int row = row0 + lane;
   float v[32];
 #pragma unroll
-  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * p.alpha;
-
+  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+  // alpha and bias in one packed FFMA2 per column pair; alpha == 1 without bias costs nothing
   if (p.bias) {
 #pragma unroll
     for (int j = 0; j < 32; j += 4) {
       const float4 b = *reinterpret_cast<const float4*>(sbias + j);   // same address in every lane: broadcast
-      v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+      ffma2(v[j], v[j + 1], p.alpha, p.alpha, b.x, b.y);
+      ffma2(v[j + 2], v[j + 3], p.alpha, p.alpha, b.z, b.w);
     }
+  } else if (p.alpha != 1.f) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 2) fmul2(v[j], v[j + 1], p.alpha, p.alpha);
   }
   if (p.relu) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
   }
   if (p.drop_thresh) {
+    // N % 4 == 0 and col0 % 32 == 0: the four columns j..j+3 share one hash word
     const uint32_t base = static_cast<uint32_t>(row) * static_cast<uint32_t>(p.N) + static_cast<uint32_t>(col0);
 #pragma unroll
-    for (int j = 0; j < 32; j += 2) {
-      bool k0, k1;
-      drop_keep_pair(dkey, base + j, p.drop_thresh, k0, k1);
-      v[j] = k0 ? v[j] * p.drop_scale : 0.f;
-      v[j + 1] = k1 ? v[j + 1] * p.drop_scale : 0.f;
+    for (int j = 0; j < 32; j += 4) {
+      bool k[4];
+      drop_keep_quad(dkey, base + j, p.drop_thresh, k);
+      fmul2(v[j], v[j + 1], k[0] ? p.drop_scale : 0.f, k[1] ? p.drop_scale : 0.f);
+      fmul2(v[j + 2], v[j + 3], k[2] ? p.drop_scale : 0.f, k[3] ? p.drop_scale : 0.f);
     }
   }
   if (p.residual || p.gate) {
@@ -139,24 +152,25 @@ __device__ __forceinline__ void gemm_epilogue_chunk(const GemmParams& p, const u
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
         const float4 x = *reinterpret_cast<const float4*>(stg_unit(in, lane, u));
-        v[4 * u] += x.x; v[4 * u + 1] += x.y; v[4 * u + 2] += x.z; v[4 * u + 3] += x.w;
+        fadd2(v[4 * u], v[4 * u + 1], x.x, x.y);
+        fadd2(v[4 * u + 2], v[4 * u + 3], x.z, x.w);
       }
     } else {
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        const uint4 x = *stg_unit(in, lane, u);
+        const uint4 x = *stg_unit_bf(in, lane, u);
         const uint32_t w[4] = {x.x, x.y, x.z, x.w};
 #pragma unroll
         for (int h = 0; h < 4; ++h) {
-          const float2 f = unpack_bf16(w[h]);
+          // gate > 0 on the packed bf16 pair without unpacking: a positive bf16 is a positive int16
+          const bool g0 = static_cast<int32_t>(w[h] << 16) > 0;
+          const bool g1 = static_cast<int32_t>(w[h]) > 0xFFFF;
           const int j = u * 8 + h * 2;
-          v[j] = f.x > 0.f ? v[j] * p.gate_scale : 0.f;
-          v[j + 1] = f.y > 0.f ? v[j + 1] * p.gate_scale : 0.f;
+          fmul2(v[j], v[j + 1], g0 ? p.gate_scale : 0.f, g1 ? p.gate_scale : 0.f);
         }
       }
     }
     __syncwarp();
-    if (next_col0 >= 0) epi_prefetch(p, in, lane, row0, next_col0);
   }
   if (p.out_f32) {
 #pragma unroll
@@ -167,7 +181,7 @@ __device__ __forceinline__ void gemm_epilogue_chunk(const GemmParams& p, const u
     for (int it = 0; it < 8; ++it) {
       const int rr = it * 4 + (lane >> 3), u = lane & 7;
       const int gr = row0 + rr, gc = col0 + u * 4;
-      if (gr < p.M && gc + 4 <= p.N) {
+      if (gr < p.M && gc + 4 <= p.N && p.debug != 2) {
         const float4 x = *reinterpret_cast<const float4*>(stg_unit(out, rr, u));
         float* o = p.out_f32 + static_cast<size_t>(gr) * p.ld_f32 + gc;
         if (p.accumulate) red_add_f32x4(o, x.x, x.y, x.z, x.w);
@@ -184,18 +198,20 @@ __device__ __forceinline__ void gemm_epilogue_chunk(const GemmParams& p, const u
       x.y = pack_bf16(v[u * 8 + 2], v[u * 8 + 3]);
       x.z = pack_bf16(v[u * 8 + 4], v[u * 8 + 5]);
       x.w = pack_bf16(v[u * 8 + 6], v[u * 8 + 7]);
-      *stg_unit(out, lane, u) = x;
+      *stg_unit_bf(out, lane, u) = x;
     }
     __syncwarp();
 #pragma unroll
     for (int it = 0; it < 4; ++it) {
       const int rr = it * 8 + (lane >> 2), u = lane & 3;
       const int gr = row0 + rr, gc = col0 + u * 8;
-      if (gr < p.M && gc + 8 <= p.N)
-        *reinterpret_cast<uint4*>(p.out_bf16 + static_cast<size_t>(gr) * p.ld_bf16 + gc) = *stg_unit(out, rr, u);
+      if (gr < p.M && gc + 8 <= p.N && p.debug != 2)
+        *reinterpret_cast<uint4*>(p.out_bf16 + static_cast<size_t>(gr) * p.ld_bf16 + gc) = *stg_unit_bf(out, rr, u);
     }
     __syncwarp();
   }
+  // the staging tile is free again: fetch the residual / gate block of this warp's next chunk
+  if ((p.residual || p.gate) && next_col0 >= 0) epi_prefetch(p, in, lane, row0, next_col0);
 }
 
 template <bool A_MN, bool B_MN>
@@ -212,10 +228,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int block_n = p.block_n;
   const uint32_t b_bytes = static_cast<uint32_t>(block_n) * kBlockK * 2;
 
+  const int kblocks = (p.K + kBlockK - 1) / kBlockK;
   uint8_t* sA = smem;
   uint8_t* sB = smem + static_cast<size_t>(stages) * kABytes;
-  uint8_t* sStage = sB + static_cast<size_t>(stages) * b_bytes;  // kEpiWarps x 4 KB staging tiles
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sStage + kEpiWarps * kEpiBytesPerWarp);
+  uint8_t* sStage = sB + static_cast<size_t>(stages) * b_bytes;  // kEpiWarps staging tiles
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sStage + static_cast<size_t>(kEpiWarps) * p.stg_bytes);
   uint64_t* empty_bar = full_bar + stages;
   uint64_t* tfull_bar = empty_bar + stages;
   uint64_t* tempty_bar = tfull_bar + 2;
@@ -254,8 +271,6 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int tiles_m = (p.M + kBlockM - 1) / kBlockM;
   const int tiles_n = (p.N + block_n - 1) / block_n;
   const int num_tiles = tiles_m * tiles_n * p.k_splits;
-  const int kblocks = (p.K + kBlockK - 1) / kBlockK;
-
   if (warp == 0) {
     if (elect_one()) {
       int stage = 0;
@@ -270,9 +285,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           mbar_wait(&empty_bar[stage], phase ^ 1u);
           mbar_arrive_expect_tx(&full_bar[stage], kABytes + b_bytes);
           uint8_t* a_dst = sA + static_cast<size_t>(stage) * kABytes;
-          uint8_t* b_dst = sB + static_cast<size_t>(stage) * b_bytes;
           if (A_MN) tma_load_3d(a_dst, &tmA, &full_bar[stage], 0, kb * kBlockK, m_blk * (kBlockM / 64));
           else      tma_load_2d(a_dst, &tmA, &full_bar[stage], kb * kBlockK, m_blk * kBlockM);
+          uint8_t* b_dst = sB + static_cast<size_t>(stage) * b_bytes;
           if (B_MN) tma_load_3d(b_dst, &tmB, &full_bar[stage], 0, kb * kBlockK, n_blk * (block_n / 64));
           else      tma_load_2d(b_dst, &tmB, &full_bar[stage], kb * kBlockK, n_blk * block_n);
           if (++stage == stages) { stage = 0; phase ^= 1u; }
@@ -317,13 +332,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
     }
   } else if (warp >= 4) {
-    // 8 epilogue warps: warp % 4 selects the TMEM lane quarter (hardware rule), the two warps
-    // sharing a quarter take alternate 32-column chunks of the tile.
+    // 16 epilogue warps (4 per scheduler: the chunk pipeline is a chain of TMEM / shared / global
+    // latencies, hidden by switching warps rather than by unrolling). warp % 4 selects the TMEM lane
+    // quarter (hardware rule); the four warps sharing a quarter take every 4th 32-column chunk.
     const int ew = warp - 4;
-    const int q = ew & 3, half = ew >> 2;
-    uint8_t* stg_out = sStage + static_cast<size_t>(ew) * kEpiBytesPerWarp;
-    uint8_t* stg_in = stg_out + kStageBytesPerWarp;
-    float* sbias = reinterpret_cast<float*>(stg_in + kStageBytesPerWarp);   // [4 chunks][32]
+    const int q = ew & 3, sub = ew >> 2;
+    uint8_t* stg = sStage + static_cast<size_t>(ew) * p.stg_bytes;
+    float* sbias = reinterpret_cast<float*>(stg + p.stg_bytes - kBiasBytesPerWarp);   // [2 chunks][32]
     const uint64_t seed = p.drop_seed + ((p.drop_thresh && p.drop_seed_dev) ? *p.drop_seed_dev : 0ull);
     const uint32_t dkey = drop_key(seed, p.drop_site);
     const int nchunks = block_n / 32;
@@ -332,7 +347,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const bool has_in = p.residual || p.gate;
     if (has_in && static_cast<int>(blockIdx.x) < num_tiles) {
       const int mn = static_cast<int>(blockIdx.x) / p.k_splits;
-      epi_prefetch_l2(p, lane, (mn / tiles_n) * kBlockM + q * 32, (mn % tiles_n) * block_n, half, nchunks);
+      epi_prefetch_l2(p, lane, (mn / tiles_n) * kBlockM + q * 32, (mn % tiles_n) * block_n, sub, nchunks);
     }
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
       const int mn = t / p.k_splits;
@@ -341,43 +356,33 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int colbase = n_blk * block_n;
       if (has_in && t + static_cast<int>(gridDim.x) < num_tiles) {   // next tile's lines -> L2 while this one computes
         const int mn2 = (t + static_cast<int>(gridDim.x)) / p.k_splits;
-        epi_prefetch_l2(p, lane, (mn2 / tiles_n) * kBlockM + q * 32, (mn2 % tiles_n) * block_n, half, nchunks);
+        epi_prefetch_l2(p, lane, (mn2 / tiles_n) * kBlockM + q * 32, (mn2 % tiles_n) * block_n, sub, nchunks);
       }
       // Everything that does not depend on the accumulator is issued before waiting for it:
       // the bias slice of this warp's chunks and the first residual / gate block.
       if (p.bias) {
         __syncwarp();
-        for (int k = 0, c = half; c < nchunks; c += 2, ++k) {
+        for (int k = 0, c = sub; c < nchunks; c += kEpiWarps / 4, ++k) {
           const int col = colbase + c * 32 + lane;
           sbias[k * 32 + lane] = col < p.N ? __ldg(p.bias + col) : 0.f;
         }
       }
-      if ((p.residual || p.gate) && half < nchunks) epi_prefetch(p, stg_in, lane, row0, colbase + half * 32);
+      if (has_in && sub < nchunks) epi_prefetch(p, stg, lane, row0, colbase + sub * 32);
       mbar_wait(&tfull_bar[acc], acc_phase);
       __syncwarp();
       tc_fence_after();
       const uint32_t t_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
                               static_cast<uint32_t>(acc * block_n);
-      uint32_t r0[32], r1[32];
-      int c = half, k = 0;
-      if (c < nchunks) tmem_ld32(t_base + static_cast<uint32_t>(c * 32), r0);
-      while (c < nchunks) {
+      uint32_t r[32];
+      for (int c = sub, k = 0; c < nchunks; c += kEpiWarps / 4, ++k) {
+        tmem_ld32(t_base + static_cast<uint32_t>(c * 32), r);
         tmem_ld_wait();
-        if (c + 2 < nchunks) tmem_ld32(t_base + static_cast<uint32_t>((c + 2) * 32), r1);
-        if (!p.debug)
-          gemm_epilogue_chunk(p, r0, stg_out, stg_in, sbias + k * 32, lane, row0, colbase + c * 32,
-                              c + 2 < nchunks ? colbase + (c + 2) * 32 : -1, dkey);
-        c += 2; ++k;
-        if (c >= nchunks) break;
-        tmem_ld_wait();
-        if (c + 2 < nchunks) tmem_ld32(t_base + static_cast<uint32_t>((c + 2) * 32), r0);
-        if (!p.debug)
-          gemm_epilogue_chunk(p, r1, stg_out, stg_in, sbias + k * 32, lane, row0, colbase + c * 32,
-                              c + 2 < nchunks ? colbase + (c + 2) * 32 : -1, dkey);
-        c += 2; ++k;
+        const int cn = c + kEpiWarps / 4;
+        if (p.debug != 1)
+          gemm_epilogue_chunk(p, r, stg, stg, sbias + k * 32, lane, row0, colbase + c * 32,
+                              cn < nchunks ? colbase + cn * 32 : -1, dkey);
       }
-      if (p.debug) cp_async_wait_all();
-      tmem_ld_wait();
+      if (p.debug == 1) cp_async_wait_all();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
@@ -391,9 +396,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == 2) tmem_dealloc(tmem_base, tmem_cols);
 }
 
-static size_t gemm_smem_bytes(int block_n, int stages) {
-  return 1024 + static_cast<size_t>(stages) * (kABytes + static_cast<size_t>(block_n) * kBlockK * 2) +
-         kEpiWarps * kEpiBytesPerWarp + (2 * stages + 4) * sizeof(uint64_t) + 16;
+static constexpr size_t kSmemLimit = 232448;
+static size_t gemm_fixed_smem(int stg_bytes) {   // alignment pad, staging, barriers (<= 8 stages), TMEM slot
+  return 1024 + static_cast<size_t>(kEpiWarps) * stg_bytes + (2 * 8 + 4) * sizeof(uint64_t) + 16;
 }
 
 template <bool A_MN, bool B_MN>
@@ -405,7 +410,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
     configured = true;
   }
-  TT_REQUIRE(smem <= 232448, "tt_gemm_bf16: %zu B of shared memory requested", smem);
+  TT_REQUIRE(smem <= kSmemLimit, "tt_gemm_bf16: %zu B of shared memory requested", smem);
   TT_CHECK_CUDA(launch_k(gemm_bf16_kernel<A_MN, B_MN>, dim3(grid), dim3(kGemmThreads), smem, stream, tmA, tmB, p));
   TT_LAUNCH_CHECK();
   return TT_OK;
@@ -442,19 +447,30 @@ extern "C" int tt_gemm_bf16(const tt_gemm_args* a, void* stream_) {
   p.M = a->M; p.N = a->N; p.K = a->K;
   int bn = a->block_n;
   if (bn == 0) {
-    if (a->accumulate) bn = a->N >= 512 ? 128 : 64;   // split-K: prefer output tiles over k-splits
+    if (a->accumulate) {
+      // Split-K. A deep reduction (the encoder's weight gradients, K = tokens) is bound by the L2 -> smem
+      // operand stream, so it wants the widest tile (half the operand bytes per flop of a 64-wide one;
+      // measured 45 -> 31 us on 1024x256x51200). A shallow one wants CTAs, i.e. many small tiles.
+      if (a->K >= 4096) bn = a->N >= 256 ? 256 : (a->N > 64 ? 128 : 64);
+      else bn = a->N >= 512 ? 128 : 64;
+    }
     else bn = a->N > 128 ? 256 : (a->N > 64 ? 128 : 64);
   }
   TT_REQUIRE(bn == 64 || bn == 128 || bn == 256, "tt_gemm_bf16: block_n must be 64/128/256");
   p.block_n = bn;
-  const size_t stage_bytes = kABytes + static_cast<size_t>(bn) * kBlockK * 2;
-  int stages = static_cast<int>((232448 - 1024 - kEpiWarps * kEpiBytesPerWarp - 256) / stage_bytes);
-  if (stages > 8) stages = 8;
-  p.stages = stages;
-
   const int tiles_m = (a->M + kBlockM - 1) / kBlockM;
   const int tiles_n = (a->N + bn - 1) / bn;
   const int kblocks = (a->K + kBlockK - 1) / kBlockK;
+  const size_t b_bytes = static_cast<size_t>(bn) * kBlockK * 2;
+  // bf16-only epilogues stage 64-byte rows: half the staging, more pipeline stages
+  p.stg_bytes = static_cast<int>(((a->out_f32 || a->residual) ? kStageBytesF32 : kStageBytesBf16) +
+                                 (a->bias ? kBiasBytesPerWarp : 0u));
+  const size_t fixed = gemm_fixed_smem(p.stg_bytes);
+  int stages = static_cast<int>((kSmemLimit - fixed) / (kABytes + b_bytes));
+  if (stages > 8) stages = 8;
+  TT_REQUIRE(stages >= 2, "tt_gemm_bf16: no room for a 2-stage pipeline (block_n %d)", bn);
+  p.stages = stages;
+
   int ks = a->k_splits;
   if (ks <= 0) {
     ks = 1;
@@ -530,7 +546,7 @@ extern "C" int tt_gemm_bf16(const tt_gemm_args* a, void* stream_) {
 
   const int num_tiles = tiles_m * tiles_n * ks;
   int grid = num_tiles < num_sms() ? num_tiles : num_sms();
-  const size_t smem = gemm_smem_bytes(bn, stages);
+  const size_t smem = fixed + static_cast<size_t>(stages) * (kABytes + b_bytes);
   if (a->a_mn) {
     return a->b_mn ? launch_gemm<true, true>(tmA, tmB, p, grid, smem, stream)
                    : launch_gemm<true, false>(tmA, tmB, p, grid, smem, stream);

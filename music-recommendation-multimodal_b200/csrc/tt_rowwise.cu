@@ -238,7 +238,7 @@ __global__ void __launch_bounds__(kRowThreads) chain_fwd_kernel(const ChainParam
 // Backward of the chain: the forward is recomputed from x, then
 // dout -> [L2 bwd] -> [dropout] -> [ReLU] -> [LN bwd] -> (+resid) -> dx.
 template <int NV>
-__global__ void __launch_bounds__(kRowThreads) chain_bwd_kernel(const ChainParams p) {
+__global__ void __launch_bounds__(kRowThreads, 2) chain_bwd_kernel(const ChainParams p) {
   pdl_launch_dependents();
   pdl_wait();
   constexpr int W = 128 * NV, E = 4 * NV;
@@ -250,10 +250,25 @@ __global__ void __launch_bounds__(kRowThreads) chain_bwd_kernel(const ChainParam
   for (int i = 0; i < E; ++i) { dg[i] = 0.f; db[i] = 0.f; cs[i] = 0.f; w[i] = 1.f; b[i] = 0.f; }
   if (p.ln_w) { load_row<NV>(p.ln_w, lane, w); load_row<NV>(p.ln_b, lane, b); }
   const uint64_t seed = (p.drop_thresh || p.drop2_thresh) ? read_seed(p.seed, p.seed_dev) : 0;
-  for (int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < p.R; row += warps_total) {
-    float x[E], g[E], xhat[E], y[E];
-    load_row<NV>(p.x + static_cast<size_t>(row) * W, lane, x);
-    load_row<NV>(p.dout + static_cast<size_t>(row) * W, lane, g);
+  // Software pipeline: the three input rows of the NEXT iteration are requested before this row's
+  // arithmetic (two warp reductions deep), so each warp keeps two rows of loads in flight.
+  int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  float xn[E], gn[E], rn[E];
+  if (row < p.R) {
+    load_row<NV>(p.x + static_cast<size_t>(row) * W, lane, xn);
+    load_row<NV>(p.dout + static_cast<size_t>(row) * W, lane, gn);
+    if (p.resid) load_row<NV>(p.resid + static_cast<size_t>(row) * W, lane, rn);
+  }
+  for (; row < p.R; row += warps_total) {
+    float x[E], g[E], r[E], xhat[E], y[E];
+#pragma unroll
+    for (int i = 0; i < E; ++i) { x[i] = xn[i]; g[i] = gn[i]; r[i] = rn[i]; }
+    const int nrow = row + warps_total;
+    if (nrow < p.R) {
+      load_row<NV>(p.x + static_cast<size_t>(nrow) * W, lane, xn);
+      load_row<NV>(p.dout + static_cast<size_t>(nrow) * W, lane, gn);
+      if (p.resid) load_row<NV>(p.resid + static_cast<size_t>(nrow) * W, lane, rn);
+    }
     float mean = 0.f, rstd = 1.f;
     if (p.ln_w) {
       ln_stats<NV>(x, p.ln_eps, mean, rstd);
@@ -307,8 +322,6 @@ __global__ void __launch_bounds__(kRowThreads) chain_bwd_kernel(const ChainParam
       for (int i = 0; i < E; ++i) g[i] = rstd * (g[i] - s1 - xhat[i] * s2);
     }
     if (p.resid) {
-      float r[E];
-      load_row<NV>(p.resid + static_cast<size_t>(row) * W, lane, r);
 #pragma unroll
       for (int i = 0; i < E; ++i) g[i] += r[i];
     }

@@ -128,6 +128,8 @@ class TwoTowerEngine:
         #: (exact). False runs every layer on every position like the reference.
         self.prune_last_layer = True
         #: run weight-gradient GEMMs / bias column sums on a second stream (see _wg)
+        #: measurement aid: issue everything on the current stream (per-kernel event timing without overlap)
+        self.serialize = False
         self.overlap_wgrad = os.environ.get("TT_OVERLAP_WGRAD", "1") != "0"
 
     # ------------------------------------------------------------------ parameters
@@ -271,14 +273,18 @@ class TwoTowerEngine:
         e0.record()
         ops.gemm(A, B, **kw)
         e1.record()
-        log.append((e0, e1, 2.0 * M * N * K, nbytes))
+        log.append((e0, e1, 2.0 * M * N * K, nbytes, (M, N, K)))
 
     def _side_stream(self) -> torch.cuda.Stream:
+        if self.serialize:
+            return torch.cuda.current_stream()
         if getattr(self, "_side", None) is None:
             self._side = torch.cuda.Stream(device=self.device)
         return self._side
 
     def _wgrad_stream(self) -> torch.cuda.Stream:
+        if self.serialize:
+            return torch.cuda.current_stream()
         if getattr(self, "_wside", None) is None:
             self._wside = torch.cuda.Stream(device=self.device)
         return self._wside

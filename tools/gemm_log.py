@@ -32,19 +32,20 @@ def spy(A, B, **kw):
 
 
 ops.gemm = spy
-tot = {}
+eng.serialize = True            # one stream: per-launch times without overlap
 for it in range(4):
     descr.clear()
     eng.gemm_log = []
+    torch.cuda._sleep(30_000_000)   # ~15 ms head start: the whole step is queued before the GPU starts it
     eng.forward(batch, training=True)
     eng.backward()
     torch.cuda.synchronize()
-        if it == 3:
+    if it == 3:
         total = 0.0
-        for i, ((e0, e1, f, nb), d) in enumerate(zip(eng.gemm_log, descr)):
+        for i, ((e0, e1, f, nb, _), d) in enumerate(zip(eng.gemm_log, descr)):
             us = e0.elapsed_time(e1) * 1e3
             total += us
-            print(f"{i:2d} M={d[0]:6d} N={d[1]:5d} K={d[2]:6d} {us:8.1f} us {f / us / 1e6:8.1f} TF/s  {d[3]}")
+            print(f"{i:2d} M={d[0]:6d} N={d[1]:5d} K={d[2]:6d} {us:8.1f} us {f / us / 1e6:8.1f} TF/s {nb / us / 1e3:8.1f} GB/s  {d[3]}")
         print(f"total {total:.1f} us")
     eng.gemm_log = None
     eng.grad.zero_()
