@@ -454,7 +454,16 @@ extern "C" int tt_gemm_bf16(const tt_gemm_args* a, void* stream_) {
       if (a->K >= 4096) bn = a->N >= 256 ? 256 : (a->N > 64 ? 128 : 64);
       else bn = a->N >= 512 ? 128 : 64;
     }
-    else bn = a->N > 128 ? 256 : (a->N > 64 ? 128 : 64);
+    else {
+      // The widest tile that still gives every SM a tile; problems too small for that (the B-row GEMMs of
+      // the heads and of the single-row last layer) are latency-bound and want as many CTAs as possible
+      // (256x256x256: 8.1 us with one 256-wide tile per row block, 5.0 us with four 64-wide ones).
+      const int tm = (a->M + kBlockM - 1) / kBlockM;
+      bn = 64;
+      for (int cand = 256; cand > 64; cand >>= 1) {
+        if (a->N > cand / 2 && tm * ((a->N + cand - 1) / cand) >= num_sms()) { bn = cand; break; }
+      }
+    }
   }
   TT_REQUIRE(bn == 64 || bn == 128 || bn == 256, "tt_gemm_bf16: block_n must be 64/128/256");
   p.block_n = bn;

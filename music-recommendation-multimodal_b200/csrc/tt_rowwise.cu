@@ -562,8 +562,8 @@ __global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* _
 // Backward of embed_ln_fwd w.r.t. its first LayerNorm: dx0 [T,256] -> dE (scatter-add, id 0
 // skipped: padding_idx), dP (per position), d(ln_w), d(ln_b). The pre-LN sum E[id]+P[pos] is
 // re-gathered instead of being stored.
-// Grid: one block per group of positions so that dP needs no atomics across the batch:
-// block handles position `pos`, its 8 warps stride over the batch.
+// Grid (L, S): block (pos, s) handles position `pos` for every S-th group of 8 sequences, so dP takes
+// S atomics per element; S is chosen so that all blocks are resident at 2 per SM.
 // --------------------------------------------------------------------------------------------
 struct EmbedBwdParams {
   const int64_t* ids; const float* E; const float* P; const float* ln_w; const float* ln_b;
@@ -572,7 +572,7 @@ struct EmbedBwdParams {
   float* dE; float* dP; float* dgamma; float* dbeta;
 };
 
-__global__ void __launch_bounds__(kRowThreads) embed_ln_bwd_kernel(const EmbedBwdParams p) {
+__global__ void __launch_bounds__(kRowThreads, 2) embed_ln_bwd_kernel(const EmbedBwdParams p) {
   pdl_launch_dependents();
   pdl_wait();
   constexpr int NV = 2, E_ = 8, W = 256;
@@ -585,12 +585,30 @@ __global__ void __launch_bounds__(kRowThreads) embed_ln_bwd_kernel(const EmbedBw
 #pragma unroll
   for (int i = 0; i < E_; ++i) { dg[i] = 0.f; db[i] = 0.f; dp[i] = 0.f; }
   const uint64_t seed = p.drop_thresh ? read_seed(p.seed, p.seed_dev) : 0;
-  for (int b = wib; b < p.B; b += kRowThreads / 32) {
+  // The id -> table row -> arithmetic chain is two dependent memory latencies per row; the ids run two
+  // rows ahead and the (table row, gradient row) pair one row ahead of the arithmetic.
+  const int stride = (kRowThreads / 32) * gridDim.y;
+  int b = wib * gridDim.y + blockIdx.y;
+  int64_t id_n = 0, id_nn = 0;
+  float e_n[E_], g_n[E_];
+  if (b < p.B) {
+    id_n = p.ids[static_cast<size_t>(b) * p.L + pos];
+    load_row<NV>(p.E + static_cast<size_t>(id_n) * W, lane, e_n);
+    load_row<NV>(p.dx0 + (static_cast<size_t>(b) * p.L + pos) * W, lane, g_n);
+  }
+  if (b + stride < p.B) id_nn = p.ids[static_cast<size_t>(b + stride) * p.L + pos];
+  for (; b < p.B; b += stride) {
     const size_t row = static_cast<size_t>(b) * p.L + pos;
-    const int64_t id = p.ids[row];
+    const int64_t id = id_n;
     float e[E_], g[E_], xhat[E_];
-    load_row<NV>(p.E + static_cast<size_t>(id) * W, lane, e);
-    load_row<NV>(p.dx0 + row * W, lane, g);
+#pragma unroll
+    for (int i = 0; i < E_; ++i) { e[i] = e_n[i]; g[i] = g_n[i]; }
+    id_n = id_nn;
+    if (b + stride < p.B) {
+      load_row<NV>(p.E + static_cast<size_t>(id_n) * W, lane, e_n);
+      load_row<NV>(p.dx0 + (static_cast<size_t>(b + stride) * p.L + pos) * W, lane, g_n);
+    }
+    if (b + 2 * stride < p.B) id_nn = p.ids[static_cast<size_t>(b + 2 * stride) * p.L + pos];
 #pragma unroll
     for (int i = 0; i < E_; ++i) e[i] += q[i];
     float mean, rstd;
@@ -634,7 +652,7 @@ __global__ void __launch_bounds__(kRowThreads) embed_ln_bwd_kernel(const EmbedBw
     for (int k = 0; k < kRowThreads / 32; ++k) { a0 += s_red[0][k][c]; a1 += s_red[1][k][c]; a2 += s_red[2][k][c]; }
     atomicAdd(p.dgamma + c, a0);
     atomicAdd(p.dbeta + c, a1);
-    atomicAdd(p.dP + static_cast<size_t>(pos) * W + c, a2);  // one block per position: no contention
+    atomicAdd(p.dP + static_cast<size_t>(pos) * W + c, a2);  // gridDim.y blocks per position
   }
 }
 
@@ -754,7 +772,10 @@ extern "C" int tt_embed_ln_bwd(const int64_t* ids, const float* E, const float* 
   p.drop_scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
   p.seed = seed; p.seed_dev = seed_dev; p.site = site;
   p.dE = dE; p.dP = dP; p.dgamma = dgamma; p.dbeta = dbeta;
-  TT_CHECK_CUDA(launch_k(embed_ln_bwd_kernel, dim3(L), dim3(kRowThreads), 0, stream, p));
+  int splits = (2 * num_sms()) / L;
+  if (splits < 1) splits = 1;
+  if (splits > (B + 7) / 8) splits = (B + 7) / 8;
+  TT_CHECK_CUDA(launch_k(embed_ln_bwd_kernel, dim3(L, splits), dim3(kRowThreads), 0, stream, p));
   TT_LAUNCH_CHECK();
   return TT_OK;
 }

@@ -66,3 +66,23 @@ for name, N, K, fn in cases:
         us = t(lambda i: fn(i, bn))
         row.append(f"bn={bn:3d}: {us:6.1f} us")
     print(f"{name}  " + "  ".join(row))
+
+print("== B-row (M = 256) shapes: latency-bound, more CTAs vs wider tiles")
+xb = torch.randn(256, FF, **bf)
+ob16 = torch.empty(256, FF, **bf)
+ob32 = torch.empty(256, FF, device=dev)
+tiny = [
+    ("256x256x256  bias f32      ", lambda i, bn: ops.gemm(xb[:, :256], w[:256, :256], bias=bias, out_f32=ob32[:, :256], block_n=bn)),
+    ("256x1024x256 bias relu bf16", lambda i, bn: ops.gemm(xb[:, :256], w[:, :256], bias=bias, relu=True, out_bf16=ob16, block_n=bn)),
+    ("256x256x1024 bias f32      ", lambda i, bn: ops.gemm(xb, w[:256], bias=bias, out_f32=ob32[:, :256], block_n=bn)),
+    ("256x512x512  bias f32      ", lambda i, bn: ops.gemm(xb[:, :512], w[:512, :512], bias=bias, out_f32=ob32[:, :512], block_n=bn)),
+    ("256x256x256  B^T f32       ", lambda i, bn: ops.gemm(xb[:, :256], w[:256, :256], b_mn=True, out_f32=ob32[:, :256], block_n=bn)),
+    ("256x256x1024 B^T f32       ", lambda i, bn: ops.gemm(xb, w[:, :256], b_mn=True, out_f32=ob32[:, :256], block_n=bn)),
+    ("256x1024x256 B^T bf16      ", lambda i, bn: ops.gemm(xb[:, :256], w[:256], b_mn=True, out_bf16=ob16, block_n=bn)),
+]
+for name, fn in tiny:
+    row = []
+    for bn in (64, 128, 256):
+        us = t(lambda i: fn(i, bn), iters=20)
+        row.append(f"bn={bn:3d}: {us:6.2f} us")
+    print(f"{name}  " + "  ".join(row))
