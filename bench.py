@@ -273,7 +273,7 @@ def run_ours(args, rank, world, local_rank):
     step_flops = 3.0 * flops_per_sample_fwd(L, B) * B
 
     # ---- retrieval (configs[2]) -----------------------------------------------------------
-    retr = bench_retrieval(eng, rank, world, dev, peaks)
+    retr = None if args.skip_retrieval else bench_retrieval(eng, rank, world, dev, peaks)
 
     cpu = None
     if rank == 0 and world == 1 and not args.skip_cpu:
@@ -420,6 +420,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--skip-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
+    ap.add_argument("--skip-retrieval", action="store_true", help="skip the c3 retrieval section (A/B timing runs)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

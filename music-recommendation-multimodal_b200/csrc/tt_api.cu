@@ -83,13 +83,24 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t*
   return TT_OK;
 }
 
-bool pdl_enabled() {
+int pdl_mode() {
   static int v = -1;
   if (v < 0) {
-    const char* e = getenv("TT_PDL");   // opt-in: measured 1.576 ms (on) vs 1.528 ms (off) per c2 step on B200
-    v = (e && atoi(e) != 0) ? 1 : 0;
+    const char* e = getenv("TT_PDL");
+    v = e ? atoi(e) : 2;   // measured on the c2 step: 1.308 ms (0), 1.326 ms (1), 1.282 ms (2)
+    if (v < 0 || v > 2) v = 2;
   }
-  return v == 1;
+  return v;
+}
+
+int pdl_max_ctas() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("TT_PDL_MAX_CTAS");
+    v = e ? atoi(e) : 64;
+    if (v < 1) v = 64;
+  }
+  return v;
 }
 
 int num_sms() {

@@ -64,7 +64,8 @@ int num_sms();
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
-bool pdl_enabled();
+int pdl_mode();       // TT_PDL: 0 = never, 1 = every launch, 2 = small grids only (default)
+int pdl_max_ctas();   // TT_PDL_MAX_CTAS: largest grid that launches programmatically in mode 2
 
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
@@ -78,7 +79,13 @@ inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, siz
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  // Programmatic dependent launch lets this grid start (and run its prologue up to griddepcontrol.wait)
+  // while the previous kernel in the stream drains. Early CTAs of a big grid would sit on SMs the
+  // concurrent weight-gradient / item-tower streams could use, so mode 2 restricts it to the small
+  // latency-bound launches (B-row GEMMs, heads, loss), where launch + prologue latency is the cost.
+  const int mode = pdl_mode();
+  const size_t ctas = static_cast<size_t>(grid.x) * grid.y * grid.z;
+  cfg.numAttrs = (mode == 1 || (mode == 2 && ctas <= static_cast<size_t>(pdl_max_ctas()))) ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
