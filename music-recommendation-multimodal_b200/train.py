@@ -85,6 +85,7 @@ class TrainStepRunner:
             self.static["user_idx"] = torch.zeros(B, **i64)
         self.loss_host = torch.zeros((), dtype=torch.float32).pin_memory()
         self._graphs = None
+        self._cap_stream = None
         self.kernels_per_step = 0
         self._warm = False
 
@@ -218,7 +219,12 @@ class TrainStepRunner:
                     graphs.append(("comm", item))
                 else:
                     g = torch.cuda.CUDAGraph()
-                    with torch.cuda.graph(g):
+                    # captured on a high-priority stream: the kernel nodes of the main chain inherit it, the
+                    # engine's side streams (weight gradients, item tower) stay at the default priority, so
+                    # the block scheduler serves the critical path first
+                    if self._cap_stream is None:
+                        self._cap_stream = torch.cuda.Stream(device=self.eng.device, priority=-1)
+                    with torch.cuda.graph(g, stream=self._cap_stream):
                         for fn in item:
                             fn()
                     g.replay()
