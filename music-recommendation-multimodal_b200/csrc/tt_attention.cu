@@ -194,7 +194,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
           pv[t] = e;
         }
         if (p.drop_thresh) {
-          if ((didx0 & 1u) == 0u) {
+          if ((didx0 & 3u) == 0u) {          // L % 4 == 0: four keys per hash word
+#pragma unroll
+            for (int t = 0; t < 32; t += 4) {
+              bool k[4];
+              drop_keep_quad(dkey, didx0 + t, p.drop_thresh, k);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) pv[t + e] = k[e] ? pv[t + e] * p.drop_scale : 0.f;
+            }
+          } else if ((didx0 & 1u) == 0u) {
 #pragma unroll
             for (int t = 0; t < 32; t += 2) {
               bool k0, k1;
@@ -318,8 +326,11 @@ __device__ __forceinline__ void store_row32_bf16(__nv_bfloat16* dst, const uint3
 //   together. LONG = true: L <= 512 (four query tiles): the four dQ accumulators need 256 columns,
 //   so S and dP SHARE one 128-column region — P is formed from S first (un-dropped P parked as bf16
 //   in the dS tile), then dP = dO V^T overwrites S and dS replaces the parked P.
-template <bool LONG>
-__global__ void __launch_bounds__(256, 1)
+// CG = column groups: 128*CG threads, thread (row, g) owns 4/CG of the four 32-column chunks of every
+// 128-key tile. The per-iteration element-wise phase between the two MMA groups is latency-bound, so the
+// fast layout runs it with 16 warps (CG = 4); LONG keeps 8 (its register tiles are larger).
+template <bool LONG, int CG>
+__global__ void __launch_bounds__(128 * CG, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
                 const AttnBwdParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -328,7 +339,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
-  const int q = warp & 3, hf = warp >> 2;
+  const int q = warp & 3, grp = warp >> 2;
+  constexpr int CPT = 4 / CG;   // 32-column chunks per thread per key tile
   const int row = q * 32 + lane;
   const int bh = blockIdx.x;
   const int b = bh / p.H, h = bh % p.H;
@@ -391,7 +403,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     }
   }
   // delta_i = rowsum(dO * O), lse -> smem (generic loads; rows beyond L are treated as zero)
-  for (int pos = tid; pos < nq * kTile; pos += 256) {
+  for (int pos = tid; pos < nq * kTile; pos += 128 * CG) {
     float delta = 0.f, lse2 = 0.f;
     if (pos < p.L) {
       const uint4* o = reinterpret_cast<const uint4*>(p.ctx + static_cast<size_t>(seq_row0 + pos) * D + h * kDh);
@@ -421,8 +433,6 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
   const uint32_t idesc_q = umma_idesc_bf16(kTile, kDh, false, true);       // dS K
   uint32_t it = 0;  // (j,i) iteration counter -> mbarrier phase
   uint32_t dq_started = 0;  // bit i set once dQ_i has received its first MMA
-  uint8_t* pchunk = sPd + static_cast<size_t>(hf) * kTileBytes;
-  uint8_t* dchunk = sDS + static_cast<size_t>(hf) * kTileBytes;
 
   for (int j = 0; j < nq; ++j) {
     if (tid == 0) {
@@ -471,9 +481,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       if constexpr (LONG) {
         // ---- part A: P from S. Pd -> sPd, un-dropped P parked (bf16) in the dS tile ---------------
 #pragma unroll
-        for (int cc = 0; cc < 2; ++cc) {
-          const int cg = 2 * hf + cc;
-          const int u0 = cc * 4;
+        for (int cc = 0; cc < CPT; ++cc) {
+          const int cg = CPT * grp + cc;
+          const int u0 = (cg & 1) * 4;
+          uint8_t* pchunk = sPd + static_cast<size_t>(cg >> 1) * kTileBytes;
+          uint8_t* dchunk = sDS + static_cast<size_t>(cg >> 1) * kTileBytes;
           if (!(diag && cg > q)) {
             uint32_t rs[32];
             tmem_ld32(lane_base + T_S + cg * 32, rs);
@@ -528,9 +540,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         tc_fence_after();
         // ---- part B: dS = P * (dropout(dP) - delta) * scale replaces the parked P ------------------
 #pragma unroll
-        for (int cc = 0; cc < 2; ++cc) {
-          const int cg = 2 * hf + cc;
-          const int u0 = cc * 4;
+        for (int cc = 0; cc < CPT; ++cc) {
+          const int cg = CPT * grp + cc;
+          const int u0 = (cg & 1) * 4;
+          uint8_t* pchunk = sPd + static_cast<size_t>(cg >> 1) * kTileBytes;
+          uint8_t* dchunk = sDS + static_cast<size_t>(cg >> 1) * kTileBytes;
           if (!(diag && cg > q)) {
             uint32_t rp[32];
             tmem_ld32(lane_base + T_DP + cg * 32, rp);
@@ -566,9 +580,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         }
       } else {
 #pragma unroll
-      for (int cc = 0; cc < 2; ++cc) {
-        const int cg = 2 * hf + cc;
-        const int u0 = cc * 4;
+      for (int cc = 0; cc < CPT; ++cc) {
+        const int cg = CPT * grp + cc;
+        const int u0 = (cg & 1) * 4;
+        uint8_t* pchunk = sPd + static_cast<size_t>(cg >> 1) * kTileBytes;
+        uint8_t* dchunk = sDS + static_cast<size_t>(cg >> 1) * kTileBytes;
         if (!(diag && cg > q)) {
           uint32_t rs[32], rp[32];
           tmem_ld32(lane_base + T_S + cg * 32, rs);
@@ -579,7 +595,15 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
           uint32_t keepmask = 0xFFFFFFFFu;
           if (p.drop_thresh) {
             keepmask = 0u;
-            if ((didx0 & 1u) == 0u) {
+            if ((didx0 & 3u) == 0u) {
+#pragma unroll
+              for (int t = 0; t < 32; t += 4) {
+                bool k[4];
+                drop_keep_quad(dkey, didx0 + t, p.drop_thresh, k);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) keepmask |= (k[e] ? 1u : 0u) << (t + e);
+              }
+            } else if ((didx0 & 1u) == 0u) {
 #pragma unroll
               for (int t = 0; t < 32; t += 2) {
                 bool k0, k1;
@@ -661,17 +685,24 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       tc_fence_after();
     }
     // ---- dK_j, dV_j complete: TMEM -> dqkv (each thread: 32 of the 64 columns) -------------
-    {
+    if (CG == 2 || grp < 2) {
+      // 64 output columns = two 32-column halves: warps of groups 0/1 (CG = 4: groups 0,1 take dK, 2,3 dV)
+      const int hf = grp & 1;
       const int pos = j * kTile + row;
       __nv_bfloat16* grow = p.dqkv + static_cast<size_t>(seq_row0 + pos) * (3 * D) + h * kDh + hf * 32;
-      uint32_t rk[32], rv[32];
+      uint32_t rk[32];
       tmem_ld32(lane_base + T_DK + hf * 32, rk);
+      tmem_ld_wait();
+      if (pos < p.L) store_row32_bf16(grow + D, rk);
+    }
+    if (CG == 2 || grp >= 2) {
+      const int hf = grp & 1;
+      const int pos = j * kTile + row;
+      __nv_bfloat16* grow = p.dqkv + static_cast<size_t>(seq_row0 + pos) * (3 * D) + h * kDh + hf * 32;
+      uint32_t rv[32];
       tmem_ld32(lane_base + T_DV + hf * 32, rv);
       tmem_ld_wait();
-      if (pos < p.L) {
-        store_row32_bf16(grow + D, rk);
-        store_row32_bf16(grow + 2 * D, rv);
-      }
+      if (pos < p.L) store_row32_bf16(grow + 2 * D, rv);
     }
     tc_fence_before();
     __syncthreads();  // everyone has drained dK/dV before the next j overwrites them
@@ -679,7 +710,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
   }
 
   // ---- dQ_i -> dqkv ---------------------------------------------------------------------
-  for (int i = 0; i < nq; ++i) {
+  for (int i = (CG == 2 ? 0 : (grp >> 1)); i < nq; i += (CG == 2 ? 1 : 2)) {   // CG = 4: groups (0,1) / (2,3) alternate tiles
+    const int hf = grp & 1;
     const int pos = i * kTile + row;
     uint32_t r[32];
     tmem_ld32(lane_base + T_DQ + i * kDh + hf * 32, r);
@@ -777,13 +809,13 @@ extern "C" int tt_attn_causal_bwd(const void* qkv, const void* ctx, const void* 
                       static_cast<size_t>(2 * p.nq * kTile) * sizeof(float);
   static bool configured = false;
   if (!configured) {
-    TT_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
-    TT_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    TT_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    TT_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
     configured = true;
   }
   TT_REQUIRE(smem <= 232448, "tt_attn_causal_bwd: shared memory %zu too large", smem);
-  if (p.nq <= 2) TT_CHECK_CUDA(launch_k(attn_bwd_kernel<false>, dim3(B * H), dim3(256), smem, stream, tmQ, tmDO, p));
-  else TT_CHECK_CUDA(launch_k(attn_bwd_kernel<true>, dim3(B * H), dim3(256), smem, stream, tmQ, tmDO, p));
+  if (p.nq <= 2) TT_CHECK_CUDA(launch_k(attn_bwd_kernel<false, 4>, dim3(B * H), dim3(512), smem, stream, tmQ, tmDO, p));
+  else TT_CHECK_CUDA(launch_k(attn_bwd_kernel<true, 2>, dim3(B * H), dim3(256), smem, stream, tmQ, tmDO, p));
   TT_LAUNCH_CHECK();
   return TT_OK;
 }
