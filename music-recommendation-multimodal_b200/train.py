@@ -74,18 +74,31 @@ class TrainStepRunner:
             self._pack_lse = torch.empty(B, 2, device=engine.device)
             self._pack_lse_all = torch.empty(world_size * B, 2, device=engine.device)
         dev, m = engine.device, engine.cfg.modality_dim
-        i64 = dict(device=dev, dtype=torch.long)
-        self.static: Dict[str, torch.Tensor] = {
-            "history_ids": torch.zeros(B, L, **i64), "history_mask": torch.zeros(B, L, **i64),
-            "user_gender": torch.zeros(B, **i64), "user_country": torch.zeros(B, **i64),
-            "target_audio": torch.zeros(B, m, device=dev), "target_image": torch.zeros(B, m, device=dev),
-            "target_input_ids": torch.zeros(B, m, device=dev), "target_tabular": torch.zeros(B, m, device=dev),
-        }
+        # One device buffer holds every input of a step (each field 256-byte aligned); the `static` tensors the
+        # graph reads are views into it, so a batch packed the same way on the host (`pack_host`) arrives with
+        # ONE host->device copy.
+        fields = [("history_ids", (B, L), torch.long), ("history_mask", (B, L), torch.long),
+                  ("user_gender", (B,), torch.long), ("user_country", (B,), torch.long),
+                  ("target_audio", (B, m), torch.float32), ("target_image", (B, m), torch.float32),
+                  ("target_input_ids", (B, m), torch.float32), ("target_tabular", (B, m), torch.float32)]
         if with_user_idx:
-            self.static["user_idx"] = torch.zeros(B, **i64)
+            fields.append(("user_idx", (B,), torch.long))
+        self._fields, off = [], 0
+        for name, shape, dt in fields:
+            n = 1
+            for d in shape:
+                n *= d
+            nbytes = n * torch.empty((), dtype=dt).element_size()
+            self._fields.append((name, shape, dt, off, nbytes))
+            off += (nbytes + 255) // 256 * 256
+        self._static_buf = torch.zeros(off, device=dev, dtype=torch.uint8)
+        self.static: Dict[str, torch.Tensor] = {
+            name: self._static_buf[o:o + nb].view(dt).view(shape) for name, shape, dt, o, nb in self._fields}
         self.loss_host = torch.zeros((), dtype=torch.float32).pin_memory()
         self._graphs = None
         self._cap_stream = None
+        self._stage = None
+        self._staged = False
         self.kernels_per_step = 0
         self._warm = False
 
@@ -238,10 +251,54 @@ class TrainStepRunner:
                 item.replay()
         return self._loss_tensor()
 
-    def step_from_host(self, host_batch: Dict[str, torch.Tensor]) -> float:
-        """Host batch -> device -> step -> loss on the host (one sync, like the reference's loss.item())."""
-        self.load_batch(host_batch)
+    # -- double-buffered input: the NEXT batch crosses PCIe while the current step computes ----------
+    def pack_host(self, batch: Dict[str, torch.Tensor]) -> torch.Tensor:
+        """A batch as ONE pinned uint8 buffer in the layout of the device input buffer (a collate function
+        would write this directly); `stage_batch` / `step_from_host` move it with a single copy."""
+        out = torch.empty(self._static_buf.numel(), dtype=torch.uint8).pin_memory()
+        for name, shape, dt, o, nb in self._fields:
+            out[o:o + nb].view(dt).view(shape).copy_(batch[name])
+        return out
+
+    def stage_batch(self, host_batch) -> None:
+        """Start the host->device copy of a (pinned) batch — a dict or a `pack_host` buffer — into the staging
+        buffer on the copy stream. The following ``step_from_host(None)`` consumes it with one device copy."""
+        if self._stage is None:
+            self._stage_buf = torch.empty_like(self._static_buf)
+            self._stage = {name: self._stage_buf[o:o + nb].view(dt).view(shape)
+                           for name, shape, dt, o, nb in self._fields}
+            self._copy_stream = torch.cuda.Stream(device=self.eng.device)
+            self._staged_ev = torch.cuda.Event()
+            self._consumed_ev = torch.cuda.Event()
+            self._consumed_ev.record()
+        self._copy_stream.wait_event(self._consumed_ev)      # the previous staged batch has been picked up
+        with torch.cuda.stream(self._copy_stream):
+            if isinstance(host_batch, torch.Tensor):
+                self._stage_buf.copy_(host_batch, non_blocking=True)
+            else:
+                for k, dst in self._stage.items():
+                    dst.copy_(host_batch[k], non_blocking=True)
+            self._staged_ev.record()
+        self._staged = True
+
+    def step_from_host(self, host_batch, prefetch=None) -> float:
+        """Host batch -> device -> step -> loss on the host (one sync, like the reference's loss.item()).
+        ``host_batch=None`` takes the batch announced by ``stage_batch`` / the previous call's ``prefetch``;
+        ``prefetch`` (the next batch, pinned) is copied while this step runs."""
+        if isinstance(host_batch, torch.Tensor):
+            self._static_buf.copy_(host_batch, non_blocking=True)
+        elif host_batch is not None:
+            self.load_batch(host_batch)
+        else:
+            assert self._staged, "step_from_host(None) needs a staged batch (stage_batch / prefetch=)"
+            main = torch.cuda.current_stream()
+            main.wait_event(self._staged_ev)
+            self._static_buf.copy_(self._stage_buf, non_blocking=True)
+            self._consumed_ev.record()
+            self._staged = False
         loss = self.step_resident()
+        if prefetch is not None:
+            self.stage_batch(prefetch)
         if self.gathered:
             loss = loss.clone()
             dist.all_reduce(loss, op=dist.ReduceOp.SUM, group=self.group)
@@ -256,14 +313,28 @@ def train_one_epoch(model, dataloader, optimizer, device, epoch, is_main_process
     total_loss, num_batches = 0.0, len(dataloader)
     runner: Optional[TrainStepRunner] = None
     fused = isinstance(optimizer, FusedAdamW)
+    staged = False
     world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
-    for i, batch in enumerate(dataloader):
+    it = iter(dataloader)
+    batch = next(it, None)
+    i = -1
+    while batch is not None:
+        i += 1
+        nxt = next(it, None)
         if fused:
             B, L = batch["history_ids"].shape
             if runner is None or (runner.B, runner.L) != (B, L):
                 runner = TrainStepRunner(model.engine, B, L, world_size=world, lr=optimizer.lr,
                                          with_user_idx="user_idx" in batch)
-            loss_val = runner.step_from_host({k: v for k, v in batch.items() if k in _BATCH_KEYS})
+                staged = False
+            cur = None if staged else {k: v for k, v in batch.items() if k in _BATCH_KEYS}
+            # the next batch goes over PCIe during this step when it is pinned and has the same shape
+            pre = None
+            if nxt is not None and tuple(nxt["history_ids"].shape) == (B, L) and \
+                    all(v.is_pinned() for k, v in nxt.items() if k in _BATCH_KEYS and isinstance(v, torch.Tensor)):
+                pre = {k: v for k, v in nxt.items() if k in _BATCH_KEYS}
+            loss_val = runner.step_from_host(cur, prefetch=pre)
+            staged = pre is not None
         else:
             for k, v in batch.items():
                 if isinstance(v, torch.Tensor):
@@ -277,6 +348,7 @@ def train_one_epoch(model, dataloader, optimizer, device, epoch, is_main_process
         total_loss += loss_val
         if is_main_process and (i + 1) % log_interval == 0:
             logger.info(f"Epoch {epoch} [{i+1}/{num_batches}] | Loss: {loss_val:.4f}")
+        batch = nxt
     return total_loss / max(num_batches, 1)
 
 

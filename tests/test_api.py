@@ -67,6 +67,45 @@ def test_train_one_epoch_fused_reduces_loss():
     assert 0.0 <= r <= 1.0
 
 
+def test_train_one_epoch_prefetch_path_is_the_same_training():
+    """Pinned batches take the double-buffered route (next batch copied during the current step); the loss
+    sequence must be the one the plain route produces from the same state (dropout off: deterministic up to
+    atomic-add order)."""
+    from mrm_b200 import synthetic
+    from mrm_b200.train import FusedAdamW, train_one_epoch
+    cfg0 = _model(dropout=0.0).engine.cfg
+    batches = [synthetic.make_batch(cfg0, 64, seed=40 + i) for i in range(5)]
+    pinned = [{k: v.pin_memory() for k, v in b.items()} for b in batches]
+    means = []
+    for loader in (batches, pinned):
+        m = _model(dropout=0.0)
+        opt = FusedAdamW(m, lr=1e-3)
+        means.append([train_one_epoch(m, loader, opt, torch.device("cuda"), epoch=e, is_main_process=False)
+                      for e in range(2)])
+    for a, b in zip(*means):
+        assert abs(a - b) < 5e-3, means
+
+
+def test_packed_host_batch_is_the_same_step():
+    """One pinned buffer (TrainStepRunner.pack_host) in, same loss out as the dict route."""
+    from mrm_b200 import synthetic
+    from mrm_b200.train import TrainStepRunner
+    losses = []
+    for packed in (False, True):
+        m = _model(dropout=0.0)
+        cfg = m.engine.cfg
+        batches = [synthetic.make_batch(cfg, 64, seed=70 + i) for i in range(3)]
+        r = TrainStepRunner(m.engine, 64, 50, lr=1e-3)
+        if packed:
+            bufs = [r.pack_host(b) for b in batches]
+            r.stage_batch(bufs[0])
+            losses.append([r.step_from_host(None, prefetch=bufs[(i + 1) % 3]) for i in range(3)])
+        else:
+            losses.append([r.step_from_host(b) for b in batches])
+    for a, b in zip(*losses):
+        assert abs(a - b) < 5e-3, losses
+
+
 def test_calculate_metrics_global_matches_oracle():
     from mrm_b200 import synthetic
     from mrm_b200.evaluate_metrics import calculate_metrics_global
