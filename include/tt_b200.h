@@ -157,6 +157,12 @@ typedef struct tt_chain_args {
   float* dgamma;
   float* dbeta;
   float* dx_colsum;
+  /* backward, sparse residual: instead of a dense `resid`, sequence b (rows [b*seq_len, (b+1)*seq_len)) adds
+   * resid_rows[b, :] to its row b*seq_len + resid_last_idx[b] only — the residual-stream gradient of the
+   * single-row last layer, which is non-zero for one position per sequence. Exclusive with `resid`. */
+  const float* resid_rows;
+  const int32_t* resid_last_idx;
+  int32_t resid_seq_len;
 } tt_chain_args;
 int tt_chain_fwd(const tt_chain_args* args, void* stream);
 int tt_chain_bwd(const tt_chain_args* args, void* stream);

@@ -103,6 +103,7 @@ class ChainArgs(ctypes.Structure):
         ("dout", c_void_p), ("resid", c_void_p), ("dx_f32", c_void_p), ("dx_bf16", c_void_p),
         ("drop2_p", c_float), ("drop2_site", c_uint32),
         ("dgamma", c_void_p), ("dbeta", c_void_p), ("dx_colsum", c_void_p),
+        ("resid_rows", c_void_p), ("resid_last_idx", c_void_p), ("resid_seq_len", c_int32),
     ]
 
 

@@ -191,6 +191,9 @@ struct ChainParams {
   // backward only
   const float* dout;       // [R, W] gradient w.r.t. the chain output
   const float* resid;      // nullable [R, W]: added to dx
+  const float* resid_rows; // nullable [R / resid_L, W]: added to row b*resid_L + resid_idx[b] of sequence b only
+  const int32_t* resid_idx;
+  int resid_L;
   float* dx_f32;           // nullable
   __nv_bfloat16* dx_bf16;  // nullable; receives dropout2(dx) when drop2_thresh != 0
   uint32_t drop2_thresh; float drop2_scale; uint32_t site2;
@@ -324,6 +327,14 @@ __global__ void __launch_bounds__(kRowThreads, 2) chain_bwd_kernel(const ChainPa
     if (p.resid) {
 #pragma unroll
       for (int i = 0; i < E; ++i) g[i] += r[i];
+    } else if (p.resid_rows) {
+      const int b = row / p.resid_L;
+      if (row - b * p.resid_L == __ldg(p.resid_idx + b)) {     // warp-uniform: one row per sequence
+        float rr[E];
+        load_row<NV>(p.resid_rows + static_cast<size_t>(b) * W, lane, rr);
+#pragma unroll
+        for (int i = 0; i < E; ++i) g[i] += rr[i];
+      }
     }
     if (p.dx_f32) store_row<NV>(p.dx_f32 + static_cast<size_t>(row) * W, lane, g);
     if (p.dx_bf16) {
@@ -793,6 +804,10 @@ static int fill_chain(ChainParams& p, const tt_chain_args* a, const char* who) {
   p.l2norm = a->l2norm; p.l2_eps = a->l2_eps > 0.f ? a->l2_eps : 1e-12f;
   p.out_f32 = a->out_f32; p.out_bf16 = static_cast<__nv_bfloat16*>(a->out_bf16);
   p.dout = a->dout; p.resid = a->resid; p.dx_f32 = a->dx_f32;
+  p.resid_rows = a->resid_rows; p.resid_idx = a->resid_last_idx; p.resid_L = a->resid_seq_len;
+  TT_REQUIRE(!(a->resid && a->resid_rows), "%s: resid and resid_rows are exclusive", who);
+  TT_REQUIRE(!a->resid_rows || (a->resid_last_idx && a->resid_seq_len > 0 && a->rows % a->resid_seq_len == 0),
+             "%s: resid_rows needs resid_last_idx and a seq_len dividing rows", who);
   p.dx_bf16 = static_cast<__nv_bfloat16*>(a->dx_bf16);
   p.drop2_thresh = drop_threshold(a->drop2_p);
   p.drop2_scale = a->drop2_p > 0.f ? 1.f / (1.f - a->drop2_p) : 1.f;

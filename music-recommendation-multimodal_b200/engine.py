@@ -423,14 +423,15 @@ class TwoTowerEngine:
         gemm(dkv, Wqkv[D:], b_mn=True, out_f32=ws["dh"])
         ops.scatter_rows_add(ws["dhq"], ws["last_idx"], B, L, ws["dh"], accumulate=True)
         # --- residual gradient of the layer input: only the gathered rows carry one
-        dx.zero_()
-        ops.scatter_rows_add(ws["dxmid_q"], ws["last_idx"], B, L, dx, accumulate=False)
+        # the residual-stream gradient into this layer's input is non-zero for ONE row per sequence
+        # (dxmid_q): chain_bwd adds it to that row instead of reading a zero-filled [T, 256] tensor
         extra = {}
         if l > 0:
             extra = dict(dx_bf16=ws[f"dy2_{l - 1}"], drop2_p=dp, drop2_site=_site(l - 1, 3),
                          dx_colsum=g[self._lp(l - 1, "linear2.bias")])
         ops.chain_bwd(x_in, ln=(p[self._lp(l, "norm1.weight")], p[self._lp(l, "norm1.bias")]), dout=ws["dh"],
-                      resid=dx, dx_f32=dx_other, seed=seed, seed_dev=sdev, dgamma=g[self._lp(l, "norm1.weight")],
+                      resid_rows=ws["dxmid_q"], resid_last_idx=ws["last_idx"], resid_seq_len=L, dx_f32=dx_other,
+                      seed=seed, seed_dev=sdev, dgamma=g[self._lp(l, "norm1.weight")],
                       dbeta=g[self._lp(l, "norm1.bias")], **extra)
         return dx_other, dx
 

@@ -149,8 +149,10 @@ def embed_ln_bwd(ids, E, P, ln_w, ln_b, dx0, B, L, dE, dP, dgamma, dbeta, drop_p
 
 def _chain_args(x, *, ln=None, relu=False, drop_p=0.0, seed=0, seed_dev=None, site=0, l2norm=False,
                 l2_eps=1e-12, out_f32=None, out_bf16=None, dout=None, resid=None, dx_f32=None, dx_bf16=None,
-                drop2_p=0.0, drop2_site=0, dgamma=None, dbeta=None, dx_colsum=None) -> ChainArgs:
-    _require_cuda(x, out_f32, out_bf16, dout, resid, dx_f32, dx_bf16, dgamma, dbeta, dx_colsum)
+                drop2_p=0.0, drop2_site=0, dgamma=None, dbeta=None, dx_colsum=None, resid_rows=None,
+                resid_last_idx=None, resid_seq_len=0) -> ChainArgs:
+    _require_cuda(x, out_f32, out_bf16, dout, resid, dx_f32, dx_bf16, dgamma, dbeta, dx_colsum, resid_rows,
+                  resid_last_idx)
     assert x.dtype == torch.float32 and x.dim() == 2 and x.is_contiguous()
     a = ChainArgs()
     a.x, a.rows, a.width = x.data_ptr(), x.shape[0], x.shape[1]
@@ -164,6 +166,11 @@ def _chain_args(x, *, ln=None, relu=False, drop_p=0.0, seed=0, seed_dev=None, si
     a.dout, a.resid, a.dx_f32, a.dx_bf16 = _ptr(dout), _ptr(resid), _ptr(dx_f32), _ptr(dx_bf16)
     a.drop2_p, a.drop2_site = drop2_p, drop2_site
     a.dgamma, a.dbeta, a.dx_colsum = _ptr(dgamma), _ptr(dbeta), _ptr(dx_colsum)
+    if resid_rows is not None:
+        assert resid is None and resid_last_idx is not None and resid_seq_len > 0
+        assert resid_rows.dtype == torch.float32 and resid_rows.is_contiguous() and resid_rows.shape[1] == x.shape[1]
+        assert resid_last_idx.dtype == torch.int32 and x.shape[0] == resid_rows.shape[0] * resid_seq_len
+    a.resid_rows, a.resid_last_idx, a.resid_seq_len = _ptr(resid_rows), _ptr(resid_last_idx), resid_seq_len
     return a
 
 

@@ -88,6 +88,28 @@ def test_chain_fwd_bwd(ln, relu, l2):
         assert (db - br.grad).abs().max().item() < 2e-3
 
 
+def test_chain_bwd_sparse_residual_equals_dense():
+    """resid_rows (one row per sequence, selected by last_idx) == a dense residual that is zero elsewhere."""
+    from mrm_b200 import ops
+    Bq, L, W = 12, 25, 256
+    R = Bq * L
+    x, dout = _randn(R, W, seed=31), _randn(R, W, seed=32)
+    w, b = 1 + _randn(W, seed=33, scale=0.1), _randn(W, seed=34, scale=0.1)
+    rows = _randn(Bq, W, seed=35)
+    last = torch.randint(0, L, (Bq,), device="cuda", dtype=torch.int32)
+    dense = torch.zeros(R, W, device="cuda")
+    dense[torch.arange(Bq, device="cuda") * L + last.long()] = rows
+    outs = []
+    for kw in (dict(resid=dense), dict(resid_rows=rows, resid_last_idx=last, resid_seq_len=L)):
+        dx = torch.empty(R, W, device="cuda")
+        dg, db = torch.zeros(W, device="cuda"), torch.zeros(W, device="cuda")
+        ops.chain_bwd(x, ln=(w, b), dout=dout, dx_f32=dx, dgamma=dg, dbeta=db, **kw)
+        outs.append((dx, dg, db))
+    torch.cuda.synchronize()
+    assert torch.equal(outs[0][0], outs[1][0])
+    assert torch.allclose(outs[0][1], outs[1][1], atol=1e-4) and torch.allclose(outs[0][2], outs[1][2], atol=1e-4)
+
+
 def test_chain_dropout_fwd_bwd_consistent():
     """Same (seed, site) in forward and backward: d/dx of sum(dropout(LN(x)) * c) matches a finite mask."""
     from mrm_b200 import ops
