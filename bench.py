@@ -402,9 +402,25 @@ def bench_retrieval(eng, rank, world, dev, peaks):
     if world > 1:
         dist.all_reduce(e2e_tower, op=dist.ReduceOp.MAX)
 
+    # single-user recommendation latency (src/inference.py:283-306): one user, 50 history items excluded, top-10
+    rec_ms = None
+    if world == 1:
+        from mrm_b200 import inference
+        g1 = torch.Generator(device=dev).manual_seed(9)
+        hist = torch.randint(1, N, (1, 50), device=dev, generator=g1)
+        one = users[:1].contiguous()
+        for _ in range(3):
+            inference.recommend_topk(one, index, hist, 10)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(20):
+            ridx, _ = inference.recommend_topk(one, index, hist, 10)
+            ridx.cpu()                      # the caller reads the ids: one sync per query
+        rec_ms = (time.perf_counter() - t0) / 20 * 1e3
+
     flops = 2.0 * U * (N + 1) * 256 / world
     peak_tf = peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops"))
-    return {"metric": "top-100 retrieval users/sec @1M items", "users_per_s": U / (ms.item() * 1e-3),
+    return {"metric": "top-100 retrieval users/sec @1M items", "recommend_1user_ms": rec_ms, "users_per_s": U / (ms.item() * 1e-3),
             "ms_per_pass": ms.item(), "e2e_users_per_s": U / e2e.item(),
             "e2e_users_per_s_incl_user_tower": U / e2e_tower.item(),
             "scoring_tflops_per_gpu": flops / (ms.item() * 1e-3) / 1e12,

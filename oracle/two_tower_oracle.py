@@ -221,6 +221,21 @@ def retrieval_scores(user_emb: torch.Tensor, item_embeddings: torch.Tensor) -> t
     return s
 
 
+def recommend(user_emb: torch.Tensor, item_embeddings: torch.Tensor, history_ids: Sequence[int],
+              k: int = 10) -> Tuple[torch.Tensor, torch.Tensor]:
+    """The scoring part of recommend_for_user (src/inference.py:283-303) for ONE user: re-normalise with
+    eps 1e-8 (:286), scores = u @ E^T (:291), padding id 0 and every history item masked to -inf (:296-302),
+    top-k (:306) under the canonical order. Returns (scores (k,), item ids (k,))."""
+    u = F.normalize(user_emb.view(1, -1), p=2, dim=1, eps=1e-8)
+    s = (u @ item_embeddings.t()).squeeze(0)
+    s[0] = float("-inf")
+    for h in history_ids:
+        if h < s.numel():
+            s[h] = float("-inf")
+    vals, idx = canonical_topk(s.view(1, -1), k)
+    return vals[0], idx[0]
+
+
 def rank_metrics(topk_idx: torch.Tensor, targets: torch.Tensor, k_list: Sequence[int]) -> Dict[str, torch.Tensor]:
     """Per-row Recall@k / NDCG@k (evaluate_metrics.py:159-185): hit if target in the first k;
     gain 1/log2(rank+2) with the 0-based rank, single relevant item => IDCG = 1."""

@@ -104,3 +104,21 @@ def test_oracle_retrieval_matches_reference(name):
             assert abs(m[k] - v) <= 0.03, (k, m[k], v)
         else:
             assert m[k] == v, (k, m[k], v)
+
+
+def test_oracle_recommend_masks_padding_and_history():
+    """oracle.recommend == torch.topk on the masked score vector (src/inference.py:291-306) when scores are
+    distinct; padding id 0 and history ids never come back."""
+    from oracle import two_tower_oracle as oracle
+    g = torch.Generator().manual_seed(3)
+    table = torch.nn.functional.normalize(torch.randn(500, 256, generator=g), dim=1)
+    table[0] = 0
+    u = torch.randn(256, generator=g)
+    hist = [3, 17, 17, 250, 499]
+    vals, idx = oracle.recommend(u, table, hist, 10)
+    s = (torch.nn.functional.normalize(u.view(1, -1), dim=1, eps=1e-8) @ table.t())[0]
+    s[0] = float("-inf")
+    s[torch.tensor(hist)] = float("-inf")
+    tv, ti = torch.topk(s, 10)
+    assert idx.tolist() == ti.tolist() and torch.equal(vals, tv)
+    assert 0 not in idx.tolist() and not set(idx.tolist()) & set(hist)

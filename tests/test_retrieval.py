@@ -145,3 +145,59 @@ def test_rank_metrics_kernel():
     for j, k in enumerate([10, 20, 50, 100]):
         assert torch.equal(r[j].cpu(), ref[f"Recall@{k}"])
         assert torch.equal(n[j].cpu(), ref[f"NDCG@{k}"])
+
+
+def _assert_same_ranking(got_idx, got_score, want_idx, want_score, tol=2e-6):
+    """Same ids in the same order, except that items whose exact scores are closer than `tol` may swap (the user
+    vector is re-normalised on two different devices, so scores agree to an ulp, not bit for bit)."""
+    got_idx, want_idx = got_idx.cpu().tolist(), want_idx.tolist()
+    assert torch.allclose(got_score.cpu(), want_score, atol=tol), (got_score, want_score)
+    for pos, (a, b) in enumerate(zip(got_idx, want_idx)):
+        if a != b:
+            assert a in want_idx, (pos, a, want_idx)
+            assert abs(want_score[want_idx.index(a)].item() - want_score[pos].item()) <= tol, (pos, a, b)
+
+
+@pytest.mark.gpu
+def test_recommend_topk_excludes_history_like_the_oracle():
+    """src/inference.py:283-306 for a batch of users: padding id and history masked, canonical top-10. The
+    histories are built from each user's own best items, so the exclusion changes every answer."""
+    from mrm_b200 import inference, retrieval, synthetic
+    from oracle import two_tower_oracle as oracle
+    table = synthetic.make_catalog(3000, 256, seed=5, grid=2.0 ** -7)            # exactly summable scores
+    users, _ = synthetic.make_queries(table, 9, seed=6, grid=2.0 ** -7)
+    index = retrieval.CatalogIndex(table)
+    k, m = 10, 50
+    hist = torch.zeros(9, m, dtype=torch.long)
+    for u in range(9):
+        _, best = oracle.canonical_topk(oracle.retrieval_scores(users[u:u + 1], table), 40)
+        picks = best[0, ::2][:3 + 2 * u]                                           # 3..19 of the user's top-40
+        hist[u, :picks.numel()] = picks
+    idx, score = inference.recommend_topk(users.cuda(), index, hist.cuda(), k)
+    for u in range(9):
+        want_s, want_i = oracle.recommend(users[u], table, [h for h in hist[u].tolist() if h], k)
+        _assert_same_ranking(idx[u], score[u], want_i, want_s)
+        assert not set(idx[u].cpu().tolist()) & set(hist[u].tolist())
+
+
+@pytest.mark.gpu
+def test_recommend_for_user_end_to_end():
+    """History -> CUDA user tower -> index -> top-10, against the oracle run on the same user embedding."""
+    from mrm_b200 import inference, retrieval, synthetic
+    from mrm_b200.models import TwoTowerModel
+    from oracle import two_tower_oracle as oracle
+    V = 2001
+    model = TwoTowerModel(vocab_size=V, tabular_input_dim=17, num_genders=3, num_countries=50, max_seq_len=50,
+                          user_embedding_dim=256, item_embedding_dim=256, use_lora=True, seed=3)
+    table = synthetic.make_catalog(V - 1, 256, seed=8)
+    index = retrieval.CatalogIndex(table)
+    history = [int(x) for x in torch.randint(1, V, (73,), generator=torch.Generator().manual_seed(1))]
+    idx, score = inference.recommend_for_user(model, index, history, user_gender=1, user_country=7, k=10)
+    used = history[-50:]
+    ids = torch.zeros(1, 50, dtype=torch.long)
+    ids[0, :50] = torch.tensor(used)
+    model.eval()
+    u = model.get_user_embedding(ids.cuda(), (ids != 0).long().cuda(), torch.tensor([1]).cuda(), torch.tensor([7]).cuda())
+    want_s, want_i = oracle.recommend(u[0].cpu(), table, used, 10)
+    _assert_same_ranking(idx, score, want_i, want_s)
+    assert not set(idx.cpu().tolist()) & set(used) and 0 not in idx.cpu().tolist()
