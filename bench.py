@@ -214,15 +214,19 @@ def run_ours(args, rank, world, local_rank):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     l0 = _lib.launch_count
+    marks = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     e0.record()
-    for _ in range(args.steps):
+    for i in range(args.steps):
         runner.step_resident()
+        marks[i].record()
     e1.record()
     barrier()
     ms_total = torch.tensor([e0.elapsed_time(e1)], device=dev)
     if world > 1:
         dist.all_reduce(ms_total, op=dist.ReduceOp.MAX)
     ms_step = ms_total.item() / args.steps
+    per_step = sorted([e0.elapsed_time(marks[0])] + [marks[i - 1].elapsed_time(marks[i]) for i in range(1, args.steps)])
+    pct = {f"p{q}": per_step[min(len(per_step) - 1, int(q / 100.0 * len(per_step)))] for q in (10, 50, 90)}
     value = world * B * 1e3 / ms_step
     launches = runner.kernels_per_step * args.steps + (_lib.launch_count - l0)
 
@@ -245,6 +249,27 @@ def run_ours(args, rank, world, local_rank):
     e2e_value = world * B * args.steps / e2e_s.item()
     sampler.stop_flag = True
     sampler.join(timeout=2)
+
+    # ---- forward + backward only (no optimizer step) -------------------------
+    fb = None
+    if world == 1:
+        eng2 = TwoTowerEngine(cfg, dev)
+        eng2.load_state_dict(synthetic.make_state_dict(cfg, seed=0))
+        r2 = TrainStepRunner(eng2, B, L, with_optimizer=False)
+        r2.load_batch(host_batches[0])
+        for _ in range(4):
+            r2.step_resident()
+        torch.cuda.synchronize()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        for _ in range(20):
+            r2.step_resident()
+        f1.record()
+        torch.cuda.synchronize()
+        fb_ms = f0.elapsed_time(f1) / 20
+        fb = {"ms_per_step": fb_ms, "samples_per_s": B * 1e3 / fb_ms,
+              "what": "forward + backward + InfoNCE, gradient buffer cleared instead of the AdamW step"}
+        del r2, eng2
 
     # ---- roofline of the dominant kernel (tcgen05 GEMM) -----------------------------------
     g_all, g, gemm_launches = time_gemm_roofline(eng, runner.static, peaks)
@@ -305,6 +330,8 @@ def run_ours(args, rank, world, local_rank):
                                      "read: K/V for all positions, query/out_proj/FFN for one row per sequence)",
                        "l2": "per-step working set (~1.2 GB activations + 410 MB optimizer state) exceeds the 126 MB L2"},
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4},
+            "ms_per_step_percentiles": pct,
+            "fwd_bwd_only": fb,
             "gpu_launches": launches,
             "kernels_per_step": runner.kernels_per_step,
             "step_tflops": step_flops / (ms_step * 1e-3) / 1e12,

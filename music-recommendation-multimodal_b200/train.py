@@ -55,9 +55,13 @@ class TrainStepRunner:
 
     def __init__(self, engine: TwoTowerEngine, B: int, L: int, world_size: int = 1, lr: float = 1e-4,
                  use_graph: bool = True, with_user_idx: bool = True, negatives: str = "gathered",
-                 rank: Optional[int] = None, group=None, shard_optimizer: bool = True):
+                 rank: Optional[int] = None, group=None, shard_optimizer: bool = True,
+                 with_optimizer: bool = True):
         self.eng, self.B, self.L, self.world, self.lr, self.use_graph = engine, B, L, world_size, lr, use_graph
         self.group = group
+        #: False = forward + backward only (the gradient buffer is cleared instead of consumed): the
+        #: "without optimizer step" timing SURVEY.md §8d asks for; parameters do not change
+        self.with_optimizer = with_optimizer
         self.rank = (dist.get_rank(group) if world_size > 1 else 0) if rank is None else rank
         self.gathered = world_size > 1 and negatives == "gathered"
         # ZeRO-1 style: reduce-scatter the gradient, AdamW on this rank's 1/world shard (moments are
@@ -126,6 +130,11 @@ class TrainStepRunner:
         else:
             self.eng.adamw_step(lr=self.lr)
 
+    def _phase_drop_grad(self):
+        from . import ops
+        self.eng.grad.zero_()
+        ops.step_counters_advance(None, self.eng.seed_dev)     # dropout masks still change from step to step
+
     def _phase_post_opt(self):
         """After the parameter all-gather: zero the local gradient buffer, refresh the bf16 operand shadow."""
         self.eng.grad.zero_()
@@ -185,6 +194,8 @@ class TrainStepRunner:
         else:
             seq += [(self._phase_loss_rows, False)]
         seq += [(self._phase_backward, False)]
+        if not self.with_optimizer:
+            return seq + [(self._phase_drop_grad, False)]
         if self.world > 1:
             seq += [(self._comm_grads, True)]
         seq += [(self._phase_opt, False)]
