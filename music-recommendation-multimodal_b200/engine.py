@@ -131,13 +131,41 @@ class TwoTowerEngine:
         #: measurement aid: issue everything on the current stream (per-kernel event timing without overlap)
         self.serialize = False
         self.overlap_wgrad = os.environ.get("TT_OVERLAP_WGRAD", "1") != "0"
+        #: row-sharded ID table (sharding.RowShardedTable, config 5): when set, `table_rows` [1 + B*L, 256] holds
+        #: the rows the exchange fetched for this step's tokens (row 0 unused) and the embedding kernels index
+        #: it with the token number instead of the item id; `table_rows_grad` receives the per-token gradient
+        #: rows, which the owner ranks then scatter-add. The flat buffer's own table region is a 2-row dummy.
+        self.table_rows: Optional[torch.Tensor] = None
+        self.table_rows_grad: Optional[torch.Tensor] = None
+        self._virt_ids: Dict[Tuple[int, int], torch.Tensor] = {}
 
     # ------------------------------------------------------------------ parameters
+    def use_external_table(self, B: int, L: int) -> None:
+        """Switch the ID-embedding lookups to the per-step row buffer of a row-sharded table."""
+        D = self.cfg.embedding_dim
+        self.table_rows = torch.zeros(1 + B * L, D, device=self.device)
+        self.table_rows_grad = torch.zeros(1 + B * L, D, device=self.device)
+
+    def _embed_operands(self, ids: torch.Tensor):
+        """(ids, table, table_grad) the embedding kernels see: the real ones, or token numbers 1..B*L into the
+        fetched-rows buffer when the table is row-sharded."""
+        ut = "user_tower."
+        if self.table_rows is None:
+            return ids.view(-1), self.p[ut + "item_embedding.weight"], self.g[ut + "item_embedding.weight"]
+        B, L = ids.shape
+        assert self.table_rows.shape[0] == 1 + B * L, "use_external_table was sized for another (B, L)"
+        if (B, L) not in self._virt_ids:
+            self._virt_ids[(B, L)] = torch.arange(1, 1 + B * L, device=self.device, dtype=torch.long)
+        return self._virt_ids[(B, L)], self.table_rows, self.table_rows_grad
+
     def load_state_dict(self, sd: Dict[str, torch.Tensor]) -> None:
         """Copy a reference-format state dict (src/train.py:327-330; optional 'module.' prefix,
-        encoder keys ignored) into the flat buffer."""
+        encoder keys ignored) into the flat buffer. With a row-sharded table the ID table entry is skipped
+        (RowShardedTable.load_full takes it)."""
         sd = {(k[7:] if k.startswith("module.") else k): v for k, v in sd.items()}
         for name, t in self.p.items():
+            if self.table_rows is not None and name == "user_tower.item_embedding.weight":
+                continue
             t.copy_(sd[name].to(device=self.device, dtype=torch.float32))
         it = "item_tower.fusion_layer.1."
         if it + "running_mean" in sd:
@@ -320,7 +348,8 @@ class TwoTowerEngine:
         seed, sdev = self.base_seed, self.seed_dev
         ut = "user_tower."
         ops.last_index(ids, mask, ws["last_idx"])
-        ops.embed_ln_fwd(ids.view(-1), p[ut + "item_embedding.weight"], p[ut + "position_embedding.weight"],
+        e_ids, e_table, _ = self._embed_operands(ids)
+        ops.embed_ln_fwd(e_ids, e_table, p[ut + "position_embedding.weight"],
                          p[ut + "layer_norm.weight"], p[ut + "layer_norm.bias"],
                          p[self._lp(0, "norm1.weight")], p[self._lp(0, "norm1.bias")], B, L,
                          ws["x_in0"], ws["h1_0"], drop_p=dp, seed=seed, seed_dev=sdev, site=SITE_EMB)
@@ -652,9 +681,10 @@ class TwoTowerEngine:
             dx, dx_other = dx_other, dx
 
         # ---- embedding LayerNorm + lookup
-        ops.embed_ln_bwd(ids.view(-1), p[ut + "item_embedding.weight"], p[ut + "position_embedding.weight"],
+        e_ids, e_table, e_grad = self._embed_operands(ids)
+        ops.embed_ln_bwd(e_ids, e_table, p[ut + "position_embedding.weight"],
                          p[ut + "layer_norm.weight"], p[ut + "layer_norm.bias"], dx, B, L,
-                         g[ut + "item_embedding.weight"], g[ut + "position_embedding.weight"],
+                         e_grad, g[ut + "position_embedding.weight"],
                          g[ut + "layer_norm.weight"], g[ut + "layer_norm.bias"], drop_p=dp, seed=seed,
                          seed_dev=sdev, site=SITE_EMB)
         main.wait_stream(side)

@@ -24,3 +24,91 @@ def merge_canonical(scores: torch.Tensor, idx: torch.Tensor):
     s, i = s.gather(1, order), i.gather(1, order)
     order = torch.argsort(s, dim=1, descending=True, stable=True)  # ... then score descending (stable)
     return i.gather(1, order)[:, :K].to(idx.dtype), s.gather(1, order)[:, :K]
+
+
+class RowShardedTable:
+    """Row-sharded item-ID embedding table for catalogs that do not fit replicated.
+
+    Reference semantics: ``nn.Embedding(vocab_size, 256, padding_idx=0)`` and its dense gradient
+    (src/models/user_tower.py:26,86; autograd `embedding_dense_backward`), AdamW over every row
+    (src/train.py:302). Rank r owns the contiguous rows `shard_bounds(V, world, r)`. A lookup is the exchange
+    step the path really has: token ids go to their owners (all-to-all), owners gather the rows, rows come back
+    (all-to-all); the backward sends gradient rows the same way and the owner scatter-adds them. The optimizer
+    touches local rows only. Written with torch ops + torch.distributed so the exchange logic is testable with
+    gloo on CPU; on GPUs the same calls run over NCCL/NVLink.
+    """
+
+    def __init__(self, vocab_size: int, dim: int, rank: int, world: int, device, group=None):
+        self.vocab_size, self.dim, self.rank, self.world, self.group = vocab_size, dim, rank, world, group
+        self.per = (vocab_size + world - 1) // world
+        self.first, self.rows = shard_bounds(vocab_size, world, rank)
+        self.weight = torch.zeros(self.rows, dim, device=device)
+        self.grad = torch.zeros(self.rows, dim, device=device)
+        self.exp_avg = None
+        self.exp_avg_sq = None
+        self._saved = None
+
+    def load_full(self, full_table: torch.Tensor) -> None:
+        self.weight.copy_(full_table[self.first:self.first + self.rows])
+
+    def _a2a(self, out: torch.Tensor, inp: torch.Tensor, out_splits, in_splits) -> None:
+        if self.world == 1:
+            out.copy_(inp)
+            return
+        import torch.distributed as dist
+        dist.all_to_all_single(out, inp, out_splits, in_splits, group=self.group)
+
+    def lookup(self, ids: torch.Tensor) -> torch.Tensor:
+        """rows[t] = table[ids[t]] for this rank's tokens (ids int64 [T], global item ids). Collective."""
+        ids = ids.reshape(-1)
+        owner = torch.div(ids, self.per, rounding_mode="floor")
+        order = torch.argsort(owner, stable=True)
+        send_counts = torch.bincount(owner, minlength=self.world)
+        recv_counts = torch.empty_like(send_counts)
+        self._a2a(recv_counts, send_counts, None, None)
+        send_splits, recv_splits = send_counts.tolist(), recv_counts.tolist()      # host sync: variable message sizes
+        ids_sorted = ids[order]
+        ids_recv = torch.empty(sum(recv_splits), dtype=ids.dtype, device=ids.device)
+        self._a2a(ids_recv, ids_sorted, recv_splits, send_splits)
+        local = ids_recv - self.first
+        rows_out = self.weight.index_select(0, local)
+        rows_back = torch.empty(ids.numel(), self.dim, device=ids.device, dtype=self.weight.dtype)
+        self._a2a(rows_back, rows_out, send_splits, recv_splits)
+        rows = torch.empty_like(rows_back)
+        rows[order] = rows_back
+        self._saved = (order, send_splits, recv_splits, ids_recv, local)
+        return rows
+
+    def backward(self, drows: torch.Tensor, scale: float = 1.0) -> None:
+        """grad[id] += scale * sum over all ranks' tokens with that id of drows (rows of id 0 excluded: padding_idx).
+        `drows` [T, dim] is the gradient w.r.t. what `lookup` returned. Collective."""
+        order, send_splits, recv_splits, ids_recv, local = self._saved
+        d_sorted = drows.reshape(-1, self.dim)[order]
+        d_recv = torch.empty(ids_recv.numel(), self.dim, device=drows.device, dtype=drows.dtype)
+        self._a2a(d_recv, d_sorted, recv_splits, send_splits)
+        d_recv = d_recv * scale
+        d_recv[ids_recv == 0] = 0          # padding_idx=0 never receives a gradient
+        self.grad.index_add_(0, local, d_recv.to(self.grad.dtype))
+
+    def adamw_step(self, step_dev: torch.Tensor, lr: float = 1e-4, betas=(0.9, 0.999), eps: float = 1e-8,
+                   weight_decay: float = 0.01) -> None:
+        """Dense AdamW over the local rows (every row decays every step, like the replicated table); `step_dev`
+        is the engine's already-advanced device step counter. CUDA only (tt_adamw_step)."""
+        from . import ops
+        if self.exp_avg is None:
+            self.exp_avg = torch.zeros_like(self.weight)
+            self.exp_avg_sq = torch.zeros_like(self.weight)
+        n = self.weight.numel()
+        ops.adamw_step(self.weight.view(n), self.grad.view(n), self.exp_avg.view(n), self.exp_avg_sq.view(n), step_dev,
+                       lr, betas[0], betas[1], eps, weight_decay, shadow=None, zero_grad=True)
+
+    def gather_full(self) -> torch.Tensor:
+        """The whole (V, dim) table on every rank (checkpointing / tests)."""
+        if self.world == 1:
+            return self.weight.clone()
+        import torch.distributed as dist
+        pad = torch.zeros(self.per, self.dim, device=self.weight.device, dtype=self.weight.dtype)
+        pad[:self.rows] = self.weight
+        out = torch.empty(self.world * self.per, self.dim, device=self.weight.device, dtype=self.weight.dtype)
+        dist.all_gather_into_tensor(out, pad, group=self.group)
+        return out[:self.vocab_size]

@@ -56,12 +56,17 @@ class TrainStepRunner:
     def __init__(self, engine: TwoTowerEngine, B: int, L: int, world_size: int = 1, lr: float = 1e-4,
                  use_graph: bool = True, with_user_idx: bool = True, negatives: str = "gathered",
                  rank: Optional[int] = None, group=None, shard_optimizer: bool = True,
-                 with_optimizer: bool = True):
+                 with_optimizer: bool = True, sharded_table=None):
         self.eng, self.B, self.L, self.world, self.lr, self.use_graph = engine, B, L, world_size, lr, use_graph
         self.group = group
         #: False = forward + backward only (the gradient buffer is cleared instead of consumed): the
         #: "without optimizer step" timing SURVEY.md §8d asks for; parameters do not change
         self.with_optimizer = with_optimizer
+        #: sharding.RowShardedTable: the item-ID table lives row-sharded across the ranks (config 5); every step
+        #: starts with the id/row all-to-all and ends with the gradient-row all-to-all + the local-row AdamW
+        self.table = sharded_table
+        if sharded_table is not None and engine.table_rows is None:
+            engine.use_external_table(B, L)
         self.rank = (dist.get_rank(group) if world_size > 1 else 0) if rank is None else rank
         self.gathered = world_size > 1 and negatives == "gathered"
         # ZeRO-1 style: reduce-scatter the gradient, AdamW on this rank's 1/world shard (moments are
@@ -184,9 +189,22 @@ class TrainStepRunner:
         n = self.eng.numel // self.world
         dist.all_gather_into_tensor(self.eng.flat, self.eng.flat[self.rank * n:(self.rank + 1) * n], group=self.group)
 
+    def _comm_lookup(self):
+        rows = self.table.lookup(self.static["history_ids"].view(-1))
+        self.eng.table_rows[1:].copy_(rows)
+
+    def _comm_table_grad(self):
+        g = self.eng.table_rows_grad
+        self.table.backward(g[1:], scale=1.0 / self.world)      # same averaging as the dense gradient
+        g.zero_()
+
+    def _phase_table_opt(self):
+        self.table.adamw_step(self.eng.step_dev, lr=self.lr)    # step counter already advanced by the engine
+
     def _sequence(self):
         """[(callable, is_communication)] of one step."""
-        seq = [(self._phase_towers, False)]
+        seq = [(self._comm_lookup, True)] if self.table is not None else []
+        seq += [(self._phase_towers, False)]
         if self.gathered:
             seq += [(self._phase_pack_emb, False), (self._comm_embeddings, True), (self._phase_unpack_emb, False),
                     (self._phase_loss_rows, False), (self._phase_pack_lse, False), (self._comm_lse, True),
@@ -194,11 +212,15 @@ class TrainStepRunner:
         else:
             seq += [(self._phase_loss_rows, False)]
         seq += [(self._phase_backward, False)]
+        if self.table is not None:
+            seq += [(self._comm_table_grad, True)]
         if not self.with_optimizer:
             return seq + [(self._phase_drop_grad, False)]
         if self.world > 1:
             seq += [(self._comm_grads, True)]
         seq += [(self._phase_opt, False)]
+        if self.table is not None:
+            seq += [(self._phase_table_opt, False)]
         if self.shard_opt:
             seq += [(self._comm_params, True), (self._phase_post_opt, False)]
         return seq

@@ -100,3 +100,43 @@ def _dp_worker(rank, world):
 
 def test_dp_gradient_average_world2():
     _run(_dp_worker, 2)
+
+
+def _sharded_table_worker(rank, world):
+    """Row-sharded ID table: lookups and gradient scatter through the all-to-all
+    exchange == the replicated table's index_select / dense embedding backward (padding row excluded)."""
+    from mrm_b200.sharding import RowShardedTable
+    torch.set_num_threads(1)
+    V, D, T = 1003, 16, 700                      # V not divisible by the world size: ragged last shard
+    full = torch.randn(V, D, generator=torch.Generator().manual_seed(1))
+    t = RowShardedTable(V, D, rank, world, "cpu")
+    t.load_full(full)
+    g = torch.Generator().manual_seed(10 + rank)
+    ids = torch.randint(0, V, (T,), generator=g)
+    ids[:50] = 0                                  # padding tokens
+    ids[50:90] = V - 1                            # hot row on the last shard
+    rows = t.lookup(ids)
+    assert torch.equal(rows, full[ids]), f"rank {rank}: lookup differs"
+    drows = torch.randn(T, D, generator=g)
+    t.backward(drows, scale=1.0 / world)
+    # reference: every rank's tokens contribute, averaged over ranks, row 0 gets nothing
+    all_ids = [torch.empty_like(ids) for _ in range(world)]
+    all_d = [torch.empty_like(drows) for _ in range(world)]
+    dist.all_gather(all_ids, ids)
+    dist.all_gather(all_d, drows)
+    ref = torch.zeros(V, D)
+    for i_r, d_r in zip(all_ids, all_d):
+        d_r = d_r.clone() / world
+        d_r[i_r == 0] = 0
+        ref.index_add_(0, i_r, d_r)
+    assert torch.allclose(t.grad, ref[t.first:t.first + t.rows], atol=1e-5), f"rank {rank}: gradient differs"
+    assert t.first != 0 or t.grad[0].abs().max().item() == 0.0
+    assert torch.equal(t.gather_full(), full)
+
+
+def test_row_sharded_table_exchange_world2():
+    _run(_sharded_table_worker, 2)
+
+
+def test_row_sharded_table_exchange_world3():
+    _run(_sharded_table_worker, 3)

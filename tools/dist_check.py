@@ -15,6 +15,7 @@ from mrm_b200.train import TrainStepRunner  # noqa: E402
 
 
 def main():
+    sharded = "--sharded-table" in sys.argv     # config-5 layout: row-sharded ID table (all-to-all lookups)
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -22,12 +23,28 @@ def main():
     sd = synthetic.make_state_dict(cfg, seed=7)
     B, L, steps, lr = 32, 50, 3, 1e-3
     batches = [[synthetic.make_batch(cfg, B, seed=100 + 10 * s + r, num_users=20) for r in range(world)] for s in range(steps)]
-    eng = TwoTowerEngine(cfg)
-    eng.load_state_dict(sd)
-    runner = TrainStepRunner(eng, B, L, world_size=world, lr=lr, use_graph=True)
+    tname = "user_tower.item_embedding.weight"
+    if sharded:
+        import dataclasses
+        from mrm_b200.sharding import RowShardedTable
+        eng = TwoTowerEngine(dataclasses.replace(cfg, vocab_size=2))
+        table = RowShardedTable(cfg.vocab_size, 256, rank, world, eng.device)
+        runner = TrainStepRunner(eng, B, L, world_size=world, lr=lr, use_graph=True, sharded_table=table)
+        eng.load_state_dict(sd)
+        table.load_full(sd[tname].cuda())
+    else:
+        eng = TwoTowerEngine(cfg)
+        eng.load_state_dict(sd)
+        runner = TrainStepRunner(eng, B, L, world_size=world, lr=lr, use_graph=True)
     losses = [runner.step_from_host(batches[s][rank]) for s in range(steps)]
     torch.cuda.synchronize()
-    mine = eng.flat.clone()
+    if sharded:     # same flat layout as the replicated engine: [full table | everything else]
+        ref_layout = TwoTowerEngine(cfg)
+        ref_layout.load_state_dict({**eng.state_dict(), tname: table.gather_full()})
+        mine = ref_layout.flat.clone()
+        del ref_layout
+    else:
+        mine = eng.flat.clone()
     gathered = [torch.empty_like(mine) for _ in range(world)]
     dist.all_gather(gathered, mine)
     ok = True
