@@ -19,15 +19,24 @@ logger = logging.getLogger(__name__)
 
 
 def compute_all_item_embeddings(model, item_features: Dict[str, torch.Tensor], item_ids: torch.Tensor,
-                                batch_size: int, device, vocab_size: int):
+                                batch_size: int, device, vocab_size: int, shard=None):
     """Catalog indexing (src/evaluate_metrics.py:24-104) on precomputed modality embeddings:
-    item tower in eval mode, NaN -> 0, re-normalise with eps 1e-8, scatter into the dense table."""
+    item tower in eval mode, NaN -> 0, re-normalise with eps 1e-8, scatter into the dense table.
+
+    ``shard=(rank, world)`` indexes only the rank-th contiguous slice of the item list (eval-mode BatchNorm has
+    no cross-row dependency, so the catalog splits freely over GPUs); rows of other slices stay
+    zero, so the full table is the SUM over ranks (`dist.all_reduce`) or each rank keeps its slice."""
     model.eval()
     D = model.engine.cfg.embedding_dim
     dense = torch.zeros(vocab_size, D)
-    n = item_ids.shape[0]
+    n_all = item_ids.shape[0]
+    lo, n = 0, n_all
+    if shard is not None:
+        r, w = shard
+        per = (n_all + w - 1) // w
+        lo, n = min(r * per, n_all), min(n_all, (r + 1) * per)
     with torch.no_grad():
-        for s in range(0, n, batch_size):
+        for s in range(lo, n, batch_size):
             sl = slice(s, min(n, s + batch_size))
             emb = model.get_item_embedding(images=item_features["target_image"][sl], audio=item_features["target_audio"][sl],
                                            input_ids=item_features["target_input_ids"][sl], attention_mask=None,

@@ -86,6 +86,21 @@ def test_train_one_epoch_prefetch_path_is_the_same_training():
         assert abs(a - b) < 5e-3, means
 
 
+def test_catalog_indexing_shards_sum_to_the_full_table():
+    """compute_all_item_embeddings over two item slices (what two ranks would do) == the unsharded table."""
+    from mrm_b200.evaluate_metrics import compute_all_item_embeddings
+    m = _model(V=501)
+    g = torch.Generator().manual_seed(4)
+    n = 300
+    feats = {k: torch.randn(n, 128, generator=g) for k in ("target_image", "target_audio", "target_input_ids", "target_tabular")}
+    ids = torch.randperm(500, generator=g)[:n] + 1
+    full, _ = compute_all_item_embeddings(m, feats, ids, 64, torch.device("cuda"), 501)
+    parts = [compute_all_item_embeddings(m, feats, ids, 64, torch.device("cuda"), 501, shard=(r, 2))[0] for r in range(2)]
+    assert torch.equal(parts[0] + parts[1], full)
+    assert (parts[0].abs().sum(1) > 0).sum() + (parts[1].abs().sum(1) > 0).sum() == n
+    assert full[0].abs().max().item() == 0.0
+
+
 def test_packed_host_batch_is_the_same_step():
     """One pinned buffer (TrainStepRunner.pack_host) in, same loss out as the dict route."""
     from mrm_b200 import synthetic
