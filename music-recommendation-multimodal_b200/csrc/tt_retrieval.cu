@@ -65,7 +65,7 @@ struct TopkParams {
 
 // Warp-cooperative prune of one row's candidate list to its kprime largest keys.
 // Returns the new count; T receives a threshold with count(keys >= T) == new count.
-__device__ int warp_prune(unsigned long long* buf, int n, int kprime, int lane, unsigned long long& T) {
+__device__ __noinline__ int warp_prune(unsigned long long* buf, int n, int kprime, int lane, unsigned long long& T) {
   __syncwarp();
   unsigned long long k[kCap / 32];
 #pragma unroll
@@ -107,27 +107,45 @@ __device__ __forceinline__ float chunk_max(const uint32_t (&r)[32]) {
   return m;
 }
 
-// Filter one 32-score chunk of this lane's user row against the row threshold. The common case
-// (no score of any lane beats its threshold) costs a max tree and one vote; otherwise only the
-// 4-score groups that actually contain a candidate are examined.
-__device__ __forceinline__ void scan_chunk(const uint32_t (&r)[32], int idx0, const TopkParams& p, int lane, int row,
-                                           unsigned long long* buf, int& cnt, unsigned long long& thr_key,
-                                           float& thr_s) {
-  float g[8];
-#pragma unroll
-  for (int k = 0; k < 8; ++k)
-    g[k] = fmaxf(fmaxf(__uint_as_float(r[4 * k]), __uint_as_float(r[4 * k + 1])),
-                 fmaxf(__uint_as_float(r[4 * k + 2]), __uint_as_float(r[4 * k + 3])));
-  const float mx = fmaxf(fmaxf(fmaxf(g[0], g[1]), fmaxf(g[2], g[3])), fmaxf(fmaxf(g[4], g[5]), fmaxf(g[6], g[7])));
-  if (!__any_sync(0xffffffffu, mx >= thr_s)) return;
+// Filter one 32-score chunk of this lane's user row against the row threshold.
+//
+// The epilogue loop has to stay SMALL: an earlier version examined the 32 registers of a chunk with
+// fully unrolled nested branches (4 096 SASS instructions in the kernel) and the ncu source page
+// showed the epilogue warps stalled on instruction fetch (stall_no_inst first, ahead of every data
+// dependency) whenever a chunk held a candidate — which, at ~1 candidate per 1 000 scores, is two
+// chunks out of three. Now the registers only feed a max tree (one 8-bit "which 4-score groups beat
+// the threshold" mask per lane); they are dead afterwards, so the NEXT chunk's tcgen05.ld is issued
+// into the same registers before the vote, and the rare groups that do hold a candidate are RE-READ
+// from TMEM four columns at a time (the TMEM address is a run-time value, a register index is not)
+// in a short warp-uniform loop.
+__device__ __forceinline__ uint32_t chunk_group_mask(const uint32_t (&r)[32], float thr_s) {
+  uint32_t gm = 0;
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
-    if (g[k] >= thr_s) {
+    const float g = fmaxf(fmaxf(__uint_as_float(r[4 * k]), __uint_as_float(r[4 * k + 1])),
+                          fmaxf(__uint_as_float(r[4 * k + 2]), __uint_as_float(r[4 * k + 3])));
+    gm |= (g >= thr_s) ? (1u << k) : 0u;
+  }
+  return gm;
+}
+
+__device__ __forceinline__ void collect_groups(uint32_t gm, uint32_t t_chunk, int idx0, const TopkParams& p, int lane,
+                                               int row, unsigned long long* buf, int& cnt,
+                                               unsigned long long& thr_key, float& thr_s) {
+  uint32_t wm = __reduce_or_sync(0xffffffffu, gm);   // groups in which ANY lane has a candidate (warp-uniform)
+#pragma unroll 1
+  while (wm) {
+    const int k = __ffs(wm) - 1;
+    wm &= wm - 1;
+    uint32_t v[4];
+    tmem_ld4(t_chunk + 4u * k, v);
+    tmem_ld_wait();
+    if ((gm >> k) & 1u) {
 #pragma unroll
-      for (int t = 4 * k; t < 4 * k + 4; ++t) {
-        const float s = __uint_as_float(r[t]);
+      for (int t = 0; t < 4; ++t) {
+        const float s = __uint_as_float(v[t]);
         if (s >= thr_s) {
-          const int idx = idx0 + t;
+          const int idx = idx0 + 4 * k + t;
           const uint32_t gidx = static_cast<uint32_t>(p.item_base + idx);
           if (idx < p.N && !(p.mask_item0 && gidx == 0u)) {
             const unsigned long long key = make_key(s, gidx);
@@ -154,6 +172,7 @@ __device__ __forceinline__ void scan_chunk(const uint32_t (&r)[32], int idx0, co
   }
 }
 
+template <bool kSample>
 __global__ void __launch_bounds__(kTopkThreads, 1)
 score_topk_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUtensorMap tmI,
                   const TopkParams p) {
@@ -282,10 +301,10 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant
         tc_fence_after();
         const uint32_t t_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
                                 static_cast<uint32_t>(acc * 256 + mt * 128);
-        uint32_t r0[32], r1[32];
-        tmem_ld32(t_base, r0);
-        if (p.smax != nullptr) {
+        if constexpr (kSample) {
           // sample pass: one float per (user, chunk) — the chunk's best score; layout [user][chunk]
+          uint32_t r0[32], r1[32];
+          tmem_ld32(t_base, r0);
           float* dst = p.smax + static_cast<size_t>(row) * (p.total_tiles * (kIT / 32)) + tile * (kIT / 32);
 #pragma unroll 1
           for (int c = 0; c < kIT / 32; c += 2) {
@@ -297,14 +316,15 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant
             dst[c + 1] = chunk_max(r1);
           }
         } else {
+          uint32_t r[32];
+          tmem_ld32(t_base, r);
 #pragma unroll 1
-          for (int c = 0; c < kIT / 32; c += 2) {
+          for (int c = 0; c < kIT / 32; ++c) {
             tmem_ld_wait();
-            tmem_ld32(t_base + (c + 1) * 32, r1);
-            scan_chunk(r0, tile * p.tile_stride * kIT + c * 32, p, lane, row, buf, cnt, thr_key, thr_s);
-            tmem_ld_wait();
-            if (c + 2 < kIT / 32) tmem_ld32(t_base + (c + 2) * 32, r0);
-            scan_chunk(r1, tile * p.tile_stride * kIT + (c + 1) * 32, p, lane, row, buf, cnt, thr_key, thr_s);
+            const uint32_t gm = chunk_group_mask(r, thr_s);
+            if (c + 1 < kIT / 32) tmem_ld32(t_base + (c + 1) * 32, r);   // r is dead: next chunk flies during the vote
+            if (__any_sync(0xffffffffu, gm != 0u))
+              collect_groups(gm, t_base + c * 32, tile * kIT + c * 32, p, lane, row, buf, cnt, thr_key, thr_s);
           }
         }
         tc_fence_before();
@@ -313,7 +333,7 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1u;
       }
-      if (p.smax == nullptr) p.cand_cnt[static_cast<size_t>(range) * p.u_pad + row] = active ? cnt : 0;
+      if constexpr (!kSample) p.cand_cnt[static_cast<size_t>(range) * p.u_pad + row] = active ? cnt : 0;
     }
   }
 
@@ -496,19 +516,33 @@ __global__ void __launch_bounds__(256) topk_finalize_kernel(const FinalizeParams
     const float4 x = __ldg(reinterpret_cast<const float4*>(urow) + k * 32 + lane);
     uf[4 * k] = x.x; uf[4 * k + 1] = x.y; uf[4 * k + 2] = x.z; uf[4 * k + 3] = x.w;
   }
-  for (int cidx = warp; cidx < nsel; cidx += 8) {
-    const uint32_t gidx = key_idx(s_sel[cidx]);
-    const float* irow = p.items + static_cast<size_t>(gidx - p.item_base) * kD;
-    double acc = 0.0;
+  // Four candidates per warp iteration: their eight 16-byte loads per lane are all issued before the first
+  // dependent fp64 operation (a random 1 KB row gather is latency-bound otherwise: 36 % of the HBM peak with
+  // one row in flight per warp). The per-candidate operation order is unchanged, so scores are bit-identical.
+  for (int c0 = warp; c0 < nsel; c0 += 32) {
+    float4 x[4][2];
+    uint32_t gi[4];
 #pragma unroll
-    for (int k = 0; k < 2; ++k) {
-      const float4 x = __ldg(reinterpret_cast<const float4*>(irow) + k * 32 + lane);
-      acc += static_cast<double>(uf[4 * k]) * x.x + static_cast<double>(uf[4 * k + 1]) * x.y +
-             static_cast<double>(uf[4 * k + 2]) * x.z + static_cast<double>(uf[4 * k + 3]) * x.w;
+    for (int j = 0; j < 4; ++j) {
+      const int cidx = c0 + 8 * j;
+      gi[j] = key_idx(s_sel[cidx < nsel ? cidx : c0]);
+      const float* irow = p.items + static_cast<size_t>(gi[j] - p.item_base) * kD;
+#pragma unroll
+      for (int k = 0; k < 2; ++k) x[j][k] = __ldg(reinterpret_cast<const float4*>(irow) + k * 32 + lane);
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (lane == 0) s_keys[cidx] = make_key(static_cast<float>(acc), gidx);
+    for (int j = 0; j < 4; ++j) {
+      double acc = 0.0;
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        acc += static_cast<double>(uf[4 * k]) * x[j][k].x + static_cast<double>(uf[4 * k + 1]) * x[j][k].y +
+               static_cast<double>(uf[4 * k + 2]) * x[j][k].z + static_cast<double>(uf[4 * k + 3]) * x[j][k].w;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      const int cidx = c0 + 8 * j;
+      if (lane == 0 && cidx < nsel) s_keys[cidx] = make_key(static_cast<float>(acc), gi[j]);
+    }
   }
   __syncthreads();
   bitonic_sort_desc_256(s_keys);
@@ -673,10 +707,24 @@ extern "C" int tt_topk_plan_make(int U, int N, int kprime, tt_topk_plan* plan) {
   plan->U = U; plan->N = N; plan->kprime = kprime; plan->cap = kCap;
   plan->n_ut = (U + kUT - 1) / kUT;
   const int total_tiles = (N + kIT - 1) / kIT;
-  int n_ranges = (4 * num_sms() + plan->n_ut - 1) / plan->n_ut;
-  const int max_ranges = (total_tiles + 63) / 64;  // at least 64 item tiles (8192 items) per range
-  if (n_ranges > max_ranges) n_ranges = max_ranges;
-  if (n_ranges < 1) n_ranges = 1;
+  // Work units (user tile x item range) are dealt round-robin to one persistent CTA per SM, so the pass
+  // lasts as long as the SM with the most units: pick the number of ranges whose busiest SM scores the
+  // fewest tiles (600 units on 148 SMs = five units on eight SMs, four on the rest: 23 % over the
+  // balanced time; 440 units = 2.97 waves is within 1.5 %). Fewer ranges win ties (fewer lists).
+  int max_ranges = (total_tiles + 63) / 64;        // at least 64 item tiles (8192 items) per range
+  if (max_ranges > 4 * num_sms()) max_ranges = 4 * num_sms();
+  if (max_ranges < 1) max_ranges = 1;
+  int n_ranges = 1;
+  {
+    long best = -1;
+    for (int c = 1; c <= max_ranges; ++c) {
+      const int tpr = (total_tiles + c - 1) / c;
+      const int nr = (total_tiles + tpr - 1) / tpr;
+      const long waves = (static_cast<long>(plan->n_ut) * nr + num_sms() - 1) / num_sms();
+      const long cost = waves * (tpr + 3);           // +3 tile-times: reload of the resident user tile per unit
+      if (best < 0 || cost < best) { best = cost; n_ranges = c; }
+    }
+  }
   plan->tiles_per_range = (total_tiles + n_ranges - 1) / n_ranges;
   plan->n_ranges = (total_tiles + plan->tiles_per_range - 1) / plan->tiles_per_range;
   const int64_t u_pad = static_cast<int64_t>(plan->n_ut) * kUT;
@@ -725,12 +773,16 @@ static int launch_score_topk(const void* users_bf16, const void* items_bf16, Top
   const size_t smem = 1024 + (2 * kKB + kBStages) * kTile16K + 256;
   static bool configured = false;
   if (!configured) {
-    TT_CHECK_CUDA(cudaFuncSetAttribute(score_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    TT_CHECK_CUDA(cudaFuncSetAttribute(score_topk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    TT_CHECK_CUDA(cudaFuncSetAttribute(score_topk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
     configured = true;
   }
   const int units = p.n_ut * p.n_ranges;
   const int grid = units < num_sms() ? units : num_sms();
-  TT_CHECK_CUDA(launch_k(score_topk_kernel, dim3(grid), dim3(kTopkThreads), smem, stream, tmU, tmI, p));
+  if (p.smax != nullptr)
+    TT_CHECK_CUDA(launch_k(score_topk_kernel<true>, dim3(grid), dim3(kTopkThreads), smem, stream, tmU, tmI, p));
+  else
+    TT_CHECK_CUDA(launch_k(score_topk_kernel<false>, dim3(grid), dim3(kTopkThreads), smem, stream, tmU, tmI, p));
   TT_LAUNCH_CHECK();
   return TT_OK;
 }
@@ -755,9 +807,20 @@ extern "C" int tt_score_topk(const void* users_bf16, const void* items_bf16, int
   p.smax = nullptr;
   if (plan->sample_stride > 1 && smax != nullptr && plan->sample_tiles * 4 <= 1024) {
     const int sample_tiles = plan->sample_tiles;
-    int sr = (num_sms() + p.n_ut - 1) / p.n_ut;           // enough (user tile, range) units for every SM
-    if (sr > sample_tiles) sr = sample_tiles;
-    if (sr < 1) sr = 1;
+    // ranges per user tile: the split whose busiest SM gets the fewest tiles (units are dealt round-robin
+    // to the SMs, so 160 units on 148 SMs would cost two full units on 12 of them)
+    int sr = 1;
+    {
+      long best = -1;
+      const int sr_max = sample_tiles < 16 ? sample_tiles : 16;
+      for (int c = 1; c <= sr_max; ++c) {
+        const int tpr = (sample_tiles + c - 1) / c;
+        const int nr = (sample_tiles + tpr - 1) / tpr;
+        const long waves = (static_cast<long>(p.n_ut) * nr + num_sms() - 1) / num_sms();
+        const long cost = waves * (tpr + 2);              // +2: the resident user tile reload per unit
+        if (best < 0 || cost < best) { best = cost; sr = c; }
+      }
+    }
     p.tile_stride = plan->sample_stride;
     p.tiles_per_range = (sample_tiles + sr - 1) / sr;
     p.n_ranges = (sample_tiles + p.tiles_per_range - 1) / p.tiles_per_range;
