@@ -268,7 +268,9 @@ int tt_infonce_loss(const float* lse_a, const float* pos_a, const float* lse_b, 
  *                     N items (this shard), K' = kprime candidates per user (8..256).
  * tt_score_topk     : fused U E^T (bf16 tensor cores, fp32 accumulate) + streaming top-K' per
  *                     user; replaces the matmul at :148, the column-0 mask at :152 and topk at
- *                     :156 without materialising the (U, N) score matrix.
+ *                     :156 without materialising the (U, N) score matrix. Runs on CTA pairs
+ *                     (clusters of 2, tcgen05 cta_group::2): a work unit is 256 users x a range of
+ *                     256-item steps ("tiles" in the plan below).
  *                     users_bf16 [U,256], items_bf16 [N,256]; item_base = global index of row 0
  *                     of this shard; mask_item0 excludes global item 0 (the padding id).
  *                     cand/cand_cnt/thr/smax are scratch of plan->{cand,cnt,thr,smax}_bytes (smax may be
@@ -286,7 +288,7 @@ int tt_infonce_loss(const float* lse_a, const float* pos_a, const float* lse_b, 
 typedef struct tt_topk_plan {
   int32_t U, N, kprime, cap;
   int32_t n_ut, n_ranges, tiles_per_range;
-  int32_t sample_stride, sample_rank, sample_tiles; /* sample pass (0 = none): every sample_stride-th item tile
+  int32_t sample_stride, sample_rank, sample_tiles; /* sample pass (0 = none): every sample_stride-th item step
                                                        is scored first, keeping the maximum of each 32-score chunk;
                                                        each user's sample_rank-th largest chunk maximum becomes the
                                                        main pass's start threshold (verified later, never trusted) */

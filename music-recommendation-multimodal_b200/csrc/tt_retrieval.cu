@@ -7,14 +7,18 @@
 //   torch.topk(scores, max_k)               (:156, radix select over V-long rows)
 //   per-k hit / NDCG bookkeeping            (:159-185, nonzero() syncs)
 //
-// tt_score_topk (tcgen05): a work unit = 256 users x one contiguous item range. The user tile
-// (2 x 128 rows x 256 dims, bf16, 128 KB) stays resident in shared memory, item tiles of 128
-// rows stream through a 5-stage TMA ring, two M=128,N=128 accumulators per item tile live in
-// TMEM (double-buffered: 512 columns). Eight epilogue warps read the accumulators with
-// tcgen05.ld; each thread owns one user row, keeps that row's running threshold in a register
-// and appends (score, item) keys that beat it to a per-(range,row) candidate list in global
-// memory; a full list is pruned to its K' best by the whole warp (bitwise binary search on
-// the 64-bit keys with ballot/popc + compaction). The score matrix never exists.
+// tt_score_topk (tcgen05, cta_group::2): a work unit = 256 users x one contiguous item range, run by a
+// PAIR of CTAs (cluster of 2). Each CTA keeps 128 of the users resident in shared memory (64 KB,
+// bf16) and streams 128 of every 256-item step through an 8-stage TMA ring; the leader CTA issues
+// M=256, N=256 MMAs that read both CTAs' shared memory, so per SM the tensor pipe reads 8 KB of
+// operands per 128-cycle MMA instead of the 16 KB two M=128,N=128 MMAs need (the single-CTA version
+// of this kernel sat at 60 % tensor-pipe activity whatever the epilogue or ring depth: shared-memory
+// operand bandwidth). Accumulators: 128 lanes x 256 columns per CTA, double-buffered (512 columns).
+// Eight epilogue warps per CTA read them with tcgen05.ld; a warp owns 32 user rows x 128 item
+// columns, each thread keeps its row's running threshold in a register and appends (score, item)
+// keys that beat it to a per-(range, column half, row) candidate list in global memory; a full list
+// is pruned to its K' best by the whole warp (bitwise binary search on the 64-bit keys with
+// ballot/popc + compaction). The score matrix never exists.
 // Keys are totally ordered: (score descending, item index ascending) — the canonical order.
 //
 // tt_topk_finalize: per user, select the K' best keys over all ranges, re-score them EXACTLY
@@ -26,13 +30,15 @@
 
 namespace tt {
 
-static constexpr int kUT = 256;        // users per work unit
-static constexpr int kIT = 128;        // items per MMA tile
+static constexpr int kUT = 256;        // users per work unit: 128 per CTA of the pair (MMA M = 256, cta_group::2)
+static constexpr int kIT = 256;        // items per MMA step (N = 256): 128 from each CTA's shared memory
+static constexpr int kLists = 4;       // candidate lists per (range, user row): one per 64-item column quarter of a step
 static constexpr int kD = 256;         // embedding dim
 static constexpr int kKB = kD / 64;    // k-blocks
 static constexpr uint32_t kTile16K = 128 * 64 * 2;
-static constexpr int kBStages = 5;
-static constexpr int kTopkThreads = 384;
+static constexpr int kChunks = kIT / 32; // 32-score chunks per item step
+static constexpr int kBStages = 8;     // 16 KB item slices in flight per CTA
+static constexpr int kTopkThreads = 640;   // TMA, MMA, TMEM-alloc, spare + 16 epilogue warps
 static constexpr int kCap = 512;       // candidate list capacity per (range, row)
 static constexpr int kPoolCap = 4096;  // finalize: per-user key pool in shared memory
 
@@ -57,8 +63,8 @@ struct TopkParams {
   float* smax;               // non-null: SAMPLE pass — store each 32-score chunk's maximum, collect nothing
   int kprime;
   int u_pad;
-  unsigned long long* cand;  // [n_ranges][u_pad][kCap]
-  int* cand_cnt;             // [n_ranges][u_pad]
+  unsigned long long* cand;  // [n_ranges * kLists][u_pad][kCap]
+  int* cand_cnt;             // [n_ranges * kLists][u_pad]
   unsigned long long* thr;   // [u_pad]
   int mask_item0;
 };
@@ -155,7 +161,7 @@ __device__ __forceinline__ void collect_groups(uint32_t gm, uint32_t t_chunk, in
       }
     }
   }
-  unsigned full = __ballot_sync(0xffffffffu, cnt > kCap - 32);
+  unsigned full = __ballot_sync(0xffffffffu, cnt > kCap - 64)   /* a call appends at most 64 keys per lane */;
   while (full) {
     const int src = __ffs(full) - 1;
     full &= full - 1;
@@ -182,16 +188,18 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant
 
   const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();              // 0 = leader (issues the MMAs of the pair)
+  const int cluster = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
 
-  uint8_t* sA = smem;                                   // [2 mt][4 kb] x 16 KB
-  uint8_t* sB = smem + 2 * kKB * kTile16K;              // kBStages x 16 KB
+  uint8_t* sA = smem;                                   // [4 kb] x 16 KB: this CTA's 128 users
+  uint8_t* sB = smem + kKB * kTile16K;                  // kBStages x 16 KB: this CTA's 128 items of a 256-item step
   uint64_t* bars = reinterpret_cast<uint64_t*>(sB + kBStages * kTile16K);
-  uint64_t* a_full = bars + 0;
-  uint64_t* a_empty = bars + 1;
-  uint64_t* b_full = bars + 2;
-  uint64_t* b_empty = b_full + kBStages;
-  uint64_t* t_full = b_empty + kBStages;
-  uint64_t* t_empty = t_full + 2;
+  uint64_t* a_full = bars + 0;                          // leader's copy is the live one (tx bytes of both CTAs)
+  uint64_t* a_empty = bars + 1;                         // every CTA's copy is live (multicast commit)
+  uint64_t* b_full = bars + 2;                          // leader's
+  uint64_t* b_empty = b_full + kBStages;                // every CTA's
+  uint64_t* t_full = b_empty + kBStages;                // every CTA's
+  uint64_t* t_empty = t_full + 2;                       // leader's: 16 epilogue warps x 2 CTAs
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
 
   if (warp == 0 && elect_one()) {
@@ -202,21 +210,20 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant
     mbar_init(a_full, 1);
     mbar_init(a_empty, 1);
     for (int s = 0; s < kBStages; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&t_full[a], 1); mbar_init(&t_empty[a], 8); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&t_full[a], 1); mbar_init(&t_empty[a], 32); }
     fence_barrier_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_slot, 512);
-    tmem_relinquish();
+    tmem_alloc_pair(tmem_slot, 512);
+    tmem_relinquish_pair();
   }
   tc_fence_before();
-  __syncthreads();
+  __syncwarp();           // the elected lanes above rejoin their warps: barrier.cluster is .aligned
+  cluster_sync_all();     // barriers of BOTH CTAs initialised and TMEM of both allocated before anyone signals
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  // The trigger comes AFTER this CTA owns its TMEM columns: a dependent CTA scheduled early on the same
-  // SM could otherwise take them first and wait forever for this grid to finish.
   pdl_launch_dependents();
-  pdl_wait();   // prologue (barriers, TMEM, tensor-map prefetch) overlapped the previous kernel's tail
+  pdl_wait();
 
   const int units = p.n_ut * p.n_ranges;
 
@@ -224,31 +231,31 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0, it = 0;
-      for (int unit = blockIdx.x; unit < units; unit += gridDim.x, ++it) {
+      for (int unit = cluster; unit < units; unit += n_clusters, ++it) {
         const int ut = unit % p.n_ut, range = unit / p.n_ut;
         mbar_wait(a_empty, (it & 1u) ^ 1u);
-        mbar_arrive_expect_tx(a_full, 2 * kKB * kTile16K);
-        for (int mt = 0; mt < 2; ++mt)
-          for (int kb = 0; kb < kKB; ++kb)
-            tma_load_2d(sA + (mt * kKB + kb) * kTile16K, &tmU, a_full, kb * 64, ut * kUT + mt * 128);
+        if (rank == 0) mbar_arrive_expect_tx(a_full, 2 * kKB * kTile16K);
+        for (int kb = 0; kb < kKB; ++kb)
+          tma_load_2d_pair(sA + kb * kTile16K, &tmU, a_full, kb * 64, ut * kUT + static_cast<int>(rank) * 128);
         const int tile0 = range * p.tiles_per_range;
         const int tile1 = min(p.total_tiles, tile0 + p.tiles_per_range);
         for (int tile = tile0; tile < tile1; ++tile) {
           for (int kb = 0; kb < kKB; ++kb) {
             mbar_wait(&b_empty[stage], phase ^ 1u);
-            mbar_arrive_expect_tx(&b_full[stage], kTile16K);
-            tma_load_2d(sB + stage * kTile16K, &tmI, &b_full[stage], kb * 64, tile * p.tile_stride * kIT);
+            if (rank == 0) mbar_arrive_expect_tx(&b_full[stage], 2 * kTile16K);
+            tma_load_2d_pair(sB + stage * kTile16K, &tmI, &b_full[stage], kb * 64,
+                             tile * p.tile_stride * kIT + static_cast<int>(rank) * 128);
             if (++stage == kBStages) { stage = 0; phase ^= 1u; }
           }
         }
       }
     }
   } else if (warp == 1) {
-    if (elect_one()) {
-      const uint32_t idesc = umma_idesc_bf16(128, kIT, false, false);
+    if (rank == 0 && elect_one()) {
+      const uint32_t idesc = umma_idesc_bf16(256, kIT, false, false);
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0, it = 0;
-      for (int unit = blockIdx.x; unit < units; unit += gridDim.x, ++it) {
+      for (int unit = cluster; unit < units; unit += n_clusters, ++it) {
         const int range = unit / p.n_ut;
         const int tile0 = range * p.tiles_per_range;
         const int tile1 = min(p.total_tiles, tile0 + p.tiles_per_range);
@@ -257,41 +264,46 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant
         for (int tile = tile0; tile < tile1; ++tile) {
           mbar_wait(&t_empty[acc], acc_phase ^ 1u);
           tc_fence_after();
+          const uint32_t d = tmem_base + static_cast<uint32_t>(acc * kIT);
           for (int kb = 0; kb < kKB; ++kb) {
             mbar_wait(&b_full[stage], phase);
             tc_fence_after();
+            const uint32_t a_base = smem_u32(sA + kb * kTile16K);
             const uint32_t b_base = smem_u32(sB + stage * kTile16K);
 #pragma unroll
-            for (int mt = 0; mt < 2; ++mt) {
-              const uint32_t a_base = smem_u32(sA + (mt * kKB + kb) * kTile16K);
-              const uint32_t d = tmem_base + static_cast<uint32_t>(acc * 256 + mt * 128);
-#pragma unroll
-              for (int k = 0; k < 4; ++k)
-                umma_bf16(d, umma_desc_kmajor(a_base + k * 32), umma_desc_kmajor(b_base + k * 32), idesc,
-                          (kb > 0 || k > 0) ? 1u : 0u);
-            }
-            umma_commit(&b_empty[stage]);
+            for (int k = 0; k < 4; ++k)
+              umma_bf16_pair(d, umma_desc_kmajor(a_base + k * 32), umma_desc_kmajor(b_base + k * 32), idesc,
+                             (kb > 0 || k > 0) ? 1u : 0u);
+            umma_commit_pair(&b_empty[stage]);
             if (++stage == kBStages) { stage = 0; phase ^= 1u; }
           }
-          umma_commit(&t_full[acc]);
+          umma_commit_pair(&t_full[acc]);
           acc ^= 1;
           if (acc == 0) acc_phase ^= 1u;
         }
-        umma_commit(a_empty);  // the resident user tile may be replaced once these MMAs retire
+        umma_commit_pair(a_empty);  // the resident user tiles may be replaced once these MMAs retire
       }
     }
   } else if (warp >= 4) {
-    const int e = warp - 4;          // 0..7
-    const int mt = e >> 2, q = e & 3;  // q == warp % 4: TMEM lane quarter
+    // Sixteen epilogue warps per CTA: TMEM lane quarter q (32 user rows) x column quarter (64 of the step's
+    // 256 items = two 32-score chunks). What bounds a step is the LATENCY of the slowest warp's chunk chain
+    // (TMEM load -> max tree -> vote -> rare candidate re-read), because the accumulator buffer is released
+    // only when all 32 warps of the pair are done and there are just two buffers: with eight warps x four
+    // chunks the pass ran at (MMA + scan) / 2 per step with both sides waiting for each other (ncu: t_full
+    // and t_empty waits both hot); handing alternate steps to two sets of eight warps left that chain as
+    // long as before. Two chunks per warp halve it. Warps that share a user row append to separate lists.
+    const int e = warp - 4;                  // 0..15
+    const int colq = e >> 2, q = e & 3;      // q == warp % 4: TMEM lane quarter
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int unit = blockIdx.x; unit < units; unit += gridDim.x) {
+    for (int unit = cluster; unit < units; unit += n_clusters) {
       const int ut = unit % p.n_ut, range = unit / p.n_ut;
       const int tile0 = range * p.tiles_per_range;
       const int tile1 = min(p.total_tiles, tile0 + p.tiles_per_range);
-      const int row = ut * kUT + mt * 128 + q * 32 + lane;
+      const int row = ut * kUT + static_cast<int>(rank) * 128 + q * 32 + lane;
       const bool active = row < p.U;
-      unsigned long long* buf = p.cand + (static_cast<size_t>(range) * p.u_pad + row) * kCap;
+      const size_t list = static_cast<size_t>(range) * kLists + colq;
+      unsigned long long* buf = p.cand + (list * p.u_pad + row) * kCap;
       unsigned long long thr_key = active ? p.thr[row] : ~0ull;
       float thr_s = thr_key == 0ull ? -INFINITY : (active ? key_score(thr_key) : INFINITY);
       int cnt = 0;
@@ -300,46 +312,41 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant
         __syncwarp();
         tc_fence_after();
         const uint32_t t_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
-                                static_cast<uint32_t>(acc * 256 + mt * 128);
+                                static_cast<uint32_t>(acc * kIT + colq * 64);
+        uint32_t r0[32], r1[32];
+        tmem_ld32(t_base, r0);
+        tmem_ld32(t_base + 32, r1);
         if constexpr (kSample) {
           // sample pass: one float per (user, chunk) — the chunk's best score; layout [user][chunk]
-          uint32_t r0[32], r1[32];
-          tmem_ld32(t_base, r0);
-          float* dst = p.smax + static_cast<size_t>(row) * (p.total_tiles * (kIT / 32)) + tile * (kIT / 32);
-#pragma unroll 1
-          for (int c = 0; c < kIT / 32; c += 2) {
-            tmem_ld_wait();
-            tmem_ld32(t_base + (c + 1) * 32, r1);
-            dst[c] = chunk_max(r0);
-            tmem_ld_wait();
-            if (c + 2 < kIT / 32) tmem_ld32(t_base + (c + 2) * 32, r0);
-            dst[c + 1] = chunk_max(r1);
-          }
+          float* dst = p.smax + static_cast<size_t>(row) * (p.total_tiles * kChunks) + tile * kChunks + colq * 2;
+          tmem_ld_wait();
+          dst[0] = chunk_max(r0);
+          dst[1] = chunk_max(r1);
         } else {
-          uint32_t r[32];
-          tmem_ld32(t_base, r);
-#pragma unroll 1
-          for (int c = 0; c < kIT / 32; ++c) {
-            tmem_ld_wait();
-            const uint32_t gm = chunk_group_mask(r, thr_s);
-            if (c + 1 < kIT / 32) tmem_ld32(t_base + (c + 1) * 32, r);   // r is dead: next chunk flies during the vote
-            if (__any_sync(0xffffffffu, gm != 0u))
-              collect_groups(gm, t_base + c * 32, tile * kIT + c * 32, p, lane, row, buf, cnt, thr_key, thr_s);
+          tmem_ld_wait();
+          const uint32_t gm0 = chunk_group_mask(r0, thr_s);
+          const uint32_t gm1 = chunk_group_mask(r1, thr_s);
+          if (__any_sync(0xffffffffu, (gm0 | gm1) != 0u)) {
+            const int idx0 = tile * kIT + colq * 64;
+            collect_groups(gm0 | (gm1 << 8), t_base, idx0, p, lane, row, buf, cnt, thr_key, thr_s);
           }
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&t_empty[acc]);
+        if (lane == 0) mbar_arrive_cluster(&t_empty[acc], 0);
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1u;
       }
-      if constexpr (!kSample) p.cand_cnt[static_cast<size_t>(range) * p.u_pad + row] = active ? cnt : 0;
+      if constexpr (!kSample) p.cand_cnt[list * p.u_pad + row] = active ? cnt : 0;
     }
   }
 
+  // Neither CTA may leave while its partner can still read its shared memory (the leader's MMAs), signal
+  // its barriers (multicast commits, remote arrivals) or write its TMEM.
   tc_fence_before();
-  __syncthreads();
-  if (warp == 2) tmem_dealloc(tmem_base, 512);
+  __syncwarp();
+  cluster_sync_all();
+  if (warp == 2) tmem_dealloc_pair(tmem_base, 512);
 }
 
 // --------------------------------------------------------------------------------------------
@@ -439,16 +446,15 @@ __global__ void __launch_bounds__(256) topk_finalize_kernel(const FinalizeParams
   // thr[u] (the largest "K'-th best of one work unit"). If the pool still overflows, the floor is
   // raised by a bitwise search over the keys in global memory that stops as soon as the count fits.
   unsigned long long floor_key = p.thr[u];
-  int total = 0;
-  for (int r = 0; r < p.n_ranges; ++r) total += p.cand_cnt[static_cast<size_t>(r) * p.u_pad + u];
   int npool = 0;
   for (int attempt = 0; attempt < 2; ++attempt) {
     if (tid == 0) s_n = 0;
     __syncthreads();
-    for (int r = 0; r < p.n_ranges; ++r) {
+    // one warp per list (a list holds a few dozen keys): the eight count -> keys load chains run side by side
+    for (int r = warp; r < p.n_ranges; r += 8) {
       const int n = p.cand_cnt[static_cast<size_t>(r) * p.u_pad + u];
       const unsigned long long* b = p.cand + (static_cast<size_t>(r) * p.u_pad + u) * kCap;
-      for (int i = tid; i < n; i += 256) {
+      for (int i = lane; i < n; i += 32) {
         const unsigned long long k = b[i];
         if (k >= floor_key) {
           const int pos = atomicAdd(&s_n, 1);
@@ -701,54 +707,65 @@ __global__ void rank_metrics_kernel(const int* __restrict__ topk, const int64_t*
 
 using namespace tt;
 
+
+// persistent CTA pairs the launch will run: one per two SMs
+static int num_pairs() {
+  const int n = num_sms() / 2;
+  return n < 1 ? 1 : n;
+}
+
+// Work units (user tile x item range) are dealt round-robin to the persistent CTA pairs, so a pass lasts
+// as long as the pair with the most units: pick the number of ranges whose busiest pair scores the fewest
+// item steps (e.g. 600 units on 148 workers = five units on eight of them, four on the rest: 23 % over
+// the balanced time). Fewer ranges win ties (fewer candidate lists). `reload` = item steps' worth of time
+// a unit spends refilling the resident user tile.
+static int balanced_ranges(int n_ut, int total_tiles, int max_ranges, int reload) {
+  int n_ranges = 1;
+  long best = -1;
+  for (int c = 1; c <= max_ranges; ++c) {
+    const int tpr = (total_tiles + c - 1) / c;
+    const int nr = (total_tiles + tpr - 1) / tpr;
+    const long waves = (static_cast<long>(n_ut) * nr + num_pairs() - 1) / num_pairs();
+    const long cost = waves * (tpr + reload);
+    if (best < 0 || cost < best) { best = cost; n_ranges = c; }
+  }
+  return n_ranges;
+}
+
 extern "C" int tt_topk_plan_make(int U, int N, int kprime, tt_topk_plan* plan) {
   TT_REQUIRE(plan && U > 0 && N > 0, "tt_topk_plan_make: bad arguments");
   TT_REQUIRE(kprime >= 8 && kprime <= 256, "tt_topk_plan_make: kprime %d outside [8, 256]", kprime);
   plan->U = U; plan->N = N; plan->kprime = kprime; plan->cap = kCap;
   plan->n_ut = (U + kUT - 1) / kUT;
   const int total_tiles = (N + kIT - 1) / kIT;
-  // Work units (user tile x item range) are dealt round-robin to one persistent CTA per SM, so the pass
-  // lasts as long as the SM with the most units: pick the number of ranges whose busiest SM scores the
-  // fewest tiles (600 units on 148 SMs = five units on eight SMs, four on the rest: 23 % over the
-  // balanced time; 440 units = 2.97 waves is within 1.5 %). Fewer ranges win ties (fewer lists).
-  int max_ranges = (total_tiles + 63) / 64;        // at least 64 item tiles (8192 items) per range
-  if (max_ranges > 4 * num_sms()) max_ranges = 4 * num_sms();
+  int max_ranges = (total_tiles + 31) / 32;        // at least 32 item steps (8192 items) per range
+  if (max_ranges > 4 * num_pairs()) max_ranges = 4 * num_pairs();
   if (max_ranges < 1) max_ranges = 1;
-  int n_ranges = 1;
-  {
-    long best = -1;
-    for (int c = 1; c <= max_ranges; ++c) {
-      const int tpr = (total_tiles + c - 1) / c;
-      const int nr = (total_tiles + tpr - 1) / tpr;
-      const long waves = (static_cast<long>(plan->n_ut) * nr + num_sms() - 1) / num_sms();
-      const long cost = waves * (tpr + 3);           // +3 tile-times: reload of the resident user tile per unit
-      if (best < 0 || cost < best) { best = cost; n_ranges = c; }
-    }
-  }
+  const int n_ranges = balanced_ranges(plan->n_ut, total_tiles, max_ranges, 2);
   plan->tiles_per_range = (total_tiles + n_ranges - 1) / n_ranges;
   plan->n_ranges = (total_tiles + plan->tiles_per_range - 1) / plan->tiles_per_range;
   const int64_t u_pad = static_cast<int64_t>(plan->n_ut) * kUT;
-  plan->cand_bytes = static_cast<int64_t>(plan->n_ranges) * u_pad * kCap * 8;
-  plan->cnt_bytes = static_cast<int64_t>(plan->n_ranges) * u_pad * 4;
+  plan->cand_bytes = static_cast<int64_t>(plan->n_ranges) * kLists * u_pad * kCap * 8;
+  plan->cnt_bytes = static_cast<int64_t>(plan->n_ranges) * kLists * u_pad * 4;
   plan->thr_bytes = u_pad * 8;
-  // Sample pass: chunk maxima of a strided subset of the tiles (see sample_threshold_kernel).
+  // Sample pass: chunk maxima of a strided subset of the item steps (see sample_threshold_kernel).
   plan->sample_stride = 0; plan->sample_rank = 0; plan->sample_tiles = 0; plan->smax_bytes = 0;
-  if (total_tiles >= 256) {
+  if (total_tiles >= 128) {
     double target = 4.0 * kprime;
     if (target > N / 4.0) target = N / 4.0;
     const double q = target / N;
     const double pc = 1.0 - pow(1.0 - q, 32.0);
-    int tiles = static_cast<int>(24.0 / pc / 4.0 + 0.999);      // expected rank ~ 24
-    if (tiles < 8) tiles = 8;
+    int tiles = static_cast<int>(24.0 / pc / kChunks + 0.999);   // expected rank ~ 24
+    if (tiles < 4) tiles = 4;
     if (tiles > total_tiles / 4) tiles = total_tiles / 4;
-    if (tiles > 240) tiles = 240;                                 // <= 1024 chunk maxima per user (threshold kernel registers)
+    if (tiles > 120) tiles = 120;                                 // <= 1024 chunk maxima per user (threshold kernel registers)
     const int stride = total_tiles / tiles;
     plan->sample_stride = stride;
     plan->sample_tiles = (total_tiles + stride - 1) / stride;
-    int rank = static_cast<int>(pc * plan->sample_tiles * 4 + 0.5);
+    int rank = static_cast<int>(pc * plan->sample_tiles * kChunks + 0.5);
     if (rank < 4) rank = 4;
     plan->sample_rank = rank;
-    plan->smax_bytes = static_cast<int64_t>(plan->sample_tiles) * 4 * u_pad * 4;
+    plan->smax_bytes = static_cast<int64_t>(plan->sample_tiles) * kChunks * u_pad * 4;
   }
   return TT_OK;
 }
@@ -770,19 +787,31 @@ static int launch_score_topk(const void* users_bf16, const void* items_bf16, Top
     int rc = make_tmap_bf16(&tmI, items_bf16, 2, dims, str, box);
     if (rc) return rc;
   }
-  const size_t smem = 1024 + (2 * kKB + kBStages) * kTile16K + 256;
+  const size_t smem = 1024 + (kKB + kBStages) * kTile16K + 256;
   static bool configured = false;
   if (!configured) {
-    TT_CHECK_CUDA(cudaFuncSetAttribute(score_topk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
-    TT_CHECK_CUDA(cudaFuncSetAttribute(score_topk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    TT_CHECK_CUDA(cudaFuncSetAttribute(score_topk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    TT_CHECK_CUDA(cudaFuncSetAttribute(score_topk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     configured = true;
   }
   const int units = p.n_ut * p.n_ranges;
-  const int grid = units < num_sms() ? units : num_sms();
+  const int pairs = units < num_pairs() ? units : num_pairs();
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * pairs);
+  cfg.blockDim = dim3(kTopkThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
   if (p.smax != nullptr)
-    TT_CHECK_CUDA(launch_k(score_topk_kernel<true>, dim3(grid), dim3(kTopkThreads), smem, stream, tmU, tmI, p));
+    TT_CHECK_CUDA(cudaLaunchKernelEx(&cfg, score_topk_kernel<true>, tmU, tmI, p));
   else
-    TT_CHECK_CUDA(launch_k(score_topk_kernel<false>, dim3(grid), dim3(kTopkThreads), smem, stream, tmU, tmI, p));
+    TT_CHECK_CUDA(cudaLaunchKernelEx(&cfg, score_topk_kernel<false>, tmU, tmI, p));
   TT_LAUNCH_CHECK();
   return TT_OK;
 }
@@ -803,24 +832,11 @@ extern "C" int tt_score_topk(const void* users_bf16, const void* items_bf16, int
   p.mask_item0 = mask_item0;
   TT_CHECK_CUDA(cudaMemsetAsync(thr, 0, static_cast<size_t>(plan->thr_bytes), stream));
 
-  // ---- sample pass: chunk maxima of every sample_stride-th tile -> per-user start thresholds
+  // ---- sample pass: chunk maxima of every sample_stride-th item step -> per-user start thresholds
   p.smax = nullptr;
-  if (plan->sample_stride > 1 && smax != nullptr && plan->sample_tiles * 4 <= 1024) {
+  if (plan->sample_stride > 1 && smax != nullptr && plan->sample_tiles * kChunks <= 1024) {
     const int sample_tiles = plan->sample_tiles;
-    // ranges per user tile: the split whose busiest SM gets the fewest tiles (units are dealt round-robin
-    // to the SMs, so 160 units on 148 SMs would cost two full units on 12 of them)
-    int sr = 1;
-    {
-      long best = -1;
-      const int sr_max = sample_tiles < 16 ? sample_tiles : 16;
-      for (int c = 1; c <= sr_max; ++c) {
-        const int tpr = (sample_tiles + c - 1) / c;
-        const int nr = (sample_tiles + tpr - 1) / tpr;
-        const long waves = (static_cast<long>(p.n_ut) * nr + num_sms() - 1) / num_sms();
-        const long cost = waves * (tpr + 2);              // +2: the resident user tile reload per unit
-        if (best < 0 || cost < best) { best = cost; sr = c; }
-      }
-    }
+    const int sr = balanced_ranges(p.n_ut, sample_tiles, sample_tiles < 16 ? sample_tiles : 16, 2);
     p.tile_stride = plan->sample_stride;
     p.tiles_per_range = (sample_tiles + sr - 1) / sr;
     p.n_ranges = (sample_tiles + p.tiles_per_range - 1) / p.tiles_per_range;
@@ -829,7 +845,7 @@ extern "C" int tt_score_topk(const void* users_bf16, const void* items_bf16, int
     p.smax = static_cast<float*>(smax);
     int rc = launch_score_topk(users_bf16, items_bf16, p, plan->N, stream);
     if (rc) return rc;
-    TT_CHECK_CUDA(launch_k(sample_threshold_kernel, dim3((plan->U * 32 + 255) / 256), dim3(256), 0, stream, p.smax, plan->U, sample_tiles * 4, plan->sample_rank, p.thr));
+    TT_CHECK_CUDA(launch_k(sample_threshold_kernel, dim3((plan->U * 32 + 255) / 256), dim3(256), 0, stream, p.smax, plan->U, sample_tiles * kChunks, plan->sample_rank, p.thr));
     TT_LAUNCH_CHECK();
     p.total_tiles = total_saved;
     p.smax = nullptr;
@@ -848,7 +864,7 @@ extern "C" int tt_topk_finalize(const tt_topk_plan* plan, const void* cand, cons
              "tt_topk_finalize: null pointer");
   TT_REQUIRE(K > 0 && K <= plan->kprime, "tt_topk_finalize: K=%d must be in [1, kprime=%d]", K, plan->kprime);
   FinalizeParams p;
-  p.U = plan->U; p.N = plan->N; p.item_base = item_base; p.n_ranges = plan->n_ranges;
+  p.U = plan->U; p.N = plan->N; p.item_base = item_base; p.n_ranges = plan->n_ranges * kLists;   // lists per row
   p.u_pad = plan->n_ut * kUT; p.kprime = plan->kprime; p.K = K;
   p.cand = static_cast<const unsigned long long*>(cand);
   p.cand_cnt = cand_cnt; p.thr = static_cast<const unsigned long long*>(thr); p.users = users_f32; p.items = items_f32; p.eps = eps;
