@@ -40,6 +40,7 @@ static constexpr int kChunks = kIT / 32; // 32-score chunks per item step
 static constexpr int kBStages = 8;     // 16 KB item slices in flight per CTA
 static constexpr int kTopkThreads = 640;   // TMA, MMA, TMEM-alloc, spare + 16 epilogue warps
 static constexpr int kCap = 512;       // candidate list capacity per (range, row)
+static constexpr int kMaxLists = 1216;  // finalize: lists per user (ranges x kLists) the offset table holds
 static constexpr int kPoolCap = 4096;  // finalize: per-user key pool in shared memory
 
 __device__ __forceinline__ uint32_t f2ord(float f) {
@@ -438,6 +439,7 @@ __global__ void __launch_bounds__(256) topk_finalize_kernel(const FinalizeParams
   __shared__ unsigned long long s_pool[kPoolCap];
   __shared__ int s_red[8];
   __shared__ int s_n;
+  __shared__ int s_off[kMaxLists + 1];
   const int u = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
@@ -447,19 +449,43 @@ __global__ void __launch_bounds__(256) topk_finalize_kernel(const FinalizeParams
   // raised by a bitwise search over the keys in global memory that stops as soon as the count fits.
   unsigned long long floor_key = p.thr[u];
   int npool = 0;
+  // Offsets of this user's lists (a few dozen lists of a few dozen keys each): counts are loaded in one
+  // parallel round and scanned by warp 0, so that the keys can then be fetched as ONE flat array — every
+  // thread's loads are independent of each other (two global-load latencies for the whole gather instead
+  // of a count -> keys chain per list).
+  const int n_lists = p.n_ranges;
+  for (int r = tid; r < n_lists; r += 256) s_off[r + 1] = p.cand_cnt[static_cast<size_t>(r) * p.u_pad + u];
+  __syncthreads();
+  if (warp == 0) {
+    const int per = (n_lists + 31) / 32;
+    const int b0 = min(lane * per, n_lists), b1 = min(b0 + per, n_lists);
+    int sum = 0;
+    for (int r = b0; r < b1; ++r) sum += s_off[r + 1];
+    int incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    int run = incl - sum;
+    if (lane == 0) s_off[0] = 0;
+    for (int r = b0; r < b1; ++r) { run += s_off[r + 1]; s_off[r + 1] = run; }
+  }
+  __syncthreads();
+  const int total = s_off[n_lists];
   for (int attempt = 0; attempt < 2; ++attempt) {
     if (tid == 0) s_n = 0;
     __syncthreads();
-    // one warp per list (a list holds a few dozen keys): the eight count -> keys load chains run side by side
-    for (int r = warp; r < p.n_ranges; r += 8) {
-      const int n = p.cand_cnt[static_cast<size_t>(r) * p.u_pad + u];
-      const unsigned long long* b = p.cand + (static_cast<size_t>(r) * p.u_pad + u) * kCap;
-      for (int i = lane; i < n; i += 32) {
-        const unsigned long long k = b[i];
-        if (k >= floor_key) {
-          const int pos = atomicAdd(&s_n, 1);
-          if (pos < kPoolCap) s_pool[pos] = k;
-        }
+    for (int f = tid; f < total; f += 256) {
+      int lo = 0, hi = n_lists - 1;          // last list r with s_off[r] <= f
+      while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (s_off[mid] <= f) lo = mid; else hi = mid - 1;
+      }
+      const unsigned long long k = p.cand[(static_cast<size_t>(lo) * p.u_pad + u) * kCap + (f - s_off[lo])];
+      if (k >= floor_key) {
+        const int pos = atomicAdd(&s_n, 1);
+        if (pos < kPoolCap) s_pool[pos] = k;
       }
     }
     __syncthreads();
@@ -726,7 +752,7 @@ static int balanced_ranges(int n_ut, int total_tiles, int max_ranges, int reload
     const int tpr = (total_tiles + c - 1) / c;
     const int nr = (total_tiles + tpr - 1) / tpr;
     const long waves = (static_cast<long>(n_ut) * nr + num_pairs() - 1) / num_pairs();
-    const long cost = waves * (tpr + reload);
+    const long cost = 2 * waves * (tpr + reload) + c;   // + c/2 steps: every range adds lists to merge
     if (best < 0 || cost < best) { best = cost; n_ranges = c; }
   }
   return n_ranges;
@@ -740,6 +766,7 @@ extern "C" int tt_topk_plan_make(int U, int N, int kprime, tt_topk_plan* plan) {
   const int total_tiles = (N + kIT - 1) / kIT;
   int max_ranges = (total_tiles + 31) / 32;        // at least 32 item steps (8192 items) per range
   if (max_ranges > 4 * num_pairs()) max_ranges = 4 * num_pairs();
+  if (max_ranges > kMaxLists / kLists) max_ranges = kMaxLists / kLists;
   if (max_ranges < 1) max_ranges = 1;
   const int n_ranges = balanced_ranges(plan->n_ut, total_tiles, max_ranges, 2);
   plan->tiles_per_range = (total_tiles + n_ranges - 1) / n_ranges;
@@ -863,6 +890,8 @@ extern "C" int tt_topk_finalize(const tt_topk_plan* plan, const void* cand, cons
   TT_REQUIRE(plan && cand && cand_cnt && thr && users_f32 && items_f32 && out_idx && out_score && flags,
              "tt_topk_finalize: null pointer");
   TT_REQUIRE(K > 0 && K <= plan->kprime, "tt_topk_finalize: K=%d must be in [1, kprime=%d]", K, plan->kprime);
+  TT_REQUIRE(plan->n_ranges * kLists <= kMaxLists, "tt_topk_finalize: %d candidate lists per user exceed %d",
+             plan->n_ranges * kLists, kMaxLists);
   FinalizeParams p;
   p.U = plan->U; p.N = plan->N; p.item_base = item_base; p.n_ranges = plan->n_ranges * kLists;   // lists per row
   p.u_pad = plan->n_ut * kUT; p.kprime = plan->kprime; p.K = K;
