@@ -75,15 +75,16 @@ def retrieve_topk(user_emb: torch.Tensor, index: CatalogIndex, K: int, kprime: i
     plan = index.plan(U, kprime)
     sc = index._scratch[(U, kprime)]
     ops.cast_bf16(user_emb.view(-1), sc["users_bf16"].view(-1))
-    check(lib().tt_score_topk(sc["users_bf16"].data_ptr(), index.table_bf16.data_ptr(), index.item_base,
-                              ctypes.byref(plan), sc["cand"].data_ptr(), sc["cnt"].data_ptr(), sc["thr"].data_ptr(),
-                              None if sc["smax"] is None else sc["smax"].data_ptr(), int(mask_item0), _stream()),
-          "tt_score_topk")
-    # rigorous bound on |u^.e^ - u.e| (Cauchy-Schwarz on the bf16 rounding errors) + fp32 accumulation slack
+    # rigorous bound on |u^.e^ - u.e| (Cauchy-Schwarz on the bf16 rounding errors) + fp32 accumulation slack.
+    # Its host read-back happens BEFORE the scoring pass is queued, so scoring and finalize run back to back.
     u16 = sc["users_bf16"].float()
     du = (u16 - user_emb).norm(dim=1).max()
     nu = user_emb.norm(dim=1).max()
     eps = float((du * index.ne_max + nu * index.de_max + nu * index.ne_max * 2.0 ** -18).item())
+    check(lib().tt_score_topk(sc["users_bf16"].data_ptr(), index.table_bf16.data_ptr(), index.item_base,
+                              ctypes.byref(plan), sc["cand"].data_ptr(), sc["cnt"].data_ptr(), sc["thr"].data_ptr(),
+                              None if sc["smax"] is None else sc["smax"].data_ptr(), int(mask_item0), _stream()),
+          "tt_score_topk")
     dev = user_emb.device
     out_idx = torch.empty(U, K, device=dev, dtype=torch.int32)
     out_score = torch.empty(U, K, device=dev, dtype=torch.float32)

@@ -164,3 +164,65 @@ def test_gemm_mn_major_ragged_n():
     ops.gemm(A, B, b_mn=True, out_f32=out, N=N, K=K)
     torch.cuda.synchronize()
     _check(out, A.float() @ B.float(), K, "ragged MN-major N")
+
+
+# ---- encoder-sized launches: many waves of the persistent loop, odd row-block counts, ragged edges ----
+@pytest.mark.parametrize("a_mn,b_mn", LAYOUTS, ids=LAYOUT_IDS)
+def test_gemm_large_layouts(a_mn, b_mn):
+    """75 row blocks with a ragged last one, ragged N (520) and K (320), every operand layout."""
+    from mrm_b200 import ops
+    M, N, K = 128 * 75 - 56, 520, 320
+    A, B, As, Bs = _operands(M, N, K, a_mn, b_mn, seed=31)
+    if b_mn:                                  # keep the ragged 64-chunk of an MN-major B readable
+        Bfull = torch.zeros(K + 1, N, device="cuda", dtype=torch.bfloat16)
+        Bfull[:K] = Bs
+        Bs = Bfull[:K]
+    if a_mn:
+        Afull = torch.zeros(K + 1, M, device="cuda", dtype=torch.bfloat16)
+        Afull[:K] = As
+        As = Afull[:K]
+    out = torch.full((M, N), float("nan"), device="cuda", dtype=torch.float32)
+    ops.gemm(As, Bs, a_mn=a_mn, b_mn=b_mn, out_f32=out, M=M, N=N, K=K)
+    torch.cuda.synchronize()
+    _check(out, A.float() @ B.float().t(), K, "large")
+
+
+def test_gemm_large_epilogues():
+    """Encoder-sized launch (M = 51 200 / 4): bias + ReLU + dropout + residual, fp32 and bf16 outputs, gate."""
+    from mrm_b200 import ops
+    M, N, K = 12800, 768, 256
+    A, B, As, Bs = _operands(M, N, K, False, False, seed=41)
+    g = torch.Generator().manual_seed(2)
+    bias = torch.randn(N, generator=g).cuda()
+    res = torch.randn(M, N, generator=g).cuda()
+    o32 = torch.empty((M, N), device="cuda")
+    o16 = torch.empty((M, N), device="cuda", dtype=torch.bfloat16)
+    ops.gemm(As, Bs, alpha=0.5, bias=bias, relu=True, residual=res, out_f32=o32, out_bf16=o16)
+    torch.cuda.synchronize()
+    ref = torch.relu(0.5 * (A.float() @ B.float().t()) + bias) + res
+    _check(o32, ref, K, "large epilogue fp32")
+    assert (o16.float() - ref).abs().max().item() <= 2 ** -7 * ref.abs().max().item()
+    gate = _mk((M, N), 43)
+    og = torch.empty((M, N), device="cuda", dtype=torch.bfloat16)
+    ops.gemm(As, Bs, gate=gate, gate_scale=1.25, out_bf16=og)
+    torch.cuda.synchronize()
+    refg = (A.float() @ B.float().t()) * 1.25 * (gate.float() > 0)
+    assert (og.float() - refg).abs().max().item() <= 2 ** -7 * refg.abs().max().item()
+    o1 = torch.empty((M, N), device="cuda")
+    o2 = torch.empty((M, N), device="cuda")
+    ops.gemm(As, Bs, drop_p=0.25, drop_seed=5, drop_site=1, out_f32=o1)
+    ops.gemm(As, Bs, drop_p=0.25, drop_seed=5, drop_site=1, out_f32=o2, block_n=64)   # other tile width, same mask
+    torch.cuda.synchronize()
+    assert torch.equal(o1 != 0, o2 != 0)
+    assert torch.allclose(o1, o2, rtol=1e-5, atol=1e-5)
+
+
+def test_gemm_large_splitk_wgrad():
+    """Weight-gradient shape (1024 x 256 over 19 200 tokens, both operands MN-major): 8 row blocks x 18 splits."""
+    from mrm_b200 import ops
+    M, N, K = 1024, 256, 64 * 300
+    A, B, As, Bs = _operands(M, N, K, True, True, seed=51)
+    out = torch.ones((M, N), device="cuda")
+    ops.gemm(As, Bs, a_mn=True, b_mn=True, out_f32=out, accumulate=True)
+    torch.cuda.synchronize()
+    _check(out, A.float() @ B.float().t() + 1.0, K, "large split-K")
