@@ -40,6 +40,8 @@ struct GemmParams {
   __nv_bfloat16* out_bf16;
   int ld_bf16;
   int accumulate;
+  int pair;         // 1 = CTA pairs (cluster of 2, tcgen05 cta_group::2): a pair computes a 256-row x block_n tile;
+                    // each CTA stages its 128 rows of A and HALF of the B tile, the leader issues M=256 MMAs
   int stg_bytes;    // per-epilogue-warp staging bytes (tile + 256 B bias slice)
   int debug;  // profiling knob: 1 = epilogue drains TMEM only (no math, no global IO); 2 = everything but the global stores
 };
@@ -214,7 +216,7 @@ __device__ __forceinline__ void gemm_epilogue_chunk(const GemmParams& p, const u
   if ((p.residual || p.gate) && next_col0 >= 0) epi_prefetch(p, in, lane, row0, next_col0);
 }
 
-template <bool A_MN, bool B_MN>
+template <bool A_MN, bool B_MN, bool PAIR>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const GemmParams p) {
@@ -226,7 +228,19 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int lane = threadIdx.x & 31;
   const int stages = p.stages;
   const int block_n = p.block_n;
-  const uint32_t b_bytes = static_cast<uint32_t>(block_n) * kBlockK * 2;
+  // CTA-pair mode (p.pair): the two CTAs of a cluster take row blocks 2i and 2i+1 of the same column block
+  // and k range. Each stages its own A rows and HALF of the B tile (rows / 64-wide chunks [rank * half, +half));
+  // the leader's single MMA thread issues cta_group::2 MMAs (M = 256) that read both CTAs' shared memory and
+  // write 128 TMEM lanes in each. Per SM that is a third fewer operand bytes through TMA and the tensor
+  // pipe reads 8 KB instead of 12 KB of shared memory per 256-wide MMA. Barrier protocol as in score_topk:
+  // TMA bytes of both CTAs complete on the LEADER's full barrier, tcgen05.commit is multicast to the empty /
+  // accumulator-full barriers of both CTAs, epilogue warps of both release the accumulator on the leader.
+  constexpr bool pair = PAIR;   // a kernel that contains cta_group::2 instructions can only be launched as a cluster of 2
+  uint32_t rank = 0;
+  if constexpr (pair) rank = cluster_ctarank();
+  const int worker = pair ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int n_workers = pair ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+  const uint32_t b_bytes = (static_cast<uint32_t>(block_n) * kBlockK * 2) >> (pair ? 1 : 0);   // per CTA
 
   const int kblocks = (p.K + kBlockK - 1) / kBlockK;
   uint8_t* sA = smem;
@@ -251,16 +265,18 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull_bar[a], 1);
-      mbar_init(&tempty_bar[a], kEpiWarps);
+      mbar_init(&tempty_bar[a], pair ? 2 * kEpiWarps : kEpiWarps);
     }
     fence_barrier_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_slot, tmem_cols);
-    tmem_relinquish();
+    if constexpr (pair) { tmem_alloc_pair(tmem_slot, tmem_cols); tmem_relinquish_pair(); }
+    else      { tmem_alloc(tmem_slot, tmem_cols); tmem_relinquish(); }
   }
   tc_fence_before();
-  __syncthreads();
+  __syncwarp();                   // elected lanes rejoin their warps: barrier.cluster is .aligned
+  if constexpr (pair) cluster_sync_all();   // both CTAs' barriers and TMEM exist before anything is signalled across
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   // The trigger comes AFTER this CTA owns its TMEM columns: a dependent CTA scheduled early on the same
@@ -270,38 +286,52 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   const int tiles_m = (p.M + kBlockM - 1) / kBlockM;
   const int tiles_n = (p.N + block_n - 1) / block_n;
-  const int num_tiles = tiles_m * tiles_n * p.k_splits;
+  const int tiles_mw = pair ? (tiles_m + 1) / 2 : tiles_m;      // row blocks (pairs of them) a worker walks
+  const int num_tiles = tiles_mw * tiles_n * p.k_splits;
+  // row block of work item mn: in pair mode the odd CTA may get one past the end (odd tiles_m): it still
+  // loads (zero-filled) in lockstep and stores nothing.
+  auto m_block = [&](int mn) { return pair ? 2 * (mn / tiles_n) + static_cast<int>(rank) : mn / tiles_n; };
   if (warp == 0) {
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      for (int t = worker; t < num_tiles; t += n_workers) {
         const int split = t % p.k_splits;
         const int mn = t / p.k_splits;
-        const int m_blk = mn / tiles_n, n_blk = mn % tiles_n;
+        const int m_blk = m_block(mn), n_blk = mn % tiles_n;
         const int kb0 = static_cast<int>(static_cast<long long>(split) * kblocks / p.k_splits);
         const int kb1 = static_cast<int>(static_cast<long long>(split + 1) * kblocks / p.k_splits);
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1u);
-          mbar_arrive_expect_tx(&full_bar[stage], kABytes + b_bytes);
           uint8_t* a_dst = sA + static_cast<size_t>(stage) * kABytes;
-          if (A_MN) tma_load_3d(a_dst, &tmA, &full_bar[stage], 0, kb * kBlockK, m_blk * (kBlockM / 64));
-          else      tma_load_2d(a_dst, &tmA, &full_bar[stage], kb * kBlockK, m_blk * kBlockM);
           uint8_t* b_dst = sB + static_cast<size_t>(stage) * b_bytes;
-          if (B_MN) tma_load_3d(b_dst, &tmB, &full_bar[stage], 0, kb * kBlockK, n_blk * (block_n / 64));
-          else      tma_load_2d(b_dst, &tmB, &full_bar[stage], kb * kBlockK, n_blk * block_n);
+          if constexpr (pair) {
+            if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * (kABytes + b_bytes));
+            if (A_MN) tma_load_3d_pair(a_dst, &tmA, &full_bar[stage], 0, kb * kBlockK, m_blk * (kBlockM / 64));
+            else      tma_load_2d_pair(a_dst, &tmA, &full_bar[stage], kb * kBlockK, m_blk * kBlockM);
+            if (B_MN) tma_load_3d_pair(b_dst, &tmB, &full_bar[stage], 0, kb * kBlockK,
+                                       n_blk * (block_n / 64) + static_cast<int>(rank) * (block_n / 128));
+            else      tma_load_2d_pair(b_dst, &tmB, &full_bar[stage], kb * kBlockK,
+                                       n_blk * block_n + static_cast<int>(rank) * (block_n / 2));
+          } else {
+            mbar_arrive_expect_tx(&full_bar[stage], kABytes + b_bytes);
+            if (A_MN) tma_load_3d(a_dst, &tmA, &full_bar[stage], 0, kb * kBlockK, m_blk * (kBlockM / 64));
+            else      tma_load_2d(a_dst, &tmA, &full_bar[stage], kb * kBlockK, m_blk * kBlockM);
+            if (B_MN) tma_load_3d(b_dst, &tmB, &full_bar[stage], 0, kb * kBlockK, n_blk * (block_n / 64));
+            else      tma_load_2d(b_dst, &tmB, &full_bar[stage], kb * kBlockK, n_blk * block_n);
+          }
           if (++stage == stages) { stage = 0; phase ^= 1u; }
         }
       }
     }
   } else if (warp == 1) {
-    if (elect_one()) {
-      const uint32_t idesc = umma_idesc_bf16(kBlockM, block_n, A_MN, B_MN);
+    if (rank == 0 && elect_one()) {
+      const uint32_t idesc = umma_idesc_bf16(pair ? 2 * kBlockM : kBlockM, block_n, A_MN, B_MN);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      for (int t = worker; t < num_tiles; t += n_workers) {
         const int split = t % p.k_splits;
         const int kb0 = static_cast<int>(static_cast<long long>(split) * kblocks / p.k_splits);
         const int kb1 = static_cast<int>(static_cast<long long>(split + 1) * kblocks / p.k_splits);
@@ -321,12 +351,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                                         : umma_desc_kmajor(a_base + k * 32);
             const uint64_t bdesc = B_MN ? umma_desc_mnmajor(b_base + k * 2048, kBlockK * 128)
                                         : umma_desc_kmajor(b_base + k * 32);
-            umma_bf16(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            if constexpr (pair) umma_bf16_pair(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            else      umma_bf16(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
+          if constexpr (pair) umma_commit_pair(&empty_bar[stage]);   // both CTAs' smem slots reusable once these MMAs retire
+          else      umma_commit(&empty_bar[stage]);
           if (++stage == stages) { stage = 0; phase ^= 1u; }
         }
-        umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
+        if constexpr (pair) umma_commit_pair(&tfull_bar[acc]);       // accumulator complete -> both CTAs' epilogues
+        else      umma_commit(&tfull_bar[acc]);
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1u;
       }
@@ -345,18 +378,18 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     int acc = 0;
     uint32_t acc_phase = 0;
     const bool has_in = p.residual || p.gate;
-    if (has_in && static_cast<int>(blockIdx.x) < num_tiles) {
-      const int mn = static_cast<int>(blockIdx.x) / p.k_splits;
-      epi_prefetch_l2(p, lane, (mn / tiles_n) * kBlockM + q * 32, (mn % tiles_n) * block_n, sub, nchunks);
+    if (has_in && worker < num_tiles) {
+      const int mn = worker / p.k_splits;
+      epi_prefetch_l2(p, lane, m_block(mn) * kBlockM + q * 32, (mn % tiles_n) * block_n, sub, nchunks);
     }
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+    for (int t = worker; t < num_tiles; t += n_workers) {
       const int mn = t / p.k_splits;
-      const int m_blk = mn / tiles_n, n_blk = mn % tiles_n;
+      const int m_blk = m_block(mn), n_blk = mn % tiles_n;
       const int row0 = m_blk * kBlockM + q * 32;
       const int colbase = n_blk * block_n;
-      if (has_in && t + static_cast<int>(gridDim.x) < num_tiles) {   // next tile's lines -> L2 while this one computes
-        const int mn2 = (t + static_cast<int>(gridDim.x)) / p.k_splits;
-        epi_prefetch_l2(p, lane, (mn2 / tiles_n) * kBlockM + q * 32, (mn2 % tiles_n) * block_n, sub, nchunks);
+      if (has_in && t + n_workers < num_tiles) {   // next tile's lines -> L2 while this one computes
+        const int mn2 = (t + n_workers) / p.k_splits;
+        epi_prefetch_l2(p, lane, m_block(mn2) * kBlockM + q * 32, (mn2 % tiles_n) * block_n, sub, nchunks);
       }
       // Everything that does not depend on the accumulator is issued before waiting for it:
       // the bias slice of this warp's chunks and the first residual / gate block.
@@ -374,7 +407,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const uint32_t t_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
                               static_cast<uint32_t>(acc * block_n);
       uint32_t r[32];
-      for (int c = sub, k = 0; c < nchunks; c += kEpiWarps / 4, ++k) {
+      for (int c = sub, k = 0; c < nchunks && m_blk < tiles_m; c += kEpiWarps / 4, ++k) {
         tmem_ld32(t_base + static_cast<uint32_t>(c * 32), r);
         tmem_ld_wait();
         const int cn = c + kEpiWarps / 4;
@@ -385,15 +418,23 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       if (p.debug == 1) cp_async_wait_all();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (lane == 0) {
+        if constexpr (pair) mbar_arrive_cluster(&tempty_bar[acc], 0);
+        else      mbar_arrive(&tempty_bar[acc]);
+      }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
     }
   }
 
   tc_fence_before();
-  __syncthreads();
-  if (warp == 2) tmem_dealloc(tmem_base, tmem_cols);
+  __syncwarp();
+  if constexpr (pair) cluster_sync_all();   // the partner may still read this CTA's smem, signal its barriers, write its TMEM
+  else __syncthreads();
+  if (warp == 2) {
+    if constexpr (pair) tmem_dealloc_pair(tmem_base, tmem_cols);
+    else      tmem_dealloc(tmem_base, tmem_cols);
+  }
 }
 
 static constexpr size_t kSmemLimit = 232448;
@@ -401,19 +442,42 @@ static size_t gemm_fixed_smem(int stg_bytes) {   // alignment pad, staging, barr
   return 1024 + static_cast<size_t>(kEpiWarps) * stg_bytes + (2 * 8 + 4) * sizeof(uint64_t) + 16;
 }
 
-template <bool A_MN, bool B_MN>
+template <bool A_MN, bool B_MN, bool PAIR>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, int grid,
                        size_t smem, cudaStream_t stream) {
   static bool configured = false;
   if (!configured) {
-    TT_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<A_MN, B_MN>,
+    TT_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<A_MN, B_MN, PAIR>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
     configured = true;
   }
   TT_REQUIRE(smem <= kSmemLimit, "tt_gemm_bf16: %zu B of shared memory requested", smem);
-  TT_CHECK_CUDA(launch_k(gemm_bf16_kernel<A_MN, B_MN>, dim3(grid), dim3(kGemmThreads), smem, stream, tmA, tmB, p));
+  if (PAIR) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kGemmThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    TT_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_kernel<A_MN, B_MN, PAIR>, tmA, tmB, p));
+  } else {
+    TT_CHECK_CUDA(launch_k(gemm_bf16_kernel<A_MN, B_MN, PAIR>, dim3(grid), dim3(kGemmThreads), smem, stream, tmA, tmB, p));
+  }
   TT_LAUNCH_CHECK();
   return TT_OK;
+}
+
+template <bool A_MN, bool B_MN>
+static int launch_gemm_mode(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, int grid,
+                            size_t smem, cudaStream_t stream) {
+  return p.pair ? launch_gemm<A_MN, B_MN, true>(tmA, tmB, p, grid, smem, stream)
+                : launch_gemm<A_MN, B_MN, false>(tmA, tmB, p, grid, smem, stream);
 }
 
 }  // namespace tt
@@ -470,16 +534,6 @@ extern "C" int tt_gemm_bf16(const tt_gemm_args* a, void* stream_) {
   const int tiles_m = (a->M + kBlockM - 1) / kBlockM;
   const int tiles_n = (a->N + bn - 1) / bn;
   const int kblocks = (a->K + kBlockK - 1) / kBlockK;
-  const size_t b_bytes = static_cast<size_t>(bn) * kBlockK * 2;
-  // bf16-only epilogues stage 64-byte rows: half the staging, more pipeline stages
-  p.stg_bytes = static_cast<int>(((a->out_f32 || a->residual) ? kStageBytesF32 : kStageBytesBf16) +
-                                 (a->bias ? kBiasBytesPerWarp : 0u));
-  const size_t fixed = gemm_fixed_smem(p.stg_bytes);
-  int stages = static_cast<int>((kSmemLimit - fixed) / (kABytes + b_bytes));
-  if (stages > 8) stages = 8;
-  TT_REQUIRE(stages >= 2, "tt_gemm_bf16: no room for a 2-stage pipeline (block_n %d)", bn);
-  p.stages = stages;
-
   int ks = a->k_splits;
   if (ks <= 0) {
     ks = 1;
@@ -495,6 +549,30 @@ extern "C" int tt_gemm_bf16(const tt_gemm_args* a, void* stream_) {
   if (ks < 1) ks = 1;
   TT_REQUIRE(ks == 1 || a->accumulate, "tt_gemm_bf16: k_splits > 1 requires accumulate");
   p.k_splits = ks;
+
+  // CTA pairs (see the kernel): for launches where every pair of SMs still gets (nearly) a full share of
+  // work items AND the contraction per tile is deep (>= 8 k-blocks): measured on the c2 step, the K >= 512
+  // launches gain 7-15 % (dgrad 1024: 39.3 -> 33.3 us, wgrads 36.9 -> 32.8 / 45.0 -> 38.8 us) while the
+  // epilogue-bound K = 256 ones lose 10-20 % to the lockstep of the pair (QKV 37.1 -> 42.9 us).
+  // TT_GEMM_PAIR=0 disables, =2 takes every eligible launch.
+  const int pairs = num_sms() / 2 > 0 ? num_sms() / 2 : 1;
+  const long pair_items = static_cast<long>((tiles_m + 1) / 2) * tiles_n * ks;
+  {
+    static int pair_env = -1;
+    if (pair_env < 0) { const char* e = getenv("TT_GEMM_PAIR"); pair_env = e ? atoi(e) : 1; }
+    const bool eligible = bn >= 128 && tiles_m >= 2 && pair_items * 10 >= static_cast<long>(pairs) * 9;
+    const bool deep = kblocks / ks >= 8;
+    p.pair = (pair_env != 0 && eligible && (deep || pair_env == 2)) ? 1 : 0;
+  }
+  const size_t b_bytes = (static_cast<size_t>(bn) * kBlockK * 2) >> (p.pair ? 1 : 0);   // per CTA
+  // bf16-only epilogues stage 64-byte rows: half the staging, more pipeline stages
+  p.stg_bytes = static_cast<int>(((a->out_f32 || a->residual) ? kStageBytesF32 : kStageBytesBf16) +
+                                 (a->bias ? kBiasBytesPerWarp : 0u));
+  const size_t fixed = gemm_fixed_smem(p.stg_bytes);
+  int stages = static_cast<int>((kSmemLimit - fixed) / (kABytes + b_bytes));
+  if (stages > 8) stages = 8;
+  TT_REQUIRE(stages >= 2, "tt_gemm_bf16: no room for a 2-stage pipeline (block_n %d)", bn);
+  p.stages = stages;
 
   p.alpha = a->alpha;
   p.bias = a->bias;
@@ -543,23 +621,28 @@ extern "C" int tt_gemm_bf16(const tt_gemm_args* a, void* stream_) {
   if (a->b_mn) {
     uint64_t dims[3] = {64, static_cast<uint64_t>(a->K), static_cast<uint64_t>((a->N + 63) / 64)};
     uint64_t str[2] = {static_cast<uint64_t>(a->ldb) * 2, 128};
-    uint32_t box[3] = {64, kBlockK, static_cast<uint32_t>(bn / 64)};
+    uint32_t box[3] = {64, kBlockK, static_cast<uint32_t>(p.pair ? bn / 128 : bn / 64)};
     rc = make_tmap_bf16(&tmB, a->B, 3, dims, str, box);
   } else {
     uint64_t dims[2] = {static_cast<uint64_t>(a->K), static_cast<uint64_t>(a->N)};
     uint64_t str[1] = {static_cast<uint64_t>(a->ldb) * 2};
-    uint32_t box[2] = {kBlockK, static_cast<uint32_t>(bn)};
+    uint32_t box[2] = {kBlockK, static_cast<uint32_t>(p.pair ? bn / 2 : bn)};
     rc = make_tmap_bf16(&tmB, a->B, 2, dims, str, box);
   }
   if (rc) return rc;
 
-  const int num_tiles = tiles_m * tiles_n * ks;
-  int grid = num_tiles < num_sms() ? num_tiles : num_sms();
+  int grid;
+  if (p.pair) {
+    grid = 2 * static_cast<int>(pair_items < pairs ? pair_items : pairs);
+  } else {
+    const int num_tiles = tiles_m * tiles_n * ks;
+    grid = num_tiles < num_sms() ? num_tiles : num_sms();
+  }
   const size_t smem = fixed + static_cast<size_t>(stages) * (kABytes + b_bytes);
   if (a->a_mn) {
-    return a->b_mn ? launch_gemm<true, true>(tmA, tmB, p, grid, smem, stream)
-                   : launch_gemm<true, false>(tmA, tmB, p, grid, smem, stream);
+    return a->b_mn ? launch_gemm_mode<true, true>(tmA, tmB, p, grid, smem, stream)
+                   : launch_gemm_mode<true, false>(tmA, tmB, p, grid, smem, stream);
   }
-  return a->b_mn ? launch_gemm<false, true>(tmA, tmB, p, grid, smem, stream)
-                 : launch_gemm<false, false>(tmA, tmB, p, grid, smem, stream);
+  return a->b_mn ? launch_gemm_mode<false, true>(tmA, tmB, p, grid, smem, stream)
+                 : launch_gemm_mode<false, false>(tmA, tmB, p, grid, smem, stream);
 }

@@ -168,10 +168,12 @@ def test_gemm_mn_major_ragged_n():
 
 # ---- encoder-sized launches: many waves of the persistent loop, odd row-block counts, ragged edges ----
 @pytest.mark.parametrize("a_mn,b_mn", LAYOUTS, ids=LAYOUT_IDS)
-def test_gemm_large_layouts(a_mn, b_mn):
-    """75 row blocks with a ragged last one, ragged N (520) and K (320), every operand layout."""
+@pytest.mark.parametrize("K", [320, 712], ids=["k320", "k712"])
+def test_gemm_large_layouts(a_mn, b_mn, K):
+    """75 row blocks with a ragged last one, ragged N (520) and K, every operand layout. K = 712 (12 k-blocks)
+    takes the CTA-pair path (cta_group::2, the odd last pair has an empty partner), K = 320 the single-CTA one."""
     from mrm_b200 import ops
-    M, N, K = 128 * 75 - 56, 520, 320
+    M, N = 128 * 75 - 56, 520
     A, B, As, Bs = _operands(M, N, K, a_mn, b_mn, seed=31)
     if b_mn:                                  # keep the ragged 64-chunk of an MN-major B readable
         Bfull = torch.zeros(K + 1, N, device="cuda", dtype=torch.bfloat16)
@@ -187,10 +189,12 @@ def test_gemm_large_layouts(a_mn, b_mn):
     _check(out, A.float() @ B.float().t(), K, "large")
 
 
-def test_gemm_large_epilogues():
-    """Encoder-sized launch (M = 51 200 / 4): bias + ReLU + dropout + residual, fp32 and bf16 outputs, gate."""
+@pytest.mark.parametrize("K", [256, 768], ids=["k256", "k768-pairs"])
+def test_gemm_large_epilogues(K):
+    """Encoder-sized launch (M = 51 200 / 4): bias + ReLU + dropout + residual, fp32 and bf16 outputs, gate;
+    K = 768 runs on CTA pairs, K = 256 on single CTAs."""
     from mrm_b200 import ops
-    M, N, K = 12800, 768, 256
+    M, N = 12800, 768
     A, B, As, Bs = _operands(M, N, K, False, False, seed=41)
     g = torch.Generator().manual_seed(2)
     bias = torch.randn(N, generator=g).cuda()
