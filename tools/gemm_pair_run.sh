@@ -1,6 +1,6 @@
 #!/bin/bash
 # GEMM CTA-pair modes: parity tests under TT_GEMM_PAIR=$TESTMODE, then the c2 bench for each mode in $MODES
-# (0 = off, 1 = deep-K launches only (default), 2 = every eligible launch, 3 = 1 + resident-B on the shallow ones).
+# (0 = off, 1 = deep-K launches only (default), 2 = every eligible launch).
 out=gpurun_out/pair; mkdir -p $out
 TT_GEMM_PAIR=${TESTMODE:-1} timeout 400 python -m pytest tests/test_gemm.py tests/test_engine.py -m gpu -q > $out/pytest.log 2>&1; echo "pytest (TT_GEMM_PAIR=${TESTMODE:-1}) rc=$?"; tail -6 $out/pytest.log
 for P in ${MODES:-0 1}; do
