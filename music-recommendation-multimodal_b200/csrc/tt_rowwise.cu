@@ -706,7 +706,10 @@ __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, float
     reinterpret_cast<float4*>(p)[i] = pp;
     reinterpret_cast<float4*>(m)[i] = mm;
     reinterpret_cast<float4*>(v)[i] = vv;
-    if (zero_grad) reinterpret_cast<float4*>(g)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    // ID-table rows no token of the batch touched (60 % of them at c2) already hold a zero gradient: skip
+    // the 16-byte store (bit patterns compared, so a -0.0 is rewritten as +0.0 like before)
+    if (zero_grad && ((__float_as_uint(gg.x) | __float_as_uint(gg.y) | __float_as_uint(gg.z) | __float_as_uint(gg.w)) != 0u))
+      reinterpret_cast<float4*>(g)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (shadow && i >= shadow_begin4 && i < shadow_end4) {
       uint2 u;
       u.x = pack_bf16(pp.x, pp.y);

@@ -9,6 +9,7 @@ timeout 600 python bench.py --steps 50 --warmup 5 > $out/bench.json 2> $out/benc
 timeout 400 python bench.py --impl reference --steps 2 --warmup 1 > $out/bench_reference.json 2> $out/bench_reference.err; echo "bench-ref rc=$?" | tee -a $out/status.txt
 timeout 200 python tools/profile_step.py > /dev/null 2>&1 && timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file $out/launches_train.csv python tools/profile_step.py > $out/ncu_lt.log 2>&1; echo "launches-train rc=$?" | tee -a $out/status.txt
 timeout 200 python tools/profile_step.py --what retrieval > /dev/null 2>&1 && timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file $out/launches_retrieval.csv python tools/profile_step.py --what retrieval > $out/ncu_lr.log 2>&1; echo "launches-retrieval rc=$?" | tee -a $out/status.txt
+if [ "${FULL:-1}" = "1" ]; then
 timeout 500 ncu --set full --clock-control none --profile-from-start off -k regex:gemm_bf16 -o $out/gemm_full -f python tools/profile_step.py > $out/ncu_fg.log 2>&1; echo "full-gemm rc=$?" | tee -a $out/status.txt
 timeout 300 ncu --set full --clock-control none --profile-from-start off -k regex:'score_topk|topk_finalize|sample_threshold' -o $out/topk_full -f python tools/profile_step.py --what retrieval > $out/ncu_ft.log 2>&1; echo "full-topk rc=$?" | tee -a $out/status.txt
 # .ncu-rep files are too large to travel back: summarise on the box, keep the text
@@ -17,6 +18,7 @@ python tools/ncu_summary.py --gemm-traffic $out/gemm_full.ncu-rep $out/gemm_dram
 python tools/ncu_summary.py $out/topk_full.ncu-rep > $out/ncu_full_topk.summary.txt 2>&1
 ncu -i $out/gemm_full.ncu-rep --page raw --csv 2>/dev/null | cut -d, -f1-60 | head -60 > $out/ncu_full_gemm.raw.head.csv
 rm -f $out/gemm_full.ncu-rep $out/topk_full.ncu-rep
+fi   # FULL=0 skips the two --set full captures (the slow part)
 timeout 200 python tools/gemm_log.py > $out/gemm_log.txt 2>&1
 timeout 200 python tools/trace_step.py > $out/trace.txt 2>&1
 tail -3 $out/pytest_gpu.log; cut -c1-300 $out/bench.json; cut -c1-300 $out/bench_reference.json
