@@ -789,7 +789,13 @@ extern "C" int tt_topk_plan_make(int U, int N, int kprime, tt_topk_plan* plan) {
     const int stride = total_tiles / tiles;
     plan->sample_stride = stride;
     plan->sample_tiles = (total_tiles + stride - 1) / stride;
-    int rank = static_cast<int>(pc * plan->sample_tiles * kChunks + 0.5);
+    // The threshold is the rank-th largest sampled chunk maximum. With few expected hits (huge catalogs: the
+    // sample holds at most 1024 chunks, 3.2 expected hits at 10 M items) that rank statistic is noisy and
+    // one user in a thousand got a start threshold above its own K'-th best score (exact fallback: a full
+    // brute-force pass each). Two standard deviations of slack on small ranks costs candidates, not passes.
+    double rexp = pc * plan->sample_tiles * kChunks;
+    if (rexp < 16.0) rexp += 2.0 * sqrt(rexp);
+    int rank = static_cast<int>(rexp + 0.5);
     if (rank < 4) rank = 4;
     plan->sample_rank = rank;
     plan->smax_bytes = static_cast<int64_t>(plan->sample_tiles) * kChunks * u_pad * 4;

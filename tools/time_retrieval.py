@@ -31,6 +31,9 @@ def main():
         torch.cuda.synchronize()
         ts.append(a.elapsed_time(b))
     ts.sort()
+    _, _, n_fb = retrieval.retrieve_topk(users, index, 100, exact_fallback=True)   # certificate failures -> exact path
+    hit = (retrieval.retrieve_topk(users, index, 100, exact_fallback=False)[0][:, :10] == t[:, None].int()).any(1).float().mean().item()
+    print(f"users={users_n} items={items_n} fallback_users={n_fb} recall@10={hit:.3f}")
     print(f"knobs={ {k: v for k, v in os.environ.items() if k.startswith('TT_')} } ms_per_pass median={ts[len(ts)//2]:.3f} min={ts[0]:.3f}")
 
 
