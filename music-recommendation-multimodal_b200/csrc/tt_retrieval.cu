@@ -14,10 +14,10 @@
 // operands per 128-cycle MMA instead of the 16 KB two M=128,N=128 MMAs need (the single-CTA version
 // of this kernel sat at 60 % tensor-pipe activity whatever the epilogue or ring depth: shared-memory
 // operand bandwidth). Accumulators: 128 lanes x 256 columns per CTA, double-buffered (512 columns).
-// Eight epilogue warps per CTA read them with tcgen05.ld; a warp owns 32 user rows x 128 item
+// Sixteen epilogue warps per CTA read them with tcgen05.ld; a warp owns 32 user rows x 64 item
 // columns, each thread keeps its row's running threshold in a register and appends (score, item)
-// keys that beat it to a per-(range, column half, row) candidate list in global memory; a full list
-// is pruned to its K' best by the whole warp (bitwise binary search on the 64-bit keys with
+// keys that beat it to a per-(range, column quarter, row) candidate list in global memory; a full
+// list is pruned to its K' best by the whole warp (bitwise binary search on the 64-bit keys with
 // ballot/popc + compaction). The score matrix never exists.
 // Keys are totally ordered: (score descending, item index ascending) — the canonical order.
 //
@@ -121,8 +121,7 @@ __device__ __forceinline__ float chunk_max(const uint32_t (&r)[32]) {
 // showed the epilogue warps stalled on instruction fetch (stall_no_inst first, ahead of every data
 // dependency) whenever a chunk held a candidate — which, at ~1 candidate per 1 000 scores, is two
 // chunks out of three. Now the registers only feed a max tree (one 8-bit "which 4-score groups beat
-// the threshold" mask per lane); they are dead afterwards, so the NEXT chunk's tcgen05.ld is issued
-// into the same registers before the vote, and the rare groups that do hold a candidate are RE-READ
+// the threshold" mask per lane and chunk), and the rare groups that do hold a candidate are RE-READ
 // from TMEM four columns at a time (the TMEM address is a run-time value, a register index is not)
 // in a short warp-uniform loop.
 __device__ __forceinline__ uint32_t chunk_group_mask(const uint32_t (&r)[32], float thr_s) {
