@@ -379,8 +379,12 @@ def bench_retrieval(eng, rank, world, dev, peaks):
         dist.barrier()
     torch.cuda.synchronize()
     e0.record()
+    nfb = 0
     for _ in range(iters):
-        idx, score, nfb = retrieval.retrieve_topk(users, index, K, exact_fallback=False)
+        if world > 1:    # the whole sharded pass: per-shard candidates, all-gather, merge + certificate
+            idx, score = retrieval.sharded_topk(users, index, K)
+        else:
+            idx, score, nfb = retrieval.retrieve_topk(users, index, K, exact_fallback=False)
     e1.record()
     torch.cuda.synchronize()
     ms = torch.tensor([e0.elapsed_time(e1) / iters], device=dev)
@@ -454,7 +458,9 @@ def bench_retrieval(eng, rank, world, dev, peaks):
             "roofline_frac_tensor": flops / (ms.item() * 1e-3) / 1e12 / peak_tf,
             "config": {"workload": f"c3: {U} users x {N} items, top-{K}, Recall/NDCG@10/20/50/100, catalog sharded "
                                    f"over {world} GPU(s)",
-                       "users_per_s": "device-resident user embeddings: scoring + top-K + exact re-score (events)",
+                       "users_per_s": "device-resident user embeddings: scoring + top-K + exact re-score (events)"
+                                      + ("; sharded: per-shard candidate lists + bounds, all-gather, merge + certificate"
+                                         if world > 1 else ""),
                        "e2e_users_per_s": "host user embeddings -> device, retrieval, cross-shard merge, metrics -> host",
                        "e2e_users_per_s_incl_user_tower": f"host histories (L={Lh}) -> CUDA user tower (eval) -> same",
                        "kprime": 256},

@@ -279,7 +279,13 @@ int tt_infonce_loss(const float* lse_a, const float* pos_a, const float* lse_b, 
  *                     rounded once to fp32) -> canonical sort -> top K (global indices, -1 pad)
  *                     and flags[u] = 1 when the certificate "no non-candidate can reach the
  *                     exact top K" fails (eps bounds |bf16-path score - exact score|).
+ * tt_topk_finalize_bounded : sharded catalogs. Returns ALL K' candidates of this shard re-scored exactly
+ *                     ([U, K'], canonical order, -1 / -inf padded) and out_bound[u]: every item of the shard that
+ *                     is NOT in the list has exact score <= out_bound[u]. The merged top K over the shards
+ *                     (tt_topk_merge_lists) is exact for user u when its K-th score beats every shard's bound;
+ *                     a shard then only needs K' ~ (single-GPU K') / shards candidates.
  * tt_topk_merge     : top K of the union of G per-shard lists [G][U][K].
+ * tt_topk_merge_lists : the same with input lists of K_in entries and K_out outputs (-1 / -inf padded).
  * tt_exact_topk     : brute-force exact top K of one user (fallback for flagged users);
  *                     key_scratch = N * 8 bytes.
  * tt_rank_metrics   : per-row Recall@k / NDCG@k (:159-185); gain_table[r] = 1/log2(r+2) comes
@@ -301,8 +307,13 @@ int tt_topk_finalize(const tt_topk_plan* plan, const void* cand, const int32_t* 
                      const float* users_f32,
                      const float* items_f32, int item_base, int K, float eps, int32_t* out_idx, float* out_score,
                      int32_t* flags, void* stream);
+int tt_topk_finalize_bounded(const tt_topk_plan* plan, const void* cand, const int32_t* cand_cnt, const void* thr,
+                             const float* users_f32, const float* items_f32, int item_base, float eps,
+                             int32_t* out_idx, float* out_score, float* out_bound, int32_t* flags, void* stream);
 int tt_topk_merge(const float* scores, const int32_t* idx, int G, int U, int K, float* out_score, int32_t* out_idx,
                   void* stream);
+int tt_topk_merge_lists(const float* scores, const int32_t* idx, int G, int U, int K_in, int K_out, float* out_score,
+                        int32_t* out_idx, void* stream);
 int tt_exact_topk(const float* user_f32, const float* items_f32, int N, int item_base, int mask_item0, int K,
                   void* key_scratch, float* out_score, int32_t* out_idx, void* stream);
 int tt_rank_metrics(const int32_t* topk_idx, const int64_t* targets, int U, int K, const int32_t* k_list, int nk,

@@ -400,6 +400,7 @@ struct FinalizeParams {
   int* out_idx;         // [U, K] global item index, -1 padded
   float* out_score;     // [U, K]
   int* flags;           // [U] 1 = certificate failed (fallback needed)
+  float* bound;         // bounded mode (non-null): [U] every item of the shard NOT in the list has exact score <= bound
 };
 
 __device__ __forceinline__ int block_sum_int(int v, int* s_red) {
@@ -583,7 +584,13 @@ __global__ void __launch_bounds__(256) topk_finalize_kernel(const FinalizeParams
     p.out_idx[static_cast<size_t>(u) * p.K + k] = ok ? static_cast<int>(key_idx(s_keys[k])) : -1;
     p.out_score[static_cast<size_t>(u) * p.K + k] = ok ? key_score(s_keys[k]) : -INFINITY;
   }
-  if (tid == 0) {
+  if (tid == 0 && p.bound != nullptr) {
+    // Bounded mode (sharded catalogs): the list is every candidate with bf16-path key >= T, re-scored
+    // exactly; every other item of the shard has exact score <= score(T) + eps. The caller merges the
+    // shards' lists and checks that the merged K-th score beats every shard's bound.
+    p.bound[u] = overflow ? INFINITY : (T == 0ull ? -INFINITY : key_score(T) + p.eps);
+    p.flags[u] = overflow ? 1 : 0;
+  } else if (tid == 0) {
     // Certificate: every non-candidate has bf16-path key < T, hence exact score <= score(T) + eps.
     // If the exact K-th best beats that, no non-candidate can enter the top K.
     // T == 0 means every item of the shard is a candidate (tiny catalog, no threshold): exact.
@@ -601,13 +608,15 @@ __global__ void __launch_bounds__(256) topk_finalize_kernel(const FinalizeParams
 // top K of their union, canonical order. One block per user; G*K <= 1024.
 // --------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) topk_merge_kernel(const float* __restrict__ scores, const int* __restrict__ idx,
-                                                         int G, int U, int K, float* __restrict__ out_score,
+                                                         int G, int U, int K, int K_out, float* __restrict__ out_score,
                                                          int* __restrict__ out_idx) {
   pdl_launch_dependents();
   pdl_wait();
   extern __shared__ unsigned long long s_all[];  // G*K keys
+  __shared__ int s_written;
   const int u = blockIdx.x;
   const int n = G * K;
+  if (threadIdx.x == 0) s_written = 0;
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
     const int g = i / K, k = i % K;
     const size_t o = (static_cast<size_t>(g) * U + u) * K + k;
@@ -616,15 +625,24 @@ __global__ void __launch_bounds__(256) topk_merge_kernel(const float* __restrict
   }
   __syncthreads();
   // rank by counting: keys are unique (distinct items), n is small
+  int written = 0;
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
     const unsigned long long k = s_all[i];
     if (k == 0ull) continue;
     int rank = 0;
     for (int j = 0; j < n; ++j) rank += (s_all[j] > k);
-    if (rank < K) {
-      out_score[static_cast<size_t>(u) * K + rank] = key_score(k);
-      out_idx[static_cast<size_t>(u) * K + rank] = static_cast<int>(key_idx(k));
+    if (rank < K_out) {
+      out_score[static_cast<size_t>(u) * K_out + rank] = key_score(k);
+      out_idx[static_cast<size_t>(u) * K_out + rank] = static_cast<int>(key_idx(k));
+      ++written;
     }
+  }
+  if (written) atomicAdd(&s_written, written);
+  __syncthreads();
+  // fewer than K_out items in the union: pad the tail
+  for (int k = s_written + threadIdx.x; k < K_out; k += blockDim.x) {
+    out_score[static_cast<size_t>(u) * K_out + k] = -INFINITY;
+    out_idx[static_cast<size_t>(u) * K_out + k] = -1;
   }
 }
 
@@ -888,9 +906,29 @@ extern "C" int tt_score_topk(const void* users_bf16, const void* items_bf16, int
   return launch_score_topk(users_bf16, items_bf16, p, plan->N, stream);
 }
 
+static int finalize_impl(const tt_topk_plan* plan, const void* cand, const int32_t* cand_cnt, const void* thr,
+                         const float* users_f32, const float* items_f32, int item_base, int K, float eps,
+                         int32_t* out_idx, float* out_score, int32_t* flags, float* bound, void* stream_);
+
 extern "C" int tt_topk_finalize(const tt_topk_plan* plan, const void* cand, const int32_t* cand_cnt, const void* thr,
                                 const float* users_f32, const float* items_f32, int item_base, int K, float eps,
                                 int32_t* out_idx, float* out_score, int32_t* flags, void* stream_) {
+  return finalize_impl(plan, cand, cand_cnt, thr, users_f32, items_f32, item_base, K, eps, out_idx, out_score, flags,
+                       nullptr, stream_);
+}
+
+extern "C" int tt_topk_finalize_bounded(const tt_topk_plan* plan, const void* cand, const int32_t* cand_cnt,
+                                        const void* thr, const float* users_f32, const float* items_f32, int item_base,
+                                        float eps, int32_t* out_idx, float* out_score, float* out_bound,
+                                        int32_t* flags, void* stream_) {
+  TT_REQUIRE(plan && out_bound, "tt_topk_finalize_bounded: null pointer");
+  return finalize_impl(plan, cand, cand_cnt, thr, users_f32, items_f32, item_base, plan->kprime, eps, out_idx, out_score,
+                       flags, out_bound, stream_);
+}
+
+static int finalize_impl(const tt_topk_plan* plan, const void* cand, const int32_t* cand_cnt, const void* thr,
+                         const float* users_f32, const float* items_f32, int item_base, int K, float eps,
+                         int32_t* out_idx, float* out_score, int32_t* flags, float* bound, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   TT_REQUIRE(plan && cand && cand_cnt && thr && users_f32 && items_f32 && out_idx && out_score && flags,
              "tt_topk_finalize: null pointer");
@@ -902,7 +940,7 @@ extern "C" int tt_topk_finalize(const tt_topk_plan* plan, const void* cand, cons
   p.u_pad = plan->n_ut * kUT; p.kprime = plan->kprime; p.K = K;
   p.cand = static_cast<const unsigned long long*>(cand);
   p.cand_cnt = cand_cnt; p.thr = static_cast<const unsigned long long*>(thr); p.users = users_f32; p.items = items_f32; p.eps = eps;
-  p.out_idx = out_idx; p.out_score = out_score; p.flags = flags;
+  p.out_idx = out_idx; p.out_score = out_score; p.flags = flags; p.bound = bound;
   TT_CHECK_CUDA(launch_k(topk_finalize_kernel, dim3(plan->U), dim3(256), 0, stream, p));
   TT_LAUNCH_CHECK();
   return TT_OK;
@@ -910,10 +948,16 @@ extern "C" int tt_topk_finalize(const tt_topk_plan* plan, const void* cand, cons
 
 extern "C" int tt_topk_merge(const float* scores, const int32_t* idx, int G, int U, int K, float* out_score,
                              int32_t* out_idx, void* stream_) {
+  return tt_topk_merge_lists(scores, idx, G, U, K, K, out_score, out_idx, stream_);
+}
+
+extern "C" int tt_topk_merge_lists(const float* scores, const int32_t* idx, int G, int U, int K_in, int K_out,
+                                   float* out_score, int32_t* out_idx, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  TT_REQUIRE(scores && idx && out_score && out_idx && G > 0 && U > 0 && K > 0, "tt_topk_merge: bad arguments");
-  TT_REQUIRE(G * K <= 4096, "tt_topk_merge: G*K = %d too large", G * K);
-  TT_CHECK_CUDA(launch_k(topk_merge_kernel, dim3(U), dim3(256), static_cast<size_t>(G) * K * 8, stream, scores, idx, G, U, K, out_score, out_idx));
+  TT_REQUIRE(scores && idx && out_score && out_idx && G > 0 && U > 0 && K_in > 0 && K_out > 0,
+             "tt_topk_merge_lists: bad arguments");
+  TT_REQUIRE(G * K_in <= 4096, "tt_topk_merge_lists: G*K_in = %d too large", G * K_in);
+  TT_CHECK_CUDA(launch_k(topk_merge_kernel, dim3(U), dim3(256), static_cast<size_t>(G) * K_in * 8, stream, scores, idx, G, U, K_in, K_out, out_score, out_idx));
   TT_LAUNCH_CHECK();
   return TT_OK;
 }

@@ -5,6 +5,7 @@ order, Recall@K / NDCG@K — the device side of the reference's ``calculate_metr
 from __future__ import annotations
 
 import ctypes
+import os
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
@@ -72,19 +73,7 @@ def retrieve_topk(user_emb: torch.Tensor, index: CatalogIndex, K: int, kprime: i
     user_emb = user_emb.contiguous()
     U = user_emb.shape[0]
     kprime = max(kprime, K)
-    plan = index.plan(U, kprime)
-    sc = index._scratch[(U, kprime)]
-    ops.cast_bf16(user_emb.view(-1), sc["users_bf16"].view(-1))
-    # rigorous bound on |u^.e^ - u.e| (Cauchy-Schwarz on the bf16 rounding errors) + fp32 accumulation slack.
-    # Its host read-back happens BEFORE the scoring pass is queued, so scoring and finalize run back to back.
-    u16 = sc["users_bf16"].float()
-    du = (u16 - user_emb).norm(dim=1).max()
-    nu = user_emb.norm(dim=1).max()
-    eps = float((du * index.ne_max + nu * index.de_max + nu * index.ne_max * 2.0 ** -18).item())
-    check(lib().tt_score_topk(sc["users_bf16"].data_ptr(), index.table_bf16.data_ptr(), index.item_base,
-                              ctypes.byref(plan), sc["cand"].data_ptr(), sc["cnt"].data_ptr(), sc["thr"].data_ptr(),
-                              None if sc["smax"] is None else sc["smax"].data_ptr(), int(mask_item0), _stream()),
-          "tt_score_topk")
+    plan, sc, eps = _score_pass(user_emb, index, kprime, mask_item0)
     dev = user_emb.device
     out_idx = torch.empty(U, K, device=dev, dtype=torch.int32)
     out_score = torch.empty(U, K, device=dev, dtype=torch.float32)
@@ -105,6 +94,117 @@ def retrieve_topk(user_emb: torch.Tensor, index: CatalogIndex, K: int, kprime: i
                                           index.item_base, int(mask_item0), K, sc["keys"].data_ptr(),
                                           out_score[u].data_ptr(), out_idx[u].data_ptr(), _stream()), "tt_exact_topk")
     return out_idx, out_score, n_fallback
+
+
+def _score_pass(user_emb: torch.Tensor, index: "CatalogIndex", kprime: int, mask_item0: bool):
+    """bf16 scoring + streaming candidate selection of this shard (tt_score_topk); returns (plan, scratch, eps)."""
+    U = user_emb.shape[0]
+    plan = index.plan(U, kprime)
+    sc = index._scratch[(U, kprime)]
+    ops.cast_bf16(user_emb.view(-1), sc["users_bf16"].view(-1))
+    # rigorous bound on |u^.e^ - u.e| (Cauchy-Schwarz on the bf16 rounding errors) + fp32 accumulation slack.
+    # Its host read-back happens BEFORE the scoring pass is queued, so scoring and finalize run back to back.
+    u16 = sc["users_bf16"].float()
+    du = (u16 - user_emb).norm(dim=1).max()
+    nu = user_emb.norm(dim=1).max()
+    eps = float((du * index.ne_max + nu * index.de_max + nu * index.ne_max * 2.0 ** -18).item())
+    check(lib().tt_score_topk(sc["users_bf16"].data_ptr(), index.table_bf16.data_ptr(), index.item_base,
+                              ctypes.byref(plan), sc["cand"].data_ptr(), sc["cnt"].data_ptr(), sc["thr"].data_ptr(),
+                              None if sc["smax"] is None else sc["smax"].data_ptr(), int(mask_item0), _stream()),
+          "tt_score_topk")
+    return plan, sc, eps
+
+
+def retrieve_candidates(user_emb: torch.Tensor, index: "CatalogIndex", kprime: int, mask_item0: bool = True):
+    """Sharded catalogs: ALL ``kprime`` candidates of this shard per user, re-scored exactly.
+
+    Returns (idx int32 (U, kprime) global ids, -1 padded; score fp32 (U, kprime); bound fp32 (U,): every item of
+    the shard that is not in the list has exact score <= bound; overflow int32 (U,): 1 = tie flood, use the exact
+    path). With G shards a shard needs about 1/G of the single-GPU candidate budget (`shard_kprime`)."""
+    assert user_emb.is_cuda and user_emb.dtype == torch.float32 and user_emb.shape[1] == 256
+    user_emb = user_emb.contiguous()
+    U = user_emb.shape[0]
+    plan, sc, eps = _score_pass(user_emb, index, kprime, mask_item0)
+    dev = user_emb.device
+    out_idx = torch.empty(U, kprime, device=dev, dtype=torch.int32)
+    out_score = torch.empty(U, kprime, device=dev, dtype=torch.float32)
+    bound = torch.empty(U, device=dev, dtype=torch.float32)
+    flags = torch.empty(U, device=dev, dtype=torch.int32)
+    check(lib().tt_topk_finalize_bounded(ctypes.byref(plan), sc["cand"].data_ptr(), sc["cnt"].data_ptr(),
+                                         sc["thr"].data_ptr(), user_emb.data_ptr(), index.table.data_ptr(),
+                                         index.item_base, eps, out_idx.data_ptr(), out_score.data_ptr(),
+                                         bound.data_ptr(), flags.data_ptr(), _stream()), "tt_topk_finalize_bounded")
+    return out_idx, out_score, bound, flags
+
+
+def shard_kprime(kprime: int, shards: int) -> int:
+    """Candidates per user and shard: 1.5x the even share of the single-GPU budget plus 16 (the number of a
+    user's global top-K' items that fall into one shard is binomial), a multiple of 8 in [48, kprime]."""
+    if shards <= 1:
+        return kprime
+    k = int(1.5 * kprime / shards + 16 + 7) // 8 * 8
+    return max(48, min(kprime, k))
+
+
+def merge_bounded(scores: torch.Tensor, idx: torch.Tensor, bounds: torch.Tensor, K: int):
+    """Merge per-shard candidate lists [G, U, K'] (exact scores) into the global top K and certify it:
+    the result for user u is exact when its K-th score beats every shard's bound (an item missing from
+    shard s's list scores at most bounds[s, u]). Returns (idx (U, K), score (U, K), uncertified bool (U,))."""
+    G, U, Kin = scores.shape
+    scores, idx = scores.contiguous(), idx.contiguous()
+    out_s = torch.empty(U, K, device=scores.device, dtype=torch.float32)
+    out_i = torch.empty(U, K, device=scores.device, dtype=torch.int32)
+    check(lib().tt_topk_merge_lists(scores.data_ptr(), idx.data_ptr(), G, U, Kin, K, out_s.data_ptr(),
+                                    out_i.data_ptr(), _stream()), "tt_topk_merge_lists")
+    bmax = bounds.max(dim=0).values
+    # fewer than K items in the union is fine when every shard listed ALL its items (bound = -inf)
+    ok = torch.where(out_i[:, K - 1] >= 0, out_s[:, K - 1] > bmax, torch.isneginf(bmax))
+    return out_i, out_s, ~ok
+
+
+def sharded_topk(user_emb: torch.Tensor, index: "CatalogIndex", K: int, kprime: int = 256, group=None,
+                 bounded: Optional[bool] = None):
+    """Exact global top K over a catalog sharded across the ranks of ``group`` (every rank gets the result).
+
+    bounded protocol (default): per-shard candidate lists of `shard_kprime` entries + completeness bounds,
+    one all-gather, merge + certificate; users whose certificate fails (and only those) go through the
+    per-shard exact top-K protocol. ``bounded=False`` always uses the latter."""
+    import torch.distributed as dist
+    ws = dist.get_world_size(group)
+    if bounded is None:
+        bounded = os.environ.get("TT_SHARD_BOUNDED", "1") != "0"
+
+    def per_shard_exact(users):
+        i, s, _ = retrieve_topk(users, index, K, kprime)
+        all_s = torch.empty(ws, *s.shape, device=s.device, dtype=s.dtype)
+        all_i = torch.empty(ws, *i.shape, device=i.device, dtype=i.dtype)
+        dist.all_gather_into_tensor(all_s, s, group=group)
+        dist.all_gather_into_tensor(all_i, i, group=group)
+        return merge_topk(all_s, all_i)
+
+    if not bounded or K > ws * shard_kprime(kprime, ws):
+        return per_shard_exact(user_emb)
+    kps = shard_kprime(kprime, ws)
+    i, s, b, f = retrieve_candidates(user_emb, index, kps)
+    U = user_emb.shape[0]
+    # one packed all-gather: [U, kps] scores | [U, kps] ids | bound | overflow flag, as int32 words
+    pack = torch.empty(U, 2 * kps + 2, device=s.device, dtype=torch.int32)
+    pack[:, :kps] = s.view(torch.int32)
+    pack[:, kps:2 * kps] = i
+    pack[:, 2 * kps] = b.view(torch.int32)
+    pack[:, 2 * kps + 1] = f
+    allp = torch.empty(ws, U, 2 * kps + 2, device=s.device, dtype=torch.int32)
+    dist.all_gather_into_tensor(allp, pack, group=group)
+    all_s = allp[:, :, :kps].contiguous().view(torch.float32)
+    all_i = allp[:, :, kps:2 * kps].contiguous()
+    all_b = allp[:, :, 2 * kps].contiguous().view(torch.float32)
+    out_i, out_s, bad = merge_bounded(all_s, all_i, all_b, K)
+    bad |= allp[:, :, 2 * kps + 1].any(dim=0)
+    if bool(bad.any().item()):            # identical on every rank: the inputs of the test were all-gathered
+        sel = torch.nonzero(bad).flatten()
+        fi, fs = per_shard_exact(user_emb[sel].contiguous())
+        out_i[sel], out_s[sel] = fi, fs
+    return out_i, out_s
 
 
 def merge_topk(scores: torch.Tensor, idx: torch.Tensor):
@@ -145,14 +245,10 @@ def metrics_from_embeddings(user_emb: torch.Tensor, targets: torch.Tensor, index
     all-gathered and merged (result independent of the number of shards)."""
     import torch.distributed as dist
     K = max(k_list)
-    idx, score, _ = retrieve_topk(user_emb, index, K, kprime)
     if group is not None or (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
-        ws = dist.get_world_size(group)
-        all_s = torch.empty(ws, *score.shape, device=score.device, dtype=score.dtype)
-        all_i = torch.empty(ws, *idx.shape, device=idx.device, dtype=idx.dtype)
-        dist.all_gather_into_tensor(all_s, score, group=group)
-        dist.all_gather_into_tensor(all_i, idx, group=group)
-        idx, score = merge_topk(all_s, all_i)
+        idx, score = sharded_topk(user_emb, index, K, kprime, group)
+    else:
+        idx, score, _ = retrieve_topk(user_emb, index, K, kprime)
     recall, ndcg = rank_metrics(idx, targets.to(idx.device), k_list)
     r, n = recall.cpu(), ndcg.cpu()     # the mean is taken on the host exactly like the reference (:188-190)
     out = {}

@@ -85,6 +85,59 @@ def test_sharded_equals_unsharded_and_merge():
     assert torch.equal(mi.cpu(), gold["topk_idx"])
 
 
+def _bounded_shards(table, users, cuts, kps, K):
+    from mrm_b200 import retrieval
+    li, ls, lb, lf = [], [], [], []
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        shard = retrieval.CatalogIndex(table, shard=(a, b - a))
+        i, s, bd, f = retrieval.retrieve_candidates(users, shard, kps)
+        li.append(i); ls.append(s); lb.append(bd); lf.append(f)
+    mi, ms, bad = retrieval.merge_bounded(torch.stack(ls), torch.stack(li), torch.stack(lb), K)
+    bad = bad | torch.stack(lf).any(dim=0)
+    torch.cuda.synchronize()
+    return mi, ms, bad
+
+
+def test_bounded_shard_protocol_on_a_large_catalog():
+    """What the ranks of a sharded catalog exchange (retrieval.sharded_topk): per-shard candidate lists of
+    shard_kprime entries + completeness bounds, merged and certified. Certified users must equal the unsharded
+    exact top-K bit for bit (indices and scores); nearly all users must certify with 1/G-sized lists."""
+    from mrm_b200 import retrieval
+    g = torch.Generator(device="cuda").manual_seed(5)
+    N, U, K = 200_000, 1000, 100
+    table = torch.nn.functional.normalize(torch.randn(N + 1, 256, device="cuda", generator=g), dim=1)
+    table[0] = 0
+    t = torch.randint(1, N, (U,), device="cuda", generator=g)
+    users = torch.nn.functional.normalize(table[t] + 3.3 / 16 * torch.randn(U, 256, device="cuda", generator=g), dim=1)
+    full_i, full_s, nfb = retrieval.retrieve_topk(users, retrieval.CatalogIndex(table), K)
+    for G in (2, 8):
+        rows = (N + 1 + G - 1) // G
+        cuts = [min(N + 1, r * rows) for r in range(G + 1)]
+        kps = retrieval.shard_kprime(256, G)
+        mi, ms, bad = _bounded_shards(table.cpu(), users, cuts, kps, K)
+        ok = ~bad
+        assert ok.float().mean().item() > 0.97, f"G={G}: only {ok.float().mean().item():.3f} of the users certified"
+        assert torch.equal(mi[ok], full_i[ok]) and torch.equal(ms[ok], full_s[ok]), f"G={G}"
+
+
+def test_bounded_shard_protocol_with_ties_and_tiny_shards():
+    """Coarse grid (thousands of exact ties) split into 3 ragged shards: whatever certifies must be bit-exact,
+    including the canonical tie order; shards smaller than the candidate budget list everything (bound = -inf)."""
+    from mrm_b200 import retrieval
+    gold, table, users, targets = _fixture("retrieval_grid_coarse.pt")
+    K = 100
+    V = table.shape[0]
+    mi, ms, bad = _bounded_shards(table, users.cuda(), [0, 1700, 3333, V], retrieval.shard_kprime(256, 3), K)
+    ok = ~bad
+    assert torch.equal(mi[ok].cpu(), gold["topk_idx"][ok.cpu()])
+    # a catalog of 150 items in 3 shards of 50: every shard lists all of its items, everything certifies
+    small = table[:151]
+    full_i, full_s, _ = retrieval.retrieve_topk(users.cuda(), retrieval.CatalogIndex(small), K)
+    mi, ms, bad = _bounded_shards(small, users.cuda(), [0, 51, 101, 151], 64, K)
+    assert not bad.any()
+    assert torch.equal(mi, full_i) and torch.equal(ms, full_s)
+
+
 def test_exact_fallback_path_agrees():
     from mrm_b200 import retrieval
     from mrm_b200._lib import check, lib

@@ -19,14 +19,21 @@ def main():
     index = retrieval.CatalogIndex(table, device=dev)
     t = torch.randint(1, items_n, (users_n,), device=dev, generator=g)
     users = torch.nn.functional.normalize(table[t] + 3.3 / 16 * torch.randn(users_n, 256, device=dev, generator=g), dim=1)
+    kps = int(os.environ.get("SHARD_KPRIME", 0))     # > 0: time the per-shard candidate pass of the sharded protocol
+
+    def one_pass():
+        if kps:
+            return retrieval.retrieve_candidates(users, index, kps)
+        return retrieval.retrieve_topk(users, index, 100, exact_fallback=False)
+
     for _ in range(3):
-        retrieval.retrieve_topk(users, index, 100, exact_fallback=False)
+        one_pass()
     torch.cuda.synchronize()
     ts = []
     for _ in range(7):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        retrieval.retrieve_topk(users, index, 100, exact_fallback=False)
+        one_pass()
         b.record()
         torch.cuda.synchronize()
         ts.append(a.elapsed_time(b))
