@@ -166,13 +166,17 @@ def sharded_topk(user_emb: torch.Tensor, index: "CatalogIndex", K: int, kprime: 
                  bounded: Optional[bool] = None):
     """Exact global top K over a catalog sharded across the ranks of ``group`` (every rank gets the result).
 
-    bounded protocol (default): per-shard candidate lists of `shard_kprime` entries + completeness bounds,
-    one all-gather, merge + certificate; users whose certificate fails (and only those) go through the
-    per-shard exact top-K protocol. ``bounded=False`` always uses the latter."""
+    bounded protocol (default from 4 shards): per-shard candidate lists of `shard_kprime` entries +
+    completeness bounds, one all-gather, merge + certificate; users whose certificate fails (and only those) go
+    through the per-shard exact top-K protocol. ``bounded=False`` (default below 4 shards) always uses the latter."""
     import torch.distributed as dist
     ws = dist.get_world_size(group)
     if bounded is None:
-        bounded = os.environ.get("TT_SHARD_BOUNDED", "1") != "0"
+        # Measured (tools/dist_retrieval_check.py, 2 GPUs over NCCL, 10 k users x 1 M items): with 2 shards the
+        # lists are nearly as long as the single-GPU budget (208 of 256) and the bounded pass is the slower one
+        # (3.27 vs 3.06 ms); a 1/8 shard takes 1.14 ms with 64-entry lists against 1.76 ms with K' = 256.
+        env = os.environ.get("TT_SHARD_BOUNDED", "")
+        bounded = (ws >= 4) if env == "" else (env != "0")
 
     def per_shard_exact(users):
         i, s, _ = retrieve_topk(users, index, K, kprime)
