@@ -26,6 +26,26 @@ def merge_canonical(scores: torch.Tensor, idx: torch.Tensor):
     return i.gather(1, order)[:, :K].to(idx.dtype), s.gather(1, order)[:, :K]
 
 
+def merge_bounded_reference(scores: torch.Tensor, idx: torch.Tensor, bounds: torch.Tensor, K: int):
+    """Reference semantics of the bounded shard protocol (retrieval.sharded_topk / merge_bounded on the device):
+    lists [G, U, K'] hold a shard's best K' items with exact scores (-1 / -inf padded), bounds [G, U] say "no
+    item of shard g outside its list scores above bounds[g, u]". Returns (idx (U, K), score (U, K), certified
+    bool (U,)): the top K of the union is the exact global top K whenever its K-th score beats every bound —
+    then every item that could enter the top K is in some list."""
+    G, U, Kin = scores.shape
+    s = scores.permute(1, 0, 2).reshape(U, G * Kin).clone()
+    i = idx.permute(1, 0, 2).reshape(U, G * Kin).long()
+    s[i < 0] = float("-inf")
+    big = torch.iinfo(torch.int64).max
+    order = torch.argsort(torch.where(i < 0, torch.full_like(i, big), i), dim=1, stable=True)
+    s, i = s.gather(1, order), i.gather(1, order)
+    order = torch.argsort(s, dim=1, descending=True, stable=True)
+    s, i = s.gather(1, order)[:, :K], i.gather(1, order)[:, :K]
+    bmax = bounds.max(dim=0).values
+    certified = torch.where(i[:, K - 1] >= 0, s[:, K - 1] > bmax, torch.isneginf(bmax))
+    return i.to(idx.dtype), s, certified
+
+
 class RowShardedTable:
     """Row-sharded item-ID embedding table for catalogs that do not fit replicated.
 

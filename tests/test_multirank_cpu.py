@@ -13,7 +13,7 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 from mrm_b200 import synthetic
-from mrm_b200.sharding import merge_canonical, shard_bounds
+from mrm_b200.sharding import merge_bounded_reference, merge_canonical, shard_bounds
 from oracle import two_tower_oracle as oracle
 
 
@@ -63,6 +63,58 @@ def _retrieval_worker(rank, world, K):
 
 def test_sharded_retrieval_protocol_world2():
     _run(_retrieval_worker, 2, 50)
+
+
+def _bounded_retrieval_worker(rank, world, K, kps, noise, eps):
+    """The bounded shard protocol (retrieval.sharded_topk from 4 shards on): a shard ships its kps best items
+    with exact scores plus a completeness bound; the merged top K is exact wherever it is certified. The shard's
+    selection is done on PERTURBED scores (standing in for the bf16 scoring pass, |error| <= eps), the shipped
+    scores are exact — as on the device."""
+    torch.set_num_threads(1)
+    table = synthetic.make_catalog(2999, 256, seed=5)
+    users, _ = synthetic.make_queries(table, 64, seed=6, noise=noise)
+    first, rows = shard_bounds(table.shape[0], world, rank)
+    exact = (users.double() @ table[first:first + rows].double().t()).float()
+    if first == 0:
+        exact[:, 0] = float("-inf")
+    g = torch.Generator().manual_seed(100 + rank)
+    approx = exact + (torch.rand(exact.shape, generator=g) * 2 - 1) * eps      # the selection sees these
+    n = min(kps, rows)
+    sel_v, sel_i = torch.topk(approx, n, dim=1)
+    # completeness bound: everything NOT selected has approx score <= the smallest selected one, hence
+    # exact score <= that + eps; a shard that lists all of its items has nothing outside the list
+    bound = sel_v[:, -1] + eps if n < rows else torch.full((users.shape[0],), float("-inf"))
+    lv = torch.full((users.shape[0], kps), float("-inf"))
+    li = torch.full((users.shape[0], kps), -1, dtype=torch.int32)
+    ev = exact.gather(1, sel_i)
+    order = torch.argsort(ev, dim=1, descending=True, stable=True)
+    lv[:, :n] = ev.gather(1, order)
+    li[:, :n] = (sel_i.gather(1, order) + first).to(torch.int32)
+    all_v = [torch.empty_like(lv) for _ in range(world)]
+    all_i = [torch.empty_like(li) for _ in range(world)]
+    all_b = [torch.empty_like(bound) for _ in range(world)]
+    dist.all_gather(all_v, lv)
+    dist.all_gather(all_i, li)
+    dist.all_gather(all_b, bound)
+    mi, mv, ok = merge_bounded_reference(torch.stack(all_v), torch.stack(all_i), torch.stack(all_b), K)
+    rv, ri = oracle.canonical_topk(oracle.retrieval_scores(users.double(), table.double()).float(), K)
+    assert ok.float().mean() > 0.5, f"rank {rank}: only {ok.float().mean():.2f} certified — the test would prove nothing"
+    assert torch.equal(mi.long()[ok], ri[ok]), f"rank {rank}: a certified list differs from the unsharded top-K"
+    assert torch.equal(mv[ok], rv[ok])
+    # every rank holds the same merged result and the same certificate (the fallback decision is collective)
+    flat = torch.cat([mi.float().flatten(), ok.float()])
+    ref = flat.clone()
+    dist.broadcast(ref, 0)
+    assert torch.equal(flat, ref)
+
+
+def test_bounded_shard_protocol_world2():
+    _run(_bounded_retrieval_worker, 2, 50, 96, 0.35, 1e-3)
+
+
+def test_bounded_shard_protocol_world3_short_lists():
+    # lists of 24 for a top-50: certificates fail for part of the users — whatever certifies must still be exact
+    _run(_bounded_retrieval_worker, 3, 50, 24, 0.35, 1e-3)
 
 
 def test_shard_bounds_cover_catalog():
