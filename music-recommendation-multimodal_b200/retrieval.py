@@ -206,8 +206,12 @@ def sharded_topk(user_emb: torch.Tensor, index: "CatalogIndex", K: int, kprime: 
     bad |= allp[:, :, 2 * kps + 1].any(dim=0)
     if bool(bad.any().item()):            # identical on every rank: the inputs of the test were all-gathered
         sel = torch.nonzero(bad).flatten()
-        fi, fs = per_shard_exact(user_emb[sel].contiguous())
-        out_i[sel], out_s[sel] = fi, fs
+        n = sel.numel()
+        # scratch buffers are cached per user count: pad to a multiple of 256 (repeating the first user) so that
+        # a long evaluation with a few uncertified users per batch does not accumulate one scratch set per count
+        padded = torch.cat([sel, sel[:1].expand((-n) % 256)])
+        fi, fs = per_shard_exact(user_emb[padded].contiguous())
+        out_i[sel], out_s[sel] = fi[:n], fs[:n]
     return out_i, out_s
 
 
