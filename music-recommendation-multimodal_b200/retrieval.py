@@ -180,11 +180,13 @@ def sharded_topk(user_emb: torch.Tensor, index: "CatalogIndex", K: int, kprime: 
 
     def per_shard_exact(users):
         i, s, _ = retrieve_topk(users, index, K, kprime)
-        all_s = torch.empty(ws, *s.shape, device=s.device, dtype=s.dtype)
-        all_i = torch.empty(ws, *i.shape, device=i.device, dtype=i.dtype)
-        dist.all_gather_into_tensor(all_s, s, group=group)
-        dist.all_gather_into_tensor(all_i, i, group=group)
-        return merge_topk(all_s, all_i)
+        n = s.shape[0]
+        # outputs are allocated in the concatenated form (ws * n, K): the stacked form is NCCL-only
+        all_s = torch.empty(ws * n, K, device=s.device, dtype=s.dtype)
+        all_i = torch.empty(ws * n, K, device=i.device, dtype=i.dtype)
+        dist.all_gather_into_tensor(all_s, s.contiguous(), group=group)
+        dist.all_gather_into_tensor(all_i, i.contiguous(), group=group)
+        return merge_topk(all_s.view(ws, n, K), all_i.view(ws, n, K))
 
     if not bounded or K > ws * shard_kprime(kprime, ws):
         return per_shard_exact(user_emb)
@@ -197,8 +199,9 @@ def sharded_topk(user_emb: torch.Tensor, index: "CatalogIndex", K: int, kprime: 
     pack[:, kps:2 * kps] = i
     pack[:, 2 * kps] = b.view(torch.int32)
     pack[:, 2 * kps + 1] = f
-    allp = torch.empty(ws, U, 2 * kps + 2, device=s.device, dtype=torch.int32)
+    allp = torch.empty(ws * U, 2 * kps + 2, device=s.device, dtype=torch.int32)
     dist.all_gather_into_tensor(allp, pack, group=group)
+    allp = allp.view(ws, U, 2 * kps + 2)
     all_s = allp[:, :, :kps].contiguous().view(torch.float32)
     all_i = allp[:, :, kps:2 * kps].contiguous()
     all_b = allp[:, :, 2 * kps].contiguous().view(torch.float32)

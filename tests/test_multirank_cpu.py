@@ -117,6 +117,90 @@ def test_bounded_shard_protocol_world3_short_lists():
     _run(_bounded_retrieval_worker, 3, 50, 24, 0.35, 1e-3)
 
 
+class _CpuShard:
+    """Stand-in for retrieval.CatalogIndex holding a CPU shard (the device kernels are replaced below)."""
+
+    def __init__(self, table, first, rows):
+        self.table, self.item_base = table[first:first + rows], first
+
+
+def _sharded_topk_plumbing_worker(rank, world, K, kps):
+    """retrieval.sharded_topk itself (packing, the all-gathers, certificate, collective fallback on the padded
+    subset) with the four device entry points replaced by their CPU reference semantics."""
+    torch.set_num_threads(1)
+    from mrm_b200 import retrieval, sharding
+    table = synthetic.make_catalog(2999, 256, seed=5)
+    users, _ = synthetic.make_queries(table, 70, seed=6, noise=0.35)
+    first, rows = shard_bounds(table.shape[0], world, rank)
+    index = _CpuShard(table, first, rows)
+
+    def shard_scores(u, ix):
+        sc = (u.double() @ ix.table.double().t()).float()
+        if ix.item_base == 0:
+            sc[:, 0] = float("-inf")
+        return sc
+
+    def retrieve_topk(u, ix, k, kprime=256, mask_item0=True, exact_fallback=True):
+        v, i = oracle.canonical_topk(shard_scores(u, ix), k)
+        return (i + ix.item_base).to(torch.int32), v, 0
+
+    def retrieve_candidates(u, ix, kprime, mask_item0=True):
+        sc = shard_scores(u, ix)
+        n = min(kprime, sc.shape[1])
+        v, i = oracle.canonical_topk(sc, n)
+        out_v = torch.full((u.shape[0], kprime), float("-inf"))
+        out_i = torch.full((u.shape[0], kprime), -1, dtype=torch.int32)
+        out_v[:, :n], out_i[:, :n] = v, (i + ix.item_base).to(torch.int32)
+        bound = v[:, -1].clone() if n < sc.shape[1] else torch.full((u.shape[0],), float("-inf"))
+        return out_i, out_v, bound, torch.zeros(u.shape[0], dtype=torch.int32)
+
+    def merge_bounded(sc, ix, bd, k):
+        i, v, ok = sharding.merge_bounded_reference(sc, ix, bd, k)
+        return i, v, ~ok
+
+    calls = {"fallback_users": 0}
+
+    def merge_topk(sc, ix):
+        calls["fallback_users"] = sc.shape[1]
+        return merge_canonical(sc, ix)
+
+    saved = {n: getattr(retrieval, n) for n in ("retrieve_topk", "retrieve_candidates", "merge_bounded", "merge_topk",
+                                                "shard_kprime")}
+    try:
+        retrieval.retrieve_topk, retrieval.retrieve_candidates = retrieve_topk, retrieve_candidates
+        retrieval.merge_bounded, retrieval.merge_topk = merge_bounded, merge_topk
+        retrieval.shard_kprime = lambda kprime, shards: kps
+        mi, mv = retrieval.sharded_topk(users, index, K, bounded=True)
+        fallback_users = calls["fallback_users"]
+        ei, ev = retrieval.sharded_topk(users, index, K, bounded=False)
+    finally:
+        for n, f in saved.items():
+            setattr(retrieval, n, f)
+    rv, ri = oracle.canonical_topk(oracle.retrieval_scores(users.double(), table.double()).float(), K)
+    assert torch.equal(mi.long(), ri) and torch.equal(mv, rv), f"rank {rank}: bounded protocol"
+    assert torch.equal(ei.long(), ri) and torch.equal(ev, rv), f"rank {rank}: per-shard exact protocol"
+    return fallback_users
+
+
+def _plumbing_short_lists(rank, world):
+    # lists of 26 for a top-50 over 2 shards: 52 candidates, the 50th of the union almost never beats both
+    # shards' bounds -> the uncertified users go through the collective fallback, padded to 256 users
+    n = _sharded_topk_plumbing_worker(rank, world, 50, 26)
+    assert n == 256, n
+
+
+def _plumbing_long_lists(rank, world):
+    _sharded_topk_plumbing_worker(rank, world, 50, 64)
+
+
+def test_sharded_topk_plumbing_world2_all_fallback():
+    _run(_plumbing_short_lists, 2)
+
+
+def test_sharded_topk_plumbing_world3():
+    _run(_plumbing_long_lists, 3)
+
+
 def test_shard_bounds_cover_catalog():
     for V in (1, 7, 1000, 1_000_001):
         for world in (1, 2, 3, 8):
