@@ -459,7 +459,8 @@ def bench_retrieval(eng, rank, world, dev, peaks):
             "config": {"workload": f"c3: {U} users x {N} items, top-{K}, Recall/NDCG@10/20/50/100, catalog sharded "
                                    f"over {world} GPU(s)",
                        "users_per_s": "device-resident user embeddings: scoring + top-K + exact re-score (events)"
-                                      + ("; sharded: per-shard candidate lists + bounds, all-gather, merge + certificate"
+                                      + ("; sharded: per-shard pass, all-gather, merge (retrieval.sharded_topk: candidate "
+                                         "lists + bounds + certificate from 4 shards, per-shard exact top-K below)"
                                          if world > 1 else ""),
                        "e2e_users_per_s": "host user embeddings -> device, retrieval, cross-shard merge, metrics -> host",
                        "e2e_users_per_s_incl_user_tower": f"host histories (L={Lh}) -> CUDA user tower (eval) -> same",
