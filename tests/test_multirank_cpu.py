@@ -201,6 +201,21 @@ def test_sharded_topk_plumbing_world3():
     _run(_plumbing_long_lists, 3)
 
 
+def test_shard_kprime_budget():
+    """Per-shard candidate budget of the bounded protocol: the whole budget on one shard, about 1.5x the even
+    share (+16) on several, a multiple of 8 inside [48, K'], and enough lists to hold a top-100 from 2 shards on."""
+    from mrm_b200.retrieval import shard_kprime
+    assert shard_kprime(256, 1) == 256
+    got = {g: shard_kprime(256, g) for g in (2, 3, 4, 8, 16, 64)}
+    assert got[2] == 208 and got[4] == 112 and got[8] == 64, got
+    for g, k in got.items():
+        assert k % 8 == 0 and 48 <= k <= 256
+        assert k >= min(256, 1.5 * 256 / g)
+        if g >= 2:
+            assert g * k >= 100
+    assert all(got[a] >= got[b] for a, b in zip((2, 3, 4, 8, 16), (3, 4, 8, 16, 64)))
+
+
 def test_shard_bounds_cover_catalog():
     for V in (1, 7, 1000, 1_000_001):
         for world in (1, 2, 3, 8):
