@@ -645,7 +645,7 @@ class TwoTowerEngine:
             ffn_scale = 1.0 / (1.0 - dp) if dp > 0 else 1.0
             # linear2: dW2 = dy^T f ; dpre = (dy W2) gated by f (ReLU and FFN dropout in one test)
             if f"dpre_{l}" not in ws:      # prune_last_layer toggled after the workspace was built
-                ws[f"dpre_{l}"] = torch.empty(B * L, cfg.dim_feedforward, dtype=torch.bfloat16, device=self.device)
+                ws[f"dpre_{l}"] = torch.empty(B * L, cfg.ff_dim, dtype=torch.bfloat16, device=self.device)
             dy2, dy1, dpre, dqkv = ws[f"dy2_{l}"], ws[f"dy1_{l}"], ws[f"dpre_{l}"], ws[f"dqkv_{l}"]
             wg(gemm, dy2, ws[f"f_{l}"], a_mn=True, b_mn=True, out_f32=g[self._lp(l, "linear2.weight")], accumulate=True)
             gemm(dy2, w[self._lp(l, "linear2.weight")], b_mn=True, gate=ws[f"f_{l}"], gate_scale=ffn_scale,
@@ -712,6 +712,8 @@ class TwoTowerEngine:
         [rank*n/world, (rank+1)*n/world) of the flat buffer, holds AdamW moments for them only and
         updates them from the reduce-scattered, averaged gradient `grad_shard`. The caller all-gathers
         the parameter shards afterwards and refreshes the bf16 shadow. Returns the parameter shard view."""
+        assert self.numel % world == 0, \
+            f"flat buffer of {self.numel} elements does not split into {world} equal optimizer shards"
         n = self.numel // world
         lo = rank * n
         if self.exp_avg is None or self.exp_avg.numel() != n:

@@ -120,6 +120,9 @@ class _TwoTowerFunction(torch.autograd.Function):
         eng.grad.zero_()
         eng.backward(loss_scale=float(dloss.item()))
         grads = tuple(eng.g[n].clone() for n in ctx.names)
+        # gradients handed to autograd mean an external optimizer is about to change the fp32 masters behind
+        # the bf16 operand shadow: the next forward must re-cast it
+        eng.shadow_valid = False
         return (None, None) + grads
 
 
@@ -150,8 +153,30 @@ class TwoTowerModel(nn.Module):
 
     # -- checkpoints in the reference layout (src/train.py:327-330; loaders strip 'module.')
     def load_state_dict(self, state_dict, strict: bool = False):  # type: ignore[override]
-        self.engine.load_state_dict(state_dict)
-        return torch.nn.modules.module._IncompatibleKeys([], [])
+        """Reference checkpoints also carry the four modality encoders (out of scope here): their keys are
+        reported as unexpected, never an error. A key of the hot path that is absent is an error under
+        ``strict`` and is reported (and left at its current value) otherwise."""
+        sd = {(k[7:] if k.startswith("module.") else k): v for k, v in state_dict.items()}
+        own = set(self.engine.p) | {"item_tower.fusion_layer.1." + b for b in
+                                    ("running_mean", "running_var", "num_batches_tracked")}
+        missing = sorted(k for k in self.engine.p if k not in sd)
+        unexpected = sorted(k for k in sd if k not in own)
+        if missing and strict:
+            raise RuntimeError(f"Error(s) in loading state_dict for TwoTowerModel: missing keys {missing}")
+        self.engine.load_state_dict({**{k: self.engine.p[k] for k in missing}, **sd})
+        return torch.nn.modules.module._IncompatibleKeys(missing, unexpected)
+
+    def _param_version(self) -> int:
+        return sum(p._version for p in self.parameters())
+
+    def _sync_shadow(self) -> None:
+        """The bf16 operand shadow follows the fp32 masters: any in-place change of a parameter since the last
+        forward (a stock optimizer's step, ``p.data`` edits, ``p.copy_``) bumps its version counter and forces a
+        re-cast; the fused AdamW refreshes the shadow itself."""
+        v = self._param_version()
+        if v != getattr(self, "_seen_version", None):
+            self.engine.shadow_valid = False
+            object.__setattr__(self, "_seen_version", v)
 
     def _ordered_params(self):
         named = dict(self.named_parameters())
@@ -168,6 +193,7 @@ class TwoTowerModel(nn.Module):
 
     def forward(self, batch: Dict[str, torch.Tensor]):
         b = self._batch(batch)
+        self._sync_shadow()
         params = self._ordered_params()
         if torch.is_grad_enabled() and self.training:
             return _TwoTowerFunction.apply(self, b, *params)
@@ -185,6 +211,7 @@ class TwoTowerModel(nn.Module):
         mask = None if history_mask is None else history_mask.to(eng.device).long().contiguous()
         B, L = ids.shape
         ws = eng.workspace(B, L)
+        self._sync_shadow()
         if not eng.shadow_valid:
             eng.refresh_shadow()
         u = eng.user_forward(ws, ids, mask, user_gender.to(eng.device).long().contiguous(),
@@ -196,6 +223,7 @@ class TwoTowerModel(nn.Module):
         eng = self.engine
         f = [t.to(eng.device).float().contiguous() for t in (audio, images, input_ids, tabular)]
         ws = eng.workspace(f[0].shape[0], eng.cfg.max_seq_len)
+        self._sync_shadow()
         if not eng.shadow_valid:
             eng.refresh_shadow()
         return eng.item_forward(ws, f[0], f[1], f[2], f[3], training=self.training).clone()

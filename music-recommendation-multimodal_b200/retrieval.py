@@ -29,6 +29,10 @@ class CatalogIndex:
         first, rows = (0, V) if shard is None else shard
         self.vocab_size = V
         self.item_base = first
+        #: True = this object holds ONE contiguous slice of the catalog and its peers hold the rest: retrieval
+        #: must merge across the process group. Never inferred from torch.distributed's global state.
+        self.is_sharded = shard is not None
+        self._group_checked = set()
         self.table = item_embeddings[first:first + rows].to(device=dev, dtype=torch.float32).contiguous()
         assert self.table.shape[1] == 256
         self.table_bf16 = torch.empty(self.table.shape, device=dev, dtype=torch.bfloat16)
@@ -40,9 +44,42 @@ class CatalogIndex:
         self._scratch: Dict[Tuple[int, int], Dict[str, torch.Tensor]] = {}
         self._plans: Dict[Tuple[int, int], TopkPlan] = {}
 
+    @classmethod
+    def from_shard(cls, shard_rows: torch.Tensor, first_row: int, vocab_size: int, device=None) -> "CatalogIndex":
+        """Index over rows [first_row, first_row + len(shard_rows)) of a catalog of ``vocab_size`` rows whose other
+        rows live on the other ranks (the slice is already cut: no full table on this rank)."""
+        self = cls(shard_rows, device=device)
+        self.item_base, self.vocab_size, self.is_sharded = first_row, vocab_size, True
+        return self
+
     @property
     def num_rows(self) -> int:
         return self.table.shape[0]
+
+    def check_group(self, U: int, group=None) -> None:
+        """Once per (group, U): the shards of the group's ranks must tile [0, vocab_size) without gaps or overlaps
+        and every rank must bring the same number of users (the merge pairs row u of every rank). One small
+        host-synchronising all-gather; raises on every rank alike."""
+        import torch.distributed as dist
+        key = (id(group), U)
+        if key in self._group_checked:
+            return
+        ws = dist.get_world_size(group)
+        mine = torch.tensor([self.item_base, self.num_rows, U, self.vocab_size], dtype=torch.int64,
+                            device=self.table.device if dist.get_backend(group) == "nccl" else "cpu")
+        allv = torch.empty(ws * 4, dtype=torch.int64, device=mine.device)
+        dist.all_gather_into_tensor(allv, mine, group=group)
+        rows = sorted(tuple(r) for r in allv.view(ws, 4).tolist())
+        nxt = 0
+        for first, n, u, v in rows:
+            if u != U or v != self.vocab_size:
+                raise ValueError(f"sharded retrieval: ranks disagree on users / vocab size: {rows}")
+            if first != nxt:
+                raise ValueError(f"sharded retrieval: shards do not tile the catalog (gap or overlap at row {nxt}): {rows}")
+            nxt = first + n
+        if nxt != self.vocab_size:
+            raise ValueError(f"sharded retrieval: shards cover {nxt} of {self.vocab_size} rows: {rows}")
+        self._group_checked.add(key)
 
     def plan(self, U: int, kprime: int) -> TopkPlan:
         key = (U, kprime)
@@ -171,6 +208,7 @@ def sharded_topk(user_emb: torch.Tensor, index: "CatalogIndex", K: int, kprime: 
     through the per-shard exact top-K protocol. ``bounded=False`` (default below 4 shards) always uses the latter."""
     import torch.distributed as dist
     ws = dist.get_world_size(group)
+    index.check_group(user_emb.shape[0], group)
     if bounded is None:
         # Measured (tools/dist_retrieval_check.py, 2 GPUs over NCCL, 10 k users x 1 M items): with 2 shards the
         # lists are nearly as long as the single-GPU budget (208 of 256) and the bounded pass is the slower one
@@ -252,11 +290,12 @@ def metrics_from_embeddings(user_emb: torch.Tensor, targets: torch.Tensor, index
                             k_list: Sequence[int] = (10, 20), kprime: int = 256,
                             group=None) -> Dict[str, float]:
     """Recall@k / NDCG@k of precomputed user embeddings against the (possibly sharded) catalog.
-    With a process group, every rank scores its shard and the per-shard top-K lists are
-    all-gathered and merged (result independent of the number of shards)."""
-    import torch.distributed as dist
+    With an index built over one shard (``CatalogIndex(shard=...)`` / ``from_shard``) every rank of ``group``
+    (default: the world group) scores its shard and the per-shard lists are all-gathered and merged — the result
+    does not depend on the number of shards. An unsharded index never communicates, whatever process group
+    happens to be initialised (every rank then evaluates its own users against the whole catalog)."""
     K = max(k_list)
-    if group is not None or (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+    if index.is_sharded:
         idx, score = sharded_topk(user_emb, index, K, kprime, group)
     else:
         idx, score, _ = retrieve_topk(user_emb, index, K, kprime)

@@ -202,3 +202,22 @@ def make_queries(table: torch.Tensor, num_users: int, seed: int = 3, noise: floa
     else:
         u = torch.nn.functional.normalize(table[targets] + noise * n / math.sqrt(D), dim=1)
     return u, targets
+
+
+def make_item_features(cfg: TwoTowerConfig, n_items: int, vocab_size: int, seed: int = 71, nan_rows=(),
+                       state_dict: Optional[Dict[str, torch.Tensor]] = None):
+    """Catalog-indexing input (src/evaluate_metrics.py:24-104 on precomputed modality embeddings): four (n_items,
+    128) feature tensors and the item id of every row — a random subset of [1, vocab_size) in random order, so ids
+    that are not listed keep a zero row. ``nan_rows`` get a NaN feature (exercises the NaN -> 0 branch).
+    With ``state_dict`` the BatchNorm running statistics in it are replaced by non-trivial seeded values.
+    Returns (features dict, item ids int64 (n_items,))."""
+    g = _gen(seed)
+    feats = {k: torch.randn(n_items, cfg.modality_dim, generator=g)
+             for k in ("target_audio", "target_image", "target_input_ids", "target_tabular")}
+    for r in nan_rows:
+        feats["target_audio"][r, 3] = float("nan")
+    ids = torch.randperm(vocab_size - 1, generator=g)[:n_items] + 1
+    if state_dict is not None:
+        state_dict["item_tower.fusion_layer.1.running_mean"] = 0.1 * torch.randn(cfg.fusion_hidden, generator=g)
+        state_dict["item_tower.fusion_layer.1.running_var"] = 0.5 + torch.rand(cfg.fusion_hidden, generator=g)
+    return feats, ids

@@ -56,8 +56,10 @@ class TrainStepRunner:
     def __init__(self, engine: TwoTowerEngine, B: int, L: int, world_size: int = 1, lr: float = 1e-4,
                  use_graph: bool = True, with_user_idx: bool = True, negatives: str = "gathered",
                  rank: Optional[int] = None, group=None, shard_optimizer: bool = True,
-                 with_optimizer: bool = True, sharded_table=None):
+                 with_optimizer: bool = True, sharded_table=None, betas=(0.9, 0.999), eps: float = 1e-8,
+                 weight_decay: float = 0.01):
         self.eng, self.B, self.L, self.world, self.lr, self.use_graph = engine, B, L, world_size, lr, use_graph
+        self.betas, self.eps, self.weight_decay = tuple(betas), eps, weight_decay
         self.group = group
         #: False = forward + backward only (the gradient buffer is cleared instead of consumed): the
         #: "without optimizer step" timing SURVEY.md §8d asks for; parameters do not change
@@ -72,7 +74,9 @@ class TrainStepRunner:
         # ZeRO-1 style: reduce-scatter the gradient, AdamW on this rank's 1/world shard (moments are
         # held for the shard only), all-gather the updated parameters. Same bytes on NVLink as one
         # all-reduce, 1/world of the optimizer's HBM traffic.
-        self.shard_opt = world_size > 1 and shard_optimizer
+        # The flat buffer is padded to a multiple of 2048 elements (engine.py), i.e. it splits into equal 16-byte
+        # aligned shards for 1/2/4/8 ranks; any other world size keeps the replicated optimizer (one all-reduce).
+        self.shard_opt = world_size > 1 and shard_optimizer and engine.numel % (4 * world_size) == 0
         if self.shard_opt:
             self._grad_shard = torch.empty(engine.numel // world_size, device=engine.device)
         # packed exchange buffers: one all-gather for (user emb | item emb | user id), one for the two LSE vectors
@@ -131,9 +135,10 @@ class TrainStepRunner:
 
     def _phase_opt(self):
         if self.shard_opt:
-            self.eng.adamw_step_sharded(self.rank, self.world, self._grad_shard, lr=self.lr)
+            self.eng.adamw_step_sharded(self.rank, self.world, self._grad_shard, lr=self.lr, betas=self.betas,
+                                        eps=self.eps, weight_decay=self.weight_decay)
         else:
-            self.eng.adamw_step(lr=self.lr)
+            self.eng.adamw_step(lr=self.lr, betas=self.betas, eps=self.eps, weight_decay=self.weight_decay)
 
     def _phase_drop_grad(self):
         from . import ops
@@ -199,7 +204,8 @@ class TrainStepRunner:
         g.zero_()
 
     def _phase_table_opt(self):
-        self.table.adamw_step(self.eng.step_dev, lr=self.lr)    # step counter already advanced by the engine
+        self.table.adamw_step(self.eng.step_dev, lr=self.lr, betas=self.betas, eps=self.eps,
+                              weight_decay=self.weight_decay)    # step counter already advanced by the engine
 
     def _sequence(self):
         """[(callable, is_communication)] of one step."""
@@ -358,7 +364,8 @@ def train_one_epoch(model, dataloader, optimizer, device, epoch, is_main_process
             B, L = batch["history_ids"].shape
             if runner is None or (runner.B, runner.L) != (B, L):
                 runner = TrainStepRunner(model.engine, B, L, world_size=world, lr=optimizer.lr,
-                                         with_user_idx="user_idx" in batch)
+                                         betas=optimizer.betas, eps=optimizer.eps,
+                                         weight_decay=optimizer.weight_decay, with_user_idx="user_idx" in batch)
                 staged = False
             cur = None if staged else {k: v for k, v in batch.items() if k in _BATCH_KEYS}
             # the next batch goes over PCIe during this step when it is pinned and has the same shape

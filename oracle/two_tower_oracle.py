@@ -265,3 +265,98 @@ def calculate_metrics_global(user_emb: torch.Tensor, item_embeddings: torch.Tens
         for k, v in m.items():
             per[k].append(v)
     return {k: torch.cat(v).mean().item() for k, v in per.items()}
+
+
+# ----------------------------------------------------------------------------------
+# in-batch validation (train.py:78-111)
+# ----------------------------------------------------------------------------------
+def inbatch_hits(logits: torch.Tensor, k: int = 10) -> torch.Tensor:
+    """Per-row hit flags of the in-batch Recall@k of ``evaluate`` (train.py:100-103): row i hits when
+    column i is among the k best logits of row i. torch.topk leaves the order of equal logits
+    unspecified; here ties are resolved by the canonical order (logit descending, column ascending),
+    i.e. hit <=> #{j : l_ij > l_ii or (l_ij == l_ii and j < i)} < k. With k >= B every row hits
+    (the reference's topk would raise for k > B: callers keep k <= B)."""
+    B = logits.shape[0]
+    diag = logits.diagonal().unsqueeze(1)
+    col = torch.arange(logits.shape[1]).unsqueeze(0)
+    row = torch.arange(B).unsqueeze(1)
+    better = (logits > diag) | ((logits == diag) & (col < row))
+    return better.sum(dim=1) < k
+
+
+def evaluate_inbatch(logit_batches: Sequence[torch.Tensor], k: int = 10) -> float:
+    """``evaluate`` (train.py:78-111) given the per-batch logits of model(batch): hits / total over all
+    batches (the all_reduce(SUM) of :106-109 adds the per-rank hits and totals before the division)."""
+    hits, total = 0.0, 0.0
+    for lg in logit_batches:
+        hits += float(inbatch_hits(lg, k).sum().item())
+        total += lg.shape[0]
+    return hits / total if total > 0 else 0.0
+
+
+# ----------------------------------------------------------------------------------
+# catalog indexing (evaluate_metrics.py:24-104)
+# ----------------------------------------------------------------------------------
+def index_catalog(p: Params, features: Dict[str, torch.Tensor], item_ids: torch.Tensor, vocab_size: int,
+                  batch_size: int = 64) -> torch.Tensor:
+    """``compute_all_item_embeddings`` on precomputed modality embeddings: per batch (evaluate_metrics.py:63-87)
+    emb = get_item_embedding(...) = F.normalize(item tower in eval mode) (two_tower.py:159-168, eps 1e-12);
+    if the batch holds a NaN, nan_to_num(nan=0) (:79-81); F.normalize(eps=1e-8) again (:85). Then the dense
+    scatter (:98-102): table[item_id] = embedding, row 0 and every id not listed stay zero.
+    Returns the (vocab_size, D) table in the dtype of the parameters."""
+    dt = p["item_tower.fusion_layer.0.weight"].dtype
+    rows = []
+    for s in range(0, item_ids.shape[0], batch_size):
+        sl = slice(s, s + batch_size)
+        e, _ = item_fusion(p, features["target_audio"][sl].to(dt), features["target_image"][sl].to(dt),
+                           features["target_input_ids"][sl].to(dt), features["target_tabular"][sl].to(dt),
+                           training=False)
+        e = l2_normalize(e)
+        if torch.isnan(e).any():
+            e = torch.nan_to_num(e, nan=0.0)
+        rows.append(F.normalize(e, p=2, dim=1, eps=1e-8))
+    emb = torch.cat(rows, dim=0)
+    dense = torch.zeros(vocab_size, emb.shape[1], dtype=emb.dtype)
+    dense[item_ids.long()] = emb
+    return dense
+
+
+# ----------------------------------------------------------------------------------
+# data-parallel step with all-gathered negatives (BASELINE.json configs[3]; SURVEY.md §8e)
+# ----------------------------------------------------------------------------------
+def dp_loss_and_grads(p: Params, batches: Sequence[Dict[str, torch.Tensor]], temperature: float = 0.07,
+                      num_heads: int = 4, dtype: torch.dtype = torch.float64):
+    """G data-parallel ranks, rank r holding ``batches[r]``: the towers run per rank (BatchNorm batch statistics
+    per rank: the reference wraps the model in plain DDP, no SyncBatchNorm, train.py:300), the normalised
+    embeddings and user ids of all ranks are concatenated and ONE symmetric InfoNCE (two_tower.py:106-140) is
+    taken over the global batch. Returns (loss, {param: d loss / d param}, user_emb_all, item_emb_all).
+    The averaged per-rank gradient the DP step applies equals this gradient. Memory stays that of one rank:
+    embeddings first without autograd, then one autograd pass per rank seeded with d loss / d embedding."""
+    q = {k: (v.clone() if k.endswith(TRAINABLE_SKIP) else v.detach().to(dtype)) for k, v in p.items()}
+
+    def towers(params, b):
+        u = user_tower(params, b["history_ids"], b["user_gender"], b["user_country"], b.get("history_mask"), num_heads)
+        i, _ = item_fusion(params, b["target_audio"].to(dtype), b["target_image"].to(dtype),
+                           b["target_input_ids"].to(dtype), b["target_tabular"].to(dtype), True)
+        return l2_normalize(u), l2_normalize(i)
+
+    with torch.no_grad():
+        embs = [towers(q, b) for b in batches]
+    U = torch.cat([e[0] for e in embs]).requires_grad_(True)
+    I = torch.cat([e[1] for e in embs]).requires_grad_(True)
+    uid = torch.cat([b["user_idx"] for b in batches]) if "user_idx" in batches[0] else None
+    loss, _ = infonce(U, I, temperature, uid)
+    loss.backward()
+    grads = None
+    off = 0
+    for b in batches:
+        n = b["history_ids"].shape[0]
+        qr = {k: (v if k.endswith(TRAINABLE_SKIP) else v.clone().requires_grad_(True)) for k, v in q.items()}
+        u, i = towers(qr, b)
+        torch.autograd.backward([u, i], [U.grad[off:off + n], I.grad[off:off + n]])
+        gr = {k: (v.grad if v.grad is not None else torch.zeros_like(v)) for k, v in qr.items()
+              if isinstance(v, torch.Tensor) and v.requires_grad}
+        grads = gr if grads is None else {k: grads[k] + gr[k] for k in gr}
+        off += n
+    grads["user_tower.item_embedding.weight"][0] = 0
+    return loss.detach(), grads, U.detach(), I.detach()

@@ -27,45 +27,16 @@ import mrm_b200  # noqa: E402
 from mrm_b200 import synthetic  # noqa: E402
 
 
-def import_reference():
-    peft = types.ModuleType("peft")
-    peft.get_peft_model = lambda m, c: m
-    peft.LoraConfig = lambda **kw: None
-    peft.TaskType = types.SimpleNamespace(FEATURE_EXTRACTION=0)
-    sys.modules["peft"] = peft
-    data = types.ModuleType("src.data")
-    ds = types.ModuleType("src.data.dataset")
-    ds.MultimodalDataset = type("MultimodalDataset", (), {})
-    sys.modules["src.data"] = data
-    sys.modules["src.data.dataset"] = ds
-    sys.path.insert(0, REF)
-    item_tower = importlib.import_module("src.models.item_tower")
+from oracle import ref_loader  # noqa: E402
 
-    class Identity(nn.Module):
-        def __init__(self, *a, **kw):
-            super().__init__()
 
-        def forward(self, x, *rest):
-            return x
-
-    for name in ("AudioEncoder", "VisualEncoder", "TextEncoder", "TabularEncoder"):
-        setattr(item_tower, name, Identity)
-    two_tower = importlib.import_module("src.models.two_tower")
-    evalm = importlib.import_module("src.evaluate_metrics")
-    return two_tower, evalm
+def import_reference(dataset_cls=None):
+    two_tower, evalm, train, _ = ref_loader.import_reference("checkout", dataset_cls=dataset_cls)
+    return two_tower, evalm, train
 
 
 def build_reference_model(two_tower, cfg, sd, dtype):
-    m = two_tower.TwoTowerModel(
-        vocab_size=cfg.vocab_size, tabular_input_dim=cfg.modality_dim, num_genders=cfg.num_genders,
-        num_countries=cfg.num_countries, max_seq_len=cfg.max_seq_len,
-        user_embedding_dim=cfg.embedding_dim, user_num_heads=cfg.num_heads,
-        user_num_layers=cfg.num_layers, user_dropout=0.0, item_embedding_dim=cfg.embedding_dim,
-        audio_dim=cfg.modality_dim, visual_dim=cfg.modality_dim, text_dim=cfg.modality_dim,
-        tabular_dim=cfg.modality_dim, temperature=cfg.temperature)
-    m.item_tower.fusion_layer[3].p = 0.0   # hard-coded Dropout(0.1), item_tower.py:126
-    missing, unexpected = m.load_state_dict(sd, strict=True)
-    return m.to(dtype)
+    return ref_loader.build_reference_model(two_tower, cfg, sd, dtype, dropout=0.0)
 
 
 def cast_batch(batch, dtype):
@@ -190,10 +161,77 @@ def golden_retrieval(evalm, name, num_items, num_users, k_list, grid, seed, nois
     print(name, metrics)
 
 
+class _CatalogDataset(torch.utils.data.Dataset):
+    """Harness stand-in for the absent src/data/dataset.py in compute_all_item_embeddings
+    (evaluate_metrics.py:40-48): serves the precomputed modality embeddings of `FEATURES` row by row."""
+    FEATURES = None
+
+    def __init__(self, interactions_df, item_id_mapper, img_dir=None, audio_dir=None, text_data=None,
+                 tokenizer=None, encoders=None, **kw):
+        self.df, self.mapper = interactions_df.reset_index(drop=True), item_id_mapper
+
+    def __len__(self):
+        return len(self.df)
+
+    def __getitem__(self, i):
+        row = int(self.df.loc[i, "row"])
+        f = type(self).FEATURES
+        return {"target_id": torch.tensor(self.mapper[self.df.loc[i, "track_id"]]),
+                "target_image": f["target_image"][row], "target_audio": f["target_audio"][row],
+                "target_input_ids": f["target_input_ids"][row], "target_attention_mask": torch.ones(1, dtype=torch.long),
+                "target_tabular": f["target_tabular"][row]}
+
+
+def golden_evaluate(two_tower, train, name, cfg, B, n_batches, seed_w, seed_b, k):
+    """The reference's own evaluate() (src/train.py:78-111) on seeded batches, eval mode, fp64 and fp32."""
+    import torch.distributed as dist
+    if not dist.is_initialized():      # evaluate() calls dist.get_rank() unguarded (SURVEY.md App. A)
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29541")
+        dist.init_process_group("gloo", rank=0, world_size=1)
+    sd = synthetic.make_state_dict(cfg, seed=seed_w)
+    out = {"config": cfg.as_dict(), "batch_size": B, "n_batches": n_batches, "seed_w": seed_w, "seed_b": seed_b, "k": k}
+    for dtype, tag in ((torch.float64, "f64"), (torch.float32, "f32")):
+        m = build_reference_model(two_tower, cfg, sd, dtype)
+        batches = [cast_batch(synthetic.make_batch(cfg, B, seed=seed_b + j), dtype) for j in range(n_batches)]
+        out[tag] = {"recall": train.evaluate(m, batches, torch.device("cpu"), k=k)}
+        m.eval()
+        with torch.no_grad():
+            out[tag]["hits_per_batch"] = []
+            for b in batches:
+                _, logits, _, _ = m(b)
+                _, topi = torch.topk(logits, k=k, dim=1)
+                out[tag]["hits_per_batch"].append(int((topi == torch.arange(B).unsqueeze(1)).any(dim=1).sum()))
+    torch.save(out, os.path.join(HERE, name))
+    print(name, {t: out[t]["recall"] for t in ("f64", "f32")}, out["f64"]["hits_per_batch"])
+
+
+def golden_index(two_tower, evalm, name, cfg, n_items, vocab_size, seed_w, seed_f, batch_size, nan_rows):
+    """The reference's own compute_all_item_embeddings (src/evaluate_metrics.py:24-104) over a synthetic item
+    list: a permuted subset of the ids (rows of ids not listed stay zero) with a few NaN feature rows (NaN -> 0
+    branch, :79-81). Stores the dense (V, 256) fp32 table it returns."""
+    import pandas as pd
+    from types import SimpleNamespace
+    sd = synthetic.make_state_dict(cfg, seed=seed_w)
+    # features, ids and non-trivial BatchNorm running statistics (as after some training)
+    feats, ids = synthetic.make_item_features(cfg, n_items, vocab_size, seed=seed_f, nan_rows=nan_rows, state_dict=sd)
+    _CatalogDataset.FEATURES = feats
+    mapper = {f"t{int(i)}": int(i) for i in range(1, vocab_size)}
+    ds = SimpleNamespace(item_id_mapper=mapper, img_dir=None, audio_dir=None, text_data=None, tokenizer=None, encoders=None)
+    df = pd.DataFrame({"track_id": [f"t{int(i)}" for i in ids], "row": list(range(n_items))})
+    m = build_reference_model(two_tower, cfg, sd, torch.float32)
+    dense, V = evalm.compute_all_item_embeddings(m, ds, df, batch_size, torch.device("cpu"))
+    assert V == vocab_size and dense.shape == (vocab_size, cfg.embedding_dim)
+    out = {"config": cfg.as_dict(), "n_items": n_items, "vocab_size": vocab_size, "seed_w": seed_w, "seed_f": seed_f,
+           "batch_size": batch_size, "nan_rows": list(nan_rows), "dense": dense}
+    torch.save(out, os.path.join(HERE, name))
+    print(name, "rows set", int((dense.abs().sum(1) > 0).sum()), "of", n_items, "| NaNs", int(torch.isnan(dense).sum()))
+
+
 def main():
     torch.manual_seed(0)
     torch.set_num_threads(8)
-    two_tower, evalm = import_reference()
+    two_tower, evalm, train = import_reference(dataset_cls=_CatalogDataset)
     small = synthetic.TwoTowerConfig(vocab_size=501, num_genders=3, num_countries=7, max_seq_len=12,
                                      embedding_dim=64, num_heads=4, num_layers=2, modality_dim=16,
                                      fusion_hidden=512)
@@ -206,6 +244,10 @@ def main():
     golden_retrieval(evalm, "retrieval_grid.pt", 5_000, 192, (10, 20, 50, 100), 2.0 ** -7, 30, 5.0)
     golden_retrieval(evalm, "retrieval_grid_coarse.pt", 5_000, 192, (10, 20, 50, 100), 2.0 ** -3, 50, 5.0)
     golden_retrieval(evalm, "retrieval_float.pt", 5_000, 192, (10, 20, 50, 100), 0.0, 40, 5.0)
+    ev = synthetic.TwoTowerConfig(vocab_size=2_001, max_seq_len=20)
+    golden_evaluate(two_tower, train, "evaluate_inbatch.pt", ev, B=32, n_batches=3, seed_w=60, seed_b=61, k=10)
+    golden_index(two_tower, evalm, "index_catalog.pt", synthetic.TwoTowerConfig(vocab_size=401), n_items=300,
+                 vocab_size=401, seed_w=70, seed_f=71, batch_size=64, nan_rows=(5, 130))
 
 
 if __name__ == "__main__":

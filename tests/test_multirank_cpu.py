@@ -121,7 +121,14 @@ class _CpuShard:
     """Stand-in for retrieval.CatalogIndex holding a CPU shard (the device kernels are replaced below)."""
 
     def __init__(self, table, first, rows):
-        self.table, self.item_base = table[first:first + rows], first
+        from mrm_b200 import retrieval
+        self.table, self.item_base, self.vocab_size = table[first:first + rows], first, table.shape[0]
+        self.is_sharded, self._group_checked = True, set()
+        self.check_group = lambda U, group=None: retrieval.CatalogIndex.check_group(self, U, group)
+
+    @property
+    def num_rows(self):
+        return self.table.shape[0]
 
 
 def _sharded_topk_plumbing_worker(rank, world, K, kps):
@@ -180,6 +187,26 @@ def _sharded_topk_plumbing_worker(rank, world, K, kps):
     assert torch.equal(mi.long(), ri) and torch.equal(mv, rv), f"rank {rank}: bounded protocol"
     assert torch.equal(ei.long(), ri) and torch.equal(ev, rv), f"rank {rank}: per-shard exact protocol"
     return fallback_users
+
+
+def _bad_tiling_worker(rank, world):
+    """CatalogIndex.check_group: shards that overlap / leave a gap, or ranks that bring different user counts, are
+    refused on every rank alike (the merge kernels assume distinct items and paired user rows)."""
+    torch.set_num_threads(1)
+    table = synthetic.make_catalog(299, 256, seed=5)
+    first, rows = shard_bounds(table.shape[0], world, rank)
+    ok = _CpuShard(table, first, rows)
+    ok.check_group(10)
+    overlap = _CpuShard(table, 0, table.shape[0])            # every rank claims the whole catalog (unsharded index)
+    with pytest.raises(ValueError, match="tile"):
+        overlap.check_group(10)
+    ragged = _CpuShard(table, first, rows)
+    with pytest.raises(ValueError, match="disagree"):
+        ragged.check_group(10 + rank)
+
+
+def test_shard_tiling_check_world2():
+    _run(_bad_tiling_worker, 2)
 
 
 def _plumbing_short_lists(rank, world):

@@ -122,3 +122,82 @@ def test_oracle_recommend_masks_padding_and_history():
     tv, ti = torch.topk(s, 10)
     assert idx.tolist() == ti.tolist() and torch.equal(vals, tv)
     assert 0 not in idx.tolist() and not set(idx.tolist()) & set(hist)
+
+
+def test_oracle_adamw_matches_torch_optim():
+    """oracle.adamw_step == torch.optim.AdamW with the reference's settings (src/train.py:302: lr only, so
+    betas (0.9, 0.999), eps 1e-8, weight_decay 0.01) over several steps, fp64 and fp32."""
+    g = torch.Generator().manual_seed(5)
+    for dtype, tol in ((torch.float64, 1e-14), (torch.float32, 5e-7)):   # 1 ulp of values up to 4
+        p0 = torch.randn(257, 33, generator=g).to(dtype)
+        grads = [torch.randn(257, 33, generator=g).to(dtype) * s for s in (1.0, 1e-3, 0.0, 5.0, 1e-6)]
+        p_ref = torch.nn.Parameter(p0.clone())
+        opt = torch.optim.AdamW([p_ref], lr=1e-4)
+        p, m, v = p0.clone(), torch.zeros_like(p0), torch.zeros_like(p0)
+        for t, gr in enumerate(grads, start=1):
+            p_ref.grad = gr.clone()
+            opt.step()
+            p, m, v = oracle.adamw_step(p, gr, m, v, t, lr=1e-4)
+            assert (p - p_ref.detach()).abs().max().item() <= tol, (dtype, t)
+        st = opt.state[p_ref]
+        assert (m - st["exp_avg"]).abs().max().item() <= tol and (v - st["exp_avg_sq"]).abs().max().item() <= tol
+    # non-default hyper-parameters (FusedAdamW forwards them to the kernel)
+    p_ref = torch.nn.Parameter(p0.double().clone())
+    opt = torch.optim.AdamW([p_ref], lr=3e-3, betas=(0.8, 0.95), eps=1e-6, weight_decay=0.2)
+    p, m, v = p0.double().clone(), torch.zeros_like(p0.double()), torch.zeros_like(p0.double())
+    for t in range(1, 4):
+        gr = torch.randn(257, 33, generator=g).double()
+        p_ref.grad = gr.clone()
+        opt.step()
+        p, m, v = oracle.adamw_step(p, gr, m, v, t, lr=3e-3, beta1=0.8, beta2=0.95, eps=1e-6, weight_decay=0.2)
+    assert (p - p_ref.detach()).abs().max().item() <= 1e-13
+
+
+def test_oracle_evaluate_inbatch_matches_reference():
+    """oracle.evaluate_inbatch on the oracle's own eval-mode logits == the reference's evaluate()
+    (src/train.py:78-111) on the same seeded batches, and per-batch hit counts equal its torch.topk ones."""
+    gold = _load("evaluate_inbatch.pt")
+    cfg = synthetic.TwoTowerConfig(**gold["config"])
+    sd = synthetic.make_state_dict(cfg, seed=gold["seed_w"])
+    for tag, dtype in (("f64", torch.float64), ("f32", torch.float32)):
+        p = {k: (v.to(dtype) if v.is_floating_point() else v) for k, v in sd.items()}
+        logits = []
+        for j in range(gold["n_batches"]):
+            b = _cast(synthetic.make_batch(cfg, gold["batch_size"], seed=gold["seed_b"] + j), dtype)
+            logits.append(oracle.two_tower_forward(p, b, cfg.temperature, cfg.num_heads, training=False)[1])
+        hits = [int(oracle.inbatch_hits(lg, gold["k"]).sum()) for lg in logits]
+        assert hits == gold[tag]["hits_per_batch"], (tag, hits, gold[tag]["hits_per_batch"])
+        assert oracle.evaluate_inbatch(logits, gold["k"]) == pytest.approx(gold[tag]["recall"], abs=1e-7)
+
+
+def test_oracle_inbatch_hits_tie_rule():
+    """Equal logits: the lower column wins (canonical order), -1e4 collision fills sink to the bottom."""
+    lg = torch.tensor([[1.0, 1.0, 1.0, 0.0],
+                       [2.0, 1.0, 1.0, 1.0],
+                       [3.0, 3.0, 3.0, 3.0],
+                       [-1e4, 5.0, 5.0, 5.0]])
+    assert oracle.inbatch_hits(lg, 1).tolist() == [True, False, False, False]
+    assert oracle.inbatch_hits(lg, 2).tolist() == [True, True, False, False]
+    assert oracle.inbatch_hits(lg, 3).tolist() == [True, True, True, False]
+    assert oracle.inbatch_hits(lg, 4).tolist() == [True, True, True, True]
+
+
+def test_oracle_index_catalog_matches_reference():
+    """oracle.index_catalog == the dense table returned by the reference's compute_all_item_embeddings
+    (src/evaluate_metrics.py:24-104) for the same items: permuted ids, unlisted rows zero, NaN feature rows -> 0."""
+    gold = _load("index_catalog.pt")
+    cfg = synthetic.TwoTowerConfig(**gold["config"])
+    sd = synthetic.make_state_dict(cfg, seed=gold["seed_w"])
+    feats, ids = synthetic.make_item_features(cfg, gold["n_items"], gold["vocab_size"], seed=gold["seed_f"],
+                                              nan_rows=gold["nan_rows"], state_dict=sd)
+    dense = oracle.index_catalog(sd, feats, ids, gold["vocab_size"], gold["batch_size"])
+    ref = gold["dense"]
+    assert dense.shape == ref.shape and not torch.isnan(dense).any()
+    assert torch.equal(dense.abs().sum(1) > 0, ref.abs().sum(1) > 0)        # same rows populated
+    assert (dense - ref).abs().max().item() <= 2e-6
+    assert dense[0].abs().max().item() == 0.0
+    for r in gold["nan_rows"]:
+        assert dense[ids[r]].abs().max().item() == 0.0
+    d64 = oracle.index_catalog({k: (v.double() if v.is_floating_point() else v) for k, v in sd.items()},
+                               feats, ids, gold["vocab_size"], gold["batch_size"])
+    assert (d64 - ref.double()).abs().max().item() <= 2e-6
