@@ -175,7 +175,7 @@ def test_oracle_inbatch_hits_tie_rule():
     lg = torch.tensor([[1.0, 1.0, 1.0, 0.0],
                        [2.0, 1.0, 1.0, 1.0],
                        [3.0, 3.0, 3.0, 3.0],
-                       [-1e4, 5.0, 5.0, 5.0]])
+                       [5.0, 5.0, -1e4, -1e4]])
     assert oracle.inbatch_hits(lg, 1).tolist() == [True, False, False, False]
     assert oracle.inbatch_hits(lg, 2).tolist() == [True, True, False, False]
     assert oracle.inbatch_hits(lg, 3).tolist() == [True, True, True, False]
