@@ -31,6 +31,10 @@ import torch.distributed as dist  # noqa: E402
 C2 = dict(batch=256, seq_len=200, vocab=100_001)      # BASELINE.json configs[1]
 C3 = dict(users=10_000, items=1_000_000, k=100, hist_len=50)  # BASELINE.json configs[2]
 CPU_SAMPLE_BATCH = 64
+C2_WORKLOAD = ("c2: two-tower train step (fwd+bwd+InfoNCE+dense AdamW), batch 256/GPU, seq_len 200 (all positions valid), "
+               "100k-item ID table, dropout 0.1")
+C4 = dict(batch=512, seq_len=200, vocab=100_001)                 # BASELINE.json configs[3]: 8 x 512 = 4096 global
+C5 = dict(batch=512, seq_len=512, vocab=10_000_001, users=10_000, k=100)   # BASELINE.json configs[4]
 
 
 def flops_per_sample_fwd(L, B_neg, D=256, FF=1024, NL=2):
@@ -84,12 +88,66 @@ def pin(batch):
 
 
 # ------------------------------------------------------------------------------------------
-# CPU arm: the oracle port of the reference step / retrieval on the host cores
+# CPU arm: the UNMODIFIED reference (baseline/_ref, installed by __graft_entry__.build()) on the host cores;
+# the oracle port only when that install is missing
 # ------------------------------------------------------------------------------------------
-def cpu_train_samples_per_s(steps, warmup, batch_size):
+def _c2_cfg(dropout):
+    from mrm_b200 import synthetic
+    return synthetic.TwoTowerConfig(vocab_size=C2["vocab"], max_seq_len=C2["seq_len"], dropout=dropout)
+
+
+def reference_train_samples_per_s(steps, warmup, batch_size):
+    """The reference's own train_one_epoch (src/train.py:41-76: TwoTowerModel.forward, backward, torch.optim.AdamW
+    lr 1e-4 as train.py:302, dropout 0.1 as shipped) on `steps` c2 batches, on the CPU. autocast / GradScaler
+    disable themselves without CUDA, so this is the reference's fp32 path.
+    Returns (samples/s, ms/step, kind, detail)."""
+    from mrm_b200 import synthetic
+    from oracle import ref_loader
+    if ref_loader.reference_location() is None:
+        sps, ms = port_train_samples_per_s(steps, warmup, min(batch_size, CPU_SAMPLE_BATCH))
+        return sps, ms, "port", f"oracle port (baseline/_ref absent), batch {min(batch_size, CPU_SAMPLE_BATCH)}"
+    import logging
+    import warnings
+    warnings.filterwarnings("ignore")
+    two_tower, _, train, where = ref_loader.import_reference("installed")
+    logging.disable(logging.WARNING)
+    cfg = _c2_cfg(0.1)
+    model = ref_loader.build_reference_model(two_tower, cfg, synthetic.make_state_dict(cfg, seed=0), torch.float32,
+                                             dropout=0.1)
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-4)
+    dev = torch.device("cpu")
+
+    def batches(n, seed0):
+        return [synthetic.make_batch(cfg, batch_size, seed=seed0 + i, full_length=True, num_users=1_000_000)
+                for i in range(n)]
+
+    def run(loader):
+        if train is not None:
+            train.train_one_epoch(model, loader, opt, dev, 0, is_main_process=False)
+            return
+        model.train()                              # src.train not importable (tqdm/joblib): same body by hand
+        for b in loader:
+            opt.zero_grad(set_to_none=True)
+            loss, _, _, _ = model(b)
+            loss.backward()
+            opt.step()
+            loss.item()
+
+    if warmup > 0:
+        run(batches(warmup, 100))
+    timed = batches(steps, 200)
+    t0 = time.perf_counter()
+    run(timed)
+    dt = time.perf_counter() - t0
+    logging.disable(logging.NOTSET)
+    api = "train_one_epoch" if train is not None else "TwoTowerModel.forward/backward + AdamW loop"
+    return batch_size * steps / dt, dt / steps * 1e3, "reference", f"reference {api} from {where}"
+
+
+def port_train_samples_per_s(steps, warmup, batch_size):
     from mrm_b200 import synthetic
     from oracle import two_tower_oracle as oracle
-    cfg = synthetic.TwoTowerConfig(vocab_size=C2["vocab"], max_seq_len=C2["seq_len"], dropout=0.0)
+    cfg = _c2_cfg(0.0)
     sd = synthetic.make_state_dict(cfg, seed=0)
     batch = synthetic.make_batch(cfg, batch_size, seed=1, full_length=True, num_users=1_000_000)
     p = {k: v.clone() for k, v in sd.items()}
@@ -108,31 +166,65 @@ def cpu_train_samples_per_s(steps, warmup, batch_size):
     return batch_size * len(times) / total, total / len(times) * 1e3
 
 
-def cpu_retrieval_users_per_s(num_users=128):
+class _PrecomputedUsers(torch.nn.Module):
+    """calculate_metrics_global only calls .eval() and .get_user_embedding(): feeding it precomputed user embeddings
+    times the scoring / top-K / metric part (the c3 metric) of the reference's own function."""
+
+    def __init__(self, users):
+        super().__init__()
+        self.users, self.pos = users, 0
+
+    def get_user_embedding(self, history_ids, history_mask=None, user_gender=None, user_country=None):
+        n = history_ids.shape[0]
+        u = self.users[self.pos:self.pos + n]
+        self.pos += n
+        return u
+
+
+def reference_retrieval_users_per_s(num_users=128):
+    """The reference's calculate_metrics_global (src/evaluate_metrics.py:106-192; val batch 64, :203) on
+    `num_users` users against the 1M-item table, k_list [10, 20, 50, 100], on the CPU."""
     from mrm_b200 import synthetic
-    from oracle import two_tower_oracle as oracle
+    from oracle import ref_loader
     table = synthetic.make_catalog(C3["items"], 256, seed=2)
     users, targets = synthetic.make_queries(table, num_users, seed=3)
-    oracle.calculate_metrics_global(users[:64], table, targets[:64], [10, 20, 50, 100])
+    kl = [10, 20, 50, 100]
+    if ref_loader.reference_location() is None:
+        from oracle import two_tower_oracle as oracle
+        t0 = time.perf_counter()
+        oracle.calculate_metrics_global(users, table, targets, kl)
+        return num_users / (time.perf_counter() - t0), "port"
+    import logging
+    _, evalm, _, _ = ref_loader.import_reference("installed")
+    logging.disable(logging.WARNING)
+    loader = []
+    for s0 in range(0, num_users, 64):
+        n = min(64, num_users - s0)
+        z = torch.zeros(n, dtype=torch.long)
+        loader.append({"history_ids": torch.ones((n, 4), dtype=torch.long), "history_mask": torch.ones((n, 4), dtype=torch.long),
+                       "user_gender": z, "user_country": z, "target_id": targets[s0:s0 + n]})
     t0 = time.perf_counter()
-    oracle.calculate_metrics_global(users, table, targets, [10, 20, 50, 100])
-    return num_users / (time.perf_counter() - t0)
+    evalm.calculate_metrics_global(_PrecomputedUsers(users), loader, table, torch.device("cpu"), k_list=kl)
+    dt = time.perf_counter() - t0
+    logging.disable(logging.NOTSET)
+    return num_users / dt, "reference"
 
 
 def run_reference(args, rank, world):
     if rank != 0:
         return
     torch.set_num_threads(os.cpu_count() or 1)
-    sps, ms = cpu_train_samples_per_s(args.steps, args.warmup, CPU_SAMPLE_BATCH)
-    sample = (f"oracle port of the reference step (fp32 torch CPU: fwd+bwd+InfoNCE+AdamW), batch {CPU_SAMPLE_BATCH} "
-              f"of the c2 workload (L={C2['seq_len']}, V={C2['vocab']}) per step")
+    B = C2["batch"]
+    sps, ms, kind, detail = reference_train_samples_per_s(args.steps, args.warmup, B)
+    sample = (f"{detail}: fp32 torch CPU, fwd+bwd+InfoNCE+AdamW, {args.steps} timed steps of batch {B} "
+              f"(L={C2['seq_len']}, V={C2['vocab']}, dropout 0.1) after {args.warmup} warm-up steps")
     line = {
         "impl": "reference", "metric": "two-tower train samples/sec", "value": sps, "unit": "samples/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "c2: two-tower train step, batch 256/GPU, seq_len 200, 100k items",
-                   "reference_step_batch": CPU_SAMPLE_BATCH},
-        "cpu_baseline": {"value": sps, "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
+        "config": {"workload": C2_WORKLOAD, "global_batch": B, "seq_len": C2["seq_len"], "vocab_size": C2["vocab"],
+                   "reference_step_batch": B},
+        "cpu_baseline": {"value": sps, "unit": "samples/s", "cores": torch.get_num_threads(), "kind": kind,
                          "sample": sample},
         "e2e": {"value": sps, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -229,6 +321,7 @@ def run_ours(args, rank, world, local_rank):
     pct = {f"p{q}": per_step[min(len(per_step) - 1, int(q / 100.0 * len(per_step)))] for q in (10, 50, 90)}
     value = world * B * 1e3 / ms_step
     launches = runner.kernels_per_step * args.steps + (_lib.launch_count - l0)
+    kernels_per_step, runner_comm = runner.kernels_per_step, runner.comm_description()
 
     # ---- e2e: host batches, H2D + step + D2H of the loss every step -----------------------
     # Every step's batch crosses PCIe from pinned memory inside the timed region; the copy of batch i+1 is
@@ -302,30 +395,49 @@ def run_ours(args, rank, world, local_rank):
                "the timed step); algorithmic bytes = operands + outputs + residual/gate per launch"})
     step_flops = 3.0 * flops_per_sample_fwd(L, B) * B
 
+    # ---- parity of the benchmarked step with the oracle (dropout 0 on the bench batch) -------
+    parity = bench_parity_train(cfg, host_batches[0], dev) if rank == 0 else None
+
     # ---- retrieval (configs[2]) -----------------------------------------------------------
     retr = None if args.skip_retrieval else bench_retrieval(eng, rank, world, dev, peaks)
+    if retr is not None and parity is not None:
+        parity["retrieval"] = retr.pop("parity")
+
+    # ---- catalog indexing (SURVEY.md §8f-2 / §8e item-sharded) ------------------------------
+    indexing = None if args.skip_retrieval else bench_indexing(eng, rank, world, dev, peaks)
+
+    # ---- configs[3] / configs[4]: data-parallel at 512/rank, row-sharded 10M-item table ------
+    c4 = c5 = None
+    want_c45 = world == 8 or (world > 1 and os.environ.get("TT_BENCH_C45", "") == "1")
+    if want_c45 and not args.skip_c45:
+        del runner
+        eng.release_workspaces()
+        torch.cuda.empty_cache()
+        c4 = bench_c4(rank, world, dev, peaks, args)
+        torch.cuda.empty_cache()
+        c5 = bench_c5(rank, world, dev, peaks, args)
 
     cpu = None
     if rank == 0 and world == 1 and not args.skip_cpu:
         torch.set_num_threads(os.cpu_count() or 1)
-        sps, _ = cpu_train_samples_per_s(2, 1, CPU_SAMPLE_BATCH)
-        cpu = {"value": sps, "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
-               "sample": f"oracle port of the reference step on batch {CPU_SAMPLE_BATCH} of the c2 workload, "
-                         f"1 warm-up + 2 timed steps",
-               "retrieval_users_per_s": cpu_retrieval_users_per_s(128),
-               "retrieval_sample": "oracle calculate_metrics_global, 128 users x 1M items, top-100"}
+        sps, ms_cpu, kind, detail = reference_train_samples_per_s(3, 1, B)
+        rps, rkind = reference_retrieval_users_per_s(128)
+        cpu = {"value": sps, "unit": "samples/s", "cores": torch.get_num_threads(), "kind": kind,
+               "sample": f"{detail}: 3 timed steps of batch {B} of the c2 workload after 1 warm-up ({ms_cpu:.0f} ms/step)",
+               "retrieval_users_per_s": rps, "retrieval_kind": rkind,
+               "retrieval_sample": "calculate_metrics_global, 128 users x 1M items, k_list [10, 20, 50, 100] (cost is "
+                                   "linear in users)"}
 
     if rank == 0:
         line = {
             "metric": "two-tower train samples/sec", "value": value, "unit": "samples/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": "c2: two-tower train step (fwd+bwd+InfoNCE+dense AdamW), batch 256/GPU, "
-                                   "seq_len 200 (all positions valid), 100k-item ID table, dropout 0.1",
+            "config": {"workload": C2_WORKLOAD,
                        "global_batch": world * B, "seq_len": L, "vocab_size": V,
                        "parallelism": f"dp{world}" if world > 1 else "single",
-                       "negatives": ("all-gathered across ranks (NCCL all-gather of embeddings + row log-sum-exps)"
-                                     if world > 1 else "in-batch"),
+                       "negatives": ("all-gathered across ranks" if world > 1 else "in-batch"),
+                       "comm": runner_comm,
                        "last_layer": "exact single-row form (only out[b, len-1] of the last encoder layer is ever "
                                      "read: K/V for all positions, query/out_proj/FFN for one row per sequence)",
                        "l2": "per-step working set (~1.2 GB activations + 410 MB optimizer state) exceeds the 126 MB L2"},
@@ -333,40 +445,245 @@ def run_ours(args, rank, world, local_rank):
             "ms_per_step_percentiles": pct,
             "fwd_bwd_only": fb,
             "gpu_launches": launches,
-            "kernels_per_step": runner.kernels_per_step,
+            "kernels_per_step": kernels_per_step,
             "step_tflops": step_flops / (ms_step * 1e-3) / 1e12,
             "step_tflops_note": "reference-algorithm FLOPs of the step (SURVEY.md §8d formula, every layer on every "
                                 "position) per second; the executed GEMM FLOPs are roofline.flops_per_step",
             "roofline": roof,
             "clocks": sampler.summary(),
+            "parity": parity,
             "retrieval": retr,
+            "indexing": indexing,
         }
+        if c4 is not None:
+            line["c4"] = c4
+        if c5 is not None:
+            line["c5"] = c5
         if cpu is not None:
             line["cpu_baseline"] = cpu
         print(json.dumps(line), flush=True)
 
 
+def bench_parity_train(cfg, host_batch, dev):
+    """The bench batch through a fresh engine with dropout 0 against the oracle's fp32 CPU forward."""
+    import dataclasses
+    from mrm_b200 import synthetic
+    from mrm_b200.engine import TwoTowerEngine
+    from oracle import two_tower_oracle as oracle
+    cfg0 = dataclasses.replace(cfg, dropout=0.0)
+    sd = synthetic.make_state_dict(cfg0, seed=0)
+    e = TwoTowerEngine(cfg0, dev)
+    e.load_state_dict(sd)
+    loss, logits, u, i = e.forward({k: v.to(dev) for k, v in host_batch.items()}, training=True)
+    torch.cuda.synchronize()
+    torch.set_num_threads(os.cpu_count() or 1)
+    with torch.no_grad():
+        rl, rlog, ru, ri, _ = oracle.two_tower_forward(sd, {k: v.clone() for k, v in host_batch.items()},
+                                                       cfg0.temperature, cfg0.num_heads, training=True)
+    out = {"train": {"what": "c2 bench batch, dropout 0, forward: CUDA path vs oracle (fp32 CPU)",
+                     "loss": loss.item(), "oracle_loss": rl.item(), "loss_abs_err": abs(loss.item() - rl.item()),
+                     "user_emb_abs_err": (u.cpu() - ru).abs().max().item(),
+                     "item_emb_abs_err": (i.cpu() - ri).abs().max().item(),
+                     "logits_abs_err": (logits.cpu() - rlog).abs().max().item(),
+                     "tol": {"loss": 5e-3, "emb": 5e-3, "logits": 8e-2}}}
+    t = out["train"]
+    t["ok"] = bool(t["loss_abs_err"] <= 5e-3 and t["user_emb_abs_err"] <= 5e-3 and t["item_emb_abs_err"] <= 5e-3
+                   and t["logits_abs_err"] <= 8e-2)
+    del e
+    return out
+
+
+def _timed(fn, iters, dev, world):
+    """CUDA-event time of `iters` calls of fn (barrier + synchronize on both sides, max over ranks) in ms per call."""
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1) / iters], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    return ms.item()
+
+
+def _time_train(runner, host_batches, steps, warmup, dev, world):
+    runner.load_batch(host_batches[0])
+    for _ in range(max(warmup, 3)):
+        runner.step_resident()
+    return _timed(runner.step_resident, steps, dev, world)
+
+
+def bench_c4(rank, world, dev, peaks, args):
+    """BASELINE.json configs[3]: data parallel, 512 samples per rank (global 4096 on 8 GPUs), L=200, 100k items,
+    every rank's positives against the all-gathered items of all ranks."""
+    from mrm_b200 import synthetic
+    from mrm_b200.engine import TwoTowerEngine
+    from mrm_b200.train import TrainStepRunner
+    B, L, V = C4["batch"], C4["seq_len"], C4["vocab"]
+    cfg = synthetic.TwoTowerConfig(vocab_size=V, max_seq_len=L, dropout=0.1)
+    eng = TwoTowerEngine(cfg, dev)
+    eng.load_state_dict(synthetic.make_state_dict(cfg, seed=0))
+    runner = TrainStepRunner(eng, B, L, world_size=world)
+    hb = [pin(synthetic.make_batch(cfg, B, seed=500 + rank * 17 + i, full_length=True, num_users=1_000_000)) for i in range(2)]
+    ms = _time_train(runner, hb, args.steps, args.warmup, dev, world)
+    flops = 3.0 * flops_per_sample_fwd(L, world * B) * B            # per rank
+    peak_tf = peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops"))
+    out = {"workload": f"c4: data-parallel train step, {B}/rank x {world} ranks = global batch {world * B}, seq_len {L}, "
+                       f"{V - 1} items, all-gathered negatives",
+           "global_batch": world * B, "ms_per_step": ms, "samples_per_s": world * B * 1e3 / ms,
+           "step_tflops_per_gpu": flops / (ms * 1e-3) / 1e12, "roofline_frac_tensor": flops / (ms * 1e-3) / 1e12 / peak_tf,
+           "roofline_ms_tensor_per_rank": flops / (peak_tf * 1e12) * 1e3,
+           "kernels_per_step": runner.kernels_per_step, "comm": runner.comm_description()}
+    del runner, eng
+    return out
+
+
+def bench_c5(rank, world, dev, peaks, args):
+    """BASELINE.json configs[4]: 10M-item catalog, ID table row-sharded over the ranks (id/row exchange per step),
+    seq_len 512, 512 samples per rank; and retrieval of 10k users against the 10M-item table sharded over the ranks."""
+    import dataclasses
+    from mrm_b200 import retrieval, synthetic
+    from mrm_b200.engine import TwoTowerEngine
+    from mrm_b200.sharding import RowShardedTable
+    from mrm_b200.train import TrainStepRunner
+    B, L, V = C5["batch"], C5["seq_len"], C5["vocab"]
+    cfg = synthetic.TwoTowerConfig(vocab_size=V, max_seq_len=L, dropout=0.1)
+    eng = TwoTowerEngine(dataclasses.replace(cfg, vocab_size=2), dev)
+    table = RowShardedTable(V, 256, rank, world, dev)
+    small = dataclasses.replace(cfg, vocab_size=2)
+    eng.load_state_dict(synthetic.make_state_dict(small, seed=0))
+    g = torch.Generator(device=dev).manual_seed(777 + rank)
+    table.weight.copy_(torch.randn(table.rows, 256, device=dev, generator=g) * (2.0 / (V + 256)) ** 0.5)
+    runner = TrainStepRunner(eng, B, L, world_size=world, sharded_table=table)
+    hb = [pin(synthetic.make_batch(cfg, B, seed=600 + rank * 17 + i, full_length=True, num_users=1_000_000)) for i in range(2)]
+    steps = max(5, args.steps // 2)
+    ms = _time_train(runner, hb, steps, args.warmup, dev, world)
+    flops = 3.0 * flops_per_sample_fwd(L, world * B) * B
+    peak_tf = peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops"))
+    train = {"workload": f"c5 train: {V - 1} items, ID table row-sharded over {world} ranks ({table.rows} rows/rank), "
+                         f"seq_len {L}, {B}/rank, all-gathered negatives, dense AdamW on the local rows",
+             "ms_per_step": ms, "samples_per_s": world * B * 1e3 / ms,
+             "step_tflops_per_gpu": flops / (ms * 1e-3) / 1e12, "roofline_frac_tensor": flops / (ms * 1e-3) / 1e12 / peak_tf,
+             "roofline_ms_tensor_per_rank": flops / (peak_tf * 1e12) * 1e3,
+             "table_optimizer_bytes_per_rank": table.rows * 256 * 4 * 7,
+             "roofline_ms_hbm_table_optimizer": table.rows * 256 * 4 * 7 / (peaks["hbm_gbs"] * 1e9) * 1e3,
+             "exchange": table.describe(), "comm": runner.comm_description(), "kernels_per_step": runner.kernels_per_step}
+    del runner, eng, table
+    torch.cuda.empty_cache()
+    # ---- retrieval: 10k users x 10M items, catalog rows sharded contiguously over the ranks
+    U, N, K = C5["users"], V - 1, C5["k"]
+    index, users, targets = _sharded_catalog(N, U, rank, world, dev, seed=4321)
+    kl = [10, 20, 50, 100]
+    for _ in range(2):
+        m = retrieval.metrics_from_embeddings(users, targets, index, kl)
+    ms_r = _timed(lambda: retrieval.sharded_topk(users, index, K), 3, dev, world)
+    rflops = 2.0 * U * (N + 1) * 256 / world
+    retr = {"workload": f"c5 retrieval: {U} users x {N} items, top-{K}, catalog sharded over {world} GPUs",
+            "ms_per_pass": ms_r, "users_per_s": U / (ms_r * 1e-3), "scoring_tflops_per_gpu": rflops / (ms_r * 1e-3) / 1e12,
+            "roofline_frac_tensor": rflops / (ms_r * 1e-3) / 1e12 / peak_tf, "recall_at_10": m["Recall@10"]}
+    return {"train": train, "retrieval": retr}
+
+
+def _catalog_rows(lo, hi, dev, seed, chunk=1 << 18):
+    """Rows [lo, hi) of THE seeded global catalog (unit-norm rows, row 0 = padding zeros): generated in fixed chunks
+    of 2^18 rows, each from its own seed, so every rank count slices the same table without materialising it."""
+    out = torch.empty(hi - lo, 256, device=dev)
+    c0 = lo // chunk
+    while c0 * chunk < hi:
+        a, b = c0 * chunk, (c0 + 1) * chunk
+        g = torch.Generator(device=dev).manual_seed(seed * 100_003 + c0)
+        rows = torch.nn.functional.normalize(torch.randn(chunk, 256, device=dev, generator=g), dim=1)
+        s0, s1 = max(a, lo), min(b, hi)
+        out[s0 - lo:s1 - lo] = rows[s0 - a:s1 - a]
+        c0 += 1
+    if lo == 0:
+        out[0] = 0
+    return out
+
+
+def _sharded_catalog(N, U, rank, world, dev, seed):
+    """(index over this rank's contiguous shard, users, targets): the SAME catalog, users and targets for every
+    world size. Targets are planted so Recall@10 is ~0.6-0.7 (the reference's reported regime)."""
+    from mrm_b200 import retrieval
+    from mrm_b200.sharding import shard_bounds
+    first, rows = shard_bounds(N + 1, world, rank)
+    shard = _catalog_rows(first, first + rows, dev, seed)
+    index = retrieval.CatalogIndex.from_shard(shard, first, N + 1, device=dev) if world > 1 else retrieval.CatalogIndex(shard, device=dev)
+    gu = torch.Generator(device=dev).manual_seed(seed + 99)
+    targets = torch.randint(1, N + 1, (U,), device=dev, generator=gu)
+    noise = torch.randn(U, 256, device=dev, generator=gu)
+    # the planted row may live on another rank: every rank contributes the target rows it owns
+    trow = torch.zeros(U, 256, device=dev)
+    mine = (targets >= first) & (targets < first + rows)
+    trow[mine] = shard[targets[mine] - first]
+    if world > 1:
+        dist.all_reduce(trow, op=dist.ReduceOp.SUM)
+    users = torch.nn.functional.normalize(trow + 3.3 / 16.0 * noise, dim=1)
+    return index, users, targets
+
+
+def bench_indexing(eng, rank, world, dev, peaks):
+    """Catalog indexing (src/evaluate_metrics.py:24-104) of the c3 catalog's 1M items, item list split over the
+    ranks: item tower (eval) -> NaN->0 -> renormalise -> scatter by id into the dense fp32 table + bf16 copy."""
+    from mrm_b200.evaluate_metrics import index_catalog_device
+    N = C3["items"]
+    per = (N + world - 1) // world
+    lo, hi = min(rank * per, N), min(N, (rank + 1) * per)
+    n = hi - lo
+    g = torch.Generator(device=dev).manual_seed(55 + rank)
+    feats = {k: torch.randn(n, 128, device=dev, generator=g)
+             for k in ("target_audio", "target_image", "target_input_ids", "target_tabular")}
+    ids = torch.arange(lo + 1, hi + 1, device=dev)
+    ids = ids[torch.randperm(n, device=dev, generator=g)]
+
+    class _M:                      # the functions only need .engine / .eval()
+        engine = eng
+
+        def eval(self):
+            return self
+
+    table = torch.zeros(N + 1, 256, device=dev)
+    table16 = torch.zeros(N + 1, 256, device=dev, dtype=torch.bfloat16)
+    m = _M()
+    for _ in range(2):
+        index_catalog_device(m, feats, ids, N + 1, out=(table, table16))
+    ms = _timed(lambda: index_catalog_device(m, feats, ids, N + 1, out=(table, table16)), 5, dev, world)
+    bytes_alg = n * (4 * 128 * 4 + 256 * 4)                      # 2 KB of features in, 1 KB of embedding out
+    bytes_moved = n * (2048 + 1024 + 1024 + 1024 + 1024 + 1024 + 1024 + 1536)
+    gbs = bytes_alg / (ms * 1e-3) / 1e9
+    return {"workload": f"f2: catalog indexing, {N} items over {world} GPU(s) ({n} per rank), eval-mode item tower + "
+                        "NaN->0 + renormalise + scatter by id (fp32 table + bf16 copy)",
+            "ms_per_pass": ms, "items_per_s": N / (ms * 1e-3),
+            "roofline": {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"],
+                         "algorithmic_bytes_per_item": 3072, "moved_bytes_per_item": bytes_moved // max(n, 1),
+                         "moved_gbs": bytes_moved / (ms * 1e-3) / 1e9},
+            "rows_nonzero": int((table.abs().sum(1) > 0).sum().item()) if world == 1 else None}
+
+
+def _fp64_canonical_topk(users, table, K, chunk=32):
+    """Checker (plain torch on the GPU): fp64 scores rounded once to fp32, column 0 masked, stable descending sort
+    = the canonical order (score descending, item index ascending)."""
+    idx, val = [], []
+    t64 = table.double()
+    for s0 in range(0, users.shape[0], chunk):
+        sc = (users[s0:s0 + chunk].double() @ t64.t()).float()
+        sc[:, 0] = float("-inf")
+        v, i = torch.sort(sc, dim=1, descending=True, stable=True)
+        idx.append(i[:, :K].clone())
+        val.append(v[:, :K].clone())
+    return torch.cat(idx), torch.cat(val)
+
+
 def bench_retrieval(eng, rank, world, dev, peaks):
-    """10k users x 1M items, top-100 + Recall/NDCG; the catalog is sharded over the ranks."""
+    """10k users x 1M items, top-100 + Recall/NDCG; ONE seeded catalog for every world size, rows sharded
+    contiguously over the ranks."""
     from mrm_b200 import retrieval
     U, N, K = C3["users"], C3["items"], C3["k"]
-    rows = (N + 1 + world - 1) // world
-    first = rank * rows
-    n_local = max(0, min(N + 1, first + rows) - first)
-    g = torch.Generator(device=dev).manual_seed(1234 + rank)
-    shard = torch.nn.functional.normalize(torch.randn(n_local, 256, device=dev, generator=g), dim=1)
-    if rank == 0:
-        shard[0] = 0
-    index = retrieval.CatalogIndex(shard, device=dev)
-    index.item_base, index.vocab_size = first, N + 1
-    gu = torch.Generator(device=dev).manual_seed(99)
-    targets = torch.randint(1, n_local, (U,), device=dev, generator=gu)
-    users = torch.nn.functional.normalize(shard[targets] + 3.3 / 16.0 * torch.randn(U, 256, device=dev, generator=gu),
-                                          dim=1)
-    targets = targets + first
-    if world > 1:
-        dist.broadcast(users, 0)
-        dist.broadcast(targets, 0)
+    index, users, targets = _sharded_catalog(N, U, rank, world, dev, seed=1234)
     host_users = users.cpu().pin_memory()
     host_targets = targets.cpu().pin_memory()
     kl = [10, 20, 50, 100]
@@ -374,20 +691,19 @@ def bench_retrieval(eng, rank, world, dev, peaks):
         m = retrieval.metrics_from_embeddings(users, targets, index, kl)
     torch.cuda.synchronize()
     iters = 5
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    e0.record()
-    nfb = 0
-    for _ in range(iters):
-        if world > 1:    # the whole sharded pass: per-shard candidates, all-gather, merge + certificate
-            idx, score = retrieval.sharded_topk(users, index, K)
-        else:
-            idx, score, nfb = retrieval.retrieve_topk(users, index, K, exact_fallback=False)
-    e1.record()
-    torch.cuda.synchronize()
-    ms = torch.tensor([e0.elapsed_time(e1) / iters], device=dev)
+    flags = torch.zeros(U, device=dev, dtype=torch.int32)
+    res = {}
+
+    def one_pass():
+        if world > 1:    # the whole sharded pass: per-shard candidates, exchange, merge + certificate (+ fallback)
+            res["idx"], res["score"] = retrieval.sharded_topk(users, index, K)
+        else:            # certificate flags are written by every pass and read AFTER the timed region
+            res["idx"], res["score"], _ = retrieval.retrieve_topk(users, index, K, exact_fallback=False, flags_out=flags)
+
+    ms = _timed(one_pass, iters, dev, world)
+    nfb = int(flags.sum().item()) if world == 1 else int(getattr(retrieval, "last_fallback_users", 0))
+    if world == 1 and nfb:    # the timed pass left uncertified users: finish them exactly (untimed) for the checks below
+        res["idx"], res["score"], _ = retrieval.retrieve_topk(users, index, K)
     # e2e: host user embeddings -> device, retrieval, merge, metrics -> host
     t0 = time.perf_counter()
     for _ in range(iters):
@@ -396,35 +712,70 @@ def bench_retrieval(eng, rank, world, dev, peaks):
     torch.cuda.synchronize()
     e2e = torch.tensor([(time.perf_counter() - t0) / iters], device=dev)
     if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         dist.all_reduce(e2e, op=dist.ReduceOp.MAX)
+
+    # ---- parity on the bench data ----------------------------------------------------------
+    # (a) rank 0 holds the whole catalog once more and checks a 512-user sample against an fp64 canonical sort;
+    # (b) for world > 1 the sharded result must EQUAL the single-GPU result on the same catalog (independent of G).
+    parity = None
+    if rank == 0:
+        full = _catalog_rows(0, N + 1, dev, 1234) if world > 1 else index.table
+        sel = torch.arange(0, U, max(1, U // 512), device=dev)[:512]
+        ri, rv = _fp64_canonical_topk(users[sel], full, K)
+        got_i, got_s = res["idx"][sel].long(), res["score"][sel]
+        mism = int((got_i != ri).sum().item())
+        parity = {"what": f"top-{K} of {sel.numel()} sampled users vs fp64 canonical sort (torch, GPU) of the whole catalog",
+                  "index_mismatches": mism, "score_max_abs_err": (got_s - rv).abs().max().item(),
+                  "ok": bool(mism == 0)}
+        if world > 1:
+            single = retrieval.CatalogIndex(full, device=dev)
+            si, ss, _ = retrieval.retrieve_topk(users, single, K)
+            parity["sharded_equals_single_gpu"] = bool(torch.equal(si, res["idx"]) and torch.equal(ss, res["score"]))
+            parity["ok"] = parity["ok"] and parity["sharded_equals_single_gpu"]
+            del single, si, ss
+        del full
+        from oracle import two_tower_oracle as oracle
+        om = oracle.rank_metrics(res["idx"].cpu().long(), targets.cpu(), kl)
+        parity["metrics_equal_oracle_on_same_lists"] = bool(all(m[k] == om[k].mean().item() for k in m))
+        parity["ok"] = parity["ok"] and parity["metrics_equal_oracle_on_same_lists"]
+    torch.cuda.empty_cache()
+
     # ---- the same pass with the user embeddings produced by the CUDA user tower (eval mode) from HOST
-    # histories (L = 50, the reference default): H2D ids -> SASRec forward -> retrieval -> merge -> metrics
+    # histories (L = 50, the reference default): H2D ids -> SASRec forward -> retrieval -> merge -> metrics.
+    # With several ranks the USERS are split over the ranks for the tower and the 10 MB of embeddings all-gathered.
     from mrm_b200 import synthetic
     from mrm_b200.engine import TwoTowerEngine
-    Lh, UB = C3["hist_len"], 2000
+    Lh = C3["hist_len"]
     tcfg = synthetic.TwoTowerConfig(vocab_size=4096, max_seq_len=Lh, dropout=0.0)   # small ID table: ids are synthetic
     teng = TwoTowerEngine(tcfg, dev)
     teng.load_state_dict(synthetic.make_state_dict(tcfg, seed=0))
     hb = synthetic.make_batch(tcfg, U, seed=7, full_length=True)
-    h_ids, h_mask = hb["history_ids"].pin_memory(), hb["history_mask"].pin_memory()
-    h_g, h_c = hb["user_gender"].pin_memory(), hb["user_country"].pin_memory()
-    uemb = torch.empty(U, 256, device=dev)
+    per = (U + world - 1) // world
+    u0, u1 = min(rank * per, U), min(U, (rank + 1) * per)
+    UB = min(2000, per)
+    h_ids, h_mask = hb["history_ids"][u0:u1].pin_memory(), hb["history_mask"][u0:u1].pin_memory()
+    h_g, h_c = hb["user_gender"][u0:u1].pin_memory(), hb["user_country"][u0:u1].pin_memory()
+    uemb = torch.zeros(world * per, 256, device=dev)
 
     def tower_pass():
-        ws = teng.workspace(UB, Lh)
         if not teng.shadow_valid:
             teng.refresh_shadow()
-        for s0 in range(0, U, UB):
-            sl = slice(s0, s0 + UB)
+        for s0 in range(0, u1 - u0, UB):
+            n = min(UB, u1 - u0 - s0)
+            sl = slice(s0, s0 + n)
+            ws = teng.workspace(n, Lh)
             u = teng.user_forward(ws, h_ids[sl].to(dev, non_blocking=True), h_mask[sl].to(dev, non_blocking=True),
                                   h_g[sl].to(dev, non_blocking=True), h_c[sl].to(dev, non_blocking=True), training=False)
-            uemb[sl].copy_(u)
-        return retrieval.metrics_from_embeddings(uemb, host_targets.to(dev, non_blocking=True), index, kl)
+            uemb[u0 + s0:u0 + s0 + n].copy_(u)
+        if world > 1:
+            dist.all_gather_into_tensor(uemb, uemb[rank * per:(rank + 1) * per].clone())
+        return retrieval.metrics_from_embeddings(uemb[:U], host_targets.to(dev, non_blocking=True), index, kl)
 
     for _ in range(2):
         tower_pass()
     torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
     t0 = time.perf_counter()
     for _ in range(iters):
         tower_pass()
@@ -432,6 +783,7 @@ def bench_retrieval(eng, rank, world, dev, peaks):
     e2e_tower = torch.tensor([(time.perf_counter() - t0) / iters], device=dev)
     if world > 1:
         dist.all_reduce(e2e_tower, op=dist.ReduceOp.MAX)
+    del teng
 
     # single-user recommendation latency (src/inference.py:283-306): one user, 50 history items excluded, top-10
     rec_ms = None
@@ -451,21 +803,22 @@ def bench_retrieval(eng, rank, world, dev, peaks):
 
     flops = 2.0 * U * (N + 1) * 256 / world
     peak_tf = peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops"))
-    return {"metric": "top-100 retrieval users/sec @1M items", "recommend_1user_ms": rec_ms, "users_per_s": U / (ms.item() * 1e-3),
-            "ms_per_pass": ms.item(), "e2e_users_per_s": U / e2e.item(),
+    return {"metric": "top-100 retrieval users/sec @1M items", "recommend_1user_ms": rec_ms, "users_per_s": U / (ms * 1e-3),
+            "ms_per_pass": ms, "e2e_users_per_s": U / e2e.item(),
             "e2e_users_per_s_incl_user_tower": U / e2e_tower.item(),
-            "scoring_tflops_per_gpu": flops / (ms.item() * 1e-3) / 1e12,
-            "roofline_frac_tensor": flops / (ms.item() * 1e-3) / 1e12 / peak_tf,
+            "scoring_tflops_per_gpu": flops / (ms * 1e-3) / 1e12,
+            "roofline_frac_tensor": flops / (ms * 1e-3) / 1e12 / peak_tf,
             "config": {"workload": f"c3: {U} users x {N} items, top-{K}, Recall/NDCG@10/20/50/100, catalog sharded "
-                                   f"over {world} GPU(s)",
-                       "users_per_s": "device-resident user embeddings: scoring + top-K + exact re-score (events)"
-                                      + ("; sharded: per-shard pass, all-gather, merge (retrieval.sharded_topk: candidate "
-                                         "lists + bounds + certificate from 4 shards, per-shard exact top-K below)"
-                                         if world > 1 else ""),
+                                   f"over {world} GPU(s); the same seeded catalog, users and targets for every world size",
+                       "users_per_s": "device-resident user embeddings: scoring + top-K + exact re-score + certificate "
+                                      "(events)" + ("; sharded: per-shard pass, exchange, merge, certificate, fallback "
+                                                    "(retrieval.sharded_topk)" if world > 1 else
+                                                    "; certificate flags read after the timed region"),
                        "e2e_users_per_s": "host user embeddings -> device, retrieval, cross-shard merge, metrics -> host",
-                       "e2e_users_per_s_incl_user_tower": f"host histories (L={Lh}) -> CUDA user tower (eval) -> same",
+                       "e2e_users_per_s_incl_user_tower": f"host histories (L={Lh}) -> CUDA user tower (eval, users split "
+                                                          f"over the ranks, embeddings all-gathered) -> same",
                        "kprime": 256},
-            "recall_at_10": m["Recall@10"], "fallback_users": int(nfb)}
+            "recall_at_10": m["Recall@10"], "fallback_users": nfb, "parity": parity}
 
 
 def main():
@@ -476,6 +829,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--skip-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     ap.add_argument("--skip-retrieval", action="store_true", help="skip the c3 retrieval section (A/B timing runs)")
+    ap.add_argument("--skip-c45", action="store_true", help="skip the c4 / c5 blocks of multi-GPU runs")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -178,6 +178,14 @@ int tt_gather_cat_bwd(const float* dcat, const int32_t* last_idx, const int64_t*
 int tt_concat4_bf16(const float* audio, const float* visual, const float* text, const float* tabular, int B, int m,
                     void* out_bf16, void* stream);
 
+/* Catalog-indexing tail (src/evaluate_metrics.py:70-102): y fp32 [R, 256] = output of the item tower's last Linear
+ * -> LayerNorm (item_tower.py:128) -> F.normalize eps 1e-12 (two_tower.py:168) -> NaN -> 0 (:79-81) ->
+ * F.normalize eps 1e-8 (:85) -> table[ids[r], :] (fp32, the reference's cache layout) and, when table_bf16 is
+ * non-NULL, the bf16 copy the scoring kernel reads. ids must be distinct (the reference indexes unique_df);
+ * ids outside [0, V) are skipped. Rows not listed are left untouched (the caller zero-fills the table once). */
+int tt_index_rows(const float* y, int R, const float* ln_w, const float* ln_b, const int64_t* ids, int64_t V,
+                  float* table, void* table_bf16, void* stream);
+
 /* BatchNorm1d + ReLU + Dropout on fp32 [B, C] -> bf16 (src/models/item_tower.py:124-126).
  * training != 0: batch statistics, running stats / num_batches_tracked updated (momentum 0.1,
  * unbiased variance); else running statistics. */
@@ -257,6 +265,11 @@ int tt_infonce_rows(float* S, int R, int C, int ld, const int64_t* uid_rows, con
                     float* row_lse, float* pos_logit, void* stream);
 int tt_infonce_grad(const float* S, int R, int C, int ld, const float* row_lse, const float* col_lse, int pos0,
                     float coef, void* dS_bf16, int ld_d, void* stream);
+/* In-batch Recall@k of `evaluate` (src/train.py:95-103) on the logits of one batch: acc[0] += #rows whose positive
+ * (column pos0 + i) has fewer than k entries ahead of it in the canonical order (logit descending, column
+ * ascending), acc[1] += R. acc is a device float[2] the caller zeroes once per evaluation and all-reduces (SUM)
+ * over ranks at the end (:106-109). */
+int tt_inbatch_recall(const float* S, int R, int C, int ld, int pos0, int k, float* acc, void* stream);
 int tt_infonce_loss(const float* lse_a, const float* pos_a, const float* lse_b, const float* pos_b, int R, float coef,
                     float* loss, void* stream);
 

@@ -102,9 +102,52 @@ __global__ void __launch_bounds__(256) infonce_loss_kernel(const float* lse_a, c
   if (threadIdx.x == 0) *loss = s[0] * coef;
 }
 
+// In-batch Recall@k of `evaluate` (src/train.py:95-103): row i hits when its positive column is among the k
+// best logits of the row. One warp per row counts the entries that precede the positive in the canonical order
+// (logit descending, column ascending) — the rank of the positive — so no top-k list is ever formed.
+// acc[0] += hits, acc[1] += rows (integers held in fp32: exact below 2^24, summation order irrelevant).
+__global__ void __launch_bounds__(256) inbatch_recall_kernel(const float* __restrict__ S, int R, int C, int ld, int pos0,
+                                                             int k, float* __restrict__ acc) {
+  pdl_launch_dependents();
+  pdl_wait();
+  __shared__ int s_hits;
+  if (threadIdx.x == 0) s_hits = 0;
+  __syncthreads();
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (row < R) {
+    const float* s = S + static_cast<size_t>(row) * ld;
+    const int pos = pos0 + row;
+    const float d = s[pos];
+    int better = 0;
+    for (int j = lane; j < C; j += 32) {
+      const float x = s[j];
+      better += (x > d) || (x == d && j < pos);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) better += __shfl_xor_sync(0xffffffffu, better, o);
+    if (lane == 0 && better < k) atomicAdd(&s_hits, 1);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (s_hits) atomicAdd(acc, static_cast<float>(s_hits));
+    const int first = (blockIdx.x * blockDim.x) >> 5;
+    const int rows_here = min(R - first, static_cast<int>(blockDim.x >> 5));
+    if (rows_here > 0) atomicAdd(acc + 1, static_cast<float>(rows_here));
+  }
+}
+
 }  // namespace tt
 
 using namespace tt;
+
+extern "C" int tt_inbatch_recall(const float* S, int R, int C, int ld, int pos0, int k, float* acc, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  TT_REQUIRE(S && acc && R > 0 && C > 0 && ld >= C && k > 0, "tt_inbatch_recall: bad arguments");
+  TT_REQUIRE(pos0 >= 0 && pos0 + R <= C, "tt_inbatch_recall: positives [%d, %d) outside %d columns", pos0, pos0 + R, C);
+  TT_CHECK_CUDA(launch_k(inbatch_recall_kernel, dim3((R * 32 + 255) / 256), dim3(256), 0, stream, S, R, C, ld, pos0, k, acc));
+  TT_LAUNCH_CHECK();
+  return TT_OK;
+}
 
 extern "C" int tt_infonce_rows(float* S, int R, int C, int ld, const int64_t* uid_rows, const int64_t* uid_cols,
                                int pos0, float* row_lse, float* pos_logit, void* stream_) {

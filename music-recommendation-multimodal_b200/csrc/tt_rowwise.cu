@@ -719,6 +719,54 @@ __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, float
   }
 }
 
+// --------------------------------------------------------------------------------------------
+// Catalog indexing tail (src/evaluate_metrics.py:70-102 after the item tower's last Linear): LayerNorm
+// (item_tower.py:128) -> F.normalize eps 1e-12 (two_tower.py:168) -> NaN -> 0 (:79-81) -> F.normalize eps 1e-8
+// (:85) -> row `ids[r]` of the dense (V, 256) cache table, fp32 and the bf16 copy retrieval scores with.
+// The reference applies nan_to_num to a whole batch when any element is NaN; on finite elements that is the
+// identity, and +-inf cannot survive the first normalisation (inf / inf = NaN), so the per-element rule here
+// is the same function. One warp per item: 1 KB in, 1 KB + 512 B out.
+// --------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kRowThreads) index_rows_kernel(const float* __restrict__ y, int R,
+                                                                 const float* __restrict__ ln_w,
+                                                                 const float* __restrict__ ln_b,
+                                                                 const int64_t* __restrict__ ids, int64_t V,
+                                                                 float* __restrict__ table,
+                                                                 __nv_bfloat16* __restrict__ table_bf16) {
+  pdl_launch_dependents();
+  pdl_wait();
+  constexpr int NV = 2, E = 8, W = 256;
+  const int lane = threadIdx.x & 31;
+  const int warps_total = (gridDim.x * blockDim.x) >> 5;
+  float w[E], b[E];
+  load_row<NV>(ln_w, lane, w);
+  load_row<NV>(ln_b, lane, b);
+  for (int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < R; row += warps_total) {
+    const int64_t id = ids[row];
+    if (id < 0 || id >= V) continue;             // out-of-table ids are dropped (the reference would raise)
+    float v[E];
+    load_row<NV>(y + static_cast<size_t>(row) * W, lane, v);
+    float mean, rstd;
+    ln_stats<NV>(v, 1e-5f, mean, rstd);
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < E; ++i) { v[i] = (v[i] - mean) * rstd * w[i] + b[i]; s += v[i] * v[i]; }
+    float inv = 1.f / fmaxf(sqrtf(warp_sum(s)), 1e-12f);
+    s = 0.f;
+#pragma unroll
+    for (int i = 0; i < E; ++i) {
+      v[i] *= inv;
+      if (v[i] != v[i]) v[i] = 0.f;
+      s += v[i] * v[i];
+    }
+    inv = 1.f / fmaxf(sqrtf(warp_sum(s)), 1e-8f);
+#pragma unroll
+    for (int i = 0; i < E; ++i) v[i] *= inv;
+    store_row<NV>(table + static_cast<size_t>(id) * W, lane, v);
+    if (table_bf16) store_row_bf16<NV>(table_bf16 + static_cast<size_t>(id) * W, lane, v);
+  }
+}
+
 __global__ void increment_kernel(int64_t* a, uint64_t* b) {
   pdl_launch_dependents();
   pdl_wait();
@@ -940,6 +988,15 @@ extern "C" int tt_adamw_step(float* p, float* g, float* m, float* v, int64_t n, 
   int grid = static_cast<int>((n4 + 255) / 256);
   if (grid > num_sms() * 16) grid = num_sms() * 16;
   TT_CHECK_CUDA(launch_k(adamw_kernel, dim3(grid), dim3(256), 0, stream, p, g, m, v, n4, lr, beta1, beta2, eps, weight_decay, step_dev, static_cast<__nv_bfloat16*>(shadow_bf16), static_cast<size_t>(shadow_begin / 4), static_cast<size_t>(shadow_end / 4), zero_grad));
+  TT_LAUNCH_CHECK();
+  return TT_OK;
+}
+
+extern "C" int tt_index_rows(const float* y, int R, const float* ln_w, const float* ln_b, const int64_t* ids,
+                             int64_t V, float* table, void* table_bf16, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  TT_REQUIRE(y && ln_w && ln_b && ids && table && R > 0 && V > 0, "tt_index_rows: bad arguments");
+  TT_CHECK_CUDA(launch_k(index_rows_kernel, dim3(row_grid(R)), dim3(kRowThreads), 0, stream, y, R, ln_w, ln_b, ids, V, table, static_cast<__nv_bfloat16*>(table_bf16)));
   TT_LAUNCH_CHECK();
   return TT_OK;
 }

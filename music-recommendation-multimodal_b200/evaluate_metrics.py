@@ -18,35 +18,58 @@ from .retrieval import CatalogIndex, metrics_from_embeddings
 logger = logging.getLogger(__name__)
 
 
+def _shard_slice(n_all: int, shard):
+    if shard is None:
+        return 0, n_all
+    r, w = shard
+    per = (n_all + w - 1) // w
+    return min(r * per, n_all), min(n_all, (r + 1) * per)
+
+
+def index_catalog_device(model, item_features: Dict[str, torch.Tensor], item_ids: torch.Tensor, vocab_size: int,
+                         batch_size: int = 16384, shard=None, out=None):
+    """Catalog indexing (src/evaluate_metrics.py:24-104) entirely on the device: returns (table fp32 (V, 256),
+    table bf16 (V, 256)) on the model's GPU — the dense cache in the reference's layout (row i = embedding of item
+    id i, row 0 and unlisted ids zero) and the copy the scoring kernel reads. Host features are moved batch by
+    batch (pinned or not); device features are used in place. ``shard=(rank, world)``: only the rank-th contiguous
+    slice of the ITEM LIST is indexed (eval-mode BatchNorm has no cross-row dependency); the other
+    rows stay zero, so the full table is the sum over ranks. ``out=(table, table_bf16)`` reuses caller buffers."""
+    eng = model.engine
+    model.eval()
+    if hasattr(model, "_sync_shadow"):
+        model._sync_shadow()
+    dev, D = eng.device, eng.cfg.embedding_dim
+    if out is None:
+        table = torch.zeros(vocab_size, D, device=dev)
+        table_bf16 = torch.zeros(vocab_size, D, device=dev, dtype=torch.bfloat16)
+    else:
+        table, table_bf16 = out
+    lo, hi = _shard_slice(item_ids.shape[0], shard)
+    keys = ("target_audio", "target_image", "target_input_ids", "target_tabular")
+    on_dev = all(item_features[k].is_cuda for k in keys) and item_ids.is_cuda
+    # host inputs: stream them in chunks so the device never holds more than one chunk of features
+    chunk = (hi - lo) if on_dev else max(batch_size, 1 << 18)
+    for s0 in range(lo, hi, max(chunk, 1)):
+        s1 = min(hi, s0 + chunk)
+        feats = {k: item_features[k][s0:s1].to(dev, dtype=torch.float32, non_blocking=True).contiguous() for k in keys}
+        ids = item_ids[s0:s1].to(dev, dtype=torch.long, non_blocking=True).contiguous()
+        eng.index_items(feats, ids, table, table_bf16, batch_size=batch_size)
+    return table, table_bf16
+
+
+def build_catalog_index(model, item_features, item_ids, vocab_size: int, batch_size: int = 16384) -> CatalogIndex:
+    """Index the catalog and hand the device tables straight to retrieval (no host round trip, no re-cast)."""
+    table, table_bf16 = index_catalog_device(model, item_features, item_ids, vocab_size, batch_size)
+    return CatalogIndex.from_device_tables(table, table_bf16)
+
+
 def compute_all_item_embeddings(model, item_features: Dict[str, torch.Tensor], item_ids: torch.Tensor,
                                 batch_size: int, device, vocab_size: int, shard=None):
-    """Catalog indexing (src/evaluate_metrics.py:24-104) on precomputed modality embeddings:
-    item tower in eval mode, NaN -> 0, re-normalise with eps 1e-8, scatter into the dense table.
-
-    ``shard=(rank, world)`` indexes only the rank-th contiguous slice of the item list (eval-mode BatchNorm has
-    no cross-row dependency, so the catalog splits freely over GPUs); rows of other slices stay
-    zero, so the full table is the SUM over ranks (`dist.all_reduce`) or each rank keeps its slice."""
-    model.eval()
-    D = model.engine.cfg.embedding_dim
-    dense = torch.zeros(vocab_size, D)
-    n_all = item_ids.shape[0]
-    lo, n = 0, n_all
-    if shard is not None:
-        r, w = shard
-        per = (n_all + w - 1) // w
-        lo, n = min(r * per, n_all), min(n_all, (r + 1) * per)
-    with torch.no_grad():
-        for s in range(lo, n, batch_size):
-            sl = slice(s, min(n, s + batch_size))
-            emb = model.get_item_embedding(images=item_features["target_image"][sl], audio=item_features["target_audio"][sl],
-                                           input_ids=item_features["target_input_ids"][sl], attention_mask=None,
-                                           tabular=item_features["target_tabular"][sl])
-            if torch.isnan(emb).any():
-                logger.warning(f"NaNs detected in model output for batch {s // batch_size}")
-                emb = torch.nan_to_num(emb, nan=0.0)
-            emb = torch.nn.functional.normalize(emb, p=2, dim=1, eps=1e-8)
-            dense[item_ids[sl].long()] = emb.cpu()
-    return dense, vocab_size
+    """The reference's return contract (src/evaluate_metrics.py:24-104): (dense CPU FloatTensor (V, 256),
+    vocab_size) — what `main` saves as {'item_embeddings', 'vocab_size'} (:323-326). The work is
+    `index_catalog_device`; the table crosses to the host once."""
+    table, _ = index_catalog_device(model, item_features, item_ids, vocab_size, max(batch_size, 1), shard)
+    return table.cpu(), vocab_size
 
 
 def calculate_metrics_global(model, val_loader, item_embeddings, device, k_list: Sequence[int] = (10, 20),

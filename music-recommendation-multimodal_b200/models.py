@@ -90,7 +90,7 @@ class MultimodalItemEncoder(_ParamTree):
     def forward(self, images, audio, input_ids, attention_mask, tabular):
         eng = self._eng
         B = audio.shape[0]
-        ws = eng.workspace(B, eng.cfg.max_seq_len)
+        ws = eng.item_workspace(B)
         if not eng.shadow_valid:
             eng.refresh_shadow()
         f = [t.float().contiguous() for t in (audio, images, input_ids, tabular)]
@@ -222,7 +222,7 @@ class TwoTowerModel(nn.Module):
         """Normalised item embedding (src/models/two_tower.py:159-168)."""
         eng = self.engine
         f = [t.to(eng.device).float().contiguous() for t in (audio, images, input_ids, tabular)]
-        ws = eng.workspace(f[0].shape[0], eng.cfg.max_seq_len)
+        ws = eng.item_workspace(f[0].shape[0])
         self._sync_shadow()
         if not eng.shadow_valid:
             eng.refresh_shadow()

@@ -275,6 +275,26 @@ def infonce_loss(lse_a, pos_a, lse_b, pos_b, coef, loss) -> None:
                                 lse_a.numel(), coef, loss.data_ptr(), _stream()), "tt_infonce_loss")
 
 
+def inbatch_recall(S, pos0: int, k: int, acc) -> None:
+    """acc[0] += hits, acc[1] += rows of the in-batch Recall@k on logits S (tt_inbatch_recall)."""
+    _require_cuda(S, acc)
+    assert S.dtype == torch.float32 and S.stride(1) == 1 and acc.dtype == torch.float32 and acc.numel() == 2
+    check(lib().tt_inbatch_recall(S.data_ptr(), S.shape[0], S.shape[1], S.stride(0), pos0, k, acc.data_ptr(),
+                                  _stream()), "tt_inbatch_recall")
+
+
+def index_rows(y, ln_w, ln_b, ids, table, table_bf16=None) -> None:
+    """LayerNorm -> normalise -> NaN->0 -> normalise(eps 1e-8) -> table[ids] (tt_index_rows)."""
+    _require_cuda(y, ln_w, ln_b, ids, table, table_bf16)
+    assert y.dtype == torch.float32 and y.is_contiguous() and y.shape[1] == 256
+    assert ids.dtype == torch.int64 and ids.is_contiguous() and ids.numel() == y.shape[0]
+    assert table.dtype == torch.float32 and table.is_contiguous() and table.shape[1] == 256
+    if table_bf16 is not None:
+        assert table_bf16.dtype == torch.bfloat16 and table_bf16.is_contiguous() and table_bf16.shape == table.shape
+    check(lib().tt_index_rows(y.data_ptr(), y.shape[0], ln_w.data_ptr(), ln_b.data_ptr(), ids.data_ptr(),
+                              table.shape[0], table.data_ptr(), _ptr(table_bf16), _stream()), "tt_index_rows")
+
+
 # --------------------------------------------------------------------------------------
 # last-layer specialisation (one query row per sequence)
 # --------------------------------------------------------------------------------------

@@ -37,10 +37,7 @@ class CatalogIndex:
         assert self.table.shape[1] == 256
         self.table_bf16 = torch.empty(self.table.shape, device=dev, dtype=torch.bfloat16)
         ops.cast_bf16(self.table.view(-1), self.table_bf16.view(-1))
-        # terms of the error bound |bf16-path score - exact score| that depend on the items only
-        t16 = self.table_bf16.float()
-        self.de_max = (t16 - self.table).norm(dim=1).max().item()
-        self.ne_max = t16.norm(dim=1).max().item()
+        self._error_terms()
         self._scratch: Dict[Tuple[int, int], Dict[str, torch.Tensor]] = {}
         self._plans: Dict[Tuple[int, int], TopkPlan] = {}
 
@@ -51,6 +48,28 @@ class CatalogIndex:
         self = cls(shard_rows, device=device)
         self.item_base, self.vocab_size, self.is_sharded = first_row, vocab_size, True
         return self
+
+    @classmethod
+    def from_device_tables(cls, table: torch.Tensor, table_bf16: torch.Tensor) -> "CatalogIndex":
+        """Adopt device tables produced by catalog indexing (fp32 cache + the bf16 copy, same shape): no copy."""
+        assert table.is_cuda and table.dtype == torch.float32 and table.is_contiguous() and table.shape[1] == 256
+        assert table_bf16.dtype == torch.bfloat16 and table_bf16.shape == table.shape and table_bf16.is_contiguous()
+        self = cls.__new__(cls)
+        self.vocab_size, self.item_base, self.is_sharded, self._group_checked = table.shape[0], 0, False, set()
+        self.table, self.table_bf16 = table, table_bf16
+        self._error_terms()
+        self._scratch, self._plans = {}, {}
+        return self
+
+    def _error_terms(self) -> None:
+        """terms of the bound |bf16-path score - exact score| that depend on the items only (chunked: the
+        fp32 copy of a 10 M-row bf16 table would be 10 GB)"""
+        de, ne = 0.0, 0.0
+        for s0 in range(0, self.table.shape[0], 1 << 20):
+            t16 = self.table_bf16[s0:s0 + (1 << 20)].float()
+            de = max(de, (t16 - self.table[s0:s0 + (1 << 20)]).norm(dim=1).max().item())
+            ne = max(ne, t16.norm(dim=1).max().item())
+        self.de_max, self.ne_max = de, ne
 
     @property
     def num_rows(self) -> int:
@@ -100,12 +119,14 @@ class CatalogIndex:
 
 
 def retrieve_topk(user_emb: torch.Tensor, index: CatalogIndex, K: int, kprime: int = 256,
-                  mask_item0: bool = True, exact_fallback: bool = True):
+                  mask_item0: bool = True, exact_fallback: bool = True, flags_out: Optional[torch.Tensor] = None):
     """Top-K items of this shard for every user, canonical order.
 
     Returns (idx int32 (U, K) global item ids, score fp32 (U, K), n_fallback). Scores are the
     exact fp32 dot products (fp64-accumulated, rounded once). Users whose exactness certificate
-    fails are recomputed by brute force (``n_fallback`` of them; needs one host sync)."""
+    fails are recomputed by brute force (``n_fallback`` of them; needs one host sync).
+    ``exact_fallback=False`` skips that read-back: the result is only certified for users whose entry of
+    ``flags_out`` (int32 (U,), filled by the pass) is 0 — the caller must look at it."""
     assert user_emb.is_cuda and user_emb.dtype == torch.float32 and user_emb.shape[1] == 256
     user_emb = user_emb.contiguous()
     U = user_emb.shape[0]
@@ -114,7 +135,8 @@ def retrieve_topk(user_emb: torch.Tensor, index: CatalogIndex, K: int, kprime: i
     dev = user_emb.device
     out_idx = torch.empty(U, K, device=dev, dtype=torch.int32)
     out_score = torch.empty(U, K, device=dev, dtype=torch.float32)
-    flags = torch.empty(U, device=dev, dtype=torch.int32)
+    flags = torch.empty(U, device=dev, dtype=torch.int32) if flags_out is None else flags_out
+    assert flags.dtype == torch.int32 and flags.numel() == U and flags.is_cuda
     check(lib().tt_topk_finalize(ctypes.byref(plan), sc["cand"].data_ptr(), sc["cnt"].data_ptr(),
                                  sc["thr"].data_ptr(), user_emb.data_ptr(),
                                  index.table.data_ptr(), index.item_base, K, eps, out_idx.data_ptr(),
@@ -174,6 +196,10 @@ def retrieve_candidates(user_emb: torch.Tensor, index: "CatalogIndex", kprime: i
     return out_idx, out_score, bound, flags
 
 
+#: users of the most recent `sharded_topk` call that needed the per-shard exact fallback (bench bookkeeping)
+last_fallback_users = 0
+
+
 def shard_kprime(kprime: int, shards: int) -> int:
     """Candidates per user and shard: 1.5x the even share of the single-GPU budget plus 16 (the number of a
     user's global top-K' items that fall into one shard is binomial), a multiple of 8 in [48, kprime]."""
@@ -226,6 +252,8 @@ def sharded_topk(user_emb: torch.Tensor, index: "CatalogIndex", K: int, kprime: 
         dist.all_gather_into_tensor(all_i, i.contiguous(), group=group)
         return merge_topk(all_s.view(ws, n, K), all_i.view(ws, n, K))
 
+    global last_fallback_users
+    last_fallback_users = 0
     if not bounded or K > ws * shard_kprime(kprime, ws):
         return per_shard_exact(user_emb)
     kps = shard_kprime(kprime, ws)
@@ -248,6 +276,7 @@ def sharded_topk(user_emb: torch.Tensor, index: "CatalogIndex", K: int, kprime: 
     if bool(bad.any().item()):            # identical on every rank: the inputs of the test were all-gathered
         sel = torch.nonzero(bad).flatten()
         n = sel.numel()
+        last_fallback_users = n
         # scratch buffers are cached per user count: pad to a multiple of 256 (repeating the first user) so that
         # a long evaluation with a few uncertified users per batch does not accumulate one scratch set per count
         padded = torch.cat([sel, sel[:1].expand((-n) % 256)])

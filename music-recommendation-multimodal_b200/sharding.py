@@ -68,6 +68,11 @@ class RowShardedTable:
         self.exp_avg_sq = None
         self._saved = None
 
+    def describe(self) -> str:
+        return (f"contiguous row shards ({self.per} rows/rank); per step: all_to_all of counts and token ids, "
+                f"index_select on the owner, all_to_all of {self.dim * 4} B rows back; backward: all_to_all of "
+                f"gradient rows + index_add_ on the owner (torch ops over NCCL)")
+
     def load_full(self, full_table: torch.Tensor) -> None:
         self.weight.copy_(full_table[self.first:self.first + self.rows])
 

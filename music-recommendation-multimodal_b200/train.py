@@ -235,6 +235,23 @@ class TrainStepRunner:
         for fn, _ in self._sequence():
             fn()
 
+    def comm_description(self):
+        """The cross-rank exchanges of one step, in order (what bench.py prints next to the timing)."""
+        if self.world == 1:
+            return []
+        n = self.eng.numel * 4
+        names = {
+            "_comm_lookup": "NCCL all_to_all x3 (token ids -> owner ranks, rows back): row-sharded ID table lookup",
+            "_comm_embeddings": f"NCCL all_gather_into_tensor (user emb | item emb | user id), {self._pack_emb.numel()} B/rank"
+                                if self.gathered else "",
+            "_comm_lse": "NCCL all_gather_into_tensor (row log-sum-exps of both directions), 8 B/sample",
+            "_comm_table_grad": "NCCL all_to_all (gradient rows -> owner ranks)",
+            "_comm_grads": (f"NCCL reduce_scatter_tensor AVG (flat fp32 gradient, {n} B)" if self.shard_opt
+                            else f"NCCL all_reduce AVG (flat fp32 gradient, {n} B)"),
+            "_comm_params": f"NCCL all_gather_into_tensor (updated fp32 parameter shards, {n} B total)",
+        }
+        return [names.get(fn.__name__, fn.__name__) for fn, is_comm in self._sequence() if is_comm]
+
     def _loss_tensor(self) -> torch.Tensor:
         return self.eng.workspace(self.B, self.L)["loss"]
 
@@ -393,23 +410,22 @@ def train_one_epoch(model, dataloader, optimizer, device, epoch, is_main_process
 
 
 def evaluate(model, dataloader, device, k=10):
-    """In-batch Recall@k (src/train.py:78-111): the positive must be among the k best logits of its row
-    under the canonical order; hits/total are summed over ranks when a process group exists."""
+    """In-batch Recall@k (src/train.py:78-111): the positive must be among the k best logits of its row under the
+    canonical order (logit descending, column ascending). Forward in eval mode on the CUDA engine, the rank of the
+    diagonal counted by `tt_inbatch_recall` into a device (hits, total) pair — no top-k list, no per-batch host
+    sync; hits / total are summed over ranks when a process group exists (:106-109) and read back once."""
+    from . import ops
     model.eval()
-    hits = torch.tensor(0.0, device=device)
-    total = torch.tensor(0.0, device=device)
+    eng = model.engine
+    if hasattr(model, "_sync_shadow"):
+        model._sync_shadow()
+    acc = torch.zeros(2, device=eng.device)
     with torch.no_grad():
         for batch in dataloader:
-            b = {kk: v.to(device) for kk, v in batch.items() if isinstance(v, torch.Tensor)}
-            _, logits, _, _ = model(b)
-            n = logits.shape[0]
-            diag = logits.diagonal().unsqueeze(1)
-            col = torch.arange(n, device=logits.device).unsqueeze(0)
-            row = torch.arange(n, device=logits.device).unsqueeze(1)
-            better = (logits > diag) | ((logits == diag) & (col < row))   # rank of the positive, ties by index
-            hits += (better.sum(dim=1) < k).sum()
-            total += n
+            b = model._batch(batch)
+            _, logits, _, _ = eng.forward(b, training=False)
+            ops.inbatch_recall(logits, 0, k, acc)
     if dist.is_available() and dist.is_initialized():
-        dist.all_reduce(hits, op=dist.ReduceOp.SUM)
-        dist.all_reduce(total, op=dist.ReduceOp.SUM)
-    return (hits / total).item() if total > 0 else 0.0
+        dist.all_reduce(acc, op=dist.ReduceOp.SUM)
+    hits, total = acc.tolist()
+    return hits / total if total > 0 else 0.0

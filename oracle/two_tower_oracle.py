@@ -325,12 +325,13 @@ def index_catalog(p: Params, features: Dict[str, torch.Tensor], item_ids: torch.
 # data-parallel step with all-gathered negatives (BASELINE.json configs[3])
 # ----------------------------------------------------------------------------------
 def dp_loss_and_grads(p: Params, batches: Sequence[Dict[str, torch.Tensor]], temperature: float = 0.07,
-                      num_heads: int = 4, dtype: torch.dtype = torch.float64):
+                      num_heads: int = 4, dtype: torch.dtype = torch.float64, tower_grads: bool = True):
     """G data-parallel ranks, rank r holding ``batches[r]``: the towers run per rank (BatchNorm batch statistics
     per rank: the reference wraps the model in plain DDP, no SyncBatchNorm, train.py:300), the normalised
     embeddings and user ids of all ranks are concatenated and ONE symmetric InfoNCE (two_tower.py:106-140) is
-    taken over the global batch. Returns (loss, {param: d loss / d param}, user_emb_all, item_emb_all).
-    The averaged per-rank gradient the DP step applies equals this gradient. Memory stays that of one rank:
+    taken over the global batch. Returns (loss, {param: d loss / d param}, user_emb_all, item_emb_all,
+    d loss / d user_emb_all, d loss / d item_emb_all); ``tower_grads=False`` stops at the embedding gradients
+    (parameter gradients None). The averaged per-rank gradient the DP step applies equals this gradient. Memory stays that of one rank:
     embeddings first without autograd, then one autograd pass per rank seeded with d loss / d embedding."""
     q = {k: (v.clone() if k.endswith(TRAINABLE_SKIP) else v.detach().to(dtype)) for k, v in p.items()}
 
@@ -347,6 +348,8 @@ def dp_loss_and_grads(p: Params, batches: Sequence[Dict[str, torch.Tensor]], tem
     uid = torch.cat([b["user_idx"] for b in batches]) if "user_idx" in batches[0] else None
     loss, _ = infonce(U, I, temperature, uid)
     loss.backward()
+    if not tower_grads:
+        return loss.detach(), None, U.detach(), I.detach(), U.grad, I.grad
     grads = None
     off = 0
     for b in batches:
@@ -359,4 +362,4 @@ def dp_loss_and_grads(p: Params, batches: Sequence[Dict[str, torch.Tensor]], tem
         grads = gr if grads is None else {k: grads[k] + gr[k] for k in gr}
         off += n
     grads["user_tower.item_embedding.weight"][0] = 0
-    return loss.detach(), grads, U.detach(), I.detach()
+    return loss.detach(), grads, U.detach(), I.detach(), U.grad, I.grad

@@ -43,10 +43,10 @@ def test_forward_backward_through_autograd_and_torch_adamw():
     assert logits.shape == (32, 32) and u.shape == (32, 256) and i.shape == (32, 256)
     loss.backward()
     ref_loss, _, _, _, grads, _ = oracle.loss_and_grads(sd, batch, cfg.temperature, cfg.num_heads)
-    assert abs(loss.item() - ref_loss.item()) < 2e-2
+    assert abs(loss.item() - ref_loss.item()) < 5e-3
     k = "user_tower.fusion_layer.3.weight"
     g = dict(m.named_parameters())[k].grad
-    assert ((g.cpu() - grads[k]).norm() / grads[k].norm()).item() < 0.1
+    assert ((g.cpu() - grads[k]).norm() / grads[k].norm()).item() < 3e-2
     before = dict(m.named_parameters())[k].detach().clone()
     opt.step()
     assert not torch.equal(before, dict(m.named_parameters())[k].detach())
@@ -65,6 +65,12 @@ def test_train_one_epoch_fused_reduces_loss():
     assert last < first, (first, last)
     r = evaluate(m, batches[:2], torch.device("cuda"), k=10)
     assert 0.0 <= r <= 1.0
+    # the device counter == the oracle's rule applied to the model's own eval-mode logits
+    from oracle import two_tower_oracle as oracle
+    m.eval()
+    with torch.no_grad():
+        logits = [m({k: v.cuda() for k, v in b.items()})[1].cpu() for b in batches[:2]]
+    assert r == pytest.approx(oracle.evaluate_inbatch(logits, 10), abs=1e-7)
 
 
 def test_train_one_epoch_prefetch_path_is_the_same_training():
@@ -143,3 +149,88 @@ def test_calculate_metrics_global_matches_oracle():
     # metrics agree unless a score pair sits inside fp32 summation noise
     for k in ref:
         assert abs(got[k] - ref[k]) <= 1.0 / len(targets) + 1e-7, (k, got[k], ref[k])
+
+
+def test_stock_optimizer_second_step_sees_the_update():
+    """torch.optim.AdamW through the autograd node: the bf16 operand shadow must follow the fp32 masters the
+    optimizer changed, so the loss of step 2 is the oracle's loss after ITS first AdamW step (a stale shadow
+    leaves the tensor-core GEMMs on the initial weights: the step-2 loss then barely moves)."""
+    from mrm_b200 import synthetic
+    from oracle import two_tower_oracle as oracle
+    m = _model()
+    cfg = m.engine.cfg
+    sd = synthetic.make_state_dict(cfg, seed=3)
+    m.load_state_dict(sd)
+    batch = synthetic.make_batch(cfg, 32, seed=4)
+    dbatch = {k: v.cuda() for k, v in batch.items()}
+    lr = 2e-3
+    opt = torch.optim.AdamW(m.parameters(), lr=lr)
+    m.train()
+    losses = []
+    for _ in range(3):
+        opt.zero_grad(set_to_none=True)
+        loss = m(dbatch)[0]
+        loss.backward()
+        opt.step()
+        losses.append(loss.item())
+    p = {k: v.clone() for k, v in sd.items()}
+    mo = {k: torch.zeros_like(v) for k, v in p.items() if v.is_floating_point()}
+    vo = {k: torch.zeros_like(v) for k, v in p.items() if v.is_floating_point()}
+    ref = []
+    for t in range(1, 4):
+        l, _, _, _, grads, _ = oracle.loss_and_grads(p, batch, cfg.temperature, cfg.num_heads)
+        ref.append(l.item())
+        for k, g in grads.items():
+            p[k], mo[k], vo[k] = oracle.adamw_step(p[k], g, mo[k], vo[k], t, lr=lr)
+    assert ref[0] - ref[2] > 0.05, ref                   # the steps really move the loss
+    for a, b in zip(losses, ref):
+        assert abs(a - b) <= 1e-2, (losses, ref)
+    # a manual edit of a master weight is seen too
+    with torch.no_grad():
+        dict(m.named_parameters())["user_tower.fusion_layer.3.weight"].mul_(0.0)
+    m.eval()
+    with torch.no_grad():
+        u = m.get_user_embedding(dbatch["history_ids"], dbatch["history_mask"], dbatch["user_gender"], dbatch["user_country"])
+    b3 = m.engine.p["user_tower.fusion_layer.3.bias"]
+    expect = torch.nn.functional.normalize(b3.unsqueeze(0), dim=1).expand_as(u)
+    assert (u - expect).abs().max().item() < 1e-5
+
+
+def test_fused_adamw_hyperparameters_reach_the_graph_step():
+    """FusedAdamW(weight_decay, betas, eps) on the graph-replayed path == FusedAdamW.step() on the eager path."""
+    from mrm_b200 import synthetic
+    from mrm_b200.train import FusedAdamW, train_one_epoch
+    hp = dict(lr=1e-3, betas=(0.8, 0.95), eps=1e-6, weight_decay=0.3)
+    cfg0 = _model().engine.cfg
+    batches = [synthetic.make_batch(cfg0, 32, seed=80 + i) for i in range(3)]
+    key = "item_tower.fusion_layer.4.weight"
+    got = []
+    for fast in (True, False):
+        m = _model()
+        opt = FusedAdamW(m, **hp)
+        if fast:
+            train_one_epoch(m, batches, opt, torch.device("cuda"), epoch=0, is_main_process=False)
+        else:
+            m.train()
+            for b in batches:
+                m.engine.forward({k: v.cuda() for k, v in b.items()}, training=True)
+                m.engine.backward()
+                opt.step()
+        got.append(m.engine.p[key].clone())
+    w0 = _model().engine.p[key]
+    # decay alone moves the weights by lr * wd * 3 steps ~ 1e-3 relative; both routes must agree far inside that
+    assert ((got[0] - got[1]).norm() / (got[1] - w0).norm()).item() < 2e-2
+    assert ((got[1] - w0).norm() / w0.norm()).item() > 5e-4
+
+
+def test_load_state_dict_reports_missing_and_unexpected_keys():
+    from mrm_b200 import synthetic
+    m = _model()
+    sd = synthetic.make_state_dict(m.engine.cfg, seed=5)
+    sd["item_tower.visual_encoder.backbone.conv1.weight"] = torch.zeros(3)      # out-of-scope encoder key
+    del sd["user_tower.fusion_layer.3.bias"]
+    res = m.load_state_dict(sd, strict=False)
+    assert res.missing_keys == ["user_tower.fusion_layer.3.bias"]
+    assert res.unexpected_keys == ["item_tower.visual_encoder.backbone.conv1.weight"]
+    with pytest.raises(RuntimeError, match="missing keys"):
+        m.load_state_dict(sd, strict=True)

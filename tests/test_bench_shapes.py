@@ -1,0 +1,179 @@
+"""Parity AT THE BENCHMARKED SHAPES (BASELINE.json configs[1..3]); the small-shape tests live in test_engine.py /
+test_retrieval.py.
+
+  c2  B=256, L=200, V=100,001, dropout 0: forward + full backward against the fp64 CPU oracle.
+  c3  10,000 users x 1,000,000 items, top-100: indices of a 512-user sample against an fp64 canonical sort done
+      with plain torch on the GPU, Recall/NDCG of all users bit-identical to the oracle's metric code on the same
+      lists, metrics of a 96-user sample against the oracle's own CPU scoring.
+  c4  8 ranks x 512, L=200, gathered negatives: global loss and d loss / d embeddings against the oracle's
+      single-process global-batch InfoNCE (per-rank BatchNorm); full parameter gradients at a reduced shape.
+
+Tolerances (bf16 tensor-core operands, fp32 accumulation; SURVEY.md §8c-iii floors — no bf16-autocast anchor is
+stored for these shapes): normalised embeddings 5e-3 abs, logits 8e-2 abs, loss 5e-3 abs, each parameter gradient
+3e-2 * ||g_ref|| + 1e-5 * sqrt(numel) in L2, embedding gradients 3e-2 relative in L2.
+"""
+import json
+import os
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+C2 = dict(batch=256, seq_len=200, vocab=100_001)
+
+
+def _report(**kw):
+    os.makedirs("gpurun_out", exist_ok=True)
+    with open("gpurun_out/parity_report.jsonl", "a") as f:
+        f.write(json.dumps(kw) + "\n")
+
+
+def _engine(cfg, sd):
+    from mrm_b200.engine import TwoTowerEngine
+    eng = TwoTowerEngine(cfg)
+    eng.load_state_dict(sd)
+    return eng
+
+
+def test_c2_step_matches_fp64_oracle():
+    from mrm_b200 import synthetic
+    from oracle import two_tower_oracle as oracle
+    cfg = synthetic.TwoTowerConfig(vocab_size=C2["vocab"], max_seq_len=C2["seq_len"], dropout=0.0)
+    sd = synthetic.make_state_dict(cfg, seed=0)
+    batch = synthetic.make_batch(cfg, C2["batch"], seed=100, full_length=True, num_users=1_000_000)
+    batch["user_idx"][:8] = batch["user_idx"][8:16]          # a few same-user collisions (masked logits)
+    eng = _engine(cfg, sd)
+    dbatch = {k: v.cuda() for k, v in batch.items()}
+    loss, logits, u, i = eng.forward(dbatch, training=True)
+    eng.backward()
+    torch.cuda.synchronize()
+    torch.set_num_threads(os.cpu_count() or 1)
+    b64 = {k: (v.double() if v.is_floating_point() else v) for k, v in batch.items()}
+    rl, rlog, ru, ri, grads, _ = oracle.loss_and_grads(sd, b64, cfg.temperature, cfg.num_heads, dtype=torch.float64)
+    eu = (u.cpu().double() - ru).abs().max().item()
+    ei = (i.cpu().double() - ri).abs().max().item()
+    el = (logits.cpu().double() - rlog).abs().max().item()
+    eloss = abs(loss.item() - rl.item())
+    rows, bad = [], []
+    for k, ref in grads.items():
+        err = (eng.g[k].cpu().double() - ref).norm().item()
+        bound = 3e-2 * ref.norm().item() + 1e-5 * ref.numel() ** 0.5
+        rows.append((err / max(ref.norm().item(), 1e-12), k))
+        if err > bound:
+            bad.append((k, err, bound))
+    rows.sort(reverse=True)
+    _report(test="c2_step", user_emb_abs=eu, item_emb_abs=ei, logits_abs=el, loss_abs=eloss, loss=loss.item(),
+            oracle_loss=rl.item(), worst_grad_rel=rows[:5])
+    assert eu <= 5e-3 and ei <= 5e-3, (eu, ei)
+    assert el <= 8e-2, el
+    assert eloss <= 5e-3, (loss.item(), rl.item())
+    assert not bad, bad[:6]
+    assert eng.g["user_tower.item_embedding.weight"][0].abs().max().item() == 0.0
+
+
+def _fp64_canonical_topk(users, table, K, chunk=32):
+    """Plain torch on the GPU: fp64 scores rounded once to fp32 (what the retrieval path defines as the exact
+    score), column 0 masked, stable descending sort = canonical order."""
+    idx, val = [], []
+    t64 = table.double()
+    for s in range(0, users.shape[0], chunk):
+        sc = (users[s:s + chunk].double() @ t64.t()).float()
+        sc[:, 0] = float("-inf")
+        v, i = torch.sort(sc, dim=1, descending=True, stable=True)
+        idx.append(i[:, :K].clone())
+        val.append(v[:, :K].clone())
+    return torch.cat(idx), torch.cat(val)
+
+
+def test_c3_retrieval_matches_fp64_sort_and_oracle_metrics():
+    from mrm_b200 import retrieval
+    from oracle import two_tower_oracle as oracle
+    U, N, K, kl = 10_000, 1_000_000, 100, [10, 20, 50, 100]
+    g = torch.Generator(device="cuda").manual_seed(1234)
+    table = torch.nn.functional.normalize(torch.randn(N + 1, 256, device="cuda", generator=g), dim=1)
+    table[0] = 0
+    targets = torch.randint(1, N + 1, (U,), device="cuda", generator=g)
+    users = torch.nn.functional.normalize(table[targets] + 3.3 / 16.0 * torch.randn(U, 256, device="cuda", generator=g), dim=1)
+    index = retrieval.CatalogIndex(table)
+    idx, score, nfb = retrieval.retrieve_topk(users, index, K)
+    torch.cuda.synchronize()
+    # (1) indices and scores of a 512-user sample
+    sel = torch.arange(0, U, U // 512, device="cuda")[:512]
+    ri, rv = _fp64_canonical_topk(users[sel], table, K)
+    same = (idx[sel].long() == ri)
+    if not bool(same.all()):
+        # fp64 summation order differs between the two sides: a score may round to the neighbouring fp32 value
+        # (probability ~1e-8 per score). Any mismatch must be such a 1-ulp swap of adjacent entries.
+        bad = (~same).nonzero()
+        for u, k in bad.tolist():
+            assert abs(score[sel][u, k].item() - rv[u, k].item()) <= 1.2e-7, (u, k)
+        assert bad.shape[0] <= 4, bad.shape
+    assert (score[sel] - rv).abs().max().item() <= 1.2e-7
+    # (2) metrics of ALL users: device kernel == oracle metric code on the same lists, bit for bit
+    rec, ndcg = retrieval.rank_metrics(idx, targets, kl)
+    ref = oracle.rank_metrics(idx.cpu().long(), targets.cpu(), kl)
+    for j, k in enumerate(kl):
+        assert torch.equal(rec[j].cpu(), ref[f"Recall@{k}"]) and torch.equal(ndcg[j].cpu(), ref[f"NDCG@{k}"])
+    m = retrieval.metrics_from_embeddings(users, targets, index, kl)
+    for k in kl:
+        assert m[f"Recall@{k}"] == ref[f"Recall@{k}"].mean().item() and m[f"NDCG@{k}"] == ref[f"NDCG@{k}"].mean().item()
+    # (3) the oracle's own scoring (fp32 CPU matmul + stable sort) on a 96-user sample
+    torch.set_num_threads(os.cpu_count() or 1)
+    s96 = sel[:96]
+    om = oracle.calculate_metrics_global(users[s96].cpu(), table.cpu(), targets[s96].cpu(), kl, batch_size=32)
+    gm = {f"Recall@{k}": rec[j][s96].cpu().mean().item() for j, k in enumerate(kl)}
+    gm.update({f"NDCG@{k}": ndcg[j][s96].cpu().mean().item() for j, k in enumerate(kl)})
+    _report(test="c3_retrieval", fallback_users=int(nfb), recall_at_10=m["Recall@10"], sample_metrics=gm, oracle_sample_metrics=om)
+    assert gm == om, (gm, om)
+
+
+def test_c4_gathered_negatives_match_global_batch_oracle():
+    """8 virtual ranks x 512 samples, L=200, V=100,001: the (512 x 4096) logit blocks, cross-rank collision masks
+    and log-sum-exp exchange reproduce the loss and embedding gradients of ONE InfoNCE over the 4096 batch."""
+    from mrm_b200 import synthetic
+    from oracle import two_tower_oracle as oracle
+    from tests._virtual_dp import virtual_dp_step_one_engine
+    G, B = 8, 512
+    cfg = synthetic.TwoTowerConfig(vocab_size=C2["vocab"], max_seq_len=C2["seq_len"], dropout=0.0)
+    sd = synthetic.make_state_dict(cfg, seed=0)
+    batches = [synthetic.make_batch(cfg, B, seed=300 + r, full_length=True, num_users=3000) for r in range(G)]
+    eng = _engine(cfg, sd)
+    loss, gmean, dU, dI = virtual_dp_step_one_engine(eng, [{k: v.cuda() for k, v in b.items()} for b in batches])
+    torch.cuda.synchronize()
+    torch.set_num_threads(os.cpu_count() or 1)
+    rl, _, rU, rI, rdU, rdI = oracle.dp_loss_and_grads(sd, batches, cfg.temperature, cfg.num_heads,
+                                                      dtype=torch.float32, tower_grads=False)
+    eloss = abs(loss - rl.item())
+    eu = ((dU.cpu() - rdU).norm() / rdU.norm()).item()
+    ei = ((dI.cpu() - rdI).norm() / rdI.norm()).item()
+    collisions = int(sum(((torch.cat([b["user_idx"] for b in batches]).unsqueeze(0) ==
+                           batches[r]["user_idx"].unsqueeze(1)).sum() - B) for r in range(G)))
+    _report(test="c4_gathered", loss=loss, oracle_loss=rl.item(), dU_rel=eu, dI_rel=ei, collisions=collisions)
+    assert collisions > 1000                       # the cross-rank mask is exercised
+    assert eloss <= 5e-3, (loss, rl.item())
+    assert eu <= 3e-2 and ei <= 3e-2, (eu, ei)
+
+
+def test_dp_parameter_gradients_match_global_batch_oracle():
+    """4 virtual ranks x 64, L=50: the MEAN of the per-rank gradients is the gradient of the global-batch loss
+    (fp64 oracle, per-rank BatchNorm statistics), tensor by tensor."""
+    from mrm_b200 import synthetic
+    from oracle import two_tower_oracle as oracle
+    from tests._virtual_dp import virtual_dp_step_one_engine
+    G, B = 4, 64
+    cfg = synthetic.TwoTowerConfig(vocab_size=5001, max_seq_len=50, dropout=0.0)
+    sd = synthetic.make_state_dict(cfg, seed=3)
+    batches = [synthetic.make_batch(cfg, B, seed=400 + r, num_users=60) for r in range(G)]
+    eng = _engine(cfg, sd)
+    loss, gmean, _, _ = virtual_dp_step_one_engine(eng, [{k: v.cuda() for k, v in b.items()} for b in batches])
+    rl, grads, _, _, _, _ = oracle.dp_loss_and_grads(sd, batches, cfg.temperature, cfg.num_heads, dtype=torch.float64)
+    assert abs(loss - rl.item()) <= 5e-3
+    bad = []
+    for k, ref in grads.items():
+        o, shape = eng.layout[k]
+        got = gmean[o:o + ref.numel()].view(shape).cpu().double()
+        err = (got - ref).norm().item()
+        if err > 3e-2 * ref.norm().item() + 1e-5 * ref.numel() ** 0.5:
+            bad.append((k, err, ref.norm().item()))
+    assert not bad, bad[:6]

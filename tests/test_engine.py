@@ -100,15 +100,20 @@ def test_eval_embeddings_match_reference_golden():
     B, L = dbatch["history_ids"].shape
     ws = eng.workspace(B, L)
     eng.refresh_shadow()
+    auto = gold["bf16_autocast_err"]
+    tol_u, tol_i = max(2 * auto["user_emb_abs"], 5e-3), max(2 * auto["item_emb_abs"], 5e-3)
     u = eng.user_forward(ws, dbatch["history_ids"], dbatch["history_mask"], dbatch["user_gender"],
                          dbatch["user_country"], training=False)
-    assert (u.cpu().double() - g["eval_user_emb"]).abs().max().item() <= 2e-2
+    eu = (u.cpu().double() - g["eval_user_emb"]).abs().max().item()
     i = eng.item_forward(ws, dbatch["target_audio"], dbatch["target_image"], dbatch["target_input_ids"],
                          dbatch["target_tabular"], training=False)
-    assert (i.cpu().double() - g["eval_item_emb"]).abs().max().item() <= 2e-2
+    ei = (i.cpu().double() - g["eval_item_emb"]).abs().max().item()
     z = torch.zeros_like(dbatch["user_gender"])
     u2 = eng.user_forward(ws, dbatch["history_ids"], None, z, z, training=False)
-    assert (u2.cpu().double() - g["eval_user_emb_nomask"]).abs().max().item() <= 2e-2
+    eu2 = (u2.cpu().double() - g["eval_user_emb_nomask"]).abs().max().item()
+    _report(test="eval_embeddings", user_emb_abs=eu, item_emb_abs=ei, user_emb_nomask_abs=eu2, tol_user=tol_u, tol_item=tol_i)
+    assert eu <= tol_u and eu2 <= tol_u, (eu, eu2, tol_u)
+    assert ei <= tol_i, (ei, tol_i)
 
 
 def test_train_steps_follow_oracle_adamw():
@@ -129,12 +134,20 @@ def test_train_steps_follow_oracle_adamw():
     for a, b in zip(losses, losses_ref):
         assert abs(a - b) <= 5e-2, (losses, losses_ref)
     assert losses[-1] < losses[0]
-    # parameters moved the same way: compare the update direction on a dense weight
-    k = "user_tower.fusion_layer.3.weight"
-    d_ref = p[k] - sd[k]
-    d_got = eng.p[k].cpu() - sd[k]
-    cos = (d_ref * d_got).sum() / (d_ref.norm() * d_got.norm())
-    assert cos.item() > 0.9, cos.item()
+    # parameters moved the same way, element-wise. Adam normalises every element's step to ~lr, so elements whose
+    # gradient is rounding noise may move by up to 3 * lr in either direction; everywhere else the update must
+    # match: per dense tensor, the relative L2 difference of the update vectors stays small and no element is
+    # further from the oracle than the total distance an element can travel in three steps.
+    worst = []
+    for k in ("user_tower.fusion_layer.3.weight", "user_tower.fusion_layer.0.weight", "item_tower.fusion_layer.4.weight",
+              "user_tower.transformer_encoder.layers.1.linear2.weight", "user_tower.transformer_encoder.layers.0.self_attn.in_proj_weight"):
+        d_ref = p[k] - sd[k]
+        d_got = eng.p[k].cpu() - sd[k]
+        rel = ((d_ref - d_got).norm() / d_ref.norm()).item()
+        worst.append((rel, k))
+        assert rel <= 0.5, (k, rel)
+        assert (d_ref - d_got).abs().max().item() <= 2 * 3 * 1e-3 + 1e-6, k
+    _report(test="adamw_3step_updates", rel_update_diff=sorted(worst, reverse=True))
     assert eng.grad.abs().max().item() == 0.0     # zeroed by the fused step
 
 
@@ -338,3 +351,22 @@ def test_row_sharded_table_step_equals_replicated_table():
     moved = (eng.p[name].cpu() - sd[name]).abs().max().item()
     assert moved > 1e-4                       # the table really trained
     assert table.grad.abs().max().item() == 0.0 and eng2.table_rows_grad.abs().max().item() == 0.0
+
+
+def test_prune_toggle_after_a_step_restores_the_reference_schedule():
+    """prune_last_layer switched off on an engine whose (B, L) workspace already exists (built without the
+    full-layer backward buffers): the next step must run every layer on every position and agree with the
+    pruned step it replaces."""
+    gold, cfg, sd, batch, eng, dbatch = _setup("train_c1.pt")
+    l_pruned = eng.forward(dbatch, training=True)[0].item()
+    eng.backward()
+    torch.cuda.synchronize()
+    g_pruned = eng.grad.clone()
+    eng.grad.zero_()
+    eng.prune_last_layer = False
+    l_full = eng.forward(dbatch, training=True)[0].item()
+    eng.backward()
+    torch.cuda.synchronize()
+    assert abs(l_full - l_pruned) <= 2e-3
+    rel = ((eng.grad - g_pruned).norm() / g_pruned.norm()).item()
+    assert rel <= 3e-2, rel
