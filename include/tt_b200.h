@@ -332,6 +332,50 @@ int tt_exact_topk(const float* user_f32, const float* items_f32, int N, int item
 int tt_rank_metrics(const int32_t* topk_idx, const int64_t* targets, int U, int K, const int32_t* k_list, int nk,
                     const float* gain_table, float* recall, float* ndcg, void* stream);
 
+/* ---- data-parallel exchanges over NVLink peer memory -------------------------------------
+ * Replaces the NCCL traffic of the reference's DistributedDataParallel wrapper (src/train.py:29-35, 300: one
+ * gradient all-reduce per step, then torch.optim.AdamW on every rank, :302) and of the gathered-negatives
+ * exchange this repo adds (BASELINE.json configs[3]).
+ *
+ * A "team" describes ONE symmetric arena: the same allocation made by every rank, `bufs[r]` = rank r's copy as
+ * mapped into the calling process (bufs[rank] is the local one), `multicast` = the NVLS multicast mapping of the
+ * arena or NULL, `ctrl_offset` = byte offset of a tt_symm_ctrl_bytes()-sized control block inside the arena that
+ * the caller zeroes once before the first collective (and never touches again). Every rank must issue the same
+ * sequence of collectives on a team. All three entry points are stream-ordered and graph-capturable; they spin on
+ * flags in the control block, so the ranks' kernels must be able to run concurrently (one process per GPU).
+ *
+ * tt_symm_allgather : rank r's n_seg (<= 4) source blocks are stored into EVERY rank's arena at
+ *                     dst_offset + r * nbytes; ends with a cross-rank barrier (when the kernel completes, all
+ *                     ranks' blocks are visible locally). pre_barrier != 0 adds one at the start (needed when no
+ *                     collective separates this call from the peers' last reads of the destination).
+ * tt_dp_adamw_step  : flat fp32 parameters, fp32 gradients and the bf16 shadow of parameters [shadow_begin, n) live
+ *                     in the arena at the given byte offsets. Rank r owns elements [r*n/G, (r+1)*n/G): it reads the
+ *                     MEAN over ranks of the gradient slice (multimem.ld_reduce, or peer loads in rank order),
+ *                     applies torch.optim.AdamW (m, v: local moments of the slice) and stores the new values and
+ *                     their bf16 copies into every rank's arena (multimem.st / peer stores). Barriers on both
+ *                     sides: starts when every rank's gradients are final, completes when every rank's parameters
+ *                     are. Gradients are NOT cleared (the caller zeroes its local buffer afterwards).
+ * tt_symm_barrier   : barrier across the team.
+ * A wait longer than ~10 s (a peer died) sets the int32 at ctrl_offset + 8 and returns; callers check it. */
+#define TT_SYMM_MAX_RANKS 16
+typedef struct tt_symm_team {
+  int32_t rank, world;
+  void* bufs[TT_SYMM_MAX_RANKS];
+  void* multicast;
+  int64_t ctrl_offset;
+} tt_symm_team;
+typedef struct tt_symm_segment {
+  const void* src;
+  int64_t dst_offset;
+  int64_t nbytes;
+} tt_symm_segment;
+int tt_symm_ctrl_bytes(void);
+int tt_symm_allgather(const tt_symm_team* team, const tt_symm_segment* segs, int n_seg, int pre_barrier, void* stream);
+int tt_dp_adamw_step(const tt_symm_team* team, int64_t flat_offset, int64_t grad_offset, int64_t shadow_offset,
+                     int64_t n, int64_t shadow_begin, float* m, float* v, float lr, float beta1, float beta2, float eps,
+                     float weight_decay, const int64_t* step_dev, void* stream);
+int tt_symm_barrier(const tt_symm_team* team, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

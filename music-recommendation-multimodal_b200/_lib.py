@@ -133,7 +133,27 @@ class TopkPlan(ctypes.Structure):
 
 
 _I64 = ctypes.c_int64
+
+
+class SymmTeam(ctypes.Structure):
+    """Mirror of ``tt_symm_team``."""
+
+    _fields_ = [("rank", c_int32), ("world", c_int32), ("bufs", c_void_p * 16), ("multicast", c_void_p),
+                ("ctrl_offset", ctypes.c_int64)]
+
+
+class SymmSegment(ctypes.Structure):
+    """Mirror of ``tt_symm_segment``."""
+
+    _fields_ = [("src", c_void_p), ("dst_offset", ctypes.c_int64), ("nbytes", ctypes.c_int64)]
+
+
 _SIGNATURES = {
+    "tt_symm_ctrl_bytes": [],
+    "tt_symm_allgather": [ctypes.POINTER(SymmTeam), ctypes.POINTER(SymmSegment), c_int32, c_int32, c_void_p],
+    "tt_dp_adamw_step": [ctypes.POINTER(SymmTeam), _I64, _I64, _I64, _I64, _I64, c_void_p, c_void_p, c_float, c_float,
+                         c_float, c_float, c_float, c_void_p, c_void_p],
+    "tt_symm_barrier": [ctypes.POINTER(SymmTeam), c_void_p],
     "tt_gather_rows": [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p],
     "tt_scatter_rows_add": [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_int32, c_void_p],
     "tt_attn_lastq_fwd": [c_void_p] * 5 + [c_int32, c_int32, c_int32, c_float, c_uint64, c_void_p, c_uint32, c_void_p],

@@ -134,7 +134,7 @@ __device__ __forceinline__ void gemm_epilogue_chunk(const GemmParams& p, const u
   }
   if (p.relu) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+    for (int j = 0; j < 32; ++j) v[j] = v[j] < 0.f ? 0.f : v[j];   // torch.relu keeps NaN (fmaxf would drop it)
   }
   if (p.drop_thresh) {
     // N % 4 == 0 and col0 % 32 == 0: the four columns j..j+3 share one hash word

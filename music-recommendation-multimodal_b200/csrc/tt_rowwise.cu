@@ -222,7 +222,7 @@ __global__ void __launch_bounds__(kRowThreads) chain_fwd_kernel(const ChainParam
     }
     if (p.relu) {
 #pragma unroll
-      for (int i = 0; i < E; ++i) v[i] = fmaxf(v[i], 0.f);
+      for (int i = 0; i < E; ++i) v[i] = v[i] < 0.f ? 0.f : v[i];   // NaN-propagating like torch.relu
     }
     if (p.drop_thresh) row_dropout<NV>(v, drop_key(seed, p.site), row, W, lane, p.drop_thresh, p.drop_scale, nullptr);
     if (p.l2norm) {
@@ -286,7 +286,7 @@ __global__ void __launch_bounds__(kRowThreads, 2) chain_bwd_kernel(const ChainPa
     bool keep[E];
 #pragma unroll
     for (int i = 0; i < E; ++i) {
-      z[i] = p.relu ? fmaxf(y[i], 0.f) : y[i];
+      z[i] = (p.relu && y[i] < 0.f) ? 0.f : y[i];
       keep[i] = true;
     }
     if (p.drop_thresh) row_dropout<NV>(z, drop_key(seed, p.site), row, W, lane, p.drop_thresh, p.drop_scale, keep);
@@ -489,7 +489,8 @@ __global__ void __launch_bounds__(256) bn_fwd_kernel(const BnParams p) {
   const uint64_t seed = p.drop_thresh ? read_seed(p.seed, p.seed_dev) : 0;
   for (int r = threadIdx.y; r < p.B; r += 8) {
     const size_t i = static_cast<size_t>(r) * p.C + c;
-    float v = fmaxf((p.y[i] - mean) * rstd * g + be, 0.f);
+    float v = (p.y[i] - mean) * rstd * g + be;
+    v = v < 0.f ? 0.f : v;   // NaN-propagating like torch.relu
     if (p.drop_thresh) v = drop_keep(seed, p.site, i, p.drop_thresh) ? v * p.drop_scale : 0.f;
     p.out[i] = __float2bfloat16_rn(v);
   }

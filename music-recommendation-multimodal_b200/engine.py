@@ -106,15 +106,8 @@ class TwoTowerEngine:
         self.p: Dict[str, torch.Tensor] = {}
         self.g: Dict[str, torch.Tensor] = {}
         self.w: Dict[str, torch.Tensor] = {}   # bf16 shadows (dense region only)
-        for name, (o, shape) in self.layout.items():
-            n = 1
-            for s in shape:
-                n *= s
-            self.p[name] = self.flat[o:o + n].view(shape)
-            self.g[name] = self.grad[o:o + n].view(shape)
-            if o >= self.dense_begin:
-                so = o - self.dense_begin
-                self.w[name] = self.shadow[so:so + n].view(shape)
+        self.rebind_hooks = []
+        self._bind_views()
         H = cfg.fusion_hidden
         self.bn_running_mean = torch.zeros(H, device=dev)
         self.bn_running_var = torch.ones(H, device=dev)
@@ -157,6 +150,33 @@ class TwoTowerEngine:
         if (B, L) not in self._virt_ids:
             self._virt_ids[(B, L)] = torch.arange(1, 1 + B * L, device=self.device, dtype=torch.long)
         return self._virt_ids[(B, L)], self.table_rows, self.table_rows_grad
+
+    def _bind_views(self) -> None:
+        self.p, self.g, self.w = {}, {}, {}
+        for name, (o, shape) in self.layout.items():
+            n = 1
+            for s in shape:
+                n *= s
+            self.p[name] = self.flat[o:o + n].view(shape)
+            self.g[name] = self.grad[o:o + n].view(shape)
+            if o >= self.dense_begin:
+                so = o - self.dense_begin
+                self.w[name] = self.shadow[so:so + n].view(shape)
+
+    def rebind_storage(self, flat: torch.Tensor, grad: torch.Tensor, shadow: torch.Tensor) -> None:
+        """Move the parameters, gradients and the bf16 operand shadow into caller-provided buffers of the same
+        sizes (blocks of a symmetric arena, symm.SymmArena) and re-point every view at them. CUDA graphs and
+        workspaces that captured the old buffers must be rebuilt by their owners; `rebind_hooks` lets the
+        nn.Module wrappers re-point their Parameters."""
+        assert flat.numel() == self.numel and grad.numel() == self.numel and shadow.numel() == self.shadow.numel()
+        assert flat.dtype == torch.float32 and grad.dtype == torch.float32 and shadow.dtype == torch.bfloat16
+        flat.copy_(self.flat)
+        grad.copy_(self.grad)
+        shadow.copy_(self.shadow)
+        self.flat, self.grad, self.shadow = flat, grad, shadow
+        self._bind_views()
+        for hook in getattr(self, "rebind_hooks", []):
+            hook()
 
     def load_state_dict(self, sd: Dict[str, torch.Tensor]) -> None:
         """Copy a reference-format state dict (src/train.py:327-330; optional 'module.' prefix,

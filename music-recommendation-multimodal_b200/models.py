@@ -150,6 +150,12 @@ class TwoTowerModel(nn.Module):
         object.__setattr__(self, "engine", engine)
         self.user_tower = SequentialUserEncoder(_engine=engine)
         self.item_tower = MultimodalItemEncoder(_engine=engine)
+        engine.rebind_hooks.append(self._rebind_parameters)
+
+    def _rebind_parameters(self) -> None:
+        """The engine moved its flat buffers (into a symmetric arena for multi-GPU training): Parameters follow."""
+        for name, prm in self.named_parameters():
+            prm.data = self.engine.p[name]
 
     # -- checkpoints in the reference layout (src/train.py:327-330; loaders strip 'module.')
     def load_state_dict(self, state_dict, strict: bool = False):  # type: ignore[override]

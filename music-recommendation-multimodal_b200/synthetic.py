@@ -164,6 +164,14 @@ def make_batch(cfg: TwoTowerConfig, batch_size: int, seq_len: Optional[int] = No
     return batch
 
 
+def make_c2_parity_batch(cfg: TwoTowerConfig, batch_size: int = 256, seed: int = 100) -> Dict[str, torch.Tensor]:
+    """The batch of the c2-shape parity pins (tests/test_bench_shapes.py, tests/golden/anchor_c2.pt): bench-style
+    batch (all histories full, ~unique users) with eight same-user collisions planted so the -1e4 mask is live."""
+    batch = make_batch(cfg, batch_size, seed=seed, full_length=True, num_users=1_000_000)
+    batch["user_idx"][:8] = batch["user_idx"][8:16]
+    return batch
+
+
 def _quantize(t: torch.Tensor, step: float) -> torch.Tensor:
     return torch.round(t.clamp(-1, 1) / step) * step
 

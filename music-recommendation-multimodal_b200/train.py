@@ -12,6 +12,7 @@ autograd node is used (reference-compatible, slower). bf16 needs no GradScaler.
 from __future__ import annotations
 
 import logging
+import os
 from typing import Dict, Optional
 
 import torch
@@ -57,7 +58,7 @@ class TrainStepRunner:
                  use_graph: bool = True, with_user_idx: bool = True, negatives: str = "gathered",
                  rank: Optional[int] = None, group=None, shard_optimizer: bool = True,
                  with_optimizer: bool = True, sharded_table=None, betas=(0.9, 0.999), eps: float = 1e-8,
-                 weight_decay: float = 0.01):
+                 weight_decay: float = 0.01, comm: str = "auto"):
         self.eng, self.B, self.L, self.world, self.lr, self.use_graph = engine, B, L, world_size, lr, use_graph
         self.betas, self.eps, self.weight_decay = tuple(betas), eps, weight_decay
         self.group = group
@@ -71,16 +72,39 @@ class TrainStepRunner:
             engine.use_external_table(B, L)
         self.rank = (dist.get_rank(group) if world_size > 1 else 0) if rank is None else rank
         self.gathered = world_size > 1 and negatives == "gathered"
+        # comm = "symm": every exchange of the step is one of this repo's kernels over a symmetric NVLink arena
+        # (csrc/tt_symm.cu) and the whole step is ONE CUDA graph; "nccl": the library collectives between
+        # sub-graphs; "auto": symm whenever the process group can build an arena (NCCL group, <= 16 ranks) and the
+        # step is the standard one (gathered negatives, optimizer on, replicated table).
+        self.arena = None
+        if comm not in ("auto", "symm", "nccl"):
+            raise ValueError(f"comm={comm!r}")
+        want_symm = comm != "nccl" and world_size > 1 and self.gathered and with_optimizer and sharded_table is None \
+            and engine.numel % (4 * world_size) == 0 and os.environ.get("TT_COMM", "") != "nccl"
+        if want_symm:
+            from . import symm
+            if symm.available(group):
+                try:
+                    self._setup_symm(engine, B, world_size, group)
+                except Exception as exc:          # no peer access / symmetric allocator refused: library path
+                    if comm == "symm":
+                        raise
+                    logger.warning(f"symmetric arena unavailable ({exc}); using the NCCL exchanges")
+                    self.arena = None
+            elif comm == "symm":
+                raise RuntimeError("comm='symm' needs an NCCL process group on one NVLink domain")
         # ZeRO-1 style: reduce-scatter the gradient, AdamW on this rank's 1/world shard (moments are
         # held for the shard only), all-gather the updated parameters. Same bytes on NVLink as one
         # all-reduce, 1/world of the optimizer's HBM traffic.
         # The flat buffer is padded to a multiple of 2048 elements (engine.py), i.e. it splits into equal 16-byte
         # aligned shards for 1/2/4/8 ranks; any other world size keeps the replicated optimizer (one all-reduce).
         self.shard_opt = world_size > 1 and shard_optimizer and engine.numel % (4 * world_size) == 0
+        if self.arena is not None:
+            self.shard_opt = False           # the arena path shards the optimizer inside its own kernel
         if self.shard_opt:
             self._grad_shard = torch.empty(engine.numel // world_size, device=engine.device)
         # packed exchange buffers: one all-gather for (user emb | item emb | user id), one for the two LSE vectors
-        if self.gathered:
+        if self.gathered and self.arena is None:
             D = engine.cfg.embedding_dim
             self._pack_emb = torch.empty(B, 2 * D * 2 + 8, device=engine.device, dtype=torch.uint8)
             self._pack_emb_all = torch.empty(world_size * B, 2 * D * 2 + 8, device=engine.device, dtype=torch.uint8)
@@ -114,6 +138,64 @@ class TrainStepRunner:
         self._staged = False
         self.kernels_per_step = 0
         self._warm = False
+
+    # ---- symmetric-arena path -----------------------------------------------------------------
+    def _setup_symm(self, eng: TwoTowerEngine, B: int, G: int, group) -> None:
+        from .symm import SymmArena
+        D = eng.cfg.embedding_dim
+        layout = {"flat": eng.numel * 4, "grad": eng.numel * 4, "shadow": eng.shadow.numel() * 2,
+                  "U_all": G * B * D * 2, "I_all": G * B * D * 2, "uid_all": G * B * 8,
+                  "lse_r_all": G * B * 4, "lse_c_all": G * B * 4, "loss_all": G * 16}
+        self.arena = a = SymmArena(layout, group, eng.device)
+        eng.rebind_storage(a.view("flat", torch.float32, (eng.numel,)), a.view("grad", torch.float32, (eng.numel,)),
+                           a.view("shadow", torch.bfloat16, (eng.shadow.numel(),)))
+        eng.release_workspaces()
+        self._loss_pad = torch.zeros(4, device=eng.device)            # 16-byte slot: [loss share, 0, 0, 0]
+        self._loss_all_host = torch.zeros(G, 4).pin_memory()
+        n = eng.numel // G
+        if eng.exp_avg is None or eng.exp_avg.numel() != n:
+            eng.exp_avg = torch.zeros(n, device=eng.device)
+            eng.exp_avg_sq = torch.zeros(n, device=eng.device)
+
+    def _symm_gathered(self, ws):
+        """The gathered workspace of the engine with its exchanged members living in the arena."""
+        eng, a, G, B = self.eng, self.arena, self.world, self.B
+        key = f"_gath{G}"
+        if key not in ws:
+            D, dev = eng.cfg.embedding_dim, eng.device
+            Cp = (G * B + 7) // 8 * 8
+            ws[key] = {
+                "U_all": a.view("U_all", torch.bfloat16, (G * B, D)), "I_all": a.view("I_all", torch.bfloat16, (G * B, D)),
+                "uid_all": a.view("uid_all", torch.long, (G * B,)),
+                "lse_r_all": a.view("lse_r_all", torch.float32, (G * B,)),
+                "lse_c_all": a.view("lse_c_all", torch.float32, (G * B,)),
+                "S": torch.empty(B, Cp, device=dev)[:, :G * B], "S2": torch.empty(B, Cp, device=dev)[:, :G * B],
+                "dS": torch.zeros(B, Cp, device=dev, dtype=torch.bfloat16)[:, :G * B],
+                "dS2": torch.zeros(B, Cp, device=dev, dtype=torch.bfloat16)[:, :G * B],
+            }
+        return ws[key]
+
+    def _phase_symm_step(self):
+        """The whole data-parallel step, every exchange a kernel of this repo: capturable as ONE graph."""
+        from . import ops
+        eng, a = self.eng, self.arena
+        ws = self._ws = eng.forward_towers(self.static, training=True)
+        g = self._symm_gathered(ws)
+        uid = self.static.get("user_idx")
+        # no leading barrier: the peers' last reads of these blocks (previous step's backward) precede the
+        # barrier that ended the previous step's optimizer kernel
+        blocks = [(ws["un_bf"], "U_all"), (ws["in_bf"], "I_all")] + ([(uid, "uid_all")] if uid is not None else [])
+        a.allgather(blocks)
+        eng.loss_forward(ws, uid, gathered=g, rank=self.rank)
+        eng.loss_value(ws, self.world * self.B)
+        self._loss_pad[:1].copy_(ws["loss"].view(1))
+        a.allgather([(ws["lse_r"], "lse_r_all"), (ws["lse_c"], "lse_c_all"), (self._loss_pad, "loss_all")])
+        eng.backward()
+        ops.step_counters_advance(eng.step_dev, eng.seed_dev)
+        a.dp_adamw_step("flat", "grad", "shadow", eng.numel, eng.dense_begin, eng.exp_avg, eng.exp_avg_sq, eng.step_dev,
+                        self.lr, self.betas, self.eps, self.weight_decay)
+        eng.grad.zero_()
+        eng.shadow_valid = True
 
     def load_batch(self, batch: Dict[str, torch.Tensor]) -> None:
         for k, dst in self.static.items():
@@ -209,6 +291,8 @@ class TrainStepRunner:
 
     def _sequence(self):
         """[(callable, is_communication)] of one step."""
+        if self.arena is not None:
+            return [(self._phase_symm_step, False)]
         seq = [(self._comm_lookup, True)] if self.table is not None else []
         seq += [(self._phase_towers, False)]
         if self.gathered:
@@ -239,6 +323,12 @@ class TrainStepRunner:
         """The cross-rank exchanges of one step, in order (what bench.py prints next to the timing)."""
         if self.world == 1:
             return []
+        if self.arena is not None:
+            how = "NVLS multicast (multimem.ld_reduce / multimem.st)" if self.arena.multicast else "peer loads / stores"
+            return [f"tt_symm_allgather (user emb | item emb | user id), {how}",
+                    "tt_symm_allgather (row log-sum-exps of both directions | loss share)",
+                    f"tt_dp_adamw_step: gradient reduce-scatter -> AdamW -> parameter + bf16 shadow all-gather in one "
+                    f"kernel over {self.eng.numel * 4} B, {how}; no library collective, the step is one CUDA graph"]
         n = self.eng.numel * 4
         names = {
             "_comm_lookup": "NCCL all_to_all x3 (token ids -> owner ranks, rows back): row-sharded ID table lookup",
@@ -355,6 +445,14 @@ class TrainStepRunner:
         loss = self.step_resident()
         if prefetch is not None:
             self.stage_batch(prefetch)
+        if self.arena is not None:
+            # every rank's loss share came with the log-sum-exp exchange: one small D2H, no collective
+            self._loss_all_host.copy_(self.arena.view("loss_all", torch.float32, (self.world, 4)), non_blocking=True)
+            self.arena._err_host.copy_(self.arena.error_word(), non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            if int(self.arena._err_host[0]) != 0:
+                raise RuntimeError("a cross-GPU wait timed out (peer rank missing or stalled)")
+            return float(self._loss_all_host[:, 0].sum())
         if self.gathered:
             loss = loss.clone()
             dist.all_reduce(loss, op=dist.ReduceOp.SUM, group=self.group)

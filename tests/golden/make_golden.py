@@ -6,7 +6,9 @@ parameters of `synthetic.make_state_dict`, runs the reference's TwoTowerModel.fo
 backward, get_user_embedding and calculate_metrics_global on seeded synthetic batches and
 stores the OUTPUTS (not the inputs: those are regenerated from the seed) as small .pt files.
 
-    python tests/golden/make_golden.py          # writes tests/golden/*.pt
+    python tests/golden/make_golden.py          # writes tests/golden/*.pt (small fixtures, ~20 s)
+    python tests/golden/make_golden.py --all    # + anchor_c2.pt: the reference at the c2 shape in fp64 and under
+                                                #   bf16 autocast (minutes of CPU); --anchor-only for just that
 
 /root/reference does not exist on the GPU box; tests only read the committed fixtures.
 """
@@ -161,6 +163,38 @@ def golden_retrieval(evalm, name, num_items, num_users, k_list, grid, seed, nois
     print(name, metrics)
 
 
+def golden_anchor(two_tower, name, cfg, batch, seed_w):
+    """Tolerance anchor only at a shape too large to store outputs for: the error of the
+    REFERENCE's own modules under bf16 autocast against its fp64 run — loss, embeddings, logits and every
+    parameter gradient (relative / absolute L2, fp64 norm). A few hundred numbers."""
+    sd = synthetic.make_state_dict(cfg, seed=seed_w)
+    m64 = build_reference_model(two_tower, cfg, sd, torch.float64)
+    m64.train()
+    l64, lg64, u64, i64 = m64(cast_batch(batch, torch.float64))
+    l64.backward()
+    g64 = {k: p.grad.detach() for k, p in m64.named_parameters() if p.grad is not None}
+    mb = build_reference_model(two_tower, cfg, sd, torch.float32)
+    mb.train()
+    with torch.autocast(device_type="cpu", dtype=torch.bfloat16):
+        lb, lgb, ub, ib = mb(cast_batch(batch, torch.float32))
+    lb.backward()
+    gb = {k: p.grad.detach() for k, p in mb.named_parameters() if p.grad is not None}
+    auto = {
+        "loss64": l64.item(),
+        "loss_abs": abs(lb.item() - l64.item()),
+        "logits_abs": (lgb.double() - lg64).abs().max().item(),
+        "user_emb_abs": (ub.double() - u64).abs().max().item(),
+        "item_emb_abs": (ib.double() - i64).abs().max().item(),
+        "grad_rel": {k: ((gb[k].double() - g64[k]).norm() / g64[k].norm().clamp_min(1e-300)).item() for k in g64},
+        "grad_abs": {k: (gb[k].double() - g64[k]).norm().item() for k in g64},
+        "grad_norm64": {k: g64[k].norm().item() for k in g64},
+    }
+    torch.save({"config": cfg.as_dict(), "seed_w": seed_w, "bf16_autocast_err": auto}, os.path.join(HERE, name))
+    worst = sorted(((v, k) for k, v in auto["grad_rel"].items() if auto["grad_norm64"][k] > 1e-6), reverse=True)[:5]
+    print(name, "loss64", auto["loss64"], "autocast: loss", auto["loss_abs"], "logits", auto["logits_abs"], "user",
+          auto["user_emb_abs"], "item", auto["item_emb_abs"], "worst grad rel", worst)
+
+
 class _CatalogDataset(torch.utils.data.Dataset):
     """Harness stand-in for the absent src/data/dataset.py in compute_all_item_embeddings
     (evaluate_metrics.py:40-48): serves the precomputed modality embeddings of `FEATURES` row by row."""
@@ -232,6 +266,11 @@ def main():
     torch.manual_seed(0)
     torch.set_num_threads(8)
     two_tower, evalm, train = import_reference(dataset_cls=_CatalogDataset)
+    if "--anchor-only" in sys.argv or "--all" in sys.argv:
+        c2 = synthetic.TwoTowerConfig(vocab_size=100_001, max_seq_len=200, dropout=0.0)
+        golden_anchor(two_tower, "anchor_c2.pt", c2, synthetic.make_c2_parity_batch(c2), seed_w=0)
+        if "--anchor-only" in sys.argv:
+            return
     small = synthetic.TwoTowerConfig(vocab_size=501, num_genders=3, num_countries=7, max_seq_len=12,
                                      embedding_dim=64, num_heads=4, num_layers=2, modality_dim=16,
                                      fusion_hidden=512)

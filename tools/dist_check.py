@@ -16,6 +16,7 @@ from mrm_b200.train import TrainStepRunner  # noqa: E402
 
 def main():
     sharded = "--sharded-table" in sys.argv     # config-5 layout: row-sharded ID table (all-to-all lookups)
+    comm = "nccl" if "--nccl" in sys.argv else "auto"   # auto = symmetric-arena kernels (csrc/tt_symm.cu)
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -35,7 +36,9 @@ def main():
     else:
         eng = TwoTowerEngine(cfg)
         eng.load_state_dict(sd)
-        runner = TrainStepRunner(eng, B, L, world_size=world, lr=lr, use_graph=True)
+        runner = TrainStepRunner(eng, B, L, world_size=world, lr=lr, use_graph=True, comm=comm)
+        if rank == 0:
+            print("exchanges:", runner.comm_description())
     losses = [runner.step_from_host(batches[s][rank]) for s in range(steps)]
     torch.cuda.synchronize()
     if sharded:     # same flat layout as the replicated engine: [full table | everything else]
