@@ -548,16 +548,18 @@ def bench_c5(rank, world, dev, peaks, args):
     import dataclasses
     from mrm_b200 import retrieval, synthetic
     from mrm_b200.engine import TwoTowerEngine
-    from mrm_b200.sharding import RowShardedTable
+    from mrm_b200.sharding import RowShardedTable, SymmShardedTable
     from mrm_b200.train import TrainStepRunner
+    from mrm_b200 import symm
     B, L, V = C5["batch"], C5["seq_len"], C5["vocab"]
     cfg = synthetic.TwoTowerConfig(vocab_size=V, max_seq_len=L, dropout=0.1)
     eng = TwoTowerEngine(dataclasses.replace(cfg, vocab_size=2), dev)
-    table = RowShardedTable(V, 256, rank, world, dev)
+    use_symm = symm.available() and os.environ.get("TT_COMM", "") != "nccl"
+    table = SymmShardedTable(V, 256, device=dev) if use_symm else RowShardedTable(V, 256, rank, world, dev)
     small = dataclasses.replace(cfg, vocab_size=2)
     eng.load_state_dict(synthetic.make_state_dict(small, seed=0))
     g = torch.Generator(device=dev).manual_seed(777 + rank)
-    table.weight.copy_(torch.randn(table.rows, 256, device=dev, generator=g) * (2.0 / (V + 256)) ** 0.5)
+    table.weight[:table.rows].copy_(torch.randn(table.rows, 256, device=dev, generator=g) * (2.0 / (V + 256)) ** 0.5)
     runner = TrainStepRunner(eng, B, L, world_size=world, sharded_table=table)
     hb = [pin(synthetic.make_batch(cfg, B, seed=600 + rank * 17 + i, full_length=True, num_users=1_000_000)) for i in range(2)]
     steps = max(5, args.steps // 2)

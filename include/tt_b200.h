@@ -220,11 +220,12 @@ int tt_bn_relu_bwd(const tt_bn_args* args, void* stream);
 int tt_colsum_bf16(const void* x_bf16, int R, int N, int ld, float* out, void* stream);
 
 /* Fused dense AdamW over a flat fp32 buffer (torch.optim.AdamW as used at src/train.py:302,
- * 64-65): p,g,m,v [n]; *step_dev is the 1-based step count on the device; optionally writes a
- * bf16 shadow of p[shadow_begin:shadow_end] and zeroes g. */
+ * 64-65): p,g,m,v [n]; the gradient used is grad_scale * g (1 / world for a buffer that holds the SUM of the
+ * ranks' gradients, e.g. the owner's shard of a row-sharded ID table); *step_dev is the 1-based step count on the
+ * device; optionally writes a bf16 shadow of p[shadow_begin:shadow_end] and zeroes g. */
 int tt_adamw_step(float* p, float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
-                  float weight_decay, const int64_t* step_dev, void* shadow_bf16, int64_t shadow_begin,
-                  int64_t shadow_end, int zero_grad, void* stream);
+                  float weight_decay, float grad_scale, const int64_t* step_dev, void* shadow_bf16,
+                  int64_t shadow_begin, int64_t shadow_end, int zero_grad, void* stream);
 /* ++*step_dev; *seed_dev += golden-ratio increment (either may be NULL). */
 int tt_step_counters_advance(int64_t* step_dev, uint64_t* seed_dev, void* stream);
 
@@ -331,6 +332,26 @@ int tt_exact_topk(const float* user_f32, const float* items_f32, int N, int item
                   void* key_scratch, float* out_score, int32_t* out_idx, void* stream);
 int tt_rank_metrics(const int32_t* topk_idx, const int64_t* targets, int U, int K, const int32_t* k_list, int nk,
                     const float* gain_table, float* recall, float* ndcg, void* stream);
+
+/* ---- ID-embedding lookups against a table row-sharded over the ranks of one NVLink domain ----------
+ * (BASELINE.json configs[4]: 10M items; reference: nn.Embedding(vocab_size, 256, padding_idx=0) and its dense
+ * gradient, src/models/user_tower.py:26,86.) The table and its gradient live in a symmetric arena (tt_symm_team
+ * below): rank r holds rows [r * rows_per_rank, (r+1) * rows_per_rank) at byte `weight_offset` / `grad_offset` of
+ * its copy. Same computation as tt_embed_ln_fwd / tt_embed_ln_bwd; a token's row is read from — and its gradient
+ * row added (red.global.add.v4.f32) into — the OWNER's memory over NVLink. No ids or rows are exchanged between
+ * ranks. row_stash (nullable, fp32 [B*L, 256]): the forward keeps the gathered rows, the backward reads them
+ * instead of crossing NVLink a second time. The caller separates steps with tt_symm_barrier (owners' updates
+ * visible before the next gather; all ranks' gradient rows landed before the owner's AdamW). */
+struct tt_symm_team;
+int tt_embed_ln_fwd_sharded(const int64_t* ids, const struct tt_symm_team* team, int64_t weight_offset,
+                            int rows_per_rank, float* row_stash, const float* P, const float* ln_w, const float* ln_b,
+                            const float* next_w, const float* next_b, int B, int L, float drop_p, uint64_t seed,
+                            const uint64_t* seed_dev, uint32_t site, float* x0, void* h_bf16, void* stream);
+int tt_embed_ln_bwd_sharded(const int64_t* ids, const struct tt_symm_team* team, int64_t weight_offset,
+                            int64_t grad_offset, int rows_per_rank, const float* row_stash, const float* P,
+                            const float* ln_w, const float* ln_b, const float* dx0, int B, int L, float drop_p,
+                            uint64_t seed, const uint64_t* seed_dev, uint32_t site, float* dP, float* dgamma,
+                            float* dbeta, void* stream);
 
 /* ---- data-parallel exchanges over NVLink peer memory -------------------------------------
  * Replaces the NCCL traffic of the reference's DistributedDataParallel wrapper (src/train.py:29-35, 300: one

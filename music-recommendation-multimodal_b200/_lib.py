@@ -184,8 +184,13 @@ _SIGNATURES = {
     "tt_bn_relu_fwd": [ctypes.POINTER(BnArgs), c_void_p],
     "tt_bn_relu_bwd": [ctypes.POINTER(BnArgs), c_void_p],
     "tt_colsum_bf16": [c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p],
-    "tt_adamw_step": [c_void_p] * 4 + [_I64, c_float, c_float, c_float, c_float, c_float, c_void_p, c_void_p,
+    "tt_adamw_step": [c_void_p] * 4 + [_I64, c_float, c_float, c_float, c_float, c_float, c_float, c_void_p, c_void_p,
                                        _I64, _I64, c_int32, c_void_p],
+    "tt_embed_ln_fwd_sharded": [c_void_p, ctypes.POINTER(SymmTeam), _I64, c_int32] + [c_void_p] * 6 +
+                               [c_int32, c_int32, c_float, c_uint64, c_void_p, c_uint32, c_void_p, c_void_p, c_void_p],
+    "tt_embed_ln_bwd_sharded": [c_void_p, ctypes.POINTER(SymmTeam), _I64, _I64, c_int32] + [c_void_p] * 5 +
+                               [c_int32, c_int32, c_float, c_uint64, c_void_p, c_uint32, c_void_p, c_void_p, c_void_p,
+                                c_void_p],
     "tt_step_counters_advance": [c_void_p, c_void_p, c_void_p],
     "tt_infonce_rows": [c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_int32, c_void_p, c_void_p,
                         c_void_p],

@@ -130,9 +130,25 @@ __global__ void last_index_kernel(const int64_t* __restrict__ ids, const int64_t
 // x0 = dropout(LN_emb(E[id] + P[pos]));  h = LN_next(x0) as bf16       (user_tower.py:86-93 and
 // the first norm1 of the encoder). D = 256.
 // --------------------------------------------------------------------------------------------
+// The ID table as the embedding kernels see it: one replicated table (per == 0: row id lives at base[0]) or a
+// table row-sharded over the ranks of one NVLink domain (row id lives at local row id % per of rank id / per;
+// base[r] = rank r's shard as mapped into this process, symmetric arena) — then the gather / scatter-add goes
+// straight to the owner's memory over NVLink, no id or row exchange between the ranks.
+struct TableRef {
+  float* base[TT_SYMM_MAX_RANKS];
+  int per;
+  __device__ __forceinline__ float* row(int64_t id) const {
+    if (per == 0) return base[0] + static_cast<size_t>(id) * 256;
+    const int owner = static_cast<int>(id / per);
+    return base[owner] + static_cast<size_t>(id - static_cast<int64_t>(owner) * per) * 256;
+  }
+};
+
 struct EmbedParams {
   const int64_t* ids;
-  const float* E;
+  TableRef E;
+  float* stash;        // nullable [T, 256]: the gathered table rows, kept for the backward pass (sharded tables:
+                       // saves the second trip over NVLink)
   const float* P;
   const float* ln_w; const float* ln_b;
   const float* nw; const float* nb;
@@ -158,8 +174,9 @@ __global__ void __launch_bounds__(kRowThreads) embed_ln_fwd_kernel(const EmbedPa
     const int64_t id = p.ids[row];
     const int pos = row % p.L;
     float e[8], q[8];
-    load_row<NV>(p.E + static_cast<size_t>(id) * 256, lane, e);
+    load_row<NV>(p.E.row(id), lane, e);
     load_row<NV>(p.P + static_cast<size_t>(pos) * 256, lane, q);
+    if (p.stash) store_row<NV>(p.stash + static_cast<size_t>(row) * 256, lane, e);
 #pragma unroll
     for (int i = 0; i < 8; ++i) e[i] += q[i];
     float mean, rstd;
@@ -578,10 +595,14 @@ __global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* _
 // S atomics per element; S is chosen so that all blocks are resident at 2 per SM.
 // --------------------------------------------------------------------------------------------
 struct EmbedBwdParams {
-  const int64_t* ids; const float* E; const float* P; const float* ln_w; const float* ln_b;
+  const int64_t* ids; TableRef E; const float* stash; const float* P; const float* ln_w; const float* ln_b;
   const float* dx0; int B, L;
   uint32_t drop_thresh; float drop_scale; uint64_t seed; const uint64_t* seed_dev; uint32_t site;
-  float* dE; float* dP; float* dgamma; float* dbeta;
+  TableRef dE; float* dP; float* dgamma; float* dbeta;
+  // the table row of token `row` with id `id`: the forward's stash when there is one, else the table itself
+  __device__ __forceinline__ const float* src_row(size_t row, int64_t id) const {
+    return stash ? stash + row * 256 : E.row(id);
+  }
 };
 
 __global__ void __launch_bounds__(kRowThreads, 2) embed_ln_bwd_kernel(const EmbedBwdParams p) {
@@ -605,7 +626,7 @@ __global__ void __launch_bounds__(kRowThreads, 2) embed_ln_bwd_kernel(const Embe
   float e_n[E_], g_n[E_];
   if (b < p.B) {
     id_n = p.ids[static_cast<size_t>(b) * p.L + pos];
-    load_row<NV>(p.E + static_cast<size_t>(id_n) * W, lane, e_n);
+    load_row<NV>(p.src_row(static_cast<size_t>(b) * p.L + pos, id_n), lane, e_n);
     load_row<NV>(p.dx0 + (static_cast<size_t>(b) * p.L + pos) * W, lane, g_n);
   }
   if (b + stride < p.B) id_nn = p.ids[static_cast<size_t>(b + stride) * p.L + pos];
@@ -617,7 +638,7 @@ __global__ void __launch_bounds__(kRowThreads, 2) embed_ln_bwd_kernel(const Embe
     for (int i = 0; i < E_; ++i) { e[i] = e_n[i]; g[i] = g_n[i]; }
     id_n = id_nn;
     if (b + stride < p.B) {
-      load_row<NV>(p.E + static_cast<size_t>(id_n) * W, lane, e_n);
+      load_row<NV>(p.src_row(static_cast<size_t>(b + stride) * p.L + pos, id_n), lane, e_n);
       load_row<NV>(p.dx0 + (static_cast<size_t>(b + stride) * p.L + pos) * W, lane, g_n);
     }
     if (b + 2 * stride < p.B) id_nn = p.ids[static_cast<size_t>(b + 2 * stride) * p.L + pos];
@@ -644,7 +665,7 @@ __global__ void __launch_bounds__(kRowThreads, 2) embed_ln_bwd_kernel(const Embe
       dp[i] += g[i];
     }
     if (id != 0) {
-      float* dst = p.dE + static_cast<size_t>(id) * W;
+      float* dst = p.dE.row(id);
 #pragma unroll
       for (int k = 0; k < NV; ++k)
         red_add_f32x4(dst + (k * 32 + lane) * 4, g[4 * k + 0], g[4 * k + 1], g[4 * k + 2], g[4 * k + 3]);
@@ -666,6 +687,9 @@ __global__ void __launch_bounds__(kRowThreads, 2) embed_ln_bwd_kernel(const Embe
     atomicAdd(p.dbeta + c, a1);
     atomicAdd(p.dP + static_cast<size_t>(pos) * W + c, a2);  // gridDim.y blocks per position
   }
+  // sharded table: the gradient rows went to other GPUs; make them globally performed before the grid retires
+  // (the optimizer kernels of the owners start after a cross-rank barrier that follows this kernel)
+  if (p.dE.per != 0) __threadfence_system();
 }
 
 // --------------------------------------------------------------------------------------------
@@ -676,7 +700,8 @@ __global__ void __launch_bounds__(kRowThreads, 2) embed_ln_bwd_kernel(const Embe
 // --------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m,
                                                     float* __restrict__ v, size_t n4, float lr, float beta1,
-                                                    float beta2, float eps, float wd, const int64_t* step_dev,
+                                                    float beta2, float eps, float wd, float grad_scale,
+                                                    const int64_t* step_dev,
                                                     __nv_bfloat16* __restrict__ shadow, size_t shadow_begin4,
                                                     size_t shadow_end4, int zero_grad) {
   pdl_launch_dependents();
@@ -690,10 +715,11 @@ __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, float
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
     float4 pp = reinterpret_cast<float4*>(p)[i];
     const float4 gg = reinterpret_cast<const float4*>(g)[i];
+    const float4 gs = make_float4(gg.x * grad_scale, gg.y * grad_scale, gg.z * grad_scale, gg.w * grad_scale);
     float4 mm = reinterpret_cast<float4*>(m)[i];
     float4 vv = reinterpret_cast<float4*>(v)[i];
     float* pa = reinterpret_cast<float*>(&pp);
-    const float* ga = reinterpret_cast<const float*>(&gg);
+    const float* ga = reinterpret_cast<const float*>(&gs);
     float* ma = reinterpret_cast<float*>(&mm);
     float* va = reinterpret_cast<float*>(&vv);
 #pragma unroll
@@ -804,15 +830,33 @@ extern "C" int tt_last_index(const int64_t* ids, const int64_t* mask, int B, int
   return TT_OK;
 }
 
-extern "C" int tt_embed_ln_fwd(const int64_t* ids, const float* E, const float* P, const float* ln_w,
-                               const float* ln_b, const float* next_w, const float* next_b, int B, int L,
-                               float drop_p, uint64_t seed, const uint64_t* seed_dev, uint32_t site, float* x0,
-                               void* h_bf16, void* stream_) {
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  TT_REQUIRE(ids && E && P && ln_w && ln_b && next_w && next_b && x0 && h_bf16, "tt_embed_ln_fwd: null pointer");
+static TableRef single_table(const float* E) {
+  TableRef t;
+  for (int r = 0; r < TT_SYMM_MAX_RANKS; ++r) t.base[r] = nullptr;
+  t.base[0] = const_cast<float*>(E);
+  t.per = 0;
+  return t;
+}
+
+static int sharded_table(TableRef& t, const tt_symm_team* team, int64_t offset, int rows_per_rank, const char* who) {
+  TT_REQUIRE(team && team->world >= 1 && team->world <= TT_SYMM_MAX_RANKS && rows_per_rank > 0 && offset >= 0 &&
+                 offset % 16 == 0,
+             "%s: bad team / shard geometry", who);
+  for (int r = 0; r < TT_SYMM_MAX_RANKS; ++r)
+    t.base[r] = r < team->world ? reinterpret_cast<float*>(static_cast<uint8_t*>(team->bufs[r]) + offset) : nullptr;
+  for (int r = 0; r < team->world; ++r) TT_REQUIRE(team->bufs[r] != nullptr, "%s: rank %d has no mapping", who, r);
+  t.per = rows_per_rank;
+  return TT_OK;
+}
+
+static int embed_fwd_impl(const int64_t* ids, const TableRef& E, float* stash, const float* P, const float* ln_w,
+                          const float* ln_b, const float* next_w, const float* next_b, int B, int L, float drop_p,
+                          uint64_t seed, const uint64_t* seed_dev, uint32_t site, float* x0, void* h_bf16,
+                          cudaStream_t stream) {
+  TT_REQUIRE(ids && P && ln_w && ln_b && next_w && next_b && x0 && h_bf16, "tt_embed_ln_fwd: null pointer");
   TT_REQUIRE(B > 0 && L > 0, "tt_embed_ln_fwd: empty batch");
   EmbedParams p;
-  p.ids = ids; p.E = E; p.P = P; p.ln_w = ln_w; p.ln_b = ln_b; p.nw = next_w; p.nb = next_b;
+  p.ids = ids; p.E = E; p.stash = stash; p.P = P; p.ln_w = ln_w; p.ln_b = ln_b; p.nw = next_w; p.nb = next_b;
   p.T = B * L; p.L = L;
   p.drop_thresh = drop_threshold(drop_p);
   p.drop_scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
@@ -823,14 +867,13 @@ extern "C" int tt_embed_ln_fwd(const int64_t* ids, const float* E, const float* 
   return TT_OK;
 }
 
-extern "C" int tt_embed_ln_bwd(const int64_t* ids, const float* E, const float* P, const float* ln_w,
-                               const float* ln_b, const float* dx0, int B, int L, float drop_p, uint64_t seed,
-                               const uint64_t* seed_dev, uint32_t site, float* dE, float* dP, float* dgamma,
-                               float* dbeta, void* stream_) {
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  TT_REQUIRE(ids && E && P && ln_w && ln_b && dx0 && dE && dP && dgamma && dbeta, "tt_embed_ln_bwd: null pointer");
+static int embed_bwd_impl(const int64_t* ids, const TableRef& E, const float* stash, const float* P, const float* ln_w,
+                          const float* ln_b, const float* dx0, int B, int L, float drop_p, uint64_t seed,
+                          const uint64_t* seed_dev, uint32_t site, const TableRef& dE, float* dP, float* dgamma,
+                          float* dbeta, cudaStream_t stream) {
+  TT_REQUIRE(ids && P && ln_w && ln_b && dx0 && dP && dgamma && dbeta, "tt_embed_ln_bwd: null pointer");
   EmbedBwdParams p;
-  p.ids = ids; p.E = E; p.P = P; p.ln_w = ln_w; p.ln_b = ln_b; p.dx0 = dx0; p.B = B; p.L = L;
+  p.ids = ids; p.E = E; p.stash = stash; p.P = P; p.ln_w = ln_w; p.ln_b = ln_b; p.dx0 = dx0; p.B = B; p.L = L;
   p.drop_thresh = drop_threshold(drop_p);
   p.drop_scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
   p.seed = seed; p.seed_dev = seed_dev; p.site = site;
@@ -841,6 +884,50 @@ extern "C" int tt_embed_ln_bwd(const int64_t* ids, const float* E, const float* 
   TT_CHECK_CUDA(launch_k(embed_ln_bwd_kernel, dim3(L, splits), dim3(kRowThreads), 0, stream, p));
   TT_LAUNCH_CHECK();
   return TT_OK;
+}
+
+extern "C" int tt_embed_ln_fwd(const int64_t* ids, const float* E, const float* P, const float* ln_w,
+                               const float* ln_b, const float* next_w, const float* next_b, int B, int L,
+                               float drop_p, uint64_t seed, const uint64_t* seed_dev, uint32_t site, float* x0,
+                               void* h_bf16, void* stream_) {
+  TT_REQUIRE(E, "tt_embed_ln_fwd: null table");
+  return embed_fwd_impl(ids, single_table(E), nullptr, P, ln_w, ln_b, next_w, next_b, B, L, drop_p, seed, seed_dev, site,
+                        x0, h_bf16, static_cast<cudaStream_t>(stream_));
+}
+
+extern "C" int tt_embed_ln_bwd(const int64_t* ids, const float* E, const float* P, const float* ln_w,
+                               const float* ln_b, const float* dx0, int B, int L, float drop_p, uint64_t seed,
+                               const uint64_t* seed_dev, uint32_t site, float* dE, float* dP, float* dgamma,
+                               float* dbeta, void* stream_) {
+  TT_REQUIRE(E && dE, "tt_embed_ln_bwd: null table");
+  return embed_bwd_impl(ids, single_table(E), nullptr, P, ln_w, ln_b, dx0, B, L, drop_p, seed, seed_dev, site,
+                        single_table(dE), dP, dgamma, dbeta, static_cast<cudaStream_t>(stream_));
+}
+
+extern "C" int tt_embed_ln_fwd_sharded(const int64_t* ids, const tt_symm_team* team, int64_t weight_offset,
+                                       int rows_per_rank, float* row_stash, const float* P, const float* ln_w,
+                                       const float* ln_b, const float* next_w, const float* next_b, int B, int L,
+                                       float drop_p, uint64_t seed, const uint64_t* seed_dev, uint32_t site, float* x0,
+                                       void* h_bf16, void* stream_) {
+  TableRef E;
+  int rc = sharded_table(E, team, weight_offset, rows_per_rank, "tt_embed_ln_fwd_sharded");
+  if (rc) return rc;
+  return embed_fwd_impl(ids, E, row_stash, P, ln_w, ln_b, next_w, next_b, B, L, drop_p, seed, seed_dev, site, x0, h_bf16,
+                        static_cast<cudaStream_t>(stream_));
+}
+
+extern "C" int tt_embed_ln_bwd_sharded(const int64_t* ids, const tt_symm_team* team, int64_t weight_offset,
+                                       int64_t grad_offset, int rows_per_rank, const float* row_stash, const float* P,
+                                       const float* ln_w, const float* ln_b, const float* dx0, int B, int L,
+                                       float drop_p, uint64_t seed, const uint64_t* seed_dev, uint32_t site, float* dP,
+                                       float* dgamma, float* dbeta, void* stream_) {
+  TableRef E, dE;
+  int rc = sharded_table(E, team, weight_offset, rows_per_rank, "tt_embed_ln_bwd_sharded");
+  if (rc) return rc;
+  rc = sharded_table(dE, team, grad_offset, rows_per_rank, "tt_embed_ln_bwd_sharded");
+  if (rc) return rc;
+  return embed_bwd_impl(ids, E, row_stash, P, ln_w, ln_b, dx0, B, L, drop_p, seed, seed_dev, site, dE, dP, dgamma, dbeta,
+                        static_cast<cudaStream_t>(stream_));
 }
 
 static int fill_chain(ChainParams& p, const tt_chain_args* a, const char* who) {
@@ -979,8 +1066,8 @@ extern "C" int tt_colsum_bf16(const void* x, int R, int N, int ld, float* out, v
 }
 
 extern "C" int tt_adamw_step(float* p, float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
-                             float eps, float weight_decay, const int64_t* step_dev, void* shadow_bf16,
-                             int64_t shadow_begin, int64_t shadow_end, int zero_grad, void* stream_) {
+                             float eps, float weight_decay, float grad_scale, const int64_t* step_dev,
+                             void* shadow_bf16, int64_t shadow_begin, int64_t shadow_end, int zero_grad, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   TT_REQUIRE(p && g && m && v && step_dev && n > 0 && n % 4 == 0, "tt_adamw_step: bad arguments");
   TT_REQUIRE(shadow_begin % 4 == 0 && shadow_end % 4 == 0 && shadow_begin <= shadow_end && shadow_end <= n,
@@ -988,7 +1075,7 @@ extern "C" int tt_adamw_step(float* p, float* g, float* m, float* v, int64_t n, 
   const size_t n4 = static_cast<size_t>(n / 4);
   int grid = static_cast<int>((n4 + 255) / 256);
   if (grid > num_sms() * 16) grid = num_sms() * 16;
-  TT_CHECK_CUDA(launch_k(adamw_kernel, dim3(grid), dim3(256), 0, stream, p, g, m, v, n4, lr, beta1, beta2, eps, weight_decay, step_dev, static_cast<__nv_bfloat16*>(shadow_bf16), static_cast<size_t>(shadow_begin / 4), static_cast<size_t>(shadow_end / 4), zero_grad));
+  TT_CHECK_CUDA(launch_k(adamw_kernel, dim3(grid), dim3(256), 0, stream, p, g, m, v, n4, lr, beta1, beta2, eps, weight_decay, grad_scale, step_dev, static_cast<__nv_bfloat16*>(shadow_bf16), static_cast<size_t>(shadow_begin / 4), static_cast<size_t>(shadow_end / 4), zero_grad));
   TT_LAUNCH_CHECK();
   return TT_OK;
 }

@@ -131,6 +131,10 @@ class TwoTowerEngine:
         self.table_rows: Optional[torch.Tensor] = None
         self.table_rows_grad: Optional[torch.Tensor] = None
         self._virt_ids: Dict[Tuple[int, int], torch.Tensor] = {}
+        #: sharding.SymmShardedTable: the ID table lives row-sharded in a symmetric NVLink arena; the embedding
+        #: kernels read rows from / add gradient rows into the OWNER's memory directly (no exchange step). The flat
+        #: buffer's own table region is a 2-row dummy.
+        self.peer_table = None
 
     # ------------------------------------------------------------------ parameters
     def use_external_table(self, B: int, L: int) -> None:
@@ -184,7 +188,7 @@ class TwoTowerEngine:
         (RowShardedTable.load_full takes it)."""
         sd = {(k[7:] if k.startswith("module.") else k): v for k, v in sd.items()}
         for name, t in self.p.items():
-            if self.table_rows is not None and name == "user_tower.item_embedding.weight":
+            if (self.table_rows is not None or self.peer_table is not None) and name == "user_tower.item_embedding.weight":
                 continue
             t.copy_(sd[name].to(device=self.device, dtype=torch.float32))
         it = "item_tower.fusion_layer.1."
@@ -388,11 +392,21 @@ class TwoTowerEngine:
         seed, sdev = self.base_seed, self.seed_dev
         ut = "user_tower."
         ops.last_index(ids, mask, ws["last_idx"])
-        e_ids, e_table, _ = self._embed_operands(ids)
-        ops.embed_ln_fwd(e_ids, e_table, p[ut + "position_embedding.weight"],
-                         p[ut + "layer_norm.weight"], p[ut + "layer_norm.bias"],
-                         p[self._lp(0, "norm1.weight")], p[self._lp(0, "norm1.bias")], B, L,
-                         ws["x_in0"], ws["h1_0"], drop_p=dp, seed=seed, seed_dev=sdev, site=SITE_EMB)
+        if self.peer_table is not None:
+            t = self.peer_table
+            if "row_stash" not in ws:
+                ws["row_stash"] = torch.empty(B * L, cfg.embedding_dim, device=self.device)
+            ops.embed_ln_fwd_sharded(ids.view(-1), t.arena.team, t.arena.offset("weight"), t.per, ws["row_stash"],
+                                     p[ut + "position_embedding.weight"], p[ut + "layer_norm.weight"],
+                                     p[ut + "layer_norm.bias"], p[self._lp(0, "norm1.weight")],
+                                     p[self._lp(0, "norm1.bias")], B, L, ws["x_in0"], ws["h1_0"], drop_p=dp, seed=seed,
+                                     seed_dev=sdev, site=SITE_EMB)
+        else:
+            e_ids, e_table, _ = self._embed_operands(ids)
+            ops.embed_ln_fwd(e_ids, e_table, p[ut + "position_embedding.weight"],
+                             p[ut + "layer_norm.weight"], p[ut + "layer_norm.bias"],
+                             p[self._lp(0, "norm1.weight")], p[self._lp(0, "norm1.bias")], B, L,
+                             ws["x_in0"], ws["h1_0"], drop_p=dp, seed=seed, seed_dev=sdev, site=SITE_EMB)
         x_in = ws["x_in0"]
         for l in range(cfg.num_layers):
             if self.prune_last_layer and l == cfg.num_layers - 1:
@@ -746,12 +760,20 @@ class TwoTowerEngine:
             dx, dx_other = dx_other, dx
 
         # ---- embedding LayerNorm + lookup
-        e_ids, e_table, e_grad = self._embed_operands(ids)
-        ops.embed_ln_bwd(e_ids, e_table, p[ut + "position_embedding.weight"],
-                         p[ut + "layer_norm.weight"], p[ut + "layer_norm.bias"], dx, B, L,
-                         e_grad, g[ut + "position_embedding.weight"],
-                         g[ut + "layer_norm.weight"], g[ut + "layer_norm.bias"], drop_p=dp, seed=seed,
-                         seed_dev=sdev, site=SITE_EMB)
+        if self.peer_table is not None:
+            t = self.peer_table
+            ops.embed_ln_bwd_sharded(ids.view(-1), t.arena.team, t.arena.offset("weight"), t.arena.offset("grad"), t.per,
+                                     ws["row_stash"], p[ut + "position_embedding.weight"], p[ut + "layer_norm.weight"],
+                                     p[ut + "layer_norm.bias"], dx, B, L, g[ut + "position_embedding.weight"],
+                                     g[ut + "layer_norm.weight"], g[ut + "layer_norm.bias"], drop_p=dp, seed=seed,
+                                     seed_dev=sdev, site=SITE_EMB)
+        else:
+            e_ids, e_table, e_grad = self._embed_operands(ids)
+            ops.embed_ln_bwd(e_ids, e_table, p[ut + "position_embedding.weight"],
+                             p[ut + "layer_norm.weight"], p[ut + "layer_norm.bias"], dx, B, L,
+                             e_grad, g[ut + "position_embedding.weight"],
+                             g[ut + "layer_norm.weight"], g[ut + "layer_norm.bias"], drop_p=dp, seed=seed,
+                             seed_dev=sdev, site=SITE_EMB)
         main.wait_stream(side)
         if self.overlap_wgrad:
             main.wait_stream(self._wgrad_stream())

@@ -147,6 +147,26 @@ def embed_ln_bwd(ids, E, P, ln_w, ln_b, dx0, B, L, dE, dP, dgamma, dbeta, drop_p
                                 dP.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(), _stream()), "tt_embed_ln_bwd")
 
 
+def embed_ln_fwd_sharded(ids, team, weight_offset, rows_per_rank, stash, P, ln_w, ln_b, next_w, next_b, B, L, x0, h,
+                         drop_p=0.0, seed=0, seed_dev=None, site=0):
+    """tt_embed_ln_fwd_sharded: the ID table is row-sharded over the ranks of a symmetric arena."""
+    _require_cuda(ids, stash, P, x0, h)
+    assert ids.dtype == torch.int64 and P.shape[0] >= L
+    check(lib().tt_embed_ln_fwd_sharded(ids.data_ptr(), ctypes.byref(team), weight_offset, rows_per_rank, _ptr(stash),
+                                        P.data_ptr(), ln_w.data_ptr(), ln_b.data_ptr(), next_w.data_ptr(),
+                                        next_b.data_ptr(), B, L, drop_p, seed, _ptr(seed_dev), site, x0.data_ptr(),
+                                        h.data_ptr(), _stream()), "tt_embed_ln_fwd_sharded")
+
+
+def embed_ln_bwd_sharded(ids, team, weight_offset, grad_offset, rows_per_rank, stash, P, ln_w, ln_b, dx0, B, L, dP,
+                         dgamma, dbeta, drop_p=0.0, seed=0, seed_dev=None, site=0):
+    _require_cuda(ids, stash, P, dx0, dP, dgamma, dbeta)
+    check(lib().tt_embed_ln_bwd_sharded(ids.data_ptr(), ctypes.byref(team), weight_offset, grad_offset, rows_per_rank,
+                                        _ptr(stash), P.data_ptr(), ln_w.data_ptr(), ln_b.data_ptr(), dx0.data_ptr(), B,
+                                        L, drop_p, seed, _ptr(seed_dev), site, dP.data_ptr(), dgamma.data_ptr(),
+                                        dbeta.data_ptr(), _stream()), "tt_embed_ln_bwd_sharded")
+
+
 def _chain_args(x, *, ln=None, relu=False, drop_p=0.0, seed=0, seed_dev=None, site=0, l2norm=False,
                 l2_eps=1e-12, out_f32=None, out_bf16=None, dout=None, resid=None, dx_f32=None, dx_bf16=None,
                 drop2_p=0.0, drop2_site=0, dgamma=None, dbeta=None, dx_colsum=None, resid_rows=None,
@@ -240,13 +260,13 @@ def colsum_bf16(x: torch.Tensor, out: torch.Tensor) -> None:
 
 
 def adamw_step(p, g, m, v, step_dev, lr=1e-4, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.01,
-               shadow=None, shadow_begin=0, shadow_end=0, zero_grad=True) -> None:
+               shadow=None, shadow_begin=0, shadow_end=0, zero_grad=True, grad_scale=1.0) -> None:
     _require_cuda(p, g, m, v, step_dev, shadow)
     for t in (p, g, m, v):
         assert t.dtype == torch.float32 and t.is_contiguous() and t.numel() == p.numel()
     assert step_dev.dtype == torch.int64
     check(lib().tt_adamw_step(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), lr, beta1, beta2,
-                              eps, weight_decay, step_dev.data_ptr(), _ptr(shadow), shadow_begin, shadow_end,
+                              eps, weight_decay, grad_scale, step_dev.data_ptr(), _ptr(shadow), shadow_begin, shadow_end,
                               int(zero_grad), _stream()), "tt_adamw_step")
 
 

@@ -137,3 +137,56 @@ class RowShardedTable:
         out = torch.empty(self.world * self.per, self.dim, device=self.weight.device, dtype=self.weight.dtype)
         dist.all_gather_into_tensor(out, pad, group=self.group)
         return out[:self.vocab_size]
+
+
+class SymmShardedTable:
+    """Row-sharded ID table in a symmetric NVLink arena (BASELINE.json configs[4]): rank r owns the
+    contiguous rows [r * per, (r + 1) * per) (per = ceil(V / world)) of ``nn.Embedding(vocab_size, 256,
+    padding_idx=0)`` (src/models/user_tower.py:26) and of its dense gradient, in one allocation that every rank maps.
+    There is no lookup exchange: the embedding kernels (tt_embed_ln_fwd_sharded / _bwd_sharded) read a token's row
+    from, and add its gradient row into, the owner's memory over NVLink. The owner runs dense AdamW
+    (src/train.py:302) over its rows with the gradient SUM scaled by 1 / world (the data-parallel mean)."""
+
+    def __init__(self, vocab_size: int, dim: int, group=None, device=None):
+        from .symm import SymmArena
+        import torch.distributed as dist
+        self.vocab_size, self.dim = vocab_size, dim
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.per = (vocab_size + self.world - 1) // self.world
+        self.first = min(self.rank * self.per, vocab_size)
+        self.rows = max(0, min(vocab_size, self.first + self.per) - self.first)
+        self.arena = SymmArena({"weight": self.per * dim * 4, "grad": self.per * dim * 4}, group, device)
+        self.weight = self.arena.view("weight", torch.float32, (self.per, dim))
+        self.grad = self.arena.view("grad", torch.float32, (self.per, dim))
+        self.exp_avg = None
+        self.exp_avg_sq = None
+
+    def describe(self) -> str:
+        how = "NVLS-capable arena" if self.arena.multicast else "peer-mapped arena"
+        return (f"contiguous row shards ({self.per} rows/rank) in a symmetric {how}; forward: rows gathered from the "
+                f"owner's memory over NVLink inside the embedding kernel (kept in a local stash for the backward), "
+                f"backward: red.global.add.v4.f32 into the owner's gradient shard; no id/row exchange, one barrier "
+                f"kernel per step")
+
+    def load_full(self, full_table: torch.Tensor) -> None:
+        self.weight[:self.rows].copy_(full_table[self.first:self.first + self.rows])
+
+    def barrier(self) -> None:
+        self.arena.barrier()
+
+    def adamw_step(self, step_dev: torch.Tensor, lr: float = 1e-4, betas=(0.9, 0.999), eps: float = 1e-8,
+                   weight_decay: float = 0.01) -> None:
+        from . import ops
+        if self.exp_avg is None:
+            self.exp_avg = torch.zeros(self.per * self.dim, device=self.weight.device)
+            self.exp_avg_sq = torch.zeros(self.per * self.dim, device=self.weight.device)
+        n = self.per * self.dim
+        ops.adamw_step(self.weight.view(n), self.grad.view(n), self.exp_avg, self.exp_avg_sq, step_dev, lr, betas[0],
+                       betas[1], eps, weight_decay, shadow=None, zero_grad=True, grad_scale=1.0 / self.world)
+
+    def gather_full(self) -> torch.Tensor:
+        import torch.distributed as dist
+        out = torch.empty(self.world * self.per, self.dim, device=self.weight.device)
+        dist.all_gather_into_tensor(out, self.weight.contiguous(), group=self.arena.group)
+        return out[:self.vocab_size]

@@ -68,7 +68,8 @@ class TrainStepRunner:
         #: sharding.RowShardedTable: the item-ID table lives row-sharded across the ranks (config 5); every step
         #: starts with the id/row all-to-all and ends with the gradient-row all-to-all + the local-row AdamW
         self.table = sharded_table
-        if sharded_table is not None and engine.table_rows is None:
+        from .sharding import RowShardedTable
+        if isinstance(sharded_table, RowShardedTable) and engine.table_rows is None:
             engine.use_external_table(B, L)
         self.rank = (dist.get_rank(group) if world_size > 1 else 0) if rank is None else rank
         self.gathered = world_size > 1 and negatives == "gathered"
@@ -79,8 +80,15 @@ class TrainStepRunner:
         self.arena = None
         if comm not in ("auto", "symm", "nccl"):
             raise ValueError(f"comm={comm!r}")
-        want_symm = comm != "nccl" and world_size > 1 and self.gathered and with_optimizer and sharded_table is None \
+        from .sharding import SymmShardedTable
+        peer_table = isinstance(sharded_table, SymmShardedTable)
+        if peer_table:
+            engine.peer_table = sharded_table
+        want_symm = comm != "nccl" and world_size > 1 and self.gathered and with_optimizer \
+            and (sharded_table is None or peer_table) \
             and engine.numel % (4 * world_size) == 0 and os.environ.get("TT_COMM", "") != "nccl"
+        if peer_table and not want_symm:
+            raise ValueError("a SymmShardedTable needs the symmetric-arena step (gathered negatives, optimizer on)")
         if want_symm:
             from . import symm
             if symm.available(group):
@@ -179,6 +187,8 @@ class TrainStepRunner:
         """The whole data-parallel step, every exchange a kernel of this repo: capturable as ONE graph."""
         from . import ops
         eng, a = self.eng, self.arena
+        if self.table is not None:
+            self.table.barrier()      # every owner's AdamW of the previous step is visible before rows are gathered
         ws = self._ws = eng.forward_towers(self.static, training=True)
         g = self._symm_gathered(ws)
         uid = self.static.get("user_idx")
@@ -194,6 +204,10 @@ class TrainStepRunner:
         ops.step_counters_advance(eng.step_dev, eng.seed_dev)
         a.dp_adamw_step("flat", "grad", "shadow", eng.numel, eng.dense_begin, eng.exp_avg, eng.exp_avg_sq, eng.step_dev,
                         self.lr, self.betas, self.eps, self.weight_decay)
+        if self.table is not None:
+            # the kernel above started only after EVERY rank finished its backward pass (phase-A barrier), so all
+            # gradient rows have landed in this owner's shard
+            self.table.adamw_step(eng.step_dev, self.lr, self.betas, self.eps, self.weight_decay)
         eng.grad.zero_()
         eng.shadow_valid = True
 
@@ -325,7 +339,10 @@ class TrainStepRunner:
             return []
         if self.arena is not None:
             how = "NVLS multicast (multimem.ld_reduce / multimem.st)" if self.arena.multicast else "peer loads / stores"
-            return [f"tt_symm_allgather (user emb | item emb | user id), {how}",
+            pre = [] if self.table is None else [
+                "tt_symm_barrier + ID-table rows read from / gradient rows added into the owner's memory over NVLink "
+                "inside tt_embed_ln_fwd_sharded / tt_embed_ln_bwd_sharded"]
+            return pre + [f"tt_symm_allgather (user emb | item emb | user id), {how}",
                     "tt_symm_allgather (row log-sum-exps of both directions | loss share)",
                     f"tt_dp_adamw_step: gradient reduce-scatter -> AdamW -> parameter + bf16 shadow all-gather in one "
                     f"kernel over {self.eng.numel * 4} B, {how}; no library collective, the step is one CUDA graph"]

