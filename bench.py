@@ -275,16 +275,16 @@ def run_ours(args, rank, world, local_rank):
     import mrm_b200
     from mrm_b200 import _lib, retrieval, synthetic
     from mrm_b200.engine import TwoTowerEngine
-    from mrm_b200.train import TrainStepRunner
+    from mrm_b200.train import TrainStepRunner, make_dp_engine
 
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
     peaks, peak_src = load_peaks()
     B, L, V = C2["batch"], C2["seq_len"], C2["vocab"]
     cfg = synthetic.TwoTowerConfig(vocab_size=V, max_seq_len=L, dropout=0.1)
-    eng = TwoTowerEngine(cfg, dev)
+    eng, table = make_dp_engine(cfg, world, dev)
     eng.load_state_dict(synthetic.make_state_dict(cfg, seed=0))
-    runner = TrainStepRunner(eng, B, L, world_size=world)
+    runner = TrainStepRunner(eng, B, L, world_size=world, sharded_table=table)
     host_batches = [pin(synthetic.make_batch(cfg, B, seed=100 + rank * 17 + i, full_length=True,
                                              num_users=1_000_000)) for i in range(4)]
     h2d_bytes = sum(v.numel() * v.element_size() for k, v in host_batches[0].items() if k in runner.static)
@@ -322,6 +322,7 @@ def run_ours(args, rank, world, local_rank):
     value = world * B * 1e3 / ms_step
     launches = runner.kernels_per_step * args.steps + (_lib.launch_count - l0)
     kernels_per_step, runner_comm = runner.kernels_per_step, runner.comm_description()
+    id_table_desc = "replicated on every rank" if table is None else table.describe()
 
     # ---- e2e: host batches, H2D + step + D2H of the loss every step -----------------------
     # Every step's batch crosses PCIe from pinned memory inside the timed region; the copy of batch i+1 is
@@ -366,6 +367,11 @@ def run_ours(args, rank, world, local_rank):
 
     # ---- roofline of the dominant kernel (tcgen05 GEMM) -----------------------------------
     g_all, g, gemm_launches = time_gemm_roofline(eng, runner.static, peaks)
+    if table is not None:        # those eager passes added gradient rows into the owners' shards: discard them
+        torch.cuda.synchronize()
+        dist.barrier()
+        table.grad.zero_()
+        table.barrier()
     peak_tf = peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops"))
     hbm_bound = g["byte_secs"] >= g["flop_secs"]
     if hbm_bound:
@@ -437,6 +443,7 @@ def run_ours(args, rank, world, local_rank):
                        "global_batch": world * B, "seq_len": L, "vocab_size": V,
                        "parallelism": f"dp{world}" if world > 1 else "single",
                        "negatives": ("all-gathered across ranks" if world > 1 else "in-batch"),
+                       "id_table": id_table_desc,
                        "comm": runner_comm,
                        "last_layer": "exact single-row form (only out[b, len-1] of the last encoder layer is ever "
                                      "read: K/V for all positions, query/out_proj/FFN for one row per sequence)",
@@ -522,12 +529,12 @@ def bench_c4(rank, world, dev, peaks, args):
     every rank's positives against the all-gathered items of all ranks."""
     from mrm_b200 import synthetic
     from mrm_b200.engine import TwoTowerEngine
-    from mrm_b200.train import TrainStepRunner
+    from mrm_b200.train import TrainStepRunner, make_dp_engine
     B, L, V = C4["batch"], C4["seq_len"], C4["vocab"]
     cfg = synthetic.TwoTowerConfig(vocab_size=V, max_seq_len=L, dropout=0.1)
-    eng = TwoTowerEngine(cfg, dev)
+    eng, table = make_dp_engine(cfg, world, dev)
     eng.load_state_dict(synthetic.make_state_dict(cfg, seed=0))
-    runner = TrainStepRunner(eng, B, L, world_size=world)
+    runner = TrainStepRunner(eng, B, L, world_size=world, sharded_table=table)
     hb = [pin(synthetic.make_batch(cfg, B, seed=500 + rank * 17 + i, full_length=True, num_users=1_000_000)) for i in range(2)]
     ms = _time_train(runner, hb, args.steps, args.warmup, dev, world)
     flops = 3.0 * flops_per_sample_fwd(L, world * B) * B            # per rank
@@ -537,8 +544,9 @@ def bench_c4(rank, world, dev, peaks, args):
            "global_batch": world * B, "ms_per_step": ms, "samples_per_s": world * B * 1e3 / ms,
            "step_tflops_per_gpu": flops / (ms * 1e-3) / 1e12, "roofline_frac_tensor": flops / (ms * 1e-3) / 1e12 / peak_tf,
            "roofline_ms_tensor_per_rank": flops / (peak_tf * 1e12) * 1e3,
+           "id_table": "replicated" if table is None else table.describe(),
            "kernels_per_step": runner.kernels_per_step, "comm": runner.comm_description()}
-    del runner, eng
+    del runner, eng, table
     return out
 
 

@@ -188,7 +188,10 @@ class TwoTowerEngine:
         (RowShardedTable.load_full takes it)."""
         sd = {(k[7:] if k.startswith("module.") else k): v for k, v in sd.items()}
         for name, t in self.p.items():
-            if (self.table_rows is not None or self.peer_table is not None) and name == "user_tower.item_embedding.weight":
+            if name == "user_tower.item_embedding.weight" and self.peer_table is not None:
+                self.peer_table.load_full(sd[name])       # every rank keeps the rows it owns
+                continue
+            if self.table_rows is not None and name == "user_tower.item_embedding.weight":
                 continue
             t.copy_(sd[name].to(device=self.device, dtype=torch.float32))
         it = "item_tower.fusion_layer.1."
@@ -200,6 +203,8 @@ class TwoTowerEngine:
 
     def state_dict(self) -> Dict[str, torch.Tensor]:
         out = {k: v.detach().clone() for k, v in self.p.items()}
+        if self.peer_table is not None:      # collective: the owners' shards are all-gathered
+            out["user_tower.item_embedding.weight"] = self.peer_table.gather_full()
         it = "item_tower.fusion_layer.1."
         out[it + "running_mean"] = self.bn_running_mean.clone()
         out[it + "running_var"] = self.bn_running_var.clone()

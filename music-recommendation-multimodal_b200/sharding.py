@@ -171,6 +171,7 @@ class SymmShardedTable:
 
     def load_full(self, full_table: torch.Tensor) -> None:
         self.weight[:self.rows].copy_(full_table[self.first:self.first + self.rows])
+        self.barrier()           # peers gather from this shard: nobody reads it before every owner has loaded
 
     def barrier(self) -> None:
         self.arena.barrier()

@@ -42,6 +42,30 @@ class FusedAdamW:
         self.engine.adamw_step(self.lr, self.betas, self.eps, self.weight_decay)
 
 
+def make_dp_engine(cfg, world_size: int, device=None, group=None, table: str = "auto"):
+    """(engine, table) for data-parallel training on ``world_size`` GPUs of one NVLink domain.
+
+    table="sharded" (what "auto" picks whenever a symmetric arena can be built): the ID table — 92 % of the
+    parameters at 100k items — is row-sharded over the ranks (sharding.SymmShardedTable) instead of replicated:
+    rows are gathered from / gradient rows added into the owner's memory over NVLink inside the embedding kernels
+    and each owner runs AdamW over its V / world rows. Per step and rank that moves B * L rows each way (52 MB at
+    batch 256 x 200) where the replicated table needs the whole 102 MB gradient reduced and the whole table
+    re-broadcast, and the optimizer touches 1 / world of the rows. Same arithmetic as the replicated step
+    (mean of the ranks' gradients, dense AdamW on every row). table="replicated": the reference's DDP layout."""
+    import dataclasses
+    from . import symm
+    from .sharding import SymmShardedTable
+    if table == "auto":
+        env = os.environ.get("TT_TABLE", "")
+        table = env if env in ("sharded", "replicated") else \
+            ("sharded" if world_size > 1 and symm.available(group) and os.environ.get("TT_COMM", "") != "nccl" else "replicated")
+    if table == "replicated" or world_size == 1:
+        return TwoTowerEngine(cfg, device), None
+    eng = TwoTowerEngine(dataclasses.replace(cfg, vocab_size=2), device)
+    eng.peer_table = SymmShardedTable(cfg.vocab_size, cfg.embedding_dim, group, eng.device)
+    return eng, eng.peer_table
+
+
 class TrainStepRunner:
     """One training step (src/train.py:54-65) over static device buffers, replayed as CUDA graphs.
 
