@@ -317,13 +317,26 @@ typedef struct tt_topk_plan {
 int tt_topk_plan_make(int U, int N, int kprime, tt_topk_plan* plan);
 int tt_score_topk(const void* users_bf16, const void* items_bf16, int item_base, const tt_topk_plan* plan,
                   void* cand, int32_t* cand_cnt, void* thr, void* smax, int mask_item0, void* stream);
+/* eps: bound on |bf16-path score - exact score| used by the certificate. Either a host value (eps_stats == NULL) or
+ * evaluated on the device from eps_stats = {max ||bf16(u)-u||, max ||u||} written by tt_users_prepare for this pass
+ * and the item-side constants ne_max = max ||bf16(e)||, de_max = max ||bf16(e)-e||: no host read precedes the launch. */
+int tt_users_prepare(const float* users_f32, void* users_bf16, int U, float* stats, void* stream);
 int tt_topk_finalize(const tt_topk_plan* plan, const void* cand, const int32_t* cand_cnt, const void* thr,
-                     const float* users_f32,
-                     const float* items_f32, int item_base, int K, float eps, int32_t* out_idx, float* out_score,
+                     const float* users_f32, const float* items_f32, int item_base, int K, float eps,
+                     const float* eps_stats, float ne_max, float de_max, int32_t* out_idx, float* out_score,
                      int32_t* flags, void* stream);
+/* bounded variant: user u's list goes to out_idx / out_score + u * ld_out, its bound and flag to out_bound / flags
+ * + u * ld_aux — with out_score = pack, out_idx = pack + K', out_bound = pack + 2K', flags = pack + 2K' + 1 and
+ * ld_out = ld_aux = 2K' + 2 the kernel writes the exchange buffer of retrieval.sharded_topk directly. */
 int tt_topk_finalize_bounded(const tt_topk_plan* plan, const void* cand, const int32_t* cand_cnt, const void* thr,
                              const float* users_f32, const float* items_f32, int item_base, float eps,
-                             int32_t* out_idx, float* out_score, float* out_bound, int32_t* flags, void* stream);
+                             const float* eps_stats, float ne_max, float de_max, int32_t* out_idx, float* out_score,
+                             int ld_out, float* out_bound, int32_t* flags, int ld_aux, void* stream);
+/* merge of the all-gathered exchange buffer in place: packed [G][U][ld] int32 words, row = [K_in scores | K_in global
+ * ids | bound | flag]; writes the merged top K_out and bad[u] = 1 where the certificate fails (K_out-th merged score
+ * does not beat every shard's bound, or a shard flagged a tie flood). */
+int tt_topk_merge_packed(const int32_t* packed, int ld, int G, int U, int K_in, int K_out, float* out_score,
+                         int32_t* out_idx, int32_t* bad, void* stream);
 int tt_topk_merge(const float* scores, const int32_t* idx, int G, int U, int K, float* out_score, int32_t* out_idx,
                   void* stream);
 int tt_topk_merge_lists(const float* scores, const int32_t* idx, int G, int U, int K_in, int K_out, float* out_score,

@@ -161,10 +161,14 @@ _SIGNATURES = {
     "tt_topk_plan_make": [c_int32, c_int32, c_int32, ctypes.POINTER(TopkPlan)],
     "tt_score_topk": [c_void_p, c_void_p, c_int32, ctypes.POINTER(TopkPlan), c_void_p, c_void_p, c_void_p, c_void_p,
                       c_int32, c_void_p],
-    "tt_topk_finalize": [ctypes.POINTER(TopkPlan), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_float,
-                         c_void_p, c_void_p, c_void_p, c_void_p],
-    "tt_topk_finalize_bounded": [ctypes.POINTER(TopkPlan), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_float,
-                                 c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
+    "tt_users_prepare": [c_void_p, c_void_p, c_int32, c_void_p, c_void_p],
+    "tt_topk_finalize": [ctypes.POINTER(TopkPlan), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32,
+                         c_float, c_void_p, c_float, c_float, c_void_p, c_void_p, c_void_p, c_void_p],
+    "tt_topk_finalize_bounded": [ctypes.POINTER(TopkPlan), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32,
+                                 c_float, c_void_p, c_float, c_float, c_void_p, c_void_p, c_int32, c_void_p, c_void_p,
+                                 c_int32, c_void_p],
+    "tt_topk_merge_packed": [c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p,
+                             c_void_p],
     "tt_topk_merge": [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p],
     "tt_topk_merge_lists": [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p],
     "tt_exact_topk": [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p],

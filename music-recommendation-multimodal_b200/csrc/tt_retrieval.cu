@@ -396,12 +396,23 @@ struct FinalizeParams {
   const unsigned long long* thr;  // [u_pad] published thresholds
   const float* users;   // [U, 256] fp32
   const float* items;   // [N, 256] fp32 (this shard)
-  float eps;            // bound on |bf16-path score - exact score|
-  int* out_idx;         // [U, K] global item index, -1 padded
-  float* out_score;     // [U, K]
-  int* flags;           // [U] 1 = certificate failed (fallback needed)
-  float* bound;         // bounded mode (non-null): [U] every item of the shard NOT in the list has exact score <= bound
+  float eps;            // bound on |bf16-path score - exact score| (host value), or, when eps_stats != nullptr,
+  const float* eps_stats;  // device {max ||bf16(u) - u||, max ||u||} of this pass (users_prepare_kernel):
+  float ne_max, de_max;    //   eps = du * ne_max + nu * de_max + nu * ne_max * 2^-18, evaluated on the device
+  int* out_idx;         // [U, ld_out] global item index, -1 padded
+  float* out_score;     // [U, ld_out]
+  int ld_out;           // elements between consecutive users in out_idx / out_score
+  int* flags;           // [U * ld_aux] 1 = certificate failed (fallback needed)
+  float* bound;         // bounded mode (non-null): [U * ld_aux] every item of the shard NOT in the list has exact score <= bound
+  int ld_aux;
 };
+
+__device__ __forceinline__ float finalize_eps(const FinalizeParams& p) {
+  if (p.eps_stats == nullptr) return p.eps;
+  const float du = p.eps_stats[0], nu = p.eps_stats[1];
+  // Cauchy-Schwarz on the bf16 rounding errors of both operands + fp32 accumulation slack, rounded up
+  return (du * p.ne_max + nu * p.de_max + nu * p.ne_max * 3.8146973e-06f) * 1.000001f;
+}
 
 __device__ __forceinline__ int block_sum_int(int v, int* s_red) {
 #pragma unroll
@@ -581,15 +592,16 @@ __global__ void __launch_bounds__(256) topk_finalize_kernel(const FinalizeParams
 
   for (int k = tid; k < p.K; k += 256) {
     const bool ok = k < nsel;
-    p.out_idx[static_cast<size_t>(u) * p.K + k] = ok ? static_cast<int>(key_idx(s_keys[k])) : -1;
-    p.out_score[static_cast<size_t>(u) * p.K + k] = ok ? key_score(s_keys[k]) : -INFINITY;
+    p.out_idx[static_cast<size_t>(u) * p.ld_out + k] = ok ? static_cast<int>(key_idx(s_keys[k])) : -1;
+    p.out_score[static_cast<size_t>(u) * p.ld_out + k] = ok ? key_score(s_keys[k]) : -INFINITY;
   }
+  const float eps = finalize_eps(p);
   if (tid == 0 && p.bound != nullptr) {
     // Bounded mode (sharded catalogs): the list is every candidate with bf16-path key >= T, re-scored
     // exactly; every other item of the shard has exact score <= score(T) + eps. The caller merges the
     // shards' lists and checks that the merged K-th score beats every shard's bound.
-    p.bound[u] = overflow ? INFINITY : (T == 0ull ? -INFINITY : key_score(T) + p.eps);
-    p.flags[u] = overflow ? 1 : 0;
+    p.bound[static_cast<size_t>(u) * p.ld_aux] = overflow ? INFINITY : (T == 0ull ? -INFINITY : key_score(T) + eps);
+    p.flags[static_cast<size_t>(u) * p.ld_aux] = overflow ? 1 : 0;
   } else if (tid == 0) {
     // Certificate: every non-candidate has bf16-path key < T, hence exact score <= score(T) + eps.
     // If the exact K-th best beats that, no non-candidate can enter the top K.
@@ -597,9 +609,9 @@ __global__ void __launch_bounds__(256) topk_finalize_kernel(const FinalizeParams
     int flag = overflow ? 1 : 0;
     if (!overflow && T != 0ull) {
       if (nsel < p.K) flag = 1;   // the start threshold was too high for this user
-      else flag = !(key_score(s_keys[p.K - 1]) > key_score(T) + p.eps);
+      else flag = !(key_score(s_keys[p.K - 1]) > key_score(T) + eps);
     }
-    p.flags[u] = flag;
+    p.flags[static_cast<size_t>(u) * p.ld_aux] = flag;
   }
 }
 
@@ -607,19 +619,26 @@ __global__ void __launch_bounds__(256) topk_finalize_kernel(const FinalizeParams
 // Cross-shard merge: lists [G][U][K] of (score, global idx) sorted canonically per shard ->
 // top K of their union, canonical order. One block per user; G*K <= 1024.
 // --------------------------------------------------------------------------------------------
+// Rows of shard g / user u start at (g * U + u) * row_stride in `scores` and `idx` (two views of one packed buffer
+// or two separate arrays). aux != nullptr (packed exchange buffer, retrieval.sharded_topk): aux[(g*U+u)*row_stride]
+// is the shard's completeness bound (fp32 bits) and the next word its tie-flood flag; then bad[u] receives the
+// merged list's certificate: 0 iff the K_out-th merged score beats every shard's bound (or every shard listed all
+// of its items) and no shard flagged the user.
 __global__ void __launch_bounds__(256) topk_merge_kernel(const float* __restrict__ scores, const int* __restrict__ idx,
+                                                         long long row_stride, const int* __restrict__ aux,
                                                          int G, int U, int K, int K_out, float* __restrict__ out_score,
-                                                         int* __restrict__ out_idx) {
+                                                         int* __restrict__ out_idx, int* __restrict__ bad) {
   pdl_launch_dependents();
   pdl_wait();
   extern __shared__ unsigned long long s_all[];  // G*K keys
   __shared__ int s_written;
+  __shared__ float s_kth;
   const int u = blockIdx.x;
   const int n = G * K;
-  if (threadIdx.x == 0) s_written = 0;
+  if (threadIdx.x == 0) { s_written = 0; s_kth = -INFINITY; }
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
     const int g = i / K, k = i % K;
-    const size_t o = (static_cast<size_t>(g) * U + u) * K + k;
+    const size_t o = (static_cast<size_t>(g) * U + u) * row_stride + k;
     const int id = idx[o];
     s_all[i] = id < 0 ? 0ull : make_key(scores[o], static_cast<uint32_t>(id));
   }
@@ -634,11 +653,23 @@ __global__ void __launch_bounds__(256) topk_merge_kernel(const float* __restrict
     if (rank < K_out) {
       out_score[static_cast<size_t>(u) * K_out + rank] = key_score(k);
       out_idx[static_cast<size_t>(u) * K_out + rank] = static_cast<int>(key_idx(k));
+      if (rank == K_out - 1) s_kth = key_score(k);
       ++written;
     }
   }
   if (written) atomicAdd(&s_written, written);
   __syncthreads();
+  if (bad != nullptr && threadIdx.x == 0) {
+    float bmax = -INFINITY;
+    int flagged = 0;
+    for (int g = 0; g < G; ++g) {
+      const size_t o = (static_cast<size_t>(g) * U + u) * row_stride;
+      bmax = fmaxf(bmax, __int_as_float(aux[o]));
+      flagged |= aux[o + 1];
+    }
+    const bool ok = s_written >= K_out ? (s_kth > bmax) : (bmax == -INFINITY);
+    bad[u] = (!ok || flagged) ? 1 : 0;
+  }
   // fewer than K_out items in the union: pad the tail
   for (int k = s_written + threadIdx.x; k < K_out; k += blockDim.x) {
     out_score[static_cast<size_t>(u) * K_out + k] = -INFINITY;
@@ -746,9 +777,48 @@ __global__ void rank_metrics_kernel(const int* __restrict__ topk, const int64_t*
   }
 }
 
+// fp32 user rows -> bf16 operand rows, plus the two user-side terms of the scoring-error bound for THIS pass:
+// stats[0] = max_u ||bf16(u) - u||_2, stats[1] = max_u ||u||_2 (non-negative floats: integer atomicMax on the bits).
+__global__ void __launch_bounds__(256) users_prepare_kernel(const float* __restrict__ users, __nv_bfloat16* __restrict__ out,
+                                                            int U, float* __restrict__ stats) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int u = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (u >= U) return;
+  float d2 = 0.f, n2 = 0.f;
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const float4 x = __ldg(reinterpret_cast<const float4*>(users + static_cast<size_t>(u) * kD) + k * 32 + lane);
+    uint2 b;
+    b.x = pack_bf16(x.x, x.y);
+    b.y = pack_bf16(x.z, x.w);
+    reinterpret_cast<uint2*>(out + static_cast<size_t>(u) * kD)[k * 32 + lane] = b;
+    const float2 r0 = unpack_bf16(b.x), r1 = unpack_bf16(b.y);
+    const float e0 = r0.x - x.x, e1 = r0.y - x.y, e2 = r1.x - x.z, e3 = r1.y - x.w;
+    d2 += e0 * e0 + e1 * e1 + e2 * e2 + e3 * e3;
+    n2 += x.x * x.x + x.y * x.y + x.z * x.z + x.w * x.w;
+  }
+  d2 = warp_sum(d2);
+  n2 = warp_sum(n2);
+  if (lane == 0) {
+    // rounded up by a few ulps: these feed an upper bound
+    atomicMax(reinterpret_cast<int*>(stats), __float_as_int(sqrtf(d2) * 1.00001f));
+    atomicMax(reinterpret_cast<int*>(stats) + 1, __float_as_int(sqrtf(n2) * 1.00001f));
+  }
+}
+
 }  // namespace tt
 
 using namespace tt;
+
+extern "C" int tt_users_prepare(const float* users_f32, void* users_bf16, int U, float* stats, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  TT_REQUIRE(users_f32 && users_bf16 && stats && U > 0, "tt_users_prepare: bad arguments");
+  TT_CHECK_CUDA(cudaMemsetAsync(stats, 0, 2 * sizeof(float), stream));
+  TT_CHECK_CUDA(launch_k(users_prepare_kernel, dim3((U * 32 + 255) / 256), dim3(256), 0, stream, users_f32, static_cast<__nv_bfloat16*>(users_bf16), U, stats));
+  TT_LAUNCH_CHECK();
+  return TT_OK;
+}
 
 
 // persistent CTA pairs the launch will run: one per two SMs
@@ -906,44 +976,48 @@ extern "C" int tt_score_topk(const void* users_bf16, const void* items_bf16, int
   return launch_score_topk(users_bf16, items_bf16, p, plan->N, stream);
 }
 
-static int finalize_impl(const tt_topk_plan* plan, const void* cand, const int32_t* cand_cnt, const void* thr,
-                         const float* users_f32, const float* items_f32, int item_base, int K, float eps,
-                         int32_t* out_idx, float* out_score, int32_t* flags, float* bound, void* stream_);
-
-extern "C" int tt_topk_finalize(const tt_topk_plan* plan, const void* cand, const int32_t* cand_cnt, const void* thr,
-                                const float* users_f32, const float* items_f32, int item_base, int K, float eps,
-                                int32_t* out_idx, float* out_score, int32_t* flags, void* stream_) {
-  return finalize_impl(plan, cand, cand_cnt, thr, users_f32, items_f32, item_base, K, eps, out_idx, out_score, flags,
-                       nullptr, stream_);
-}
-
-extern "C" int tt_topk_finalize_bounded(const tt_topk_plan* plan, const void* cand, const int32_t* cand_cnt,
-                                        const void* thr, const float* users_f32, const float* items_f32, int item_base,
-                                        float eps, int32_t* out_idx, float* out_score, float* out_bound,
-                                        int32_t* flags, void* stream_) {
-  TT_REQUIRE(plan && out_bound, "tt_topk_finalize_bounded: null pointer");
-  return finalize_impl(plan, cand, cand_cnt, thr, users_f32, items_f32, item_base, plan->kprime, eps, out_idx, out_score,
-                       flags, out_bound, stream_);
-}
+struct EpsSpec { float eps; const float* stats; float ne_max, de_max; };
 
 static int finalize_impl(const tt_topk_plan* plan, const void* cand, const int32_t* cand_cnt, const void* thr,
-                         const float* users_f32, const float* items_f32, int item_base, int K, float eps,
-                         int32_t* out_idx, float* out_score, int32_t* flags, float* bound, void* stream_) {
+                         const float* users_f32, const float* items_f32, int item_base, int K, EpsSpec eps,
+                         int32_t* out_idx, float* out_score, int ld_out, int32_t* flags, float* bound, int ld_aux,
+                         void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   TT_REQUIRE(plan && cand && cand_cnt && thr && users_f32 && items_f32 && out_idx && out_score && flags,
              "tt_topk_finalize: null pointer");
   TT_REQUIRE(K > 0 && K <= plan->kprime, "tt_topk_finalize: K=%d must be in [1, kprime=%d]", K, plan->kprime);
+  TT_REQUIRE(ld_out >= K && ld_aux >= 1, "tt_topk_finalize: output strides too small");
   TT_REQUIRE(plan->n_ranges * kLists <= kMaxLists, "tt_topk_finalize: %d candidate lists per user exceed %d",
              plan->n_ranges * kLists, kMaxLists);
   FinalizeParams p;
   p.U = plan->U; p.N = plan->N; p.item_base = item_base; p.n_ranges = plan->n_ranges * kLists;   // lists per row
   p.u_pad = plan->n_ut * kUT; p.kprime = plan->kprime; p.K = K;
   p.cand = static_cast<const unsigned long long*>(cand);
-  p.cand_cnt = cand_cnt; p.thr = static_cast<const unsigned long long*>(thr); p.users = users_f32; p.items = items_f32; p.eps = eps;
-  p.out_idx = out_idx; p.out_score = out_score; p.flags = flags; p.bound = bound;
+  p.cand_cnt = cand_cnt; p.thr = static_cast<const unsigned long long*>(thr); p.users = users_f32; p.items = items_f32;
+  p.eps = eps.eps; p.eps_stats = eps.stats; p.ne_max = eps.ne_max; p.de_max = eps.de_max;
+  p.out_idx = out_idx; p.out_score = out_score; p.ld_out = ld_out; p.flags = flags; p.bound = bound; p.ld_aux = ld_aux;
   TT_CHECK_CUDA(launch_k(topk_finalize_kernel, dim3(plan->U), dim3(256), 0, stream, p));
   TT_LAUNCH_CHECK();
   return TT_OK;
+}
+
+extern "C" int tt_topk_finalize(const tt_topk_plan* plan, const void* cand, const int32_t* cand_cnt, const void* thr,
+                                const float* users_f32, const float* items_f32, int item_base, int K, float eps,
+                                const float* eps_stats, float ne_max, float de_max,
+                                int32_t* out_idx, float* out_score, int32_t* flags, void* stream_) {
+  return finalize_impl(plan, cand, cand_cnt, thr, users_f32, items_f32, item_base, K, EpsSpec{eps, eps_stats, ne_max, de_max},
+                       out_idx, out_score, K, flags, nullptr, 1, stream_);
+}
+
+extern "C" int tt_topk_finalize_bounded(const tt_topk_plan* plan, const void* cand, const int32_t* cand_cnt,
+                                        const void* thr, const float* users_f32, const float* items_f32, int item_base,
+                                        float eps, const float* eps_stats, float ne_max, float de_max,
+                                        int32_t* out_idx, float* out_score, int ld_out, float* out_bound,
+                                        int32_t* flags, int ld_aux, void* stream_) {
+  TT_REQUIRE(plan && out_bound, "tt_topk_finalize_bounded: null pointer");
+  return finalize_impl(plan, cand, cand_cnt, thr, users_f32, items_f32, item_base, plan->kprime,
+                       EpsSpec{eps, eps_stats, ne_max, de_max}, out_idx, out_score, ld_out, flags, out_bound, ld_aux,
+                       stream_);
 }
 
 extern "C" int tt_topk_merge(const float* scores, const int32_t* idx, int G, int U, int K, float* out_score,
@@ -957,7 +1031,18 @@ extern "C" int tt_topk_merge_lists(const float* scores, const int32_t* idx, int 
   TT_REQUIRE(scores && idx && out_score && out_idx && G > 0 && U > 0 && K_in > 0 && K_out > 0,
              "tt_topk_merge_lists: bad arguments");
   TT_REQUIRE(G * K_in <= 4096, "tt_topk_merge_lists: G*K_in = %d too large", G * K_in);
-  TT_CHECK_CUDA(launch_k(topk_merge_kernel, dim3(U), dim3(256), static_cast<size_t>(G) * K_in * 8, stream, scores, idx, G, U, K_in, K_out, out_score, out_idx));
+  TT_CHECK_CUDA(launch_k(topk_merge_kernel, dim3(U), dim3(256), static_cast<size_t>(G) * K_in * 8, stream, scores, idx, static_cast<long long>(K_in), static_cast<const int*>(nullptr), G, U, K_in, K_out, out_score, out_idx, static_cast<int*>(nullptr)));
+  TT_LAUNCH_CHECK();
+  return TT_OK;
+}
+
+extern "C" int tt_topk_merge_packed(const int32_t* packed, int ld, int G, int U, int K_in, int K_out, float* out_score,
+                                    int32_t* out_idx, int32_t* bad, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  TT_REQUIRE(packed && out_score && out_idx && bad && G > 0 && U > 0 && K_in > 0 && K_out > 0 && ld >= 2 * K_in + 2,
+             "tt_topk_merge_packed: bad arguments");
+  TT_REQUIRE(G * K_in <= 4096, "tt_topk_merge_packed: G*K_in = %d too large", G * K_in);
+  TT_CHECK_CUDA(launch_k(topk_merge_kernel, dim3(U), dim3(256), static_cast<size_t>(G) * K_in * 8, stream, reinterpret_cast<const float*>(packed), packed + K_in, static_cast<long long>(ld), packed + 2 * K_in, G, U, K_in, K_out, out_score, out_idx, bad));
   TT_LAUNCH_CHECK();
   return TT_OK;
 }

@@ -113,9 +113,21 @@ class CatalogIndex:
                 "thr": torch.empty(p.thr_bytes // 8, device=dev, dtype=torch.int64),
                 "smax": (torch.empty(p.smax_bytes // 4, device=dev, dtype=torch.float32) if p.smax_bytes else None),
                 "users_bf16": torch.empty(U, 256, device=dev, dtype=torch.bfloat16),
+                "eps_stats": torch.zeros(2, device=dev),
                 "keys": None,
             }
         return self._plans[key]
+
+
+def exchange_buffers(index, U: int, ld: int, world: int) -> Dict[str, torch.Tensor]:
+    """Reused buffers of the sharded protocol: this shard's packed lists, the all-gathered ones, the flags."""
+    key = ("xchg", U, ld, world)
+    if key not in index._scratch:
+        dev = index.table.device
+        index._scratch[key] = {"pack": torch.empty(U, ld, device=dev, dtype=torch.int32),
+                               "all": torch.empty(world * U, ld, device=dev, dtype=torch.int32),
+                               "bad": torch.zeros(U, device=dev, dtype=torch.int32)}
+    return index._scratch[key]
 
 
 def retrieve_topk(user_emb: torch.Tensor, index: CatalogIndex, K: int, kprime: int = 256,
@@ -131,7 +143,7 @@ def retrieve_topk(user_emb: torch.Tensor, index: CatalogIndex, K: int, kprime: i
     user_emb = user_emb.contiguous()
     U = user_emb.shape[0]
     kprime = max(kprime, K)
-    plan, sc, eps = _score_pass(user_emb, index, kprime, mask_item0)
+    plan, sc = _score_pass(user_emb, index, kprime, mask_item0)
     dev = user_emb.device
     out_idx = torch.empty(U, K, device=dev, dtype=torch.int32)
     out_score = torch.empty(U, K, device=dev, dtype=torch.float32)
@@ -139,7 +151,8 @@ def retrieve_topk(user_emb: torch.Tensor, index: CatalogIndex, K: int, kprime: i
     assert flags.dtype == torch.int32 and flags.numel() == U and flags.is_cuda
     check(lib().tt_topk_finalize(ctypes.byref(plan), sc["cand"].data_ptr(), sc["cnt"].data_ptr(),
                                  sc["thr"].data_ptr(), user_emb.data_ptr(),
-                                 index.table.data_ptr(), index.item_base, K, eps, out_idx.data_ptr(),
+                                 index.table.data_ptr(), index.item_base, K, 0.0, sc["eps_stats"].data_ptr(),
+                                 index.ne_max, index.de_max, out_idx.data_ptr(),
                                  out_score.data_ptr(), flags.data_ptr(), _stream()), "tt_topk_finalize")
     n_fallback = 0
     if exact_fallback:
@@ -156,44 +169,49 @@ def retrieve_topk(user_emb: torch.Tensor, index: CatalogIndex, K: int, kprime: i
 
 
 def _score_pass(user_emb: torch.Tensor, index: "CatalogIndex", kprime: int, mask_item0: bool):
-    """bf16 scoring + streaming candidate selection of this shard (tt_score_topk); returns (plan, scratch, eps)."""
+    """bf16 scoring + streaming candidate selection of this shard (tt_score_topk); returns (plan, scratch).
+    The user-side terms of the certificate's error bound (max ||bf16(u) - u||, max ||u||) are reduced on the device by
+    the cast kernel into scratch['eps_stats'] and combined with the index's item-side terms inside the finalize kernel
+    (rigorous bound on |u^.e^ - u.e|: Cauchy-Schwarz on the bf16 rounding errors + fp32 accumulation slack) — nothing
+    is read back to the host before or between the launches."""
     U = user_emb.shape[0]
     plan = index.plan(U, kprime)
     sc = index._scratch[(U, kprime)]
-    ops.cast_bf16(user_emb.view(-1), sc["users_bf16"].view(-1))
-    # rigorous bound on |u^.e^ - u.e| (Cauchy-Schwarz on the bf16 rounding errors) + fp32 accumulation slack.
-    # Its host read-back happens BEFORE the scoring pass is queued, so scoring and finalize run back to back.
-    u16 = sc["users_bf16"].float()
-    du = (u16 - user_emb).norm(dim=1).max()
-    nu = user_emb.norm(dim=1).max()
-    eps = float((du * index.ne_max + nu * index.de_max + nu * index.ne_max * 2.0 ** -18).item())
+    check(lib().tt_users_prepare(user_emb.data_ptr(), sc["users_bf16"].data_ptr(), U, sc["eps_stats"].data_ptr(),
+                                 _stream()), "tt_users_prepare")
     check(lib().tt_score_topk(sc["users_bf16"].data_ptr(), index.table_bf16.data_ptr(), index.item_base,
                               ctypes.byref(plan), sc["cand"].data_ptr(), sc["cnt"].data_ptr(), sc["thr"].data_ptr(),
                               None if sc["smax"] is None else sc["smax"].data_ptr(), int(mask_item0), _stream()),
           "tt_score_topk")
-    return plan, sc, eps
+    return plan, sc
 
 
-def retrieve_candidates(user_emb: torch.Tensor, index: "CatalogIndex", kprime: int, mask_item0: bool = True):
+def retrieve_candidates(user_emb: torch.Tensor, index: "CatalogIndex", kprime: int, mask_item0: bool = True,
+                        pack: Optional[torch.Tensor] = None):
     """Sharded catalogs: ALL ``kprime`` candidates of this shard per user, re-scored exactly.
 
     Returns (idx int32 (U, kprime) global ids, -1 padded; score fp32 (U, kprime); bound fp32 (U,): every item of
     the shard that is not in the list has exact score <= bound; overflow int32 (U,): 1 = tie flood, use the exact
-    path). With G shards a shard needs about 1/G of the single-GPU candidate budget (`shard_kprime`)."""
+    path). With G shards a shard needs about 1/G of the single-GPU candidate budget (`shard_kprime`).
+    ``pack`` int32 (U, 2 * kprime + 2): the kernel writes the exchange layout [scores | ids | bound | flag] of
+    `sharded_topk` directly and the four results are views of it."""
     assert user_emb.is_cuda and user_emb.dtype == torch.float32 and user_emb.shape[1] == 256
     user_emb = user_emb.contiguous()
     U = user_emb.shape[0]
-    plan, sc, eps = _score_pass(user_emb, index, kprime, mask_item0)
+    plan, sc = _score_pass(user_emb, index, kprime, mask_item0)
     dev = user_emb.device
-    out_idx = torch.empty(U, kprime, device=dev, dtype=torch.int32)
-    out_score = torch.empty(U, kprime, device=dev, dtype=torch.float32)
-    bound = torch.empty(U, device=dev, dtype=torch.float32)
-    flags = torch.empty(U, device=dev, dtype=torch.int32)
+    ld = 2 * kprime + 2
+    if pack is None:
+        pack = torch.empty(U, ld, device=dev, dtype=torch.int32)
+    assert pack.dtype == torch.int32 and pack.shape == (U, ld) and pack.is_contiguous()
+    base = pack.data_ptr()
     check(lib().tt_topk_finalize_bounded(ctypes.byref(plan), sc["cand"].data_ptr(), sc["cnt"].data_ptr(),
                                          sc["thr"].data_ptr(), user_emb.data_ptr(), index.table.data_ptr(),
-                                         index.item_base, eps, out_idx.data_ptr(), out_score.data_ptr(),
-                                         bound.data_ptr(), flags.data_ptr(), _stream()), "tt_topk_finalize_bounded")
-    return out_idx, out_score, bound, flags
+                                         index.item_base, 0.0, sc["eps_stats"].data_ptr(), index.ne_max, index.de_max,
+                                         base + 4 * kprime, base, ld, base + 8 * kprime, base + 8 * kprime + 4, ld,
+                                         _stream()), "tt_topk_finalize_bounded")
+    return (pack[:, kprime:2 * kprime], pack[:, :kprime].view(torch.float32), pack[:, 2 * kprime].view(torch.float32),
+            pack[:, 2 * kprime + 1])
 
 
 #: users of the most recent `sharded_topk` call that needed the per-shard exact fallback (bench bookkeeping)
@@ -226,12 +244,14 @@ def merge_bounded(scores: torch.Tensor, idx: torch.Tensor, bounds: torch.Tensor,
 
 
 def sharded_topk(user_emb: torch.Tensor, index: "CatalogIndex", K: int, kprime: int = 256, group=None,
-                 bounded: Optional[bool] = None):
+                 bounded: Optional[bool] = None, defer_check: bool = False):
     """Exact global top K over a catalog sharded across the ranks of ``group`` (every rank gets the result).
 
     bounded protocol (default from 4 shards): per-shard candidate lists of `shard_kprime` entries +
     completeness bounds, one all-gather, merge + certificate; users whose certificate fails (and only those) go
-    through the per-shard exact top-K protocol. ``bounded=False`` (default below 4 shards) always uses the latter."""
+    through the per-shard exact top-K protocol. ``bounded=False`` (default below 4 shards) always uses the latter.
+    ``defer_check=True`` (bounded protocol only) returns (idx, score, bad) without reading the certificate back:
+    the caller checks ``bad`` together with its own read-back and calls `finish_sharded_topk` if any flag is set."""
     import torch.distributed as dist
     ws = dist.get_world_size(group)
     index.check_group(user_emb.shape[0], group)
@@ -255,34 +275,60 @@ def sharded_topk(user_emb: torch.Tensor, index: "CatalogIndex", K: int, kprime: 
     global last_fallback_users
     last_fallback_users = 0
     if not bounded or K > ws * shard_kprime(kprime, ws):
-        return per_shard_exact(user_emb)
+        out = per_shard_exact(user_emb)
+        return (out[0], out[1], torch.zeros(user_emb.shape[0], device=user_emb.device, dtype=torch.int32)) \
+            if defer_check else out
     kps = shard_kprime(kprime, ws)
-    i, s, b, f = retrieve_candidates(user_emb, index, kps)
     U = user_emb.shape[0]
-    # one packed all-gather: [U, kps] scores | [U, kps] ids | bound | overflow flag, as int32 words
-    pack = torch.empty(U, 2 * kps + 2, device=s.device, dtype=torch.int32)
-    pack[:, :kps] = s.view(torch.int32)
-    pack[:, kps:2 * kps] = i
-    pack[:, 2 * kps] = b.view(torch.int32)
-    pack[:, 2 * kps + 1] = f
-    allp = torch.empty(ws * U, 2 * kps + 2, device=s.device, dtype=torch.int32)
-    dist.all_gather_into_tensor(allp, pack, group=group)
-    allp = allp.view(ws, U, 2 * kps + 2)
-    all_s = allp[:, :, :kps].contiguous().view(torch.float32)
-    all_i = allp[:, :, kps:2 * kps].contiguous()
-    all_b = allp[:, :, 2 * kps].contiguous().view(torch.float32)
-    out_i, out_s, bad = merge_bounded(all_s, all_i, all_b, K)
-    bad |= allp[:, :, 2 * kps + 1].any(dim=0)
-    if bool(bad.any().item()):            # identical on every rank: the inputs of the test were all-gathered
-        sel = torch.nonzero(bad).flatten()
-        n = sel.numel()
-        last_fallback_users = n
-        # scratch buffers are cached per user count: pad to a multiple of 256 (repeating the first user) so that
-        # a long evaluation with a few uncertified users per batch does not accumulate one scratch set per count
-        padded = torch.cat([sel, sel[:1].expand((-n) % 256)])
-        fi, fs = per_shard_exact(user_emb[padded].contiguous())
-        out_i[sel], out_s[sel] = fi[:n], fs[:n]
+    ld = 2 * kps + 2
+    buf = exchange_buffers(index, U, ld, ws)
+    # the finalize kernel writes this shard's lists, bounds and flags in the exchange layout; ONE all-gather; the merge
+    # kernel reads the gathered buffer in place and emits the certificate
+    retrieve_candidates(user_emb, index, kps, pack=buf["pack"])
+    dist.all_gather_into_tensor(buf["all"], buf["pack"], group=group)
+    bad = buf["bad"]
+    out_i, out_s = merge_packed(buf["all"], ws, U, kps, K, bad)
+    if defer_check:
+        return out_i, out_s, bad
+    finish_sharded_topk(user_emb, index, K, out_i, out_s, bad, kprime, group)
     return out_i, out_s
+
+
+def merge_packed(allp: torch.Tensor, G: int, U: int, kps: int, K: int, bad: torch.Tensor):
+    """Merge the all-gathered exchange buffer [G * U, 2 * kps + 2] (rows [scores | ids | bound | flag]) into the global
+    top K per user, in place of any unpacking; ``bad`` (int32 (U,)) receives the certificate (1 = not certified)."""
+    out_s = torch.empty(U, K, device=allp.device, dtype=torch.float32)
+    out_i = torch.empty(U, K, device=allp.device, dtype=torch.int32)
+    check(lib().tt_topk_merge_packed(allp.data_ptr(), 2 * kps + 2, G, U, kps, K, out_s.data_ptr(), out_i.data_ptr(),
+                                     bad.data_ptr(), _stream()), "tt_topk_merge_packed")
+    return out_i, out_s
+
+
+def finish_sharded_topk(user_emb, index, K, out_i, out_s, bad, kprime: int = 256, group=None) -> int:
+    """Second half of the bounded protocol: users whose merged list is not certified (`bad`, identical on every rank
+    because it was computed from all-gathered data) go through the per-shard exact top-K + merge, in place. One host
+    read of the flags; returns the number of such users. Collective."""
+    import torch.distributed as dist
+    global last_fallback_users
+    ws = dist.get_world_size(group)
+    sel = torch.nonzero(bad).flatten()        # host sync: the (rare) fallback is a different launch sequence
+    n = sel.numel()
+    last_fallback_users = n
+    if n == 0:
+        return 0
+    # scratch buffers are cached per user count: pad to a multiple of 256 (repeating the first user) so that
+    # a long evaluation with a few uncertified users per batch does not accumulate one scratch set per count
+    padded = torch.cat([sel, sel[:1].expand((-n) % 256)])
+    users = user_emb[padded].contiguous()
+    i, s, _ = retrieve_topk(users, index, K, kprime)
+    m = s.shape[0]
+    all_s = torch.empty(ws * m, K, device=s.device, dtype=s.dtype)
+    all_i = torch.empty(ws * m, K, device=i.device, dtype=i.dtype)
+    dist.all_gather_into_tensor(all_s, s.contiguous(), group=group)
+    dist.all_gather_into_tensor(all_i, i.contiguous(), group=group)
+    fi, fs = merge_topk(all_s.view(ws, m, K), all_i.view(ws, m, K))
+    out_i[sel], out_s[sel] = fi[:n], fs[:n]
+    return n
 
 
 def merge_topk(scores: torch.Tensor, idx: torch.Tensor):
@@ -324,12 +370,23 @@ def metrics_from_embeddings(user_emb: torch.Tensor, targets: torch.Tensor, index
     does not depend on the number of shards. An unsharded index never communicates, whatever process group
     happens to be initialised (every rank then evaluates its own users against the whole catalog)."""
     K = max(k_list)
+    targets = targets.to(user_emb.device)
     if index.is_sharded:
-        idx, score = sharded_topk(user_emb, index, K, kprime, group)
+        # the certificate flags travel to the host WITH the metrics: one synchronisation per call; only if a flag is
+        # set (rare) the exact per-shard protocol repairs those users and the metrics are taken again
+        idx, score, bad = sharded_topk(user_emb, index, K, kprime, group, defer_check=True)
+        recall, ndcg = rank_metrics(idx, targets, k_list)
+        packed = torch.cat([recall.flatten(), ndcg.flatten(), bad.max().float().view(1)]).cpu()
+        if packed[-1].item() != 0:
+            finish_sharded_topk(user_emb, index, K, idx, score, bad, kprime, group)
+            recall, ndcg = rank_metrics(idx, targets, k_list)
+            packed = torch.cat([recall.flatten(), ndcg.flatten()]).cpu()
+        r = packed[:recall.numel()].view(recall.shape)
+        n = packed[recall.numel():2 * recall.numel()].view(ndcg.shape)
     else:
         idx, score, _ = retrieve_topk(user_emb, index, K, kprime)
-    recall, ndcg = rank_metrics(idx, targets.to(idx.device), k_list)
-    r, n = recall.cpu(), ndcg.cpu()     # the mean is taken on the host exactly like the reference (:188-190)
+        recall, ndcg = rank_metrics(idx, targets, k_list)
+        r, n = recall.cpu(), ndcg.cpu()     # the mean is taken on the host exactly like the reference (:188-190)
     out = {}
     for j, k in enumerate(k_list):
         out[f"Recall@{k}"] = r[j].mean().item()

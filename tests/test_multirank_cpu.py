@@ -123,7 +123,7 @@ class _CpuShard:
     def __init__(self, table, first, rows):
         from mrm_b200 import retrieval
         self.table, self.item_base, self.vocab_size = table[first:first + rows], first, table.shape[0]
-        self.is_sharded, self._group_checked = True, set()
+        self.is_sharded, self._group_checked, self._scratch = True, set(), {}
         self.check_group = lambda U, group=None: retrieval.CatalogIndex.check_group(self, U, group)
 
     @property
@@ -151,7 +151,8 @@ def _sharded_topk_plumbing_worker(rank, world, K, kps):
         v, i = oracle.canonical_topk(shard_scores(u, ix), k)
         return (i + ix.item_base).to(torch.int32), v, 0
 
-    def retrieve_candidates(u, ix, kprime, mask_item0=True):
+    def retrieve_candidates(u, ix, kprime, mask_item0=True, pack=None):
+        """writes the exchange layout [scores | ids | bound | flag] like tt_topk_finalize_bounded"""
         sc = shard_scores(u, ix)
         n = min(kprime, sc.shape[1])
         v, i = oracle.canonical_topk(sc, n)
@@ -159,11 +160,20 @@ def _sharded_topk_plumbing_worker(rank, world, K, kps):
         out_i = torch.full((u.shape[0], kprime), -1, dtype=torch.int32)
         out_v[:, :n], out_i[:, :n] = v, (i + ix.item_base).to(torch.int32)
         bound = v[:, -1].clone() if n < sc.shape[1] else torch.full((u.shape[0],), float("-inf"))
+        pack[:, :kprime] = out_v.view(torch.int32)
+        pack[:, kprime:2 * kprime] = out_i
+        pack[:, 2 * kprime] = bound.view(torch.int32)
+        pack[:, 2 * kprime + 1] = 0
         return out_i, out_v, bound, torch.zeros(u.shape[0], dtype=torch.int32)
 
-    def merge_bounded(sc, ix, bd, k):
-        i, v, ok = sharding.merge_bounded_reference(sc, ix, bd, k)
-        return i, v, ~ok
+    def merge_packed(allp, G, U, kp, k, bad):
+        """reference semantics of tt_topk_merge_packed on the gathered exchange buffer"""
+        a = allp.view(G, U, 2 * kp + 2)
+        i, v, ok = sharding.merge_bounded_reference(a[:, :, :kp].contiguous().view(torch.float32),
+                                                    a[:, :, kp:2 * kp].contiguous(),
+                                                    a[:, :, 2 * kp].contiguous().view(torch.float32), k)
+        bad.copy_((~ok | a[:, :, 2 * kp + 1].any(dim=0)).to(torch.int32))
+        return i, v
 
     calls = {"fallback_users": 0}
 
@@ -171,11 +181,11 @@ def _sharded_topk_plumbing_worker(rank, world, K, kps):
         calls["fallback_users"] = sc.shape[1]
         return merge_canonical(sc, ix)
 
-    saved = {n: getattr(retrieval, n) for n in ("retrieve_topk", "retrieve_candidates", "merge_bounded", "merge_topk",
+    saved = {n: getattr(retrieval, n) for n in ("retrieve_topk", "retrieve_candidates", "merge_packed", "merge_topk",
                                                 "shard_kprime")}
     try:
         retrieval.retrieve_topk, retrieval.retrieve_candidates = retrieve_topk, retrieve_candidates
-        retrieval.merge_bounded, retrieval.merge_topk = merge_bounded, merge_topk
+        retrieval.merge_packed, retrieval.merge_topk = merge_packed, merge_topk
         retrieval.shard_kprime = lambda kprime, shards: kps
         mi, mv = retrieval.sharded_topk(users, index, K, bounded=True)
         fallback_users = calls["fallback_users"]

@@ -86,16 +86,24 @@ def test_sharded_equals_unsharded_and_merge():
 
 
 def _bounded_shards(table, users, cuts, kps, K):
+    """The exchange of retrieval.sharded_topk replayed on one GPU: every shard's finalize kernel writes its slot of
+    the gathered buffer in the packed layout, tt_topk_merge_packed merges it in place and emits the certificate.
+    Cross-checked against the stacked-tensor route (tt_topk_merge_lists + torch certificate)."""
     from mrm_b200 import retrieval
+    G, U = len(cuts) - 1, users.shape[0]
+    allp = torch.empty(G * U, 2 * kps + 2, device="cuda", dtype=torch.int32)
     li, ls, lb, lf = [], [], [], []
-    for a, b in zip(cuts[:-1], cuts[1:]):
+    for g, (a, b) in enumerate(zip(cuts[:-1], cuts[1:])):
         shard = retrieval.CatalogIndex(table, shard=(a, b - a))
-        i, s, bd, f = retrieval.retrieve_candidates(users, shard, kps)
+        i, s, bd, f = retrieval.retrieve_candidates(users, shard, kps, pack=allp[g * U:(g + 1) * U])
         li.append(i); ls.append(s); lb.append(bd); lf.append(f)
-    mi, ms, bad = retrieval.merge_bounded(torch.stack(ls), torch.stack(li), torch.stack(lb), K)
-    bad = bad | torch.stack(lf).any(dim=0)
+    mi0, ms0, bad0 = retrieval.merge_bounded(torch.stack(ls), torch.stack(li), torch.stack(lb), K)
+    bad0 = bad0 | torch.stack(lf).any(dim=0)
+    bad = torch.zeros(U, device="cuda", dtype=torch.int32)
+    mi, ms = retrieval.merge_packed(allp, G, U, kps, K, bad)
     torch.cuda.synchronize()
-    return mi, ms, bad
+    assert torch.equal(mi, mi0) and torch.equal(ms, ms0) and torch.equal(bad.bool(), bad0)
+    return mi, ms, bad.bool()
 
 
 def test_bounded_shard_protocol_on_a_large_catalog():

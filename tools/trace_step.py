@@ -12,16 +12,23 @@ import torch  # noqa: E402
 from torch.profiler import ProfilerActivity, profile  # noqa: E402
 from mrm_b200 import synthetic  # noqa: E402
 from mrm_b200.engine import TwoTowerEngine  # noqa: E402
-from mrm_b200.train import TrainStepRunner  # noqa: E402
+from mrm_b200.train import TrainStepRunner, make_dp_engine  # noqa: E402
 
 
 def main():
-    B, L, V = 256, 200, 100_001
+    """Single process, or under torchrun (rank 0 prints the timeline of ITS GPU): the data-parallel step."""
+    import torch.distributed as dist
+    rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    B = int(os.environ.get("TT_TRACE_BATCH", 256))
+    L, V = 200, 100_001
     cfg = synthetic.TwoTowerConfig(vocab_size=V, max_seq_len=L, dropout=0.1)
-    eng = TwoTowerEngine(cfg)
+    eng, table = make_dp_engine(cfg, world)
     eng.load_state_dict(synthetic.make_state_dict(cfg, seed=0))
-    runner = TrainStepRunner(eng, B, L)
-    batch = synthetic.make_batch(cfg, B, seed=1, full_length=True, num_users=1_000_000)
+    runner = TrainStepRunner(eng, B, L, world_size=world, sharded_table=table)
+    batch = synthetic.make_batch(cfg, B, seed=1 + rank, full_length=True, num_users=1_000_000)
     runner.load_batch({k: v.cuda() for k, v in batch.items()})
     for _ in range(5):
         runner.step_resident()
@@ -30,6 +37,12 @@ def main():
         for _ in range(3):
             runner.step_resident()
         torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
     path = os.path.join(tempfile.gettempdir(), "trace.json")
     prof.export_chrome_trace(path)
     ev = json.load(open(path))["traceEvents"]
@@ -60,6 +73,8 @@ def main():
             cur_e = max(cur_e, e)
     busy += cur_e - cur_s
     print(f"# union busy {busy:.1f} us of {end - t0:.1f} us span; sum of durations {sum(e['dur'] for e in ks):.1f} us")
+    if world > 1:
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":
