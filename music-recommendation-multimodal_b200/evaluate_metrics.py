@@ -73,22 +73,47 @@ def compute_all_item_embeddings(model, item_features: Dict[str, torch.Tensor], i
 
 
 def calculate_metrics_global(model, val_loader, item_embeddings, device, k_list: Sequence[int] = (10, 20),
-                             index: CatalogIndex = None) -> Dict[str, float]:
+                             index: CatalogIndex = None, group=None) -> Dict[str, float]:
     """Reference signature (src/evaluate_metrics.py:106). User embeddings come from the CUDA user
     tower batch by batch; scoring / top-K / metrics run once over all validation rows with the
-    fused retrieval kernels (the per-row results do not depend on the batching)."""
+    fused retrieval kernels (the per-row results do not depend on the batching).
+
+    With a catalog index built over one shard per rank (``index.is_sharded``) every rank iterates the SAME loader;
+    the user tower then runs on 1 / world of the batches per rank (batch i on rank i % world) and the embeddings are
+    all-gathered (1 KB per user) before the sharded scoring — the tower is not replicated work."""
     logger.info(f"Iniciando evaluación global con K={list(k_list)}...")
     model.eval()
     if isinstance(item_embeddings, dict):
         item_embeddings = item_embeddings["item_embeddings"]
     if index is None:
         index = CatalogIndex(item_embeddings, device=device)
-    users, targets = [], []
+    import torch.distributed as dist
+    world = dist.get_world_size(group) if index.is_sharded else 1
+    rank = dist.get_rank(group) if index.is_sharded else 0
+    users, targets, sizes = [], [], []
     with torch.no_grad():
-        for batch in val_loader:
+        for i, batch in enumerate(val_loader):
+            n = batch["history_ids"].shape[0]
+            sizes.append(n)
+            targets.append(batch["target_id"].to(device))
+            if i % world != rank:
+                users.append(None)
+                continue
             users.append(model.get_user_embedding(history_ids=batch["history_ids"].to(device),
                                                   history_mask=batch["history_mask"].to(device),
                                                   user_gender=batch["user_gender"].to(device),
                                                   user_country=batch["user_country"].to(device)))
-            targets.append(batch["target_id"].to(device))
-    return metrics_from_embeddings(torch.cat(users), torch.cat(targets), index, list(k_list))
+    D = model.engine.cfg.embedding_dim
+    if world > 1:
+        # one sum-all-reduce of the (U, 256) matrix in which every rank filled its own batches
+        full = torch.zeros(sum(sizes), D, device=device)
+        off = 0
+        for n, u in zip(sizes, users):
+            if u is not None:
+                full[off:off + n] = u
+            off += n
+        dist.all_reduce(full, op=dist.ReduceOp.SUM, group=group)
+        all_users = full
+    else:
+        all_users = torch.cat(users)
+    return metrics_from_embeddings(all_users, torch.cat(targets), index, list(k_list), group=group)

@@ -25,8 +25,7 @@ def main():
     shard = torch.nn.functional.normalize(torch.randn(n_local, 256, device=dev, generator=g), dim=1)
     if rank == 0:
         shard[0] = 0
-    index = retrieval.CatalogIndex(shard, device=dev)
-    index.item_base, index.vocab_size = first, N + 1
+    index = retrieval.CatalogIndex.from_shard(shard, first, N + 1, device=dev)
     gu = torch.Generator(device=dev).manual_seed(99)
     t = torch.randint(1, n_local, (U,), device=dev, generator=gu)
     users = torch.nn.functional.normalize(shard[t] + 3.3 / 16.0 * torch.randn(U, 256, device=dev, generator=gu), dim=1)
