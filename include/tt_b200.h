@@ -349,22 +349,43 @@ int tt_rank_metrics(const int32_t* topk_idx, const int64_t* targets, int U, int 
 /* ---- ID-embedding lookups against a table row-sharded over the ranks of one NVLink domain ----------
  * (BASELINE.json configs[4]: 10M items; reference: nn.Embedding(vocab_size, 256, padding_idx=0) and its dense
  * gradient, src/models/user_tower.py:26,86.) The table and its gradient live in a symmetric arena (tt_symm_team
- * below): rank r holds rows [r * rows_per_rank, (r+1) * rows_per_rank) at byte `weight_offset` / `grad_offset` of
- * its copy. Same computation as tt_embed_ln_fwd / tt_embed_ln_bwd; a token's row is read from — and its gradient
+ * below): the rows are dealt ROUND-ROBIN (item popularity is Zipfian in the id: contiguous ranges would send most
+ * lookups to rank 0): row id is local row id / world of rank id % world, at byte `weight_offset` / `grad_offset` of
+ * that rank's copy. Same computation as tt_embed_ln_fwd / tt_embed_ln_bwd; a token's row is read from — and its gradient
  * row added (red.global.add.v4.f32) into — the OWNER's memory over NVLink. No ids or rows are exchanged between
  * ranks. row_stash (nullable, fp32 [B*L, 256]): the forward keeps the gathered rows, the backward reads them
  * instead of crossing NVLink a second time. The caller separates steps with tt_symm_barrier (owners' updates
  * visible before the next gather; all ranks' gradient rows landed before the owner's AdamW). */
 struct tt_symm_team;
 int tt_embed_ln_fwd_sharded(const int64_t* ids, const struct tt_symm_team* team, int64_t weight_offset,
-                            int rows_per_rank, float* row_stash, const float* P, const float* ln_w, const float* ln_b,
+                            float* row_stash, const float* P, const float* ln_w, const float* ln_b,
                             const float* next_w, const float* next_b, int B, int L, float drop_p, uint64_t seed,
                             const uint64_t* seed_dev, uint32_t site, float* x0, void* h_bf16, void* stream);
 int tt_embed_ln_bwd_sharded(const int64_t* ids, const struct tt_symm_team* team, int64_t weight_offset,
-                            int64_t grad_offset, int rows_per_rank, const float* row_stash, const float* P,
+                            int64_t grad_offset, const float* row_stash, const float* P,
                             const float* ln_w, const float* ln_b, const float* dx0, int B, int L, float drop_p,
                             uint64_t seed, const uint64_t* seed_dev, uint32_t site, float* dP, float* dgamma,
                             float* dbeta, void* stream);
+
+/* Duplicate-free traffic for a row-sharded (or replicated) ID table. Histories are Zipfian in the item id: at batch
+ * 256 x 200 about a third of the tokens carry a distinct id, so a step first reduces its ids to the distinct ones.
+ * tt_ids_dedup   : ids[T] -> uniq[0..n) int64 (uniq[0] = 0, the padding id; order unspecified), inverse[t] = slot of
+ *                  ids[t] (0 for padding / out-of-table ids), state[1] = n. Scratch: flag, slot int32 [V] and state
+ *                  int32 [2], zero-filled by the caller ONCE; uniq needs T + 1 entries. Every call clears the flags
+ *                  the previous call set.
+ * tt_rows_gather : cache[s, :] = table row uniq[s] for s < *n_uniq — read from the owner's shard over NVLink
+ *                  (team + weight_offset) or from a local table (table_local); each distinct row crosses the link
+ *                  once. The embedding kernels (tt_embed_ln_fwd / _bwd) then run on `cache` with `inverse` as ids.
+ * tt_rows_scatter_add : owner's gradient row uniq[s] += gacc[s, :] (red.global.add.v4.f32), then gacc[s, :] = 0, for
+ *                  1 <= s < *n_uniq: gacc is the compact gradient buffer the embedding backward accumulated into
+ *                  (duplicates combined locally, L2-resident), one remote reduction per distinct row remains.
+ * max_rows bounds the launch (the count itself is read on the device). */
+int tt_ids_dedup(const int64_t* ids, int T, int64_t V, int32_t* flag, int32_t* slot, int64_t* uniq, int32_t* state,
+                 int64_t* inverse, void* stream);
+int tt_rows_gather(const struct tt_symm_team* team, int64_t weight_offset, const float* table_local, const int64_t* uniq,
+                   const int32_t* n_uniq, int max_rows, float* cache, void* stream);
+int tt_rows_scatter_add(const struct tt_symm_team* team, int64_t grad_offset, float* grad_local, const int64_t* uniq,
+                        const int32_t* n_uniq, int max_rows, float* gacc, void* stream);
 
 /* ---- data-parallel exchanges over NVLink peer memory -------------------------------------
  * Replaces the NCCL traffic of the reference's DistributedDataParallel wrapper (src/train.py:29-35, 300: one
@@ -389,6 +410,11 @@ int tt_embed_ln_bwd_sharded(const int64_t* ids, const struct tt_symm_team* team,
  *                     their bf16 copies into every rank's arena (multimem.st / peer stores). Barriers on both
  *                     sides: starts when every rank's gradients are final, completes when every rank's parameters
  *                     are. Gradients are NOT cleared (the caller zeroes its local buffer afterwards).
+ *                     shard_* (shard_n > 0): this rank's rows of a row-sharded ID table in plain local memory
+ *                     (parameters, gradient SUM over ranks, moments): updated by the same kernel between the two
+ *                     barriers with gradient = shard_g / world, shard_g cleared in the same pass — the first barrier
+ *                     guarantees every rank's gradient rows have landed, the second that every owner's rows are
+ *                     final before any rank's next step gathers them.
  * tt_symm_barrier   : barrier across the team.
  * A wait longer than ~10 s (a peer died) sets the int32 at ctrl_offset + 8 and returns; callers check it. */
 #define TT_SYMM_MAX_RANKS 16
@@ -407,7 +433,8 @@ int tt_symm_ctrl_bytes(void);
 int tt_symm_allgather(const tt_symm_team* team, const tt_symm_segment* segs, int n_seg, int pre_barrier, void* stream);
 int tt_dp_adamw_step(const tt_symm_team* team, int64_t flat_offset, int64_t grad_offset, int64_t shadow_offset,
                      int64_t n, int64_t shadow_begin, float* m, float* v, float lr, float beta1, float beta2, float eps,
-                     float weight_decay, const int64_t* step_dev, void* stream);
+                     float weight_decay, const int64_t* step_dev, float* shard_p, float* shard_g, float* shard_m,
+                     float* shard_v, int64_t shard_n, void* stream);
 int tt_symm_barrier(const tt_symm_team* team, void* stream);
 
 #ifdef __cplusplus

@@ -152,7 +152,7 @@ _SIGNATURES = {
     "tt_symm_ctrl_bytes": [],
     "tt_symm_allgather": [ctypes.POINTER(SymmTeam), ctypes.POINTER(SymmSegment), c_int32, c_int32, c_void_p],
     "tt_dp_adamw_step": [ctypes.POINTER(SymmTeam), _I64, _I64, _I64, _I64, _I64, c_void_p, c_void_p, c_float, c_float,
-                         c_float, c_float, c_float, c_void_p, c_void_p],
+                         c_float, c_float, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, _I64, c_void_p],
     "tt_symm_barrier": [ctypes.POINTER(SymmTeam), c_void_p],
     "tt_gather_rows": [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p],
     "tt_scatter_rows_add": [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_int32, c_void_p],
@@ -190,9 +190,12 @@ _SIGNATURES = {
     "tt_colsum_bf16": [c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p],
     "tt_adamw_step": [c_void_p] * 4 + [_I64, c_float, c_float, c_float, c_float, c_float, c_float, c_void_p, c_void_p,
                                        _I64, _I64, c_int32, c_void_p],
-    "tt_embed_ln_fwd_sharded": [c_void_p, ctypes.POINTER(SymmTeam), _I64, c_int32] + [c_void_p] * 6 +
+    "tt_ids_dedup": [c_void_p, c_int32, _I64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
+    "tt_rows_gather": [ctypes.POINTER(SymmTeam), _I64, c_void_p, c_void_p, c_void_p, c_int32, c_void_p, c_void_p],
+    "tt_rows_scatter_add": [ctypes.POINTER(SymmTeam), _I64, c_void_p, c_void_p, c_void_p, c_int32, c_void_p, c_void_p],
+    "tt_embed_ln_fwd_sharded": [c_void_p, ctypes.POINTER(SymmTeam), _I64] + [c_void_p] * 6 +
                                [c_int32, c_int32, c_float, c_uint64, c_void_p, c_uint32, c_void_p, c_void_p, c_void_p],
-    "tt_embed_ln_bwd_sharded": [c_void_p, ctypes.POINTER(SymmTeam), _I64, _I64, c_int32] + [c_void_p] * 5 +
+    "tt_embed_ln_bwd_sharded": [c_void_p, ctypes.POINTER(SymmTeam), _I64, _I64] + [c_void_p] * 5 +
                                [c_int32, c_int32, c_float, c_uint64, c_void_p, c_uint32, c_void_p, c_void_p, c_void_p,
                                 c_void_p],
     "tt_step_counters_advance": [c_void_p, c_void_p, c_void_p],

@@ -10,6 +10,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "../../include/tt_b200.h"
+
 namespace tt {
 
 // ----------------------------------------------------------------------------
@@ -47,6 +49,24 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t*
                    const uint64_t* strides_bytes, const uint32_t* box);
 
 int num_sms();
+
+// The ID table as the embedding / sparse kernels see it: one replicated table (world == 0: row `id` lives at
+// base[0] + id * 256) or a table row-sharded ROUND-ROBIN over the ranks of one NVLink domain (row id lives at local
+// row id / world of rank id % world; base[r] = rank r's shard as mapped into this process, symmetric arena).
+// Round-robin because item popularity is Zipfian in the id: contiguous ranges would put most of
+// every rank's lookups on rank 0.
+struct TableRef {
+  float* base[16];
+  int world;
+#ifdef __CUDACC__
+  __device__ __forceinline__ float* row(int64_t id) const {
+    if (world == 0) return base[0] + static_cast<size_t>(id) * 256;
+    const int64_t local = id / world;
+    return base[static_cast<int>(id - local * world)] + static_cast<size_t>(local) * 256;
+  }
+#endif
+};
+int make_sharded_table(TableRef& t, const ::tt_symm_team* team, int64_t offset, const char* who);   // tt_sparse.cu
 
 #ifdef __CUDACC__
 // ----------------------------------------------------------------------------

@@ -130,19 +130,8 @@ __global__ void last_index_kernel(const int64_t* __restrict__ ids, const int64_t
 // x0 = dropout(LN_emb(E[id] + P[pos]));  h = LN_next(x0) as bf16       (user_tower.py:86-93 and
 // the first norm1 of the encoder). D = 256.
 // --------------------------------------------------------------------------------------------
-// The ID table as the embedding kernels see it: one replicated table (per == 0: row id lives at base[0]) or a
-// table row-sharded over the ranks of one NVLink domain (row id lives at local row id % per of rank id / per;
-// base[r] = rank r's shard as mapped into this process, symmetric arena) — then the gather / scatter-add goes
-// straight to the owner's memory over NVLink, no id or row exchange between the ranks.
-struct TableRef {
-  float* base[TT_SYMM_MAX_RANKS];
-  int per;
-  __device__ __forceinline__ float* row(int64_t id) const {
-    if (per == 0) return base[0] + static_cast<size_t>(id) * 256;
-    const int owner = static_cast<int>(id / per);
-    return base[owner] + static_cast<size_t>(id - static_cast<int64_t>(owner) * per) * 256;
-  }
-};
+// TableRef (tt_common.cuh): one replicated table, or a table row-sharded round-robin over the ranks of one
+// NVLink domain — then a gather / scatter-add goes straight to the owner's memory, no id or row exchange.
 
 struct EmbedParams {
   const int64_t* ids;
@@ -689,7 +678,7 @@ __global__ void __launch_bounds__(kRowThreads, 2) embed_ln_bwd_kernel(const Embe
   }
   // sharded table: the gradient rows went to other GPUs; make them globally performed before the grid retires
   // (the optimizer kernels of the owners start after a cross-rank barrier that follows this kernel)
-  if (p.dE.per != 0) __threadfence_system();
+  if (p.dE.world != 0) __threadfence_system();
 }
 
 // --------------------------------------------------------------------------------------------
@@ -834,19 +823,12 @@ static TableRef single_table(const float* E) {
   TableRef t;
   for (int r = 0; r < TT_SYMM_MAX_RANKS; ++r) t.base[r] = nullptr;
   t.base[0] = const_cast<float*>(E);
-  t.per = 0;
+  t.world = 0;
   return t;
 }
 
-static int sharded_table(TableRef& t, const tt_symm_team* team, int64_t offset, int rows_per_rank, const char* who) {
-  TT_REQUIRE(team && team->world >= 1 && team->world <= TT_SYMM_MAX_RANKS && rows_per_rank > 0 && offset >= 0 &&
-                 offset % 16 == 0,
-             "%s: bad team / shard geometry", who);
-  for (int r = 0; r < TT_SYMM_MAX_RANKS; ++r)
-    t.base[r] = r < team->world ? reinterpret_cast<float*>(static_cast<uint8_t*>(team->bufs[r]) + offset) : nullptr;
-  for (int r = 0; r < team->world; ++r) TT_REQUIRE(team->bufs[r] != nullptr, "%s: rank %d has no mapping", who, r);
-  t.per = rows_per_rank;
-  return TT_OK;
+static int sharded_table(TableRef& t, const tt_symm_team* team, int64_t offset, const char* who) {
+  return make_sharded_table(t, team, offset, who);
 }
 
 static int embed_fwd_impl(const int64_t* ids, const TableRef& E, float* stash, const float* P, const float* ln_w,
@@ -905,26 +887,26 @@ extern "C" int tt_embed_ln_bwd(const int64_t* ids, const float* E, const float* 
 }
 
 extern "C" int tt_embed_ln_fwd_sharded(const int64_t* ids, const tt_symm_team* team, int64_t weight_offset,
-                                       int rows_per_rank, float* row_stash, const float* P, const float* ln_w,
+                                       float* row_stash, const float* P, const float* ln_w,
                                        const float* ln_b, const float* next_w, const float* next_b, int B, int L,
                                        float drop_p, uint64_t seed, const uint64_t* seed_dev, uint32_t site, float* x0,
                                        void* h_bf16, void* stream_) {
   TableRef E;
-  int rc = sharded_table(E, team, weight_offset, rows_per_rank, "tt_embed_ln_fwd_sharded");
+  int rc = sharded_table(E, team, weight_offset, "tt_embed_ln_fwd_sharded");
   if (rc) return rc;
   return embed_fwd_impl(ids, E, row_stash, P, ln_w, ln_b, next_w, next_b, B, L, drop_p, seed, seed_dev, site, x0, h_bf16,
                         static_cast<cudaStream_t>(stream_));
 }
 
 extern "C" int tt_embed_ln_bwd_sharded(const int64_t* ids, const tt_symm_team* team, int64_t weight_offset,
-                                       int64_t grad_offset, int rows_per_rank, const float* row_stash, const float* P,
+                                       int64_t grad_offset, const float* row_stash, const float* P,
                                        const float* ln_w, const float* ln_b, const float* dx0, int B, int L,
                                        float drop_p, uint64_t seed, const uint64_t* seed_dev, uint32_t site, float* dP,
                                        float* dgamma, float* dbeta, void* stream_) {
   TableRef E, dE;
-  int rc = sharded_table(E, team, weight_offset, rows_per_rank, "tt_embed_ln_bwd_sharded");
+  int rc = sharded_table(E, team, weight_offset, "tt_embed_ln_bwd_sharded");
   if (rc) return rc;
-  rc = sharded_table(dE, team, grad_offset, rows_per_rank, "tt_embed_ln_bwd_sharded");
+  rc = sharded_table(dE, team, grad_offset, "tt_embed_ln_bwd_sharded");
   if (rc) return rc;
   return embed_bwd_impl(ids, E, row_stash, P, ln_w, ln_b, dx0, B, L, drop_p, seed, seed_dev, site, dE, dP, dgamma, dbeta,
                         static_cast<cudaStream_t>(stream_));

@@ -179,6 +179,12 @@ struct DpAdamwParams {
   float* m; float* v;                         // local moments of the owned slice [n4 / world * 4]
   float lr, beta1, beta2, eps, wd;
   const int64_t* step_dev;
+  // optional: this rank's shard of a row-sharded ID table (plain local memory). It is updated in the same kernel,
+  // between the two barriers: phase A guarantees every rank's gradient rows have landed in loc_g, phase B that
+  // every owner's rows are final before anybody's next step gathers them.
+  float* loc_p; float* loc_g; float* loc_m; float* loc_v;
+  long long loc_n4;
+  float loc_scale;                            // gradient used = loc_scale * loc_g (1 / world: loc_g holds the SUM)
 };
 
 template <bool kMulticast>
@@ -259,6 +265,31 @@ __global__ void __launch_bounds__(256) dp_adamw_kernel(const DpAdamwParams p) {
       }
     }
   }
+  // the owned rows of the row-sharded ID table: dense AdamW, gradient cleared in the same pass
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < p.loc_n4; i += nthreads) {
+    float4 pp = reinterpret_cast<float4*>(p.loc_p)[i];
+    const float4 gg = reinterpret_cast<const float4*>(p.loc_g)[i];
+    float4 mm = reinterpret_cast<float4*>(p.loc_m)[i];
+    float4 vv = reinterpret_cast<float4*>(p.loc_v)[i];
+    float* pa = reinterpret_cast<float*>(&pp);
+    const float* ga = reinterpret_cast<const float*>(&gg);
+    float* ma = reinterpret_cast<float*>(&mm);
+    float* va = reinterpret_cast<float*>(&vv);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float gk = ga[k] * p.loc_scale;
+      const float x = pa[k] * decay;
+      ma[k] = p.beta1 * ma[k] + (1.f - p.beta1) * gk;
+      va[k] = p.beta2 * va[k] + (1.f - p.beta2) * gk * gk;
+      const float denom = sqrtf(va[k]) / bc2_sqrt + p.eps;
+      pa[k] = x - step_size * ma[k] / denom;
+    }
+    reinterpret_cast<float4*>(p.loc_p)[i] = pp;
+    reinterpret_cast<float4*>(p.loc_m)[i] = mm;
+    reinterpret_cast<float4*>(p.loc_v)[i] = vv;
+    if ((__float_as_uint(gg.x) | __float_as_uint(gg.y) | __float_as_uint(gg.z) | __float_as_uint(gg.w)) != 0u)
+      reinterpret_cast<float4*>(p.loc_g)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
   // phase B: all ranks have read my gradients and written my parameters when the kernel completes
   finish_collective(t, e);
 }
@@ -332,6 +363,7 @@ extern "C" int tt_symm_allgather(const tt_symm_team* team, const tt_symm_segment
 extern "C" int tt_dp_adamw_step(const tt_symm_team* team, int64_t flat_offset, int64_t grad_offset,
                                 int64_t shadow_offset, int64_t n, int64_t shadow_begin, float* m, float* v, float lr,
                                 float beta1, float beta2, float eps, float weight_decay, const int64_t* step_dev,
+                                float* shard_p, float* shard_g, float* shard_m, float* shard_v, int64_t shard_n,
                                 void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   DpAdamwParams p;
@@ -346,8 +378,14 @@ extern "C" int tt_dp_adamw_step(const tt_symm_team* team, int64_t flat_offset, i
   p.flat_off = flat_offset; p.grad_off = grad_offset; p.shadow_off = shadow_offset;
   p.n4 = n / 4; p.shadow_begin4 = shadow_begin / 4;
   p.m = m; p.v = v; p.lr = lr; p.beta1 = beta1; p.beta2 = beta2; p.eps = eps; p.wd = weight_decay; p.step_dev = step_dev;
+  TT_REQUIRE(shard_n >= 0 && shard_n % 4 == 0 && (shard_n == 0 || (shard_p && shard_g && shard_m && shard_v)),
+             "tt_dp_adamw_step: the local table shard needs p, g, m, v and a multiple of 4 elements");
+  p.loc_p = shard_p; p.loc_g = shard_g; p.loc_m = shard_m; p.loc_v = shard_v; p.loc_n4 = shard_n / 4;
+  p.loc_scale = 1.f / static_cast<float>(team->world);
   const long long per = p.n4 / team->world;
   long long grid = (per + 256 * 4 - 1) / (256 * 4);
+  const long long grid_loc = (p.loc_n4 + 256 * 4 - 1) / (256 * 4);
+  if (grid_loc > grid) grid = grid_loc;
   const long long cap = static_cast<long long>(num_sms()) * 4;
   if (grid > cap) grid = cap;
   if (grid < 1) grid = 1;

@@ -135,6 +135,10 @@ class TwoTowerEngine:
         #: kernels read rows from / add gradient rows into the OWNER's memory directly (no exchange step). The flat
         #: buffer's own table region is a 2-row dummy.
         self.peer_table = None
+        #: with a peer table: reduce the step's ids to the distinct ones first (TT_TABLE_DEDUP=0: every token's row
+        #: crosses NVLink on its own, kept for A/B timing)
+        self.dedup_ids = os.environ.get("TT_TABLE_DEDUP", "1") != "0"
+        self._sparse: Dict[int, Dict[str, torch.Tensor]] = {}
 
     # ------------------------------------------------------------------ parameters
     def use_external_table(self, B: int, L: int) -> None:
@@ -305,6 +309,18 @@ class TwoTowerEngine:
         self._ws[key] = ws
         return ws
 
+    def _sparse_ws(self, T: int) -> Dict[str, torch.Tensor]:
+        """Scratch of the id de-duplication for T tokens per step (direct-address flag / slot tables over the
+        vocabulary, distinct-id list, per-token slots, compact row cache and gradient accumulator)."""
+        if T not in self._sparse:
+            dev, V, D = self.device, self.peer_table.vocab_size, self.cfg.embedding_dim
+            self._sparse[T] = {
+                "flag": torch.zeros(V, device=dev, dtype=torch.int32), "slot": torch.zeros(V, device=dev, dtype=torch.int32),
+                "uniq": torch.zeros(T + 1, device=dev, dtype=torch.int64), "state": torch.zeros(2, device=dev, dtype=torch.int32),
+                "inverse": torch.zeros(T, device=dev, dtype=torch.int64),
+                "cache": torch.zeros(T + 1, D, device=dev), "gacc": torch.zeros(T + 1, D, device=dev)}
+        return self._sparse[T]
+
     def release_workspaces(self) -> None:
         """Drop every activation workspace (they are rebuilt on demand; CUDA graphs that captured them must be
         dropped by their owner first)."""
@@ -397,11 +413,21 @@ class TwoTowerEngine:
         seed, sdev = self.base_seed, self.seed_dev
         ut = "user_tower."
         ops.last_index(ids, mask, ws["last_idx"])
-        if self.peer_table is not None:
+        if self.peer_table is not None and self.dedup_ids:
+            # distinct ids of the step -> each distinct row crosses NVLink once into a compact (L2-resident) cache;
+            # the embedding kernel then runs on the cache with the slot numbers as ids
+            t, sp = self.peer_table, self._sparse_ws(B * L)
+            ops.ids_dedup(ids.view(-1), t.vocab_size, sp["flag"], sp["slot"], sp["uniq"], sp["state"], sp["inverse"])
+            ops.rows_gather(sp["uniq"], sp["state"], sp["cache"], team=t.arena.team, weight_offset=t.arena.offset("weight"))
+            ops.embed_ln_fwd(sp["inverse"], sp["cache"], p[ut + "position_embedding.weight"],
+                             p[ut + "layer_norm.weight"], p[ut + "layer_norm.bias"],
+                             p[self._lp(0, "norm1.weight")], p[self._lp(0, "norm1.bias")], B, L,
+                             ws["x_in0"], ws["h1_0"], drop_p=dp, seed=seed, seed_dev=sdev, site=SITE_EMB)
+        elif self.peer_table is not None:
             t = self.peer_table
             if "row_stash" not in ws:
                 ws["row_stash"] = torch.empty(B * L, cfg.embedding_dim, device=self.device)
-            ops.embed_ln_fwd_sharded(ids.view(-1), t.arena.team, t.arena.offset("weight"), t.per, ws["row_stash"],
+            ops.embed_ln_fwd_sharded(ids.view(-1), t.arena.team, t.arena.offset("weight"), ws["row_stash"],
                                      p[ut + "position_embedding.weight"], p[ut + "layer_norm.weight"],
                                      p[ut + "layer_norm.bias"], p[self._lp(0, "norm1.weight")],
                                      p[self._lp(0, "norm1.bias")], B, L, ws["x_in0"], ws["h1_0"], drop_p=dp, seed=seed,
@@ -765,9 +791,19 @@ class TwoTowerEngine:
             dx, dx_other = dx_other, dx
 
         # ---- embedding LayerNorm + lookup
-        if self.peer_table is not None:
+        if self.peer_table is not None and self.dedup_ids:
+            # per-token gradient rows are combined in the compact local buffer (atomics on L2-resident memory), then
+            # ONE remote reduction per distinct row goes to its owner
+            t, sp = self.peer_table, self._sparse_ws(B * L)
+            ops.embed_ln_bwd(sp["inverse"], sp["cache"], p[ut + "position_embedding.weight"],
+                             p[ut + "layer_norm.weight"], p[ut + "layer_norm.bias"], dx, B, L,
+                             sp["gacc"], g[ut + "position_embedding.weight"],
+                             g[ut + "layer_norm.weight"], g[ut + "layer_norm.bias"], drop_p=dp, seed=seed,
+                             seed_dev=sdev, site=SITE_EMB)
+            ops.rows_scatter_add(sp["uniq"], sp["state"], sp["gacc"], team=t.arena.team, grad_offset=t.arena.offset("grad"))
+        elif self.peer_table is not None:
             t = self.peer_table
-            ops.embed_ln_bwd_sharded(ids.view(-1), t.arena.team, t.arena.offset("weight"), t.arena.offset("grad"), t.per,
+            ops.embed_ln_bwd_sharded(ids.view(-1), t.arena.team, t.arena.offset("weight"), t.arena.offset("grad"),
                                      ws["row_stash"], p[ut + "position_embedding.weight"], p[ut + "layer_norm.weight"],
                                      p[ut + "layer_norm.bias"], dx, B, L, g[ut + "position_embedding.weight"],
                                      g[ut + "layer_norm.weight"], g[ut + "layer_norm.bias"], drop_p=dp, seed=seed,

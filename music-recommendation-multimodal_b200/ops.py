@@ -147,24 +147,51 @@ def embed_ln_bwd(ids, E, P, ln_w, ln_b, dx0, B, L, dE, dP, dgamma, dbeta, drop_p
                                 dP.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(), _stream()), "tt_embed_ln_bwd")
 
 
-def embed_ln_fwd_sharded(ids, team, weight_offset, rows_per_rank, stash, P, ln_w, ln_b, next_w, next_b, B, L, x0, h,
+def embed_ln_fwd_sharded(ids, team, weight_offset, stash, P, ln_w, ln_b, next_w, next_b, B, L, x0, h,
                          drop_p=0.0, seed=0, seed_dev=None, site=0):
     """tt_embed_ln_fwd_sharded: the ID table is row-sharded over the ranks of a symmetric arena."""
     _require_cuda(ids, stash, P, x0, h)
     assert ids.dtype == torch.int64 and P.shape[0] >= L
-    check(lib().tt_embed_ln_fwd_sharded(ids.data_ptr(), ctypes.byref(team), weight_offset, rows_per_rank, _ptr(stash),
+    check(lib().tt_embed_ln_fwd_sharded(ids.data_ptr(), ctypes.byref(team), weight_offset, _ptr(stash),
                                         P.data_ptr(), ln_w.data_ptr(), ln_b.data_ptr(), next_w.data_ptr(),
                                         next_b.data_ptr(), B, L, drop_p, seed, _ptr(seed_dev), site, x0.data_ptr(),
                                         h.data_ptr(), _stream()), "tt_embed_ln_fwd_sharded")
 
 
-def embed_ln_bwd_sharded(ids, team, weight_offset, grad_offset, rows_per_rank, stash, P, ln_w, ln_b, dx0, B, L, dP,
+def embed_ln_bwd_sharded(ids, team, weight_offset, grad_offset, stash, P, ln_w, ln_b, dx0, B, L, dP,
                          dgamma, dbeta, drop_p=0.0, seed=0, seed_dev=None, site=0):
     _require_cuda(ids, stash, P, dx0, dP, dgamma, dbeta)
-    check(lib().tt_embed_ln_bwd_sharded(ids.data_ptr(), ctypes.byref(team), weight_offset, grad_offset, rows_per_rank,
+    check(lib().tt_embed_ln_bwd_sharded(ids.data_ptr(), ctypes.byref(team), weight_offset, grad_offset,
                                         _ptr(stash), P.data_ptr(), ln_w.data_ptr(), ln_b.data_ptr(), dx0.data_ptr(), B,
                                         L, drop_p, seed, _ptr(seed_dev), site, dP.data_ptr(), dgamma.data_ptr(),
                                         dbeta.data_ptr(), _stream()), "tt_embed_ln_bwd_sharded")
+
+
+def ids_dedup(ids, V, flag, slot, uniq, state, inverse) -> None:
+    """tt_ids_dedup: distinct ids of a step (uniq, state[1] = count) and every token's slot (inverse)."""
+    _require_cuda(ids, flag, slot, uniq, state, inverse)
+    T = ids.numel()
+    assert ids.dtype == torch.int64 and ids.is_contiguous() and inverse.dtype == torch.int64 and inverse.numel() == T
+    assert flag.dtype == torch.int32 and slot.dtype == torch.int32 and flag.numel() >= V and slot.numel() >= V
+    assert uniq.dtype == torch.int64 and uniq.numel() >= T + 1 and state.dtype == torch.int32 and state.numel() >= 2
+    check(lib().tt_ids_dedup(ids.data_ptr(), T, V, flag.data_ptr(), slot.data_ptr(), uniq.data_ptr(), state.data_ptr(),
+                             inverse.data_ptr(), _stream()), "tt_ids_dedup")
+
+
+def rows_gather(uniq, state, cache, team=None, weight_offset=0, table_local=None) -> None:
+    _require_cuda(uniq, state, cache, table_local)
+    assert cache.dtype == torch.float32 and cache.is_contiguous() and cache.shape[1] == 256
+    check(lib().tt_rows_gather(None if team is None else ctypes.byref(team), weight_offset, _ptr(table_local),
+                               uniq.data_ptr(), state.data_ptr() + 4, cache.shape[0], cache.data_ptr(), _stream()),
+          "tt_rows_gather")
+
+
+def rows_scatter_add(uniq, state, gacc, team=None, grad_offset=0, grad_local=None) -> None:
+    _require_cuda(uniq, state, gacc, grad_local)
+    assert gacc.dtype == torch.float32 and gacc.is_contiguous() and gacc.shape[1] == 256
+    check(lib().tt_rows_scatter_add(None if team is None else ctypes.byref(team), grad_offset, _ptr(grad_local),
+                                    uniq.data_ptr(), state.data_ptr() + 4, gacc.shape[0], gacc.data_ptr(), _stream()),
+          "tt_rows_scatter_add")
 
 
 def _chain_args(x, *, ln=None, relu=False, drop_p=0.0, seed=0, seed_dev=None, site=0, l2norm=False,

@@ -140,12 +140,13 @@ class RowShardedTable:
 
 
 class SymmShardedTable:
-    """Row-sharded ID table in a symmetric NVLink arena (BASELINE.json configs[4]): rank r owns the
-    contiguous rows [r * per, (r + 1) * per) (per = ceil(V / world)) of ``nn.Embedding(vocab_size, 256,
-    padding_idx=0)`` (src/models/user_tower.py:26) and of its dense gradient, in one allocation that every rank maps.
-    There is no lookup exchange: the embedding kernels (tt_embed_ln_fwd_sharded / _bwd_sharded) read a token's row
-    from, and add its gradient row into, the owner's memory over NVLink. The owner runs dense AdamW
-    (src/train.py:302) over its rows with the gradient SUM scaled by 1 / world (the data-parallel mean)."""
+    """Row-sharded ID table in a symmetric NVLink arena (BASELINE.json configs[4]): the rows of
+    ``nn.Embedding(vocab_size, 256, padding_idx=0)`` (src/models/user_tower.py:26) and of its dense gradient are
+    dealt round-robin — row id lives at local row id // world of rank id % world — in one allocation that every rank
+    maps. Round-robin because item popularity is Zipfian in the id: contiguous ranges would put ~90 % of every
+    rank's lookups on rank 0. There is no lookup exchange: a step's distinct rows are read from, and its combined
+    gradient rows added into, the owners' memory over NVLink (tt_rows_gather / tt_rows_scatter_add). The owner runs
+    dense AdamW (src/train.py:302) over its rows with the gradient SUM scaled by 1 / world (data-parallel mean)."""
 
     def __init__(self, vocab_size: int, dim: int, group=None, device=None):
         from .symm import SymmArena
@@ -154,8 +155,7 @@ class SymmShardedTable:
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
         self.per = (vocab_size + self.world - 1) // self.world
-        self.first = min(self.rank * self.per, vocab_size)
-        self.rows = max(0, min(vocab_size, self.first + self.per) - self.first)
+        self.rows = max(0, (vocab_size - self.rank + self.world - 1) // self.world)     # ids rank, rank + world, ...
         self.arena = SymmArena({"weight": self.per * dim * 4, "grad": self.per * dim * 4}, group, device)
         self.weight = self.arena.view("weight", torch.float32, (self.per, dim))
         self.grad = self.arena.view("grad", torch.float32, (self.per, dim))
@@ -164,13 +164,13 @@ class SymmShardedTable:
 
     def describe(self) -> str:
         how = "NVLS-capable arena" if self.arena.multicast else "peer-mapped arena"
-        return (f"contiguous row shards ({self.per} rows/rank) in a symmetric {how}; forward: rows gathered from the "
-                f"owner's memory over NVLink inside the embedding kernel (kept in a local stash for the backward), "
-                f"backward: red.global.add.v4.f32 into the owner's gradient shard; no id/row exchange, one barrier "
-                f"kernel per step")
+        return (f"rows dealt round-robin over {self.world} ranks ({self.per} rows/rank) in a symmetric {how}; forward: "
+                f"the step's DISTINCT rows are gathered once from the owners' memory over NVLink into a compact cache, "
+                f"backward: per-token gradients combined locally, one red.global.add.v4.f32 per distinct row into the "
+                f"owner's gradient shard; no id/row exchange between ranks; owners run AdamW on V/world rows")
 
     def load_full(self, full_table: torch.Tensor) -> None:
-        self.weight[:self.rows].copy_(full_table[self.first:self.first + self.rows])
+        self.weight[:self.rows].copy_(full_table[self.rank::self.world])
         self.barrier()           # peers gather from this shard: nobody reads it before every owner has loaded
 
     def barrier(self) -> None:
@@ -186,8 +186,21 @@ class SymmShardedTable:
         ops.adamw_step(self.weight.view(n), self.grad.view(n), self.exp_avg, self.exp_avg_sq, step_dev, lr, betas[0],
                        betas[1], eps, weight_decay, shadow=None, zero_grad=True, grad_scale=1.0 / self.world)
 
+    def shard_tensors(self):
+        """(p, g, m, v) of the owned rows as flat tensors — what tt_dp_adamw_step updates inside its barriers."""
+        n = self.per * self.dim
+        if self.exp_avg is None:
+            self.exp_avg = torch.zeros(n, device=self.weight.device)
+            self.exp_avg_sq = torch.zeros(n, device=self.weight.device)
+        return self.weight.view(n), self.grad.view(n), self.exp_avg, self.exp_avg_sq
+
     def gather_full(self) -> torch.Tensor:
         import torch.distributed as dist
-        out = torch.empty(self.world * self.per, self.dim, device=self.weight.device)
-        dist.all_gather_into_tensor(out, self.weight.contiguous(), group=self.arena.group)
-        return out[:self.vocab_size]
+        parts = torch.empty(self.world, self.per, self.dim, device=self.weight.device)
+        dist.all_gather_into_tensor(parts.view(self.world * self.per, self.dim), self.weight.contiguous(),
+                                    group=self.arena.group)
+        out = torch.empty(self.vocab_size, self.dim, device=self.weight.device)
+        for r in range(self.world):
+            n = max(0, (self.vocab_size - r + self.world - 1) // self.world)
+            out[r::self.world] = parts[r, :n]
+        return out

@@ -96,11 +96,17 @@ class SymmArena:
 
     def dp_adamw_step(self, flat: str, grad: str, shadow: str, n: int, shadow_begin: int, m: torch.Tensor,
                       v: torch.Tensor, step_dev: torch.Tensor, lr: float, betas=(0.9, 0.999), eps: float = 1e-8,
-                      weight_decay: float = 0.01) -> None:
+                      weight_decay: float = 0.01, table_shard=None) -> None:
+        """``table_shard`` = (p, g, m, v) flat fp32 tensors of this rank's rows of a row-sharded ID table: updated in
+        the same kernel, between its two barriers (gradient = g / world, g cleared)."""
         assert m.dtype == torch.float32 and v.dtype == torch.float32 and m.numel() == n // self.world == v.numel()
+        sp = [None] * 4 if table_shard is None else [t.data_ptr() for t in table_shard]
+        sn = 0 if table_shard is None else table_shard[0].numel()
+        if table_shard is not None:
+            assert all(t.dtype == torch.float32 and t.is_contiguous() and t.numel() == sn for t in table_shard)
         check(lib().tt_dp_adamw_step(ctypes.byref(self.team), self.offsets[flat][0], self.offsets[grad][0],
                                      self.offsets[shadow][0], n, shadow_begin, m.data_ptr(), v.data_ptr(), lr, betas[0],
-                                     betas[1], eps, weight_decay, step_dev.data_ptr(),
+                                     betas[1], eps, weight_decay, step_dev.data_ptr(), sp[0], sp[1], sp[2], sp[3], sn,
                                      torch.cuda.current_stream().cuda_stream), "tt_dp_adamw_step")
 
 

@@ -211,8 +211,8 @@ class TrainStepRunner:
         """The whole data-parallel step, every exchange a kernel of this repo: capturable as ONE graph."""
         from . import ops
         eng, a = self.eng, self.arena
-        if self.table is not None:
-            self.table.barrier()      # every owner's AdamW of the previous step is visible before rows are gathered
+        # (row-sharded ID table: the owners' rows were made final by the barrier that ended the previous step's
+        # optimizer kernel, so the gathers below need no barrier of their own)
         ws = self._ws = eng.forward_towers(self.static, training=True)
         g = self._symm_gathered(ws)
         uid = self.static.get("user_idx")
@@ -226,12 +226,11 @@ class TrainStepRunner:
         a.allgather([(ws["lse_r"], "lse_r_all"), (ws["lse_c"], "lse_c_all"), (self._loss_pad, "loss_all")])
         eng.backward()
         ops.step_counters_advance(eng.step_dev, eng.seed_dev)
+        # one kernel: barrier (every rank's backward done, all gradient rows landed) -> reduce-scatter + AdamW +
+        # all-gather of the replicated parameters and AdamW of this rank's ID-table rows -> barrier
         a.dp_adamw_step("flat", "grad", "shadow", eng.numel, eng.dense_begin, eng.exp_avg, eng.exp_avg_sq, eng.step_dev,
-                        self.lr, self.betas, self.eps, self.weight_decay)
-        if self.table is not None:
-            # the kernel above started only after EVERY rank finished its backward pass (phase-A barrier), so all
-            # gradient rows have landed in this owner's shard
-            self.table.adamw_step(eng.step_dev, self.lr, self.betas, self.eps, self.weight_decay)
+                        self.lr, self.betas, self.eps, self.weight_decay,
+                        table_shard=None if self.table is None else self.table.shard_tensors())
         eng.grad.zero_()
         eng.shadow_valid = True
 
@@ -364,8 +363,8 @@ class TrainStepRunner:
         if self.arena is not None:
             how = "NVLS multicast (multimem.ld_reduce / multimem.st)" if self.arena.multicast else "peer loads / stores"
             pre = [] if self.table is None else [
-                "tt_symm_barrier + ID-table rows read from / gradient rows added into the owner's memory over NVLink "
-                "inside tt_embed_ln_fwd_sharded / tt_embed_ln_bwd_sharded"]
+                "tt_ids_dedup + tt_rows_gather / tt_rows_scatter_add: the step's distinct ID-table rows read from / "
+                "combined gradient rows added into the owners' memory over NVLink (no exchange between ranks)"]
             return pre + [f"tt_symm_allgather (user emb | item emb | user id), {how}",
                     "tt_symm_allgather (row log-sum-exps of both directions | loss share)",
                     f"tt_dp_adamw_step: gradient reduce-scatter -> AdamW -> parameter + bf16 shadow all-gather in one "

@@ -56,13 +56,24 @@ def main():
         ref_shadow = torch.zeros(n - dense_begin, device=dev, dtype=torch.bfloat16)
         m, v = torch.zeros(n // world, device=dev), torch.zeros(n // world, device=dev)
         step = torch.zeros((), device=dev, dtype=torch.long)
+        # a local table shard updated inside the same kernel: gradient SUM over ranks sits in sg, scaled by 1 / world
+        sn = 8192
+        gs = torch.Generator(device=dev).manual_seed(77 + rank)
+        shard = [torch.randn(sn, device=dev, generator=gs), torch.zeros(sn, device=dev), torch.zeros(sn, device=dev),
+                 torch.zeros(sn, device=dev)]
+        ref_shard = [t.clone() for t in shard]
         for it in range(3):
             gr = torch.Generator(device=dev).manual_seed(100 * it + rank)
             grad.copy_(torch.randn(n, device=dev, generator=gr) * (0.1 if it else 1.0))
             gsum = grad.clone()
             dist.all_reduce(gsum, op=dist.ReduceOp.SUM)
             step += 1
-            ar.dp_adamw_step("flat", "grad", "shadow", n, dense_begin, m, v, step, 1e-3)
+            sg = torch.randn(sn, device=dev, generator=gs)
+            sg[::3] = 0
+            shard[1].copy_(sg)
+            ar.dp_adamw_step("flat", "grad", "shadow", n, dense_begin, m, v, step, 1e-3, table_shard=shard)
+            ops.adamw_step(ref_shard[0], sg.clone(), ref_shard[2], ref_shard[3], step, 1e-3, shadow=None, zero_grad=False,
+                           grad_scale=1.0 / world)
             gmean = gsum / world
             ops.adamw_step(ref_p, gmean, ref_m, ref_v, step, 1e-3, shadow=ref_shadow, shadow_begin=dense_begin,
                            shadow_end=n, zero_grad=False)
@@ -79,7 +90,8 @@ def main():
             same &= bool(torch.equal(shadow, flat[dense_begin:].to(torch.bfloat16)))
             if rank == 0:
                 print(f"n={n} step {it}: max |p - ref| {d:.3e}, shadow {ds:.3e}, replicas identical {same}")
-            ok &= d < 2e-6 and same
+            dsh = (shard[0] - ref_shard[0]).abs().max().item()
+            ok &= d < 2e-6 and same and dsh == 0.0 and shard[1].abs().max().item() == 0.0
         ar.check()
         if n > 1_000_000:
             def timed(fn, iters=20):
