@@ -565,7 +565,7 @@ class TwoTowerEngine:
         return ws["in"]
 
     def index_items(self, features: Dict[str, torch.Tensor], item_ids: torch.Tensor, table: torch.Tensor,
-                    table_bf16: Optional[torch.Tensor] = None, batch_size: int = 16384) -> None:
+                    table_bf16: Optional[torch.Tensor] = None, batch_size: int = 131072) -> None:
         """Catalog indexing (src/evaluate_metrics.py:24-104) on device tensors: item tower in eval mode over
         ``features`` (four (n, 128) fp32 device tensors), NaN -> 0, re-normalise (eps 1e-8), rows scattered by
         ``item_ids`` into ``table`` fp32 (V, 256) (+ its bf16 copy). Eval-mode BatchNorm is an affine map per

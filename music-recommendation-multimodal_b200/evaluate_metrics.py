@@ -27,7 +27,7 @@ def _shard_slice(n_all: int, shard):
 
 
 def index_catalog_device(model, item_features: Dict[str, torch.Tensor], item_ids: torch.Tensor, vocab_size: int,
-                         batch_size: int = 16384, shard=None, out=None):
+                         batch_size: int = 131072, shard=None, out=None):
     """Catalog indexing (src/evaluate_metrics.py:24-104) entirely on the device: returns (table fp32 (V, 256),
     table bf16 (V, 256)) on the model's GPU — the dense cache in the reference's layout (row i = embedding of item
     id i, row 0 and unlisted ids zero) and the copy the scoring kernel reads. Host features are moved batch by
@@ -57,7 +57,7 @@ def index_catalog_device(model, item_features: Dict[str, torch.Tensor], item_ids
     return table, table_bf16
 
 
-def build_catalog_index(model, item_features, item_ids, vocab_size: int, batch_size: int = 16384) -> CatalogIndex:
+def build_catalog_index(model, item_features, item_ids, vocab_size: int, batch_size: int = 131072) -> CatalogIndex:
     """Index the catalog and hand the device tables straight to retrieval (no host round trip, no re-cast)."""
     table, table_bf16 = index_catalog_device(model, item_features, item_ids, vocab_size, batch_size)
     return CatalogIndex.from_device_tables(table, table_bf16)
@@ -68,7 +68,9 @@ def compute_all_item_embeddings(model, item_features: Dict[str, torch.Tensor], i
     """The reference's return contract (src/evaluate_metrics.py:24-104): (dense CPU FloatTensor (V, 256),
     vocab_size) — what `main` saves as {'item_embeddings', 'vocab_size'} (:323-326). The work is
     `index_catalog_device`; the table crosses to the host once."""
-    table, _ = index_catalog_device(model, item_features, item_ids, vocab_size, max(batch_size, 1), shard)
+    # the reference's batch_size is its DataLoader's; eval-mode rows are independent, so the device path batches
+    # by what fills the GPU
+    table, _ = index_catalog_device(model, item_features, item_ids, vocab_size, max(batch_size, 131072), shard)
     return table.cpu(), vocab_size
 
 
