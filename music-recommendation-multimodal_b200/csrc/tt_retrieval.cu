@@ -630,35 +630,42 @@ __global__ void __launch_bounds__(256) topk_merge_kernel(const float* __restrict
                                                          int* __restrict__ out_idx, int* __restrict__ bad) {
   pdl_launch_dependents();
   pdl_wait();
-  extern __shared__ unsigned long long s_all[];  // G*K keys
-  __shared__ int s_written;
-  __shared__ float s_kth;
+  extern __shared__ unsigned long long s_all[];  // n_pad keys (next power of two >= G*K, zero padded)
   const int u = blockIdx.x;
   const int n = G * K;
-  if (threadIdx.x == 0) { s_written = 0; s_kth = -INFINITY; }
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    const int g = i / K, k = i % K;
-    const size_t o = (static_cast<size_t>(g) * U + u) * row_stride + k;
-    const int id = idx[o];
-    s_all[i] = id < 0 ? 0ull : make_key(scores[o], static_cast<uint32_t>(id));
+  int n_pad = 1;
+  while (n_pad < n) n_pad <<= 1;
+  for (int i = threadIdx.x; i < n_pad; i += blockDim.x) {
+    unsigned long long key = 0ull;
+    if (i < n) {
+      const int g = i / K, k = i % K;
+      const size_t o = (static_cast<size_t>(g) * U + u) * row_stride + k;
+      const int id = idx[o];
+      key = id < 0 ? 0ull : make_key(scores[o], static_cast<uint32_t>(id));
+    }
+    s_all[i] = key;
   }
-  __syncthreads();
-  // rank by counting: keys are unique (distinct items), n is small
-  int written = 0;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    const unsigned long long k = s_all[i];
-    if (k == 0ull) continue;
-    int rank = 0;
-    for (int j = 0; j < n; ++j) rank += (s_all[j] > k);
-    if (rank < K_out) {
-      out_score[static_cast<size_t>(u) * K_out + rank] = key_score(k);
-      out_idx[static_cast<size_t>(u) * K_out + rank] = static_cast<int>(key_idx(k));
-      if (rank == K_out - 1) s_kth = key_score(k);
-      ++written;
+  // Bitonic sort, descending, of the n_pad keys (keys are unique: distinct items; padding = 0 sinks to the end).
+  // The first version ranked every key by counting the larger ones — n^2 comparisons per user, 430 us for
+  // 10 k users x 8 shards x 64 entries; this is n log^2 n / 2.
+  for (int size = 2; size <= n_pad; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      __syncthreads();
+      for (int t = threadIdx.x; t < (n_pad >> 1); t += blockDim.x) {
+        const int i = ((t / stride) * (stride << 1)) + (t % stride);   // lower index of the pair
+        const int j = i + stride;
+        const unsigned long long a = s_all[i], b = s_all[j];
+        const bool desc = ((i & size) == 0);
+        if (desc ? (a < b) : (a > b)) { s_all[i] = b; s_all[j] = a; }
+      }
     }
   }
-  if (written) atomicAdd(&s_written, written);
   __syncthreads();
+  for (int k = threadIdx.x; k < K_out; k += blockDim.x) {
+    const unsigned long long key = k < n_pad ? s_all[k] : 0ull;
+    out_score[static_cast<size_t>(u) * K_out + k] = key ? key_score(key) : -INFINITY;
+    out_idx[static_cast<size_t>(u) * K_out + k] = key ? static_cast<int>(key_idx(key)) : -1;
+  }
   if (bad != nullptr && threadIdx.x == 0) {
     float bmax = -INFINITY;
     int flagged = 0;
@@ -667,13 +674,11 @@ __global__ void __launch_bounds__(256) topk_merge_kernel(const float* __restrict
       bmax = fmaxf(bmax, __int_as_float(aux[o]));
       flagged |= aux[o + 1];
     }
-    const bool ok = s_written >= K_out ? (s_kth > bmax) : (bmax == -INFINITY);
+    const unsigned long long kth = (K_out - 1 < n_pad) ? s_all[K_out - 1] : 0ull;
+    // K_out merged entries exist: the K_out-th must beat every shard's bound; fewer: fine only when every shard
+    // listed ALL of its items (bound = -inf)
+    const bool ok = kth != 0ull ? (key_score(kth) > bmax) : (bmax == -INFINITY);
     bad[u] = (!ok || flagged) ? 1 : 0;
-  }
-  // fewer than K_out items in the union: pad the tail
-  for (int k = s_written + threadIdx.x; k < K_out; k += blockDim.x) {
-    out_score[static_cast<size_t>(u) * K_out + k] = -INFINITY;
-    out_idx[static_cast<size_t>(u) * K_out + k] = -1;
   }
 }
 
@@ -1020,6 +1025,12 @@ extern "C" int tt_topk_finalize_bounded(const tt_topk_plan* plan, const void* ca
                        stream_);
 }
 
+static size_t merge_smem_bytes(int n) {
+  int n_pad = 1;
+  while (n_pad < n) n_pad <<= 1;
+  return static_cast<size_t>(n_pad) * 8;
+}
+
 extern "C" int tt_topk_merge(const float* scores, const int32_t* idx, int G, int U, int K, float* out_score,
                              int32_t* out_idx, void* stream_) {
   return tt_topk_merge_lists(scores, idx, G, U, K, K, out_score, out_idx, stream_);
@@ -1031,7 +1042,7 @@ extern "C" int tt_topk_merge_lists(const float* scores, const int32_t* idx, int 
   TT_REQUIRE(scores && idx && out_score && out_idx && G > 0 && U > 0 && K_in > 0 && K_out > 0,
              "tt_topk_merge_lists: bad arguments");
   TT_REQUIRE(G * K_in <= 4096, "tt_topk_merge_lists: G*K_in = %d too large", G * K_in);
-  TT_CHECK_CUDA(launch_k(topk_merge_kernel, dim3(U), dim3(256), static_cast<size_t>(G) * K_in * 8, stream, scores, idx, static_cast<long long>(K_in), static_cast<const int*>(nullptr), G, U, K_in, K_out, out_score, out_idx, static_cast<int*>(nullptr)));
+  TT_CHECK_CUDA(launch_k(topk_merge_kernel, dim3(U), dim3(256), merge_smem_bytes(G * K_in), stream, scores, idx, static_cast<long long>(K_in), static_cast<const int*>(nullptr), G, U, K_in, K_out, out_score, out_idx, static_cast<int*>(nullptr)));
   TT_LAUNCH_CHECK();
   return TT_OK;
 }
@@ -1042,7 +1053,7 @@ extern "C" int tt_topk_merge_packed(const int32_t* packed, int ld, int G, int U,
   TT_REQUIRE(packed && out_score && out_idx && bad && G > 0 && U > 0 && K_in > 0 && K_out > 0 && ld >= 2 * K_in + 2,
              "tt_topk_merge_packed: bad arguments");
   TT_REQUIRE(G * K_in <= 4096, "tt_topk_merge_packed: G*K_in = %d too large", G * K_in);
-  TT_CHECK_CUDA(launch_k(topk_merge_kernel, dim3(U), dim3(256), static_cast<size_t>(G) * K_in * 8, stream, reinterpret_cast<const float*>(packed), packed + K_in, static_cast<long long>(ld), packed + 2 * K_in, G, U, K_in, K_out, out_score, out_idx, bad));
+  TT_CHECK_CUDA(launch_k(topk_merge_kernel, dim3(U), dim3(256), merge_smem_bytes(G * K_in), stream, reinterpret_cast<const float*>(packed), packed + K_in, static_cast<long long>(ld), packed + 2 * K_in, G, U, K_in, K_out, out_score, out_idx, bad));
   TT_LAUNCH_CHECK();
   return TT_OK;
 }

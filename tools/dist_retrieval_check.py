@@ -52,6 +52,39 @@ def main():
         print(f"world={world} users={U} items={N}: bounded {out['bounded'][2]:.3f} ms/pass = {U / out['bounded'][2] * 1e3:.0f} users/s, "
               f"per-shard exact {out['per-shard exact'][2]:.3f} ms/pass; identical results on every rank: {bool(flag.item())}")
         print("DIST_RETRIEVAL_OK" if flag.item() else "DIST_RETRIEVAL_MISMATCH")
+    # host-side anatomy of one metrics_from_embeddings call (what bench.py's e2e_users_per_s times): every stage
+    # followed by a device synchronisation so wall-clock differences are attributable
+    import time
+    targets = (t + first).clone()
+    dist.broadcast(targets, 0)
+    hu, ht = users.cpu().pin_memory(), targets.cpu().pin_memory()
+    kl = [10, 20, 50, 100]
+    for _ in range(2):
+        retrieval.metrics_from_embeddings(users, targets, index, kl)
+    torch.cuda.synchronize()
+    marks = []
+
+    def mark(name):
+        torch.cuda.synchronize()
+        marks.append((name, time.perf_counter()))
+
+    dist.barrier()
+    mark("start")
+    du, dt = hu.to(dev, non_blocking=True), ht.to(dev, non_blocking=True)
+    mark("h2d")
+    i, s, bad = retrieval.sharded_topk(du, index, K, defer_check=True)
+    mark("sharded_topk")
+    rec, nd = retrieval.rank_metrics(i, dt, kl)
+    mark("rank_metrics")
+    packed = torch.cat([rec.flatten(), nd.flatten(), bad.max().float().view(1)]).cpu()
+    mark("readback")
+    t0 = time.perf_counter()
+    m = retrieval.metrics_from_embeddings(hu.to(dev, non_blocking=True), ht.to(dev, non_blocking=True), index, kl)
+    torch.cuda.synchronize()
+    whole = time.perf_counter() - t0
+    if rank == 0:
+        print("e2e anatomy (ms):", ", ".join(f"{b[0]} {1e3 * (b[1] - a[1]):.2f}" for a, b in zip(marks[:-1], marks[1:])),
+              f"| whole call {1e3 * whole:.2f}", f"recall@10 {m['Recall@10']:.4f}")
     dist.destroy_process_group()
 
 

@@ -11,7 +11,8 @@ import torch  # noqa: E402
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--what", default="train", choices=["train", "retrieval"])
+    ap.add_argument("--what", default="train", choices=["train", "retrieval", "shard"])
+    ap.add_argument("--shards", type=int, default=8, help="--what shard: the per-rank pass of a catalog sharded this many ways")
     ap.add_argument("--batch", type=int, default=256)
     ap.add_argument("--seq-len", type=int, default=200)
     ap.add_argument("--vocab", type=int, default=100_001)
@@ -33,6 +34,32 @@ def main():
         torch.cuda.synchronize()
         torch.cuda.profiler.start()
         eng.train_step(batch)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+    elif args.what == "shard":
+        # what ONE rank of an N-way sharded catalog runs per pass (retrieval.sharded_topk, bounded protocol): the
+        # candidate pass over items/N rows writing the exchange layout, then the merge of N gathered buffers
+        G = args.shards
+        n = (args.items + 1 + G - 1) // G
+        g = torch.Generator(device=dev).manual_seed(1)
+        table = torch.nn.functional.normalize(torch.randn(n, 256, device=dev, generator=g), dim=1)
+        index = retrieval.CatalogIndex.from_shard(table, n, args.items + 1, device=dev)     # a middle shard
+        t = torch.randint(1, n, (args.users,), device=dev, generator=g)
+        users = torch.nn.functional.normalize(table[t] + 3.3 / 16 * torch.randn(args.users, 256, device=dev, generator=g), dim=1)
+        kps = retrieval.shard_kprime(256, G)
+        buf = retrieval.exchange_buffers(index, args.users, 2 * kps + 2, G)
+
+        def one():
+            retrieval.retrieve_candidates(users, index, kps, pack=buf["pack"])
+            for r in range(G):                       # stands in for the all-gather
+                buf["all"][r * args.users:(r + 1) * args.users].copy_(buf["pack"])
+            return retrieval.merge_packed(buf["all"], G, args.users, kps, 100, buf["bad"])
+
+        for _ in range(2):
+            one()
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        one()
         torch.cuda.synchronize()
         torch.cuda.profiler.stop()
     else:
