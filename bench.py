@@ -9,10 +9,17 @@ all histories full length, synthetic precomputed modality embeddings.
           step's batch and D2H of its loss inside the timed region.
   roofline     : the tcgen05 GEMM (dominant kernel): algorithmic FLOPs / event-timed duration of
                  the step's own GEMM launches, against MEASURED_PEAKS.json bf16 sustained.
-  cpu_baseline : the oracle port of the reference step on this box's host cores (bounded sample).
+  cpu_baseline : the reference's OWN train_one_epoch / calculate_metrics_global (baseline/_ref) on this box's host
+                 cores, bounded sample, rank 0 at N=1.
+  parity       : loss / embeddings of the bench batch (dropout 0) against the oracle; top-100 of 512 bench users
+                 against an fp64 canonical sort; sharded == single-GPU retrieval result.
   retrieval    : evaluate_metrics workload (BASELINE.json configs[2]): 10k users x 1M items,
-                 top-100 + Recall/NDCG, catalog sharded over the N GPUs.
-`--impl reference` times the reference's CPU implementation (oracle port) for the same metric.
+                 top-100 + Recall/NDCG, ONE seeded catalog sharded over the N GPUs.
+  indexing     : catalog indexing of those 1M items (item list split over the N GPUs), GB/s vs 3 KB/item.
+  c4, c5       : (8 GPUs) BASELINE.json configs[3] and [4]: global batch 4096 with all-gathered negatives; 10M-item
+                 row-sharded ID table at seq len 512 (train step) and 10k x 10M retrieval.
+`--impl reference` runs the UNMODIFIED reference (baseline/_ref, installed by __graft_entry__.build()) for the same
+metric and config on the host cores; rank 0 only.
 """
 import argparse
 import json
@@ -71,7 +78,7 @@ class ClockSampler(threading.Thread):
                     self.samples.append(parts)
             except Exception:
                 pass
-            time.sleep(0.05)
+            time.sleep(0.01)
 
     def summary(self):
         if not self.samples:
@@ -295,14 +302,14 @@ def run_ours(args, rank, world, local_rank):
         torch.cuda.synchronize()
 
     # ---- warm-up (includes graph capture) -------------------------------------------------
+    sampler = ClockSampler(local_rank)     # samples clocks / throttle reasons from here to the end of the e2e loop
+    sampler.start()
     runner.load_batch(host_batches[0])
     for _ in range(max(args.warmup, 3)):
         runner.step_resident()
     torch.cuda.synchronize()
 
     # ---- value: device-resident inputs ----------------------------------------------------
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     l0 = _lib.launch_count

@@ -443,7 +443,7 @@ __device__ __forceinline__ void bitonic_sort_desc_256(unsigned long long* keys, 
   __syncthreads();
 }
 
-__global__ void __launch_bounds__(256) topk_finalize_kernel(const FinalizeParams p) {
+__global__ void __launch_bounds__(256, 4) topk_finalize_kernel(const FinalizeParams p) {
   pdl_launch_dependents();
   pdl_wait();
   __shared__ unsigned long long s_keys[256];
@@ -495,15 +495,8 @@ __global__ void __launch_bounds__(256) topk_finalize_kernel(const FinalizeParams
         if (s_off[mid] <= f) lo = mid; else hi = mid - 1;
       }
       const unsigned long long k = p.cand[(static_cast<size_t>(lo) * p.u_pad + u) * kCap + (f - s_off[lo])];
-      // warp-aggregated append: one shared-memory atomic per warp instead of one per key
-      const bool keep = k >= floor_key;
-      const unsigned m = __ballot_sync(__activemask(), keep);
-      if (keep) {
-        const int leader = __ffs(m) - 1;
-        int base = 0;
-        if (lane == leader) base = atomicAdd(&s_n, __popc(m));
-        base = __shfl_sync(m, base, leader);
-        const int pos = base + __popc(m & ((1u << lane) - 1u));
+      if (k >= floor_key) {
+        const int pos = atomicAdd(&s_n, 1);
         if (pos < p.pool_cap) s_pool[pos] = k;
       }
     }
