@@ -295,6 +295,8 @@ __global__ void __launch_bounds__(256) dp_adamw_kernel(const DpAdamwParams p) {
 }
 
 __global__ void symm_barrier_kernel(const Team t) {
+  pdl_launch_dependents();
+  pdl_wait();      // the epoch must be read after the previous collective on this arena has published it
   SymmCtrl* c = ctrl_of(t, t.rank);
   const uint32_t e = c->epoch + 1u;
   if (threadIdx.x == 0) {

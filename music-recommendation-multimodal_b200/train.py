@@ -62,7 +62,14 @@ def make_dp_engine(cfg, world_size: int, device=None, group=None, table: str = "
     if table == "replicated" or world_size == 1:
         return TwoTowerEngine(cfg, device), None
     eng = TwoTowerEngine(dataclasses.replace(cfg, vocab_size=2), device)
-    eng.peer_table = SymmShardedTable(cfg.vocab_size, cfg.embedding_dim, group, eng.device)
+    try:
+        eng.peer_table = SymmShardedTable(cfg.vocab_size, cfg.embedding_dim, group, eng.device)
+    except Exception as exc:      # no peer access / symmetric allocator refused (same outcome on every rank)
+        if table == "sharded" and os.environ.get("TT_TABLE", "") == "sharded":
+            raise
+        logger.warning(f"symmetric arena for the ID table unavailable ({exc}); keeping the table replicated")
+        del eng
+        return TwoTowerEngine(cfg, device), None
     return eng, eng.peer_table
 
 
