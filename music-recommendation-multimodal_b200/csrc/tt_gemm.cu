@@ -19,9 +19,6 @@
 
 namespace tt {
 
-bool rowgemm_eligible(const tt_gemm_args* a);                 // tt_rowgemm.cu
-int rowgemm_launch(const tt_gemm_args* a, cudaStream_t stream);
-
 struct GemmParams {
   int M, N, K;
   int block_n, stages, k_splits;
@@ -509,9 +506,6 @@ extern "C" int tt_gemm_bf16(const tt_gemm_args* a, void* stream_) {
   TT_REQUIRE(!(a->gate && a->residual), "tt_gemm_bf16: gate and residual cannot be combined");
   TT_REQUIRE(!a->accumulate || (a->out_f32 && !a->out_bf16),
              "tt_gemm_bf16: accumulate needs an fp32-only output");
-
-  // small problems (the B-row GEMMs of the heads, the single-row last layer, the logits): latency-optimised path
-  if (rowgemm_eligible(a)) return rowgemm_launch(a, stream);
 
   GemmParams p;
   p.M = a->M; p.N = a->N; p.K = a->K;
