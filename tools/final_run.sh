@@ -6,7 +6,7 @@ out=gpurun_out/final; mkdir -p $out
 timeout 400 python -m pytest tests -m gpu -q > $out/pytest_gpu.log 2>&1; echo "pytest rc=$?" | tee -a $out/status.txt
 timeout 200 python -c "import __graft_entry__ as g; g.smoke()" > $out/smoke.log 2>&1; echo "smoke rc=$?" | tee -a $out/status.txt
 timeout 600 python bench.py --steps 50 --warmup 5 > $out/bench.json 2> $out/bench.err; echo "bench rc=$?" | tee -a $out/status.txt
-timeout 400 python bench.py --impl reference --steps 2 --warmup 1 > $out/bench_reference.json 2> $out/bench_reference.err; echo "bench-ref rc=$?" | tee -a $out/status.txt
+timeout 400 python bench.py --impl reference --steps 5 --warmup 1 > $out/bench_reference.json 2> $out/bench_reference.err; echo "bench-ref rc=$?" | tee -a $out/status.txt
 timeout 200 python tools/profile_step.py > /dev/null 2>&1 && timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file $out/launches_train.csv python tools/profile_step.py > $out/ncu_lt.log 2>&1; echo "launches-train rc=$?" | tee -a $out/status.txt
 timeout 200 python tools/profile_step.py --what retrieval > /dev/null 2>&1 && timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file $out/launches_retrieval.csv python tools/profile_step.py --what retrieval > $out/ncu_lr.log 2>&1; echo "launches-retrieval rc=$?" | tee -a $out/status.txt
 if [ "${FULL:-1}" = "1" ]; then
@@ -19,6 +19,7 @@ python tools/ncu_summary.py $out/topk_full.ncu-rep > $out/ncu_full_topk.summary.
 ncu -i $out/gemm_full.ncu-rep --page raw --csv 2>/dev/null | cut -d, -f1-60 | head -60 > $out/ncu_full_gemm.raw.head.csv
 rm -f $out/gemm_full.ncu-rep $out/topk_full.ncu-rep
 fi   # FULL=0 skips the two --set full captures (the slow part)
+timeout 200 python tools/profile_step.py --what shard > /dev/null 2>&1 && timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file $out/launches_retrieval_shard8.csv python tools/profile_step.py --what shard > $out/ncu_ls.log 2>&1; echo "launches-shard rc=$?" | tee -a $out/status.txt
 timeout 200 python tools/gemm_log.py > $out/gemm_log.txt 2>&1
 timeout 200 python tools/trace_step.py > $out/trace.txt 2>&1
 tail -3 $out/pytest_gpu.log; cut -c1-300 $out/bench.json; cut -c1-300 $out/bench_reference.json
