@@ -25,7 +25,8 @@ def test_ids_dedup_gather_scatter_match_torch(V, T):
     cache = torch.zeros(T + 1, 256, device="cuda")
     gacc = torch.zeros(T + 1, 256, device="cuda")
     grad = torch.zeros(V, 256, device="cuda")
-    ref_grad = torch.zeros(V, 256, device="cuda")
+    ref_grad = torch.zeros(V, 256, device="cuda", dtype=torch.float64)
+    ref_abs = torch.zeros(V, 256, device="cuda", dtype=torch.float64)     # sum of |terms|: scale of the fp32 summation error
     for step in range(3):              # the flag table is cleaned by the NEXT call: several steps, different ids
         ids = synthetic.make_batch(cfg, T // 50, seed=step, zipf=True)["history_ids"].cuda().view(-1)[:T].contiguous()
         ops.ids_dedup(ids, V, sc["flag"], sc["slot"], sc["uniq"], sc["state"], sc["inverse"])
@@ -42,11 +43,13 @@ def test_ids_dedup_gather_scatter_match_torch(V, T):
         d[ids == 0] = 0
         gacc.index_add_(0, sc["inverse"], d)
         gacc[0] = 0
-        ref_grad.index_add_(0, ids, d)
+        ref_grad.index_add_(0, ids, d.double())
+        ref_abs.index_add_(0, ids, d.double().abs())
         ops.rows_scatter_add(sc["uniq"], sc["state"], gacc, grad_local=grad)
         torch.cuda.synchronize()
         assert gacc.abs().max().item() == 0.0                             # cleared for the next step
-        assert (grad - ref_grad).abs().max().item() <= 1e-4
+        # hot rows sum thousands of terms in an unspecified order: fp32 error scales with the sum of |terms|
+        assert bool(((grad.double() - ref_grad).abs() <= 1e-6 * ref_abs + 1e-6).all())
     assert grad[0].abs().max().item() == 0.0
 
 
