@@ -739,6 +739,52 @@ def bench_retrieval(eng, rank, world, dev, peaks):
 
     e2e_call()
     torch.cuda.synchronize()
+    anatomy = None
+    if os.environ.get("TT_BENCH_ANATOMY", "") == "1":      # diagnostic: where one e2e call spends its host time
+        marks = []
+
+        def mark(name):
+            torch.cuda.synchronize()
+            marks.append((name, time.perf_counter()))
+
+        if world > 1:
+            dist.barrier()
+        mark("start")
+        du, dt = host_users.to(dev, non_blocking=True), host_targets.to(dev, non_blocking=True)
+        mark("h2d")
+        if world > 1:
+            ai, as_, ab = retrieval.sharded_topk(du, index, K, defer_check=True)
+        else:
+            ai, as_, _ = retrieval.retrieve_topk(du, index, K)
+        mark("topk")
+        rec, nd = retrieval.rank_metrics(ai, dt, kl)
+        mark("rank_metrics")
+        torch.cat([rec.flatten(), nd.flatten()]).cpu()
+        mark("readback")
+        anatomy = {b[0]: 1e3 * (b[1] - a[1]) for a, b in zip(marks[:-1], marks[1:])}
+        # the same statements as metrics_from_embeddings, host clock only (no added synchronisation)
+        hm = [("start", time.perf_counter())]
+        du, dt = host_users.to(dev, non_blocking=True), host_targets.to(dev, non_blocking=True)
+        hm.append(("h2d_enqueue", time.perf_counter()))
+        if world > 1:
+            ai, as_, ab = retrieval.sharded_topk(du, index, K, 256, None, defer_check=True)
+        else:
+            ai, as_, _ = retrieval.retrieve_topk(du, index, K)
+            ab = torch.zeros(U, device=dev, dtype=torch.int32)
+        hm.append(("topk_enqueue", time.perf_counter()))
+        rec, nd = retrieval.rank_metrics(ai, dt, kl)
+        hm.append(("rank_metrics_enqueue", time.perf_counter()))
+        bm = ab.max().float().view(1)
+        hm.append(("bad_max", time.perf_counter()))
+        pk = torch.cat([rec.flatten(), nd.flatten(), bm])
+        hm.append(("cat", time.perf_counter()))
+        pk = pk.cpu()
+        hm.append(("cpu", time.perf_counter()))
+        _ = pk[-1].item()
+        rr = pk[:rec.numel()].view(rec.shape)
+        _ = [rr[j].mean().item() for j in range(rr.shape[0])]
+        hm.append(("means", time.perf_counter()))
+        anatomy["host_only"] = {b[0]: 1e3 * (b[1] - a[1]) for a, b in zip(hm[:-1], hm[1:])}
     if world > 1:
         dist.barrier()
     e2e_calls = []
@@ -842,7 +888,7 @@ def bench_retrieval(eng, rank, world, dev, peaks):
     flops = 2.0 * U * (N + 1) * 256 / world
     peak_tf = peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops"))
     return {"metric": "top-100 retrieval users/sec @1M items", "recommend_1user_ms": rec_ms, "users_per_s": U / (ms * 1e-3),
-            "ms_per_pass": ms, "e2e_users_per_s": U / e2e.item(), "e2e_ms_per_call_rank0": e2e_calls,
+            "ms_per_pass": ms, "e2e_users_per_s": U / e2e.item(), "e2e_ms_per_call_rank0": e2e_calls, "e2e_anatomy_ms": anatomy,
             "e2e_users_per_s_incl_user_tower": U / e2e_tower.item(),
             "scoring_tflops_per_gpu": flops / (ms * 1e-3) / 1e12,
             "roofline_frac_tensor": flops / (ms * 1e-3) / 1e12 / peak_tf,

@@ -119,15 +119,43 @@ class CatalogIndex:
         return self._plans[key]
 
 
-def exchange_buffers(index, U: int, ld: int, world: int) -> Dict[str, torch.Tensor]:
-    """Reused buffers of the sharded protocol: this shard's packed lists, the all-gathered ones, the flags."""
+def exchange_buffers(index, U: int, ld: int, world: int, group=None) -> Dict[str, torch.Tensor]:
+    """Reused buffers of the sharded protocol: this shard's packed rows [U, ld] int32, the gathered ones
+    [world * U, ld], the certificate flags. On an NCCL group of one NVLink domain the gathered buffer lives in a
+    symmetric arena and `exchange` moves the rows with this repo's all-gather kernel (peer / multicast stores + an
+    in-kernel barrier); otherwise (gloo tests, no peer access) with the library collective. Collective on first use."""
     key = ("xchg", U, ld, world)
     if key not in index._scratch:
         dev = index.table.device
-        index._scratch[key] = {"pack": torch.empty(U, ld, device=dev, dtype=torch.int32),
-                               "all": torch.empty(world * U, ld, device=dev, dtype=torch.int32),
-                               "bad": torch.zeros(U, device=dev, dtype=torch.int32)}
+        buf = {"pack": torch.empty(U, ld, device=dev, dtype=torch.int32),
+               "bad": torch.zeros(U, device=dev, dtype=torch.int32), "arena": None}
+        if dev.type == "cuda" and os.environ.get("TT_COMM", "") != "nccl":
+            from . import symm
+            if symm.available(group):
+                try:
+                    buf["arena"] = symm.SymmArena({"all": world * U * ld * 4}, group, dev)
+                    buf["all"] = buf["arena"].view("all", torch.int32, (world * U, ld))
+                except Exception:          # same outcome on every rank: fall back to the library collective
+                    buf["arena"] = None
+        if buf["arena"] is None:
+            buf["all"] = torch.empty(world * U, ld, device=dev, dtype=torch.int32)
+        index._scratch[key] = buf
     return index._scratch[key]
+
+
+def _pitch(k: int) -> int:
+    """Row pitch (int32 words) of the exchange layout [k scores | k ids | bound | flag], padded to 16 bytes."""
+    return (2 * k + 2 + 3) // 4 * 4
+
+
+def exchange(buf: Dict[str, torch.Tensor], group=None) -> None:
+    """buf['all'][r * U:(r + 1) * U] = rank r's buf['pack'] on every rank."""
+    if buf["arena"] is not None:
+        # leading barrier: a peer may still be merging the previous pass out of its gathered buffer
+        buf["arena"].allgather([(buf["pack"], "all")], pre_barrier=True)
+    else:
+        import torch.distributed as dist
+        dist.all_gather_into_tensor(buf["all"], buf["pack"], group=group)
 
 
 def retrieve_topk(user_emb: torch.Tensor, index: CatalogIndex, K: int, kprime: int = 256,
@@ -193,17 +221,17 @@ def retrieve_candidates(user_emb: torch.Tensor, index: "CatalogIndex", kprime: i
     Returns (idx int32 (U, kprime) global ids, -1 padded; score fp32 (U, kprime); bound fp32 (U,): every item of
     the shard that is not in the list has exact score <= bound; overflow int32 (U,): 1 = tie flood, use the exact
     path). With G shards a shard needs about 1/G of the single-GPU candidate budget (`shard_kprime`).
-    ``pack`` int32 (U, 2 * kprime + 2): the kernel writes the exchange layout [scores | ids | bound | flag] of
+    ``pack`` int32 (U, >= 2 * kprime + 2): the kernel writes the exchange layout [scores | ids | bound | flag] of
     `sharded_topk` directly and the four results are views of it."""
     assert user_emb.is_cuda and user_emb.dtype == torch.float32 and user_emb.shape[1] == 256
     user_emb = user_emb.contiguous()
     U = user_emb.shape[0]
     plan, sc = _score_pass(user_emb, index, kprime, mask_item0)
     dev = user_emb.device
-    ld = 2 * kprime + 2
     if pack is None:
-        pack = torch.empty(U, ld, device=dev, dtype=torch.int32)
-    assert pack.dtype == torch.int32 and pack.shape == (U, ld) and pack.is_contiguous()
+        pack = torch.empty(U, 2 * kprime + 2, device=dev, dtype=torch.int32)
+    ld = pack.shape[1]           # row pitch in words: >= 2 * kprime + 2 (padded so rows stay 16-byte multiples)
+    assert pack.dtype == torch.int32 and pack.shape[0] == U and ld >= 2 * kprime + 2 and pack.is_contiguous()
     base = pack.data_ptr()
     check(lib().tt_topk_finalize_bounded(ctypes.byref(plan), sc["cand"].data_ptr(), sc["cnt"].data_ptr(),
                                          sc["thr"].data_ptr(), user_emb.data_ptr(), index.table.data_ptr(),
@@ -265,12 +293,16 @@ def sharded_topk(user_emb: torch.Tensor, index: "CatalogIndex", K: int, kprime: 
     def per_shard_exact(users):
         i, s, _ = retrieve_topk(users, index, K, kprime)
         n = s.shape[0]
-        # outputs are allocated in the concatenated form (ws * n, K): the stacked form is NCCL-only
-        all_s = torch.empty(ws * n, K, device=s.device, dtype=s.dtype)
-        all_i = torch.empty(ws * n, K, device=i.device, dtype=i.dtype)
-        dist.all_gather_into_tensor(all_s, s.contiguous(), group=group)
-        dist.all_gather_into_tensor(all_i, i.contiguous(), group=group)
-        return merge_topk(all_s.view(ws, n, K), all_i.view(ws, n, K))
+        # one exchange of [scores | ids | bound = -inf | flag = 0] rows, merged in place like the bounded protocol
+        # (every shard's list IS its exact top K, so the certificate is trivially satisfied)
+        xb = exchange_buffers(index, n, _pitch(K), ws, group)
+        pk = xb["pack"]
+        pk[:, :K] = s.view(torch.int32)
+        pk[:, K:2 * K] = i
+        pk[:, 2 * K] = -8388608        # fp32 -inf as int32 (0xFF800000)
+        pk[:, 2 * K + 1] = 0
+        exchange(xb, group)
+        return merge_packed(xb["all"], ws, n, K, K, xb["bad"])
 
     global last_fallback_users
     last_fallback_users = 0
@@ -280,12 +312,11 @@ def sharded_topk(user_emb: torch.Tensor, index: "CatalogIndex", K: int, kprime: 
             if defer_check else out
     kps = shard_kprime(kprime, ws)
     U = user_emb.shape[0]
-    ld = 2 * kps + 2
-    buf = exchange_buffers(index, U, ld, ws)
+    buf = exchange_buffers(index, U, _pitch(kps), ws, group)
     # the finalize kernel writes this shard's lists, bounds and flags in the exchange layout; ONE all-gather; the merge
     # kernel reads the gathered buffer in place and emits the certificate
     retrieve_candidates(user_emb, index, kps, pack=buf["pack"])
-    dist.all_gather_into_tensor(buf["all"], buf["pack"], group=group)
+    exchange(buf, group)
     bad = buf["bad"]
     out_i, out_s = merge_packed(buf["all"], ws, U, kps, K, bad)
     if defer_check:
@@ -295,11 +326,11 @@ def sharded_topk(user_emb: torch.Tensor, index: "CatalogIndex", K: int, kprime: 
 
 
 def merge_packed(allp: torch.Tensor, G: int, U: int, kps: int, K: int, bad: torch.Tensor):
-    """Merge the all-gathered exchange buffer [G * U, 2 * kps + 2] (rows [scores | ids | bound | flag]) into the global
+    """Merge the all-gathered exchange buffer [G * U, ld >= 2 * kps + 2] (rows [scores | ids | bound | flag]) into the global
     top K per user, in place of any unpacking; ``bad`` (int32 (U,)) receives the certificate (1 = not certified)."""
     out_s = torch.empty(U, K, device=allp.device, dtype=torch.float32)
     out_i = torch.empty(U, K, device=allp.device, dtype=torch.int32)
-    check(lib().tt_topk_merge_packed(allp.data_ptr(), 2 * kps + 2, G, U, kps, K, out_s.data_ptr(), out_i.data_ptr(),
+    check(lib().tt_topk_merge_packed(allp.data_ptr(), allp.shape[1], G, U, kps, K, out_s.data_ptr(), out_i.data_ptr(),
                                      bad.data_ptr(), _stream()), "tt_topk_merge_packed")
     return out_i, out_s
 
@@ -371,12 +402,22 @@ def metrics_from_embeddings(user_emb: torch.Tensor, targets: torch.Tensor, index
     happens to be initialised (every rank then evaluates its own users against the whole catalog)."""
     K = max(k_list)
     targets = targets.to(user_emb.device)
+    _dbg = os.environ.get("TT_RETRIEVAL_TRACE", "") == "1"
+    if _dbg:
+        import time as _t
+        _marks = [("enter", _t.perf_counter())]
     if index.is_sharded:
         # the certificate flags travel to the host WITH the metrics: one synchronisation per call; only if a flag is
         # set (rare) the exact per-shard protocol repairs those users and the metrics are taken again
         idx, score, bad = sharded_topk(user_emb, index, K, kprime, group, defer_check=True)
+        if _dbg:
+            _marks.append(("sharded_topk", _t.perf_counter()))
         recall, ndcg = rank_metrics(idx, targets, k_list)
+        if _dbg:
+            _marks.append(("rank_metrics", _t.perf_counter()))
         packed = torch.cat([recall.flatten(), ndcg.flatten(), bad.max().float().view(1)]).cpu()
+        if _dbg:
+            _marks.append(("readback", _t.perf_counter()))
         if packed[-1].item() != 0:
             finish_sharded_topk(user_emb, index, K, idx, score, bad, kprime, group)
             recall, ndcg = rank_metrics(idx, targets, k_list)
@@ -392,4 +433,8 @@ def metrics_from_embeddings(user_emb: torch.Tensor, targets: torch.Tensor, index
         out[f"Recall@{k}"] = r[j].mean().item()
     for j, k in enumerate(k_list):
         out[f"NDCG@{k}"] = n[j].mean().item()
+    if _dbg:
+        _marks.append(("means", _t.perf_counter()))
+        print("metrics_from_embeddings host ms:", ", ".join(f"{b[0]} {1e3 * (b[1] - a[1]):.2f}" for a, b in zip(_marks[:-1], _marks[1:])),
+              file=__import__("sys").stderr, flush=True)
     return out

@@ -147,7 +147,7 @@ def _sharded_topk_plumbing_worker(rank, world, K, kps):
             sc[:, 0] = float("-inf")
         return sc
 
-    def retrieve_topk(u, ix, k, kprime=256, mask_item0=True, exact_fallback=True):
+    def retrieve_topk(u, ix, k, kprime=256, mask_item0=True, exact_fallback=True, flags_out=None):
         v, i = oracle.canonical_topk(shard_scores(u, ix), k)
         return (i + ix.item_base).to(torch.int32), v, 0
 
@@ -168,7 +168,7 @@ def _sharded_topk_plumbing_worker(rank, world, K, kps):
 
     def merge_packed(allp, G, U, kp, k, bad):
         """reference semantics of tt_topk_merge_packed on the gathered exchange buffer"""
-        a = allp.view(G, U, 2 * kp + 2)
+        a = allp.view(G, U, allp.shape[1])
         i, v, ok = sharding.merge_bounded_reference(a[:, :, :kp].contiguous().view(torch.float32),
                                                     a[:, :, kp:2 * kp].contiguous(),
                                                     a[:, :, 2 * kp].contiguous().view(torch.float32), k)

@@ -47,7 +47,7 @@ def main():
         t = torch.randint(1, n, (args.users,), device=dev, generator=g)
         users = torch.nn.functional.normalize(table[t] + 3.3 / 16 * torch.randn(args.users, 256, device=dev, generator=g), dim=1)
         kps = retrieval.shard_kprime(256, G)
-        buf = retrieval.exchange_buffers(index, args.users, 2 * kps + 2, G)
+        buf = retrieval.exchange_buffers(index, args.users, retrieval._pitch(kps), G)
 
         def one():
             retrieval.retrieve_candidates(users, index, kps, pack=buf["pack"])
