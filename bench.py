@@ -793,6 +793,8 @@ def bench_retrieval(eng, rank, world, dev, peaks):
         t1 = time.perf_counter()
         m = e2e_call()
         e2e_calls.append((time.perf_counter() - t1) * 1e3)
+        if os.environ.get("TT_RETRIEVAL_TRACE", "") == "1":
+            print(f"[rank {rank}] e2e call done at {time.time() % 100:.4f} took {e2e_calls[-1]:.2f} ms", file=sys.stderr, flush=True)
     torch.cuda.synchronize()
     e2e = torch.tensor([(time.perf_counter() - t0) / iters], device=dev)
     if world > 1:

@@ -725,6 +725,387 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
   if (warp == 0) tmem_dealloc(tmem_base, tmem_cols);
 }
 
+// --------------------------------------------------------------------------------------------
+// Backward, persistent and pipelined (L <= 256: one or two 128-row tiles). The kernel above spends most
+// of a CTA's life in chains of dependent latencies (TMEM allocation -> TMA -> MMA -> element-wise -> MMA,
+// one CTA per SM, nothing to overlap them with). Here a CTA per SM walks (sequence, head) items:
+//   * warps 0-15 (512 threads): the element-wise phase, thread (row, 32-column chunk) as above; they
+//     never issue anything, they only wait on / arrive at mbarriers;
+//   * warp 16, one lane: every TMA load and every MMA. S/dP of iteration g+1 are issued as soon as all
+//     512 threads hold S/dP of iteration g in registers (bar_drain), so those MMAs run under the
+//     element-wise phase of g; operand tiles of the NEXT item are loaded into each shared-memory slot
+//     as soon as the last MMA reading the slot has retired (Q0/dO0 after iteration 0, K0/V0 after
+//     iteration 1, the rest after iteration 2), so no load latency is exposed between items;
+//   * warp 17: delta = rowsum(dO * O) and the log-sum-exps of the next item, double-buffered.
+// Iterations of an item (key tile j, query tile i): (0,0), (0,1), (1,1); TMEM columns as in the fast
+// layout above. One __syncthreads at each end of the kernel, none inside.
+// --------------------------------------------------------------------------------------------
+static constexpr int kBwdComputeThreads = 512;
+static constexpr int kBwdCtrlRegs = 56, kBwdComputeRegs = 104;   // 512 * 104 + 128 * 56 <= 640 * 96
+static constexpr int kBwdThreads = kBwdComputeThreads + 128;   // + one warpgroup: issuer warp, delta warp, two idle
+
+__global__ void __launch_bounds__(kBwdThreads, 1)
+attn_bwd_persist_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
+                        const AttnBwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t pad = (1024u - (smem_u32(smem_raw) & 1023u)) & 1023u;
+  uint8_t* smem = smem_raw + pad;
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int D = p.H * kDh;
+  const int nq = p.nq;                       // 1 or 2
+  const int niter = nq == 2 ? 3 : 1;
+  const int n_items = p.B * p.H;
+
+  uint8_t* sQ = smem;                        // [2] tiles
+  uint8_t* sDO = sQ + 2 * kTileBytes;        // [2]
+  uint8_t* sK = sDO + 2 * kTileBytes;        // [2]
+  uint8_t* sV = sK + 2 * kTileBytes;         // [2]
+  uint8_t* sPd = sV + 2 * kTileBytes;        // 2 chunks
+  uint8_t* sDS = sPd + 2 * kTileBytes;       // 2 chunks
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sDS + 2 * kTileBytes);
+  uint64_t* bar_q = bars + 0;      // [2] Q_i + dO_i landed (one phase per item)
+  uint64_t* bar_kv = bars + 2;     // [2] K_j + V_j landed (one phase per item)
+  uint64_t* bar_mm1 = bars + 4;    // S and dP of iteration g ready
+  uint64_t* bar_drain = bars + 5;  // all compute threads hold S/dP of iteration g in registers
+  uint64_t* bar_stage = bars + 6;  // Pd / dS of iteration g are in shared memory
+  uint64_t* bar_mm2 = bars + 7;    // dV/dK/dQ MMAs of iteration g retired
+  uint64_t* bar_dfull = bars + 8;  // [2] delta / lse buffer filled
+  uint64_t* bar_dfree = bars + 10; // [2] delta / lse buffer no longer read
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+  float* sDelta = reinterpret_cast<float*>(bars + 14);  // [2][256]
+  float* sLse = sDelta + 2 * 2 * kTile;                 // [2][256], pre-multiplied by log2e
+
+  if (tid == 0) {
+    tma_prefetch_desc(&tmQKV);
+    tma_prefetch_desc(&tmDO);
+    mbar_init(bar_q + 0, 1);
+    mbar_init(bar_q + 1, 1);
+    mbar_init(bar_kv + 0, 1);
+    mbar_init(bar_kv + 1, 1);
+    mbar_init(bar_mm1, 1);
+    mbar_init(bar_drain, kBwdComputeThreads);
+    mbar_init(bar_stage, kBwdComputeThreads);
+    mbar_init(bar_mm2, 1);
+    mbar_init(bar_dfull + 0, 96);
+    mbar_init(bar_dfull + 1, 96);
+    mbar_init(bar_dfree + 0, kBwdComputeThreads);
+    mbar_init(bar_dfree + 1, kBwdComputeThreads);
+    fence_barrier_init();
+  }
+  __syncwarp();
+  if (warp == 16) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();
+  pdl_wait();
+  constexpr uint32_t T_S = 0, T_DP = 128, T_DV = 256, T_DK = 320, T_DQ = 384;
+
+  // 640 threads start with 96 registers each (the 20-warp allocation granule). The element-wise phase wants
+  // 64 raw values + ~40 of state per thread: the control warpgroup hands registers over to the compute warpgroups.
+  if (warp >= 16) {
+  reg_dealloc<kBwdCtrlRegs>();
+  if (warp == 16) {
+    // ======================= issuer: TMA loads and MMAs, one lane ==============================
+    if (lane == 0) {
+      const uint32_t idesc_s = umma_idesc_bf16(kTile, kTile, false, false);    // Q K^T, dO V^T
+      const uint32_t idesc_t = umma_idesc_bf16(kTile, kDh, true, true);        // X^T Y (dV, dK)
+      const uint32_t idesc_q = umma_idesc_bf16(kTile, kDh, false, true);       // dS K
+      auto load_q = [&](int item, int i) {      // Q_i, dO_i of `item` -> slot i
+        const int b = item / p.H, h = item % p.H;
+        mbar_arrive_expect_tx(bar_q + i, 2 * kTileBytes);
+        tma_load_2d(sQ + static_cast<size_t>(i) * kTileBytes, &tmQKV, bar_q + i, h * kDh, b * p.L + i * kTile);
+        tma_load_2d(sDO + static_cast<size_t>(i) * kTileBytes, &tmDO, bar_q + i, h * kDh, b * p.L + i * kTile);
+      };
+      auto load_kv = [&](int item, int j) {     // K_j, V_j of `item` -> slot j
+        const int b = item / p.H, h = item % p.H;
+        mbar_arrive_expect_tx(bar_kv + j, 2 * kTileBytes);
+        tma_load_2d(sK + static_cast<size_t>(j) * kTileBytes, &tmQKV, bar_kv + j, D + h * kDh, b * p.L + j * kTile);
+        tma_load_2d(sV + static_cast<size_t>(j) * kTileBytes, &tmQKV, bar_kv + j, 2 * D + h * kDh, b * p.L + j * kTile);
+      };
+      auto issue_mm1 = [&](int j, int i) {      // S = Q_i K_j^T, dP = dO_i V_j^T
+        const uint32_t q_base = smem_u32(sQ + static_cast<size_t>(i) * kTileBytes);
+        const uint32_t do_base = smem_u32(sDO + static_cast<size_t>(i) * kTileBytes);
+        const uint32_t k_base = smem_u32(sK + static_cast<size_t>(j) * kTileBytes);
+        const uint32_t v_base = smem_u32(sV + static_cast<size_t>(j) * kTileBytes);
+#pragma unroll
+        for (int k = 0; k < kDh / 16; ++k)
+          umma_bf16(tmem_base + T_S, umma_desc_kmajor(q_base + k * 32), umma_desc_kmajor(k_base + k * 32),
+                    idesc_s, k > 0 ? 1u : 0u);
+#pragma unroll
+        for (int k = 0; k < kDh / 16; ++k)
+          umma_bf16(tmem_base + T_DP, umma_desc_kmajor(do_base + k * 32), umma_desc_kmajor(v_base + k * 32),
+                    idesc_s, k > 0 ? 1u : 0u);
+        umma_commit(bar_mm1);
+      };
+      auto issue_mm2 = [&](int j, int i) {
+        const uint32_t pd_base = smem_u32(sPd), ds_base = smem_u32(sDS);
+        const uint32_t q_base = smem_u32(sQ + static_cast<size_t>(i) * kTileBytes);
+        const uint32_t do_base = smem_u32(sDO + static_cast<size_t>(i) * kTileBytes);
+        const uint32_t k_base = smem_u32(sK + static_cast<size_t>(j) * kTileBytes);
+        const uint32_t acc_kv = i > j ? 1u : 0u;   // first query tile of a key tile starts dV_j / dK_j
+        const uint32_t acc_q = j > 0 ? 1u : 0u;    // key tile 0 starts dQ_i
+#pragma unroll
+        for (int k = 0; k < kTile / 16; ++k)   // dV_j += Pd^T dO_i
+          umma_bf16(tmem_base + T_DV, umma_desc_mnmajor(pd_base + k * 2048, kTileBytes),
+                    umma_desc_mnmajor(do_base + k * 2048, kTileBytes), idesc_t, (acc_kv || k > 0) ? 1u : 0u);
+#pragma unroll
+        for (int k = 0; k < kTile / 16; ++k)   // dK_j += dS^T Q_i
+          umma_bf16(tmem_base + T_DK, umma_desc_mnmajor(ds_base + k * 2048, kTileBytes),
+                    umma_desc_mnmajor(q_base + k * 2048, kTileBytes), idesc_t, (acc_kv || k > 0) ? 1u : 0u);
+#pragma unroll
+        for (int k = 0; k < kTile / 16; ++k)   // dQ_i += dS K_j
+          umma_bf16(tmem_base + T_DQ + i * kDh,
+                    umma_desc_kmajor(ds_base + (k >> 2) * kTileBytes + (k & 3) * 32),
+                    umma_desc_mnmajor(k_base + k * 2048, kTileBytes), idesc_q, (acc_q || k > 0) ? 1u : 0u);
+        umma_commit(bar_mm2);
+      };
+
+      int item = blockIdx.x;
+      if (item < n_items) {
+        load_q(item, 0);
+        load_kv(item, 0);
+        if (nq == 2) {
+          load_q(item, 1);
+          load_kv(item, 1);
+        }
+        mbar_wait(bar_q + 0, 0);
+        mbar_wait(bar_kv + 0, 0);
+        tc_fence_after();
+        issue_mm1(0, 0);
+      }
+      uint32_t g = 0;
+      for (uint32_t n = 0; item < n_items; ++n, item += gridDim.x) {
+        const int next = item + static_cast<int>(gridDim.x);
+        const bool has_next = next < n_items;
+        const uint32_t par = n & 1u, npar = (n + 1u) & 1u;
+        for (int it = 0; it < niter; ++it, ++g) {
+          const int j = it == 2 ? 1 : 0, i = it == 0 ? 0 : 1;
+          mbar_wait(bar_drain, g & 1u);          // S/dP(g) sit in registers: their columns are free
+          tc_fence_after();
+          if (it + 1 < niter) {                   // next iteration of this item: (0,1) or (1,1)
+            if (it == 0) mbar_wait(bar_q + 1, par); else mbar_wait(bar_kv + 1, par);
+            tc_fence_after();
+            issue_mm1(it == 0 ? 0 : 1, 1);
+          }
+          mbar_wait(bar_stage, g & 1u);          // Pd / dS of g staged (and every earlier TMEM drain done)
+          tc_fence_after();
+          issue_mm2(j, i);
+          if (niter == 3) {
+            if (it == 2 && has_next) {            // first iteration of the next item; its tiles were requested
+              mbar_wait(bar_q + 0, npar);         // after iterations 0 and 1 of this item
+              mbar_wait(bar_kv + 0, npar);
+              tc_fence_after();
+              issue_mm1(0, 0);
+            }
+            mbar_wait(bar_mm2, g & 1u);          // the slots this iteration read last are free now
+            if (has_next) {
+              if (it == 0) load_q(next, 0);
+              else if (it == 1) load_kv(next, 0);
+              else { load_q(next, 1); load_kv(next, 1); }
+            }
+          } else {
+            mbar_wait(bar_mm2, g & 1u);
+            if (has_next) {
+              load_q(next, 0);
+              load_kv(next, 0);
+              mbar_wait(bar_q + 0, npar);
+              mbar_wait(bar_kv + 0, npar);
+              tc_fence_after();
+              issue_mm1(0, 0);
+            }
+          }
+        }
+      }
+    }
+  } else {
+    // ======================= warps 17-19: delta / lse of the item after the one being processed ====
+    int item = blockIdx.x;
+    for (uint32_t n = 0; item < n_items; ++n, item += gridDim.x) {
+      const uint32_t bsel = n & 1u;
+      if (n >= 2) mbar_wait(bar_dfree + bsel, ((n >> 1) - 1u) & 1u);
+      const int b = item / p.H, h = item % p.H;
+      const int seq_row0 = b * p.L;
+      for (int pos = (warp - 17) * 32 + lane; pos < nq * kTile; pos += 96) {
+        float delta = 0.f, lse2 = 0.f;
+        if (pos < p.L) {
+          const uint4* o = reinterpret_cast<const uint4*>(p.ctx + static_cast<size_t>(seq_row0 + pos) * D + h * kDh);
+          const uint4* gq = reinterpret_cast<const uint4*>(p.dctx + static_cast<size_t>(seq_row0 + pos) * D + h * kDh);
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const uint4 a = __ldg(o + u), c = __ldg(gq + u);
+            const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, cw[4] = {c.x, c.y, c.z, c.w};
+#pragma unroll
+            for (int w = 0; w < 4; ++w) {
+              const float2 x = unpack_bf16(aw[w]), y = unpack_bf16(cw[w]);
+              delta += x.x * y.x + x.y * y.y;
+            }
+          }
+          lse2 = p.lse[static_cast<size_t>(item) * p.L + pos] * kLog2e;
+        }
+        sDelta[bsel * 2 * kTile + pos] = delta;
+        sLse[bsel * 2 * kTile + pos] = lse2;
+      }
+      mbar_arrive(bar_dfull + bsel);
+    }
+  }
+  } else {
+    reg_alloc<kBwdComputeRegs>();
+    // ======================= compute warps ====================================================
+    const int q = warp & 3, grp = warp >> 2;   // TMEM lane quarter, 32-column chunk of the key tile
+    const int row = q * 32 + lane;
+    const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    const float c1 = p.scale * kLog2e;
+    const uint64_t seed = p.drop_seed + ((p.drop_thresh && p.drop_seed_dev) ? *p.drop_seed_dev : 0ull);
+    const uint32_t dkey = drop_key(seed, p.drop_site);
+    const int cg = grp;
+    const int u0 = (cg & 1) * 4;
+    uint8_t* pchunk = sPd + static_cast<size_t>(cg >> 1) * kTileBytes;
+    uint8_t* dchunk = sDS + static_cast<size_t>(cg >> 1) * kTileBytes;
+    // Key tile j of `ditem` complete: dK_j, dV_j TMEM -> dqkv (warp groups 0,1: the two 32-column halves of dK;
+    // 2,3: of dV); with_dq: the item is complete, dQ_i -> dqkv (groups (0,1) take tile 0, (2,3) tile 1).
+    // Called one iteration AFTER the MMAs were issued, so their completion barrier has long flipped.
+    auto drain = [&](int ditem, int j, bool with_dq) {
+      __syncwarp();
+      tc_fence_after();
+      const int b = ditem / p.H, h = ditem % p.H;
+      const int hf = grp & 1;
+      const int pos = j * kTile + row;
+      __nv_bfloat16* base = p.dqkv + static_cast<size_t>(b * p.L) * (3 * D) + h * kDh + hf * 32;
+      uint32_t r[32];
+      tmem_ld32(lane_base + (grp < 2 ? T_DK : T_DV) + hf * 32, r);
+      tmem_ld_wait();
+      if (pos < p.L) store_row32_bf16(base + static_cast<size_t>(pos) * (3 * D) + (grp < 2 ? D : 2 * D), r);
+      const int qi = grp >> 1;
+      if (with_dq && qi < nq) {
+        const int qpos = qi * kTile + row;
+        tmem_ld32(lane_base + T_DQ + qi * kDh + hf * 32, r);
+        tmem_ld_wait();
+        if (qpos < p.L) store_row32_bf16(base + static_cast<size_t>(qpos) * (3 * D), r);
+      }
+      tc_fence_before();
+    };
+    uint32_t g = 0;
+    int item = blockIdx.x;
+    for (uint32_t n = 0; item < n_items; ++n, item += gridDim.x) {
+      const uint32_t bsel = n & 1u;
+      mbar_wait(bar_dfull + bsel, (n >> 1) & 1u);
+      for (int it = 0; it < niter; ++it, ++g) {
+        const int j = it == 2 ? 1 : 0, i = it == 0 ? 0 : 1;
+        const int q_pos = i * kTile + row;
+        const float lse2 = sLse[bsel * 2 * kTile + q_pos];
+        const float delta = sDelta[bsel * 2 * kTile + q_pos];
+        if (it == niter - 1) mbar_arrive(bar_dfree + bsel);   // last read of this buffer
+        const bool diag = (i == j);
+        const bool row_ok = q_pos < p.L;
+        const bool active = !(diag && cg > q);
+        // the dropout decisions of this thread's 32 elements do not depend on S / dP: formed while the MMAs run
+        const int kv0 = j * kTile + cg * 32;
+        uint32_t keepmask = 0xFFFFFFFFu;
+        if (active && p.drop_thresh) {
+          const uint32_t didx0 = (static_cast<uint32_t>(item) * p.L + q_pos) * p.L + kv0;
+          keepmask = 0u;
+          if ((didx0 & 3u) == 0u) {
+#pragma unroll
+            for (int t = 0; t < 32; t += 4) {
+              bool k[4];
+              drop_keep_quad(dkey, didx0 + t, p.drop_thresh, k);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) keepmask |= (k[e] ? 1u : 0u) << (t + e);
+            }
+          } else if ((didx0 & 1u) == 0u) {
+#pragma unroll
+            for (int t = 0; t < 32; t += 2) {
+              bool k0, k1;
+              drop_keep_pair(dkey, didx0 + t, p.drop_thresh, k0, k1);
+              keepmask |= (k0 ? 1u : 0u) << t;
+              keepmask |= (k1 ? 1u : 0u) << (t + 1);
+            }
+          } else {
+#pragma unroll
+            for (int t = 0; t < 32; ++t)
+              keepmask |= (drop_keep_k(dkey, didx0 + t, p.drop_thresh) ? 1u : 0u) << t;
+          }
+        }
+        mbar_wait(bar_mm1, g & 1u);
+        __syncwarp();
+        tc_fence_after();
+        // Two halves of 16 columns: 32 raw registers live instead of 64 (the element-wise phase also carries the
+        // 32 packed results and ~30 registers of state; 64 raw ones spilled). S / dP are released to the MMAs of
+        // the next iteration once the second half sits in registers, i.e. after half of the arithmetic.
+        uint4 vp[4], vd[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) vp[u] = vd[u] = make_uint4(0, 0, 0, 0);
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          uint32_t rs[16], rp[16];
+          if (active) {
+            tmem_ld16(lane_base + T_S + cg * 32 + half * 16, rs);
+            tmem_ld16(lane_base + T_DP + cg * 32 + half * 16, rp);
+            tmem_ld_wait();
+          }
+          if (half == 1) {
+            tc_fence_before();
+            mbar_arrive(bar_drain);
+          }
+          if (active) {
+#pragma unroll
+            for (int uu = 0; uu < 2; ++uu) {
+              const int u = half * 2 + uu;
+              float pd[8], ds[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                const int t = u * 8 + e;
+                float pr = fast_exp2(__uint_as_float(rs[uu * 8 + e]) * c1 - lse2);
+                if ((diag && kv0 + t > q_pos) || !row_ok) pr = 0.f;
+                const bool keep = (keepmask >> t) & 1u;
+                const float dp = keep ? __uint_as_float(rp[uu * 8 + e]) * p.drop_scale : 0.f;
+                pd[e] = keep ? pr * p.drop_scale : 0.f;
+                ds[e] = pr * (dp - delta) * p.scale;
+              }
+              vp[u].x = pack_bf16(pd[0], pd[1]);
+              vp[u].y = pack_bf16(pd[2], pd[3]);
+              vp[u].z = pack_bf16(pd[4], pd[5]);
+              vp[u].w = pack_bf16(pd[6], pd[7]);
+              vd[u].x = pack_bf16(ds[0], ds[1]);
+              vd[u].y = pack_bf16(ds[2], ds[3]);
+              vd[u].z = pack_bf16(ds[4], ds[5]);
+              vd[u].w = pack_bf16(ds[6], ds[7]);
+            }
+          }
+        }
+        // The previous iteration's MMAs no longer read Pd / dS; this wait is also what the deferred drain of
+        // their dK/dV/dQ accumulators needs. It was issued a whole element-wise phase ago: no stall.
+        if (g > 0) {
+          mbar_wait(bar_mm2, (g - 1u) & 1u);
+          if (it != 1) drain(it == 0 ? item - static_cast<int>(gridDim.x) : item, (niter == 3 && it == 0) ? 1 : 0, it == 0);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          st_swizzled_unit(pchunk, row, u0 + u, vp[u]);
+          st_swizzled_unit(dchunk, row, u0 + u, vd[u]);
+        }
+        fence_proxy_async_smem();
+        mbar_arrive(bar_stage);
+      }
+    }
+    if (g > 0) {   // the last item's key tile nq-1 and its dQ
+      mbar_wait(bar_mm2, (g - 1u) & 1u);
+      drain(item - static_cast<int>(gridDim.x), nq - 1, true);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 16) tmem_dealloc(tmem_base, 512);
+}
+
 static int make_rows_map(CUtensorMap* m, const void* base, int rows, int cols) {
   uint64_t dims[2] = {static_cast<uint64_t>(cols), static_cast<uint64_t>(rows)};
   uint64_t str[1] = {static_cast<uint64_t>(cols) * 2};
@@ -814,8 +1195,23 @@ extern "C" int tt_attn_causal_bwd(const void* qkv, const void* ctx, const void* 
     configured = true;
   }
   TT_REQUIRE(smem <= 232448, "tt_attn_causal_bwd: shared memory %zu too large", smem);
-  if (p.nq <= 2) TT_CHECK_CUDA(launch_k(attn_bwd_kernel<false, 4>, dim3(B * H), dim3(512), smem, stream, tmQ, tmDO, p));
-  else TT_CHECK_CUDA(launch_k(attn_bwd_kernel<true, 2>, dim3(B * H), dim3(256), smem, stream, tmQ, tmDO, p));
+  // TT_ATTN_BWD=legacy keeps the one-CTA-per-(sequence, head) kernel for L <= 256 (A/B runs, bit-equality test)
+  const char* mode = getenv("TT_ATTN_BWD");
+  const bool legacy = mode && mode[0] == 'l';
+  if (p.nq <= 2 && !legacy) {
+    const size_t psmem = 1024 + 12 * static_cast<size_t>(kTileBytes) + 128 + 2 * 2 * 2 * kTile * sizeof(float);
+    static bool pconfigured = false;
+    if (!pconfigured) {
+      TT_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+      pconfigured = true;
+    }
+    const int grid = B * H < num_sms() ? B * H : num_sms();
+    TT_CHECK_CUDA(launch_k(attn_bwd_persist_kernel, dim3(grid), dim3(kBwdThreads), psmem, stream, tmQ, tmDO, p));
+  } else if (p.nq <= 2) {
+    TT_CHECK_CUDA(launch_k(attn_bwd_kernel<false, 4>, dim3(B * H), dim3(512), smem, stream, tmQ, tmDO, p));
+  } else {
+    TT_CHECK_CUDA(launch_k(attn_bwd_kernel<true, 2>, dim3(B * H), dim3(256), smem, stream, tmQ, tmDO, p));
+  }
   TT_LAUNCH_CHECK();
   return TT_OK;
 }

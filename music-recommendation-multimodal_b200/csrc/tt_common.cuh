@@ -244,6 +244,17 @@ __device__ __forceinline__ void red_add_f32x4(float* addr, float a, float b, flo
                : "memory");
 }
 
+// Register re-partitioning between warpgroups (setmaxnreg): every warp of a warpgroup (4 consecutive
+// warps) executes the same instruction; the increase blocks until other warpgroups released enough.
+template <int N>
+__device__ __forceinline__ void reg_alloc() {
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N));
+}
+template <int N>
+__device__ __forceinline__ void reg_dealloc() {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));
+}
+
 // ----------------------------------------------------------------------------
 // mbarrier
 // ----------------------------------------------------------------------------

@@ -435,6 +435,7 @@ def metrics_from_embeddings(user_emb: torch.Tensor, targets: torch.Tensor, index
         out[f"NDCG@{k}"] = n[j].mean().item()
     if _dbg:
         _marks.append(("means", _t.perf_counter()))
-        print("metrics_from_embeddings host ms:", ", ".join(f"{b[0]} {1e3 * (b[1] - a[1]):.2f}" for a, b in zip(_marks[:-1], _marks[1:])),
+        print(f"[rank {os.environ.get('RANK', '0')}] metrics_from_embeddings t0 {_t.time() % 100:.4f} host ms:",
+              ", ".join(f"{b[0]} {1e3 * (b[1] - a[1]):.2f}" for a, b in zip(_marks[:-1], _marks[1:])),
               file=__import__("sys").stderr, flush=True)
     return out

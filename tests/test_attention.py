@@ -89,3 +89,28 @@ def test_attn_dropout_statistics():
     diff = (acc / n - base.float()).view(B, L, -1)[:, deep].abs().mean().item()
     ref = base.float().view(B, L, -1)[:, deep].abs().mean().item()
     assert diff <= 0.25 * ref, (diff, ref)
+
+
+@pytest.mark.parametrize("B,L,H,drop", [(3, 200, 4, 0.0), (160, 200, 4, 0.1), (150, 50, 4, 0.1), (40, 256, 2, 0.2),
+                                        (37, 129, 4, 0.1), (2, 128, 4, 0.0)])
+def test_attn_bwd_persistent_equals_legacy(B, L, H, drop, monkeypatch):
+    """The persistent, pipelined backward (L <= 256) runs the same arithmetic in the same order as the
+    one-CTA-per-(sequence, head) kernel: bit-identical dq/dk/dv, with and without dropout, with more
+    items than SMs (several items per CTA) and with fewer."""
+    from mrm_b200 import ops
+    g = torch.Generator().manual_seed(7 * L + B)
+    qkv = (torch.randn(B * L, 3 * H * 64, generator=g) * 1.2).cuda().bfloat16()
+    dctx = torch.randn(B * L, H * 64, generator=g).cuda().bfloat16()
+    ctx = torch.empty((B * L, H * 64), device="cuda", dtype=torch.bfloat16)
+    lse = torch.empty(B, H, L, device="cuda")
+    ops.attn_fwd(qkv, ctx, lse, B, L, H, drop_p=drop, drop_seed=11, drop_site=2)
+    out = {}
+    for mode in ("legacy", "persistent"):
+        monkeypatch.setenv("TT_ATTN_BWD", mode)
+        d = torch.full((B * L, 3 * H * 64), float("nan"), device="cuda", dtype=torch.bfloat16)
+        for _ in range(2):      # twice: the second launch must not depend on state left by the first
+            ops.attn_bwd(qkv, ctx, dctx, lse, d, B, L, H, drop_p=drop, drop_seed=11, drop_site=2)
+        torch.cuda.synchronize()
+        out[mode] = d
+    assert torch.isfinite(out["persistent"].float()).all()
+    assert torch.equal(out["legacy"], out["persistent"])
