@@ -310,15 +310,19 @@ struct AttnBwdParams {
   __nv_bfloat16* dqkv;        // [T, 3*H*64]
 };
 
+// 32 fp32 accumulator columns -> 32 bf16 = 64 bytes of one row, as two 32-byte stores: every store fills a whole
+// sector (the rows of a warp are 1.5 KB apart, so nothing coalesces across lanes; 16-byte stores left half-written
+// sectors for the L2 to merge). dst is 64-byte aligned (row pitch, head offset and column half all are).
 __device__ __forceinline__ void store_row32_bf16(__nv_bfloat16* dst, const uint32_t (&r)[32]) {
 #pragma unroll
-  for (int u = 0; u < 4; ++u) {
-    uint4 v;
-    v.x = pack_bf16(__uint_as_float(r[u * 8 + 0]), __uint_as_float(r[u * 8 + 1]));
-    v.y = pack_bf16(__uint_as_float(r[u * 8 + 2]), __uint_as_float(r[u * 8 + 3]));
-    v.z = pack_bf16(__uint_as_float(r[u * 8 + 4]), __uint_as_float(r[u * 8 + 5]));
-    v.w = pack_bf16(__uint_as_float(r[u * 8 + 6]), __uint_as_float(r[u * 8 + 7]));
-    *reinterpret_cast<uint4*>(dst + u * 8) = v;
+  for (int u = 0; u < 2; ++u) {
+    uint32_t w[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e)
+      w[e] = pack_bf16(__uint_as_float(r[u * 16 + 2 * e]), __uint_as_float(r[u * 16 + 2 * e + 1]));
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst + u * 16), "r"(w[0]), "r"(w[1]),
+                 "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7])
+                 : "memory");
   }
 }
 
@@ -926,8 +930,10 @@ attn_bwd_persist_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
     }
   } else {
     // ======================= warps 17-19: delta / lse of the item after the one being processed ====
-    int item = blockIdx.x;
-    for (uint32_t n = 0; item < n_items; ++n, item += gridDim.x) {
+    // (the first item's values are formed by the compute threads themselves, one position each: nothing else
+    // for them to do at kernel start, and it takes one load round trip instead of three)
+    int item = blockIdx.x + gridDim.x;
+    for (uint32_t n = 1; item < n_items; ++n, item += gridDim.x) {
       const uint32_t bsel = n & 1u;
       if (n >= 2) mbar_wait(bar_dfree + bsel, ((n >> 1) - 1u) & 1u);
       const int b = item / p.H, h = item % p.H;
@@ -993,9 +999,32 @@ attn_bwd_persist_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
     };
     uint32_t g = 0;
     int item = blockIdx.x;
+    if (tid < nq * kTile) {   // delta / lse of this CTA's first item
+      const int b = item / p.H, h = item % p.H;
+      float delta = 0.f, lse2 = 0.f;
+      if (tid < p.L) {
+        const uint4* o = reinterpret_cast<const uint4*>(p.ctx + static_cast<size_t>(b * p.L + tid) * D + h * kDh);
+        const uint4* gq = reinterpret_cast<const uint4*>(p.dctx + static_cast<size_t>(b * p.L + tid) * D + h * kDh);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const uint4 a = __ldg(o + u), c = __ldg(gq + u);
+          const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, cw[4] = {c.x, c.y, c.z, c.w};
+#pragma unroll
+          for (int w = 0; w < 4; ++w) {
+            const float2 x = unpack_bf16(aw[w]), y = unpack_bf16(cw[w]);
+            delta += x.x * y.x + x.y * y.y;
+          }
+        }
+        lse2 = p.lse[static_cast<size_t>(item) * p.L + tid] * kLog2e;
+      }
+      sDelta[tid] = delta;
+      sLse[tid] = lse2;
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(kBwdComputeThreads) : "memory");
     for (uint32_t n = 0; item < n_items; ++n, item += gridDim.x) {
       const uint32_t bsel = n & 1u;
-      mbar_wait(bar_dfull + bsel, (n >> 1) & 1u);
+      // buffer 1 is filled for items 1, 3, ... (completion n >> 1), buffer 0 for items 2, 4, ... ((n >> 1) - 1)
+      if (n > 0) mbar_wait(bar_dfull + bsel, ((n >> 1) - (bsel ? 0u : 1u)) & 1u);
       for (int it = 0; it < niter; ++it, ++g) {
         const int j = it == 2 ? 1 : 0, i = it == 0 ? 0 : 1;
         const int q_pos = i * kTile + row;
@@ -1004,7 +1033,8 @@ attn_bwd_persist_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
         if (it == niter - 1) mbar_arrive(bar_dfree + bsel);   // last read of this buffer
         const bool diag = (i == j);
         const bool row_ok = q_pos < p.L;
-        const bool active = !(diag && cg > q);
+        // inactive (warp-uniform): above the diagonal, or all 32 query rows / all 32 key columns beyond the sequence
+        const bool active = !(diag && cg > q) && (i * kTile + q * 32 < p.L) && (j * kTile + cg * 32 < p.L);
         // the dropout decisions of this thread's 32 elements do not depend on S / dP: formed while the MMAs run
         const int kv0 = j * kTile + cg * 32;
         uint32_t keepmask = 0xFFFFFFFFu;
