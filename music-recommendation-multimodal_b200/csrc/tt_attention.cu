@@ -833,41 +833,41 @@ attn_bwd_persist_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
         tma_load_2d(sK + static_cast<size_t>(j) * kTileBytes, &tmQKV, bar_kv + j, D + h * kDh, b * p.L + j * kTile);
         tma_load_2d(sV + static_cast<size_t>(j) * kTileBytes, &tmQKV, bar_kv + j, 2 * D + h * kDh, b * p.L + j * kTile);
       };
+      // Descriptors are formed once per tile; a k-step only adds its byte offset (>> 4) to the start-address
+      // field (shared-memory addresses < 256 KB: the 14-bit field cannot carry). The issue loop of the 24
+      // accumulator MMAs is on the critical path of every iteration: ~8 instead of ~14 instructions per MMA.
       auto issue_mm1 = [&](int j, int i) {      // S = Q_i K_j^T, dP = dO_i V_j^T
-        const uint32_t q_base = smem_u32(sQ + static_cast<size_t>(i) * kTileBytes);
-        const uint32_t do_base = smem_u32(sDO + static_cast<size_t>(i) * kTileBytes);
-        const uint32_t k_base = smem_u32(sK + static_cast<size_t>(j) * kTileBytes);
-        const uint32_t v_base = smem_u32(sV + static_cast<size_t>(j) * kTileBytes);
+        const uint64_t dq = umma_desc_kmajor(smem_u32(sQ + static_cast<size_t>(i) * kTileBytes));
+        const uint64_t dd = umma_desc_kmajor(smem_u32(sDO + static_cast<size_t>(i) * kTileBytes));
+        const uint64_t dk = umma_desc_kmajor(smem_u32(sK + static_cast<size_t>(j) * kTileBytes));
+        const uint64_t dv = umma_desc_kmajor(smem_u32(sV + static_cast<size_t>(j) * kTileBytes));
 #pragma unroll
         for (int k = 0; k < kDh / 16; ++k)
-          umma_bf16(tmem_base + T_S, umma_desc_kmajor(q_base + k * 32), umma_desc_kmajor(k_base + k * 32),
-                    idesc_s, k > 0 ? 1u : 0u);
+          umma_bf16(tmem_base + T_S, dq + (k * 32 >> 4), dk + (k * 32 >> 4), idesc_s, k > 0 ? 1u : 0u);
 #pragma unroll
         for (int k = 0; k < kDh / 16; ++k)
-          umma_bf16(tmem_base + T_DP, umma_desc_kmajor(do_base + k * 32), umma_desc_kmajor(v_base + k * 32),
-                    idesc_s, k > 0 ? 1u : 0u);
+          umma_bf16(tmem_base + T_DP, dd + (k * 32 >> 4), dv + (k * 32 >> 4), idesc_s, k > 0 ? 1u : 0u);
         umma_commit(bar_mm1);
       };
       auto issue_mm2 = [&](int j, int i) {
-        const uint32_t pd_base = smem_u32(sPd), ds_base = smem_u32(sDS);
-        const uint32_t q_base = smem_u32(sQ + static_cast<size_t>(i) * kTileBytes);
-        const uint32_t do_base = smem_u32(sDO + static_cast<size_t>(i) * kTileBytes);
-        const uint32_t k_base = smem_u32(sK + static_cast<size_t>(j) * kTileBytes);
+        const uint64_t dpd = umma_desc_mnmajor(smem_u32(sPd), kTileBytes);
+        const uint64_t dds = umma_desc_mnmajor(smem_u32(sDS), kTileBytes);
+        const uint64_t ddsk = umma_desc_kmajor(smem_u32(sDS));
+        const uint64_t dq = umma_desc_mnmajor(smem_u32(sQ + static_cast<size_t>(i) * kTileBytes), kTileBytes);
+        const uint64_t dd = umma_desc_mnmajor(smem_u32(sDO + static_cast<size_t>(i) * kTileBytes), kTileBytes);
+        const uint64_t dk = umma_desc_mnmajor(smem_u32(sK + static_cast<size_t>(j) * kTileBytes), kTileBytes);
         const uint32_t acc_kv = i > j ? 1u : 0u;   // first query tile of a key tile starts dV_j / dK_j
         const uint32_t acc_q = j > 0 ? 1u : 0u;    // key tile 0 starts dQ_i
 #pragma unroll
         for (int k = 0; k < kTile / 16; ++k)   // dV_j += Pd^T dO_i
-          umma_bf16(tmem_base + T_DV, umma_desc_mnmajor(pd_base + k * 2048, kTileBytes),
-                    umma_desc_mnmajor(do_base + k * 2048, kTileBytes), idesc_t, (acc_kv || k > 0) ? 1u : 0u);
+          umma_bf16(tmem_base + T_DV, dpd + (k * 2048 >> 4), dd + (k * 2048 >> 4), idesc_t, (acc_kv || k > 0) ? 1u : 0u);
 #pragma unroll
         for (int k = 0; k < kTile / 16; ++k)   // dK_j += dS^T Q_i
-          umma_bf16(tmem_base + T_DK, umma_desc_mnmajor(ds_base + k * 2048, kTileBytes),
-                    umma_desc_mnmajor(q_base + k * 2048, kTileBytes), idesc_t, (acc_kv || k > 0) ? 1u : 0u);
+          umma_bf16(tmem_base + T_DK, dds + (k * 2048 >> 4), dq + (k * 2048 >> 4), idesc_t, (acc_kv || k > 0) ? 1u : 0u);
 #pragma unroll
-        for (int k = 0; k < kTile / 16; ++k)   // dQ_i += dS K_j
-          umma_bf16(tmem_base + T_DQ + i * kDh,
-                    umma_desc_kmajor(ds_base + (k >> 2) * kTileBytes + (k & 3) * 32),
-                    umma_desc_mnmajor(k_base + k * 2048, kTileBytes), idesc_q, (acc_q || k > 0) ? 1u : 0u);
+        for (int k = 0; k < kTile / 16; ++k)   // dQ_i += dS K_j (A K-major: 64-column chunk k/4, 32 B per k-step inside)
+          umma_bf16(tmem_base + T_DQ + i * kDh, ddsk + (((k >> 2) * kTileBytes + (k & 3) * 32) >> 4),
+                    dk + (k * 2048 >> 4), idesc_q, (acc_q || k > 0) ? 1u : 0u);
         umma_commit(bar_mm2);
       };
 
@@ -898,16 +898,16 @@ attn_bwd_persist_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
             tc_fence_after();
             issue_mm1(it == 0 ? 0 : 1, 1);
           }
+          if (niter == 3 && it == 2 && has_next) {   // first iteration of the next item; its tiles were requested
+            mbar_wait(bar_q + 0, npar);              // after iterations 0 and 1 of this item (K0/V0 about one
+            mbar_wait(bar_kv + 0, npar);             // element-wise phase ago: the stage barrier below is later still)
+            tc_fence_after();
+            issue_mm1(0, 0);
+          }
           mbar_wait(bar_stage, g & 1u);          // Pd / dS of g staged (and every earlier TMEM drain done)
           tc_fence_after();
           issue_mm2(j, i);
           if (niter == 3) {
-            if (it == 2 && has_next) {            // first iteration of the next item; its tiles were requested
-              mbar_wait(bar_q + 0, npar);         // after iterations 0 and 1 of this item
-              mbar_wait(bar_kv + 0, npar);
-              tc_fence_after();
-              issue_mm1(0, 0);
-            }
             mbar_wait(bar_mm2, g & 1u);          // the slots this iteration read last are free now
             if (has_next) {
               if (it == 0) load_q(next, 0);
