@@ -125,6 +125,21 @@ int tt_embed_ln_bwd(const int64_t* ids, const float* E, const float* P, const fl
                     const float* dx0, int B, int L, float drop_p, uint64_t seed, const uint64_t* seed_dev,
                     uint32_t site, float* dE, float* dP, float* dgamma, float* dbeta, void* stream);
 
+/* Deterministic form of tt_embed_ln_bwd for the table gradient (the reference's embedding backward is
+ * autograd's embedding_dense_backward, src/models/user_tower.py:26; its CUDA form is deterministic only under
+ * torch.use_deterministic_algorithms). Token t adds its gradient row into acc64[slot_of_token[t]] (int64
+ * [slots, 256], slot 0 = padding: skipped) in 64-bit fixed point, 2^-40 units: integer addition is associative,
+ * so the sums do not depend on the order in which duplicate ids arrive and are bit-identical from run to run.
+ * slot_of_token / the distinct-id list come from tt_ids_dedup; tt_rows_scatter_add_i64 rounds every sum once to
+ * fp32, adds it to the table's gradient row (one writer per row) and clears the accumulator. dP / d(ln_w) /
+ * d(ln_b) as in tt_embed_ln_bwd. */
+int tt_embed_ln_bwd_det(const int64_t* ids, const float* E, const float* P, const float* ln_w, const float* ln_b,
+                        const float* dx0, int B, int L, float drop_p, uint64_t seed, const uint64_t* seed_dev,
+                        uint32_t site, const int64_t* slot_of_token, int64_t* acc64, float* dP, float* dgamma,
+                        float* dbeta, void* stream);
+int tt_rows_scatter_add_i64(float* grad_local, const int64_t* uniq, const int32_t* n_uniq, int max_rows,
+                            int64_t* acc64, void* stream);
+
 /* Row chain on fp32 rows of width 256 or 512:
  *   forward : [LayerNorm] -> [ReLU] -> [dropout] -> [L2 normalise] -> out_f32 / out_bf16
  *   backward: recomputes the forward from x, then dout -> ... -> (+resid) -> dx_f32 / dx_bf16,

@@ -50,6 +50,22 @@ __device__ __forceinline__ float fast_exp2(float x) {
   return y;
 }
 
+// 32 fp32 accumulator columns -> 32 bf16 = 64 bytes of one row, as two 32-byte stores: every store fills a whole
+// sector (the rows of a warp are 1.5 KB apart, so nothing coalesces across lanes; 16-byte stores left half-written
+// sectors for the L2 to merge). dst is 64-byte aligned (row pitch, head offset and column half all are).
+__device__ __forceinline__ void store_row32_bf16(__nv_bfloat16* dst, const uint32_t (&r)[32]) {
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    uint32_t w[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e)
+      w[e] = pack_bf16(__uint_as_float(r[u * 16 + 2 * e]), __uint_as_float(r[u * 16 + 2 * e + 1]));
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst + u * 16), "r"(w[0]), "r"(w[1]),
+                 "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7])
+                 : "memory");
+  }
+}
+
 // Forward. 256 threads: warp w -> TMEM lane quarter (w & 3), column half (w >> 2). Thread
 // (row, hf) owns query row `row` of the tile and the 64-column half `hf` of every 128-key tile.
 // Shared memory per CTA (nq = 2): Q 16 KB + K/V slots 32 KB (K first, then reused for V once the
@@ -264,14 +280,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
     tmem_ld_wait();
     if (valid) {
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        uint4 v;
-        v.x = pack_bf16(__uint_as_float(r[u * 8 + 0]) * inv_l, __uint_as_float(r[u * 8 + 1]) * inv_l);
-        v.y = pack_bf16(__uint_as_float(r[u * 8 + 2]) * inv_l, __uint_as_float(r[u * 8 + 3]) * inv_l);
-        v.z = pack_bf16(__uint_as_float(r[u * 8 + 4]) * inv_l, __uint_as_float(r[u * 8 + 5]) * inv_l);
-        v.w = pack_bf16(__uint_as_float(r[u * 8 + 6]) * inv_l, __uint_as_float(r[u * 8 + 7]) * inv_l);
-        *reinterpret_cast<uint4*>(orow + u * 8) = v;
-      }
+      for (int t = 0; t < 32; ++t) r[t] = __float_as_uint(__uint_as_float(r[t]) * inv_l);
+      store_row32_bf16(orow, r);   // two 32-byte stores: whole sectors (rows are 512 B apart, nothing coalesces)
       if (hf == 0 && p.lse) p.lse[static_cast<size_t>(bh) * p.L + q_pos] = m * p.scale + __logf(l);
     }
   }
@@ -309,22 +319,6 @@ struct AttnBwdParams {
   const float* lse;           // [B,H,L]
   __nv_bfloat16* dqkv;        // [T, 3*H*64]
 };
-
-// 32 fp32 accumulator columns -> 32 bf16 = 64 bytes of one row, as two 32-byte stores: every store fills a whole
-// sector (the rows of a warp are 1.5 KB apart, so nothing coalesces across lanes; 16-byte stores left half-written
-// sectors for the L2 to merge). dst is 64-byte aligned (row pitch, head offset and column half all are).
-__device__ __forceinline__ void store_row32_bf16(__nv_bfloat16* dst, const uint32_t (&r)[32]) {
-#pragma unroll
-  for (int u = 0; u < 2; ++u) {
-    uint32_t w[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e)
-      w[e] = pack_bf16(__uint_as_float(r[u * 16 + 2 * e]), __uint_as_float(r[u * 16 + 2 * e + 1]));
-    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst + u * 16), "r"(w[0]), "r"(w[1]),
-                 "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7])
-                 : "memory");
-  }
-}
 
 // LONG = false: L <= 256 (two query tiles): S and dP have their own TMEM columns and are issued
 //   together. LONG = true: L <= 512 (four query tiles): the four dQ accumulators need 256 columns,

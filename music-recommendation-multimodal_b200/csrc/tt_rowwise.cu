@@ -583,11 +583,17 @@ __global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* _
 // Grid (L, S): block (pos, s) handles position `pos` for every S-th group of 8 sequences, so dP takes
 // S atomics per element; S is chosen so that all blocks are resident at 2 per SM.
 // --------------------------------------------------------------------------------------------
+// Fixed-point scale of the deterministic table-gradient accumulation: 2^40 (resolution 9.1e-13, |sum| < 8.3e6).
+static constexpr float kGradFixScale = 1099511627776.f;
+
 struct EmbedBwdParams {
   const int64_t* ids; TableRef E; const float* stash; const float* P; const float* ln_w; const float* ln_b;
   const float* dx0; int B, L;
   uint32_t drop_thresh; float drop_scale; uint64_t seed; const uint64_t* seed_dev; uint32_t site;
   TableRef dE; float* dP; float* dgamma; float* dbeta;
+  // deterministic mode (both set): token `row` adds its gradient row into acc64[acc_slot[row]] in 64-bit fixed
+  // point instead of dE (slot 0 = padding: skipped); tt_rows_scatter_add_i64 then rounds each sum once
+  unsigned long long* acc64; const int64_t* acc_slot;
   // the table row of token `row` with id `id`: the forward's stash when there is one, else the table itself
   __device__ __forceinline__ const float* src_row(size_t row, int64_t id) const {
     return stash ? stash + row * 256 : E.row(id);
@@ -653,7 +659,20 @@ __global__ void __launch_bounds__(kRowThreads, 2) embed_ln_bwd_kernel(const Embe
       g[i] = rstd * (g[i] - s1 - xhat[i] * s2);
       dp[i] += g[i];
     }
-    if (id != 0) {
+    if (p.acc64) {
+      // Integer addition is associative: whatever order the tokens of an id arrive in, the 64-bit sum is the
+      // same, so the table gradient is bit-identical from run to run (floating-point atomics are not).
+      const int64_t slot = p.acc_slot[row];
+      if (slot != 0) {
+        unsigned long long* dst = p.acc64 + static_cast<size_t>(slot) * W;
+#pragma unroll
+        for (int k = 0; k < NV; ++k)
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            atomicAdd(dst + (k * 32 + lane) * 4 + e,
+                      static_cast<unsigned long long>(__float2ll_rn(g[4 * k + e] * kGradFixScale)));
+      }
+    } else if (id != 0) {
       float* dst = p.dE.row(id);
 #pragma unroll
       for (int k = 0; k < NV; ++k)
@@ -852,7 +871,8 @@ static int embed_fwd_impl(const int64_t* ids, const TableRef& E, float* stash, c
 static int embed_bwd_impl(const int64_t* ids, const TableRef& E, const float* stash, const float* P, const float* ln_w,
                           const float* ln_b, const float* dx0, int B, int L, float drop_p, uint64_t seed,
                           const uint64_t* seed_dev, uint32_t site, const TableRef& dE, float* dP, float* dgamma,
-                          float* dbeta, cudaStream_t stream) {
+                          float* dbeta, cudaStream_t stream, unsigned long long* acc64 = nullptr,
+                          const int64_t* acc_slot = nullptr) {
   TT_REQUIRE(ids && P && ln_w && ln_b && dx0 && dP && dgamma && dbeta, "tt_embed_ln_bwd: null pointer");
   EmbedBwdParams p;
   p.ids = ids; p.E = E; p.stash = stash; p.P = P; p.ln_w = ln_w; p.ln_b = ln_b; p.dx0 = dx0; p.B = B; p.L = L;
@@ -860,6 +880,7 @@ static int embed_bwd_impl(const int64_t* ids, const TableRef& E, const float* st
   p.drop_scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
   p.seed = seed; p.seed_dev = seed_dev; p.site = site;
   p.dE = dE; p.dP = dP; p.dgamma = dgamma; p.dbeta = dbeta;
+  p.acc64 = acc64; p.acc_slot = acc_slot;
   int splits = (2 * num_sms()) / L;
   if (splits < 1) splits = 1;
   if (splits > (B + 7) / 8) splits = (B + 7) / 8;
@@ -884,6 +905,17 @@ extern "C" int tt_embed_ln_bwd(const int64_t* ids, const float* E, const float* 
   TT_REQUIRE(E && dE, "tt_embed_ln_bwd: null table");
   return embed_bwd_impl(ids, single_table(E), nullptr, P, ln_w, ln_b, dx0, B, L, drop_p, seed, seed_dev, site,
                         single_table(dE), dP, dgamma, dbeta, static_cast<cudaStream_t>(stream_));
+}
+
+extern "C" int tt_embed_ln_bwd_det(const int64_t* ids, const float* E, const float* P, const float* ln_w,
+                                   const float* ln_b, const float* dx0, int B, int L, float drop_p, uint64_t seed,
+                                   const uint64_t* seed_dev, uint32_t site, const int64_t* slot_of_token, int64_t* acc64,
+                                   float* dP, float* dgamma, float* dbeta, void* stream_) {
+  TT_REQUIRE(E && slot_of_token && acc64, "tt_embed_ln_bwd_det: null pointer");
+  TableRef none = single_table(nullptr);
+  return embed_bwd_impl(ids, single_table(E), nullptr, P, ln_w, ln_b, dx0, B, L, drop_p, seed, seed_dev, site, none, dP,
+                        dgamma, dbeta, static_cast<cudaStream_t>(stream_), reinterpret_cast<unsigned long long*>(acc64),
+                        slot_of_token);
 }
 
 extern "C" int tt_embed_ln_fwd_sharded(const int64_t* ids, const tt_symm_team* team, int64_t weight_offset,

@@ -114,6 +114,32 @@ __global__ void __launch_bounds__(256) rows_scatter_add_kernel(const TableRef gr
   __threadfence_system();      // remote reductions performed before the grid retires (owners' AdamW follows a barrier)
 }
 
+// Deterministic mode: one warp per distinct id; the 64-bit fixed-point sum of its tokens' gradient rows (2^-40
+// units, accumulated by tt_embed_ln_bwd_det) is rounded ONCE to fp32 and added to the table's gradient row by
+// the only warp that touches that row; the accumulator row is cleared for the next step.
+__global__ void __launch_bounds__(256) rows_scatter_add_i64_kernel(float* __restrict__ grad, const int64_t* __restrict__ uniq,
+                                                                   const int* __restrict__ n_uniq,
+                                                                   long long* __restrict__ acc) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int n = *n_uniq, lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  constexpr double kInv = 1.0 / 1099511627776.0;   // 2^-40
+  for (int s = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) + 1; s < n; s += warps) {
+    longlong2* src = reinterpret_cast<longlong2*>(acc + static_cast<size_t>(s) * 256);
+    float2* dst = reinterpret_cast<float2*>(grad + static_cast<size_t>(uniq[s]) * 256);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const longlong2 a = src[k * 32 + lane];
+      float2 d = dst[k * 32 + lane];
+      d.x += static_cast<float>(static_cast<double>(a.x) * kInv);
+      d.y += static_cast<float>(static_cast<double>(a.y) * kInv);
+      dst[k * 32 + lane] = d;
+      src[k * 32 + lane] = make_longlong2(0, 0);
+    }
+  }
+}
+
 }  // namespace tt
 
 using namespace tt;
@@ -172,6 +198,16 @@ extern "C" int tt_rows_scatter_add(const tt_symm_team* team, int64_t grad_offset
     t.world = 0;
   }
   TT_CHECK_CUDA(launch_k(rows_scatter_add_kernel, dim3(small_grid(max_rows * 32)), dim3(256), 0, stream, t, uniq, n_uniq, gacc));
+  TT_LAUNCH_CHECK();
+  return TT_OK;
+}
+
+extern "C" int tt_rows_scatter_add_i64(float* grad_local, const int64_t* uniq, const int32_t* n_uniq, int max_rows,
+                                       int64_t* acc64, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  TT_REQUIRE(grad_local && uniq && n_uniq && acc64 && max_rows > 0, "tt_rows_scatter_add_i64: bad arguments");
+  TT_CHECK_CUDA(launch_k(rows_scatter_add_i64_kernel, dim3(small_grid(max_rows * 32)), dim3(256), 0, stream, grad_local,
+                         uniq, n_uniq, reinterpret_cast<long long*>(acc64)));
   TT_LAUNCH_CHECK();
   return TT_OK;
 }

@@ -139,6 +139,12 @@ class TwoTowerEngine:
         #: crosses NVLink on its own, kept for A/B timing)
         self.dedup_ids = os.environ.get("TT_TABLE_DEDUP", "1") != "0"
         self._sparse: Dict[int, Dict[str, torch.Tensor]] = {}
+        #: deterministic table gradient (TT_DETERMINISTIC=1): the per-token gradient rows of duplicate ids are summed
+        #: in 64-bit fixed point per distinct id (tt_embed_ln_bwd_det), so the result does not depend on the order the
+        #: atomics land in. Local (replicated / single-GPU) table only; costs the id de-duplication (3 small kernels)
+        #: and 2 KB of accumulator per distinct id and step.
+        self.deterministic_table_grad = os.environ.get("TT_DETERMINISTIC", "0") == "1"
+        self._det: Dict[int, Dict[str, torch.Tensor]] = {}
 
     # ------------------------------------------------------------------ parameters
     def use_external_table(self, B: int, L: int) -> None:
@@ -320,6 +326,16 @@ class TwoTowerEngine:
                 "inverse": torch.zeros(T, device=dev, dtype=torch.int64),
                 "cache": torch.zeros(T + 1, D, device=dev), "gacc": torch.zeros(T + 1, D, device=dev)}
         return self._sparse[T]
+
+    def _det_ws(self, T: int) -> Dict[str, torch.Tensor]:
+        if T not in self._det:
+            dev, V, D = self.device, self.cfg.vocab_size, self.cfg.embedding_dim
+            self._det[T] = {
+                "flag": torch.zeros(V, device=dev, dtype=torch.int32), "slot": torch.zeros(V, device=dev, dtype=torch.int32),
+                "uniq": torch.zeros(T + 1, device=dev, dtype=torch.int64), "state": torch.zeros(2, device=dev, dtype=torch.int32),
+                "inverse": torch.zeros(T, device=dev, dtype=torch.int64),
+                "acc64": torch.zeros(T + 1, D, device=dev, dtype=torch.int64)}
+        return self._det[T]
 
     def release_workspaces(self) -> None:
         """Drop every activation workspace (they are rebuilt on demand; CUDA graphs that captured them must be
@@ -808,6 +824,14 @@ class TwoTowerEngine:
                                      p[ut + "layer_norm.bias"], dx, B, L, g[ut + "position_embedding.weight"],
                                      g[ut + "layer_norm.weight"], g[ut + "layer_norm.bias"], drop_p=dp, seed=seed,
                                      seed_dev=sdev, site=SITE_EMB)
+        elif self.deterministic_table_grad and self.table_rows is None:
+            dw = self._det_ws(T)
+            ops.ids_dedup(ids.view(-1), cfg.vocab_size, dw["flag"], dw["slot"], dw["uniq"], dw["state"], dw["inverse"])
+            ops.embed_ln_bwd_det(ids.view(-1), p[ut + "item_embedding.weight"], p[ut + "position_embedding.weight"],
+                                 p[ut + "layer_norm.weight"], p[ut + "layer_norm.bias"], dx, B, L, dw["inverse"],
+                                 dw["acc64"], g[ut + "position_embedding.weight"], g[ut + "layer_norm.weight"],
+                                 g[ut + "layer_norm.bias"], drop_p=dp, seed=seed, seed_dev=sdev, site=SITE_EMB)
+            ops.rows_scatter_add_i64(dw["uniq"], dw["state"], dw["acc64"], g[ut + "item_embedding.weight"])
         else:
             e_ids, e_table, e_grad = self._embed_operands(ids)
             ops.embed_ln_bwd(e_ids, e_table, p[ut + "position_embedding.weight"],

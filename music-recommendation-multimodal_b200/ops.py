@@ -147,6 +147,27 @@ def embed_ln_bwd(ids, E, P, ln_w, ln_b, dx0, B, L, dE, dP, dgamma, dbeta, drop_p
                                 dP.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(), _stream()), "tt_embed_ln_bwd")
 
 
+def embed_ln_bwd_det(ids, E, P, ln_w, ln_b, dx0, B, L, slot_of_token, acc64, dP, dgamma, dbeta, drop_p=0.0, seed=0,
+                     seed_dev=None, site=0):
+    """tt_embed_ln_bwd_det: the table gradient is accumulated per distinct id in 64-bit fixed point (order-independent,
+    bit-identical from run to run); rows_scatter_add_i64 rounds the sums into the table's gradient."""
+    _require_cuda(ids, E, P, dx0, slot_of_token, acc64, dP, dgamma, dbeta)
+    assert acc64.dtype == torch.int64 and acc64.is_contiguous() and acc64.shape[1] == 256
+    assert slot_of_token.dtype == torch.int64 and slot_of_token.numel() == B * L
+    check(lib().tt_embed_ln_bwd_det(ids.data_ptr(), E.data_ptr(), P.data_ptr(), ln_w.data_ptr(), ln_b.data_ptr(),
+                                    dx0.data_ptr(), B, L, drop_p, seed, _ptr(seed_dev), site, slot_of_token.data_ptr(),
+                                    acc64.data_ptr(), dP.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(), _stream()),
+          "tt_embed_ln_bwd_det")
+
+
+def rows_scatter_add_i64(uniq, state, acc64, grad_local) -> None:
+    _require_cuda(uniq, state, acc64, grad_local)
+    assert acc64.dtype == torch.int64 and acc64.is_contiguous() and acc64.shape[1] == 256
+    assert grad_local.dtype == torch.float32 and grad_local.is_contiguous()
+    check(lib().tt_rows_scatter_add_i64(grad_local.data_ptr(), uniq.data_ptr(), state.data_ptr() + 4, acc64.shape[0],
+                                        acc64.data_ptr(), _stream()), "tt_rows_scatter_add_i64")
+
+
 def embed_ln_fwd_sharded(ids, team, weight_offset, stash, P, ln_w, ln_b, next_w, next_b, B, L, x0, h,
                          drop_p=0.0, seed=0, seed_dev=None, site=0):
     """tt_embed_ln_fwd_sharded: the ID table is row-sharded over the ranks of a symmetric arena."""

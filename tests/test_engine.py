@@ -370,3 +370,26 @@ def test_prune_toggle_after_a_step_restores_the_reference_schedule():
     assert abs(l_full - l_pruned) <= 2e-3
     rel = ((eng.grad - g_pruned).norm() / g_pruned.norm()).item()
     assert rel <= 3e-2, rel
+
+
+def test_deterministic_table_gradient_mode_of_the_engine():
+    """engine.deterministic_table_grad: the ID-table gradient of a whole backward is bit-identical from run to run and
+    agrees with the default (floating-point atomics) mode to fp32 rounding; every other gradient is untouched."""
+    gold, cfg, sd, batch, eng, dbatch = _setup("train_l200.pt")
+    key = "user_tower.item_embedding.weight"
+
+    def grads(det):
+        eng.deterministic_table_grad = det
+        eng.grad.zero_()
+        eng.forward(dbatch, training=True)
+        eng.backward()
+        torch.cuda.synchronize()
+        return eng.grad.clone(), eng.g[key].clone()
+
+    flat_a, tab_a = grads(True)
+    flat_b, tab_b = grads(True)
+    assert torch.equal(tab_a, tab_b)
+    flat_c, tab_c = grads(False)
+    scale = float(tab_c.abs().max())
+    assert scale > 0 and float((tab_a - tab_c).abs().max()) <= 2e-6 * scale
+    assert float(tab_a[0].abs().max()) == 0.0           # padding_idx row
