@@ -68,8 +68,8 @@ __device__ __forceinline__ void store_row32_bf16(__nv_bfloat16* dst, const uint3
 
 // Forward. 256 threads: warp w -> TMEM lane quarter (w & 3), column half (w >> 2). Thread
 // (row, hf) owns query row `row` of the tile and the 64-column half `hf` of every 128-key tile.
-// Shared memory per CTA (nq = 2): Q 16 KB + K/V slots 32 KB (K first, then reused for V once the
-// S MMAs have retired) + P 32 KB = 80 KB -> two CTAs per SM (TMEM: 128 or 256 columns each).
+// Shared memory per CTA (nq = 2): Q 16 KB + K slots 32 KB (reused for V_1.. once the S MMAs have retired) + V_0
+// 16 KB + P 32 KB = 96 KB -> two CTAs per SM (TMEM: 128 or 256 columns each).
 __global__ void __launch_bounds__(256, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -89,14 +89,16 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
 
   uint8_t* sQ = smem;
   uint8_t* sKV = sQ + kTileBytes;
-  uint8_t* sP = sKV + static_cast<size_t>(p.nq) * kTileBytes;  // 2 chunks x 16 KB
+  uint8_t* sV0 = sKV + static_cast<size_t>(p.nq) * kTileBytes;   // V_0 has its own slot: loaded with Q / K, not after S
+  uint8_t* sP = sV0 + kTileBytes;                                 // 2 chunks x 16 KB
   uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * kTileBytes);
   uint64_t* bar_qk = bars + 0;
   uint64_t* bar_v = bars + 1;
   uint64_t* bar_s = bars + 2;
   uint64_t* bar_pv = bars + 3;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
-  float* s_red = reinterpret_cast<float*>(bars + 6);  // [2][128]
+  uint64_t* bar_v0 = bars + 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+  float* s_red = reinterpret_cast<float*>(bars + 7);  // [2][128]
 
   uint32_t tmem_cols = 128;
   while (tmem_cols < static_cast<uint32_t>(n_kv * kTile)) tmem_cols <<= 1;
@@ -107,6 +109,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
     mbar_init(bar_v, 1);
     mbar_init(bar_s, 1);
     mbar_init(bar_pv, 1);
+    mbar_init(bar_v0, 1);
     fence_barrier_init();
   }
   __syncwarp();
@@ -131,23 +134,27 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
     tma_load_2d(sQ, &tmQKV, bar_qk, h * kDh, q_row0);
     for (int j = 0; j < n_kv; ++j)
       tma_load_2d(sKV + static_cast<size_t>(j) * kTileBytes, &tmQKV, bar_qk, D + h * kDh, seq_row0 + j * kTile);
+    mbar_arrive_expect_tx(bar_v0, kTileBytes);
+    tma_load_2d(sV0, &tmQKV, bar_v0, 2 * D + h * kDh, seq_row0);
     mbar_wait(bar_qk, 0);
     tc_fence_after();
     const uint32_t idesc_s = umma_idesc_bf16(kTile, kTile, false, false);
-    const uint32_t q_base = smem_u32(sQ);
+    // descriptors once per tile, a k-step adds its byte offset >> 4 to the address field (addresses < 256 KB)
+    const uint64_t q_desc = umma_desc_kmajor(smem_u32(sQ));
     for (int j = 0; j < n_kv; ++j) {
-      const uint32_t k_base = smem_u32(sKV + static_cast<size_t>(j) * kTileBytes);
+      const uint64_t k_desc = umma_desc_kmajor(smem_u32(sKV + static_cast<size_t>(j) * kTileBytes));
 #pragma unroll
       for (int k = 0; k < kDh / 16; ++k)
-        umma_bf16(tmem_base + j * kTile, umma_desc_kmajor(q_base + k * 32), umma_desc_kmajor(k_base + k * 32),
-                  idesc_s, k > 0 ? 1u : 0u);
+        umma_bf16(tmem_base + j * kTile, q_desc + (k * 32 >> 4), k_desc + (k * 32 >> 4), idesc_s, k > 0 ? 1u : 0u);
     }
     umma_commit(bar_s);
-    // the K slots are free once the S MMAs retired: V tiles take their place
-    mbar_wait(bar_s, 0);
-    mbar_arrive_expect_tx(bar_v, n_kv * kTileBytes);
-    for (int j = 0; j < n_kv; ++j)
-      tma_load_2d(sKV + static_cast<size_t>(j) * kTileBytes, &tmQKV, bar_v, 2 * D + h * kDh, seq_row0 + j * kTile);
+    // the K slots are free once the S MMAs retired: V_1.. take their place (needed one P tile later than V_0)
+    if (n_kv > 1) {
+      mbar_wait(bar_s, 0);
+      mbar_arrive_expect_tx(bar_v, (n_kv - 1) * kTileBytes);
+      for (int j = 1; j < n_kv; ++j)
+        tma_load_2d(sKV + static_cast<size_t>(j - 1) * kTileBytes, &tmQKV, bar_v, 2 * D + h * kDh, seq_row0 + j * kTile);
+    }
   }
 
   // ---- pass A: row maximum over the causal prefix (each thread: its column half) ----------
@@ -156,13 +163,16 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
   tc_fence_after();
   const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
   const int q_pos = qt * kTile + row;  // position of this thread's query inside the sequence
+  const bool dead_rows = qt * kTile + q * 32 >= p.L;
   float m = -INFINITY;
   for (int j = 0; j < n_kv; ++j) {
     const bool diag = (j == qt);
 #pragma unroll
     for (int cc = 0; cc < 2; ++cc) {
       const int cg = 2 * hf + cc;       // 32-column chunk index inside the key tile
-      if (diag && cg > q) continue;     // fully above the diagonal for every row of this warp
+      // nothing to do (warp-uniform): above the diagonal for every row of this warp, or the warp's 32 query rows /
+      // the chunk's 32 keys lie wholly beyond the sequence (L = 200: a quarter of the second tile's warps)
+      if ((diag && cg > q) || dead_rows || j * kTile + cg * 32 >= p.L) continue;
       uint32_t r[32];
       tmem_ld32(lane_base + j * kTile + cg * 32, r);
       tmem_ld_wait();
@@ -195,7 +205,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
     for (int cc = 0; cc < 2; ++cc) {
       const int cg = 2 * hf + cc;
       const int u0 = cc * 4;
-      if (!(diag && cg > q)) {
+      if (!((diag && cg > q) || dead_rows || j * kTile + cg * 32 >= p.L)) {
         uint32_t r[32];
         tmem_ld32(lane_base + j * kTile + cg * 32, r);
         tmem_ld_wait();
@@ -251,15 +261,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
     __syncthreads();
     if (tid == 0) {
       tc_fence_after();
-      if (j == 0) mbar_wait(bar_v, 0);
-      const uint32_t p_base = smem_u32(sP);
-      const uint32_t v_base = smem_u32(sKV + static_cast<size_t>(j) * kTileBytes);
+      if (j == 0) mbar_wait(bar_v0, 0);
+      else if (j == 1) mbar_wait(bar_v, 0);
+      const uint64_t p_desc = umma_desc_kmajor(smem_u32(sP));
+      const uint64_t v_desc = umma_desc_mnmajor(smem_u32(j == 0 ? sV0 : sKV + static_cast<size_t>(j - 1) * kTileBytes), kTileBytes);
 #pragma unroll
       for (int k = 0; k < kTile / 16; ++k) {
         // A = P: chunk (k/4), 32 B per 16 kv columns; B = V rows (MN-major): 16 kv rows = 2048 B
-        const uint64_t adesc = umma_desc_kmajor(p_base + (k >> 2) * kTileBytes + (k & 3) * 32);
-        const uint64_t bdesc = umma_desc_mnmajor(v_base + k * 2048, kTileBytes);
-        umma_bf16(tmem_base, adesc, bdesc, idesc_pv, (j > 0 || k > 0) ? 1u : 0u);
+        umma_bf16(tmem_base, p_desc + (((k >> 2) * kTileBytes + (k & 3) * 32) >> 4), v_desc + (k * 2048 >> 4), idesc_pv,
+                  (j > 0 || k > 0) ? 1u : 0u);
       }
       umma_commit(bar_pv);
     }
@@ -289,6 +299,325 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
   tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem_base, tmem_cols);
+}
+
+// --------------------------------------------------------------------------------------------
+// Forward, persistent and pipelined (L <= 256). The kernel above is a chain of dependent latencies per CTA
+// (TMEM allocation -> TMA -> S MMAs -> row max -> P -> PV MMA -> epilogue) with two CTAs per SM to hide them.
+// Here a CTA per SM walks (sequence, head) items; per item the (query tile u, key tile j <= u) pairs are
+// (0,0), (1,0), (1,1), S tile t = pair index at TMEM columns 128 t, O_u at 384 + 64 u:
+//   * warps 0-15: thread (row, 32-column chunk). Per query tile: row max over its S tiles (combined across the
+//     four chunk groups through shared memory), then per pair P = dropout(exp2(.)) -> bf16 -> one of two
+//     32 KB P tiles. O_u is divided by the row sum and stored one pair AFTER its last PV MMA was issued, so
+//     that MMA is never waited for;
+//   * warp 16 (control flow by the whole warp, issue by one elected lane): TMA loads and MMAs. The S tile t
+//     of the NEXT item is issued as soon as every thread has read tile t of this one for the last time, so
+//     it is ready long before it is needed; Q / K of the next item are requested when this item's S MMAs
+//     have retired, V (two sets of slots) one item ahead.
+// --------------------------------------------------------------------------------------------
+static constexpr int kFwdComputeThreads = 512;
+static constexpr int kFwdThreads = kFwdComputeThreads + 128;
+
+__global__ void __launch_bounds__(kFwdThreads, 1)
+attn_fwd_persist_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t pad = (1024u - (smem_u32(smem_raw) & 1023u)) & 1023u;
+  uint8_t* smem = smem_raw + pad;
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int D = p.H * kDh;
+  const int nq = p.nq;                         // 1 or 2
+  const int np = nq == 2 ? 3 : 1;              // (query tile, key tile) pairs per item
+  const int n_items = p.B * p.H;
+
+  uint8_t* sQ = smem;                          // [2]
+  uint8_t* sK = sQ + 2 * kTileBytes;           // [2]
+  uint8_t* sV = sK + 2 * kTileBytes;           // [2 sets][2]
+  uint8_t* sP = sV + 4 * kTileBytes;           // [2 slots] x (2 chunks of 64 key columns)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 4 * kTileBytes);
+  uint64_t* bar_q = bars + 0;       // [2] Q_u landed (a phase per item)
+  uint64_t* bar_k = bars + 2;       // [2] K_j landed (a phase per item)
+  uint64_t* bar_v = bars + 4;       // [2 sets][2] V_j landed (a phase per two items)
+  uint64_t* bar_s = bars + 8;       // [3] S tile t ready (a phase per item)
+  uint64_t* bar_sfree = bars + 11;  // [3] every thread has read S tile t for the last time (a phase per item)
+  uint64_t* bar_pfull = bars + 14;  // [2] P slot staged (a phase per use)
+  uint64_t* bar_pv = bars + 16;     // [2] the PV MMAs reading P slot s retired (a phase per use)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
+  float* s_max = reinterpret_cast<float*>(bars + 20);   // [2 buffers][4 groups][128 rows]
+  float* s_sum = s_max + 2 * 4 * kTile;                 // [2 buffers][4 groups][128 rows]
+
+  if (tid == 0) {
+    tma_prefetch_desc(&tmQKV);
+    for (int i = 0; i < 8; ++i) mbar_init(bars + i, 1);
+    for (int i = 0; i < 3; ++i) mbar_init(bar_s + i, 1);
+    for (int i = 0; i < 3; ++i) mbar_init(bar_sfree + i, kFwdComputeThreads);
+    for (int i = 0; i < 2; ++i) mbar_init(bar_pfull + i, kFwdComputeThreads);
+    for (int i = 0; i < 2; ++i) mbar_init(bar_pv + i, 1);
+    fence_barrier_init();
+  }
+  __syncwarp();
+  if (warp == 16) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();
+  pdl_wait();
+  constexpr uint32_t T_O = 384;
+
+  if (warp >= 16) {
+    if (warp == 16) {
+      // ======================= issuer =========================================================
+      const uint32_t idesc_s = umma_idesc_bf16(kTile, kTile, false, false);
+      const uint32_t idesc_pv = umma_idesc_bf16(kTile, kDh, false, true);
+      auto load_qk = [&](int item) {          // Q_u -> slot u, K_j -> slot j
+        const int b = item / p.H, h = item % p.H;
+        if (elect_one()) {
+          for (int u = 0; u < nq; ++u) {
+            mbar_arrive_expect_tx(bar_q + u, kTileBytes);
+            tma_load_2d(sQ + static_cast<size_t>(u) * kTileBytes, &tmQKV, bar_q + u, h * kDh, b * p.L + u * kTile);
+            mbar_arrive_expect_tx(bar_k + u, kTileBytes);
+            tma_load_2d(sK + static_cast<size_t>(u) * kTileBytes, &tmQKV, bar_k + u, D + h * kDh, b * p.L + u * kTile);
+          }
+        }
+        __syncwarp();
+      };
+      auto load_v = [&](int item, int set) {
+        const int b = item / p.H, h = item % p.H;
+        if (elect_one()) {
+          for (int j = 0; j < nq; ++j) {
+            mbar_arrive_expect_tx(bar_v + set * 2 + j, kTileBytes);
+            tma_load_2d(sV + static_cast<size_t>(set * 2 + j) * kTileBytes, &tmQKV, bar_v + set * 2 + j, 2 * D + h * kDh,
+                        b * p.L + j * kTile);
+          }
+        }
+        __syncwarp();
+      };
+      auto issue_s = [&](int t) {              // S tile t = Q_u K_j^T, (u, j) = (0,0), (1,0), (1,1)
+        const int u = t == 0 ? 0 : 1, j = t == 2 ? 1 : 0;
+        const uint64_t dq = umma_desc_kmajor(smem_u32(sQ + static_cast<size_t>(u) * kTileBytes));
+        const uint64_t dk = umma_desc_kmajor(smem_u32(sK + static_cast<size_t>(j) * kTileBytes));
+        if (elect_one()) {
+#pragma unroll
+          for (int k = 0; k < kDh / 16; ++k)
+            umma_bf16(tmem_base + t * kTile, dq + (k * 32 >> 4), dk + (k * 32 >> 4), idesc_s, k > 0 ? 1u : 0u);
+          umma_commit(bar_s + t);
+        }
+        __syncwarp();
+      };
+      auto issue_pv = [&](int t, int slot, int set) {   // O_u (+)= P[slot] V_j
+        const int u = t == 0 ? 0 : 1, j = t == 2 ? 1 : 0;
+        const uint64_t dp = umma_desc_kmajor(smem_u32(sP + static_cast<size_t>(slot) * 2 * kTileBytes));
+        const uint64_t dv = umma_desc_mnmajor(smem_u32(sV + static_cast<size_t>(set * 2 + j) * kTileBytes), kTileBytes);
+        if (elect_one()) {
+#pragma unroll
+          for (int k = 0; k < kTile / 16; ++k)
+            umma_bf16(tmem_base + T_O + u * kDh, dp + (((k >> 2) * kTileBytes + (k & 3) * 32) >> 4), dv + (k * 2048 >> 4),
+                      idesc_pv, (j > 0 || k > 0) ? 1u : 0u);
+          umma_commit(bar_pv + slot);
+        }
+        __syncwarp();
+      };
+
+      int item = blockIdx.x;
+      load_qk(item);
+      load_v(item, 0);
+      for (int t = 0; t < np; ++t) {
+        const int u = t == 0 ? 0 : 1, j = t == 2 ? 1 : 0;
+        mbar_wait(bar_q + u, 0);
+        mbar_wait(bar_k + j, 0);
+        tc_fence_after();
+        issue_s(t);
+      }
+      uint32_t gk = 0;
+      for (uint32_t n = 0; item < n_items; ++n, item += gridDim.x) {
+        const int next = item + static_cast<int>(gridDim.x);
+        const bool has_next = next < n_items;
+        const uint32_t par = n & 1u, npar = (n + 1u) & 1u;
+        const int set = static_cast<int>(n & 1u);
+        mbar_wait(bar_s + (np - 1), par);        // this item's S MMAs retired: the Q / K slots are free
+        if (has_next) load_qk(next);
+        for (int t = 0; t < np; ++t, ++gk) {
+          const int u = t == 0 ? 0 : 1, j = t == 2 ? 1 : 0;
+          const int slot = static_cast<int>(gk & 1u);
+          mbar_wait(bar_pfull + slot, (gk >> 1) & 1u);
+          if (t == 0 || t == 2) mbar_wait(bar_v + set * 2 + j, (n >> 1) & 1u);   // first use of V_j in this item
+          tc_fence_after();
+          issue_pv(t, slot, set);
+          if (has_next) {
+            if (t == 0) {
+              // the other V set was last read by the previous item's last PV MMAs
+              if (gk >= 1) mbar_wait(bar_pv + ((gk - 1u) & 1u), ((gk - 1u) >> 1) & 1u);
+              load_v(next, set ^ 1);
+            }
+            mbar_wait(bar_sfree + t, par);        // S tile t fully consumed: the next item's tile takes its columns
+            mbar_wait(bar_q + u, npar);
+            mbar_wait(bar_k + j, npar);
+            tc_fence_after();
+            issue_s(t);
+          }
+        }
+      }
+    }
+  } else {
+    // ======================= compute warps ====================================================
+    const int q = warp & 3, cg = warp >> 2;     // TMEM lane quarter, 32-column chunk of a key tile
+    const int row = q * 32 + lane;
+    const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    const float c1 = p.scale * kLog2e;
+    const uint64_t seed = p.drop_seed + ((p.drop_thresh && p.drop_seed_dev) ? *p.drop_seed_dev : 0ull);
+    const uint32_t dkey = drop_key(seed, p.drop_site);
+    const int u0 = (cg & 1) * 4;
+    // state of the query tile whose O is still to be stored (one pair after its last PV MMA was issued)
+    int d_item = -1, d_u = 0, d_buf = 0;
+    float d_m = 0.f;
+    uint32_t d_gk = 0;
+    auto drain = [&]() {
+      // O_u / l -> ctx, log-sum-exp -> lse: thread (row, chunk group) takes 16 of the 64 columns
+      mbar_wait(bar_pv + (d_gk & 1u), (d_gk >> 1) & 1u);
+      __syncwarp();
+      tc_fence_after();
+      const float* ls = s_sum + d_buf * 4 * kTile;
+      const float l = (ls[row] + ls[kTile + row]) + (ls[2 * kTile + row] + ls[3 * kTile + row]);
+      const int q_pos = d_u * kTile + row;
+      uint32_t r[16];
+      tmem_ld16(lane_base + T_O + d_u * kDh + cg * 16, r);
+      tmem_ld_wait();
+      tc_fence_before();
+      if (q_pos < p.L) {
+        const int b = d_item / p.H, h = d_item % p.H;
+        const float inv_l = 1.f / l;
+        uint32_t w[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+          w[e] = pack_bf16(__uint_as_float(r[2 * e]) * inv_l, __uint_as_float(r[2 * e + 1]) * inv_l);
+        __nv_bfloat16* dst = p.ctx + static_cast<size_t>(b * p.L + q_pos) * D + h * kDh + cg * 16;
+        asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst), "r"(w[0]), "r"(w[1]),
+                     "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7])
+                     : "memory");
+        if (cg == 0 && p.lse) p.lse[static_cast<size_t>(d_item) * p.L + q_pos] = d_m * p.scale + __logf(l);
+      }
+      d_item = -1;
+    };
+
+    uint32_t gk = 0, gu = 0;     // global pair / query-tile counters of this CTA
+    int item = blockIdx.x;
+    for (uint32_t n = 0; item < n_items; ++n, item += gridDim.x) {
+      for (int u = 0; u < nq; ++u, ++gu) {
+        const int q_pos = u * kTile + row;
+        const bool dead_rows = u * kTile + q * 32 >= p.L;
+        const int buf = static_cast<int>(gu & 1u);
+        // ---- row maximum over the causal prefix: S tiles (u, 0..u) --------------------------------
+        float m = -INFINITY;
+        for (int j = 0; j <= u; ++j) {
+          const int t = u + j;
+          const bool diag = (j == u);
+          mbar_wait(bar_s + t, n & 1u);
+          __syncwarp();
+          tc_fence_after();
+          if ((diag && cg > q) || dead_rows || j * kTile + cg * 32 >= p.L) continue;
+          uint32_t r[32];
+          tmem_ld32(lane_base + t * kTile + cg * 32, r);
+          tmem_ld_wait();
+          const int kv0 = j * kTile + cg * 32;
+#pragma unroll
+          for (int e = 0; e < 32; ++e)
+            if (!diag || kv0 + e <= q_pos) m = fmaxf(m, __uint_as_float(r[e]));
+        }
+        s_max[(buf * 4 + cg) * kTile + row] = m;
+        asm volatile("bar.sync 1, %0;" ::"n"(kFwdComputeThreads) : "memory");
+        {
+          const float* ms = s_max + buf * 4 * kTile;
+          m = fmaxf(fmaxf(ms[row], ms[kTile + row]), fmaxf(ms[2 * kTile + row], ms[3 * kTile + row]));
+        }
+        const float mc = m * c1;
+        // ---- per pair: P -> shared memory, then the PV MMAs are the issuer's business ---------------
+        float l = 0.f;
+        for (int j = 0; j <= u; ++j, ++gk) {
+          const int t = u + j;
+          const bool diag = (j == u);
+          const bool active = !((diag && cg > q) || dead_rows || j * kTile + cg * 32 >= p.L);
+          const int slot = static_cast<int>(gk & 1u);
+          uint8_t* chunk = sP + static_cast<size_t>(slot) * 2 * kTileBytes + static_cast<size_t>(cg >> 1) * kTileBytes;
+          uint4 v[4];
+#pragma unroll
+          for (int x = 0; x < 4; ++x) v[x] = make_uint4(0, 0, 0, 0);
+          if (active) {
+            uint32_t r[32];
+            tmem_ld32(lane_base + t * kTile + cg * 32, r);
+            tmem_ld_wait();
+            tc_fence_before();
+            mbar_arrive(bar_sfree + t);
+            const int kv0 = j * kTile + cg * 32;
+            const uint32_t didx0 = (static_cast<uint32_t>(item) * p.L + q_pos) * p.L + kv0;
+            float pv[32];
+#pragma unroll
+            for (int e = 0; e < 32; ++e) {
+              float x = fast_exp2(__uint_as_float(r[e]) * c1 - mc);
+              if (diag && kv0 + e > q_pos) x = 0.f;
+              l += x;
+              pv[e] = x;
+            }
+            if (p.drop_thresh) {
+              if ((didx0 & 3u) == 0u) {          // L % 4 == 0: four keys per hash word
+#pragma unroll
+                for (int e = 0; e < 32; e += 4) {
+                  bool k[4];
+                  drop_keep_quad(dkey, didx0 + e, p.drop_thresh, k);
+#pragma unroll
+                  for (int x = 0; x < 4; ++x) pv[e + x] = k[x] ? pv[e + x] * p.drop_scale : 0.f;
+                }
+              } else if ((didx0 & 1u) == 0u) {
+#pragma unroll
+                for (int e = 0; e < 32; e += 2) {
+                  bool k0, k1;
+                  drop_keep_pair(dkey, didx0 + e, p.drop_thresh, k0, k1);
+                  pv[e] = k0 ? pv[e] * p.drop_scale : 0.f;
+                  pv[e + 1] = k1 ? pv[e + 1] * p.drop_scale : 0.f;
+                }
+              } else {
+#pragma unroll
+                for (int e = 0; e < 32; ++e)
+                  pv[e] = drop_keep_k(dkey, didx0 + e, p.drop_thresh) ? pv[e] * p.drop_scale : 0.f;
+              }
+            }
+#pragma unroll
+            for (int x = 0; x < 4; ++x) {
+              v[x].x = pack_bf16(pv[x * 8 + 0], pv[x * 8 + 1]);
+              v[x].y = pack_bf16(pv[x * 8 + 2], pv[x * 8 + 3]);
+              v[x].z = pack_bf16(pv[x * 8 + 4], pv[x * 8 + 5]);
+              v[x].w = pack_bf16(pv[x * 8 + 6], pv[x * 8 + 7]);
+            }
+          } else {
+            tc_fence_before();
+            mbar_arrive(bar_sfree + t);
+          }
+          // the PV MMAs that read this P slot two pairs ago have retired
+          if (gk >= 2) mbar_wait(bar_pv + slot, ((gk >> 1) - 1u) & 1u);
+#pragma unroll
+          for (int x = 0; x < 4; ++x) st_swizzled_unit(chunk, row, u0 + x, v[x]);
+          fence_proxy_async_smem();
+          mbar_arrive(bar_pfull + slot);
+          if (j == u) s_sum[(buf * 4 + cg) * kTile + row] = l;
+          // the query tile whose last PV MMAs were issued one pair ago: its O is complete by now
+          if (d_item >= 0) drain();
+          if (j == u) { d_item = item; d_u = u; d_buf = buf; d_m = m; d_gk = gk; }
+        }
+      }
+    }
+    if (d_item >= 0) {
+      asm volatile("bar.sync 1, %0;" ::"n"(kFwdComputeThreads) : "memory");   // the last tile's row sums are all written
+      drain();
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 16) tmem_dealloc(tmem_base, 512);
 }
 
 // --------------------------------------------------------------------------------------------
@@ -1170,13 +1499,28 @@ extern "C" int tt_attn_causal_fwd(const void* qkv, void* ctx, float* lse, int B,
   CUtensorMap tm;
   int rc = make_rows_map(&tm, qkv, B * L, 3 * D);
   if (rc) return rc;
-  const size_t smem = 1024 + static_cast<size_t>(1 + p.nq + 2) * kTileBytes + 64 + 2 * 128 * sizeof(float);
+  const size_t smem = 1024 + static_cast<size_t>(1 + p.nq + 1 + 2) * kTileBytes + 64 + 2 * 128 * sizeof(float);
   static bool configured = false;
   if (!configured) {
     TT_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
     configured = true;
   }
   TT_REQUIRE(smem <= 232448, "tt_attn_causal_fwd: shared memory %zu too large", smem);
+  // TT_ATTN_FWD=legacy keeps the one-CTA-per-(sequence, head, query tile) kernel for L <= 256
+  const char* mode = getenv("TT_ATTN_FWD");
+  const bool legacy = mode && mode[0] == 'l';
+  if (p.nq <= 2 && !legacy) {
+    const size_t psmem = 1024 + 12 * static_cast<size_t>(kTileBytes) + 256 + 4 * 4 * kTile * sizeof(float);
+    static bool pconfigured = false;
+    if (!pconfigured) {
+      TT_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+      pconfigured = true;
+    }
+    const int grid = B * H < num_sms() ? B * H : num_sms();
+    TT_CHECK_CUDA(launch_k(attn_fwd_persist_kernel, dim3(grid), dim3(kFwdThreads), psmem, stream, tm, p));
+    TT_LAUNCH_CHECK();
+    return TT_OK;
+  }
   TT_CHECK_CUDA(launch_k(attn_fwd_kernel, dim3(B * H * p.nq), dim3(256), smem, stream, tm, p));
   TT_LAUNCH_CHECK();
   return TT_OK;

@@ -98,16 +98,18 @@ __device__ __forceinline__ float quad_sum(float v) {
   v += __shfl_xor_sync(0xffffffffu, v, 2);
   return v;
 }
+// 16 scaled values -> 16 bf16 = one 32-byte store: a whole sector per lane (two 16-byte stores left every sector
+// half-written until the second instruction; the four lanes of a key row cover its 128 bytes)
+__device__ __forceinline__ void st_global_v8(void* p, const uint32_t (&w)[8]) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(w[0]), "r"(w[1]), "r"(w[2]),
+               "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7])
+               : "memory");
+}
 __device__ __forceinline__ void store16_scaled(__nv_bfloat16* p, const float (&v)[16], float s) {
+  uint32_t w[8];
 #pragma unroll
-  for (int u = 0; u < 2; ++u) {
-    uint4 x;
-    x.x = pack_bf16(v[u * 8 + 0] * s, v[u * 8 + 1] * s);
-    x.y = pack_bf16(v[u * 8 + 2] * s, v[u * 8 + 3] * s);
-    x.z = pack_bf16(v[u * 8 + 4] * s, v[u * 8 + 5] * s);
-    x.w = pack_bf16(v[u * 8 + 6] * s, v[u * 8 + 7] * s);
-    reinterpret_cast<uint4*>(p)[u] = x;
-  }
+  for (int e = 0; e < 8; ++e) w[e] = pack_bf16(v[2 * e] * s, v[2 * e + 1] * s);
+  st_global_v8(p, w);
 }
 
 // One block (4 warps) per (b, h). The 32 key slots of an iteration are spread over the block:
@@ -260,11 +262,9 @@ __global__ void __launch_bounds__(128) attn_lastq_bwd_kernel(const LastQParams p
       store16_scaled(dk, q, ds);    // dK_j = dS_j * q
       store16_scaled(dv, g, pd);    // dV_j = Pd_j * dO
     } else if (inrange) {
-#pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        reinterpret_cast<uint4*>(dk)[u] = make_uint4(0, 0, 0, 0);
-        reinterpret_cast<uint4*>(dv)[u] = make_uint4(0, 0, 0, 0);
-      }
+      const uint32_t z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      st_global_v8(dk, z);
+      st_global_v8(dv, z);
     }
   }
   __syncthreads();

@@ -114,3 +114,29 @@ def test_attn_bwd_persistent_equals_legacy(B, L, H, drop, monkeypatch):
         out[mode] = d
     assert torch.isfinite(out["persistent"].float()).all()
     assert torch.equal(out["legacy"], out["persistent"])
+
+
+@pytest.mark.parametrize("B,L,H,drop", [(3, 200, 4, 0.0), (160, 200, 4, 0.1), (150, 50, 4, 0.1), (40, 256, 2, 0.2),
+                                        (37, 129, 4, 0.1), (2, 128, 4, 0.0)])
+def test_attn_fwd_persistent_equals_legacy(B, L, H, drop, monkeypatch):
+    """The persistent forward (L <= 256) forms the same P tiles and issues the same MMAs as the per-tile kernel; only the
+    row sums are added in another order (four column groups instead of two halves), so ctx may differ by one bf16
+    rounding and the log-sum-exp by fp32 rounding. With more items than SMs and with fewer; with and without dropout."""
+    from mrm_b200 import ops
+    g = torch.Generator().manual_seed(11 * L + B)
+    qkv = (torch.randn(B * L, 3 * H * 64, generator=g) * 1.2).cuda().bfloat16()
+    out = {}
+    for mode in ("legacy", "persistent"):
+        monkeypatch.setenv("TT_ATTN_FWD", mode)
+        ctx = torch.full((B * L, H * 64), float("nan"), device="cuda", dtype=torch.bfloat16)
+        lse = torch.full((B, H, L), float("nan"), device="cuda")
+        for _ in range(2):
+            ops.attn_fwd(qkv, ctx, lse, B, L, H, drop_p=drop, drop_seed=11, drop_site=2)
+        torch.cuda.synchronize()
+        out[mode] = (ctx, lse)
+    a, b = out["legacy"], out["persistent"]
+    assert torch.isfinite(b[0].float()).all() and torch.isfinite(b[1]).all()
+    assert float((a[1] - b[1]).abs().max()) <= 2e-5
+    diff = (a[0].float() - b[0].float()).abs()
+    assert float(diff.max()) <= 2.0 ** -7 * max(1.0, float(a[0].float().abs().max()))
+    assert float((diff > 0).float().mean()) < 0.02        # almost everywhere the very same bits
