@@ -344,8 +344,7 @@ attn_fwd_persist_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnPar
   uint64_t* bar_pfull = bars + 14;  // [2] P slot staged (a phase per use)
   uint64_t* bar_pv = bars + 16;     // [2] the PV MMAs reading P slot s retired (a phase per use)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
-  float* s_max = reinterpret_cast<float*>(bars + 20);   // [2 buffers][4 groups][128 rows]
-  float* s_sum = s_max + 2 * 4 * kTile;                 // [2 buffers][4 groups][128 rows]
+  float* s_sum = reinterpret_cast<float*>(bars + 20);   // [3 buffers][4 chunk groups][128 rows]
 
   if (tid == 0) {
     tma_prefetch_desc(&tmQKV);
@@ -510,8 +509,10 @@ attn_fwd_persist_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnPar
       for (int u = 0; u < nq; ++u, ++gu) {
         const int q_pos = u * kTile + row;
         const bool dead_rows = u * kTile + q * 32 >= p.L;
-        const int buf = static_cast<int>(gu & 1u);
-        // ---- row maximum over the causal prefix: S tiles (u, 0..u) --------------------------------
+        const int buf = static_cast<int>(gu % 3u);
+        // ---- row maximum over the causal prefix: S tiles (u, 0..u). Every thread scans its WHOLE row (the four
+        // threads of a row repeat each other's 128 comparisons per tile): combining four partial maxima needed a
+        // 512-thread barrier per query tile, and the warps' skew made that wait a fifth of the kernel.
         float m = -INFINITY;
         for (int j = 0; j <= u; ++j) {
           const int t = u + j;
@@ -519,20 +520,22 @@ attn_fwd_persist_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnPar
           mbar_wait(bar_s + t, n & 1u);
           __syncwarp();
           tc_fence_after();
-          if ((diag && cg > q) || dead_rows || j * kTile + cg * 32 >= p.L) continue;
-          uint32_t r[32];
-          tmem_ld32(lane_base + t * kTile + cg * 32, r);
-          tmem_ld_wait();
-          const int kv0 = j * kTile + cg * 32;
+          if (dead_rows) continue;
+          for (int c = 0; c < 4; ++c) {
+            if ((diag && c > q) || j * kTile + c * 32 >= p.L) break;     // nothing further right is visible to these rows
+            uint32_t r[32];
+            tmem_ld32(lane_base + t * kTile + c * 32, r);
+            tmem_ld_wait();
+            if (diag && c == q) {
+              const int kv0 = j * kTile + c * 32;
 #pragma unroll
-          for (int e = 0; e < 32; ++e)
-            if (!diag || kv0 + e <= q_pos) m = fmaxf(m, __uint_as_float(r[e]));
-        }
-        s_max[(buf * 4 + cg) * kTile + row] = m;
-        asm volatile("bar.sync 1, %0;" ::"n"(kFwdComputeThreads) : "memory");
-        {
-          const float* ms = s_max + buf * 4 * kTile;
-          m = fmaxf(fmaxf(ms[row], ms[kTile + row]), fmaxf(ms[2 * kTile + row], ms[3 * kTile + row]));
+              for (int e = 0; e < 32; ++e)
+                if (kv0 + e <= q_pos) m = fmaxf(m, __uint_as_float(r[e]));
+            } else {
+#pragma unroll
+              for (int e = 0; e < 32; ++e) m = fmaxf(m, __uint_as_float(r[e]));
+            }
+          }
         }
         const float mc = m * c1;
         // ---- per pair: P -> shared memory, then the PV MMAs are the issuer's business ---------------
@@ -600,11 +603,15 @@ attn_fwd_persist_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnPar
           if (gk >= 2) mbar_wait(bar_pv + slot, ((gk >> 1) - 1u) & 1u);
 #pragma unroll
           for (int x = 0; x < 4; ++x) st_swizzled_unit(chunk, row, u0 + x, v[x]);
-          fence_proxy_async_smem();
-          mbar_arrive(bar_pfull + slot);
+          // Row-sum partials of the four chunk groups meet through shared memory without a barrier of their own:
+          // written before this pair's arrive, read (drain) after the wait for the PV MMAs that the issuer started
+          // once all 512 arrives were in. Three buffers: a thread can only be staging a pair if every thread has
+          // arrived for the pair two before, i.e. has finished the drain that preceded that arrive.
           if (j == u) s_sum[(buf * 4 + cg) * kTile + row] = l;
           // the query tile whose last PV MMAs were issued one pair ago: its O is complete by now
           if (d_item >= 0) drain();
+          fence_proxy_async_smem();
+          mbar_arrive(bar_pfull + slot);
           if (j == u) { d_item = item; d_u = u; d_buf = buf; d_m = m; d_gk = gk; }
         }
       }
@@ -1510,7 +1517,7 @@ extern "C" int tt_attn_causal_fwd(const void* qkv, void* ctx, float* lse, int B,
   const char* mode = getenv("TT_ATTN_FWD");
   const bool legacy = mode && mode[0] == 'l';
   if (p.nq <= 2 && !legacy) {
-    const size_t psmem = 1024 + 12 * static_cast<size_t>(kTileBytes) + 256 + 4 * 4 * kTile * sizeof(float);
+    const size_t psmem = 1024 + 12 * static_cast<size_t>(kTileBytes) + 256 + 3 * 4 * kTile * sizeof(float);
     static bool pconfigured = false;
     if (!pconfigured) {
       TT_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
