@@ -19,7 +19,7 @@ python tools/ncu_summary.py $out/topk_full.ncu-rep > $out/ncu_full_topk.summary.
 ncu -i $out/gemm_full.ncu-rep --page raw --csv 2>/dev/null | cut -d, -f1-60 | head -60 > $out/ncu_full_gemm.raw.head.csv
 rm -f $out/gemm_full.ncu-rep $out/topk_full.ncu-rep
 # attention (persistent forward / backward): full capture with source, summarised on the box
-timeout 100 python tools/time_attention.py > $out/attention_times.txt 2>&1 && timeout 300 ncu --set full --clock-control none --import-source on -k regex:'attn_(fwd|bwd)_persist' -s 4 -c 2 -o $out/attn_full -f python tools/time_attention.py > $out/ncu_fa.log 2>&1; echo "full-attn rc=$?" | tee -a $out/status.txt
+timeout 100 python tools/time_attention.py > $out/attention_times.txt 2>&1 && timeout 300 ncu --set full --clock-control none --import-source on -k regex:'attn_(fwd|bwd)_persist' -s 6 -c 8 -o $out/attn_full -f python tools/time_attention.py > $out/ncu_fa.log 2>&1; echo "full-attn rc=$?" | tee -a $out/status.txt
 python tools/ncu_summary.py $out/attn_full.ncu-rep > $out/ncu_full_attn.summary.txt 2>&1
 python tools/ncu_stalls.py $out/attn_full.ncu-rep attn_bwd_persist > $out/ncu_stalls_attn_bwd.txt 2>&1
 python tools/ncu_stalls.py $out/attn_full.ncu-rep attn_fwd_persist > $out/ncu_stalls_attn_fwd.txt 2>&1
