@@ -140,26 +140,6 @@ int tt_embed_ln_bwd_det(const int64_t* ids, const float* E, const float* P, cons
 int tt_rows_scatter_add_i64(float* grad_local, const int64_t* uniq, const int32_t* n_uniq, int max_rows,
                             int64_t* acc64, void* stream);
 
-/* Last encoder layer without K / V (4 heads of 64, d = 256). Only out[b, len_b - 1] of the last layer is read
- * (src/models/user_tower.py:122-132), so its attention has one query per (sequence, head); with
- * k_j = Wk h1_j + bk, v_j = Wv h1_j + bv (in_proj of nn.MultiheadAttention, src/models/user_tower.py:37-45, h1 = norm1
- * output) the scores are (scale Wk_h^T q_h) . h1_j + const and the context is Wv_h (sum_j pd_j h1_j) + bv_h sum_j pd_j:
- * no [T, 512] K|V tensor, no dgrad / wgrad GEMM over all T tokens for it. One block per sequence.
- * forward: gathers row len-1 (hq bf16, xq_in fp32 residual), q = Wq hq + bq, a_h = scale Wk_h^T q_h, softmax over
- * j <= len-1 with dropout (same counter hash as tt_attn_lastq_fwd), r_h = sum_j pd_j h1_j, ctx. Kept for backward:
- * q (bf16), a, r (fp32 + bf16), lse, sumpd [B, 4].
- * backward: dctx -> dh [B*L, 256] fp32 = gradient w.r.t. h1 for EVERY position (zeros beyond len; includes
- * Wq^T dq at row len-1), dq (bf16 [B,256]: operand of the Wq weight gradient), da = scale * sum_j ds_j h1_j (bf16
- * [B, 4*256]: dWk_h = q_h^T da_h), d(bv) accumulated; dWv_h = dctx_h^T r_h and the K bias gradient is exactly 0. */
-int tt_lastrow_attn_fwd(const void* h1_bf16, const float* x_in, const int32_t* last_idx, const void* Wqkv_bf16,
-                        const float* bqkv, int B, int L, int H, float drop_p, uint64_t seed, const uint64_t* seed_dev,
-                        uint32_t site, void* hq_bf16, float* xq_in, void* q_bf16, float* a_f32, float* r_f32,
-                        void* r_bf16, float* lse, float* sumpd, void* ctx_bf16, void* stream);
-int tt_lastrow_attn_bwd(const void* h1_bf16, const int32_t* last_idx, const void* Wqkv_bf16, const float* bqkv,
-                        const void* dctx_bf16, const float* a_f32, const float* lse, const float* sumpd, int B, int L,
-                        int H, float drop_p, uint64_t seed, const uint64_t* seed_dev, uint32_t site, float* dh,
-                        void* dq_bf16, void* da_bf16, float* dbv, void* stream);
-
 /* Row chain on fp32 rows of width 256 or 512:
  *   forward : [LayerNorm] -> [ReLU] -> [dropout] -> [L2 normalise] -> out_f32 / out_bf16
  *   backward: recomputes the forward from x, then dout -> ... -> (+resid) -> dx_f32 / dx_bf16,

@@ -183,10 +183,6 @@ _SIGNATURES = {
     "tt_embed_ln_bwd_det": [c_void_p] * 6 + [c_int32, c_int32, c_float, c_uint64, c_void_p, c_uint32,
                                              c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
     "tt_rows_scatter_add_i64": [c_void_p, c_void_p, c_void_p, c_int32, c_void_p, c_void_p],
-    "tt_lastrow_attn_fwd": [c_void_p] * 5 + [c_int32, c_int32, c_int32, c_float, c_uint64, c_void_p, c_uint32] +
-                           [c_void_p] * 10,
-    "tt_lastrow_attn_bwd": [c_void_p] * 8 + [c_int32, c_int32, c_int32, c_float, c_uint64, c_void_p, c_uint32] +
-                           [c_void_p] * 5,
     "tt_chain_fwd": [ctypes.POINTER(ChainArgs), c_void_p],
     "tt_chain_bwd": [ctypes.POINTER(ChainArgs), c_void_p],
     "tt_gather_cat_fwd": [c_void_p] * 6 + [c_int32, c_int32, c_void_p, c_void_p],

@@ -387,29 +387,6 @@ def attn_lastq_fwd(q, qkv, last_idx, ctx, lse, B, L, H, drop_p=0.0, seed=0, seed
                                   drop_p, seed, _ptr(seed_dev), site, _stream()), "tt_attn_lastq_fwd")
 
 
-def lastrow_attn_fwd(h1, x_in, last_idx, Wqkv, bqkv, B, L, H, hq, xq_in, q_bf, a_f32, r_f32, r_bf, lse, sumpd, ctx,
-                     drop_p=0.0, seed=0, seed_dev=None, site=0) -> None:
-    """tt_lastrow_attn_fwd: the last layer's single-query attention without materialising K / V."""
-    _require_cuda(h1, x_in, last_idx, Wqkv, bqkv, hq, xq_in, q_bf, a_f32, r_f32, r_bf, lse, sumpd, ctx)
-    assert h1.dtype == torch.bfloat16 and h1.is_contiguous() and Wqkv.dtype == torch.bfloat16 and Wqkv.is_contiguous()
-    assert Wqkv.shape == (768, 256) and bqkv.numel() == 768 and x_in.dtype == torch.float32 and x_in.is_contiguous()
-    check(lib().tt_lastrow_attn_fwd(h1.data_ptr(), x_in.data_ptr(), last_idx.data_ptr(), Wqkv.data_ptr(), bqkv.data_ptr(),
-                                    B, L, H, drop_p, seed, _ptr(seed_dev), site, hq.data_ptr(), xq_in.data_ptr(),
-                                    q_bf.data_ptr(), a_f32.data_ptr(), r_f32.data_ptr(), r_bf.data_ptr(), lse.data_ptr(),
-                                    sumpd.data_ptr(), ctx.data_ptr(), _stream()), "tt_lastrow_attn_fwd")
-
-
-def lastrow_attn_bwd(h1, last_idx, Wqkv, bqkv, dctx, a_f32, lse, sumpd, B, L, H, dh, dq_bf, da_bf, dbv,
-                     drop_p=0.0, seed=0, seed_dev=None, site=0) -> None:
-    """tt_lastrow_attn_bwd: dh (gradient w.r.t. the layer's norm1 output, every position), dq, da, d(bias of V)."""
-    _require_cuda(h1, last_idx, Wqkv, bqkv, dctx, a_f32, lse, sumpd, dh, dq_bf, da_bf, dbv)
-    assert dh.dtype == torch.float32 and dh.is_contiguous() and dh.shape == (B * L, 256)
-    check(lib().tt_lastrow_attn_bwd(h1.data_ptr(), last_idx.data_ptr(), Wqkv.data_ptr(), bqkv.data_ptr(), dctx.data_ptr(),
-                                    a_f32.data_ptr(), lse.data_ptr(), sumpd.data_ptr(), B, L, H, drop_p, seed,
-                                    _ptr(seed_dev), site, dh.data_ptr(), dq_bf.data_ptr(), da_bf.data_ptr(), _ptr(dbv),
-                                    _stream()), "tt_lastrow_attn_bwd")
-
-
 def attn_lastq_bwd(q, qkv, last_idx, ctx, dctx, lse, dq, dqkv, B, L, H, drop_p=0.0, seed=0, seed_dev=None, site=0) -> None:
     _require_cuda(q, qkv, last_idx, ctx, dctx, lse, dq, dqkv)
     check(lib().tt_attn_lastq_bwd(q.data_ptr(), qkv.data_ptr(), last_idx.data_ptr(), ctx.data_ptr(), dctx.data_ptr(),
