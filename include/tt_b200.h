@@ -79,6 +79,10 @@ typedef struct tt_gemm_args {
   int32_t accumulate;      /* 1: out_f32 += (red.add), required when k_splits > 1 */
   int32_t k_splits;        /* 0 => choose automatically (only >1 when accumulate) */
   int32_t block_n;         /* 0 => choose automatically (64/128/256) */
+  float* a_colsum;         /* optional fp32 [K]: a_colsum[k] += sum_m A[m,k] (K-major A, no split-K, K <= 2048): the bias
+                            * gradient sum(dY, dim=0) that autograd's Linear backward (src/models/user_tower.py:37-45
+                            * layers, src/train.py:62) takes next to dX = dY W, here from the dY tiles the dgrad GEMM
+                            * stages anyway instead of a second pass over dY */
 } tt_gemm_args;
 
 int tt_gemm_bf16(const tt_gemm_args* args, void* stream);

@@ -46,6 +46,7 @@ class GemmArgs(ctypes.Structure):
         ("accumulate", c_int32),
         ("k_splits", c_int32),
         ("block_n", c_int32),
+        ("a_colsum", c_void_p),
     ]
 
 

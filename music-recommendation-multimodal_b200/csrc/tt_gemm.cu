@@ -6,6 +6,8 @@
 //   warp 0      : TMA producer (one elected lane) — A/B tiles, 128B swizzle, N-stage ring
 //   warp 1      : MMA issuer (one elected lane)  — tcgen05.mma M=128, N=block_n, K=16
 //   warp 2      : TMEM allocator (2 accumulator buffers of block_n columns)
+//   warps 2, 3  : optional column sums of the A operand (the bias gradient that belongs to a dgrad GEMM's
+//                 dY operand), read from the staged A tiles while the MMAs run
 //   warps 4..19 : epilogue — tcgen05.ld (warp % 4 = TMEM lane quarter, the four warps of a quarter
 //                 take every 4th 32-column chunk), fused bias / ReLU / dropout / gate / residual;
 //                 all global traffic goes through a swizzled per-warp smem tile so loads/stores
@@ -43,6 +45,7 @@ struct GemmParams {
   int pair;         // 1 = CTA pairs (cluster of 2, tcgen05 cta_group::2): a pair computes a 256-row x block_n tile;
                     // each CTA stages its 128 rows of A and HALF of the B tile, the leader issues M=256 MMAs
   int stg_bytes;    // per-epilogue-warp staging bytes (tile + 256 B bias slice)
+  float* a_colsum;  // optional [K]: += column sums of the (K-major) A operand, taken from the staged tiles by warps 2 and 3
   int debug;  // profiling knob: 1 = epilogue drains TMEM only (no math, no global IO); 2 = everything but the global stores
 };
 
@@ -250,7 +253,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* empty_bar = full_bar + stages;
   uint64_t* tfull_bar = empty_bar + stages;
   uint64_t* tempty_bar = tfull_bar + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* cs_bar = tempty_bar + 2;            // pair mode + column sums: "MMAs of this stage retired" in both CTAs
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(cs_bar + stages);
+  float* csum = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 15) & ~static_cast<uintptr_t>(15));   // [2 warps][kblocks * 64] when p.a_colsum
+  const bool colsum = p.a_colsum != nullptr;
 
   const uint32_t tmem_cols = static_cast<uint32_t>(2 * block_n);  // 128 / 256 / 512
 
@@ -261,7 +267,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == 1 && elect_one()) {
     for (int s = 0; s < stages; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], colsum ? 3 : 1);   // MMA commit (+ the two column-sum warps)
+      mbar_init(&cs_bar[s], 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull_bar[a], 1);
@@ -354,8 +361,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             if constexpr (pair) umma_bf16_pair(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
             else      umma_bf16(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
-          if constexpr (pair) umma_commit_pair(&empty_bar[stage]);   // both CTAs' smem slots reusable once these MMAs retire
-          else      umma_commit(&empty_bar[stage]);
+          if constexpr (pair) {
+            umma_commit_pair(&empty_bar[stage]);   // both CTAs' smem slots reusable once these MMAs retire
+            // the follower's full barrier is never signalled (all TMA bytes land on the leader's): its column-sum
+            // warps take "the MMAs that read this stage have retired" as "the tile is there"
+            if (colsum) umma_commit_pair(&cs_bar[stage]);
+          } else {
+            umma_commit(&empty_bar[stage]);
+          }
           if (++stage == stages) { stage = 0; phase ^= 1u; }
         }
         if constexpr (pair) umma_commit_pair(&tfull_bar[acc]);       // accumulator complete -> both CTAs' epilogues
@@ -364,7 +377,65 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (acc == 0) acc_phase ^= 1u;
       }
     }
-  } else if (warp >= 4) {
+  } else if (warp < 4 && colsum) {
+    // warps 2 and 3: column sums of this CTA's A tiles (K-major: row r = 128 B, 16-byte unit u stored at
+    // u ^ (r & 7)). Lane = (row group rg, logical unit u): 4 rows per instruction, no bank conflicts; warp 2
+    // takes rows 0..63, warp 3 rows 64..127. Every (row block, k-block) tile is staged exactly once per
+    // column block, so only the tiles of column block 0 are summed. Rows beyond M arrive zero-filled.
+    const int w2 = warp - 2;
+    float* my = csum + w2 * (kblocks * kBlockK);
+    for (int i = lane; i < kblocks * kBlockK; i += 32) my[i] = 0.f;
+    __syncwarp();
+    const int u = lane & 7, rg = lane >> 3;
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int t = worker; t < num_tiles; t += n_workers) {
+      const int split = t % p.k_splits;
+      const int mn = t / p.k_splits;
+      const bool take = (mn % tiles_n) == 0;
+      const int kb0 = static_cast<int>(static_cast<long long>(split) * kblocks / p.k_splits);
+      const int kb1 = static_cast<int>(static_cast<long long>(split + 1) * kblocks / p.k_splits);
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(pair ? &cs_bar[stage] : &full_bar[stage], phase);
+        if (take) {
+          const uint8_t* a = sA + static_cast<size_t>(stage) * kABytes + static_cast<size_t>(w2) * 64 * 128;
+          float acc[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+#pragma unroll 8
+          for (int i = 0; i < 16; ++i) {
+            const int r = i * 4 + rg;
+            const uint4 x = *reinterpret_cast<const uint4*>(a + r * 128 + ((u ^ (r & 7)) << 4));
+            const uint32_t w[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+            for (int h = 0; h < 4; ++h)
+              fadd2(acc[2 * h], acc[2 * h + 1], __uint_as_float(w[h] << 16), __uint_as_float(w[h] & 0xFFFF0000u));
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 8);
+            acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 16);
+          }
+          if (rg == 0) {
+            float4* dst = reinterpret_cast<float4*>(my + kb * kBlockK + u * 8);
+            float4 lo = dst[0], hi = dst[1];
+            lo.x += acc[0]; lo.y += acc[1]; lo.z += acc[2]; lo.w += acc[3];
+            hi.x += acc[4]; hi.y += acc[5]; hi.z += acc[6]; hi.w += acc[7];
+            dst[0] = lo; dst[1] = hi;
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty_bar[stage]);   // this warp is done with the slot
+        if (++stage == stages) { stage = 0; phase ^= 1u; }
+      }
+    }
+    __syncwarp();
+    for (int i = lane; i < p.K; i += 32) {
+      const float v = my[i];
+      if (v != 0.f) atomicAdd(p.a_colsum + i, v);
+    }
+  }
+  if (warp >= 4) {
     // 16 epilogue warps (4 per scheduler: the chunk pipeline is a chain of TMEM / shared / global
     // latencies, hidden by switching warps rather than by unrolling). warp % 4 selects the TMEM lane
     // quarter (hardware rule); the four warps sharing a quarter take every 4th 32-column chunk.
@@ -438,8 +509,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 }
 
 static constexpr size_t kSmemLimit = 232448;
-static size_t gemm_fixed_smem(int stg_bytes) {   // alignment pad, staging, barriers (<= 8 stages), TMEM slot
-  return 1024 + static_cast<size_t>(kEpiWarps) * stg_bytes + (2 * 8 + 4) * sizeof(uint64_t) + 16;
+static size_t gemm_fixed_smem(int stg_bytes, int colsum_k) {   // alignment pad, staging, barriers (<= 8 stages), TMEM slot,
+  return 1024 + static_cast<size_t>(kEpiWarps) * stg_bytes + (3 * 8 + 4) * sizeof(uint64_t) + 32 +   // column sums
+         2 * sizeof(float) * static_cast<size_t>(colsum_k);
 }
 
 template <bool A_MN, bool B_MN, bool PAIR>
@@ -568,7 +640,10 @@ extern "C" int tt_gemm_bf16(const tt_gemm_args* a, void* stream_) {
   // bf16-only epilogues stage 64-byte rows: half the staging, more pipeline stages
   p.stg_bytes = static_cast<int>(((a->out_f32 || a->residual) ? kStageBytesF32 : kStageBytesBf16) +
                                  (a->bias ? kBiasBytesPerWarp : 0u));
-  const size_t fixed = gemm_fixed_smem(p.stg_bytes);
+  p.a_colsum = a->a_colsum;
+  TT_REQUIRE(!a->a_colsum || (!a->a_mn && ks == 1 && a->K <= 2048),
+             "tt_gemm_bf16: a_colsum needs a K-major A operand, no split-K and K <= 2048 (K=%d)", a->K);
+  const size_t fixed = gemm_fixed_smem(p.stg_bytes, a->a_colsum ? kblocks * kBlockK : 0);
   int stages = static_cast<int>((kSmemLimit - fixed) / (kABytes + b_bytes));
   if (stages > 8) stages = 8;
   TT_REQUIRE(stages >= 2, "tt_gemm_bf16: no room for a 2-stage pipeline (block_n %d)", bn);

@@ -124,6 +124,9 @@ class TwoTowerEngine:
         #: measurement aid: issue everything on the current stream (per-kernel event timing without overlap)
         self.serialize = False
         self.overlap_wgrad = os.environ.get("TT_OVERLAP_WGRAD", "1") != "0"
+        #: bias gradients of the linear layers whose dY is a dgrad GEMM's A operand: column sums taken inside that
+        #: GEMM (tt_gemm_args.a_colsum) instead of a separate pass over dY (tt_colsum_bf16)
+        self.fuse_bias_colsum = os.environ.get("TT_FUSE_BIAS_COLSUM", "1") != "0"
         #: row-sharded ID table (sharding.RowShardedTable, config 5): when set, `table_rows` [1 + B*L, 256] holds
         #: the rows the exchange fetched for this step's tokens (row 0 unused) and the embedding kernels index
         #: it with the token number instead of the item id; `table_rows_grad` receives the per-token gradient
@@ -414,6 +417,16 @@ class TwoTowerEngine:
         with torch.cuda.stream(wst):
             fn(*a, **kw)
 
+    def _dgrad_bias(self, dy, W, gbias, **kw) -> None:
+        """dX = dY W on the main chain together with the bias gradient sum(dY, dim=0) -> gbias (accumulated).
+        By default the GEMM's two idle warps take the column sums from the dY tiles it stages anyway
+        (``a_colsum``); with ``fuse_bias_colsum`` off a separate pass over dY runs on the wgrad stream."""
+        if self.fuse_bias_colsum:
+            self._gemm(dy, W, b_mn=True, a_colsum=gbias, **kw)
+        else:
+            self._wg(ops.colsum_bf16, dy, gbias)
+            self._gemm(dy, W, b_mn=True, **kw)
+
     def _lp(self, l: int, name: str) -> str:
         return f"user_tower.transformer_encoder.layers.{l}.{name}"
 
@@ -530,9 +543,8 @@ class TwoTowerEngine:
         wg(gemm, ws["dy_q"], ws["fq"], a_mn=True, b_mn=True, out_f32=g[self._lp(l, "linear2.weight")], accumulate=True)
         gemm(ws["dy_q"], w[self._lp(l, "linear2.weight")], b_mn=True, gate=ws["fq"], gate_scale=ffn_scale,
              out_bf16=ws["dpre_q"])
-        wg(ops.colsum_bf16, ws["dpre_q"], g[self._lp(l, "linear1.bias")])
         wg(gemm, ws["dpre_q"], ws["h2q"], a_mn=True, b_mn=True, out_f32=g[self._lp(l, "linear1.weight")], accumulate=True)
-        gemm(ws["dpre_q"], w[self._lp(l, "linear1.weight")], b_mn=True, out_f32=ws["dh_q"])
+        self._dgrad_bias(ws["dpre_q"], w[self._lp(l, "linear1.weight")], g[self._lp(l, "linear1.bias")], out_f32=ws["dh_q"])
         ops.chain_bwd(ws["xmid_q"], ln=(p[self._lp(l, "norm2.weight")], p[self._lp(l, "norm2.bias")]), dout=ws["dh_q"],
                       resid=ws["dxq"], dx_f32=ws["dxmid_q"], dx_bf16=ws["dy_q1"], drop2_p=dp, drop2_site=_site(l, 1),
                       seed=seed, seed_dev=sdev, dgamma=g[self._lp(l, "norm2.weight")],
@@ -544,13 +556,11 @@ class TwoTowerEngine:
         dqkv = ws[f"dqkv_{l}"]
         ops.attn_lastq_bwd(ws["qq"], ws[f"qkv_{l}"], ws["last_idx"], ws["ctxq"], ws["dctx_q"], ws["lseq"], ws["dq_q"],
                            dqkv, B, L, cfg.num_heads, drop_p=dp, seed=seed, seed_dev=sdev, site=_site(l, 0))
-        wg(ops.colsum_bf16, ws["dq_q"], gb[:D])
         wg(gemm, ws["dq_q"], ws["hq"], a_mn=True, b_mn=True, out_f32=gW[:D], accumulate=True)
-        gemm(ws["dq_q"], Wqkv[:D], b_mn=True, out_f32=ws["dhq"])
+        self._dgrad_bias(ws["dq_q"], Wqkv[:D], gb[:D], out_f32=ws["dhq"])
         dkv = dqkv[:, D:]
-        wg(ops.colsum_bf16, dkv, gb[D:])
         wg(gemm, dkv, ws[f"h1_{l}"], a_mn=True, b_mn=True, out_f32=gW[D:], accumulate=True)
-        gemm(dkv, Wqkv[D:], b_mn=True, out_f32=ws["dh"])
+        self._dgrad_bias(dkv, Wqkv[D:], gb[D:], out_f32=ws["dh"])
         ops.scatter_rows_add(ws["dhq"], ws["last_idx"], B, L, ws["dh"], accumulate=True)
         # --- residual gradient of the layer input: only the gathered rows carry one
         # the residual-stream gradient into this layer's input is non-zero for ONE row per sequence
@@ -776,10 +786,9 @@ class TwoTowerEngine:
             wg(gemm, dy2, ws[f"f_{l}"], a_mn=True, b_mn=True, out_f32=g[self._lp(l, "linear2.weight")], accumulate=True)
             gemm(dy2, w[self._lp(l, "linear2.weight")], b_mn=True, gate=ws[f"f_{l}"], gate_scale=ffn_scale,
                  out_bf16=dpre)
-            wg(ops.colsum_bf16, dpre, g[self._lp(l, "linear1.bias")])
             wg(gemm, dpre, ws[f"h2_{l}"], a_mn=True, b_mn=True, out_f32=g[self._lp(l, "linear1.weight")],
                accumulate=True)
-            gemm(dpre, w[self._lp(l, "linear1.weight")], b_mn=True, out_f32=ws["dh"])
+            self._dgrad_bias(dpre, w[self._lp(l, "linear1.weight")], g[self._lp(l, "linear1.bias")], out_f32=ws["dh"])
             # norm2 backward (+ residual); emits dy for out_proj (dropout-1 mask) and its bias grad
             ops.chain_bwd(ws[f"xmid_{l}"], ln=(p[self._lp(l, "norm2.weight")], p[self._lp(l, "norm2.bias")]),
                           dout=ws["dh"], resid=dx, dx_f32=dx_other, dx_bf16=dy1, drop2_p=dp,
@@ -792,10 +801,10 @@ class TwoTowerEngine:
             gemm(dy1, w[self._lp(l, "self_attn.out_proj.weight")], b_mn=True, out_bf16=ws["dctx"])
             ops.attn_bwd(ws[f"qkv_{l}"], ws[f"ctx_{l}"], ws["dctx"], ws[f"lse_{l}"], dqkv, B, L, cfg.num_heads,
                          drop_p=dp, drop_seed=seed, drop_seed_dev=sdev, drop_site=_site(l, 0))
-            wg(ops.colsum_bf16, dqkv, g[self._lp(l, "self_attn.in_proj_bias")])
             wg(gemm, dqkv, ws[f"h1_{l}"], a_mn=True, b_mn=True, out_f32=g[self._lp(l, "self_attn.in_proj_weight")],
                accumulate=True)
-            gemm(dqkv, w[self._lp(l, "self_attn.in_proj_weight")], b_mn=True, out_f32=ws["dh"])
+            self._dgrad_bias(dqkv, w[self._lp(l, "self_attn.in_proj_weight")], g[self._lp(l, "self_attn.in_proj_bias")],
+                             out_f32=ws["dh"])
             # norm1 backward (+ residual); for l > 0 also dy for the previous layer's linear2
             extra = {}
             if l > 0:

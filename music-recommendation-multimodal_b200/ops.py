@@ -29,13 +29,13 @@ def gemm(A: torch.Tensor, B: torch.Tensor, *, a_mn: bool = False, b_mn: bool = F
          drop_seed_dev: Optional[torch.Tensor] = None, gate: Optional[torch.Tensor] = None, gate_scale: float = 1.0,
          residual: Optional[torch.Tensor] = None,
          out_f32: Optional[torch.Tensor] = None, out_bf16: Optional[torch.Tensor] = None,
-         accumulate: bool = False, k_splits: int = 0, block_n: int = 0,
+         accumulate: bool = False, k_splits: int = 0, block_n: int = 0, a_colsum: Optional[torch.Tensor] = None,
          M: Optional[int] = None, N: Optional[int] = None, K: Optional[int] = None) -> None:
     """C[M,N] = epi(alpha * A @ B^T). See ``tt_gemm_bf16`` in include/tt_b200.h.
 
     a_mn=False: A is [M,K]; a_mn=True: A is stored [K,M]. Same for B with N.
     """
-    _require_cuda(A, B, bias, gate, residual, out_f32, out_bf16)
+    _require_cuda(A, B, bias, gate, residual, out_f32, out_bf16, a_colsum)
     assert A.dtype == torch.bfloat16 and B.dtype == torch.bfloat16
     assert A.dim() == 2 and B.dim() == 2 and A.stride(1) == 1 and B.stride(1) == 1
     if a_mn:
@@ -81,6 +81,9 @@ def gemm(A: torch.Tensor, B: torch.Tensor, *, a_mn: bool = False, b_mn: bool = F
     args.accumulate = int(accumulate)
     args.k_splits = k_splits
     args.block_n = block_n
+    if a_colsum is not None:      # a_colsum[k] += sum_m A[m, k]: the bias gradient next to a dgrad GEMM
+        assert a_colsum.dtype == torch.float32 and a_colsum.is_contiguous() and a_colsum.numel() >= K and not a_mn
+    args.a_colsum = _ptr(a_colsum)
     check(lib().tt_gemm_bf16(ctypes.byref(args), _stream()), "tt_gemm_bf16")
 
 

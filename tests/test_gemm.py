@@ -230,3 +230,43 @@ def test_gemm_large_splitk_wgrad():
     ops.gemm(As, Bs, a_mn=True, b_mn=True, out_f32=out, accumulate=True)
     torch.cuda.synchronize()
     _check(out, A.float() @ B.float().t() + 1.0, K, "large split-K")
+
+
+@pytest.mark.parametrize("M,N,K,b_mn", [
+    (256, 256, 256, True),        # B-row dgrad of the single-row last layer: several column blocks, only block 0 sums
+    (200, 104, 304, False),       # ragged rows / columns / reduction (zero-filled tails must not count)
+    (128 * 13 + 40, 256, 1024, True),   # CTA pairs (deep reduction), odd number of row blocks
+    (51200, 256, 768, True),      # the c2 dgrad of the packed in_proj: dY = dqkv
+    (51200, 256, 1024, True),     # the c2 dgrad of linear1: dY = dpre
+    (2048, 512, 512, True),       # two column blocks per row block with a 256-wide tile
+])
+def test_gemm_a_colsum(M, N, K, b_mn):
+    """a_colsum[k] += sum_m A[m, k] next to the product (the bias gradient that belongs to a dgrad GEMM's dY
+    operand), against an fp64 column sum of the same bf16 values; the product itself must not change."""
+    from mrm_b200 import ops
+    lda = ((K + 63) // 64) * 64 + 64          # a view into a wider buffer, like dqkv[:, D:]
+    A = _mk((M, lda), 21)[:, 64:64 + K]
+    B = _mk((N, K), 22)
+    Bs = B.t().contiguous() if b_mn else B
+    out = torch.empty((M, N), device="cuda", dtype=torch.float32)
+    ref_out = torch.empty_like(out)
+    cs = torch.full((K,), 0.25, device="cuda", dtype=torch.float32)      # accumulated, not overwritten
+    ops.gemm(A, Bs, b_mn=b_mn, out_f32=ref_out)
+    ops.gemm(A, Bs, b_mn=b_mn, out_f32=out, a_colsum=cs)
+    torch.cuda.synchronize()
+    assert torch.equal(out, ref_out)
+    ref = A.double().sum(dim=0) + 0.25
+    err = (cs.double() - ref).abs().max().item()
+    assert err <= 1e-6 * A.float().abs().sum(dim=0).max().item() + 1e-6, err
+
+
+def test_gemm_a_colsum_rejects_mn_major_and_splitk():
+    from mrm_b200 import ops
+    from mrm_b200._lib import TTError
+    A, B = _mk((256, 128), 1), _mk((128, 128), 2)
+    out = torch.zeros((128, 128), device="cuda", dtype=torch.float32)
+    cs = torch.zeros(512, device="cuda")
+    with pytest.raises((TTError, AssertionError)):
+        ops.gemm(A, B.t().contiguous(), a_mn=True, b_mn=True, out_f32=out, a_colsum=cs)
+    with pytest.raises(TTError):
+        ops.gemm(_mk((128, 512), 3), _mk((128, 512), 4), out_f32=out, accumulate=True, k_splits=2, a_colsum=cs)
