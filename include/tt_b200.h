@@ -182,6 +182,10 @@ typedef struct tt_chain_args {
   const float* resid_rows;
   const int32_t* resid_last_idx;
   int32_t resid_seq_len;
+  /* backward: the incoming gradient as bf16 [rows, width] instead of `dout` (exactly one of the two). Under
+   * autocast the reference's Linear backward returns dX in bf16 (src/train.py:57-62), so a dgrad GEMM may hand
+   * its result over in that type: half the bytes written there and read here. */
+  const void* dout_bf16;
 } tt_chain_args;
 int tt_chain_fwd(const tt_chain_args* args, void* stream);
 int tt_chain_bwd(const tt_chain_args* args, void* stream);

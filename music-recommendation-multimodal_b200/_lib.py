@@ -105,6 +105,7 @@ class ChainArgs(ctypes.Structure):
         ("drop2_p", c_float), ("drop2_site", c_uint32),
         ("dgamma", c_void_p), ("dbeta", c_void_p), ("dx_colsum", c_void_p),
         ("resid_rows", c_void_p), ("resid_last_idx", c_void_p), ("resid_seq_len", c_int32),
+        ("dout_bf16", c_void_p),
     ]
 
 

@@ -196,6 +196,7 @@ struct ChainParams {
   __nv_bfloat16* out_bf16; // nullable
   // backward only
   const float* dout;       // [R, W] gradient w.r.t. the chain output
+  const __nv_bfloat16* dout_bf16;   // the same as bf16 (exclusive with dout): what a dgrad GEMM hands back under autocast
   const float* resid;      // nullable [R, W]: added to dx
   const float* resid_rows; // nullable [R / resid_L, W]: added to row b*resid_L + resid_idx[b] of sequence b only
   const int32_t* resid_idx;
@@ -265,7 +266,8 @@ __global__ void __launch_bounds__(kRowThreads, 2) chain_bwd_kernel(const ChainPa
   float xn[E], gn[E], rn[E];
   if (row < p.R) {
     load_row<NV>(p.x + static_cast<size_t>(row) * W, lane, xn);
-    load_row<NV>(p.dout + static_cast<size_t>(row) * W, lane, gn);
+    if (p.dout_bf16) load_row_bf16<NV>(p.dout_bf16 + static_cast<size_t>(row) * W, lane, gn);
+    else load_row<NV>(p.dout + static_cast<size_t>(row) * W, lane, gn);
     if (p.resid) load_row<NV>(p.resid + static_cast<size_t>(row) * W, lane, rn);
   }
   for (; row < p.R; row += warps_total) {
@@ -275,7 +277,8 @@ __global__ void __launch_bounds__(kRowThreads, 2) chain_bwd_kernel(const ChainPa
     const int nrow = row + warps_total;
     if (nrow < p.R) {
       load_row<NV>(p.x + static_cast<size_t>(nrow) * W, lane, xn);
-      load_row<NV>(p.dout + static_cast<size_t>(nrow) * W, lane, gn);
+      if (p.dout_bf16) load_row_bf16<NV>(p.dout_bf16 + static_cast<size_t>(nrow) * W, lane, gn);
+      else load_row<NV>(p.dout + static_cast<size_t>(nrow) * W, lane, gn);
       if (p.resid) load_row<NV>(p.resid + static_cast<size_t>(nrow) * W, lane, rn);
     }
     float mean = 0.f, rstd = 1.f;
@@ -956,7 +959,7 @@ static int fill_chain(ChainParams& p, const tt_chain_args* a, const char* who) {
   p.seed = a->drop_seed; p.seed_dev = a->drop_seed_dev; p.site = a->drop_site;
   p.l2norm = a->l2norm; p.l2_eps = a->l2_eps > 0.f ? a->l2_eps : 1e-12f;
   p.out_f32 = a->out_f32; p.out_bf16 = static_cast<__nv_bfloat16*>(a->out_bf16);
-  p.dout = a->dout; p.resid = a->resid; p.dx_f32 = a->dx_f32;
+  p.dout = a->dout; p.dout_bf16 = static_cast<const __nv_bfloat16*>(a->dout_bf16); p.resid = a->resid; p.dx_f32 = a->dx_f32;
   p.resid_rows = a->resid_rows; p.resid_idx = a->resid_last_idx; p.resid_L = a->resid_seq_len;
   TT_REQUIRE(!(a->resid && a->resid_rows), "%s: resid and resid_rows are exclusive", who);
   TT_REQUIRE(!a->resid_rows || (a->resid_last_idx && a->resid_seq_len > 0 && a->rows % a->resid_seq_len == 0),
@@ -986,7 +989,8 @@ extern "C" int tt_chain_bwd(const tt_chain_args* a, void* stream_) {
   ChainParams p;
   int rc = fill_chain(p, a, "tt_chain_bwd");
   if (rc) return rc;
-  TT_REQUIRE(p.dout && (p.dx_f32 || p.dx_bf16), "tt_chain_bwd: dout and a dx output are required");
+  TT_REQUIRE((p.dout != nullptr) != (p.dout_bf16 != nullptr) && (p.dx_f32 || p.dx_bf16),
+             "tt_chain_bwd: exactly one of dout / dout_bf16 and a dx output are required");
   TT_REQUIRE(!p.ln_w || (p.dgamma && p.dbeta), "tt_chain_bwd: LayerNorm needs dgamma/dbeta");
   TT_REQUIRE(a->width == 256, "tt_chain_bwd: width %d unsupported (256)", a->width);
   int grid = row_grid(p.R);

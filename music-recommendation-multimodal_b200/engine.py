@@ -127,6 +127,9 @@ class TwoTowerEngine:
         #: bias gradients of the linear layers whose dY is a dgrad GEMM's A operand: column sums taken inside that
         #: GEMM (tt_gemm_args.a_colsum) instead of a separate pass over dY (tt_colsum_bf16)
         self.fuse_bias_colsum = os.environ.get("TT_FUSE_BIAS_COLSUM", "1") != "0"
+        #: dX of linear1 / in_proj of the full-sequence layers travels to the LayerNorm backward as bf16 (the dtype
+        #: autograd gives it under the reference's autocast, src/train.py:57-62) instead of fp32
+        self.bf16_linear_dgrad = os.environ.get("TT_BF16_LINEAR_DGRAD", "1") != "0"
         #: row-sharded ID table (sharding.RowShardedTable, config 5): when set, `table_rows` [1 + B*L, 256] holds
         #: the rows the exchange fetched for this step's tokens (row 0 unused) and the embedding kernels index
         #: it with the token number instead of the item id; `table_rows_grad` receives the per-token gradient
@@ -314,6 +317,7 @@ class TwoTowerEngine:
             if l < NL - 1 or not self.prune_last_layer:
                 ws[f"dpre_{l}"] = torch.empty(T, FF, **bf)
         ws["dh"] = torch.empty(T, D, **f32)        # grad w.r.t. a LayerNorm output
+        ws["dh_bf"] = torch.empty(T, D, **bf)      # the same in bf16 (what a Linear's backward returns under autocast)
         ws["dctx"] = torch.empty(T, D, **bf)
         self._ws[key] = ws
         return ws
@@ -783,15 +787,21 @@ class TwoTowerEngine:
             if f"dpre_{l}" not in ws:      # prune_last_layer toggled after the workspace was built
                 ws[f"dpre_{l}"] = torch.empty(B * L, cfg.ff_dim, dtype=torch.bfloat16, device=self.device)
             dy2, dy1, dpre, dqkv = ws[f"dy2_{l}"], ws[f"dy1_{l}"], ws[f"dpre_{l}"], ws[f"dqkv_{l}"]
+            # the gradient a Linear hands back to the LayerNorm in front of it: bf16 like the reference's autocast
+            # backward (half the bytes between the dgrad GEMM and the LayerNorm backward), or fp32
+            if self.bf16_linear_dgrad:
+                dh_out, dh_in = dict(out_bf16=ws["dh_bf"]), dict(dout_bf16=ws["dh_bf"])
+            else:
+                dh_out, dh_in = dict(out_f32=ws["dh"]), dict(dout=ws["dh"])
             wg(gemm, dy2, ws[f"f_{l}"], a_mn=True, b_mn=True, out_f32=g[self._lp(l, "linear2.weight")], accumulate=True)
             gemm(dy2, w[self._lp(l, "linear2.weight")], b_mn=True, gate=ws[f"f_{l}"], gate_scale=ffn_scale,
                  out_bf16=dpre)
             wg(gemm, dpre, ws[f"h2_{l}"], a_mn=True, b_mn=True, out_f32=g[self._lp(l, "linear1.weight")],
                accumulate=True)
-            self._dgrad_bias(dpre, w[self._lp(l, "linear1.weight")], g[self._lp(l, "linear1.bias")], out_f32=ws["dh"])
+            self._dgrad_bias(dpre, w[self._lp(l, "linear1.weight")], g[self._lp(l, "linear1.bias")], **dh_out)
             # norm2 backward (+ residual); emits dy for out_proj (dropout-1 mask) and its bias grad
             ops.chain_bwd(ws[f"xmid_{l}"], ln=(p[self._lp(l, "norm2.weight")], p[self._lp(l, "norm2.bias")]),
-                          dout=ws["dh"], resid=dx, dx_f32=dx_other, dx_bf16=dy1, drop2_p=dp,
+                          resid=dx, dx_f32=dx_other, dx_bf16=dy1, drop2_p=dp, **dh_in,
                           drop2_site=_site(l, 1), seed=seed, seed_dev=sdev,
                           dgamma=g[self._lp(l, "norm2.weight")], dbeta=g[self._lp(l, "norm2.bias")],
                           dx_colsum=g[self._lp(l, "self_attn.out_proj.bias")])
@@ -804,13 +814,13 @@ class TwoTowerEngine:
             wg(gemm, dqkv, ws[f"h1_{l}"], a_mn=True, b_mn=True, out_f32=g[self._lp(l, "self_attn.in_proj_weight")],
                accumulate=True)
             self._dgrad_bias(dqkv, w[self._lp(l, "self_attn.in_proj_weight")], g[self._lp(l, "self_attn.in_proj_bias")],
-                             out_f32=ws["dh"])
+                             **dh_out)
             # norm1 backward (+ residual); for l > 0 also dy for the previous layer's linear2
             extra = {}
             if l > 0:
                 extra = dict(dx_bf16=ws[f"dy2_{l - 1}"], drop2_p=dp, drop2_site=_site(l - 1, 3),
                              dx_colsum=g[self._lp(l - 1, "linear2.bias")])
-            ops.chain_bwd(x_in, ln=(p[self._lp(l, "norm1.weight")], p[self._lp(l, "norm1.bias")]), dout=ws["dh"],
+            ops.chain_bwd(x_in, ln=(p[self._lp(l, "norm1.weight")], p[self._lp(l, "norm1.bias")]), **dh_in,
                           resid=dx, dx_f32=dx_other, seed=seed, seed_dev=sdev,
                           dgamma=g[self._lp(l, "norm1.weight")], dbeta=g[self._lp(l, "norm1.bias")], **extra)
             dx, dx_other = dx_other, dx

@@ -221,8 +221,8 @@ def rows_scatter_add(uniq, state, gacc, team=None, grad_offset=0, grad_local=Non
 def _chain_args(x, *, ln=None, relu=False, drop_p=0.0, seed=0, seed_dev=None, site=0, l2norm=False,
                 l2_eps=1e-12, out_f32=None, out_bf16=None, dout=None, resid=None, dx_f32=None, dx_bf16=None,
                 drop2_p=0.0, drop2_site=0, dgamma=None, dbeta=None, dx_colsum=None, resid_rows=None,
-                resid_last_idx=None, resid_seq_len=0) -> ChainArgs:
-    _require_cuda(x, out_f32, out_bf16, dout, resid, dx_f32, dx_bf16, dgamma, dbeta, dx_colsum, resid_rows,
+                resid_last_idx=None, resid_seq_len=0, dout_bf16=None) -> ChainArgs:
+    _require_cuda(x, out_f32, out_bf16, dout, dout_bf16, resid, dx_f32, dx_bf16, dgamma, dbeta, dx_colsum, resid_rows,
                   resid_last_idx)
     assert x.dtype == torch.float32 and x.dim() == 2 and x.is_contiguous()
     a = ChainArgs()
@@ -242,6 +242,9 @@ def _chain_args(x, *, ln=None, relu=False, drop_p=0.0, seed=0, seed_dev=None, si
         assert resid_rows.dtype == torch.float32 and resid_rows.is_contiguous() and resid_rows.shape[1] == x.shape[1]
         assert resid_last_idx.dtype == torch.int32 and x.shape[0] == resid_rows.shape[0] * resid_seq_len
     a.resid_rows, a.resid_last_idx, a.resid_seq_len = _ptr(resid_rows), _ptr(resid_last_idx), resid_seq_len
+    if dout_bf16 is not None:
+        assert dout is None and dout_bf16.dtype == torch.bfloat16 and dout_bf16.is_contiguous() and dout_bf16.shape == x.shape
+    a.dout_bf16 = _ptr(dout_bf16)
     return a
 
 

@@ -110,6 +110,29 @@ def test_chain_bwd_sparse_residual_equals_dense():
     assert torch.allclose(outs[0][1], outs[1][1], atol=1e-4) and torch.allclose(outs[0][2], outs[1][2], atol=1e-4)
 
 
+def test_chain_bwd_bf16_incoming_gradient():
+    """dout_bf16 == dout holding the same (bf16-representable) values: the incoming gradient of a LayerNorm whose
+    consumer is a Linear arrives in bf16 under autocast; only the load differs."""
+    from mrm_b200 import ops
+    from mrm_b200._lib import TTError
+    R, W = 777, 256
+    x, resid = _randn(R, W, seed=41), _randn(R, W, seed=43)
+    d16 = _randn(R, W, seed=42).to(torch.bfloat16)
+    w, b = 1 + _randn(W, seed=44, scale=0.1), _randn(W, seed=45, scale=0.1)
+    outs = []
+    for kw in (dict(dout=d16.float()), dict(dout_bf16=d16)):
+        dx, dxb = torch.empty(R, W, device="cuda"), torch.empty(R, W, device="cuda", dtype=torch.bfloat16)
+        dg, db, cs = (torch.zeros(W, device="cuda") for _ in range(3))
+        ops.chain_bwd(x, ln=(w, b), resid=resid, dx_f32=dx, dx_bf16=dxb, dgamma=dg, dbeta=db, dx_colsum=cs, **kw)
+        outs.append((dx, dxb, dg, db, cs))
+    torch.cuda.synchronize()
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    for a, c in zip(outs[0][2:], outs[1][2:]):
+        assert torch.allclose(a, c, atol=1e-3, rtol=1e-5)
+    with pytest.raises(TTError):       # exactly one of the two
+        ops.chain_bwd(x, ln=(w, b), dx_f32=outs[0][0], dgamma=outs[0][2], dbeta=outs[0][3])
+
+
 def test_chain_dropout_fwd_bwd_consistent():
     """Same (seed, site) in forward and backward: d/dx of sum(dropout(LN(x)) * c) matches a finite mask."""
     from mrm_b200 import ops
