@@ -44,9 +44,12 @@ struct GemmParams {
   int accumulate;
   int pair;         // 1 = CTA pairs (cluster of 2, tcgen05 cta_group::2): a pair computes a 256-row x block_n tile;
                     // each CTA stages its 128 rows of A and HALF of the B tile, the leader issues M=256 MMAs
-  int stg_bytes;    // per-epilogue-warp staging bytes (tile + 256 B bias slice)
+  int stg_bytes;    // per-epilogue-warp staging tile bytes (the 256 B bias slices follow the 16 tiles)
+  int tma_store;    // 1: finished 32 x 32 output blocks leave through TMA tensor stores straight from the (swizzled)
+                    // staging tile instead of a transposed LDS + STG pass by the warp
   float* a_colsum;  // optional [K]: += column sums of the (K-major) A operand, taken from the staged tiles by warps 2 and 3
-  int debug;  // profiling knob: 1 = epilogue drains TMEM only (no math, no global IO); 2 = everything but the global stores
+  int debug;  // profiling knob: low 4 bits 1 = epilogue drains TMEM only (no math, no global IO), 2 = everything but the
+              // global stores; +16 / +32 = operand loads skipped after the first ring revolution (B only / A and B)
 };
 
 static constexpr int kBlockM = 128;
@@ -116,9 +119,18 @@ __device__ __forceinline__ void epi_prefetch_l2(const GemmParams& p, int lane, i
 
 // One 32-column chunk of one accumulator row per lane. `next_col0` >= 0 asks for the prefetch of
 // the warp's next chunk once the staging tile (`in` and `out` may be the same tile) is free again.
+// The staging tile may still be read by a TMA store issued from it: wait (lane 0 issued it) before it is rewritten.
+__device__ __forceinline__ void stg_acquire(const GemmParams& p, int lane) {
+  if (p.tma_store) {
+    if (lane == 0) tma_store_wait_read();
+    __syncwarp();
+  }
+}
+
 __device__ __forceinline__ void gemm_epilogue_chunk(const GemmParams& p, const uint32_t (&r)[32], uint8_t* out,
                                                     uint8_t* in, const float* sbias, int lane, int row0, int col0,
-                                                    int next_col0, uint32_t dkey) {
+                                                    int next_col0, uint32_t dkey, const CUtensorMap* tmO32,
+                                                    const CUtensorMap* tmO16) {
   const int row = row0 + lane;
   float v[32];
 #pragma unroll
@@ -178,15 +190,23 @@ __device__ __forceinline__ void gemm_epilogue_chunk(const GemmParams& p, const u
     __syncwarp();
   }
   if (p.out_f32) {
+    stg_acquire(p, lane);
 #pragma unroll
     for (int u = 0; u < 8; ++u)
       *reinterpret_cast<float4*>(stg_unit(out, lane, u)) = make_float4(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]);
+    if (p.tma_store) {
+      // the tile is laid out exactly as the 128-byte TMA swizzle expects (unit ^ (row & 7)); rows / columns beyond
+      // M / N are clipped by the tensor map
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0 && (p.debug & 15) != 2) { tma_store_2d(tmO32, out, col0, row0); tma_store_commit(); }
+    } else {
     __syncwarp();
 #pragma unroll
     for (int it = 0; it < 8; ++it) {
       const int rr = it * 4 + (lane >> 3), u = lane & 7;
       const int gr = row0 + rr, gc = col0 + u * 4;
-      if (gr < p.M && gc + 4 <= p.N && p.debug != 2) {
+      if (gr < p.M && gc + 4 <= p.N && (p.debug & 15) != 2) {
         const float4 x = *reinterpret_cast<const float4*>(stg_unit(out, rr, u));
         float* o = p.out_f32 + static_cast<size_t>(gr) * p.ld_f32 + gc;
         if (p.accumulate) red_add_f32x4(o, x.x, x.y, x.z, x.w);
@@ -194,8 +214,10 @@ __device__ __forceinline__ void gemm_epilogue_chunk(const GemmParams& p, const u
       }
     }
     __syncwarp();
+    }
   }
   if (p.out_bf16) {
+    stg_acquire(p, lane);
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       uint4 x;
@@ -205,23 +227,33 @@ __device__ __forceinline__ void gemm_epilogue_chunk(const GemmParams& p, const u
       x.w = pack_bf16(v[u * 8 + 6], v[u * 8 + 7]);
       *stg_unit_bf(out, lane, u) = x;
     }
+    if (p.tma_store) {   // 64-byte TMA swizzle == unit ^ ((row >> 1) & 3)
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0 && (p.debug & 15) != 2) { tma_store_2d(tmO16, out, col0, row0); tma_store_commit(); }
+    } else {
     __syncwarp();
 #pragma unroll
     for (int it = 0; it < 4; ++it) {
       const int rr = it * 8 + (lane >> 2), u = lane & 3;
       const int gr = row0 + rr, gc = col0 + u * 8;
-      if (gr < p.M && gc + 8 <= p.N && p.debug != 2)
+      if (gr < p.M && gc + 8 <= p.N && (p.debug & 15) != 2)
         *reinterpret_cast<uint4*>(p.out_bf16 + static_cast<size_t>(gr) * p.ld_bf16 + gc) = *stg_unit_bf(out, rr, u);
     }
     __syncwarp();
+    }
   }
   // the staging tile is free again: fetch the residual / gate block of this warp's next chunk
-  if ((p.residual || p.gate) && next_col0 >= 0) epi_prefetch(p, in, lane, row0, next_col0);
+  if ((p.residual || p.gate) && next_col0 >= 0) {
+    stg_acquire(p, lane);
+    epi_prefetch(p, in, lane, row0, next_col0);
+  }
 }
 
 template <bool A_MN, bool B_MN, bool PAIR>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const __grid_constant__ CUtensorMap tmO32, const __grid_constant__ CUtensorMap tmO16,
                  const GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t pad = (1024u - (smem_u32(smem_raw) & 1023u)) & 1023u;
@@ -249,7 +281,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint8_t* sA = smem;
   uint8_t* sB = smem + static_cast<size_t>(stages) * kABytes;
   uint8_t* sStage = sB + static_cast<size_t>(stages) * b_bytes;  // kEpiWarps staging tiles
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sStage + static_cast<size_t>(kEpiWarps) * p.stg_bytes);
+  uint8_t* sBias = sStage + static_cast<size_t>(kEpiWarps) * p.stg_bytes;     // kEpiWarps x 256 B when p.bias
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sBias + (p.bias ? kEpiWarps * kBiasBytesPerWarp : 0u));
   uint64_t* empty_bar = full_bar + stages;
   uint64_t* tfull_bar = empty_bar + stages;
   uint64_t* tempty_bar = tfull_bar + 2;
@@ -300,7 +333,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   auto m_block = [&](int mn) { return pair ? 2 * (mn / tiles_n) + static_cast<int>(rank) : mn / tiles_n; };
   if (warp == 0) {
     if (elect_one()) {
-      int stage = 0;
+      int stage = 0, issued = 0;
       uint32_t phase = 0;
       for (int t = worker; t < num_tiles; t += n_workers) {
         const int split = t % p.k_splits;
@@ -321,10 +354,16 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             else      tma_load_2d_pair(b_dst, &tmB, &full_bar[stage], kb * kBlockK,
                                        n_blk * block_n + static_cast<int>(rank) * (block_n / 2));
           } else {
-            mbar_arrive_expect_tx(&full_bar[stage], kABytes + b_bytes);
-            if (A_MN) tma_load_3d(a_dst, &tmA, &full_bar[stage], 0, kb * kBlockK, m_blk * (kBlockM / 64));
+            // profiling knobs (results are garbage): +16 = B tiles are fetched for the first ring revolution only
+            // (what a weight-resident form would stream), +32 = neither operand after that
+            const bool skip_b = (p.debug & 48) && issued >= stages, skip_a = (p.debug & 32) && issued >= stages;
+            ++issued;
+            mbar_arrive_expect_tx(&full_bar[stage], (skip_a ? 0u : kABytes) + (skip_b ? 0u : b_bytes));
+            if (skip_a) {}
+            else if (A_MN) tma_load_3d(a_dst, &tmA, &full_bar[stage], 0, kb * kBlockK, m_blk * (kBlockM / 64));
             else      tma_load_2d(a_dst, &tmA, &full_bar[stage], kb * kBlockK, m_blk * kBlockM);
-            if (B_MN) tma_load_3d(b_dst, &tmB, &full_bar[stage], 0, kb * kBlockK, n_blk * (block_n / 64));
+            if (skip_b) {}
+            else if (B_MN) tma_load_3d(b_dst, &tmB, &full_bar[stage], 0, kb * kBlockK, n_blk * (block_n / 64));
             else      tma_load_2d(b_dst, &tmB, &full_bar[stage], kb * kBlockK, n_blk * block_n);
           }
           if (++stage == stages) { stage = 0; phase ^= 1u; }
@@ -442,7 +481,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int ew = warp - 4;
     const int q = ew & 3, sub = ew >> 2;
     uint8_t* stg = sStage + static_cast<size_t>(ew) * p.stg_bytes;
-    float* sbias = reinterpret_cast<float*>(stg + p.stg_bytes - kBiasBytesPerWarp);   // [2 chunks][32]
+    float* sbias = reinterpret_cast<float*>(sBias + static_cast<size_t>(ew) * kBiasBytesPerWarp);   // [2 chunks][32]
     const uint64_t seed = p.drop_seed + ((p.drop_thresh && p.drop_seed_dev) ? *p.drop_seed_dev : 0ull);
     const uint32_t dkey = drop_key(seed, p.drop_site);
     const int nchunks = block_n / 32;
@@ -471,7 +510,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           sbias[k * 32 + lane] = col < p.N ? __ldg(p.bias + col) : 0.f;
         }
       }
-      if (has_in && sub < nchunks) epi_prefetch(p, stg, lane, row0, colbase + sub * 32);
+      if (has_in && sub < nchunks) {
+        stg_acquire(p, lane);
+        epi_prefetch(p, stg, lane, row0, colbase + sub * 32);
+      }
       mbar_wait(&tfull_bar[acc], acc_phase);
       __syncwarp();
       tc_fence_after();
@@ -482,11 +524,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         tmem_ld32(t_base + static_cast<uint32_t>(c * 32), r);
         tmem_ld_wait();
         const int cn = c + kEpiWarps / 4;
-        if (p.debug != 1)
+        if ((p.debug & 15) != 1)
           gemm_epilogue_chunk(p, r, stg, stg, sbias + k * 32, lane, row0, colbase + c * 32,
-                              cn < nchunks ? colbase + cn * 32 : -1, dkey);
+                              cn < nchunks ? colbase + cn * 32 : -1, dkey, &tmO32, &tmO16);
       }
-      if (p.debug == 1) cp_async_wait_all();
+      if ((p.debug & 15) == 1) cp_async_wait_all();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
@@ -496,6 +538,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
     }
+    if (p.tma_store && lane == 0) tma_store_wait_all();   // shared memory stays valid until the engine has read it
   }
 
   tc_fence_before();
@@ -515,8 +558,8 @@ static size_t gemm_fixed_smem(int stg_bytes, int colsum_k) {   // alignment pad,
 }
 
 template <bool A_MN, bool B_MN, bool PAIR>
-static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, int grid,
-                       size_t smem, cudaStream_t stream) {
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO32,
+                       const CUtensorMap& tmO16, const GemmParams& p, int grid, size_t smem, cudaStream_t stream) {
   static bool configured = false;
   if (!configured) {
     TT_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<A_MN, B_MN, PAIR>,
@@ -537,19 +580,19 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    TT_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_kernel<A_MN, B_MN, PAIR>, tmA, tmB, p));
+    TT_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_kernel<A_MN, B_MN, PAIR>, tmA, tmB, tmO32, tmO16, p));
   } else {
-    TT_CHECK_CUDA(launch_k(gemm_bf16_kernel<A_MN, B_MN, PAIR>, dim3(grid), dim3(kGemmThreads), smem, stream, tmA, tmB, p));
+    TT_CHECK_CUDA(launch_k(gemm_bf16_kernel<A_MN, B_MN, PAIR>, dim3(grid), dim3(kGemmThreads), smem, stream, tmA, tmB, tmO32, tmO16, p));
   }
   TT_LAUNCH_CHECK();
   return TT_OK;
 }
 
 template <bool A_MN, bool B_MN>
-static int launch_gemm_mode(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, int grid,
-                            size_t smem, cudaStream_t stream) {
-  return p.pair ? launch_gemm<A_MN, B_MN, true>(tmA, tmB, p, grid, smem, stream)
-                : launch_gemm<A_MN, B_MN, false>(tmA, tmB, p, grid, smem, stream);
+static int launch_gemm_mode(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO32,
+                            const CUtensorMap& tmO16, const GemmParams& p, int grid, size_t smem, cudaStream_t stream) {
+  return p.pair ? launch_gemm<A_MN, B_MN, true>(tmA, tmB, tmO32, tmO16, p, grid, smem, stream)
+                : launch_gemm<A_MN, B_MN, false>(tmA, tmB, tmO32, tmO16, p, grid, smem, stream);
 }
 
 }  // namespace tt
@@ -638,12 +681,12 @@ extern "C" int tt_gemm_bf16(const tt_gemm_args* a, void* stream_) {
   }
   const size_t b_bytes = (static_cast<size_t>(bn) * kBlockK * 2) >> (p.pair ? 1 : 0);   // per CTA
   // bf16-only epilogues stage 64-byte rows: half the staging, more pipeline stages
-  p.stg_bytes = static_cast<int>(((a->out_f32 || a->residual) ? kStageBytesF32 : kStageBytesBf16) +
-                                 (a->bias ? kBiasBytesPerWarp : 0u));
+  p.stg_bytes = static_cast<int>((a->out_f32 || a->residual) ? kStageBytesF32 : kStageBytesBf16);
   p.a_colsum = a->a_colsum;
   TT_REQUIRE(!a->a_colsum || (!a->a_mn && ks == 1 && a->K <= 2048),
              "tt_gemm_bf16: a_colsum needs a K-major A operand, no split-K and K <= 2048 (K=%d)", a->K);
-  const size_t fixed = gemm_fixed_smem(p.stg_bytes, a->a_colsum ? kblocks * kBlockK : 0);
+  const size_t fixed = gemm_fixed_smem(p.stg_bytes + (a->bias ? static_cast<int>(kBiasBytesPerWarp) : 0),
+                                       a->a_colsum ? kblocks * kBlockK : 0);
   int stages = static_cast<int>((kSmemLimit - fixed) / (kABytes + b_bytes));
   if (stages > 8) stages = 8;
   TT_REQUIRE(stages >= 2, "tt_gemm_bf16: no room for a 2-stage pipeline (block_n %d)", bn);
@@ -706,6 +749,28 @@ extern "C" int tt_gemm_bf16(const tt_gemm_args* a, void* stream_) {
   }
   if (rc) return rc;
 
+  // Output tensor maps (32 x 32 blocks, the staging tile's swizzle): plain stores only — split-K keeps red.add
+  CUtensorMap tmO32 = tmA, tmO16 = tmA;   // placeholders when unused
+  {
+    static int tma_env = -1;
+    if (tma_env < 0) { const char* e = getenv("TT_GEMM_TMA_STORE"); tma_env = e ? atoi(e) : 1; }
+    p.tma_store = (tma_env != 0 && !a->accumulate) ? 1 : 0;
+  }
+  if (p.tma_store && a->out_f32) {
+    uint64_t dims[2] = {static_cast<uint64_t>(a->N), static_cast<uint64_t>(a->M)};
+    uint64_t str[1] = {static_cast<uint64_t>(a->ld_f32) * 4};
+    uint32_t box[2] = {32, 32};
+    rc = make_tmap(&tmO32, a->out_f32, 2, dims, str, box, 1, 128);
+    if (rc) return rc;
+  }
+  if (p.tma_store && a->out_bf16) {
+    uint64_t dims[2] = {static_cast<uint64_t>(a->N), static_cast<uint64_t>(a->M)};
+    uint64_t str[1] = {static_cast<uint64_t>(a->ld_bf16) * 2};
+    uint32_t box[2] = {32, 32};
+    rc = make_tmap(&tmO16, a->out_bf16, 2, dims, str, box, 0, 64);
+    if (rc) return rc;
+  }
+
   int grid;
   if (p.pair) {
     grid = 2 * static_cast<int>(pair_items < pairs ? pair_items : pairs);
@@ -715,9 +780,9 @@ extern "C" int tt_gemm_bf16(const tt_gemm_args* a, void* stream_) {
   }
   const size_t smem = fixed + static_cast<size_t>(stages) * (kABytes + b_bytes);
   if (a->a_mn) {
-    return a->b_mn ? launch_gemm_mode<true, true>(tmA, tmB, p, grid, smem, stream)
-                   : launch_gemm_mode<true, false>(tmA, tmB, p, grid, smem, stream);
+    return a->b_mn ? launch_gemm_mode<true, true>(tmA, tmB, tmO32, tmO16, p, grid, smem, stream)
+                   : launch_gemm_mode<true, false>(tmA, tmB, tmO32, tmO16, p, grid, smem, stream);
   }
-  return a->b_mn ? launch_gemm_mode<false, true>(tmA, tmB, p, grid, smem, stream)
-                 : launch_gemm_mode<false, false>(tmA, tmB, p, grid, smem, stream);
+  return a->b_mn ? launch_gemm_mode<false, true>(tmA, tmB, tmO32, tmO16, p, grid, smem, stream)
+                 : launch_gemm_mode<false, false>(tmA, tmB, tmO32, tmO16, p, grid, smem, stream);
 }
