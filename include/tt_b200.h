@@ -129,6 +129,23 @@ int tt_embed_ln_bwd(const int64_t* ids, const float* E, const float* P, const fl
                     const float* dx0, int B, int L, float drop_p, uint64_t seed, const uint64_t* seed_dev,
                     uint32_t site, float* dE, float* dP, float* dgamma, float* dbeta, void* stream);
 
+/* tt_embed_ln_bwd with the first encoder layer's norm1 backward (src/models/user_tower.py:37-45, norm_first=True:
+ * x + attn(norm1(x))) in front of it: d(loss)/d(x0) = LayerNorm1'(x0; dh) + resid is formed per token in registers from
+ * x0 recomputed out of the table row (same dropout hash as the forward), so neither x0 nor dx0 is read or written.
+ * dgamma / dbeta of norm1 are accumulated like the others. */
+typedef struct tt_norm1_bwd {
+  const void* dh_bf16;   /* bf16 [B*L,256]: gradient w.r.t. norm1's output (dX of the packed in_proj) */
+  const float* resid;    /* fp32 [B*L,256]: residual-stream gradient arriving at x0 */
+  const float* ln_w;     /* norm1.weight / norm1.bias */
+  const float* ln_b;
+  float* dgamma;
+  float* dbeta;
+} tt_norm1_bwd;
+int tt_embed_ln_bwd_norm1(const tt_norm1_bwd* n1, const int64_t* ids, const float* E, const float* P,
+                          const float* ln_w, const float* ln_b, int B, int L, float drop_p, uint64_t seed,
+                          const uint64_t* seed_dev, uint32_t site, float* dE, float* dP, float* dgamma, float* dbeta,
+                          void* stream);
+
 /* Deterministic form of tt_embed_ln_bwd for the table gradient (the reference's embedding backward is
  * autograd's embedding_dense_backward, src/models/user_tower.py:26; its CUDA form is deterministic only under
  * torch.use_deterministic_algorithms). Token t adds its gradient row into acc64[slot_of_token[t]] (int64

@@ -109,6 +109,13 @@ class ChainArgs(ctypes.Structure):
     ]
 
 
+class Norm1Bwd(ctypes.Structure):
+    """Mirror of ``tt_norm1_bwd``."""
+
+    _fields_ = [("dh_bf16", c_void_p), ("resid", c_void_p), ("ln_w", c_void_p), ("ln_b", c_void_p),
+                ("dgamma", c_void_p), ("dbeta", c_void_p)]
+
+
 class BnArgs(ctypes.Structure):
     """Mirror of ``tt_bn_args``."""
 
@@ -182,6 +189,9 @@ _SIGNATURES = {
                                          c_void_p, c_void_p, c_void_p],
     "tt_embed_ln_bwd": [c_void_p] * 6 + [c_int32, c_int32, c_float, c_uint64, c_void_p, c_uint32,
                                          c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
+    "tt_embed_ln_bwd_norm1": [ctypes.POINTER(Norm1Bwd)] + [c_void_p] * 5 + [c_int32, c_int32, c_float, c_uint64, c_void_p,
+                                                                       c_uint32, c_void_p, c_void_p, c_void_p, c_void_p,
+                                                                       c_void_p],
     "tt_embed_ln_bwd_det": [c_void_p] * 6 + [c_int32, c_int32, c_float, c_uint64, c_void_p, c_uint32,
                                              c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
     "tt_rows_scatter_add_i64": [c_void_p, c_void_p, c_void_p, c_int32, c_void_p, c_void_p],

@@ -597,58 +597,110 @@ struct EmbedBwdParams {
   // deterministic mode (both set): token `row` adds its gradient row into acc64[acc_slot[row]] in 64-bit fixed
   // point instead of dE (slot 0 = padding: skipped); tt_rows_scatter_add_i64 then rounds each sum once
   unsigned long long* acc64; const int64_t* acc_slot;
+  // fused form (n1_dh set, dx0 unused): the first encoder layer's norm1 backward runs in front, on x0 recomputed from
+  // the table row: dx0 = LayerNorm1'(x0; n1_dh) + n1_resid never travels through memory and x0 is not read
+  const __nv_bfloat16* n1_dh; const float* n1_resid; const float* n1_w; const float* n1_b;
+  float* n1_dgamma; float* n1_dbeta;
   // the table row of token `row` with id `id`: the forward's stash when there is one, else the table itself
   __device__ __forceinline__ const float* src_row(size_t row, int64_t id) const {
     return stash ? stash + row * 256 : E.row(id);
   }
 };
 
+template <bool FUSED>
 __global__ void __launch_bounds__(kRowThreads, 2) embed_ln_bwd_kernel(const EmbedBwdParams p) {
   pdl_launch_dependents();
   pdl_wait();
-  constexpr int NV = 2, E_ = 8, W = 256;
-  __shared__ float s_red[3][kRowThreads / 32][W];
+  constexpr int NV = 2, E_ = 8, W = 256, NRED = FUSED ? 5 : 3;
+  __shared__ float s_red[NRED][kRowThreads / 32][W];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int pos = blockIdx.x;
-  float w[E_], dg[E_], db[E_], dp[E_], q[E_];
+  float w[E_], dg[E_], db[E_], dp[E_], q[E_], dg1[FUSED ? E_ : 1], db1[FUSED ? E_ : 1];
   load_row<NV>(p.ln_w, lane, w);
   load_row<NV>(p.P + static_cast<size_t>(pos) * W, lane, q);
 #pragma unroll
   for (int i = 0; i < E_; ++i) { dg[i] = 0.f; db[i] = 0.f; dp[i] = 0.f; }
+  if constexpr (FUSED) {
+#pragma unroll
+    for (int i = 0; i < E_; ++i) { dg1[i] = 0.f; db1[i] = 0.f; }
+  }
   const uint64_t seed = p.drop_thresh ? read_seed(p.seed, p.seed_dev) : 0;
   // The id -> table row -> arithmetic chain is two dependent memory latencies per row; the ids run two
-  // rows ahead and the (table row, gradient row) pair one row ahead of the arithmetic.
+  // rows ahead and the (table row, gradient row[, residual row]) group one row ahead of the arithmetic.
   const int stride = (kRowThreads / 32) * gridDim.y;
   int b = wib * gridDim.y + blockIdx.y;
   int64_t id_n = 0, id_nn = 0;
-  float e_n[E_], g_n[E_];
+  float e_n[E_], g_n[E_], r_n[FUSED ? E_ : 1];
+  auto load_grad = [&](size_t row) {
+    if constexpr (FUSED) {
+      load_row_bf16<NV>(p.n1_dh + row * W, lane, g_n);
+      load_row<NV>(p.n1_resid + row * W, lane, r_n);
+    } else {
+      load_row<NV>(p.dx0 + row * W, lane, g_n);
+    }
+  };
   if (b < p.B) {
     id_n = p.ids[static_cast<size_t>(b) * p.L + pos];
     load_row<NV>(p.src_row(static_cast<size_t>(b) * p.L + pos, id_n), lane, e_n);
-    load_row<NV>(p.dx0 + (static_cast<size_t>(b) * p.L + pos) * W, lane, g_n);
+    load_grad(static_cast<size_t>(b) * p.L + pos);
   }
   if (b + stride < p.B) id_nn = p.ids[static_cast<size_t>(b + stride) * p.L + pos];
   for (; b < p.B; b += stride) {
     const size_t row = static_cast<size_t>(b) * p.L + pos;
     const int64_t id = id_n;
-    float e[E_], g[E_], xhat[E_];
+    float e[E_], g[E_], xhat[E_], r[FUSED ? E_ : 1];
 #pragma unroll
     for (int i = 0; i < E_; ++i) { e[i] = e_n[i]; g[i] = g_n[i]; }
+    if constexpr (FUSED) {
+#pragma unroll
+      for (int i = 0; i < E_; ++i) r[i] = r_n[i];
+    }
     id_n = id_nn;
     if (b + stride < p.B) {
       load_row<NV>(p.src_row(static_cast<size_t>(b + stride) * p.L + pos, id_n), lane, e_n);
-      load_row<NV>(p.dx0 + (static_cast<size_t>(b + stride) * p.L + pos) * W, lane, g_n);
+      load_grad(static_cast<size_t>(b + stride) * p.L + pos);
     }
     if (b + 2 * stride < p.B) id_nn = p.ids[static_cast<size_t>(b + 2 * stride) * p.L + pos];
 #pragma unroll
     for (int i = 0; i < E_; ++i) e[i] += q[i];
     float mean, rstd;
     ln_stats<NV>(e, 1e-5f, mean, rstd);
+#pragma unroll
+    for (int i = 0; i < E_; ++i) xhat[i] = (e[i] - mean) * rstd;
+    if constexpr (FUSED) {
+      // x0 = dropout(LayerNorm_emb(e)) exactly as the forward formed it, then norm1's backward on it
+      float x0[E_], bE[E_], w1[E_];
+      bool keep[E_];
+      load_row<NV>(p.ln_b, lane, bE);
+#pragma unroll
+      for (int i = 0; i < E_; ++i) { x0[i] = xhat[i] * w[i] + bE[i]; keep[i] = true; }
+      if (p.drop_thresh) row_dropout<NV>(x0, drop_key(seed, p.site), row, W, lane, p.drop_thresh, p.drop_scale, keep);
+      float m1, rs1;
+      ln_stats<NV>(x0, 1e-5f, m1, rs1);
+      load_row<NV>(p.n1_w, lane, w1);
+      float t1 = 0.f, t2 = 0.f;
+#pragma unroll
+      for (int i = 0; i < E_; ++i) {
+        x0[i] = (x0[i] - m1) * rs1;          // xhat of norm1
+        dg1[i] += g[i] * x0[i];
+        db1[i] += g[i];
+        g[i] *= w1[i];
+        t1 += g[i];
+        t2 += g[i] * x0[i];
+      }
+      t1 = warp_sum(t1) * (1.f / W);
+      t2 = warp_sum(t2) * (1.f / W);
+#pragma unroll
+      for (int i = 0; i < E_; ++i) {
+        g[i] = rs1 * (g[i] - t1 - x0[i] * t2) + r[i];                 // = d(loss)/d(x0)
+        if (p.drop_thresh) g[i] = keep[i] ? g[i] * p.drop_scale : 0.f;   // the embedding dropout's backward
+      }
+    } else {
+      if (p.drop_thresh) row_dropout<NV>(g, drop_key(seed, p.site), row, W, lane, p.drop_thresh, p.drop_scale, nullptr);
+    }
     float s1 = 0.f, s2 = 0.f;
-    if (p.drop_thresh) row_dropout<NV>(g, drop_key(seed, p.site), row, W, lane, p.drop_thresh, p.drop_scale, nullptr);
 #pragma unroll
     for (int i = 0; i < E_; ++i) {
-      xhat[i] = (e[i] - mean) * rstd;
       dg[i] += g[i] * xhat[i];
       db[i] += g[i];
       g[i] *= w[i];
@@ -688,15 +740,26 @@ __global__ void __launch_bounds__(kRowThreads, 2) embed_ln_bwd_kernel(const Embe
     s_red[0][wib][c] = dg[i];
     s_red[1][wib][c] = db[i];
     s_red[2][wib][c] = dp[i];
+    if constexpr (FUSED) {
+      s_red[3][wib][c] = dg1[i];
+      s_red[4][wib][c] = db1[i];
+    }
   }
   __syncthreads();
   for (int c = threadIdx.x; c < W; c += blockDim.x) {
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, a4 = 0.f;
 #pragma unroll
-    for (int k = 0; k < kRowThreads / 32; ++k) { a0 += s_red[0][k][c]; a1 += s_red[1][k][c]; a2 += s_red[2][k][c]; }
+    for (int k = 0; k < kRowThreads / 32; ++k) {
+      a0 += s_red[0][k][c]; a1 += s_red[1][k][c]; a2 += s_red[2][k][c];
+      if constexpr (FUSED) { a3 += s_red[3][k][c]; a4 += s_red[4][k][c]; }
+    }
     atomicAdd(p.dgamma + c, a0);
     atomicAdd(p.dbeta + c, a1);
     atomicAdd(p.dP + static_cast<size_t>(pos) * W + c, a2);  // gridDim.y blocks per position
+    if constexpr (FUSED) {
+      atomicAdd(p.n1_dgamma + c, a3);
+      atomicAdd(p.n1_dbeta + c, a4);
+    }
   }
   // sharded table: the gradient rows went to other GPUs; make them globally performed before the grid retires
   // (the optimizer kernels of the owners start after a cross-rank barrier that follows this kernel)
@@ -875,8 +938,10 @@ static int embed_bwd_impl(const int64_t* ids, const TableRef& E, const float* st
                           const float* ln_b, const float* dx0, int B, int L, float drop_p, uint64_t seed,
                           const uint64_t* seed_dev, uint32_t site, const TableRef& dE, float* dP, float* dgamma,
                           float* dbeta, cudaStream_t stream, unsigned long long* acc64 = nullptr,
-                          const int64_t* acc_slot = nullptr) {
-  TT_REQUIRE(ids && P && ln_w && ln_b && dx0 && dP && dgamma && dbeta, "tt_embed_ln_bwd: null pointer");
+                          const int64_t* acc_slot = nullptr, const tt_norm1_bwd* n1 = nullptr) {
+  TT_REQUIRE(ids && P && ln_w && ln_b && (dx0 || n1) && dP && dgamma && dbeta, "tt_embed_ln_bwd: null pointer");
+  TT_REQUIRE(!n1 || (n1->dh_bf16 && n1->resid && n1->ln_w && n1->ln_b && n1->dgamma && n1->dbeta),
+             "tt_embed_ln_bwd_norm1: incomplete norm1 description");
   EmbedBwdParams p;
   p.ids = ids; p.E = E; p.stash = stash; p.P = P; p.ln_w = ln_w; p.ln_b = ln_b; p.dx0 = dx0; p.B = B; p.L = L;
   p.drop_thresh = drop_threshold(drop_p);
@@ -884,10 +949,14 @@ static int embed_bwd_impl(const int64_t* ids, const TableRef& E, const float* st
   p.seed = seed; p.seed_dev = seed_dev; p.site = site;
   p.dE = dE; p.dP = dP; p.dgamma = dgamma; p.dbeta = dbeta;
   p.acc64 = acc64; p.acc_slot = acc_slot;
+  p.n1_dh = n1 ? static_cast<const __nv_bfloat16*>(n1->dh_bf16) : nullptr;
+  p.n1_resid = n1 ? n1->resid : nullptr; p.n1_w = n1 ? n1->ln_w : nullptr; p.n1_b = n1 ? n1->ln_b : nullptr;
+  p.n1_dgamma = n1 ? n1->dgamma : nullptr; p.n1_dbeta = n1 ? n1->dbeta : nullptr;
   int splits = (2 * num_sms()) / L;
   if (splits < 1) splits = 1;
   if (splits > (B + 7) / 8) splits = (B + 7) / 8;
-  TT_CHECK_CUDA(launch_k(embed_ln_bwd_kernel, dim3(L, splits), dim3(kRowThreads), 0, stream, p));
+  if (n1) TT_CHECK_CUDA(launch_k(embed_ln_bwd_kernel<true>, dim3(L, splits), dim3(kRowThreads), 0, stream, p));
+  else TT_CHECK_CUDA(launch_k(embed_ln_bwd_kernel<false>, dim3(L, splits), dim3(kRowThreads), 0, stream, p));
   TT_LAUNCH_CHECK();
   return TT_OK;
 }
@@ -908,6 +977,15 @@ extern "C" int tt_embed_ln_bwd(const int64_t* ids, const float* E, const float* 
   TT_REQUIRE(E && dE, "tt_embed_ln_bwd: null table");
   return embed_bwd_impl(ids, single_table(E), nullptr, P, ln_w, ln_b, dx0, B, L, drop_p, seed, seed_dev, site,
                         single_table(dE), dP, dgamma, dbeta, static_cast<cudaStream_t>(stream_));
+}
+
+extern "C" int tt_embed_ln_bwd_norm1(const tt_norm1_bwd* n1, const int64_t* ids, const float* E, const float* P,
+                                     const float* ln_w, const float* ln_b, int B, int L, float drop_p, uint64_t seed,
+                                     const uint64_t* seed_dev, uint32_t site, float* dE, float* dP, float* dgamma,
+                                     float* dbeta, void* stream_) {
+  TT_REQUIRE(n1 && E && dE, "tt_embed_ln_bwd_norm1: null pointer");
+  return embed_bwd_impl(ids, single_table(E), nullptr, P, ln_w, ln_b, nullptr, B, L, drop_p, seed, seed_dev, site,
+                        single_table(dE), dP, dgamma, dbeta, static_cast<cudaStream_t>(stream_), nullptr, nullptr, n1);
 }
 
 extern "C" int tt_embed_ln_bwd_det(const int64_t* ids, const float* E, const float* P, const float* ln_w,

@@ -130,6 +130,10 @@ class TwoTowerEngine:
         #: dX of linear1 / in_proj of the full-sequence layers travels to the LayerNorm backward as bf16 (the dtype
         #: autograd gives it under the reference's autocast, src/train.py:57-62) instead of fp32
         self.bf16_linear_dgrad = os.environ.get("TT_BF16_LINEAR_DGRAD", "1") != "0"
+        #: layer 0's norm1 backward inside the embedding backward (tt_embed_ln_bwd_norm1): dx0 never exists in memory.
+        #: Off by default: 156 MB less traffic per c2 step, but the kernel's one-block-per-position grid (200 blocks of
+        #: 8 warps, three dependent row reductions per token) leaves it latency-bound — measured 1.181 vs 1.170 ms.
+        self.fuse_norm1_embed_bwd = os.environ.get("TT_FUSE_NORM1_EMBED_BWD", "0") != "0"
         #: row-sharded ID table (sharding.RowShardedTable, config 5): when set, `table_rows` [1 + B*L, 256] holds
         #: the rows the exchange fetched for this step's tokens (row 0 unused) and the embedding kernels index
         #: it with the token number instead of the item id; `table_rows_grad` receives the per-token gradient
@@ -777,6 +781,13 @@ class TwoTowerEngine:
                           seed_dev=sdev, dx_colsum=g[self._lp(top, "linear2.bias")])
 
         # ---- encoder layers, last to first
+        # the single-table embedding backward (local table, or the compact cache of the step's distinct rows) can take
+        # layer 0's norm1 backward with it when that layer runs the full-sequence schedule with a bf16 dX
+        single_table = (self.peer_table is not None and self.dedup_ids) or \
+            (self.peer_table is None and not (self.deterministic_table_grad and self.table_rows is None))
+        fuse_n1 = (self.fuse_norm1_embed_bwd and self.bf16_linear_dgrad and single_table and
+                   not (self.prune_last_layer and top == 0))
+        n1 = None
         for l in range(cfg.num_layers - 1, -1, -1):
             x_in = ws[f"xout_{l - 1}"] if l > 0 else ws["x_in0"]
             if self.prune_last_layer and l == top:
@@ -820,6 +831,11 @@ class TwoTowerEngine:
             if l > 0:
                 extra = dict(dx_bf16=ws[f"dy2_{l - 1}"], drop2_p=dp, drop2_site=_site(l - 1, 3),
                              dx_colsum=g[self._lp(l - 1, "linear2.bias")])
+            if l == 0 and fuse_n1:
+                # layer 0's norm1 backward runs inside the embedding backward below (x0 recomputed, dx0 never stored)
+                n1 = (ws["dh_bf"], dx, p[self._lp(0, "norm1.weight")], p[self._lp(0, "norm1.bias")],
+                      g[self._lp(0, "norm1.weight")], g[self._lp(0, "norm1.bias")])
+                continue
             ops.chain_bwd(x_in, ln=(p[self._lp(l, "norm1.weight")], p[self._lp(l, "norm1.bias")]), **dh_in,
                           resid=dx, dx_f32=dx_other, seed=seed, seed_dev=sdev,
                           dgamma=g[self._lp(l, "norm1.weight")], dbeta=g[self._lp(l, "norm1.bias")], **extra)
@@ -830,11 +846,18 @@ class TwoTowerEngine:
             # per-token gradient rows are combined in the compact local buffer (atomics on L2-resident memory), then
             # ONE remote reduction per distinct row goes to its owner
             t, sp = self.peer_table, self._sparse_ws(B * L)
-            ops.embed_ln_bwd(sp["inverse"], sp["cache"], p[ut + "position_embedding.weight"],
-                             p[ut + "layer_norm.weight"], p[ut + "layer_norm.bias"], dx, B, L,
-                             sp["gacc"], g[ut + "position_embedding.weight"],
-                             g[ut + "layer_norm.weight"], g[ut + "layer_norm.bias"], drop_p=dp, seed=seed,
-                             seed_dev=sdev, site=SITE_EMB)
+            if n1 is not None:
+                ops.embed_ln_bwd_norm1(sp["inverse"], sp["cache"], p[ut + "position_embedding.weight"],
+                                       p[ut + "layer_norm.weight"], p[ut + "layer_norm.bias"], *n1, B, L,
+                                       sp["gacc"], g[ut + "position_embedding.weight"],
+                                       g[ut + "layer_norm.weight"], g[ut + "layer_norm.bias"], drop_p=dp, seed=seed,
+                                       seed_dev=sdev, site=SITE_EMB)
+            else:
+                ops.embed_ln_bwd(sp["inverse"], sp["cache"], p[ut + "position_embedding.weight"],
+                                 p[ut + "layer_norm.weight"], p[ut + "layer_norm.bias"], dx, B, L,
+                                 sp["gacc"], g[ut + "position_embedding.weight"],
+                                 g[ut + "layer_norm.weight"], g[ut + "layer_norm.bias"], drop_p=dp, seed=seed,
+                                 seed_dev=sdev, site=SITE_EMB)
             ops.rows_scatter_add(sp["uniq"], sp["state"], sp["gacc"], team=t.arena.team, grad_offset=t.arena.offset("grad"))
         elif self.peer_table is not None:
             t = self.peer_table
@@ -853,11 +876,18 @@ class TwoTowerEngine:
             ops.rows_scatter_add_i64(dw["uniq"], dw["state"], dw["acc64"], g[ut + "item_embedding.weight"])
         else:
             e_ids, e_table, e_grad = self._embed_operands(ids)
-            ops.embed_ln_bwd(e_ids, e_table, p[ut + "position_embedding.weight"],
-                             p[ut + "layer_norm.weight"], p[ut + "layer_norm.bias"], dx, B, L,
-                             e_grad, g[ut + "position_embedding.weight"],
-                             g[ut + "layer_norm.weight"], g[ut + "layer_norm.bias"], drop_p=dp, seed=seed,
-                             seed_dev=sdev, site=SITE_EMB)
+            if n1 is not None:
+                ops.embed_ln_bwd_norm1(e_ids, e_table, p[ut + "position_embedding.weight"],
+                                       p[ut + "layer_norm.weight"], p[ut + "layer_norm.bias"], *n1, B, L,
+                                       e_grad, g[ut + "position_embedding.weight"],
+                                       g[ut + "layer_norm.weight"], g[ut + "layer_norm.bias"], drop_p=dp, seed=seed,
+                                       seed_dev=sdev, site=SITE_EMB)
+            else:
+                ops.embed_ln_bwd(e_ids, e_table, p[ut + "position_embedding.weight"],
+                                 p[ut + "layer_norm.weight"], p[ut + "layer_norm.bias"], dx, B, L,
+                                 e_grad, g[ut + "position_embedding.weight"],
+                                 g[ut + "layer_norm.weight"], g[ut + "layer_norm.bias"], drop_p=dp, seed=seed,
+                                 seed_dev=sdev, site=SITE_EMB)
         main.wait_stream(side)
         if self.overlap_wgrad:
             main.wait_stream(self._wgrad_stream())

@@ -150,6 +150,22 @@ def embed_ln_bwd(ids, E, P, ln_w, ln_b, dx0, B, L, dE, dP, dgamma, dbeta, drop_p
                                 dP.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(), _stream()), "tt_embed_ln_bwd")
 
 
+def embed_ln_bwd_norm1(ids, E, P, ln_w, ln_b, dh_bf16, resid, n1_w, n1_b, n1_dgamma, n1_dbeta, B, L, dE, dP, dgamma, dbeta,
+                       drop_p=0.0, seed=0, seed_dev=None, site=0):
+    """tt_embed_ln_bwd_norm1: the first encoder layer's norm1 backward and the embedding LayerNorm / lookup backward
+    in one pass (x0 is recomputed from the table rows, dx0 never exists in memory)."""
+    from ._lib import Norm1Bwd
+    _require_cuda(ids, E, P, dh_bf16, resid, n1_w, n1_b, n1_dgamma, n1_dbeta, dE, dP, dgamma, dbeta)
+    assert dh_bf16.dtype == torch.bfloat16 and dh_bf16.is_contiguous() and dh_bf16.shape == (B * L, 256)
+    assert resid.dtype == torch.float32 and resid.is_contiguous() and resid.shape == (B * L, 256)
+    n1 = Norm1Bwd(dh_bf16.data_ptr(), resid.data_ptr(), n1_w.data_ptr(), n1_b.data_ptr(), n1_dgamma.data_ptr(),
+                  n1_dbeta.data_ptr())
+    check(lib().tt_embed_ln_bwd_norm1(ctypes.byref(n1), ids.data_ptr(), E.data_ptr(), P.data_ptr(), ln_w.data_ptr(),
+                                      ln_b.data_ptr(), B, L, drop_p, seed, _ptr(seed_dev), site, dE.data_ptr(),
+                                      dP.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(), _stream()),
+          "tt_embed_ln_bwd_norm1")
+
+
 def embed_ln_bwd_det(ids, E, P, ln_w, ln_b, dx0, B, L, slot_of_token, acc64, dP, dgamma, dbeta, drop_p=0.0, seed=0,
                      seed_dev=None, site=0):
     """tt_embed_ln_bwd_det: the table gradient is accumulated per distinct id in 64-bit fixed point (order-independent,

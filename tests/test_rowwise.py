@@ -55,6 +55,51 @@ def test_embed_ln_fwd_bwd():
     assert (db - br.grad).abs().max().item() < 1e-3
 
 
+@pytest.mark.parametrize("drop_p", [0.0, 0.25])
+def test_embed_ln_bwd_norm1_equals_the_two_kernels(drop_p):
+    """tt_embed_ln_bwd_norm1 (layer 0's norm1 backward inside the embedding backward, x0 recomputed) against
+    chain_bwd(norm1) followed by embed_ln_bwd on the stored x0 / dx0 — and, without dropout, against autograd."""
+    from mrm_b200 import ops
+    B, L, V = 9, 41, 203
+    gen = torch.Generator().manual_seed(13)
+    ids = torch.randint(0, V, (B, L), generator=gen).cuda()
+    E, P = _randn(V, 256, seed=14, scale=0.1), _randn(64, 256, seed=15, scale=0.1)
+    w, b = 1 + _randn(256, seed=16, scale=0.1), _randn(256, seed=17, scale=0.1)
+    w1, b1 = 1 + _randn(256, seed=18, scale=0.1), _randn(256, seed=19, scale=0.1)
+    kw = dict(drop_p=drop_p, seed=99, site=7)
+    x0 = torch.empty(B * L, 256, device="cuda")
+    h = torch.empty(B * L, 256, device="cuda", dtype=torch.bfloat16)
+    ops.embed_ln_fwd(ids.view(-1), E, P, w, b, w1, b1, B, L, x0, h, **kw)
+    dh = _randn(B * L, 256, seed=20).to(torch.bfloat16)
+    resid = _randn(B * L, 256, seed=21)
+
+    def grads():
+        return (torch.zeros_like(E), torch.zeros_like(P), torch.zeros(256, device="cuda"), torch.zeros(256, device="cuda"),
+                torch.zeros(256, device="cuda"), torch.zeros(256, device="cuda"))
+
+    dE_a, dP_a, dg_a, db_a, dg1_a, db1_a = grads()
+    dx0 = torch.empty(B * L, 256, device="cuda")
+    ops.chain_bwd(x0, ln=(w1, b1), dout_bf16=dh, resid=resid, dx_f32=dx0, dgamma=dg1_a, dbeta=db1_a)
+    ops.embed_ln_bwd(ids.view(-1), E, P, w, b, dx0, B, L, dE_a, dP_a, dg_a, db_a, **kw)
+    dE_b, dP_b, dg_b, db_b, dg1_b, db1_b = grads()
+    ops.embed_ln_bwd_norm1(ids.view(-1), E, P, w, b, dh, resid, w1, b1, dg1_b, db1_b, B, L, dE_b, dP_b, dg_b, db_b, **kw)
+    torch.cuda.synchronize()
+    for a, c, tol in ((dE_a, dE_b, 2e-4), (dP_a, dP_b, 2e-4), (dg_a, dg_b, 2e-3), (db_a, db_b, 2e-3),
+                      (dg1_a, dg1_b, 2e-3), (db1_a, db1_b, 2e-3)):
+        assert (a - c).abs().max().item() < tol
+    if drop_p == 0.0:
+        Er, Pr, wr, br, w1r, b1r = (t.clone().requires_grad_(True) for t in (E, P, w, b, w1, b1))
+        x = F.layer_norm(Er[ids] + Pr[:L].unsqueeze(0), (256,), wr, br).view(B * L, 256)
+        y = F.layer_norm(x, (256,), w1r, b1r)
+        (y * dh.float()).sum().backward(retain_graph=True)
+        x.backward(resid)
+        dE_ref = Er.grad.clone()
+        dE_ref[0] = 0
+        assert (dE_b - dE_ref).abs().max().item() < 2e-4
+        assert (dP_b - Pr.grad).abs().max().item() < 2e-4
+        assert (dg1_b - w1r.grad).abs().max().item() < 2e-3 and (db1_b - b1r.grad).abs().max().item() < 2e-3
+
+
 @pytest.mark.parametrize("ln,relu,l2", [(True, False, False), (True, True, False), (False, False, True),
                                         (True, False, True)])
 def test_chain_fwd_bwd(ln, relu, l2):
