@@ -1567,6 +1567,7 @@ extern "C" int tt_attn_causal_bwd(const void* qkv, const void* ctx, const void* 
   if (!configured) {
     TT_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
     TT_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    TT_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
     configured = true;
   }
   TT_REQUIRE(smem <= 232448, "tt_attn_causal_bwd: shared memory %zu too large", smem);
@@ -1585,7 +1586,11 @@ extern "C" int tt_attn_causal_bwd(const void* qkv, const void* ctx, const void* 
   } else if (p.nq <= 2) {
     TT_CHECK_CUDA(launch_k(attn_bwd_kernel<false, 4>, dim3(B * H), dim3(512), smem, stream, tmQ, tmDO, p));
   } else {
-    TT_CHECK_CUDA(launch_k(attn_bwd_kernel<true, 2>, dim3(B * H), dim3(256), smem, stream, tmQ, tmDO, p));
+    // L <= 512: 16 warps in the element-wise phase (CG = 4) like the fast layout; TT_ATTN_BWD_LONG_CG=2 keeps 8
+    static int long_cg = -1;
+    if (long_cg < 0) { const char* e = getenv("TT_ATTN_BWD_LONG_CG"); long_cg = e ? atoi(e) : 4; }
+    if (long_cg == 4) TT_CHECK_CUDA(launch_k(attn_bwd_kernel<true, 4>, dim3(B * H), dim3(512), smem, stream, tmQ, tmDO, p));
+    else TT_CHECK_CUDA(launch_k(attn_bwd_kernel<true, 2>, dim3(B * H), dim3(256), smem, stream, tmQ, tmDO, p));
   }
   TT_LAUNCH_CHECK();
   return TT_OK;
