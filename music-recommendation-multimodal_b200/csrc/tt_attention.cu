@@ -642,6 +642,33 @@ attn_fwd_persist_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnPar
 // Pd and dS are staged as bf16 in 128B-swizzled smem tiles. Thread (row, hf) owns query row
 // `row` and the 64-column half `hf` of the 128-key tile (warp & 3 = TMEM lane quarter).
 // --------------------------------------------------------------------------------------------
+// Keep decisions of 32 consecutive elements starting at didx0 as a bit mask: one hash per 4 (2, 1) elements
+// depending on the alignment of didx0 — the same decisions drop_keep_k gives element by element.
+__device__ __forceinline__ uint32_t drop_keepmask32(uint32_t dkey, uint32_t didx0, uint32_t thresh) {
+  uint32_t keepmask = 0u;
+  if ((didx0 & 3u) == 0u) {
+#pragma unroll
+    for (int t = 0; t < 32; t += 4) {
+      bool k[4];
+      drop_keep_quad(dkey, didx0 + t, thresh, k);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) keepmask |= (k[e] ? 1u : 0u) << (t + e);
+    }
+  } else if ((didx0 & 1u) == 0u) {
+#pragma unroll
+    for (int t = 0; t < 32; t += 2) {
+      bool k0, k1;
+      drop_keep_pair(dkey, didx0 + t, thresh, k0, k1);
+      keepmask |= (k0 ? 1u : 0u) << t;
+      keepmask |= (k1 ? 1u : 0u) << (t + 1);
+    }
+  } else {
+#pragma unroll
+    for (int t = 0; t < 32; ++t) keepmask |= (drop_keep_k(dkey, didx0 + t, thresh) ? 1u : 0u) << t;
+  }
+  return keepmask;
+}
+
 struct AttnBwdParams {
   int B, L, H, nq;
   float scale;
@@ -814,6 +841,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       const bool row_ok = q_pos < p.L;
       if constexpr (LONG) {
         // ---- part A: P from S. Pd -> sPd, un-dropped P parked (bf16) in the dS tile ---------------
+        uint32_t km[CPT];   // dropout keep bits of this thread's chunks, formed once and reused by part B
 #pragma unroll
         for (int cc = 0; cc < CPT; ++cc) {
           const int cg = CPT * grp + cc;
@@ -826,13 +854,14 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
             tmem_ld_wait();
             const int kv0 = j * kTile + cg * 32;
             const uint32_t didx0 = (static_cast<uint32_t>(bh) * p.L + q_pos) * p.L + kv0;
+            km[cc] = p.drop_thresh ? drop_keepmask32(dkey, didx0, p.drop_thresh) : 0xFFFFFFFFu;
             float pr[32], pd[32];
 #pragma unroll
             for (int t = 0; t < 32; ++t) {
               float x = fast_exp2(__uint_as_float(rs[t]) * c1 - lse2);
               if ((diag && kv0 + t > q_pos) || !row_ok) x = 0.f;
               pr[t] = x;
-              pd[t] = (p.drop_thresh && !drop_keep_k(dkey, didx0 + t, p.drop_thresh)) ? 0.f : x * p.drop_scale;
+              pd[t] = ((km[cc] >> t) & 1u) ? x * p.drop_scale : 0.f;
             }
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
@@ -849,6 +878,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
               st_swizzled_unit(dchunk, row, u0 + u, w);
             }
           } else {
+            km[cc] = 0u;
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
               st_swizzled_unit(pchunk, row, u0 + u, make_uint4(0, 0, 0, 0));
@@ -898,7 +928,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
                 for (int e = 0; e < 2; ++e) {
                   const int t = u * 8 + h2 * 2 + e;
                   const float prv = e ? pr2.y : pr2.x;
-                  const bool keep = !p.drop_thresh || drop_keep_k(dkey, didx0 + t, p.drop_thresh);
+                  const bool keep = (km[cc] >> t) & 1u;
                   const float dp = keep ? __uint_as_float(rp[t]) * p.drop_scale : 0.f;
                   ds[h2 * 2 + e] = prv * (dp - delta) * p.scale;
                 }
@@ -926,31 +956,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
           tmem_ld_wait();
           const int kv0 = j * kTile + cg * 32;
           const uint32_t didx0 = (static_cast<uint32_t>(bh) * p.L + q_pos) * p.L + kv0;
-          uint32_t keepmask = 0xFFFFFFFFu;
-          if (p.drop_thresh) {
-            keepmask = 0u;
-            if ((didx0 & 3u) == 0u) {
-#pragma unroll
-              for (int t = 0; t < 32; t += 4) {
-                bool k[4];
-                drop_keep_quad(dkey, didx0 + t, p.drop_thresh, k);
-#pragma unroll
-                for (int e = 0; e < 4; ++e) keepmask |= (k[e] ? 1u : 0u) << (t + e);
-              }
-            } else if ((didx0 & 1u) == 0u) {
-#pragma unroll
-              for (int t = 0; t < 32; t += 2) {
-                bool k0, k1;
-                drop_keep_pair(dkey, didx0 + t, p.drop_thresh, k0, k1);
-                keepmask |= (k0 ? 1u : 0u) << t;
-                keepmask |= (k1 ? 1u : 0u) << (t + 1);
-              }
-            } else {
-#pragma unroll
-              for (int t = 0; t < 32; ++t)
-                keepmask |= (drop_keep_k(dkey, didx0 + t, p.drop_thresh) ? 1u : 0u) << t;
-            }
-          }
+          const uint32_t keepmask = p.drop_thresh ? drop_keepmask32(dkey, didx0, p.drop_thresh) : 0xFFFFFFFFu;
           float pd[32], ds[32];
 #pragma unroll
           for (int t = 0; t < 32; ++t) {
