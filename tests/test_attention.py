@@ -140,3 +140,55 @@ def test_attn_fwd_persistent_equals_legacy(B, L, H, drop, monkeypatch):
     diff = (a[0].float() - b[0].float()).abs()
     assert float(diff.max()) <= 2.0 ** -7 * max(1.0, float(a[0].float().abs().max()))
     assert float((diff > 0).float().mean()) < 0.02        # almost everywhere the very same bits
+
+
+@pytest.mark.parametrize("B,L,H", [(2, 200, 2), (2, 384, 2), (1, 512, 2), (2, 300, 4)])
+def test_attn_bwd_uses_the_forward_dropout_mask(B, L, H):
+    """The backward re-creates the forward's dropout mask from the hash. Here the mask is READ OUT of the forward kernel
+    (one-hot V blocks turn ctx into the dropped probabilities themselves) and a torch backward with exactly that mask
+    is the reference — for the two-tile (persistent) and the four-tile (L > 256) kernels, whose hash evaluation differs
+    (one word per 4 / 2 / 1 keys depending on alignment)."""
+    from mrm_b200 import ops
+    p_drop, seed, site = 0.3, 4242, 5
+    D = H * 64
+    g = torch.Generator().manual_seed(7 * L + B)
+    qkv = (torch.randn(B * L, 3 * D, generator=g) * 1.0).cuda().bfloat16()
+
+    def probs(drop):
+        """[B, H, L, L] probabilities as the kernel forms them (dropout applied when drop > 0), via one-hot V."""
+        out = torch.zeros(B, H, L, L, device="cuda")
+        x = qkv.clone().view(B, L, 3, H, 64)
+        ctx = torch.empty(B * L, D, device="cuda", dtype=torch.bfloat16)
+        for k0 in range(0, L, 64):
+            x[:, :, 2] = 0
+            n = min(64, L - k0)
+            x[:, k0:k0 + n, 2, :, :n] = torch.eye(n, device="cuda", dtype=torch.bfloat16)[None, :, None, :]
+            ops.attn_fwd(x.view(B * L, 3 * D), ctx, None, B, L, H, drop_p=drop, drop_seed=seed, drop_site=site)
+            out[:, :, :, k0:k0 + n] = ctx.float().view(B, L, H, 64)[..., :n].permute(0, 2, 1, 3)
+        return out
+
+    P, Pd = probs(0.0), probs(p_drop)
+    known = P > 1e-5          # bf16 keeps the relative precision of small probabilities; below this they do not matter
+    keep = torch.where(known, Pd > 0.5 * P, torch.ones_like(known))
+    frac = keep[known].float().mean().item()
+    assert abs(frac - (1 - p_drop)) < 0.03, frac
+    # the backward on the real V with the hash-made mask against torch with the read-out mask
+    dctx = torch.randn(B * L, D, generator=g).cuda().bfloat16()
+    ctx = torch.empty(B * L, D, device="cuda", dtype=torch.bfloat16)
+    lse = torch.empty(B, H, L, device="cuda")
+    ops.attn_fwd(qkv, ctx, lse, B, L, H, drop_p=p_drop, drop_seed=seed, drop_site=site)
+    dqkv = torch.empty(B * L, 3 * D, device="cuda", dtype=torch.bfloat16)
+    ops.attn_bwd(qkv, ctx, dctx, lse, dqkv, B, L, H, drop_p=p_drop, drop_seed=seed, drop_site=site)
+    torch.cuda.synchronize()
+    x = qkv.float().view(B, L, 3, H, 64).requires_grad_(True)
+    q, k, v = x[:, :, 0].transpose(1, 2), x[:, :, 1].transpose(1, 2), x[:, :, 2].transpose(1, 2)
+    s = (q @ k.transpose(-1, -2)) / 8.0
+    s = s.masked_fill(torch.triu(torch.ones(L, L, dtype=torch.bool, device="cuda"), 1), float("-inf"))
+    o = ((torch.softmax(s, dim=-1) * keep / (1 - p_drop)) @ v).transpose(1, 2).reshape(B * L, D)
+    assert (ctx.float() - o.detach()).abs().max().item() <= 4e-2
+    o.backward(dctx.float())
+    dref = x.grad.reshape(B * L, 3 * D)
+    for name, sl in (("dq", slice(0, D)), ("dk", slice(D, 2 * D)), ("dv", slice(2 * D, 3 * D))):
+        a, r = dqkv[:, sl].float(), dref[:, sl]
+        err = (a - r).abs().max().item()
+        assert err <= 4e-2 * max(r.abs().max().item(), 1.0), f"{name}: err {err}"
