@@ -334,15 +334,20 @@ def run_ours(args, rank, world, local_rank):
     # ---- e2e: host batches, H2D + step + D2H of the loss every step -----------------------
     # Every step's batch crosses PCIe from pinned memory inside the timed region; the copy of batch i+1 is
     # issued while step i computes (double-buffered staging, TrainStepRunner.stage_batch), the loss of every
-    # step is read back to the host before the next one is launched.
+    # step is read back to the host — one step behind: the host enqueues step i + 1, then waits for loss i
+    # (what train.train_one_epoch does between the reference's log lines).
     for i in range(3):
         runner.step_from_host(host_batches[i % 4])
     packed = [runner.pack_host(b) for b in host_batches]      # one pinned buffer per batch: one H2D copy
     runner.stage_batch(packed[0])
     barrier()
     t0 = time.perf_counter()
+    e2e_losses = []
     for i in range(args.steps):
-        runner.step_from_host(None, prefetch=packed[(i + 1) % 4])   # K copies for K steps
+        # K copies for K steps; the loss of step i - 1 is returned while step i is already enqueued
+        e2e_losses.append(runner.step_from_host(None, prefetch=packed[(i + 1) % 4], defer_loss=True))
+    e2e_losses.append(runner.flush_loss())          # the last step's loss: K losses on the host inside the region
+    assert sum(l is not None for l in e2e_losses) == args.steps
     torch.cuda.synchronize()
     e2e_s = torch.tensor([time.perf_counter() - t0], device=dev)
     if world > 1:

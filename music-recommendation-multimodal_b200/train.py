@@ -171,6 +171,12 @@ class TrainStepRunner:
         self.static: Dict[str, torch.Tensor] = {
             name: self._static_buf[o:o + nb].view(dt).view(shape) for name, shape, dt, o, nb in self._fields}
         self.loss_host = torch.zeros((), dtype=torch.float32).pin_memory()
+        # two pinned read-back slots: the loss of step i is copied while step i + 1 is being enqueued (step_from_host)
+        self._loss_slots = [{"loss": torch.zeros((), dtype=torch.float32).pin_memory(),
+                             "all": torch.zeros(max(world_size, 1), 4).pin_memory(),
+                             "err": torch.zeros(1, dtype=torch.int32).pin_memory(),
+                             "ev": torch.cuda.Event()} for _ in range(2)]
+        self._loss_turn, self._loss_pending = 0, None
         self._graphs = None
         self._cap_stream = None
         self._stage = None
@@ -474,10 +480,13 @@ class TrainStepRunner:
             self._staged_ev.record()
         self._staged = True
 
-    def step_from_host(self, host_batch, prefetch=None) -> float:
+    def step_from_host(self, host_batch, prefetch=None, defer_loss: bool = False):
         """Host batch -> device -> step -> loss on the host (one sync, like the reference's loss.item()).
         ``host_batch=None`` takes the batch announced by ``stage_batch`` / the previous call's ``prefetch``;
-        ``prefetch`` (the next batch, pinned) is copied while this step runs."""
+        ``prefetch`` (the next batch, pinned) is copied while this step runs.
+        ``defer_loss=True`` pipelines the read-back: the call enqueues this step and its loss copy, then returns the
+        loss of the PREVIOUS deferred step (None on the first call) — every step's loss still crosses to the host, but
+        the host stays one step ahead of the GPU instead of draining it every step; `flush_loss()` returns the last one."""
         if isinstance(host_batch, torch.Tensor):
             self._static_buf.copy_(host_batch, non_blocking=True)
         elif host_batch is not None:
@@ -492,20 +501,38 @@ class TrainStepRunner:
         loss = self.step_resident()
         if prefetch is not None:
             self.stage_batch(prefetch)
-        if self.arena is not None:
-            # every rank's loss share came with the log-sum-exp exchange: one small D2H, no collective
-            self._loss_all_host.copy_(self.arena.view("loss_all", torch.float32, (self.world, 4)), non_blocking=True)
-            self.arena._err_host.copy_(self.arena.error_word(), non_blocking=True)
-            torch.cuda.current_stream().synchronize()
-            if int(self.arena._err_host[0]) != 0:
-                raise RuntimeError("a cross-GPU wait timed out (peer rank missing or stalled)")
-            return float(self._loss_all_host[:, 0].sum())
-        if self.gathered:
+        if self.arena is None and self.gathered:
             loss = loss.clone()
             dist.all_reduce(loss, op=dist.ReduceOp.SUM, group=self.group)
-        self.loss_host.copy_(loss, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        return float(self.loss_host)
+        # this step's loss (and, with the NVLink arena, every rank's share + the arena's error word) -> pinned slot
+        slot = self._loss_slots[self._loss_turn]
+        if self.arena is not None:
+            # every rank's loss share came with the log-sum-exp exchange: one small D2H, no collective
+            slot["all"].copy_(self.arena.view("loss_all", torch.float32, (self.world, 4)), non_blocking=True)
+            slot["err"].copy_(self.arena.error_word(), non_blocking=True)
+        else:
+            slot["loss"].copy_(loss, non_blocking=True)
+        slot["ev"].record()
+        prev = self.flush_loss()          # the previous deferred step's loss (None if nothing is pending)
+        self._loss_pending = self._loss_turn
+        self._loss_turn ^= 1
+        if defer_loss:
+            return prev
+        assert prev is None, "flush_loss() before switching from deferred to immediate loss reads"
+        return self.flush_loss()
+
+    def flush_loss(self):
+        """Wait for and return the loss of the most recent step whose read-back is still pending (None if none)."""
+        if self._loss_pending is None:
+            return None
+        slot = self._loss_slots[self._loss_pending]
+        self._loss_pending = None
+        slot["ev"].synchronize()
+        if self.arena is not None:
+            if int(slot["err"][0]) != 0:
+                raise RuntimeError("a cross-GPU wait timed out (peer rank missing or stalled)")
+            return float(slot["all"][:, 0].sum())
+        return float(slot["loss"])
 
 
 def train_one_epoch(model, dataloader, optimizer, device, epoch, is_main_process=True, log_interval=50):
@@ -525,6 +552,10 @@ def train_one_epoch(model, dataloader, optimizer, device, epoch, is_main_process
         if fused:
             B, L = batch["history_ids"].shape
             if runner is None or (runner.B, runner.L) != (B, L):
+                if runner is not None:          # a loss of the previous shape's runner may still be on its way
+                    pending = runner.flush_loss()
+                    if pending is not None:
+                        total_loss += pending
                 runner = TrainStepRunner(model.engine, B, L, world_size=world, lr=optimizer.lr,
                                          betas=optimizer.betas, eps=optimizer.eps,
                                          weight_decay=optimizer.weight_decay, with_user_idx="user_idx" in batch)
@@ -535,8 +566,19 @@ def train_one_epoch(model, dataloader, optimizer, device, epoch, is_main_process
             if nxt is not None and tuple(nxt["history_ids"].shape) == (B, L) and \
                     all(v.is_pinned() for k, v in nxt.items() if k in _BATCH_KEYS and isinstance(v, torch.Tensor)):
                 pre = {k: v for k, v in nxt.items() if k in _BATCH_KEYS}
-            loss_val = runner.step_from_host(cur, prefetch=pre)
+            # the loss is read one step behind (the host enqueues step i + 1 while step i runs) except where the
+            # reference logs it, so the GPU is not drained every step; every step's loss still reaches the host
+            prev_loss = runner.step_from_host(cur, prefetch=pre, defer_loss=True)
             staged = pre is not None
+            if prev_loss is not None:
+                total_loss += prev_loss
+            if (is_main_process and (i + 1) % log_interval == 0) or nxt is None:
+                loss_val = runner.flush_loss()
+                total_loss += loss_val
+                if is_main_process and (i + 1) % log_interval == 0:
+                    logger.info(f"Epoch {epoch} [{i+1}/{num_batches}] | Loss: {loss_val:.4f}")
+            batch = nxt
+            continue
         else:
             for k, v in batch.items():
                 if isinstance(v, torch.Tensor):

@@ -130,6 +130,30 @@ def test_packed_host_batch_is_the_same_step():
         assert abs(a - b) < 5e-3, losses
 
 
+def test_deferred_loss_reads_return_every_loss_once_and_in_order():
+    """step_from_host(defer_loss=True) hands back the PREVIOUS step's loss (None first) and flush_loss() the last one:
+    the same sequence as the immediate reads of an identical run; train_one_epoch's mean uses every step once."""
+    from mrm_b200 import synthetic
+    from mrm_b200.train import TrainStepRunner
+    seqs = []
+    for defer in (False, True):
+        m = _model(dropout=0.0)
+        cfg = m.engine.cfg
+        batches = [synthetic.make_batch(cfg, 64, seed=90 + i) for i in range(5)]
+        r = TrainStepRunner(m.engine, 64, 50, lr=1e-3)
+        if defer:
+            got = [r.step_from_host(b, defer_loss=True) for b in batches]
+            assert got[0] is None and r.flush_loss() is not None and r.flush_loss() is None
+        else:
+            got = [None] + [r.step_from_host(b) for b in batches]
+            assert r.flush_loss() is None
+        seqs.append(got[1:])
+    # deferred run: losses of steps 0..3 (the fifth was taken by flush_loss above)
+    for a, b in zip(seqs[0][:4], seqs[1]):
+        assert abs(a - b) < 5e-3, seqs
+    assert seqs[0][0] == seqs[1][0]          # the first step starts from identical parameters: identical loss
+
+
 def test_calculate_metrics_global_matches_oracle():
     from mrm_b200 import synthetic
     from mrm_b200.evaluate_metrics import calculate_metrics_global
