@@ -170,7 +170,6 @@ class TrainStepRunner:
         self._static_buf = torch.zeros(off, device=dev, dtype=torch.uint8)
         self.static: Dict[str, torch.Tensor] = {
             name: self._static_buf[o:o + nb].view(dt).view(shape) for name, shape, dt, o, nb in self._fields}
-        self.loss_host = torch.zeros((), dtype=torch.float32).pin_memory()
         # two pinned read-back slots: the loss of step i is copied while step i + 1 is being enqueued (step_from_host)
         self._loss_slots = [{"loss": torch.zeros((), dtype=torch.float32).pin_memory(),
                              "all": torch.zeros(max(world_size, 1), 4).pin_memory(),
@@ -196,7 +195,6 @@ class TrainStepRunner:
                            a.view("shadow", torch.bfloat16, (eng.shadow.numel(),)))
         eng.release_workspaces()
         self._loss_pad = torch.zeros(4, device=eng.device)            # 16-byte slot: [loss share, 0, 0, 0]
-        self._loss_all_host = torch.zeros(G, 4).pin_memory()
         n = eng.numel // G
         if eng.exp_avg is None or eng.exp_avg.numel() != n:
             eng.exp_avg = torch.zeros(n, device=eng.device)
