@@ -9,6 +9,7 @@
 // cross-warp parameter-gradient combine.
 #include "../../include/tt_b200.h"
 #include "tt_common.cuh"
+#include <stdlib.h>
 
 namespace tt {
 
@@ -584,7 +585,7 @@ __global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* _
 // skipped: padding_idx), dP (per position), d(ln_w), d(ln_b). The pre-LN sum E[id]+P[pos] is
 // re-gathered instead of being stored.
 // Grid (L, S): block (pos, s) handles position `pos` for every S-th group of 8 sequences, so dP takes
-// S atomics per element; S is chosen so that all blocks are resident at 2 per SM.
+// S atomics per element; S is chosen for ~6 blocks per SM (see embed_bwd_impl).
 // --------------------------------------------------------------------------------------------
 // Fixed-point scale of the deterministic table-gradient accumulation: 2^40 (resolution 9.1e-13, |sum| < 8.3e6).
 static constexpr float kGradFixScale = 1099511627776.f;
@@ -952,7 +953,15 @@ static int embed_bwd_impl(const int64_t* ids, const TableRef& E, const float* st
   p.n1_dh = n1 ? static_cast<const __nv_bfloat16*>(n1->dh_bf16) : nullptr;
   p.n1_resid = n1 ? n1->resid : nullptr; p.n1_w = n1 ? n1->ln_w : nullptr; p.n1_b = n1 ? n1->ln_b : nullptr;
   p.n1_dgamma = n1 ? n1->dgamma : nullptr; p.n1_dbeta = n1 ? n1->dbeta : nullptr;
-  int splits = (2 * num_sms()) / L;
+  // ~6 blocks per SM in total (three waves at two resident blocks per SM): measured on the c2 step (L = 200), 1 / 2 /
+  // 3 / 4 / 6 / 8 blocks per position -> 1.172 / 1.169 / 1.160 / 1.158 / 1.161 / 1.161 ms per step; one block per
+  // position left every warp with a 32-row serial id -> row -> atomics chain and the SMs two thirds empty
+  int splits = (6 * num_sms() + L / 2) / L;
+  {
+    static int env = -1;
+    if (env < 0) { const char* e = getenv("TT_EMBED_BWD_SPLITS"); env = e ? atoi(e) : 0; }
+    if (env > 0) splits = env;
+  }
   if (splits < 1) splits = 1;
   if (splits > (B + 7) / 8) splits = (B + 7) / 8;
   if (n1) TT_CHECK_CUDA(launch_k(embed_ln_bwd_kernel<true>, dim3(L, splits), dim3(kRowThreads), 0, stream, p));
