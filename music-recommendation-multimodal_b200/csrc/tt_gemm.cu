@@ -669,12 +669,14 @@ extern "C" int tt_gemm_bf16(const tt_gemm_args* a, void* stream_) {
   // work items AND the contraction per tile is deep (>= 8 k-blocks): measured on the c2 step, the K >= 512
   // launches gain 7-15 % (dgrad 1024: 39.3 -> 33.3 us, wgrads 36.9 -> 32.8 / 45.0 -> 38.8 us) while the
   // epilogue-bound K = 256 ones lose 10-20 % to the lockstep of the pair (QKV 37.1 -> 42.9 us).
-  // TT_GEMM_PAIR=0 disables, =2 takes every eligible launch.
+  // Since the epilogue stores through TMA (round 2, third session) the pair no longer loses on the K = 256 launches
+  // (c2 step 1.160 -> 1.146 ms with every eligible launch on pairs), so that is the default now.
+  // TT_GEMM_PAIR=0 disables, =1 takes only the deep launches, =2 (default) every eligible launch.
   const int pairs = num_sms() / 2 > 0 ? num_sms() / 2 : 1;
   const long pair_items = static_cast<long>((tiles_m + 1) / 2) * tiles_n * ks;
   {
     static int pair_env = -1;
-    if (pair_env < 0) { const char* e = getenv("TT_GEMM_PAIR"); pair_env = e ? atoi(e) : 1; }
+    if (pair_env < 0) { const char* e = getenv("TT_GEMM_PAIR"); pair_env = e ? atoi(e) : 2; }
     const bool eligible = bn >= 128 && tiles_m >= 2 && pair_items * 10 >= static_cast<long>(pairs) * 9;
     const bool deep = kblocks / ks >= 8;
     p.pair = (pair_env != 0 && eligible && (deep || pair_env == 2)) ? 1 : 0;
